@@ -1,0 +1,226 @@
+// api.cu -- C ABI surface of libbsed.so (see include/bsed.h): context, error plumbing, and thin
+// argument-checking wrappers around the launchers.
+#include <math.h>
+#include <stdarg.h>
+
+#include <vector>
+
+#include "launch.h"
+
+using namespace bsed;
+
+static thread_local char g_err[512] = "";
+
+void bsed_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int bsed_version(void) { return BSED_ABI_VERSION; }
+extern "C" const char* bsed_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// constant tables (float64 on the host, rounded once to fp32)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+template <class T>
+int upload(T** dst, const std::vector<T>& v) {
+  BSED_CHECK_CUDA(cudaMalloc((void**)dst, sizeof(T) * v.size()));
+  BSED_CHECK_CUDA(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return BSED_OK;
+}
+
+int build_tables(bsed_context* h) {
+  const double PI = 3.14159265358979323846;
+  std::vector<float> win(kNFFT);
+  for (int n = 0; n < kNFFT; ++n) win[n] = (float)(0.54 - 0.46 * cos(2.0 * PI * n / (kNFFT - 1)));
+  std::vector<float2> t1(1024), t2(513);
+  for (int j = 0; j < 1024; ++j) t1[j] = make_float2((float)cos(2.0 * PI * j / 1024), (float)(-sin(2.0 * PI * j / 1024)));
+  for (int k = 0; k <= 512; ++k) t2[k] = make_float2((float)cos(2.0 * PI * k / 2048), (float)(-sin(2.0 * PI * k / 2048)));
+  // Slaney filterbank, librosa.filters.mel(sr=32000, n_fft=2048, n_mels=128, fmin=0, fmax=16000,
+  // htk=False, norm=None): float64 ramps stored as float32
+  const int nm = kNMels;
+  std::vector<double> edges(nm + 2);
+  const double mlo = hz_to_mel(0.0), mhi = hz_to_mel(16000.0);
+  for (int i = 0; i < nm + 2; ++i) edges[i] = mel_to_hz(mlo + (mhi - mlo) * i / (nm + 1));
+  std::vector<float> w;
+  std::vector<int> start(nm), len(nm), off(nm);
+  for (int m = 0; m < nm; ++m) {
+    int s = -1, e = -1;
+    std::vector<float> row(kNBins);
+    for (int k = 0; k < kNBins; ++k) {
+      double f = (double)k * kSampleRate / kNFFT;
+      double lower = (f - edges[m]) / (edges[m + 1] - edges[m]);
+      double upper = (edges[m + 2] - f) / (edges[m + 2] - edges[m + 1]);
+      double v = fmax(0.0, fmin(lower, upper));
+      row[k] = (float)v;
+      if (row[k] != 0.f) {
+        if (s < 0) s = k;
+        e = k;
+      }
+    }
+    if (s < 0) {
+      s = 0;
+      e = -1;
+    }
+    start[m] = s;
+    len[m] = e - s + 1;
+    off[m] = (int)w.size();
+    for (int k = s; k <= e; ++k) w.push_back(row[k]);
+  }
+  h->mel_nnz = (int)w.size();
+  BSED_REQUIRE(h->mel_nnz <= 2048, "mel filterbank has %d weights (> 2048)", h->mel_nnz);
+  if (w.empty()) w.push_back(0.f);
+  BSED_TRY(upload(&h->window, win));
+  BSED_TRY(upload(&h->tw1024, t1));
+  BSED_TRY(upload(&h->tw2048, t2));
+  BSED_TRY(upload(&h->mel_w, w));
+  BSED_TRY(upload(&h->mel_start, start));
+  BSED_TRY(upload(&h->mel_len, len));
+  BSED_TRY(upload(&h->mel_off, off));
+  return BSED_OK;
+}
+
+}  // namespace
+
+extern "C" int bsed_create(int device, bsed_handle* out) {
+  BSED_REQUIRE(out, "bsed_create: null out");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    bsed_set_error("bsed_create: no usable CUDA device (%s); this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return BSED_E_CUDA;
+  }
+  BSED_REQUIRE(device >= 0 && device < count, "bsed_create: device %d out of range [0,%d)", device, count);
+  BSED_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BSED_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    bsed_set_error("bsed_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                   prop.minor);
+    return BSED_E_CUDA;
+  }
+  bsed_context* h = new bsed_context();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  int r = build_tables(h);
+  if (r != BSED_OK) {
+    delete h;
+    return r;
+  }
+  *out = h;
+  return BSED_OK;
+}
+
+extern "C" int bsed_destroy(bsed_handle h) {
+  if (!h) return BSED_OK;
+  cudaFree(h->window);
+  cudaFree(h->tw1024);
+  cudaFree(h->tw2048);
+  cudaFree(h->mel_w);
+  cudaFree(h->mel_start);
+  cudaFree(h->mel_len);
+  cudaFree(h->mel_off);
+  delete h;
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frontend / post-processing
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsed_frontend_n_frames(int n_samples) { return n_samples < 0 ? -1 : 1 + n_samples / kHop; }
+
+extern "C" int bsed_melspec(bsed_handle h, const float* audio, int B, int n_samples, float* mel, void* stream) {
+  BSED_REQUIRE(h && audio && mel, "bsed_melspec: null argument");
+  return melspec(h, audio, B, n_samples, mel, as_stream(stream));
+}
+
+extern "C" size_t bsed_amp_to_db_workspace_bytes(int B) { return B > 0 ? sizeof(double) * (size_t)B * (kNMels + 1) : 0; }
+
+extern "C" int bsed_amp_to_db(bsed_handle h, const float* mel, const float* unit_noise, float snr_db, int B, int t_in,
+                              int frames, const float* scaler_mean, const float* scaler_std, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(h && mel && out && workspace, "bsed_amp_to_db: null argument");
+  return amp_to_db(mel, unit_noise, snr_db, B, t_in, frames, scaler_mean, scaler_std, out, workspace, workspace_bytes,
+                   as_stream(stream));
+}
+
+extern "C" int bsed_median_decode(bsed_handle h, const float* strong, int B, int T, int C, float threshold, int win,
+                                  int32_t* events, int max_events, int32_t* n_events, void* stream) {
+  BSED_REQUIRE(h && strong && events && n_events, "bsed_median_decode: null argument");
+  return median_decode(strong, B, T, C, threshold, win, events, max_events, n_events, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses / optimiser
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsed_mt_loss(bsed_handle h, const float* strong, const float* weak, int B, int T, int C, int syn_first,
+                            int syn_n, const float* syn_target, int real_first, int real_n, const float* strong_ema,
+                            const float* weak_ema, float cons_w, float* losses, float* d_strong, float* d_weak,
+                            void* stream) {
+  BSED_REQUIRE(h && strong && weak && losses && d_strong && d_weak, "bsed_mt_loss: null argument");
+  BSED_REQUIRE(syn_n == 0 || syn_target, "bsed_mt_loss: syn_target missing");
+  BSED_REQUIRE(real_n == 0 || (strong_ema && weak_ema), "bsed_mt_loss: teacher outputs missing");
+  BSED_REQUIRE(syn_first >= 0 && syn_first + syn_n <= B && real_first >= 0 && real_first + real_n <= B,
+               "bsed_mt_loss: clip ranges outside [0,B)");
+  return mt_loss(strong, weak, B, T, C, syn_first, syn_n, syn_target, real_first, real_n, strong_ema, weak_ema, cons_w,
+                 losses, d_strong, d_weak, as_stream(stream));
+}
+
+extern "C" int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m, float* v, float* ema,
+                                 int64_t n, const bsed_opt_cfg* cfg, void* stream) {
+  BSED_REQUIRE(h && params && grads && m && cfg, "bsed_opt_ema_step: null argument");
+  BSED_REQUIRE(cfg->kind != 0 || v, "bsed_opt_ema_step: Adam needs v");
+  return opt_ema_step(params, grads, m, v, ema, n, cfg, as_stream(stream));
+}
+
+extern "C" int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffers, int64_t n,
+                                const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float ema_alpha, int64_t ema_step,
+                                void* stream) {
+  BSED_REQUIRE(h && bn_buffers && ema_bn_buffers, "bsed_ema_buffers: null argument");
+  return ema_buffers(bn_buffers, ema_bn_buffers, n, nbt, ema_nbt, n_nbt, ema_alpha, ema_step, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernels (unit tests)
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsed_gemm_nn(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M,
+                            int N, int K, const float* bias, int accumulate, void* stream) {
+  BSED_REQUIRE(h && A && Bm && C, "bsed_gemm_nn: null argument");
+  return gemm_nn(A, lda, Bm, ldb, C, ldc, M, N, K, bias, accumulate, as_stream(stream));
+}
+
+extern "C" int bsed_gemm_tn(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M,
+                            int N, int K, void* stream) {
+  BSED_REQUIRE(h && A && Bm && C, "bsed_gemm_tn: null argument");
+  return gemm_tn(A, lda, Bm, ldb, C, ldc, 1, M, N, K, h->num_sms * 4, as_stream(stream));
+}
+
+extern "C" int bsed_conv3x3(bsed_handle h, const float* x, const float* weight, const float* bias, float* y, int B,
+                            int T, int F, int Cin, int Cout, float* wpack, void* stream) {
+  BSED_REQUIRE(h && x && weight && y && wpack, "bsed_conv3x3: null argument");
+  PrepTable tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.n = 1;
+  tb.ops[0].type = PREP_CONV_PACK;
+  tb.ops[0].src = weight;
+  tb.ops[0].dst = wpack;
+  tb.ops[0].d0 = Cout;
+  tb.ops[0].d1 = Cin;
+  BSED_TRY(run_prep(tb, as_stream(stream)));
+  return conv3x3_nn(x, wpack, y, B, T, F, Cin, Cout, bias, 0, as_stream(stream));
+}

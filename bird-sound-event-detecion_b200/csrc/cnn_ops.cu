@@ -1,0 +1,520 @@
+// cnn_ops.cu -- channels-last kernels of the gated CNN block around the GEMMs:
+//   conv0 (Cin = 1) forward / weight gradient, BatchNorm statistics / normalise / backward,
+//   GLU gate + dropout + average pool forward / backward.
+// Reference arithmetic: src/models/CNN.py:5-16 (GLU), :43-67 (block order), BatchNorm2d(eps=1e-3,
+// momentum=.99).  BN is applied as xhat = (y - mean) * rstd with gamma/beta folded into the GLU
+// linear (prep.cu) and into the sigmoid gate here.
+#include "launch.h"
+
+namespace bsed {
+
+__device__ __forceinline__ int group_of(const Groups& g, int clip) {
+  int r = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroups; ++i)
+    if (i < g.n && clip >= g.first[i]) r = i;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv0: x [B][T][F] -> y [B][T][F][16], weights in the reference's (16,1,3,3) layout
+// grid (chunks, clip); thread -> (pixel, channel quad)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, Groups g, FloatPtrs w,
+                                                        FloatPtrs bias, float* __restrict__ y, int T, int F,
+                                                        int Cout) {
+  __shared__ float ws[128 * 9];
+  __shared__ float bs[128];
+  const int clip = blockIdx.y;
+  const int grp = group_of(g, clip);
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i] = w.p[grp][i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias.p[grp][i];
+  __syncthreads();
+  const int nq = Cout / 4;
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long npix = (long long)T * F;
+  if (id >= npix * nq) return;
+  int q = (int)(id % nq);
+  int pix = (int)(id / nq);
+  int f = pix % F, t = pix / F;
+  const float* xc = x + (size_t)clip * npix;
+  float v[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
+    v[tap] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
+  }
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int co = q * 4 + j;
+    float a = bs[co];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) a = fmaf(v[tap], ws[co * 9 + tap], a);
+    o[j] = a;
+  }
+  float4* dst = reinterpret_cast<float4*>(y + ((size_t)clip * npix + pix) * Cout + q * 4);
+  *dst = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+int conv0_fwd(const float* x, const Groups& g, const FloatPtrs& w, const FloatPtrs& bias, float* y, int T,
+              int F, int Cout, cudaStream_t st) {
+  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128, "conv0: Cout=%d", Cout);
+  int B = g.first[g.n - 1] + g.count[g.n - 1];
+  long long work = (long long)T * F * (Cout / 4);
+  dim3 grid(ceil_div(work, 256), B);
+  conv0_fwd_kernel<<<grid, 256, 0, st>>>(x, g, w, bias, y, T, F, Cout);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// dW[co][tap] += sum_p dY[p][co] * x[p + tap]; Cout == 16 (4 quads): thread -> (pixel, quad)
+__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ dY, float* dW, int first_clip,
+                                                          int T, int F, int Cout, int iters) {
+  const int clip = first_clip + blockIdx.y;
+  const int nq = Cout / 4;
+  const long long npix = (long long)T * F;
+  const float* xc = x + (size_t)clip * npix;
+  float acc[4][9];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) acc[j][tap] = 0.f;
+  const int q = threadIdx.x % nq;
+  for (int it = 0; it < iters; ++it) {
+    long long id = ((long long)blockIdx.x * iters + it) * blockDim.x + threadIdx.x;
+    long long pix = id / nq;
+    if (pix >= npix) break;
+    int f = (int)(pix % F), t = (int)(pix / F);
+    float4 d = *reinterpret_cast<const float4*>(dY + ((size_t)clip * npix + pix) * Cout + q * 4);
+    float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
+      float xv = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][tap] = fmaf(dv[j], xv, acc[j][tap]);
+    }
+  }
+  // reduce over threads with equal q: first inside the warp (lanes l, l + nq, ...), then via smem
+  __shared__ float red[8][32 * 9 * 4 / 4];  // [warp][nq(<=32)*... ] sized for nq <= 8 below
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      float v = acc[j][tap];
+      for (int o = 16; o >= nq; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[j][tap] = v;
+    }
+  if (lane < nq) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) red[warp][(lane * 4 + j) * 9 + tap] = acc[j][tap];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) {
+    float s = 0.f;
+    for (int wdx = 0; wdx < 8; ++wdx) s += red[wdx][i];
+    atomicAdd(dW + i, s);
+  }
+}
+
+int conv0_wgrad(const float* x, const float* dY, float* dW, int first_clip, int n_clips, int T, int F,
+                int Cout, int num_sms, cudaStream_t st) {
+  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 32 && (32 % (Cout / 4)) == 0 && (256 % (Cout / 4)) == 0,
+               "conv0_wgrad: Cout=%d unsupported", Cout);
+  long long work = (long long)T * F * (Cout / 4);
+  int iters = 16;
+  dim3 grid(ceil_div(work, 256LL * iters), n_clips);
+  conv0_wgrad_kernel<<<grid, 256, 0, st>>>(x, dY, dW, first_clip, T, F, Cout, iters);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel column reductions over the rows of each clip, accumulated per group in double
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        Groups g, long long rows_per_clip, int C,
+                                                        long long rows_per_cta, double* out) {
+  const int clip_idx = blockIdx.y;  // index among the clips covered by the groups
+  // map blockIdx.y -> absolute clip: groups are contiguous, first[0] may be > 0
+  int clip = -1, grp = 0;
+  {
+    int rem = clip_idx;
+    for (int i = 0; i < g.n; ++i) {
+      if (rem < g.count[i]) {
+        clip = g.first[i] + rem;
+        grp = i;
+        break;
+      }
+      rem -= g.count[i];
+    }
+  }
+  if (clip < 0) return;
+  const int nq = C / 4;
+  const int q = threadIdx.x % nq;
+  const int r0 = threadIdx.x / nq;
+  const int rstep = blockDim.x / nq;
+  long long rbeg = (long long)blockIdx.x * rows_per_cta;
+  long long rend = rbeg + rows_per_cta;
+  if (rend > rows_per_clip) rend = rows_per_clip;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+  if (r0 < rstep) {
+    for (long long r = rbeg + r0; r < rend; r += rstep) {
+      size_t off = ((size_t)clip * rows_per_clip + r) * C + q * 4;
+      float4 av = *reinterpret_cast<const float4*>(a + off);
+      s1.x += av.x; s1.y += av.y; s1.z += av.z; s1.w += av.w;
+      if (MODE == 0) {
+        s2.x = fmaf(av.x, av.x, s2.x); s2.y = fmaf(av.y, av.y, s2.y);
+        s2.z = fmaf(av.z, av.z, s2.z); s2.w = fmaf(av.w, av.w, s2.w);
+      } else if (MODE == 1) {
+        float4 bv = *reinterpret_cast<const float4*>(b + off);
+        s2.x = fmaf(av.x, bv.x, s2.x); s2.y = fmaf(av.y, bv.y, s2.y);
+        s2.z = fmaf(av.z, bv.z, s2.z); s2.w = fmaf(av.w, bv.w, s2.w);
+      }
+    }
+  }
+  __shared__ float red[2][256][4];
+  red[0][threadIdx.x][0] = s1.x; red[0][threadIdx.x][1] = s1.y; red[0][threadIdx.x][2] = s1.z; red[0][threadIdx.x][3] = s1.w;
+  red[1][threadIdx.x][0] = s2.x; red[1][threadIdx.x][1] = s2.y; red[1][threadIdx.x][2] = s2.z; red[1][threadIdx.x][3] = s2.w;
+  __syncthreads();
+  // thread c (< C) sums the partials of its channel
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int cq = c / 4, cj = c % 4;
+    float t1 = 0.f, t2 = 0.f;
+    for (int r = 0; r < rstep; ++r) {
+      t1 += red[0][r * nq + cq][cj];
+      t2 += red[1][r * nq + cq][cj];
+    }
+    atomicAdd(out + ((size_t)grp * C + c) * 2 + 0, (double)t1);
+    if (MODE != 2) atomicAdd(out + ((size_t)grp * C + c) * 2 + 1, (double)t2);
+  }
+}
+
+int col_stats(const float* a, const float* b, int mode, const Groups& g, long long rows_per_clip, int C,
+              double* out, int num_sms, cudaStream_t st) {
+  BSED_REQUIRE(C % 4 == 0 && C / 4 <= 256, "col_stats: C=%d", C);
+  int nclips = 0;
+  for (int i = 0; i < g.n; ++i) nclips += g.count[i];
+  if (nclips == 0) return BSED_OK;
+  // aim for ~8 CTAs per SM overall, at least 64 rows per CTA
+  long long want = (long long)num_sms * 8 / nclips + 1;
+  long long rows_per_cta = (rows_per_clip + want - 1) / want;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  dim3 grid(ceil_div(rows_per_clip, rows_per_cta), nclips);
+  int threads = (C / 4) * (256 / (C / 4));  // a multiple of the quads per row, <= 256
+  if (mode == 0) col_stats_kernel<0><<<grid, threads, 0, st>>>(a, b, g, rows_per_clip, C, rows_per_cta, out);
+  else if (mode == 1) col_stats_kernel<1><<<grid, threads, 0, st>>>(a, b, g, rows_per_clip, C, rows_per_cta, out);
+  else col_stats_kernel<2><<<grid, threads, 0, st>>>(a, b, g, rows_per_clip, C, rows_per_cta, out);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+__global__ void add_double_to_float_kernel(const double* src, int stride, float* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += (float)src[(size_t)i * stride];
+}
+int add_double_to_float(const double* src, int stride, float* dst, int n, cudaStream_t st) {
+  add_double_to_float_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, stride, dst, n);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+int col_sum_to(const float* a, long long rows, int C, float* out, double* scratch, int num_sms,
+               cudaStream_t st) {
+  // treat the whole matrix as one "clip" of one group
+  Groups g;
+  g.n = 1;
+  g.first[0] = 0;
+  g.count[0] = 1;
+  BSED_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  BSED_TRY(col_stats(a, nullptr, 2, g, rows, C, scratch, num_sms, st));
+  return add_double_to_float(scratch, 2, out, C, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm finalise / eval prepare / normalise
+// ---------------------------------------------------------------------------------------------
+struct RunPtrs {
+  float* mean[kMaxGroups];
+  float* var[kMaxGroups];
+  int64_t* nbt[kMaxGroups];
+};
+
+__global__ void bn_finalize_train_kernel(const double* __restrict__ stats, Groups g, long long rows_per_clip,
+                                         int C, float eps, float momentum, BNPtrs bn, RunPtrs run) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int i = 0; i < g.n; ++i) {
+    double n = (double)g.count[i] * (double)rows_per_clip;
+    double s = stats[((size_t)i * C + c) * 2], ss = stats[((size_t)i * C + c) * 2 + 1];
+    double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0) var = 0;
+    bn.mean[i][c] = (float)mean;
+    bn.rstd[i][c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (run.mean[i]) {
+      double unb = n > 1 ? var * n / (n - 1) : var;
+      run.mean[i][c] = (1.f - momentum) * run.mean[i][c] + momentum * (float)mean;
+      run.var[i][c] = (1.f - momentum) * run.var[i][c] + momentum * (float)unb;
+    }
+    if (c == 0 && run.nbt[i]) *run.nbt[i] += 1;
+  }
+}
+
+int bn_finalize_train(const double* stats, const Groups& g, long long rows_per_clip, int C, float eps,
+                      float momentum, const BNPtrs& bn, float* const* run_mean, float* const* run_var,
+                      int64_t* const* nbt, cudaStream_t st) {
+  RunPtrs run;
+  for (int i = 0; i < kMaxGroups; ++i) {
+    run.mean[i] = i < g.n ? run_mean[i] : nullptr;
+    run.var[i] = i < g.n ? run_var[i] : nullptr;
+    run.nbt[i] = i < g.n ? nbt[i] : nullptr;
+  }
+  bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, st>>>(stats, g, rows_per_clip, C, eps, momentum, bn, run);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+__global__ void bn_prepare_eval_kernel(Groups g, int C, float eps, BNPtrs bn, RunPtrs run) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int i = 0; i < g.n; ++i) {
+    bn.mean[i][c] = run.mean[i][c];
+    bn.rstd[i][c] = 1.0f / sqrtf(run.var[i][c] + eps);
+  }
+}
+
+int bn_prepare_eval(const Groups& g, int C, float eps, const BNPtrs& bn, float* const* run_mean,
+                    float* const* run_var, cudaStream_t st) {
+  RunPtrs run;
+  for (int i = 0; i < kMaxGroups; ++i) {
+    run.mean[i] = i < g.n ? run_mean[i] : nullptr;
+    run.var[i] = i < g.n ? run_var[i] : nullptr;
+    run.nbt[i] = nullptr;
+  }
+  bn_prepare_eval_kernel<<<ceil_div(C, 128), 128, 0, st>>>(g, C, eps, bn, run);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// in place y -> xhat = (y - mean) * rstd ; grid (chunks, clip)
+__global__ void __launch_bounds__(256) bn_normalize_kernel(float* __restrict__ y, Groups g, long long elems_per_clip,
+                                                           int C, BNPtrs bn) {
+  const int clip = g.first[0] + blockIdx.y;
+  const int grp = group_of(g, clip);
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= elems_per_clip) return;
+  int c = (int)((i4 * 4) % C);
+  float4* p = reinterpret_cast<float4*>(y + (size_t)clip * elems_per_clip) + i4;
+  float4 v = *p;
+  const float* mu = bn.mean[grp] + c;
+  const float* rs = bn.rstd[grp] + c;
+  v.x = (v.x - mu[0]) * rs[0];
+  v.y = (v.y - mu[1]) * rs[1];
+  v.z = (v.z - mu[2]) * rs[2];
+  v.w = (v.w - mu[3]) * rs[3];
+  *p = v;
+}
+
+static int total_clips(const Groups& g) {
+  int n = 0;
+  for (int i = 0; i < g.n; ++i) n += g.count[i];
+  return n;
+}
+
+int bn_normalize(float* y, const Groups& g, long long rows_per_clip, int C, const BNPtrs& bn,
+                 cudaStream_t st) {
+  long long elems = rows_per_clip * C;
+  dim3 grid(ceil_div(elems / 4, 256), total_clips(g));
+  bn_normalize_kernel<<<grid, 256, 0, st>>>(y, g, elems, C, bn);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GLU gate + dropout + average pool
+//   out = lin * sigmoid(gamma * xhat + beta) * keep / (1 - p), averaged over the pt x pf window
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) glu_gate_pool_fwd_kernel(const float* __restrict__ xhat,
+                                                                const float* __restrict__ lin,
+                                                                float* __restrict__ pooled, Groups g, BNPtrs bn,
+                                                                int T, int F, int C, int pt, int pf, int To, int Fo,
+                                                                uint32_t key, uint32_t thresh, float inv_keep) {
+  const int clip = g.first[0] + blockIdx.y;
+  const int grp = group_of(g, clip);
+  const int nq = C / 4;
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)To * Fo * nq) return;
+  int q = (int)(id % nq);
+  int opix = (int)(id / nq);
+  int fo = opix % Fo, to = opix / Fo;
+  int c = q * 4;
+  float ga[4], be[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ga[j] = bn.gamma[grp][c + j];
+    be[j] = bn.beta[grp][c + j];
+  }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int dt = 0; dt < pt; ++dt)
+    for (int df = 0; df < pf; ++df) {
+      int t = to * pt + dt, f = fo * pf + df;
+      size_t e = (((size_t)clip * T + t) * F + f) * C + c;
+      float4 xv = *reinterpret_cast<const float4*>(xhat + e);
+      float4 lv = *reinterpret_cast<const float4*>(lin + e);
+      float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float ls[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = sigmoidf_(fmaf(ga[j], xs[j], be[j]));
+        float o = ls[j] * s;
+        if (thresh) o = bsed_keep((uint32_t)(e + j), key, thresh) ? o * inv_keep : 0.f;
+        acc[j] += o;
+      }
+    }
+  float inv = 1.0f / (float)(pt * pf);
+  float4 o = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<float4*>(pooled + (((size_t)clip * To + to) * Fo + fo) * C + c) = o;
+}
+
+int glu_gate_pool_fwd(const float* xhat, const float* lin, float* pooled, const Groups& g, const BNPtrs& bn,
+                      int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
+                      cudaStream_t st) {
+  int To = T / pt, Fo = F / pf;
+  long long work = (long long)To * Fo * (C / 4);
+  dim3 grid(ceil_div(work, 256), total_clips(g));
+  glu_gate_pool_fwd_kernel<<<grid, 256, 0, st>>>(xhat, lin, pooled, g, bn, T, F, C, pt, pf, To, Fo, key, thresh,
+                                                 inv_keep);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// backward: per full-resolution element
+//   g      = dpooled[window] / (pt*pf) * keep / (1-p)        (0 outside the pooled region)
+//   d_lin  = g * s                      -> overwrites lin
+//   dxn    = g * lin * s * (1 - s)      -> direct path of the gate (GLU linear path added by GEMM)
+__global__ void __launch_bounds__(256) glu_gate_pool_bwd_kernel(const float* __restrict__ xhat,
+                                                                float* __restrict__ lin_dlin,
+                                                                const float* __restrict__ dpooled,
+                                                                float* __restrict__ dxn, Groups g, BNPtrs bn, int T,
+                                                                int F, int C, int pt, int pf, int To, int Fo,
+                                                                uint32_t key, uint32_t thresh, float inv_keep) {
+  const int clip = g.first[0] + blockIdx.y;
+  const int grp = group_of(g, clip);
+  const int nq = C / 4;
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)T * F * nq) return;
+  int q = (int)(id % nq);
+  int pix = (int)(id / nq);
+  int f = pix % F, t = pix / F;
+  int c = q * 4;
+  size_t e = (((size_t)clip * T + t) * F + f) * C + c;
+  int to = t / pt, fo = f / pf;
+  float4 gv = make_float4(0, 0, 0, 0);
+  if (to < To && fo < Fo) gv = *reinterpret_cast<const float4*>(dpooled + (((size_t)clip * To + to) * Fo + fo) * C + c);
+  float4 xv = *reinterpret_cast<const float4*>(xhat + e);
+  float4 lv = *reinterpret_cast<const float4*>(lin_dlin + e);
+  float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+  float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  float ls[4] = {lv.x, lv.y, lv.z, lv.w};
+  float inv = 1.0f / (float)(pt * pf);
+  float dl[4], dx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float gg = gs[j] * inv;
+    if (thresh) gg = bsed_keep((uint32_t)(e + j), key, thresh) ? gg * inv_keep : 0.f;
+    float s = sigmoidf_(fmaf(bn.gamma[grp][c + j], xs[j], bn.beta[grp][c + j]));
+    dl[j] = gg * s;
+    dx[j] = gg * ls[j] * s * (1.f - s);
+  }
+  *reinterpret_cast<float4*>(lin_dlin + e) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+  *reinterpret_cast<float4*>(dxn + e) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+}
+
+int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
+                      const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                      float inv_keep, cudaStream_t st) {
+  int To = T / pt, Fo = F / pf;
+  long long work = (long long)T * F * (C / 4);
+  dim3 grid(ceil_div(work, 256), total_clips(g));
+  glu_gate_pool_bwd_kernel<<<grid, 256, 0, st>>>(xhat, lin_dlin, dpooled, dxn, g, bn, T, F, C, pt, pf, To, Fo,
+                                                 key, thresh, inv_keep);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// dY = gamma * rstd * (dxn - s1/n - xhat * s2/n), in place on dxn
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dxn, const float* __restrict__ xhat,
+                                                           const double* __restrict__ stats2, Groups g,
+                                                           long long elems_per_clip, long long rows_per_clip, int C,
+                                                           BNPtrs bn) {
+  const int clip = g.first[0] + blockIdx.y;
+  const int grp = group_of(g, clip);
+  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= elems_per_clip) return;
+  int c = (int)((i4 * 4) % C);
+  float invn = 1.0f / ((float)g.count[grp] * (float)rows_per_clip);
+  size_t off = (size_t)clip * elems_per_clip + i4 * 4;
+  float4 d = *reinterpret_cast<float4*>(dxn + off);
+  float4 xh = *reinterpret_cast<const float4*>(xhat + off);
+  float dv[4] = {d.x, d.y, d.z, d.w};
+  float xs[4] = {xh.x, xh.y, xh.z, xh.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float s1 = (float)stats2[((size_t)grp * C + c + j) * 2] * invn;
+    float s2 = (float)stats2[((size_t)grp * C + c + j) * 2 + 1] * invn;
+    float k = bn.gamma[grp][c + j] * bn.rstd[grp][c + j];
+    dv[j] = k * (dv[j] - s1 - xs[j] * s2);
+  }
+  *reinterpret_cast<float4*>(dxn + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+}
+
+int bn_bwd_apply(float* dxn_dy, const float* xhat, const double* stats2, const Groups& g,
+                 long long rows_per_clip, int C, const BNPtrs& bn, cudaStream_t st) {
+  long long elems = rows_per_clip * C;
+  dim3 grid(ceil_div(elems / 4, 256), total_clips(g));
+  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dxn_dy, xhat, stats2, g, elems, rows_per_clip, C, bn);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// parameter gradients of BN (gamma, beta) and the un-folding of the GLU linear gradient:
+//   lin = Wg (gamma*xhat + beta) + bg  =>  dWg[c'][c] = gamma[c] * G[c'][c] + beta[c] * dbg[c'],
+//   G = d_lin^T xhat, dbg = colsum(d_lin)
+__global__ void bn_glu_param_grads_kernel(const double* __restrict__ stats2, int n_groups, int C,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          const float* __restrict__ G, const double* __restrict__ dbg,
+                                          float* d_gamma, float* d_beta, float* d_wg, float* d_bg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    double s1 = 0, s2 = 0;
+    for (int gI = 0; gI < n_groups; ++gI) {
+      s1 += stats2[((size_t)gI * C + i) * 2];
+      s2 += stats2[((size_t)gI * C + i) * 2 + 1];
+    }
+    d_beta[i] += (float)s1;
+    d_gamma[i] += (float)s2;
+    d_bg[i] += (float)dbg[(size_t)i * 2];
+  }
+  if (i < C * C) {
+    int cp = i / C, c = i % C;
+    d_wg[i] += gamma[c] * G[i] + beta[c] * (float)dbg[(size_t)cp * 2];
+  }
+}
+
+int bn_glu_param_grads(const double* stats2, int n_groups, int C, const float* gamma, const float* beta,
+                       const float* G, const double* dbg, float* d_gamma, float* d_beta, float* d_wg,
+                       float* d_bg, cudaStream_t st) {
+  bn_glu_param_grads_kernel<<<ceil_div(C * C, 256), 256, 0, st>>>(stats2, n_groups, C, gamma, beta, G, dbg,
+                                                                  d_gamma, d_beta, d_wg, d_bg);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+}  // namespace bsed

@@ -1,0 +1,129 @@
+// common.cuh -- shared device/host helpers for libbsed (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bsed.h"
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, no exceptions across the ABI)
+// ----------------------------------------------------------------------------------------------
+void bsed_set_error(const char* fmt, ...);
+
+#define BSED_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      bsed_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return BSED_E_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define BSED_CHECK_LAUNCH()                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      bsed_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return BSED_E_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define BSED_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      bsed_set_error(__VA_ARGS__);   \
+      return BSED_E_INVALID;         \
+    }                                \
+  } while (0)
+
+#define BSED_TRY(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != BSED_OK) return _r; \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------
+constexpr int kNFFT = 2048;
+constexpr int kHop = 255;
+constexpr int kNBins = 1025;
+constexpr int kNMels = 128;
+constexpr int kSampleRate = 32000;
+
+struct bsed_context {
+  int device;
+  int num_sms;
+  // frontend tables (device)
+  float* window;        // [2048] symmetric Hamming
+  float2* tw1024;       // [1024] e^{-2 pi i j / 1024}
+  float2* tw2048;       // [513]  e^{-2 pi i k / 2048}
+  float* mel_w;         // packed non-zero filterbank weights
+  int* mel_start;       // [128] first bin of band m
+  int* mel_len;         // [128] number of bins of band m
+  int* mel_off;         // [128] offset of band m inside mel_w
+  int mel_nnz;
+};
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// stateless dropout rule; restated in numpy in oracle/crnn.py:keep_mask
+__device__ __forceinline__ bool bsed_keep(uint32_t idx, uint32_t key, uint32_t thresh) {
+  uint32_t h = (idx * 0x9E3779B1u) ^ key;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h >= thresh;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+// host-side key mixing for the dropout hash (same as oracle/crnn.py:mix_key)
+static inline uint32_t bsed_mix_key(uint64_t seed, uint64_t step, uint64_t stream) {
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + step * 0xD1B54A32D192ED03ull +
+               stream * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+static inline uint32_t bsed_drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  if (t <= 0.0) return 0u;
+  return (uint32_t)t;
+}

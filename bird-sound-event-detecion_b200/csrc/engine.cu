@@ -1,0 +1,789 @@
+// engine.cu -- CRNN + Predictor plan: parameter layout, workspace carving, forward / backward
+// orchestration over the kernels of this library.
+//
+// Reference call structure: CRNN.forward (src/models/CRNN.py:211-240) = 7 x gated conv block
+// (src/models/CNN.py:43-67) -> BiGRU x2 (src/models/RNN.py) -> dropout; Predictor.forward
+// (src/models/CRNN.py:559-577).  One "group" is one reference model call (its own BatchNorm batch
+// statistics); groups that share a parameter buffer are batched in the same GEMM launches.
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+using namespace bsed;
+
+namespace {
+
+struct LayerGeom {
+  int Cin, Cout, T, F, pt, pf, To, Fo;
+  long long rows, prows;  // T*F and To*Fo per clip
+};
+
+struct ParamLayout {
+  long long conv_w[BSED_MAX_CNN_LAYERS], conv_b[BSED_MAX_CNN_LAYERS], bn_w[BSED_MAX_CNN_LAYERS],
+      bn_b[BSED_MAX_CNN_LAYERS], glu_w[BSED_MAX_CNN_LAYERS], glu_b[BSED_MAX_CNN_LAYERS];
+  long long wih[4][2], whh[4][2], bih[4][2], bhh[4][2];
+  long long total;
+  long long dense_w, dense_b, sm_w, sm_b, pred_total;  // Predictor: its own flat buffer
+  std::vector<long long> pred_order;
+  long long rm[BSED_MAX_CNN_LAYERS], rv[BSED_MAX_CNN_LAYERS], bn_total;
+  std::vector<long long> order;
+};
+
+struct PackedLayout {
+  long long wp[BSED_MAX_CNN_LAYERS], wd[BSED_MAX_CNN_LAYERS], glu_wT[BSED_MAX_CNN_LAYERS],
+      glu_bf[BSED_MAX_CNN_LAYERS];
+  long long wihT[4], bih[4], whhT[4], whh[4], bhh[4], wih_cat[4];
+  long long total;
+  long long wcatT, bcat, wcat, pred_total;  // Predictor operands (own region)
+};
+
+constexpr int kLdl = 48;  // padded logits row: [0,20) dense, [20,40) dense_softmax, rest zero
+
+}  // namespace
+
+struct bsed_crnn_plan {
+  bsed_context* ctx;
+  bsed_crnn_cfg cfg;
+  int max_clips;
+  int Tout;
+  LayerGeom L[BSED_MAX_CNN_LAYERS];
+  ParamLayout pl;
+  PackedLayout pk;
+  // workspace offsets (bytes)
+  size_t off_packed[2];
+  size_t off_xhat[BSED_MAX_CNN_LAYERS], off_lin[BSED_MAX_CNN_LAYERS], off_pool[BSED_MAX_CNN_LAYERS];
+  size_t off_stats, off_stats2, off_meanrstd;
+  size_t off_packed_pred;
+  size_t off_xg, off_gru_out[4], off_gru_saved[4], off_enc;
+  size_t off_dxn, off_dpool[2], off_dlogits, off_denc, off_dx1, off_dxg, off_dgh;
+  size_t off_G, off_dscratch, off_tmpw;
+  size_t ws_bytes;
+  // state of the last forward
+  bool saved_valid;
+  int n_groups, B;
+  Groups groups;
+  const float* gparams[kMaxGroups];
+  int gpset[kMaxGroups];
+  const float* pset_params[2];
+  int n_psets;
+  const float* x_in;
+  uint32_t keys[BSED_MAX_CNN_LAYERS + 1];
+  uint32_t thresh;
+  float inv_keep;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int build_layouts(bsed_crnn_plan* p) {
+  const bsed_crnn_cfg& c = p->cfg;
+  BSED_REQUIRE(c.n_cnn >= 1 && c.n_cnn <= BSED_MAX_CNN_LAYERS, "plan: n_cnn=%d", c.n_cnn);
+  BSED_REQUIRE(c.rnn_hidden == 128, "plan: rnn_hidden must be 128 (got %d)", c.rnn_hidden);
+  BSED_REQUIRE(c.rnn_layers >= 1 && c.rnn_layers <= 4, "plan: rnn_layers=%d", c.rnn_layers);
+  BSED_REQUIRE(c.n_class >= 1 && c.n_class <= 20, "plan: n_class=%d", c.n_class);
+  BSED_REQUIRE(c.dropout >= 0.f && c.dropout < 1.f, "plan: dropout=%f", c.dropout);
+  int T = c.n_frames, F = c.n_mels, Cin = 1;
+  for (int i = 0; i < c.n_cnn; ++i) {
+    LayerGeom& g = p->L[i];
+    BSED_REQUIRE(c.filters[i] % 16 == 0 && c.filters[i] >= 16 && c.filters[i] <= 128, "plan: filters[%d]=%d", i, c.filters[i]);
+    BSED_REQUIRE(c.pool_t[i] >= 1 && c.pool_f[i] >= 1, "plan: pooling[%d]", i);
+    g.Cin = Cin;
+    g.Cout = c.filters[i];
+    g.T = T;
+    g.F = F;
+    g.pt = c.pool_t[i];
+    g.pf = c.pool_f[i];
+    g.To = T / g.pt;
+    g.Fo = F / g.pf;
+    BSED_REQUIRE(g.To >= 1 && g.Fo >= 1, "plan: layer %d pools to nothing", i);
+    g.rows = (long long)T * F;
+    g.prows = (long long)g.To * g.Fo;
+    T = g.To;
+    F = g.Fo;
+    Cin = g.Cout;
+  }
+  BSED_REQUIRE(F == 1, "plan: frequency axis must pool to 1 (got %d)", F);
+  BSED_REQUIRE(Cin == 128, "plan: last CNN block must have 128 channels (GRU input), got %d", Cin);
+  p->Tout = T;
+  // flat parameter layout == reference named_parameters() order
+  ParamLayout& pl = p->pl;
+  long long o = 0;
+  auto take = [&](long long n) {
+    long long r = o;
+    pl.order.push_back(r);
+    o += n;
+    return r;
+  };
+  for (int i = 0; i < c.n_cnn; ++i) {
+    const LayerGeom& g = p->L[i];
+    pl.conv_w[i] = take((long long)g.Cout * g.Cin * 9);
+    pl.conv_b[i] = take(g.Cout);
+    pl.bn_w[i] = take(g.Cout);
+    pl.bn_b[i] = take(g.Cout);
+    pl.glu_w[i] = take((long long)g.Cout * g.Cout);
+    pl.glu_b[i] = take(g.Cout);
+  }
+  for (int l = 0; l < c.rnn_layers; ++l) {
+    int In = l == 0 ? 128 : 256;
+    for (int d = 0; d < 2; ++d) {
+      pl.wih[l][d] = take(384LL * In);
+      pl.whh[l][d] = take(384LL * 128);
+      pl.bih[l][d] = take(384);
+      pl.bhh[l][d] = take(384);
+    }
+  }
+  pl.total = o;
+  {
+    long long po = 0;
+    auto ptk = [&](long long n) {
+      long long r = po;
+      pl.pred_order.push_back(r);
+      po += n;
+      return r;
+    };
+    pl.dense_w = ptk((long long)c.n_class * 256);
+    pl.dense_b = ptk(c.n_class);
+    pl.sm_w = ptk((long long)c.n_class * 256);
+    pl.sm_b = ptk(c.n_class);
+    pl.pred_total = po;
+  }
+  long long bo = 0;
+  for (int i = 0; i < c.n_cnn; ++i) {
+    pl.rm[i] = bo;
+    bo += p->L[i].Cout;
+    pl.rv[i] = bo;
+    bo += p->L[i].Cout;
+  }
+  pl.bn_total = bo;
+  // packed operand layout (per parameter set)
+  PackedLayout& pk = p->pk;
+  long long q = 0;
+  auto ptake = [&](long long n) {
+    long long r = q;
+    q += (n + 3) / 4 * 4;
+    return r;
+  };
+  for (int i = 0; i < c.n_cnn; ++i) {
+    const LayerGeom& g = p->L[i];
+    pk.wp[i] = ptake((long long)g.Cout * g.Cin * 9);
+    pk.wd[i] = ptake((long long)g.Cout * g.Cin * 9);
+    pk.glu_wT[i] = ptake((long long)g.Cout * g.Cout);
+    pk.glu_bf[i] = ptake(g.Cout);
+  }
+  for (int l = 0; l < c.rnn_layers; ++l) {
+    int In = l == 0 ? 128 : 256;
+    pk.wihT[l] = ptake(768LL * In);
+    pk.bih[l] = ptake(768);
+    pk.whhT[l] = ptake(2LL * 128 * 384);
+    pk.whh[l] = ptake(2LL * 384 * 128);
+    pk.bhh[l] = ptake(768);
+    pk.wih_cat[l] = ptake(768LL * In);
+  }
+  pk.total = q;
+  q = 0;
+  pk.wcatT = ptake(256LL * kLdl);
+  pk.bcat = ptake(kLdl);
+  pk.wcat = ptake((long long)kLdl * 256);
+  pk.pred_total = q;
+  return BSED_OK;
+}
+
+void carve_workspace(bsed_crnn_plan* p) {
+  const bsed_crnn_cfg& c = p->cfg;
+  const long long Bm = p->max_clips;
+  size_t o = 0;
+  auto takeb = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes);
+    return r;
+  };
+  for (int s = 0; s < 2; ++s) p->off_packed[s] = takeb(sizeof(float) * p->pk.total);
+  p->off_packed_pred = takeb(sizeof(float) * p->pk.pred_total);
+  long long max_full = 0, max_pool = 0;
+  for (int i = 0; i < c.n_cnn; ++i) {
+    const LayerGeom& g = p->L[i];
+    long long full = Bm * g.rows * g.Cout, pool = Bm * g.prows * g.Cout;
+    p->off_xhat[i] = takeb(sizeof(float) * full);
+    p->off_lin[i] = takeb(sizeof(float) * full);
+    p->off_pool[i] = takeb(sizeof(float) * pool);
+    if (full > max_full) max_full = full;
+    if (pool > max_pool) max_pool = pool;
+  }
+  p->off_stats = takeb(sizeof(double) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2);
+  p->off_stats2 = takeb(sizeof(double) * kMaxGroups * 128 * 2);
+  p->off_meanrstd = takeb(sizeof(float) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2);
+  const long long BT = Bm * p->Tout;
+  p->off_xg = takeb(sizeof(float) * BT * 768);
+  for (int l = 0; l < c.rnn_layers; ++l) {
+    p->off_gru_out[l] = takeb(sizeof(float) * BT * 256);
+    p->off_gru_saved[l] = takeb(sizeof(float) * BT * 2 * 4 * 128);
+  }
+  p->off_enc = takeb(sizeof(float) * BT * 256);
+  p->off_dxn = takeb(sizeof(float) * max_full);
+  p->off_dpool[0] = takeb(sizeof(float) * max_pool);
+  p->off_dpool[1] = takeb(sizeof(float) * max_pool);
+  p->off_dlogits = takeb(sizeof(float) * BT * kLdl);
+  p->off_denc = takeb(sizeof(float) * BT * 256);
+  p->off_dx1 = takeb(sizeof(float) * BT * 256);
+  p->off_dxg = takeb(sizeof(float) * BT * 768);
+  p->off_dgh = takeb(sizeof(float) * BT * 768);
+  p->off_G = takeb(sizeof(float) * 128 * 128);
+  p->off_dscratch = takeb(sizeof(double) * 2 * 768);
+  p->off_tmpw = takeb(sizeof(float) * kLdl * 256);
+  p->ws_bytes = o;
+}
+
+template <class T>
+T* wsp(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ws) + off);
+}
+
+void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
+  const bsed_crnn_cfg& c = p->cfg;
+  const ParamLayout& pl = p->pl;
+  const PackedLayout& pk = p->pk;
+  tb->n = 0;
+  auto add = [&](int type, const float* src, float* dst, int d0, int d1 = 0, int d2 = 0, int d3 = 0,
+                 const float* a0 = nullptr, const float* a1 = nullptr, const float* a2 = nullptr,
+                 float* dst2 = nullptr) {
+    PrepOp& op = tb->ops[tb->n++];
+    op.type = type;
+    op.src = src;
+    op.dst = dst;
+    op.dst2 = dst2;
+    op.aux0 = a0;
+    op.aux1 = a1;
+    op.aux2 = a2;
+    op.d0 = d0;
+    op.d1 = d1;
+    op.d2 = d2;
+    op.d3 = d3;
+  };
+  for (int i = 0; i < c.n_cnn; ++i) {
+    const LayerGeom& g = p->L[i];
+    if (i > 0) {
+      add(PREP_CONV_PACK, params + pl.conv_w[i], packed + pk.wp[i], g.Cout, g.Cin);
+      if (need_bwd) add(PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
+    }
+    add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, 0, 0, 0, params + pl.bn_w[i],
+        params + pl.bn_b[i], params + pl.glu_b[i], packed + pk.glu_bf[i]);
+  }
+  for (int l = 0; l < c.rnn_layers; ++l) {
+    int In = l == 0 ? 128 : 256;
+    for (int d = 0; d < 2; ++d) {
+      // W_ih [384][In] -> wihT [In][768] columns d*384..
+      add(PREP_TRANSPOSE, params + pl.wih[l][d], packed + pk.wihT[l], 384, In, 768, d * 384);
+      add(PREP_COPY, params + pl.bih[l][d], packed + pk.bih[l] + d * 384, 384);
+      // W_hh [384][128] -> whhT [d][128][384]
+      add(PREP_TRANSPOSE, params + pl.whh[l][d], packed + pk.whhT[l] + (long long)d * 128 * 384, 384, 128, 384, 0);
+      add(PREP_COPY, params + pl.bhh[l][d], packed + pk.bhh[l] + d * 384, 384);
+      if (need_bwd) {
+        add(PREP_COPY, params + pl.whh[l][d], packed + pk.whh[l] + (long long)d * 384 * 128, 384 * 128);
+        add(PREP_COPY, params + pl.wih[l][d], packed + pk.wih_cat[l] + (long long)d * 384 * In, 384 * In);
+      }
+    }
+  }
+}
+
+void build_prep_table_head(const bsed_crnn_plan* p, const float* params, float* packed, PrepTable* tb) {
+  const bsed_crnn_cfg& c = p->cfg;
+  const ParamLayout& pl = p->pl;
+  const PackedLayout& pk = p->pk;
+  const int C = c.n_class;
+  tb->n = 0;
+  auto add = [&](int type, const float* src, float* dst, int d0, int d1, int d2, int d3) {
+    PrepOp& op = tb->ops[tb->n++];
+    memset(&op, 0, sizeof(op));
+    op.type = type;
+    op.src = src;
+    op.dst = dst;
+    op.d0 = d0;
+    op.d1 = d1;
+    op.d2 = d2;
+    op.d3 = d3;
+  };
+  add(PREP_ZERO, nullptr, packed + pk.wcatT, 256 * kLdl, 0, 0, 0);
+  add(PREP_ZERO, nullptr, packed + pk.bcat, kLdl, 0, 0, 0);
+  add(PREP_ZERO, nullptr, packed + pk.wcat, kLdl * 256, 0, 0, 0);
+  // dense.weight [C][256] -> wcatT [256][48] cols 0..C-1 ; dense_softmax -> cols C..2C-1
+  add(PREP_TRANSPOSE, params + pl.dense_w, packed + pk.wcatT, C, 256, kLdl, 0);
+  add(PREP_TRANSPOSE, params + pl.sm_w, packed + pk.wcatT, C, 256, kLdl, C);
+  add(PREP_COPY, params + pl.dense_b, packed + pk.bcat, C, 0, 0, 0);
+  add(PREP_COPY, params + pl.sm_b, packed + pk.bcat + C, C, 0, 0, 0);
+  add(PREP_COPY, params + pl.dense_w, packed + pk.wcat, C * 256, 0, 0, 0);
+  add(PREP_COPY, params + pl.sm_w, packed + pk.wcat + (long long)C * 256, C * 256, 0, 0, 0);
+}
+
+BNPtrs make_bn_ptrs(const bsed_crnn_plan* p, void* ws, int layer, const int* group_ids, int n) {
+  BNPtrs bn;
+  float* mr = wsp<float>(ws, p->off_meanrstd);
+  for (int i = 0; i < kMaxGroups; ++i) {
+    int gi = i < n ? group_ids[i] : group_ids[0];
+    const float* par = p->gparams[gi];
+    bn.gamma[i] = par + p->pl.bn_w[layer];
+    bn.beta[i] = par + p->pl.bn_b[layer];
+    bn.mean[i] = mr + ((size_t)(layer * kMaxGroups + gi) * 2 + 0) * 128;
+    bn.rstd[i] = mr + ((size_t)(layer * kMaxGroups + gi) * 2 + 1) * 128;
+  }
+  return bn;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI: plan
+// =================================================================================================
+extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max_clips, bsed_plan* out) {
+  BSED_REQUIRE(h && cfg && out, "plan_create: null argument");
+  BSED_REQUIRE(max_clips >= 1 && max_clips <= 4096, "plan_create: max_clips=%d", max_clips);
+  bsed_crnn_plan* p = new bsed_crnn_plan();
+  p->ctx = h;
+  p->cfg = *cfg;
+  p->max_clips = max_clips;
+  p->saved_valid = false;
+  int r = build_layouts(p);
+  if (r != BSED_OK) {
+    delete p;
+    return r;
+  }
+  carve_workspace(p);
+  *out = p;
+  return BSED_OK;
+}
+
+extern "C" int bsed_plan_destroy(bsed_plan p) {
+  delete p;
+  return BSED_OK;
+}
+
+extern "C" int64_t bsed_plan_param_count(bsed_plan p) { return p ? p->pl.total : -1; }
+extern "C" int64_t bsed_plan_bn_buffer_count(bsed_plan p) { return p ? p->pl.bn_total : -1; }
+extern "C" int bsed_plan_out_frames(bsed_plan p) { return p ? p->Tout : -1; }
+extern "C" size_t bsed_plan_workspace_bytes(bsed_plan p) { return p ? p->ws_bytes : 0; }
+extern "C" int bsed_plan_param_offsets(bsed_plan p, int64_t* offsets, int max_n) {
+  if (!p) return -1;
+  int n = (int)p->pl.order.size();
+  for (int i = 0; i < n && i < max_n; ++i) offsets[i] = p->pl.order[i];
+  return n;
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_groups, const float* x, int B,
+                                 int flags, uint64_t dropout_seed, uint64_t dropout_step, float* enc,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(p && groups && x && workspace && enc, "crnn_forward: null argument");
+  BSED_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups, "crnn_forward: n_groups=%d (max %d)", n_groups, kMaxGroups);
+  BSED_REQUIRE(B >= 1 && B <= p->max_clips, "crnn_forward: B=%d exceeds plan max_clips=%d", B, p->max_clips);
+  if (workspace_bytes < p->ws_bytes) {
+    bsed_set_error("crnn_forward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+    return BSED_E_WORKSPACE;
+  }
+  const bool train = flags & BSED_F_TRAIN;
+  const bool save = flags & BSED_F_SAVE;
+  BSED_REQUIRE(!save || train, "crnn_forward: BSED_F_SAVE requires BSED_F_TRAIN");
+  cudaStream_t st = as_stream(stream);
+  const bsed_crnn_cfg& c = p->cfg;
+  void* ws = workspace;
+
+  // groups must tile [0, B)
+  Groups g;
+  g.n = n_groups;
+  int next = 0;
+  p->n_psets = 0;
+  for (int i = 0; i < kMaxGroups; ++i) {
+    g.first[i] = 0;
+    g.count[i] = 0;
+  }
+  for (int i = 0; i < n_groups; ++i) {
+    BSED_REQUIRE(groups[i].first_clip == next && groups[i].n_clips >= 1, "crnn_forward: groups must tile [0,B) in order");
+    BSED_REQUIRE(groups[i].params && groups[i].bn_buffers, "crnn_forward: group %d has null buffers", i);
+    g.first[i] = groups[i].first_clip;
+    g.count[i] = groups[i].n_clips;
+    next += groups[i].n_clips;
+    p->gparams[i] = groups[i].params;
+    int ps = -1;
+    for (int s = 0; s < p->n_psets; ++s)
+      if (p->pset_params[s] == groups[i].params) ps = s;
+    if (ps < 0) {
+      BSED_REQUIRE(p->n_psets < 2, "crnn_forward: at most 2 distinct parameter buffers per call");
+      ps = p->n_psets++;
+      p->pset_params[ps] = groups[i].params;
+    }
+    p->gpset[i] = ps;
+    if (i > 0)
+      BSED_REQUIRE(p->gpset[i] >= p->gpset[i - 1], "crnn_forward: groups sharing a parameter buffer must be adjacent");
+  }
+  BSED_REQUIRE(next == B, "crnn_forward: groups cover %d clips, B=%d", next, B);
+  p->groups = g;
+  p->n_groups = n_groups;
+  p->B = B;
+  p->x_in = x;
+  p->saved_valid = false;
+  p->thresh = train ? bsed_drop_thresh(c.dropout) : 0u;
+  p->inv_keep = train && c.dropout > 0.f ? 1.0f / (1.0f - c.dropout) : 1.0f;
+  for (int i = 0; i <= c.n_cnn; ++i) p->keys[i] = bsed_mix_key(dropout_seed, dropout_step, i == c.n_cnn ? 7 : i);
+
+  // runs of clips sharing a parameter set
+  struct Run {
+    int first, count, pset;
+  } runs[2];
+  int n_runs = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    if (n_runs && runs[n_runs - 1].pset == p->gpset[i]) runs[n_runs - 1].count += g.count[i];
+    else runs[n_runs++] = Run{g.first[i], g.count[i], p->gpset[i]};
+  }
+
+  // operand preparation
+  for (int s = 0; s < p->n_psets; ++s) {
+    PrepTable tb;
+    float* packed = wsp<float>(ws, p->off_packed[s]);
+    build_prep_table(p, p->pset_params[s], packed, save, &tb);
+    BSED_TRY(run_prep(tb, st));
+  }
+
+  int all_ids[kMaxGroups] = {0, 1, 2, 3};
+  double* stats = wsp<double>(ws, p->off_stats);
+  if (train) BSED_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2, st));
+
+  for (int i = 0; i < c.n_cnn; ++i) {
+    const LayerGeom& L = p->L[i];
+    float* y = wsp<float>(ws, p->off_xhat[i]);
+    float* lin = wsp<float>(ws, p->off_lin[i]);
+    float* pool = wsp<float>(ws, p->off_pool[i]);
+    if (i == 0) {
+      FloatPtrs w, bias;
+      for (int k = 0; k < kMaxGroups; ++k) {
+        int gi = k < n_groups ? k : 0;
+        w.p[k] = p->gparams[gi] + p->pl.conv_w[0];
+        bias.p[k] = p->gparams[gi] + p->pl.conv_b[0];
+      }
+      BSED_TRY(conv0_fwd(x, g, w, bias, y, L.T, L.F, L.Cout, st));
+    } else {
+      const float* xin = wsp<float>(ws, p->off_pool[i - 1]);
+      for (int r = 0; r < n_runs; ++r) {
+        const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+        BSED_TRY(conv3x3_nn(xin + (size_t)runs[r].first * L.rows * L.Cin, packed + p->pk.wp[i],
+                            y + (size_t)runs[r].first * L.rows * L.Cout, runs[r].count, L.T, L.F, L.Cin, L.Cout,
+                            p->pset_params[runs[r].pset] + p->pl.conv_b[i], 0, st));
+      }
+    }
+    BNPtrs bn = make_bn_ptrs(p, ws, i, all_ids, n_groups);
+    float* rmean[kMaxGroups];
+    float* rvar[kMaxGroups];
+    int64_t* nbt[kMaxGroups];
+    for (int k = 0; k < kMaxGroups; ++k) {
+      int gi = k < n_groups ? k : 0;
+      rmean[k] = groups[gi].bn_buffers + p->pl.rm[i];
+      rvar[k] = groups[gi].bn_buffers + p->pl.rv[i];
+      nbt[k] = groups[gi].num_batches_tracked ? groups[gi].num_batches_tracked + i : nullptr;
+    }
+    if (train) {
+      double* st_i = stats + (size_t)i * kMaxGroups * 128 * 2;
+      BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
+      // stats rows are indexed [group][C]: col_stats uses stride C, finalize too
+      BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, rmean, rvar, nbt, st));
+    } else {
+      BSED_TRY(bn_prepare_eval(g, L.Cout, c.bn_eps, bn, rmean, rvar, st));
+    }
+    BSED_TRY(bn_normalize(y, g, L.rows, L.Cout, bn, st));
+    for (int r = 0; r < n_runs; ++r) {
+      const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+      size_t off = (size_t)runs[r].first * L.rows * L.Cout;
+      long long M = (long long)runs[r].count * L.rows;
+      BSED_REQUIRE(M < (1ll << 31), "crnn_forward: too many pixels");
+      BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
+                       packed + p->pk.glu_bf[i], 0, st));
+    }
+    BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
+                               p->inv_keep, st));
+  }
+
+  // GRU stack
+  const int T = p->Tout;
+  float* xg = wsp<float>(ws, p->off_xg);
+  float* enc_i = wsp<float>(ws, p->off_enc);
+  for (int l = 0; l < c.rnn_layers; ++l) {
+    const int In = l == 0 ? 128 : 256;
+    const float* X = l == 0 ? wsp<float>(ws, p->off_pool[c.n_cnn - 1]) : wsp<float>(ws, p->off_gru_out[l - 1]);
+    for (int r = 0; r < n_runs; ++r) {
+      const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+      BSED_TRY(gemm_nn(X + (size_t)runs[r].first * T * In, In, packed + p->pk.wihT[l], 768,
+                       xg + (size_t)runs[r].first * T * 768, 768, runs[r].count * T, 768, In, packed + p->pk.bih[l],
+                       0, st));
+    }
+    FloatPtrs whhT, bhh;
+    for (int k = 0; k < kMaxGroups; ++k) {
+      int gi = k < n_groups ? k : 0;
+      const float* packed = wsp<float>(ws, p->off_packed[p->gpset[gi]]);
+      whhT.p[k] = packed + p->pk.whhT[l];
+      bhh.p[k] = packed + p->pk.bhh[l];
+    }
+    const bool last = l == c.rnn_layers - 1;
+    BSED_TRY(gru_forward(xg, g, whhT, bhh, wsp<float>(ws, p->off_gru_out[l]), last ? enc_i : nullptr,
+                         save ? wsp<float>(ws, p->off_gru_saved[l]) : nullptr, T, p->keys[c.n_cnn], p->thresh,
+                         p->inv_keep, st));
+  }
+
+  BSED_CHECK_CUDA(cudaMemcpyAsync(enc, enc_i, sizeof(float) * (size_t)B * T * 256, cudaMemcpyDeviceToDevice, st));
+  p->saved_valid = save;
+  return BSED_OK;
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float* d_enc, float* grads,
+                                  int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(p && grads && workspace && d_enc, "crnn_backward: null argument");
+  if (!p->saved_valid) {
+    bsed_set_error("crnn_backward: no saved forward (call bsed_crnn_forward with BSED_F_TRAIN|BSED_F_SAVE first)");
+    return BSED_E_STATE;
+  }
+  if (workspace_bytes < p->ws_bytes) {
+    bsed_set_error("crnn_backward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+    return BSED_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  const bsed_crnn_cfg& c = p->cfg;
+  const ParamLayout& pl = p->pl;
+  void* ws = workspace;
+  // contiguous subset of groups sharing one parameter buffer
+  int ids[kMaxGroups], n = 0;
+  for (int i = 0; i < p->n_groups; ++i)
+    if (group_mask & (1u << i)) ids[n++] = i;
+  BSED_REQUIRE(n >= 1, "crnn_backward: empty group mask");
+  for (int k = 1; k < n; ++k) {
+    BSED_REQUIRE(ids[k] == ids[k - 1] + 1, "crnn_backward: masked groups must be adjacent");
+    BSED_REQUIRE(p->gparams[ids[k]] == p->gparams[ids[0]], "crnn_backward: masked groups must share parameters");
+  }
+  Groups gb;
+  gb.n = n;
+  for (int k = 0; k < kMaxGroups; ++k) {
+    gb.first[k] = k < n ? p->groups.first[ids[k]] : 0;
+    gb.count[k] = k < n ? p->groups.count[ids[k]] : 0;
+  }
+  const int first = gb.first[0];
+  int nb = 0;
+  for (int k = 0; k < n; ++k) nb += gb.count[k];
+  const float* params = p->gparams[ids[0]];
+  const float* packed = wsp<float>(ws, p->off_packed[p->gpset[ids[0]]]);
+  const int T = p->Tout;
+  const int sms = p->ctx->num_sms;
+  const int target = sms * 4;
+  double* dscr = wsp<double>(ws, p->off_dscratch);
+
+  if (!accumulate) BSED_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * pl.total, st));
+
+  // ---- gradient w.r.t. the encoder output, through the final dropout
+  float* denc = wsp<float>(ws, p->off_denc);
+  const size_t ro = (size_t)first * T;  // row offset of the first masked clip in (B*T)-row matrices
+  const long long BTn = (long long)nb * T;
+  BSED_CHECK_CUDA(cudaMemcpyAsync(denc + ro * 256, d_enc + ro * 256, sizeof(float) * BTn * 256, cudaMemcpyDeviceToDevice, st));
+  BSED_TRY(dropout_bwd_mask(denc + ro * 256, nullptr, (long long)ro * 256, BTn * 256, p->keys[c.n_cnn], p->thresh,
+                            p->inv_keep, st));
+
+  // ---- GRU stack
+  float* dxg = wsp<float>(ws, p->off_dxg);
+  float* dgh = wsp<float>(ws, p->off_dgh);
+  float* dx1 = wsp<float>(ws, p->off_dx1);
+  int cur = 0;
+  float* dpool_cur = wsp<float>(ws, p->off_dpool[cur]);
+  for (int l = c.rnn_layers - 1; l >= 0; --l) {
+    const int In = l == 0 ? 128 : 256;
+    const float* X = l == 0 ? wsp<float>(ws, p->off_pool[c.n_cnn - 1]) : wsp<float>(ws, p->off_gru_out[l - 1]);
+    const float* out_l = wsp<float>(ws, p->off_gru_out[l]);
+    // gradient w.r.t. this layer's output: denc for the top layer, dx1 (ping-pong with denc) below
+    float* dout = ((c.rnn_layers - 1 - l) % 2 == 0) ? denc : dx1;
+    float* dxin = ((c.rnn_layers - 1 - l) % 2 == 0) ? dx1 : denc;
+    BSED_TRY(gru_backward(dout, wsp<float>(ws, p->off_gru_saved[l]), out_l, packed + p->pk.whh[l], dxg, dgh, T, first,
+                          nb, st));
+    for (int d = 0; d < 2; ++d) {
+      BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
+                            grads + pl.whh[l][d], T, BTn, target, st));
+      BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[l][d], In, 1, 384, In, BTn,
+                       target, st));
+    }
+    Groups one;
+    one.n = 1;
+    one.first[0] = 0;
+    one.count[0] = 1;
+    BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
+    BSED_TRY(col_stats(dxg + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
+    BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bih[l][0], 384, st));
+    BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bih[l][1], 384, st));
+    BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
+    BSED_TRY(col_stats(dgh + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
+    BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bhh[l][0], 384, st));
+    BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bhh[l][1], 384, st));
+    float* dX = l == 0 ? dpool_cur + ro * 128 : dxin + ro * 256;
+    BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[l], In, dX, In, (int)BTn, In, 768, nullptr, 0, st));
+  }
+
+  // ---- CNN blocks
+  float* dxn = wsp<float>(ws, p->off_dxn);
+  double* stats2 = wsp<double>(ws, p->off_stats2);
+  float* G = wsp<float>(ws, p->off_G);
+  for (int i = c.n_cnn - 1; i >= 0; --i) {
+    const LayerGeom& L = p->L[i];
+    float* xhat = wsp<float>(ws, p->off_xhat[i]);
+    float* lin = wsp<float>(ws, p->off_lin[i]);
+    BNPtrs bn = make_bn_ptrs(p, ws, i, ids, n);
+    const size_t off = (size_t)first * L.rows * L.Cout;
+    const long long M = (long long)nb * L.rows;
+    // gate / dropout / pool backward: lin -> d_lin (in place), dxn <- direct gate path
+    BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
+                               p->inv_keep, st));
+    // dxn += d_lin * Wg        (Wg [c'][c] is already K-major for this product)
+    BSED_TRY(gemm_nn(lin + off, L.Cout, params + pl.glu_w[i], L.Cout, dxn + off, L.Cout, (int)M, L.Cout, L.Cout,
+                     nullptr, 1, st));
+    // G = d_lin^T xhat ; dbg = colsum(d_lin)
+    BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.Cout * L.Cout, st));
+    BSED_TRY(gemm_tn(lin + off, L.Cout, xhat + off, L.Cout, G, L.Cout, 1, L.Cout, L.Cout, M, target, st));
+    Groups one;
+    one.n = 1;
+    one.first[0] = 0;
+    one.count[0] = 1;
+    BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 128, st));
+    BSED_TRY(col_stats(lin + off, nullptr, 2, one, M, L.Cout, dscr, sms, st));
+    // BN backward reductions per group
+    BSED_CHECK_CUDA(cudaMemsetAsync(stats2, 0, sizeof(double) * kMaxGroups * 128 * 2, st));
+    BSED_TRY(col_stats(dxn, xhat, 1, gb, L.rows, L.Cout, stats2, sms, st));
+    BSED_TRY(bn_glu_param_grads(stats2, n, L.Cout, params + pl.bn_w[i], params + pl.bn_b[i], G, dscr,
+                                grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i], grads + pl.glu_b[i], st));
+    BSED_TRY(bn_bwd_apply(dxn, xhat, stats2, gb, L.rows, L.Cout, bn, st));
+    // conv bias gradient
+    BSED_TRY(col_sum_to(dxn + off, M, L.Cout, grads + pl.conv_b[i], dscr, sms, st));
+    if (i > 0) {
+      const float* xin = wsp<float>(ws, p->off_pool[i - 1]) + (size_t)first * L.rows * L.Cin;
+      BSED_TRY(conv3x3_wgrad(xin, dxn + off, grads + pl.conv_w[i], nb, L.T, L.F, L.Cin, L.Cout, target, st));
+      cur ^= 1;
+      float* dnext = wsp<float>(ws, p->off_dpool[cur]);
+      BSED_TRY(conv3x3_nn(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
+                          L.Cin, nullptr, 0, st));
+      dpool_cur = dnext;
+    } else {
+      BSED_TRY(conv0_wgrad(p->x_in, dxn, grads + pl.conv_w[0], first, nb, L.T, L.F, L.Cout, sms, st));
+    }
+  }
+  p->saved_valid = false;  // lin buffers now hold gradients
+  return BSED_OK;
+}
+
+// =================================================================================================
+// debug access
+// =================================================================================================
+extern "C" int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* name, float** ptr, int64_t* numel) {
+  BSED_REQUIRE(p && workspace && name && ptr && numel, "debug_tensor: null argument");
+  std::string s(name);
+  const long long Bm = p->max_clips;
+  auto layer_of = [&](const char* prefix, int* idx) {
+    size_t n = strlen(prefix);
+    if (s.compare(0, n, prefix) != 0 || s.size() != n + 1) return false;
+    *idx = s[n] - '0';
+    return *idx >= 0;
+  };
+  int i;
+  if (layer_of("xhat", &i) && i < p->cfg.n_cnn) {
+    *ptr = wsp<float>(workspace, p->off_xhat[i]);
+    *numel = Bm * p->L[i].rows * p->L[i].Cout;
+    return BSED_OK;
+  }
+  if (layer_of("lin", &i) && i < p->cfg.n_cnn) {
+    *ptr = wsp<float>(workspace, p->off_lin[i]);
+    *numel = Bm * p->L[i].rows * p->L[i].Cout;
+    return BSED_OK;
+  }
+  if (layer_of("pool", &i) && i < p->cfg.n_cnn) {
+    *ptr = wsp<float>(workspace, p->off_pool[i]);
+    *numel = Bm * p->L[i].prows * p->L[i].Cout;
+    return BSED_OK;
+  }
+  if (layer_of("gru", &i) && i < p->cfg.rnn_layers) {
+    *ptr = wsp<float>(workspace, p->off_gru_out[i]);
+    *numel = Bm * p->Tout * 256;
+    return BSED_OK;
+  }
+  if (s == "dxn") {
+    *ptr = wsp<float>(workspace, p->off_dxn);
+    *numel = Bm * p->L[0].rows * p->L[0].Cout;
+    return BSED_OK;
+  }
+  bsed_set_error("debug_tensor: unknown tensor '%s'", name);
+  return BSED_E_INVALID;
+}
+
+// =================================================================================================
+// Predictor (attention pooling head)                                src/models/CRNN.py:548-577
+// =================================================================================================
+extern "C" int64_t bsed_predictor_param_count(bsed_plan p) { return p ? p->pl.pred_total : -1; }
+extern "C" int bsed_predictor_param_offsets(bsed_plan p, int64_t* offsets, int max_n) {
+  if (!p) return -1;
+  int n = (int)p->pl.pred_order.size();
+  for (int i = 0; i < n && i < max_n; ++i) offsets[i] = p->pl.pred_order[i];
+  return n;
+}
+extern "C" int bsed_predictor_ldl(void) { return kLdl; }
+
+extern "C" int bsed_predictor_forward(bsed_plan p, const float* pred_params, const float* enc, int n_clips,
+                                      int inference, float* logits, float* strong, float* weak, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(p && pred_params && enc && logits && strong && weak && workspace, "predictor_forward: null argument");
+  BSED_REQUIRE(n_clips >= 1, "predictor_forward: n_clips=%d", n_clips);
+  if (workspace_bytes < p->ws_bytes) {
+    bsed_set_error("predictor_forward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+    return BSED_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  float* packed = wsp<float>(workspace, p->off_packed_pred);
+  PrepTable tb;
+  build_prep_table_head(p, pred_params, packed, &tb);
+  BSED_TRY(run_prep(tb, st));
+  const int T = p->Tout;
+  BSED_TRY(gemm_nn(enc, 256, packed + p->pk.wcatT, kLdl, logits, kLdl, n_clips * T, kLdl, 256, packed + p->pk.bcat, 0,
+                   st));
+  return head_forward(logits, strong, weak, n_clips, T, p->cfg.n_class, kLdl, inference ? 1 : 0, st);
+}
+
+extern "C" int bsed_predictor_backward(bsed_plan p, const float* pred_params, const float* enc, const float* logits,
+                                       const float* strong, const float* weak, const float* d_strong,
+                                       const float* d_weak, int n_clips, float* d_enc, float* grads, int accumulate,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(p && pred_params && enc && logits && strong && weak && d_enc && grads && workspace,
+               "predictor_backward: null argument");
+  if (workspace_bytes < p->ws_bytes) {
+    bsed_set_error("predictor_backward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+    return BSED_E_WORKSPACE;
+  }
+  BSED_REQUIRE(n_clips >= 1 && n_clips <= p->max_clips, "predictor_backward: n_clips=%d", n_clips);
+  cudaStream_t st = as_stream(stream);
+  const ParamLayout& pl = p->pl;
+  const int T = p->Tout, C = p->cfg.n_class;
+  const long long BTn = (long long)n_clips * T;
+  const int sms = p->ctx->num_sms;
+  float* packed = wsp<float>(workspace, p->off_packed_pred);
+  float* dlog = wsp<float>(workspace, p->off_dlogits);
+  float* tmpw = wsp<float>(workspace, p->off_tmpw);
+  double* dscr = wsp<double>(workspace, p->off_dscratch);
+  PrepTable tb;
+  build_prep_table_head(p, pred_params, packed, &tb);
+  BSED_TRY(run_prep(tb, st));
+  if (!accumulate) BSED_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * pl.pred_total, st));
+  BSED_TRY(head_backward(logits, strong, weak, d_strong, d_weak, dlog, 0, n_clips, T, C, kLdl, st));
+  BSED_CHECK_CUDA(cudaMemsetAsync(tmpw, 0, sizeof(float) * kLdl * 256, st));
+  BSED_TRY(gemm_tn(dlog, kLdl, enc, 256, tmpw, 256, 1, kLdl, 256, BTn, sms * 4, st));
+  BSED_TRY(add_f32(grads + pl.dense_w, tmpw, (long long)C * 256, st));
+  BSED_TRY(add_f32(grads + pl.sm_w, tmpw + (size_t)C * 256, (long long)C * 256, st));
+  Groups one;
+  one.n = 1;
+  one.first[0] = 0;
+  one.count[0] = 1;
+  BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * kLdl, st));
+  BSED_TRY(col_stats(dlog, nullptr, 2, one, BTn, kLdl, dscr, sms, st));
+  BSED_TRY(add_double_to_float(dscr, 2, grads + pl.dense_b, C, st));
+  BSED_TRY(add_double_to_float(dscr + 2 * C, 2, grads + pl.sm_b, C, st));
+  return gemm_nn(dlog, kLdl, packed + p->pk.wcat, 256, d_enc, 256, (int)BTn, 256, kLdl, nullptr, 0, st);
+}

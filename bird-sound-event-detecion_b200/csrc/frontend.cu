@@ -1,0 +1,407 @@
+// frontend.cu -- framed STFT -> |X| -> Slaney mel projection (K1 + K2), and the dB / noise /
+// pad / normalise transform.
+//
+// Reference: src/data/preprocess.py:18-45 (librosa.stft n_fft=2048 hop=255 symmetric Hamming,
+// center=True reflect; melspectrogram(S=|X|, 128 Slaney bands, norm=None)), and
+// src/data/Transforms.py:74-139,155-197,304-322 (AugmentGaussianNoise, ApplyLog, PadOrTrunc,
+// Normalize).
+//
+// K1/K2 design: one CTA stages the audio of 16 consecutive frames (2048 + 15*255 samples) in
+// shared memory with one coalesced pass (reflect padding resolved at load time), so the 8x frame
+// overlap is served from SMEM, not HBM.  Each warp then owns whole frames: the 2048-point real FFT
+// is a 1024-point complex FFT (even/odd packing) done as 32 x 32 -- two in-register 32-point FFTs
+// per lane with one padded shared-memory transpose in between -- followed by the real-FFT
+// untangling, the magnitude, and the sparse mel projection (2016 non-zero weights, <= 60 bins per
+// band), all without leaving the SM.  Only the 128 mel values per frame go back to HBM.
+#include "launch.h"
+
+namespace bsed {
+
+constexpr int FE_FPC = 16;                                  // frames per CTA
+constexpr int FE_WARPS = 8;
+constexpr int FE_AUD = ((kNFFT + (FE_FPC - 1) * kHop) + 15) / 16 * 16;  // 5888 staged samples
+constexpr int FE_BUF = 33 * 32;                             // padded transpose buffer (float2)
+constexpr int FE_MAG = 1028;
+constexpr int FE_MELW = 2048;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// e^{-2 pi i idx / 32}, idx = 0..15 (compile-time idx after unrolling)
+__device__ __forceinline__ float2 tw32(int idx) {
+  switch (idx) {
+    case 0: return make_float2(1.0f, 0.0f);
+    case 1: return make_float2(0.98078528040323043f, -0.19509032201612825f);
+    case 2: return make_float2(0.92387953251128674f, -0.38268343236508978f);
+    case 3: return make_float2(0.83146961230254524f, -0.55557023301960218f);
+    case 4: return make_float2(0.70710678118654757f, -0.70710678118654757f);
+    case 5: return make_float2(0.55557023301960229f, -0.83146961230254524f);
+    case 6: return make_float2(0.38268343236508984f, -0.92387953251128674f);
+    case 7: return make_float2(0.19509032201612833f, -0.98078528040323043f);
+    case 8: return make_float2(0.0f, -1.0f);
+    case 9: return make_float2(-0.19509032201612819f, -0.98078528040323043f);
+    case 10: return make_float2(-0.38268343236508973f, -0.92387953251128674f);
+    case 11: return make_float2(-0.55557023301960196f, -0.83146961230254546f);
+    case 12: return make_float2(-0.70710678118654746f, -0.70710678118654757f);
+    case 13: return make_float2(-0.83146961230254535f, -0.55557023301960218f);
+    case 14: return make_float2(-0.92387953251128674f, -0.38268343236508989f);
+    default: return make_float2(-0.98078528040323043f, -0.19509032201612861f);
+  }
+}
+
+__device__ __forceinline__ constexpr int bitrev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// in-register radix-2 DIF FFT of 32 complex points; result X[bitrev5(i)] = v[i]
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        float2 a = v[base + j], b = v[base + j + half];
+        v[base + j] = make_float2(a.x + b.x, a.y + b.y);
+        float2 d = make_float2(a.x - b.x, a.y - b.y);
+        const int ti = j * (16 / half);
+        if (ti == 0) v[base + j + half] = d;
+        else if (ti == 8) v[base + j + half] = make_float2(d.y, -d.x);
+        else v[base + j + half] = cmul(d, tw32(ti));
+      }
+    }
+  }
+}
+
+struct FrontendTables {
+  const float* window;
+  const float2* tw1024;
+  const float2* tw2048;
+  const float* mel_w;
+  const int* mel_start;
+  const int* mel_len;
+  const int* mel_off;
+  int mel_nnz;
+};
+
+__global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* __restrict__ audio, int n_samples,
+                                                                   int n_frames, float* __restrict__ mel,
+                                                                   FrontendTables tb) {
+  extern __shared__ __align__(16) unsigned char fe_smem[];
+  float* audio_s = reinterpret_cast<float*>(fe_smem);
+  float* win_s = audio_s + FE_AUD;
+  float2* tw1024_s = reinterpret_cast<float2*>(win_s + kNFFT);
+  float2* tw2048_s = tw1024_s + 1024;
+  float* melw_s = reinterpret_cast<float*>(tw2048_s + 516);
+  int* mstart_s = reinterpret_cast<int*>(melw_s + FE_MELW);
+  int* mlen_s = mstart_s + kNMels;
+  int* moff_s = mlen_s + kNMels;
+  float2* bufs = reinterpret_cast<float2*>(moff_s + kNMels);
+  float* mags = reinterpret_cast<float*>(bufs + FE_WARPS * FE_BUF);
+
+  const int tid = threadIdx.x;
+  const int lane = tid % 32, warp = tid / 32;
+  const int b = blockIdx.y;
+  const int frame0 = blockIdx.x * FE_FPC;
+  const float* y = audio + (size_t)b * n_samples;
+
+  // stage audio (reflect padding: ypad[p] = y[reflect(p - 1024)])
+  const long long p0 = (long long)frame0 * kHop;
+  const long long padded = (long long)n_samples + kNFFT;
+  for (int i = tid; i < FE_AUD; i += blockDim.x) {
+    long long p = p0 + i;
+    float v = 0.f;
+    if (p < padded) {
+      long long j = p - kNFFT / 2;
+      if (j < 0) j = -j;
+      if (j >= n_samples) j = 2LL * (n_samples - 1) - j;
+      v = __ldg(y + j);
+    }
+    audio_s[i] = v;
+  }
+  for (int i = tid; i < kNFFT; i += blockDim.x) win_s[i] = tb.window[i];
+  for (int i = tid; i < 1024; i += blockDim.x) tw1024_s[i] = tb.tw1024[i];
+  for (int i = tid; i < 513; i += blockDim.x) tw2048_s[i] = tb.tw2048[i];
+  for (int i = tid; i < tb.mel_nnz; i += blockDim.x) melw_s[i] = tb.mel_w[i];
+  for (int i = tid; i < kNMels; i += blockDim.x) {
+    mstart_s[i] = tb.mel_start[i];
+    mlen_s[i] = tb.mel_len[i];
+    moff_s[i] = tb.mel_off[i];
+  }
+  __syncthreads();
+
+  float2* buf = bufs + warp * FE_BUF;
+  float* mag = mags + warp * FE_MAG;
+
+  for (int fi = warp; fi < FE_FPC; fi += FE_WARPS) {
+    const int t = frame0 + fi;
+    if (t >= n_frames) break;
+    const float* fr = audio_s + fi * kHop;
+    float2 v[32];
+    // pass 1: lane = b0; z[32 a + b0] = (x[64a + 2b0] w, x[64a + 2b0 + 1] w)
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+      int n0 = 64 * a + 2 * lane;
+      v[a] = make_float2(fr[n0] * win_s[n0], fr[n0 + 1] * win_s[n0 + 1]);
+    }
+    fft32(v);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float2 yv = v[bitrev5(c)];
+      if (c > 0) yv = cmul(yv, tw1024_s[lane * c]);
+      buf[c * 33 + lane] = yv;
+    }
+    __syncwarp();
+    // pass 2: lane = c; FFT over b0
+#pragma unroll
+    for (int bb = 0; bb < 32; ++bb) v[bb] = buf[lane * 33 + bb];
+    fft32(v);
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 32; ++d) buf[lane + 32 * d] = v[bitrev5(d)];
+    __syncwarp();
+    // real-FFT untangling + magnitude
+#pragma unroll 4
+    for (int jj = 0; jj < 16; ++jj) {
+      int k = lane + 32 * jj;
+      if (k == 0) {
+        float2 z0 = buf[0];
+        mag[0] = fabsf(z0.x + z0.y);
+        mag[1024] = fabsf(z0.x - z0.y);
+        float2 zh = buf[512];
+        mag[512] = sqrtf(zh.x * zh.x + zh.y * zh.y);
+      } else {
+        float2 zk = buf[k], zm = buf[1024 - k];
+        float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        float2 O = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+        float2 P = cmul(tw2048_s[k], O);
+        float xr = E.x + P.y, xi = E.y - P.x;
+        float yr = E.x - P.y, yi = -E.y - P.x;
+        mag[k] = sqrtf(xr * xr + xi * xi);
+        mag[1024 - k] = sqrtf(yr * yr + yi * yi);
+      }
+    }
+    __syncwarp();
+    // sparse mel projection: lane -> bands lane, lane+32, lane+64, lane+96
+    float* out = mel + ((size_t)b * n_frames + t) * kNMels;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int m = lane + 32 * r;
+      int s = mstart_s[m], len = mlen_s[m], off = moff_s[m];
+      float acc = 0.f;
+      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[s + j], acc);
+      out[m] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+constexpr size_t FE_SMEM_BYTES = sizeof(float) * (FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516) +
+                                 sizeof(float) * FE_MELW + sizeof(int) * 3 * kNMels +
+                                 sizeof(float2) * FE_WARPS * FE_BUF + sizeof(float) * FE_WARPS * FE_MAG;
+
+int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st) {
+  BSED_REQUIRE(n_samples >= kNFFT / 2 + 1, "melspec: n_samples=%d < 1025 (reflect padding)", n_samples);
+  BSED_REQUIRE(B > 0, "melspec: B=%d", B);
+  static bool configured = false;
+  if (!configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FE_SMEM_BYTES));
+    configured = true;
+  }
+  int n_frames = 1 + n_samples / kHop;
+  FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_w, h->mel_start, h->mel_len, h->mel_off, h->mel_nnz};
+  dim3 grid(ceil_div(n_frames, FE_FPC), B);
+  melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, mel, tb);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// amplitude_to_db (+ noise, pad/trunc, normalise).  Two kernels:
+//   1. per clip: [std_m = sqrt(mean_t(mel^2) * 10^(-snr/10))], max |x| with x = mel (+ std_m * noise)
+//   2. elementwise: max(20 log10(max(1e-5,|x|)), maxdb - 80), rows >= t_in -> 0, (v - mean_m)/std_m
+// Arithmetic in double: the reference evaluates the noisy branch in float64.
+// workspace per clip: 128 doubles (std) + 1 double (max)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) db_stats_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
+                                                        double snr_scale, int t_in, double* ws) {
+  const int b = blockIdx.x;
+  const int m = threadIdx.x % kNMels, r = threadIdx.x / kNMels;  // 8 row lanes
+  const float* x = mel + (size_t)b * t_in * kNMels;
+  double* std_out = ws + (size_t)b * (kNMels + 1);
+  __shared__ double red[8][kNMels];
+  __shared__ double std_s[kNMels];
+  if (noise) {
+    double s = 0;
+    for (int t = r; t < t_in; t += 8) {
+      double v = (double)x[(size_t)t * kNMels + m];
+      s += v * v * snr_scale;
+    }
+    red[r][m] = s;
+    __syncthreads();
+    if (r == 0) {
+      double tot = 0;
+      for (int i = 0; i < 8; ++i) tot += red[i][m];
+      std_s[m] = sqrt(tot / (double)t_in);
+      std_out[m] = std_s[m];
+    }
+    __syncthreads();
+  }
+  double mx = 0;
+  const float* nz = noise ? noise + (size_t)b * t_in * kNMels : nullptr;
+  for (int t = r; t < t_in; t += 8) {
+    double v = (double)x[(size_t)t * kNMels + m];
+    if (nz) v += std_s[m] * (double)nz[(size_t)t * kNMels + m];
+    mx = fmax(mx, fabs(v));
+  }
+  __syncthreads();
+  red[r][m] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = 0;
+    for (int i = threadIdx.x; i < 8 * kNMels; i += 32) v = fmax(v, (&red[0][0])[i]);
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) std_out[kNMels] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) db_apply_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
+                                                       int t_in, int frames, const float* __restrict__ sc_mean,
+                                                       const float* __restrict__ sc_std, const double* __restrict__ ws,
+                                                       float* __restrict__ out) {
+  const int b = blockIdx.y;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)frames * kNMels) return;
+  int m = (int)(i % kNMels), t = (int)(i / kNMels);
+  const double* w = ws + (size_t)b * (kNMels + 1);
+  double v = 0.0;
+  if (t < t_in) {
+    size_t e = ((size_t)b * t_in + t) * kNMels + m;
+    double x = (double)mel[e];
+    if (noise) x += w[m] * (double)noise[e];
+    double db = 20.0 * log10(fmax(1e-5, fabs(x)));
+    double mdb = 20.0 * log10(fmax(1e-5, w[kNMels]));
+    v = fmax(db, mdb - 80.0);
+  }
+  // ApplyLog / PadOrTrunc produce float32 (ToTensor().float()) before Normalize
+  float vf = (float)v;
+  if (sc_mean) vf = (float)(((double)vf - (double)sc_mean[m]) / (double)sc_std[m]);
+  out[((size_t)b * frames + t) * kNMels + m] = vf;
+}
+
+int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_in, int frames,
+              const float* sc_mean, const float* sc_std, float* out, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+  BSED_REQUIRE(B > 0 && t_in > 0 && frames > 0, "amp_to_db: B=%d t_in=%d frames=%d", B, t_in, frames);
+  BSED_REQUIRE((sc_mean == nullptr) == (sc_std == nullptr), "amp_to_db: scaler mean/std must come together");
+  if (ws_bytes < sizeof(double) * (size_t)B * (kNMels + 1)) {
+    bsed_set_error("amp_to_db: workspace %zu < %zu", ws_bytes, sizeof(double) * (size_t)B * (kNMels + 1));
+    return BSED_E_WORKSPACE;
+  }
+  double snr_scale = pow(10.0, -(double)snr_db / 10.0);
+  db_stats_kernel<<<B, 1024, 0, st>>>(mel, noise, snr_scale, t_in, (double*)ws);
+  BSED_CHECK_LAUNCH();
+  int t_used = t_in < frames ? t_in : frames;
+  (void)t_used;
+  dim3 grid(ceil_div((long long)frames * kNMels, 256), B);
+  db_apply_kernel<<<grid, 256, 0, st>>>(mel, noise, t_in, frames, sc_mean, sc_std, (const double*)ws, out);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold -> binary median over time -> contiguous regions        (Appendix B of SURVEY.md)
+// one CTA per clip; T <= 1024, C <= 32
+// ---------------------------------------------------------------------------------------------
+constexpr int PP_MAXT = 1024;
+constexpr int PP_MAXC = 32;
+
+__global__ void __launch_bounds__(256) median_decode_kernel(const float* __restrict__ strong, int T, int C,
+                                                            float threshold, int win, int32_t* __restrict__ events,
+                                                            int max_events, int32_t* __restrict__ n_events) {
+  extern __shared__ unsigned char pp_smem[];
+  unsigned char* bin = pp_smem;                       // [C][T]
+  unsigned char* med = bin + PP_MAXC * PP_MAXT;       // [C][T]
+  __shared__ int counts[PP_MAXC];
+  __shared__ int offsets[PP_MAXC + 1];
+  const int b = blockIdx.x;
+  const float* p = strong + (size_t)b * T * C;
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    int t = i / C, c = i % C;
+    bin[c * PP_MAXT + t] = p[i] >= threshold ? 1 : 0;
+  }
+  __syncthreads();
+  const int left = win / 2, right = win - 1 - left, need = win - win / 2;
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    int c = i / T, t = i % T;
+    int ones = 0;
+    for (int u = t - left; u <= t + right; ++u) {
+      int r = u % (2 * T);
+      if (r < 0) r += 2 * T;
+      if (r >= T) r = 2 * T - 1 - r;
+      ones += bin[c * PP_MAXT + r];
+    }
+    med[c * PP_MAXT + t] = ones >= need ? 1 : 0;
+  }
+  __syncthreads();
+  // pass A: count runs per class
+  if (threadIdx.x < C) {
+    int c = threadIdx.x, n = 0;
+    unsigned char prev = 0;
+    for (int t = 0; t < T; ++t) {
+      unsigned char cur = med[c * PP_MAXT + t];
+      if (cur && !prev) ++n;
+      prev = cur;
+    }
+    counts[c] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < C; ++c) {
+      offsets[c] = acc;
+      acc += counts[c];
+    }
+    offsets[C] = acc;
+    n_events[b] = acc;
+  }
+  __syncthreads();
+  // pass B: emit (class, on, off), class-major then time
+  if (threadIdx.x < C) {
+    int c = threadIdx.x, k = offsets[c], on = -1;
+    int32_t* ev = events + (size_t)b * max_events * 3;
+    for (int t = 0; t <= T; ++t) {
+      unsigned char cur = t < T ? med[c * PP_MAXT + t] : 0;
+      if (cur && on < 0) on = t;
+      if (!cur && on >= 0) {
+        if (k < max_events) {
+          ev[k * 3 + 0] = c;
+          ev[k * 3 + 1] = on;
+          ev[k * 3 + 2] = t;
+        }
+        ++k;
+        on = -1;
+      }
+    }
+  }
+}
+
+int median_decode(const float* strong, int B, int T, int C, float threshold, int win, int32_t* events,
+                  int max_events, int32_t* n_events, cudaStream_t st) {
+  BSED_REQUIRE(T > 0 && T <= PP_MAXT && C > 0 && C <= PP_MAXC, "median_decode: T=%d C=%d (max 1024 x 32)", T, C);
+  BSED_REQUIRE(win >= 1 && win <= 2 * T, "median_decode: win=%d", win);
+  BSED_REQUIRE(B > 0 && max_events >= 0, "median_decode: B=%d", B);
+  static bool configured = false;
+  size_t smem = 2 * PP_MAXC * PP_MAXT;
+  if (!configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(median_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  median_decode_kernel<<<B, 256, smem, st>>>(strong, T, C, threshold, win, events, max_events, n_events);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+}  // namespace bsed

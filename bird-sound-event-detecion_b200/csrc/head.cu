@@ -1,0 +1,371 @@
+// head.cu -- Predictor head (attention pooling), mean-teacher losses, optimiser + EMA, and the
+// dropout backward mask.
+//
+// Predictor.forward                                                src/models/CRNN.py:559-577
+//   strong = sigmoid(x W1^T + b1)
+//   sof    = clamp(softmax_over_classes(x W2^T + b2), 1e-7, 1)
+//   weak   = sum_t strong * sof / sum_t sof
+// The two linears are one GEMM producing logits [B][T][ldl] (cols 0..C-1 dense, C..2C-1
+// dense_softmax); this file holds everything after it.
+#include "launch.h"
+
+namespace bsed {
+
+constexpr int kMaxC = 20;
+
+__device__ __forceinline__ void softmax_row(const float* l2, int C, float* sof_raw) {
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) mx = fmaxf(mx, l2[c]);
+  float sum = 0.f;
+  for (int c = 0; c < C; ++c) {
+    sof_raw[c] = expf(l2[c] - mx);
+    sum += sof_raw[c];
+  }
+  float inv = 1.0f / sum;
+  for (int c = 0; c < C; ++c) sof_raw[c] *= inv;
+}
+
+// grid B, 256 threads; thread -> frames t = tid, tid + 256, ...
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ logits, float* __restrict__ strong,
+                                                       float* __restrict__ weak, int T, int C, int ldl,
+                                                       int inference) {
+  const int b = blockIdx.x;
+  float num[kMaxC], den[kMaxC];
+  for (int c = 0; c < kMaxC; ++c) num[c] = den[c] = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* l = logits + ((size_t)b * T + t) * ldl;
+    float l2[kMaxC], sof[kMaxC];
+    for (int c = 0; c < C; ++c) l2[c] = l[C + c];
+    softmax_row(l2, C, sof);
+    for (int c = 0; c < C; ++c) {
+      float s = 1.0f / (1.0f + expf(-l[c]));
+      float a = fminf(fmaxf(sof[c], 1e-7f), 1.0f);
+      strong[((size_t)b * T + t) * C + c] = s;
+      num[c] += s * a;
+      den[c] += a;
+    }
+  }
+  __shared__ float red[2][8][kMaxC];
+  __shared__ float weak_s[kMaxC];
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  for (int c = 0; c < C; ++c) {
+    float n = warp_sum(num[c]), d = warp_sum(den[c]);
+    if (lane == 0) {
+      red[0][warp][c] = n;
+      red[1][warp][c] = d;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float n = 0.f, d = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      n += red[0][w][threadIdx.x];
+      d += red[1][w][threadIdx.x];
+    }
+    float wk = n / d;
+    weak_s[threadIdx.x] = wk;
+    if (weak) weak[(size_t)b * C + threadIdx.x] = wk;
+  }
+  if (inference) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+      for (int c = 0; c < C; ++c)
+        if (!(weak_s[c] > 0.5f)) strong[((size_t)b * T + t) * C + c] = 0.f;
+  }
+}
+
+int head_forward(const float* logits, float* strong, float* weak, int B, int T, int C, int ldl, int inference,
+                 cudaStream_t st) {
+  BSED_REQUIRE(C <= kMaxC && ldl >= 2 * C, "head: C=%d ldl=%d", C, ldl);
+  head_fwd_kernel<<<B, 256, 0, st>>>(logits, strong, weak, T, C, ldl, inference);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// d_logits from d_strong / d_weak
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ logits,
+                                                       const float* __restrict__ strong,
+                                                       const float* __restrict__ weak,
+                                                       const float* __restrict__ d_strong,
+                                                       const float* __restrict__ d_weak,
+                                                       float* __restrict__ d_logits, int first_clip, int T, int C,
+                                                       int ldl) {
+  const int b = first_clip + blockIdx.x;
+  // pass 1: den[c] = sum_t clamp(sof)
+  float den[kMaxC];
+  for (int c = 0; c < kMaxC; ++c) den[c] = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* l = logits + ((size_t)b * T + t) * ldl;
+    float l2[kMaxC], sof[kMaxC];
+    for (int c = 0; c < C; ++c) l2[c] = l[C + c];
+    softmax_row(l2, C, sof);
+    for (int c = 0; c < C; ++c) den[c] += fminf(fmaxf(sof[c], 1e-7f), 1.0f);
+  }
+  __shared__ float red[8][kMaxC];
+  __shared__ float den_s[kMaxC], dw_s[kMaxC], wk_s[kMaxC];
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  for (int c = 0; c < C; ++c) {
+    float d = warp_sum(den[c]);
+    if (lane == 0) red[warp][c] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float d = 0.f;
+    for (int w = 0; w < 8; ++w) d += red[w][threadIdx.x];
+    den_s[threadIdx.x] = d;
+    dw_s[threadIdx.x] = d_weak ? d_weak[(size_t)b * C + threadIdx.x] : 0.f;
+    wk_s[threadIdx.x] = weak[(size_t)b * C + threadIdx.x];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const size_t rt = (size_t)b * T + t;
+    const float* l = logits + rt * ldl;
+    float* dl = d_logits + rt * ldl;
+    float l2[kMaxC], sofr[kMaxC], dsr[kMaxC];
+    for (int c = 0; c < C; ++c) l2[c] = l[C + c];
+    softmax_row(l2, C, sofr);
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float s = strong[rt * C + c];
+      float a = fminf(fmaxf(sofr[c], 1e-7f), 1.0f);
+      float inv_den = 1.0f / den_s[c];
+      float ds = (d_strong ? d_strong[rt * C + c] : 0.f) + dw_s[c] * a * inv_den;
+      dl[c] = ds * s * (1.f - s);
+      float dsof = dw_s[c] * (s - wk_s[c]) * inv_den;
+      bool pass = sofr[c] >= 1e-7f && sofr[c] <= 1.0f;
+      dsr[c] = pass ? dsof : 0.f;
+      dot += dsr[c] * sofr[c];
+    }
+    for (int c = 0; c < C; ++c) dl[C + c] = sofr[c] * (dsr[c] - dot);
+    for (int c = 2 * C; c < ldl; ++c) dl[c] = 0.f;
+  }
+}
+
+int head_backward(const float* logits, const float* strong, const float* weak, const float* d_strong,
+                  const float* d_weak, float* d_logits, int first_clip, int n_clips, int T, int C, int ldl,
+                  cudaStream_t st) {
+  BSED_REQUIRE(C <= kMaxC && ldl >= 2 * C, "head: C=%d ldl=%d", C, ldl);
+  head_bwd_kernel<<<n_clips, 256, 0, st>>>(logits, strong, weak, d_strong, d_weak, d_logits, first_clip, T, C, ldl);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// d[i] = (d[i] + extra[i]) * keep(first_elem + i) / (1 - p)
+__global__ void dropout_bwd_mask_kernel(float* d, const float* extra, long long first_elem, long long n,
+                                        uint32_t key, uint32_t thresh, float inv_keep) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = d[i] + (extra ? extra[i] : 0.f);
+  if (thresh) v = bsed_keep((uint32_t)(first_elem + i), key, thresh) ? v * inv_keep : 0.f;
+  d[i] = v;
+}
+
+__global__ void add_f32_kernel(float* dst, const float* src, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+int add_f32(float* dst, const float* src, long long n, cudaStream_t st) {
+  if (n <= 0) return BSED_OK;
+  add_f32_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dst, src, n);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long long n, uint32_t key,
+                     uint32_t thresh, float inv_keep, cudaStream_t st) {
+  if (n <= 0) return BSED_OK;
+  dropout_bwd_mask_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d, extra, first_elem, n, key, thresh, inv_keep);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean-teacher losses (src/main.py:376,405,434,439-449) and their gradients
+//   BCELoss: -(y log x + (1-y) log(1-x)), logs clamped at -100, mean; grad (x-y)/max(x(1-x),1e-12)/N
+//   MSELoss: mean (a-b)^2; grad 2(a-b)/N
+// grid: B clips; losses[4] must be zero on entry.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bce_term(float x, float y) {
+  float lx = fmaxf(logf(x), -100.f), l1x = fmaxf(logf(1.f - x), -100.f);
+  return -(y * lx + (1.f - y) * l1x);
+}
+__device__ __forceinline__ float bce_grad(float x, float y) { return (x - y) / fmaxf(x * (1.f - x), 1e-12f); }
+
+__global__ void __launch_bounds__(256) mt_loss_kernel(const float* __restrict__ strong, const float* __restrict__ weak,
+                                                      int T, int C, int syn_first, int syn_n,
+                                                      const float* __restrict__ syn_target, int real_first, int real_n,
+                                                      const float* __restrict__ strong_ema,
+                                                      const float* __restrict__ weak_ema, float cons_w, float* losses,
+                                                      float* __restrict__ d_strong, float* __restrict__ d_weak) {
+  const int b = blockIdx.x;
+  const bool is_syn = b >= syn_first && b < syn_first + syn_n;
+  const bool is_real = b >= real_first && b < real_first + real_n;
+  const int TC = T * C;
+  float acc_s = 0.f, acc_w = 0.f;
+  __shared__ float tmax[kMaxC];
+  __shared__ float red[8];
+  if (threadIdx.x < kMaxC) tmax[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (is_syn) {
+    const float* tg = syn_target + (size_t)(b - syn_first) * TC;
+    const float inv_n = 1.0f / ((float)syn_n * (float)TC);
+    for (int i = threadIdx.x; i < TC; i += blockDim.x) {
+      float x = strong[(size_t)b * TC + i], y = tg[i];
+      acc_s += bce_term(x, y);
+      d_strong[(size_t)b * TC + i] = bce_grad(x, y) * inv_n;
+      if (y > 0.f) atomicMax(reinterpret_cast<int*>(&tmax[i % C]), __float_as_int(y));
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float x = weak[(size_t)b * C + threadIdx.x], y = tmax[threadIdx.x];
+      const float inv_nw = 1.0f / ((float)syn_n * (float)C);
+      acc_w = bce_term(x, y);
+      d_weak[(size_t)b * C + threadIdx.x] = bce_grad(x, y) * inv_nw;
+    }
+  } else if (is_real) {
+    const float* se = strong_ema + (size_t)(b - real_first) * TC;
+    const float inv_n = 1.0f / ((float)real_n * (float)TC);
+    for (int i = threadIdx.x; i < TC; i += blockDim.x) {
+      float d = strong[(size_t)b * TC + i] - se[i];
+      acc_s += d * d;
+      d_strong[(size_t)b * TC + i] = 2.f * cons_w * d * inv_n;
+    }
+    if (threadIdx.x < C) {
+      const float inv_nw = 1.0f / ((float)real_n * (float)C);
+      float d = weak[(size_t)b * C + threadIdx.x] - weak_ema[(size_t)(b - real_first) * C + threadIdx.x];
+      acc_w = d * d;
+      d_weak[(size_t)b * C + threadIdx.x] = 2.f * cons_w * d * inv_nw;
+    }
+  } else {
+    for (int i = threadIdx.x; i < TC; i += blockDim.x) d_strong[(size_t)b * TC + i] = 0.f;
+    if (threadIdx.x < C) d_weak[(size_t)b * C + threadIdx.x] = 0.f;
+    return;
+  }
+  // block reduce the two partial sums
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  float s = warp_sum(acc_s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot_s = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < 8; ++w) tot_s += red[w];
+  __syncthreads();
+  float wv = warp_sum(acc_w);
+  if (lane == 0) red[warp] = wv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot_w = 0.f;
+    for (int w = 0; w < 8; ++w) tot_w += red[w];
+    if (is_syn) {
+      atomicAdd(&losses[0], tot_s / ((float)syn_n * (float)TC));
+      atomicAdd(&losses[1], tot_w / ((float)syn_n * (float)C));
+    } else {
+      atomicAdd(&losses[2], cons_w * tot_s / ((float)real_n * (float)TC));
+      atomicAdd(&losses[3], cons_w * tot_w / ((float)real_n * (float)C));
+    }
+  }
+}
+
+int mt_loss(const float* strong, const float* weak, int B, int T, int C, int syn_first, int syn_n,
+            const float* syn_target, int real_first, int real_n, const float* strong_ema, const float* weak_ema,
+            float cons_w, float* losses, float* d_strong, float* d_weak, cudaStream_t st) {
+  BSED_REQUIRE(C <= kMaxC, "mt_loss: C=%d", C);
+  BSED_CHECK_CUDA(cudaMemsetAsync(losses, 0, 4 * sizeof(float), st));
+  mt_loss_kernel<<<B, 256, 0, st>>>(strong, weak, T, C, syn_first, syn_n, syn_target, real_first, real_n,
+                                    strong_ema, weak_ema, cons_w, losses, d_strong, d_weak);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimiser + EMA over flat buffers
+// ---------------------------------------------------------------------------------------------
+struct OptScalars {
+  int kind;
+  float lr, beta1, beta2, eps, wd, momentum, grad_scale;
+  float step_size;   // lr / (1 - beta1^t)
+  float bc2_sqrt;    // sqrt(1 - beta2^t)
+  float ema_a;       // min(1 - 1/(ema_step+1), alpha)
+  float ema_b;       // (float)(1 - a), as python evaluates (1. - alpha) in double
+  int first_step;    // SGD: momentum buffer initialised with the gradient
+  int has_ema;
+};
+
+__global__ void __launch_bounds__(256) opt_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                      float* __restrict__ m, float* __restrict__ v,
+                                                      float* __restrict__ ema, long long n, OptScalars o) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * o.grad_scale;
+  float w = p[i];
+  if (o.kind == 0) {
+    if (o.wd != 0.f) grad = fmaf(o.wd, w, grad);
+    float mi = m[i], vi = v[i];
+    mi = mi + (grad - mi) * (1.f - o.beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * o.beta2 + (1.f - o.beta2) * grad * grad;  // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    float denom = sqrtf(vi) / o.bc2_sqrt + o.eps;
+    w = w - o.step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  } else {
+    if (o.wd != 0.f) grad = fmaf(o.wd, w, grad);
+    float buf = o.first_step ? grad : o.momentum * m[i] + grad;
+    m[i] = buf;
+    float upd = grad + o.momentum * buf;  // nesterov
+    w = w - o.lr * upd;
+  }
+  p[i] = w;
+  if (o.has_ema) ema[i] = __fadd_rn(__fmul_rn(ema[i], o.ema_a), __fmul_rn(w, o.ema_b));
+}
+
+int opt_ema_step(float* params, const float* grads, float* m, float* v, float* ema, long long n,
+                 const bsed_opt_cfg* cfg, cudaStream_t st) {
+  BSED_REQUIRE(cfg && (cfg->kind == 0 || cfg->kind == 1), "opt: bad cfg");
+  BSED_REQUIRE(cfg->step >= 1, "opt: step must be >= 1");
+  OptScalars o;
+  o.kind = cfg->kind;
+  o.lr = cfg->lr;
+  o.beta1 = cfg->beta1;
+  o.beta2 = cfg->beta2;
+  o.eps = cfg->eps;
+  o.wd = cfg->weight_decay;
+  o.momentum = cfg->momentum;
+  o.grad_scale = cfg->grad_scale;
+  double bc1 = 1.0 - pow((double)cfg->beta1, (double)cfg->step);
+  double bc2 = 1.0 - pow((double)cfg->beta2, (double)cfg->step);
+  o.step_size = (float)((double)cfg->lr / bc1);
+  o.bc2_sqrt = (float)sqrt(bc2);
+  double a = 1.0 - 1.0 / ((double)cfg->ema_step + 1.0);
+  if (a > (double)cfg->ema_alpha) a = (double)cfg->ema_alpha;
+  o.ema_a = (float)a;
+  o.ema_b = (float)(1.0 - a);
+  o.first_step = cfg->step == 1;
+  o.has_ema = ema != nullptr;
+  opt_ema_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, m, v, ema, n, o);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+__global__ void ema_buffers_kernel(const float* __restrict__ src, float* __restrict__ ema, long long n,
+                                   const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float a, float bcoef) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ema[i] = __fadd_rn(__fmul_rn(ema[i], a), __fmul_rn(src[i], bcoef));
+  if (i < n_nbt) {
+    float e = __fadd_rn(__fmul_rn((float)ema_nbt[i], a), __fmul_rn((float)nbt[i], bcoef));
+    ema_nbt[i] = (int64_t)e;  // load_state_dict copies the float back into the int64 buffer (truncation)
+  }
+}
+
+int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
+                int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st) {
+  double a = 1.0 - 1.0 / ((double)ema_step + 1.0);
+  if (a > (double)ema_alpha) a = (double)ema_alpha;
+  long long work = n > n_nbt ? n : n_nbt;
+  if (work <= 0) return BSED_OK;
+  ema_buffers_kernel<<<ceil_div(work, 256), 256, 0, st>>>(bn_buffers, ema_bn_buffers, n, nbt, ema_nbt,
+                                                          nbt && ema_nbt ? n_nbt : 0, (float)a, (float)(1.0 - a));
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+}  // namespace bsed

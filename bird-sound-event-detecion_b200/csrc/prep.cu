@@ -1,0 +1,69 @@
+// prep.cu -- one launch that turns the reference-layout parameters of one parameter set into the
+// operand layouts the kernels consume:
+//   conv  W[co][ci][tap]      -> Wp[tap][ci][co]   (forward implicit GEMM, B operand K-major)
+//                             -> Wd[tap][co][ci] = W[co][ci][8-tap]   (data gradient = conv with flipped taps)
+//   GLU   Wg[c'][c], BN g/b   -> WgT'[c][c'] = g[c] * Wg[c'][c],  b'[c'] = bg[c'] + sum_c Wg[c'][c] * b[c]
+//                                (lin = Wg (g*xhat + b) + bg  evaluated on xhat directly)
+//   GRU / Predictor matrices  -> transposed, concatenated copies
+#include "launch.h"
+
+namespace bsed {
+
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepTable table) {
+  const PrepOp& op = table.ops[blockIdx.x];
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x;
+  const int nth = gridDim.y * blockDim.x;
+  switch (op.type) {
+    case PREP_CONV_PACK: {
+      int Cout = op.d0, Cin = op.d1;
+      int n = Cout * Cin * 9;
+      for (int i = tid; i < n; i += nth) {  // i indexes dst [tap][ci][co]
+        int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
+        op.dst[i] = op.src[((size_t)co * Cin + ci) * 9 + tap];
+      }
+    } break;
+    case PREP_CONV_PACK_FLIP: {
+      int Cout = op.d0, Cin = op.d1;
+      int n = Cout * Cin * 9;
+      for (int i = tid; i < n; i += nth) {  // dst [tap][co][ci]
+        int ci = i % Cin, co = (i / Cin) % Cout, tap = i / (Cout * Cin);
+        op.dst[i] = op.src[((size_t)co * Cin + ci) * 9 + (8 - tap)];
+      }
+    } break;
+    case PREP_GLU_FOLD: {
+      int C = op.d0;
+      for (int i = tid; i < C * C; i += nth) {  // dst [c][c']
+        int cp = i % C, c = i / C;
+        op.dst[i] = op.aux0[c] * op.src[(size_t)cp * C + c];
+      }
+      for (int cp = tid; cp < C; cp += nth) {
+        float a = op.aux2[cp];
+        for (int c = 0; c < C; ++c) a = fmaf(op.src[(size_t)cp * C + c], op.aux1[c], a);
+        op.dst2[cp] = a;
+      }
+    } break;
+    case PREP_TRANSPOSE: {
+      int R = op.d0, Cc = op.d1, ldd = op.d2, off = op.d3;
+      for (int i = tid; i < R * Cc; i += nth) {  // src [r][c] -> dst[c*ldd + off + r]
+        int r = i % R, c = i / R;
+        op.dst[(size_t)c * ldd + off + r] = op.src[(size_t)r * Cc + c];
+      }
+    } break;
+    case PREP_COPY: {
+      for (int i = tid; i < op.d0; i += nth) op.dst[i] = op.src[i];
+    } break;
+    case PREP_ZERO: {
+      for (int i = tid; i < op.d0; i += nth) op.dst[i] = 0.f;
+    } break;
+  }
+}
+
+int run_prep(const PrepTable& table, cudaStream_t st) {
+  if (table.n == 0) return BSED_OK;
+  dim3 grid(table.n, 8);
+  prep_kernel<<<grid, 256, 0, st>>>(table);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+}  // namespace bsed

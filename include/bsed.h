@@ -1,0 +1,239 @@
+/*
+ * bsed.h -- C ABI of libbsed.so: the B200 (sm_100a) implementation of the sound-event-detection
+ * hot path of fumchin/bird-sound-event-detecion.
+ *
+ * The reference is 100% Python and has no FFI of its own; the boundary it offers is a set of Python
+ * call signatures.  Each entry point below names the reference interface it stands behind
+ * (file:line relative to the reference tree).  The Python package `bird-sound-event-detecion_b200`
+ * keeps those Python signatures and binds this library with ctypes.
+ *
+ * Conventions
+ *   - every function returns int: 0 = BSED_OK, negative = BSED_E_*; never throws, never exits.
+ *     `bsed_last_error()` gives a thread-local message for the last failure.
+ *   - all tensor arguments are DEVICE pointers to contiguous fp32 (unless stated), owned by the
+ *     caller; the library never allocates or frees caller-visible memory.  Scratch space is passed
+ *     in as `workspace` (size from the matching *_workspace_bytes call).
+ *   - all work is enqueued on the caller's stream (`void* stream` is a cudaStream_t); no hidden
+ *     synchronisation, no default-stream use => CUDA-graph capturable.
+ *   - activations inside the CRNN are channels-last (B, T, F, C); the public tensors
+ *     (B,1,T,128) input and (B,313,256)/(B,313,20)/(B,20) outputs are layout-identical to the
+ *     reference's.
+ *   - there is no CPU fallback: on a machine without a usable GPU every compute call fails with
+ *     BSED_E_CUDA.
+ */
+#ifndef BSED_H_
+#define BSED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSED_ABI_VERSION 1
+
+#define BSED_OK 0
+#define BSED_E_INVALID (-1) /* bad argument / shape / alignment */
+#define BSED_E_CUDA (-2)    /* CUDA runtime error (message has the detail) */
+#define BSED_E_WORKSPACE (-3) /* workspace too small */
+#define BSED_E_STATE (-4)   /* call order violation (e.g. backward without a saved forward) */
+
+typedef struct bsed_context* bsed_handle;
+
+int bsed_version(void);
+const char* bsed_last_error(void);
+
+/* One handle per (process, device).  Builds the constant tables (Hamming window, FFT twiddles,
+ * Slaney mel filterbank) on the device.  Constants follow src/data/config.py:47-57. */
+int bsed_create(int device, bsed_handle* out);
+int bsed_destroy(bsed_handle h);
+
+/* ------------------------------------------------------------------------------------------
+ * Frontend.
+ * ------------------------------------------------------------------------------------------ */
+
+/* 1 + n_samples / 255   (librosa.stft, center=True) */
+int bsed_frontend_n_frames(int n_samples);
+
+/* preprocess(audio, compute_log=False)            src/data/preprocess.py:18-45
+ * audio [B][n_samples] -> mel [B][n_frames][128] amplitude-mel (|STFT| x Slaney filterbank).
+ * n_samples >= 1025 (reflect padding). */
+int bsed_melspec(bsed_handle h, const float* audio, int B, int n_samples, float* mel, void* stream);
+
+/* get_transforms(frames, scaler, add_axis=0, noise_dict_params) applied to cached amplitude-mel:
+ *   [AugmentGaussianNoise(snr)] -> ApplyLog -> PadOrTrunc(frames) -> ToTensor -> [Normalize]
+ *                                                 src/data/Transforms.py:74-139,155-197,304-322
+ * mel [B][t_in][128]; unit_noise [B][t_in][128] standard-normal draws or NULL (no noise);
+ * scaler_mean / scaler_std [128] or NULL; out [B][frames][128] (rows >= t_in are 0, truncation if
+ * t_in > frames).  workspace: bsed_amp_to_db_workspace_bytes(B). */
+size_t bsed_amp_to_db_workspace_bytes(int B);
+int bsed_amp_to_db(bsed_handle h, const float* mel, const float* unit_noise, float snr_db, int B,
+                   int t_in, int frames, const float* scaler_mean, const float* scaler_std,
+                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-processing.         src/evaluation_measures.py:188-209, src/utilities/ManyHotEncoder.py:148-164
+ * strong [B][T][C] probabilities -> events, class-major then time, per clip.
+ *   b = p >= threshold ; median over `win` frames (scipy 'reflect') ; maximal runs [on, off).
+ * events [B][max_events][3] int32 (class, onset_frame, offset_frame); n_events [B] int32 (the true
+ * count; entries beyond max_events are dropped).  T <= 1024, C <= 32.
+ * ------------------------------------------------------------------------------------------ */
+int bsed_median_decode(bsed_handle h, const float* strong, int B, int T, int C, float threshold,
+                       int win, int32_t* events, int max_events, int32_t* n_events, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CRNN + Predictor engine.   src/models/CNN.py:33-84, RNN.py:7-16, CRNN.py:178-240,548-577
+ *
+ * Parameters live in ONE flat fp32 buffer in the reference's named_parameters() order
+ * (cnn.conv0.weight, cnn.conv0.bias, cnn.batchnorm0.weight, cnn.batchnorm0.bias,
+ *  cnn.glu0.linear.weight, cnn.glu0.linear.bias, ... x7, rnn.rnn.weight_ih_l0, weight_hh_l0,
+ *  bias_ih_l0, bias_hh_l0, *_reverse, *_l1, *_l1_reverse), each tensor in the reference's own shape.
+ * The Predictor has its own flat buffer (see bsed_predictor_*); hosts normally place it right after
+ * the CRNN parameters so one optimiser call covers both.
+ * BatchNorm buffers live in a second flat fp32 buffer (running_mean_i, running_var_i per block) and
+ * an int64 array num_batches_tracked[7].
+ * ------------------------------------------------------------------------------------------ */
+#define BSED_MAX_CNN_LAYERS 8
+
+typedef struct {
+  int n_frames;                        /* 1255 */
+  int n_mels;                          /* 128  */
+  int n_cnn;                           /* 7    */
+  int filters[BSED_MAX_CNN_LAYERS];    /* 16,32,64,128,128,128,128  (multiples of 16, <= 128) */
+  int pool_t[BSED_MAX_CNN_LAYERS];     /* 2,2,1,1,1,1,1 */
+  int pool_f[BSED_MAX_CNN_LAYERS];     /* 2,2,2,2,2,2,2 */
+  int rnn_hidden;                      /* 128 (fixed by the recurrence kernel) */
+  int rnn_layers;                      /* 2 */
+  int n_class;                         /* 20 (<= 20) */
+  float dropout;                       /* 0.5 */
+  float bn_eps;                        /* 1e-3 */
+  float bn_momentum;                   /* 0.99 */
+} bsed_crnn_cfg;
+
+typedef struct bsed_crnn_plan* bsed_plan;
+
+/* Build a plan for batches of up to max_clips clips. */
+int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max_clips, bsed_plan* out);
+int bsed_plan_destroy(bsed_plan p);
+
+int64_t bsed_plan_param_count(bsed_plan p);       /* floats in the flat parameter buffer  */
+int64_t bsed_plan_bn_buffer_count(bsed_plan p);   /* floats in the flat BN running-stat buffer */
+int bsed_plan_out_frames(bsed_plan p);            /* 313 */
+/* offsets (in floats) of the tensors of the flat parameter buffer, in order; returns the count.
+ * Lets the host verify its view of the layout. */
+int bsed_plan_param_offsets(bsed_plan p, int64_t* offsets, int max_n);
+size_t bsed_plan_workspace_bytes(bsed_plan p);
+
+/* A forward "group" is one reference model call: BatchNorm batch statistics (train mode) are taken
+ * over the clips of one group only; groups are processed together in the same launches.
+ * flags */
+#define BSED_F_TRAIN 1      /* BN batch statistics + running-stat update + dropout (model.train()) */
+#define BSED_F_SAVE 2       /* keep what backward needs (requires BSED_F_TRAIN)                     */
+
+typedef struct {
+  const float* params;        /* flat parameter buffer used by this group                          */
+  float* bn_buffers;          /* flat running stats (updated in train mode), may alias across groups */
+  int64_t* num_batches_tracked; /* [n_cnn] or NULL                                                  */
+  int first_clip, n_clips;    /* clips [first_clip, first_clip + n_clips) of x                     */
+} bsed_group;
+
+/* CRNN.forward for n_groups groups over x [B][n_frames][n_mels] (== (B,1,T,128)).
+ * enc [B][313][256] receives the encoder output after the final dropout (what CRNN.forward returns
+ * twice, as `x` and `d_input`).   src/models/CRNN.py:211-240
+ * dropout_seed/step key the stateless dropout hash (oracle/crnn.py: mix_key / keep_mask). */
+int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_groups, const float* x, int B,
+                      int flags, uint64_t dropout_seed, uint64_t dropout_step, float* enc,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the last BSED_F_SAVE forward for the groups whose bit is set in `group_mask`, all of
+ * which must be adjacent and share one parameter buffer.  d_enc [B][313][256]: gradient w.r.t. the
+ * encoder output (rows of unmasked clips are ignored).  grads: flat buffer, same layout as params;
+ * accumulate != 0 adds to it, else it is overwritten.  x of the forward must still be valid. */
+int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float* d_enc, float* grads,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Predictor.forward / backward                                   src/models/CRNN.py:548-577
+ * Parameters: flat fp32 buffer dense.weight [C][256], dense.bias [C], dense_softmax.weight [C][256],
+ * dense_softmax.bias [C].  enc [n][313][256]; logits [n][313][bsed_predictor_ldl()] is written by the
+ * forward and consumed by the backward (cols 0..C-1 dense, C..2C-1 dense_softmax pre-activations);
+ * strong [n][313][C], weak [n][C].  inference != 0: strong *= (weak > 0.5)   (CRNN.py:570-574).
+ * Backward: d_strong / d_weak may be NULL (= zero); writes d_enc [n][313][256] and the parameter
+ * gradients (same layout as the parameters). */
+int64_t bsed_predictor_param_count(bsed_plan p);
+int bsed_predictor_param_offsets(bsed_plan p, int64_t* offsets, int max_n);
+int bsed_predictor_ldl(void);
+int bsed_predictor_forward(bsed_plan p, const float* pred_params, const float* enc, int n_clips,
+                           int inference, float* logits, float* strong, float* weak, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int bsed_predictor_backward(bsed_plan p, const float* pred_params, const float* enc, const float* logits,
+                            const float* strong, const float* weak, const float* d_strong,
+                            const float* d_weak, int n_clips, float* d_enc, float* grads, int accumulate,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pointer to a named intermediate of the last forward/backward inside the workspace (debug and
+ * tests): "xhat<i>", "lin<i>", "pool<i>", "gru<l>", "dxn"  */
+int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* name, float** ptr,
+                           int64_t* numel);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses of the mean-teacher step.                      src/main.py:376,405,434,439-449,474-477
+ * Clips [syn_first, syn_first+syn_n) are the synthetic (strongly labelled) batch: BCE(strong, target)
+ * + BCE(weak, max_t target); clips [real_first, real_first+real_n) are the real batch: cons_w *
+ * (MSE(strong, strong_ema) + MSE(weak, weak_ema)), teacher tensors indexed from 0.
+ * Writes losses[4] = {strong_bce, weak_bce, cons_strong, cons_weak} (device), and the gradients
+ * d_strong / d_weak (same shapes as strong / weak, zero outside the two ranges).
+ * ------------------------------------------------------------------------------------------ */
+int bsed_mt_loss(bsed_handle h, const float* strong, const float* weak, int B, int T, int C,
+                 int syn_first, int syn_n, const float* syn_target, int real_first, int real_n,
+                 const float* strong_ema, const float* weak_ema, float cons_w, float* losses,
+                 float* d_strong, float* d_weak, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser + EMA in one pass over the flat buffers.
+ *   Adam   torch.optim.Adam(lr, betas=(.9,.999), eps=1e-8, weight_decay=0)   src/main.py:823-828
+ *   SGD    torch.optim.SGD(momentum=.9, weight_decay=1e-4, nesterov=True)
+ *                                                    src/main_scmt_ada_weak_seperate.py:858-870
+ *   EMA    ema = a*ema + (1-a)*param, a = min(1 - 1/(step+1), alpha)   src/main.py:86-100
+ * grad is multiplied by grad_scale first (1/world_size after a sum all-reduce).
+ * ema may be NULL (no teacher).  `step` is the 1-based optimiser step (Adam bias correction);
+ * `ema_step` is the global_step passed to update_ema_variables.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int kind;            /* 0 = Adam, 1 = SGD-Nesterov */
+  float lr, beta1, beta2, eps, weight_decay, momentum;
+  float grad_scale;
+  float ema_alpha;     /* 0.999 */
+  int64_t step;
+  int64_t ema_step;
+} bsed_opt_cfg;
+
+int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m, float* v,
+                      float* ema, int64_t n, const bsed_opt_cfg* cfg, void* stream);
+
+/* State-dict flavour of update_ema_variables for the non-parameter entries: BN running stats
+ * (fp32) and num_batches_tracked (int64, blended in fp32 and truncated, as load_state_dict does). */
+int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffers, int64_t n,
+                     const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float ema_alpha,
+                     int64_t ema_step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic kernels exported for unit tests (row-major fp32).
+ *   gemm_nn: C[M][N] (ldc) = A[M][K] (lda) * Bm[K][N] (ldb) (+ bias[N]) (+ C if accumulate)
+ *            K % 16 == 0, N % 16 == 0
+ *   gemm_tn: C[M][N] += sum_k A[k][M] * Bm[k][N]   (C must be initialised; split-K atomics)
+ *            M % 16 == 0, N % 16 == 0
+ *   conv3x3: channels-last 3x3 / stride 1 / pad 1, weight in the reference's (Cout,Cin,3,3) layout,
+ *            y [B][T][F][Cout]; wpack scratch of 9*Cin*Cout floats.
+ * ------------------------------------------------------------------------------------------ */
+int bsed_gemm_nn(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc,
+                 int M, int N, int K, const float* bias, int accumulate, void* stream);
+int bsed_gemm_tn(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc,
+                 int M, int N, int K, void* stream);
+int bsed_conv3x3(bsed_handle h, const float* x, const float* weight, const float* bias, float* y,
+                 int B, int T, int F, int Cin, int Cout, float* wpack, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSED_H_ */
