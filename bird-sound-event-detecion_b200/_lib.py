@@ -1,0 +1,142 @@
+"""ctypes binding of libbsed.so (the C ABI declared in include/bsed.h).
+
+There is no fallback: if the shared library is missing, or no B200 is usable, calls raise.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsed.so")
+
+BSED_F_TRAIN = 1
+BSED_F_SAVE = 2
+MAX_CNN_LAYERS = 8
+
+# every symbol include/bsed.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = [
+    "bsed_version", "bsed_last_error", "bsed_create", "bsed_destroy", "bsed_frontend_n_frames",
+    "bsed_melspec", "bsed_amp_to_db_workspace_bytes", "bsed_amp_to_db", "bsed_median_decode",
+    "bsed_plan_create", "bsed_plan_destroy", "bsed_plan_param_count", "bsed_plan_bn_buffer_count",
+    "bsed_plan_out_frames", "bsed_plan_param_offsets", "bsed_plan_workspace_bytes", "bsed_crnn_forward",
+    "bsed_crnn_backward", "bsed_predictor_param_count", "bsed_predictor_param_offsets",
+    "bsed_predictor_ldl", "bsed_predictor_workspace_bytes", "bsed_predictor_forward", "bsed_predictor_backward",
+    "bsed_plan_debug_tensor", "bsed_mt_loss", "bsed_opt_ema_step", "bsed_ema_buffers", "bsed_gemm_nn",
+    "bsed_gemm_tn", "bsed_conv3x3",
+]
+
+
+class CrnnCfg(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("n_mels", C.c_int), ("n_cnn", C.c_int),
+                ("filters", C.c_int * MAX_CNN_LAYERS), ("pool_t", C.c_int * MAX_CNN_LAYERS),
+                ("pool_f", C.c_int * MAX_CNN_LAYERS), ("rnn_hidden", C.c_int), ("rnn_layers", C.c_int),
+                ("n_class", C.c_int), ("dropout", C.c_float), ("bn_eps", C.c_float),
+                ("bn_momentum", C.c_float)]
+
+
+class Group(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("bn_buffers", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("first_clip", C.c_int), ("n_clips", C.c_int)]
+
+
+class OptCfg(C.Structure):
+    _fields_ = [("kind", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("momentum", C.c_float),
+                ("grad_scale", C.c_float), ("ema_alpha", C.c_float), ("step", C.c_int64),
+                ("ema_step", C.c_int64)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen libbsed.so and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32, u32, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_uint64, C.c_size_t
+        P = C.POINTER
+
+        def proto(name, res, *args):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = list(args)
+
+        proto("bsed_version", i32)
+        proto("bsed_last_error", C.c_char_p)
+        proto("bsed_create", i32, i32, P(vp))
+        proto("bsed_destroy", i32, vp)
+        proto("bsed_frontend_n_frames", i32, i32)
+        proto("bsed_melspec", i32, vp, vp, i32, i32, vp, vp)
+        proto("bsed_amp_to_db_workspace_bytes", sz, i32)
+        proto("bsed_amp_to_db", i32, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, sz, vp)
+        proto("bsed_median_decode", i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp, vp)
+        proto("bsed_plan_create", i32, vp, P(CrnnCfg), i32, P(vp))
+        proto("bsed_plan_destroy", i32, vp)
+        proto("bsed_plan_param_count", i64, vp)
+        proto("bsed_plan_bn_buffer_count", i64, vp)
+        proto("bsed_plan_out_frames", i32, vp)
+        proto("bsed_plan_param_offsets", i32, vp, P(i64), i32)
+        proto("bsed_plan_workspace_bytes", sz, vp)
+        proto("bsed_crnn_forward", i32, vp, P(Group), i32, vp, i32, i32, u64, u64, vp, vp, sz, vp)
+        proto("bsed_crnn_backward", i32, vp, u32, vp, vp, i32, vp, sz, vp)
+        proto("bsed_predictor_param_count", i64, vp)
+        proto("bsed_predictor_param_offsets", i32, vp, P(i64), i32)
+        proto("bsed_predictor_ldl", i32)
+        proto("bsed_predictor_workspace_bytes", sz, vp, i32)
+        proto("bsed_predictor_forward", i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, sz, vp)
+        proto("bsed_predictor_backward", i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, sz, vp)
+        proto("bsed_plan_debug_tensor", i32, vp, vp, C.c_char_p, P(vp), P(i64))
+        proto("bsed_mt_loss", i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, f32, vp, vp, vp, vp)
+        proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
+        proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
+        proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)
+        proto("bsed_gemm_tn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp)
+        proto("bsed_conv3x3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+        _lib = lib
+    return _lib
+
+
+class BsedError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().bsed_last_error()
+        raise BsedError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+_handles = {}
+
+
+def handle(device_index):
+    """One library context per (process, device)."""
+    lib = load()
+    if device_index not in _handles:
+        h = C.c_void_p()
+        check(lib.bsed_create(int(device_index), C.byref(h)), "bsed_create")
+        _handles[device_index] = h
+    return _handles[device_index]
+
+
+def ptr(t):
+    """Device pointer of a contiguous torch tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libbsed takes contiguous tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -54,10 +54,9 @@ struct bsed_crnn_plan {
   size_t off_packed[2];
   size_t off_xhat[BSED_MAX_CNN_LAYERS], off_lin[BSED_MAX_CNN_LAYERS], off_pool[BSED_MAX_CNN_LAYERS];
   size_t off_stats, off_stats2, off_meanrstd;
-  size_t off_packed_pred;
   size_t off_xg, off_gru_out[4], off_gru_saved[4], off_enc;
-  size_t off_dxn, off_dpool[2], off_dlogits, off_denc, off_dx1, off_dxg, off_dgh;
-  size_t off_G, off_dscratch, off_tmpw;
+  size_t off_dxn, off_dpool[2], off_denc, off_dx1, off_dxg, off_dgh;
+  size_t off_G, off_dscratch;
   size_t ws_bytes;
   // state of the last forward
   bool saved_valid;
@@ -200,7 +199,6 @@ void carve_workspace(bsed_crnn_plan* p) {
     return r;
   };
   for (int s = 0; s < 2; ++s) p->off_packed[s] = takeb(sizeof(float) * p->pk.total);
-  p->off_packed_pred = takeb(sizeof(float) * p->pk.pred_total);
   long long max_full = 0, max_pool = 0;
   for (int i = 0; i < c.n_cnn; ++i) {
     const LayerGeom& g = p->L[i];
@@ -224,14 +222,12 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_dxn = takeb(sizeof(float) * max_full);
   p->off_dpool[0] = takeb(sizeof(float) * max_pool);
   p->off_dpool[1] = takeb(sizeof(float) * max_pool);
-  p->off_dlogits = takeb(sizeof(float) * BT * kLdl);
   p->off_denc = takeb(sizeof(float) * BT * 256);
   p->off_dx1 = takeb(sizeof(float) * BT * 256);
   p->off_dxg = takeb(sizeof(float) * BT * 768);
   p->off_dgh = takeb(sizeof(float) * BT * 768);
   p->off_G = takeb(sizeof(float) * 128 * 128);
   p->off_dscratch = takeb(sizeof(double) * 2 * 768);
-  p->off_tmpw = takeb(sizeof(float) * kLdl * 256);
   p->ws_bytes = o;
 }
 
@@ -728,17 +724,43 @@ extern "C" int bsed_predictor_param_offsets(bsed_plan p, int64_t* offsets, int m
 }
 extern "C" int bsed_predictor_ldl(void) { return kLdl; }
 
+namespace {
+struct PredWs {
+  size_t packed, dlog, tmpw, dscr, total;
+};
+PredWs pred_ws(const bsed_crnn_plan* p, int n_clips) {
+  PredWs w;
+  size_t o = 0;
+  auto takeb = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes);
+    return r;
+  };
+  w.packed = takeb(sizeof(float) * p->pk.pred_total);
+  w.dlog = takeb(sizeof(float) * (size_t)n_clips * p->Tout * kLdl);
+  w.tmpw = takeb(sizeof(float) * kLdl * 256);
+  w.dscr = takeb(sizeof(double) * 2 * kLdl);
+  w.total = o;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t bsed_predictor_workspace_bytes(bsed_plan p, int n_clips) {
+  return p && n_clips > 0 ? pred_ws(p, n_clips).total : 0;
+}
+
 extern "C" int bsed_predictor_forward(bsed_plan p, const float* pred_params, const float* enc, int n_clips,
                                       int inference, float* logits, float* strong, float* weak, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   BSED_REQUIRE(p && pred_params && enc && logits && strong && weak && workspace, "predictor_forward: null argument");
   BSED_REQUIRE(n_clips >= 1, "predictor_forward: n_clips=%d", n_clips);
-  if (workspace_bytes < p->ws_bytes) {
-    bsed_set_error("predictor_forward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+  PredWs w = pred_ws(p, n_clips);
+  if (workspace_bytes < w.total) {
+    bsed_set_error("predictor_forward: workspace %zu < %zu", workspace_bytes, w.total);
     return BSED_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  float* packed = wsp<float>(workspace, p->off_packed_pred);
+  float* packed = wsp<float>(workspace, w.packed);
   PrepTable tb;
   build_prep_table_head(p, pred_params, packed, &tb);
   BSED_TRY(run_prep(tb, st));
@@ -754,20 +776,21 @@ extern "C" int bsed_predictor_backward(bsed_plan p, const float* pred_params, co
                                        void* workspace, size_t workspace_bytes, void* stream) {
   BSED_REQUIRE(p && pred_params && enc && logits && strong && weak && d_enc && grads && workspace,
                "predictor_backward: null argument");
-  if (workspace_bytes < p->ws_bytes) {
-    bsed_set_error("predictor_backward: workspace %zu < %zu", workspace_bytes, p->ws_bytes);
+  BSED_REQUIRE(n_clips >= 1, "predictor_backward: n_clips=%d", n_clips);
+  PredWs w = pred_ws(p, n_clips);
+  if (workspace_bytes < w.total) {
+    bsed_set_error("predictor_backward: workspace %zu < %zu", workspace_bytes, w.total);
     return BSED_E_WORKSPACE;
   }
-  BSED_REQUIRE(n_clips >= 1 && n_clips <= p->max_clips, "predictor_backward: n_clips=%d", n_clips);
   cudaStream_t st = as_stream(stream);
   const ParamLayout& pl = p->pl;
   const int T = p->Tout, C = p->cfg.n_class;
   const long long BTn = (long long)n_clips * T;
   const int sms = p->ctx->num_sms;
-  float* packed = wsp<float>(workspace, p->off_packed_pred);
-  float* dlog = wsp<float>(workspace, p->off_dlogits);
-  float* tmpw = wsp<float>(workspace, p->off_tmpw);
-  double* dscr = wsp<double>(workspace, p->off_dscratch);
+  float* packed = wsp<float>(workspace, w.packed);
+  float* dlog = wsp<float>(workspace, w.dlog);
+  float* tmpw = wsp<float>(workspace, w.tmpw);
+  double* dscr = wsp<double>(workspace, w.dscr);
   PrepTable tb;
   build_prep_table_head(p, pred_params, packed, &tb);
   BSED_TRY(run_prep(tb, st));

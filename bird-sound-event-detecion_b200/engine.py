@@ -1,0 +1,267 @@
+"""Thin Python layer over the C ABI: plans, workspaces and the flat-buffer call wrappers.
+
+PyTorch is used here for device memory and streams only; all arithmetic happens inside libbsed.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BSED_F_SAVE, BSED_F_TRAIN, CrnnCfg, Group, OptCfg, check, ptr, stream_ptr
+
+# crnn_kwargs of the reference (src/main.py:632-641)
+REFERENCE_CRNN_KWARGS = dict(
+    n_in_channel=1, nclass=20, attention=True, n_RNN_cell=128, n_layers_RNN=2, activation="glu",
+    dropout=0.5, kernel_size=7 * [3], padding=7 * [1], stride=7 * [1],
+    nb_filters=[16, 32, 64, 128, 128, 128, 128],
+    pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]])
+REFERENCE_PREDICTOR_KWARGS = dict(nclass=20, attention=True, n_RNN_cell=128)
+
+
+def make_cfg(nclass=20, dropout=0.5, nb_filters=(16, 32, 64, 128, 128, 128, 128),
+             pooling=((2, 2), (2, 2), (1, 2), (1, 2), (1, 2), (1, 2), (1, 2)), n_RNN_cell=128,
+             n_layers_RNN=2, n_frames=1255, n_mels=128, bn_eps=1e-3, bn_momentum=0.99):
+    cfg = CrnnCfg()
+    cfg.n_frames, cfg.n_mels, cfg.n_cnn = int(n_frames), int(n_mels), len(nb_filters)
+    for i, (c, p) in enumerate(zip(nb_filters, pooling)):
+        cfg.filters[i] = int(c)
+        cfg.pool_t[i] = int(p[0])
+        cfg.pool_f[i] = int(p[1])
+    cfg.rnn_hidden, cfg.rnn_layers, cfg.n_class = int(n_RNN_cell), int(n_layers_RNN), int(nclass)
+    cfg.dropout, cfg.bn_eps, cfg.bn_momentum = float(dropout), float(bn_eps), float(bn_momentum)
+    return cfg
+
+
+def _dev_index(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("bird-sound-event-detecion_b200 runs on a CUDA device only (no CPU fallback)")
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+class Plan:
+    """bsed_plan + its workspace.  One saved forward at a time (see models/CRNN.py for the slot pool).
+    `with_workspace=False` builds a plan that only serves the Predictor calls."""
+
+    def __init__(self, cfg, max_clips, device, with_workspace=True):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", _dev_index(device))
+        self.h = _lib.handle(self.device.index)
+        self.cfg = cfg
+        self.max_clips = int(max_clips)
+        self.p = C.c_void_p()
+        check(self.lib.bsed_plan_create(self.h, C.byref(cfg), self.max_clips, C.byref(self.p)), "bsed_plan_create")
+        self.n_params = int(self.lib.bsed_plan_param_count(self.p))
+        self.n_pred_params = int(self.lib.bsed_predictor_param_count(self.p))
+        self.n_bn = int(self.lib.bsed_plan_bn_buffer_count(self.p))
+        self.t_out = int(self.lib.bsed_plan_out_frames(self.p))
+        self.ldl = int(self.lib.bsed_predictor_ldl())
+        self.n_class = int(cfg.n_class)
+        self.n_cnn = int(cfg.n_cnn)
+        self.ws_bytes = int(self.lib.bsed_plan_workspace_bytes(self.p))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device) if with_workspace else None
+        self._pred_ws = {}
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self.p:
+                self.lib.bsed_plan_destroy(self.p)
+                self.p = None
+        except Exception:
+            pass
+
+    def param_offsets(self):
+        buf = (C.c_int64 * 256)()
+        n = self.lib.bsed_plan_param_offsets(self.p, buf, 256)
+        return [int(buf[i]) for i in range(n)]
+
+    def predictor_offsets(self):
+        buf = (C.c_int64 * 16)()
+        n = self.lib.bsed_predictor_param_offsets(self.p, buf, 16)
+        return [int(buf[i]) for i in range(n)]
+
+    # groups: list of dicts(params=flat fp32, bn=flat fp32, nbt=int64[n_cnn] or None, n=int)
+    def forward(self, groups, x, train, save, seed=0, step=0, enc=None):
+        B = sum(g["n"] for g in groups)
+        x = x.reshape(B, self.cfg.n_frames, self.cfg.n_mels)
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
+        arr = (Group * len(groups))()
+        first = 0
+        for i, g in enumerate(groups):
+            assert g["params"].numel() >= self.n_params and g["bn"].numel() == self.n_bn
+            arr[i].params = g["params"].data_ptr()
+            arr[i].bn_buffers = g["bn"].data_ptr()
+            arr[i].num_batches_tracked = g["nbt"].data_ptr() if g.get("nbt") is not None else None
+            arr[i].first_clip = first
+            arr[i].n_clips = g["n"]
+            first += g["n"]
+        if enc is None:
+            enc = torch.empty(B, self.t_out, 256, dtype=torch.float32, device=self.device)
+        flags = (BSED_F_TRAIN if train else 0) | (BSED_F_SAVE if save else 0)
+        check(self.lib.bsed_crnn_forward(self.p, arr, len(groups), ptr(x), B, flags, int(seed), int(step), ptr(enc),
+                                         ptr(self.ws), self.ws_bytes, stream_ptr()), "bsed_crnn_forward")
+        self._keep = (x, [g["params"] for g in groups]) if save else None   # backward reads them again
+        return enc
+
+    def backward(self, group_mask, d_enc, grads, accumulate=False):
+        assert d_enc.is_contiguous() and d_enc.dtype == torch.float32
+        check(self.lib.bsed_crnn_backward(self.p, int(group_mask), ptr(d_enc), ptr(grads), int(bool(accumulate)),
+                                          ptr(self.ws), self.ws_bytes, stream_ptr()), "bsed_crnn_backward")
+        self._keep = None
+
+    def _pws(self, n):
+        if n not in self._pred_ws:
+            nb = int(self.lib.bsed_predictor_workspace_bytes(self.p, n))
+            self._pred_ws[n] = (torch.empty(nb, dtype=torch.uint8, device=self.device), nb)
+        return self._pred_ws[n]
+
+    def predictor_forward(self, pred_params, enc, inference=False):
+        n = enc.shape[0]
+        ws, wsb = self._pws(n)
+        enc = enc.contiguous()
+        logits = torch.empty(n, self.t_out, self.ldl, dtype=torch.float32, device=self.device)
+        strong = torch.empty(n, self.t_out, self.n_class, dtype=torch.float32, device=self.device)
+        weak = torch.empty(n, self.n_class, dtype=torch.float32, device=self.device)
+        check(self.lib.bsed_predictor_forward(self.p, ptr(pred_params), ptr(enc), n, int(bool(inference)), ptr(logits),
+                                              ptr(strong), ptr(weak), ptr(ws), wsb, stream_ptr()),
+              "bsed_predictor_forward")
+        return logits, strong, weak
+
+    def predictor_backward(self, pred_params, enc, logits, strong, weak, d_strong, d_weak, grads, accumulate=False,
+                           d_enc=None):
+        n = enc.shape[0]
+        ws, wsb = self._pws(n)
+        if d_enc is None:
+            d_enc = torch.empty(n, self.t_out, 256, dtype=torch.float32, device=self.device)
+        check(self.lib.bsed_predictor_backward(self.p, ptr(pred_params), ptr(enc), ptr(logits), ptr(strong), ptr(weak),
+                                               ptr(d_strong), ptr(d_weak), n, ptr(d_enc), ptr(grads),
+                                               int(bool(accumulate)), ptr(ws), wsb, stream_ptr()),
+              "bsed_predictor_backward")
+        return d_enc
+
+    def debug_tensor(self, name):
+        p = C.c_void_p()
+        n = C.c_int64()
+        check(self.lib.bsed_plan_debug_tensor(self.p, ptr(self.ws), name.encode(), C.byref(p), C.byref(n)),
+              "bsed_plan_debug_tensor")
+        off = p.value - self.ws.data_ptr()
+        return self.ws[off:off + 4 * n.value].view(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# stateless wrappers
+# ------------------------------------------------------------------------------------------------
+def mt_loss(strong, weak, syn_first, syn_n, syn_target, real_first, real_n, strong_ema, weak_ema, cons_w):
+    """Losses of the mean-teacher step + gradients w.r.t. strong / weak (src/main.py:376-477)."""
+    lib = _lib.load()
+    h = _lib.handle(strong.device.index)
+    B, T, Cn = strong.shape
+    losses = torch.empty(4, dtype=torch.float32, device=strong.device)
+    d_strong = torch.empty_like(strong)
+    d_weak = torch.empty_like(weak)
+    check(lib.bsed_mt_loss(h, ptr(strong), ptr(weak), B, T, Cn, syn_first, syn_n, ptr(syn_target), real_first, real_n,
+                           ptr(strong_ema), ptr(weak_ema), float(cons_w), ptr(losses), ptr(d_strong), ptr(d_weak),
+                           stream_ptr()), "bsed_mt_loss")
+    return losses, d_strong, d_weak
+
+
+def opt_ema_step(params, grads, m, v, ema, step, ema_step=None, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, momentum=0.9, grad_scale=1.0, ema_alpha=0.999):
+    lib = _lib.load()
+    h = _lib.handle(params.device.index)
+    cfg = OptCfg()
+    cfg.kind = 0 if kind == "adam" else 1
+    cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+    cfg.weight_decay, cfg.momentum, cfg.grad_scale, cfg.ema_alpha = float(weight_decay), float(momentum), float(grad_scale), float(ema_alpha)
+    cfg.step = int(step)
+    cfg.ema_step = int(ema_step if ema_step is not None else step)
+    check(lib.bsed_opt_ema_step(h, ptr(params), ptr(grads), ptr(m), ptr(v), ptr(ema), params.numel(), C.byref(cfg),
+                                stream_ptr()), "bsed_opt_ema_step")
+
+
+def ema_buffers(bn, ema_bn, nbt, ema_nbt, ema_step, ema_alpha=0.999):
+    lib = _lib.load()
+    h = _lib.handle(bn.device.index)
+    n_nbt = nbt.numel() if nbt is not None and ema_nbt is not None else 0
+    check(lib.bsed_ema_buffers(h, ptr(bn), ptr(ema_bn), bn.numel(), ptr(nbt), ptr(ema_nbt), n_nbt, float(ema_alpha),
+                               int(ema_step), stream_ptr()), "bsed_ema_buffers")
+
+
+def melspec(audio):
+    """audio (B, n) fp32 cuda -> (B, 1 + n // 255, 128) amplitude-mel."""
+    lib = _lib.load()
+    h = _lib.handle(audio.device.index)
+    audio = audio.contiguous()
+    B, n = audio.shape
+    nf = lib.bsed_frontend_n_frames(n)
+    mel = torch.empty(B, nf, 128, dtype=torch.float32, device=audio.device)
+    check(lib.bsed_melspec(h, ptr(audio), B, n, ptr(mel), stream_ptr()), "bsed_melspec")
+    return mel
+
+
+def amp_to_db(mel, frames, unit_noise=None, snr=30.0, scaler_mean=None, scaler_std=None, out=None):
+    """(B, t_in, 128) amplitude-mel -> (B, frames, 128) log-mel (ApplyLog -> PadOrTrunc -> [Normalize])."""
+    lib = _lib.load()
+    h = _lib.handle(mel.device.index)
+    mel = mel.contiguous()
+    B, t_in, _ = mel.shape
+    if out is None:
+        out = torch.empty(B, frames, 128, dtype=torch.float32, device=mel.device)
+    wsb = int(lib.bsed_amp_to_db_workspace_bytes(B))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=mel.device)
+    check(lib.bsed_amp_to_db(h, ptr(mel), ptr(unit_noise), float(snr), B, t_in, int(frames), ptr(scaler_mean),
+                             ptr(scaler_std), ptr(out), ptr(ws), wsb, stream_ptr()), "bsed_amp_to_db")
+    return out
+
+
+def median_decode(strong, threshold=0.5, win=14, max_events=None):
+    """strong (B, T, C) -> (events int32 (B, max_events, 3), n_events int32 (B,))."""
+    lib = _lib.load()
+    h = _lib.handle(strong.device.index)
+    strong = strong.contiguous()
+    B, T, Cn = strong.shape
+    if max_events is None:
+        max_events = Cn * ((T + 1) // 2)
+    events = torch.zeros(B, max_events, 3, dtype=torch.int32, device=strong.device)
+    n_events = torch.zeros(B, dtype=torch.int32, device=strong.device)
+    check(lib.bsed_median_decode(h, ptr(strong), B, T, Cn, float(threshold), int(win), ptr(events), int(max_events),
+                                 ptr(n_events), stream_ptr()), "bsed_median_decode")
+    return events, n_events
+
+
+def gemm_nn(a, b, bias=None, out=None, accumulate=False):
+    lib = _lib.load()
+    h = _lib.handle(a.device.index)
+    M, K = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    check(lib.bsed_gemm_nn(h, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
+                           int(bool(accumulate)), stream_ptr()), "bsed_gemm_nn")
+    return out
+
+
+def gemm_tn(a, b, out):
+    """out[M][N] += a[K][M]^T @ b[K][N]"""
+    lib = _lib.load()
+    h = _lib.handle(a.device.index)
+    K, M = a.shape
+    N = b.shape[1]
+    check(lib.bsed_gemm_tn(h, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, stream_ptr()),
+          "bsed_gemm_tn")
+    return out
+
+
+def conv3x3(x, weight, bias=None):
+    """channels-last x (B, T, F, Cin), weight (Cout, Cin, 3, 3) -> (B, T, F, Cout)."""
+    lib = _lib.load()
+    h = _lib.handle(x.device.index)
+    B, T, F, Cin = x.shape
+    Cout = weight.shape[0]
+    y = torch.empty(B, T, F, Cout, dtype=torch.float32, device=x.device)
+    wpack = torch.empty(9 * Cin * Cout, dtype=torch.float32, device=x.device)
+    check(lib.bsed_conv3x3(h, ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(y), B, T, F, Cin, Cout,
+                           ptr(wpack), stream_ptr()), "bsed_conv3x3")
+    return y

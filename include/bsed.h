@@ -159,10 +159,11 @@ int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float* d_enc, flo
  * forward and consumed by the backward (cols 0..C-1 dense, C..2C-1 dense_softmax pre-activations);
  * strong [n][313][C], weak [n][C].  inference != 0: strong *= (weak > 0.5)   (CRNN.py:570-574).
  * Backward: d_strong / d_weak may be NULL (= zero); writes d_enc [n][313][256] and the parameter
- * gradients (same layout as the parameters). */
+ * gradients (same layout as the parameters).  workspace: bsed_predictor_workspace_bytes(p, n). */
 int64_t bsed_predictor_param_count(bsed_plan p);
 int bsed_predictor_param_offsets(bsed_plan p, int64_t* offsets, int max_n);
 int bsed_predictor_ldl(void);
+size_t bsed_predictor_workspace_bytes(bsed_plan p, int n_clips);
 int bsed_predictor_forward(bsed_plan p, const float* pred_params, const float* enc, int n_clips,
                            int inference, float* logits, float* strong, float* weak, void* workspace,
                            size_t workspace_bytes, void* stream);

@@ -110,7 +110,9 @@ def mt_step(model, predictor, ema_model, ema_predictor, optimizer, x, x_ema, xs,
     optimizer.step()
 
     gs = global_step + 1
-    if ema_flavour == "state_dict":
+    if ema_flavour == "none":
+        pass
+    elif ema_flavour == "state_dict":
         update_ema_state_dict(model, ema_model, 0.999, gs)
         update_ema_state_dict(predictor, ema_predictor, 0.999, gs)
     else:

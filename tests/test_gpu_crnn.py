@@ -1,0 +1,199 @@
+"""CRNN + Predictor through the C ABI against the reference fixtures (tests/golden, produced by the
+reference's own modules) and against the torch-CPU oracle on the same seeded inputs.
+Tolerance (north_star): strong / weak probabilities within 1e-3 in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bsed_models, golden, max_abs, oracle_models, rel_l2
+from bsed_b200.utilities import synth
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3
+
+
+def _nhwc(t):   # oracle NCHW -> our channels-last
+    return t.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def test_eval_forward_matches_reference_fixture():
+    g = golden("crnn_eval.npz")
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=11))
+    oc, op = oracle_models(seed=5, linear_std=0.2)
+    m, p = bsed_models(oc, op, dropout=0.5)
+    m.eval(); p.eval()
+    with torch.no_grad():
+        enc, d_in = m(x.cuda())
+        strong, weak = p(enc)
+    assert enc.shape == (2, 313, 256) and d_in is enc
+    assert max_abs(enc.cpu().numpy()[:, ::8], g["enc"]) < 1e-3
+    assert max_abs(strong.cpu().numpy(), g["strong"]) < PROB_TOL
+    assert max_abs(weak.cpu().numpy(), g["weak"]) < PROB_TOL
+    # fp32 SIMT path is much tighter than the north-star tolerance
+    assert max_abs(strong.cpu().numpy(), g["strong"]) < 5e-5
+
+
+def test_eval_forward_layer_by_layer():
+    """Localises a mismatch: every pooled CNN output and both GRU layers against the oracle."""
+    from bsed_b200 import engine
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=12))
+    oc, op = oracle_models(seed=7, linear_std=0.2)
+    m, p = bsed_models(oc, op)
+    flat, bn, nbt = m.flat_tensors()
+    plan = engine.Plan(engine.make_cfg(**m.cfg_kwargs), max_clips=2, device="cuda")
+    enc = plan.forward([dict(params=flat, bn=bn, nbt=nbt, n=2)], x.cuda(), train=False, save=False)
+    torch.cuda.synchronize()
+    h = x
+    with torch.no_grad():
+        for i in range(7):
+            for name in (f"conv{i}", f"batchnorm{i}", f"glu{i}", f"dropout{i}", f"pooling{i}"):
+                h = getattr(oc.cnn, name)(h)
+            got = plan.debug_tensor(f"pool{i}").cpu().numpy().reshape(_nhwc(h).shape)
+            assert rel_l2(got, _nhwc(h)) < 2e-5, f"block {i}"
+        seq = h.squeeze(-1).permute(0, 2, 1)
+        ref_out, _ = oc.rnn.rnn(seq)
+        # layer 0 output alone: run a 1-layer GRU with layer-0 weights
+        g0 = torch.nn.GRU(128, 128, bidirectional=True, batch_first=True, num_layers=1)
+        sd = {k: v for k, v in oc.rnn.rnn.state_dict().items() if "_l0" in k}
+        g0.load_state_dict(sd)
+        ref_l0, _ = g0(seq)
+    got0 = plan.debug_tensor("gru0").cpu().numpy().reshape(2, 313, 256)
+    got1 = plan.debug_tensor("gru1").cpu().numpy().reshape(2, 313, 256)
+    assert max_abs(got0, ref_l0.numpy()) < 5e-5
+    assert max_abs(got1, ref_out.numpy()) < 5e-5
+    assert max_abs(enc.cpu().numpy(), ref_out.numpy()) < 5e-5
+
+
+def test_train_forward_with_dropout_matches_reference_fixture():
+    g = golden("crnn_train_fwd.npz")
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=11))
+    oc, op = oracle_models(seed=5, linear_std=0.2)
+    m, p = bsed_models(oc, op, dropout=0.5)
+    from bsed_b200 import engine
+    flat, bn, nbt = m.flat_tensors()
+    plan = engine.Plan(engine.make_cfg(**m.cfg_kwargs), max_clips=2, device="cuda")
+    enc = plan.forward([dict(params=flat, bn=bn, nbt=nbt, n=2)], x.cuda(), train=True, save=False, seed=2023, step=3)
+    _, strong, weak = plan.predictor_forward(p.flat_tensors()[0], enc)
+    torch.cuda.synchronize()
+    assert max_abs(strong.cpu().numpy(), g["strong"]) < PROB_TOL
+    assert max_abs(weak.cpu().numpy(), g["weak"]) < PROB_TOL
+    assert max_abs(strong.cpu().numpy(), g["strong"]) < 1e-4
+    sd = m.state_dict()
+    assert max_abs(sd["cnn.batchnorm0.running_mean"].cpu().numpy(), g["rm0"]) < 1e-4
+    assert rel_l2(sd["cnn.batchnorm0.running_var"].cpu().numpy(), g["rv0"]) < 1e-4
+    assert rel_l2(sd["cnn.batchnorm6.running_var"].cpu().numpy(), g["rv6"]) < 1e-4
+    assert int(sd["cnn.batchnorm3.num_batches_tracked"]) == int(g["nbt"]) == 1
+
+
+def test_groups_keep_batchnorm_statistics_separate():
+    """Two groups in one launch == two separate reference calls (per-call batch statistics)."""
+    from bsed_b200 import engine
+    xa = torch.from_numpy(synth.make_logmel_like(2, seed=31))
+    xb = torch.from_numpy(synth.make_logmel_like(1, seed=32)) * 0.5 - 10
+    oc, op = oracle_models(seed=8, linear_std=0.2, train=True)
+    m, p = bsed_models(oc, op)
+    flat, bn, nbt = m.flat_tensors()
+    plan = engine.Plan(engine.make_cfg(**m.cfg_kwargs), max_clips=3, device="cuda")
+    g = [dict(params=flat, bn=bn, nbt=nbt, n=2), dict(params=flat, bn=bn, nbt=nbt, n=1)]
+    enc = plan.forward(g, torch.cat([xa, xb]).cuda(), train=True, save=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ea, _ = oc(xa)
+        eb, _ = oc(xb)
+    assert max_abs(enc[:2].cpu().numpy(), ea.numpy()) < 1e-4
+    assert max_abs(enc[2:].cpu().numpy(), eb.numpy()) < 1e-4
+    sd, osd = m.state_dict(), oc.state_dict()
+    for k in ("cnn.batchnorm0.running_mean", "cnn.batchnorm4.running_var"):
+        assert rel_l2(sd[k].cpu().numpy(), osd[k].numpy()) < 1e-4, k       # updated twice, in call order
+    assert int(sd["cnn.batchnorm2.num_batches_tracked"]) == 2
+
+
+def _oracle_grads(oc, op, x, p_drop, seed=None, step=None):
+    oc.train(); op.train()
+    if p_drop:
+        oc.set_dropout_keys(seed, step, 0)
+    enc, _ = oc(x)
+    strong, weak = op(enc)
+    rng = np.random.default_rng(77)
+    ws = torch.from_numpy(rng.standard_normal(tuple(strong.shape))).float()
+    ww = torch.from_numpy(rng.standard_normal(tuple(weak.shape))).float()
+    loss = (strong * ws).sum() + (weak * ww).sum()
+    loss.backward()
+    return ws, ww, strong.detach(), weak.detach()
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.5])
+def test_backward_matches_oracle_autograd(p_drop):
+    """Gradients of every parameter tensor, through the module / autograd API of models/CRNN.py."""
+    from bsed_b200.models import CRNN as crnn_mod
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=41))
+    oc, op = oracle_models(seed=9, linear_std=0.2, dropout=p_drop)
+    m, p = bsed_models(oc, op, dropout=p_drop)
+    m.train(); p.train()
+    crnn_mod.set_dropout_seed(2023, step=10)            # next forward uses step 11
+    ws, ww, o_strong, o_weak = _oracle_grads(oc, op, x, p_drop, seed=2023, step=11)
+    enc, _ = m(x.cuda())
+    strong, weak = p(enc)
+    assert max_abs(strong.detach().cpu().numpy(), o_strong.numpy()) < 1e-4
+    loss = (strong * ws.cuda()).sum() + (weak * ww.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    bad = []
+    ogr = dict(oc.named_parameters())
+    for name, prm in m.named_parameters():
+        ref = ogr[name].grad.numpy()
+        got = prm.grad.cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-3)
+        if name.endswith(".bias") and ".conv" in name:
+            ok = np.abs(got - ref).max() < 1e-3          # ~0 by construction (BatchNorm follows); rounding noise
+        else:
+            ok = np.abs(got - ref).max() / scale < 2e-3 and rel_l2(got, ref) < 2e-3
+        if not ok:
+            bad.append((name, float(np.abs(got - ref).max()), float(scale), rel_l2(got, ref)))
+    for name, prm in p.named_parameters():
+        ref = dict(op.named_parameters())[name].grad.numpy()
+        if rel_l2(prm.grad.cpu().numpy(), ref) > 1e-3:
+            bad.append((name, rel_l2(prm.grad.cpu().numpy(), ref)))
+    assert not bad, bad
+
+
+def test_inference_flag_gates_strong():
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=51))
+    oc, op = oracle_models(seed=10, linear_std=0.5)
+    m, p = bsed_models(oc, op)
+    m.eval(); p.eval()
+    with torch.no_grad():
+        enc, _ = m(x.cuda())
+        s1, w1 = p(enc, inference=True)
+        e2, _ = oc(x)
+        s2, w2 = op(e2, inference=True)
+    # gate decisions can flip only where weak is within rounding of 0.5
+    near = (np.abs(w2.numpy() - 0.5) < 1e-4)
+    diff = np.abs(s1.cpu().numpy() - s2.numpy()).max(axis=1)
+    assert (diff[~near] < 1e-4).all()
+
+
+def test_get_predictions_reference_entry_point():
+    from bsed_b200 import evaluation_measures as em
+    from bsed_b200.data import config as cfg
+    from bsed_b200.utilities.ManyHotEncoder import ManyHotEncoder
+    from oracle import postproc as opp
+    x = torch.from_numpy(synth.make_logmel_like(3, seed=61))
+    oc, op = oracle_models(seed=11, linear_std=0.6)
+    m, p = bsed_models(oc, op)
+    m.eval(); p.eval()
+    enc = ManyHotEncoder(cfg.bird_list, n_frames=313)
+    loader = [(((x[:2], x[:2]), torch.zeros(2, 313, 20)), ["/d/preprocess/a.npy", "/d/preprocess/b.npy"]),
+              (((x[2:], x[2:]), torch.zeros(1, 313, 20)), ["/d/preprocess/c.npy"])]
+    pred, gt, dur = em.get_predictions(m, loader, enc.decode_strong, 4, median_window=14, predictor=p)
+    with torch.no_grad():
+        s, _ = op(oc(x)[0])
+    rows = []
+    for b, name in enumerate("abc"):
+        for c, on, off in opp.to_seconds(opp.events_from_strong(s[b].numpy())):
+            rows.append((cfg.bird_list[c], on, off, name))
+    assert len(pred) == len(rows) and list(dur["filename"]) == ["a", "b", "c"] and gt is None
+    for (lab, on, off, fn), r in zip(rows, pred.itertuples(index=False)):
+        assert (lab, fn) == (r.event_label, r.filename)
+        assert abs(on - r.onset) < 1e-9 and abs(off - r.offset) < 1e-9

@@ -1,0 +1,122 @@
+"""Mean-teacher step through the fused trainer and through the generic module path, against the
+fixtures produced by the reference's modules (tests/golden/mt_step_*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bsed_models, golden, max_abs, oracle_models, rel_l2
+from bsed_b200.utilities import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs():
+    xs = torch.from_numpy(synth.make_logmel_like(2, seed=21))
+    xr = torch.from_numpy(synth.make_logmel_like(2, seed=22))
+    xr_ema = xr + 0.5 * torch.from_numpy(synth.make_logmel_like(2, seed=23)) * 0.1
+    ts = torch.from_numpy(synth.make_targets(2, seed=24))
+    return xs, xr, xr_ema, ts
+
+
+def _models(p_drop):
+    oc, op = oracle_models(seed=5, linear_std=0.2)
+    tc, tp = oracle_models(seed=6, linear_std=0.2)
+    m, p = bsed_models(oc, op, dropout=p_drop)
+    em, ep = bsed_models(tc, tp, dropout=p_drop)
+    for mod in (m, p, em, ep):
+        mod.train()
+    for prm in list(em.parameters()) + list(ep.parameters()):
+        prm.detach_()
+    return m, p, em, ep
+
+
+def _check_against_fixture(g, m, p, em, ep, losses, grads_flat=None, n_crnn=None):
+    for it in range(2):
+        lv = losses[it]
+        ref = [float(g[f"strong_class{it}"]), float(g[f"weak_class{it}"]), float(g[f"cons_strong{it}"]),
+               float(g[f"cons_weak{it}"])]
+        for a, b in zip(lv, ref):
+            assert a == pytest.approx(b, rel=3e-3, abs=2e-6), (it, lv, ref)
+        assert sum(lv) == pytest.approx(float(g[f"loss{it}"]), rel=1e-3)
+    ssd, tsd = m.state_dict(), em.state_dict()
+    for k in ("cnn.conv0.weight", "cnn.conv3.bias", "cnn.batchnorm2.weight", "cnn.glu4.linear.weight",
+              "rnn.rnn.weight_hh_l0", "rnn.rnn.bias_ih_l1_reverse", "cnn.batchnorm1.running_var",
+              "cnn.batchnorm5.running_mean"):
+        s_ref, t_ref = g["s_" + k], g["t_" + k]
+        s_got = ssd[k].cpu().numpy().reshape(-1)[:2048]
+        t_got = tsd[k].cpu().numpy().reshape(-1)[:2048]
+        # Adam's first steps move every weight by ~lr regardless of gradient size: compare to 10% of 2 steps of lr
+        tol_s = 1e-4 if "conv3.bias" not in k else 1.1e-3
+        assert max_abs(s_got, s_ref) < tol_s, (k, max_abs(s_got, s_ref))
+        assert max_abs(t_got, t_ref) < 1e-4, (k, max_abs(t_got, t_ref))
+    assert int(tsd["cnn.batchnorm0.num_batches_tracked"]) == int(g["t_nbt"])
+    assert int(ssd["cnn.batchnorm0.num_batches_tracked"]) == int(g["s_nbt"]) == 4
+    assert max_abs(p.dense.weight.detach().cpu().numpy().reshape(-1), g["s_dense_w"]) < 1e-4
+    assert max_abs(ep.dense.weight.detach().cpu().numpy().reshape(-1), g["t_dense_w"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,p_drop", [("mt_step_nodrop.npz", 0.0), ("mt_step_drop.npz", 0.5)])
+def test_fused_trainer_matches_reference_fixture(name, p_drop):
+    from bsed_b200.main import MeanTeacherTrainer
+    g = golden(name)
+    m, p, em, ep = _models(p_drop)
+    xs, xr, xr_ema, ts = [t.cuda() for t in _inputs()]
+    tr = MeanTeacherTrainer(m, p, em, ep, lr=5e-4, n_syn=2, n_real=2, dropout_seed=2023)
+    losses = []
+    for it in range(2):
+        l = tr.step(xr, xr_ema, xs, ts, global_step=100 + it, rampup_length=500)
+        losses.append([float(v) for v in l.cpu()])
+        if it == 0:
+            # gradients of the first step, tensor by tensor
+            o = 0
+            bad = []
+            for (mod, pname, shape), (fullname, _) in zip(m._param_specs + p._param_specs,
+                                                          list(m.named_parameters()) + list(p.named_parameters())):
+                k = int(np.prod(shape))
+                got = tr.grads[o:o + k].cpu().numpy()
+                o += k
+                key = ("g_crnn." + fullname.replace("cnn.", "cnn.cnn.", 1)) if o <= tr.n_crnn else "g_pred." + fullname
+                ref = g[key]
+                gs = got if got.size <= 4096 else got[:: max(1, got.size // 4096)][:4096]
+                gn = float(g[key.replace("g_", "gn_", 1)])
+                if gn < 1e-4:
+                    continue                                  # conv biases: rounding noise only
+                if rel_l2(gs, ref) > 3e-3:
+                    bad.append((fullname, rel_l2(gs, ref)))
+            assert not bad, bad
+            assert max_abs(tr.last["strong"][2:].cpu().numpy(), g["strong0"]) < 1e-3
+    _check_against_fixture(g, m, p, em, ep, losses)
+
+
+def test_generic_module_path_matches_reference_fixture():
+    """Reference statement order (teacher fwd, student fwd x2, loss, backward, torch Adam, EMA) on the
+    autograd wrappers, with a stock torch.optim.Adam."""
+    from bsed_b200 import main as bmain
+    from bsed_b200.models import CRNN as crnn_mod
+    g = golden("mt_step_nodrop.npz")
+    m, p, em, ep = _models(0.0)
+    xs, xr, xr_ema, ts = [t.cuda() for t in _inputs()]
+    opt = torch.optim.Adam(list(m.parameters()) + list(p.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    crnn_mod.set_dropout_seed(2023)
+    losses = []
+    for it in range(2):
+        gstep = 100 + it
+        from bsed_b200.utilities import ramps
+        l = bmain._generic_step(m, p, em, ep, opt, (xr, xr_ema, None), (xs, None, ts), gstep,
+                                ramps.exp_rampup(gstep, 500))
+        losses.append([float(v) for v in l.cpu()])
+    _check_against_fixture(g, m, p, em, ep, losses)
+
+
+def test_train_mt_entry_point_runs_an_epoch():
+    from bsed_b200 import main as bmain
+    m, p, em, ep = _models(0.5)
+    xs, xr, xr_ema, ts = _inputs()
+    real = [(((xr, xr_ema), torch.zeros(2, 313, 20)), ["r0", "r1"])] * 2
+    syn = [(((xs, xs), ts), ["s0", "s1"])]
+    opt = bmain.FusedAdam(list(m.parameters()) + list(p.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    before = m._flat.clone()
+    loss = bmain.train_mt(real, syn, m, opt, 0, ema_model=em, ema_predictor=ep, predictor=p)
+    assert torch.isfinite(loss) and float(loss) > 0
+    assert not torch.equal(before, m.flat_tensors()[0])
+    assert int(m.cnn.batchnorm0.num_batches_tracked) == 4 and int(em.cnn.batchnorm0.num_batches_tracked) >= 1
