@@ -300,9 +300,10 @@ void build_prep_table_head(const bsed_crnn_plan* p, const float* params, float* 
     op.d2 = d2;
     op.d3 = d3;
   };
-  add(PREP_ZERO, nullptr, packed + pk.wcatT, 256 * kLdl, 0, 0, 0);
-  add(PREP_ZERO, nullptr, packed + pk.bcat, kLdl, 0, 0, 0);
-  add(PREP_ZERO, nullptr, packed + pk.wcat, kLdl * 256, 0, 0, 0);
+  // zero only the padding (cols/rows 2C..47): the ops of one table run concurrently
+  add(PREP_ZERO_COLS, nullptr, packed + pk.wcatT, 256, kLdl, 2 * C, kLdl - 2 * C);
+  add(PREP_ZERO, nullptr, packed + pk.bcat + 2 * C, kLdl - 2 * C, 0, 0, 0);
+  add(PREP_ZERO, nullptr, packed + pk.wcat + (long long)2 * C * 256, (kLdl - 2 * C) * 256, 0, 0, 0);
   // dense.weight [C][256] -> wcatT [256][48] cols 0..C-1 ; dense_softmax -> cols C..2C-1
   add(PREP_TRANSPOSE, params + pl.dense_w, packed + pk.wcatT, C, 256, kLdl, 0);
   add(PREP_TRANSPOSE, params + pl.sm_w, packed + pk.wcatT, C, 256, kLdl, C);
@@ -703,6 +704,19 @@ extern "C" int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* 
     *numel = Bm * p->Tout * 256;
     return BSED_OK;
   }
+  struct Tap { const char* n; size_t off; long long numel; } taps[] = {
+      {"denc", p->off_denc, Bm * p->Tout * 256}, {"dx1", p->off_dx1, Bm * p->Tout * 256},
+      {"dxg", p->off_dxg, Bm * p->Tout * 768},   {"dgh", p->off_dgh, Bm * p->Tout * 768},
+      {"xg", p->off_xg, Bm * p->Tout * 768},     {"enc", p->off_enc, Bm * p->Tout * 256},
+      {"dpool0", p->off_dpool[0], Bm * p->L[0].prows * p->L[0].Cout},
+      {"dpool1", p->off_dpool[1], Bm * p->L[0].prows * p->L[0].Cout},
+      {"saved0", p->off_gru_saved[0], Bm * p->Tout * 1024}, {"saved1", p->off_gru_saved[1], Bm * p->Tout * 1024}};
+  for (const Tap& t : taps)
+    if (s == t.n) {
+      *ptr = wsp<float>(workspace, t.off);
+      *numel = t.numel;
+      return BSED_OK;
+    }
   if (s == "dxn") {
     *ptr = wsp<float>(workspace, p->off_dxn);
     *numel = Bm * p->L[0].rows * p->L[0].Cout;

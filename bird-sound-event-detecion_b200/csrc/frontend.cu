@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) median_decode_kernel(const float* __restr
 int median_decode(const float* strong, int B, int T, int C, float threshold, int win, int32_t* events,
                   int max_events, int32_t* n_events, cudaStream_t st) {
   BSED_REQUIRE(T > 0 && T <= PP_MAXT && C > 0 && C <= PP_MAXC, "median_decode: T=%d C=%d (max 1024 x 32)", T, C);
-  BSED_REQUIRE(win >= 1 && win <= 2 * T, "median_decode: win=%d", win);
+  BSED_REQUIRE(win >= 1 && win <= 65536, "median_decode: win=%d", win);
   BSED_REQUIRE(B > 0 && max_events >= 0, "median_decode: B=%d", B);
   static bool configured = false;
   size_t smem = 2 * PP_MAXC * PP_MAXT;

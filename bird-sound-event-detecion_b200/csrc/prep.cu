@@ -5,6 +5,7 @@
 //   GLU   Wg[c'][c], BN g/b   -> WgT'[c][c'] = g[c] * Wg[c'][c],  b'[c'] = bg[c'] + sum_c Wg[c'][c] * b[c]
 //                                (lin = Wg (g*xhat + b) + bg  evaluated on xhat directly)
 //   GRU / Predictor matrices  -> transposed, concatenated copies
+// All ops of a table run concurrently in one launch: no two ops may write the same element.
 #include "launch.h"
 
 namespace bsed {
@@ -54,6 +55,10 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
     } break;
     case PREP_ZERO: {
       for (int i = tid; i < op.d0; i += nth) op.dst[i] = 0.f;
+    } break;
+    case PREP_ZERO_COLS: {  // dst[r * ld + col0 + c] = 0 for r < rows, c < ncols
+      int rows = op.d0, ld = op.d1, col0 = op.d2, nc = op.d3;
+      for (int i = tid; i < rows * nc; i += nth) op.dst[(size_t)(i / nc) * ld + col0 + i % nc] = 0.f;
     } break;
   }
 }

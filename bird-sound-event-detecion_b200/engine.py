@@ -231,6 +231,12 @@ def median_decode(strong, threshold=0.5, win=14, max_events=None):
     return events, n_events
 
 
+def _rows(t):
+    """Pointer of a 2-D fp32 tensor whose rows are contiguous (row stride = leading dimension)."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    return C.c_void_p(t.data_ptr())
+
+
 def gemm_nn(a, b, bias=None, out=None, accumulate=False):
     lib = _lib.load()
     h = _lib.handle(a.device.index)
@@ -238,7 +244,7 @@ def gemm_nn(a, b, bias=None, out=None, accumulate=False):
     N = b.shape[1]
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
-    check(lib.bsed_gemm_nn(h, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
+    check(lib.bsed_gemm_nn(h, _rows(a), a.stride(0), _rows(b), b.stride(0), _rows(out), out.stride(0), M, N, K, ptr(bias),
                            int(bool(accumulate)), stream_ptr()), "bsed_gemm_nn")
     return out
 
@@ -249,7 +255,8 @@ def gemm_tn(a, b, out):
     h = _lib.handle(a.device.index)
     K, M = a.shape
     N = b.shape[1]
-    check(lib.bsed_gemm_tn(h, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, stream_ptr()),
+    check(lib.bsed_gemm_tn(h, _rows(a), a.stride(0), _rows(b), b.stride(0), _rows(out), out.stride(0), M, N, K,
+                           stream_ptr()),
           "bsed_gemm_tn")
     return out
 

@@ -129,11 +129,10 @@ class _FlatModule(nn.Module):
 
 class _CRNNFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, seed, step, *params):
+    def forward(ctx, module, x, seed, step, need_grad, *params):
         flat, bn, nbt = module.flat_tensors()
         B = x.shape[0]
         train = module.training
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         slot = module._acquire_slot(B, save=train and need_grad)
         xin = x.detach().contiguous().float()
         enc = slot.forward([dict(params=flat, bn=bn, nbt=nbt, n=B)], xin, train=train, save=train and need_grad,
@@ -158,7 +157,7 @@ class _CRNNFunction(torch.autograd.Function):
             k = math.prod(shape)
             out.append(grads[o:o + k].view(shape))
             o += k
-        return (None, None, None, None, *out)
+        return (None, None, None, None, None, *out)
 
 
 class CRNN(_FlatModule):
@@ -258,7 +257,9 @@ class CRNN(_FlatModule):
         if not self._flat.is_cuda:
             raise RuntimeError("move the model to the GPU first (model.cuda())")
         seed, step = _next_dropout_step() if self.training else (0, 0)
-        enc = _CRNNFunction.apply(self, x, seed, step, *self.param_list())
+        params = self.param_list()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # grad mode is off inside Function.forward
+        enc = _CRNNFunction.apply(self, x, seed, step, need_grad, *params)
         return enc, enc
 
 

@@ -1,1 +1,1 @@
-from .CRNN import CRNN, Predictor  # noqa: F401
+from .CRNN import CRNN, Predictor, set_dropout_seed  # noqa: F401
