@@ -18,6 +18,75 @@ void bsed_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch counter and per-class event timing (bench.py: gpu_launches, roofline.achieved)
+// ---------------------------------------------------------------------------------------------
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+void bsed_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfState {
+  int cls = PROF_NONE;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  double flops = 0, bytes = 0;
+  int launches = 0;
+  bool open = false;
+} g_prof;
+}  // namespace
+
+void bsed_prof_begin(int cls, double flops, double bytes, cudaStream_t st) {
+  if (cls != g_prof.cls || g_prof.cls == PROF_NONE) return;
+  if (g_prof.used + 2 > g_prof.ev.size()) {
+    size_t old = g_prof.ev.size();
+    g_prof.ev.resize(old + 512);
+    for (size_t i = old; i < g_prof.ev.size(); ++i) cudaEventCreate(&g_prof.ev[i]);
+  }
+  cudaEventRecord(g_prof.ev[g_prof.used], st);
+  g_prof.flops += flops;
+  g_prof.bytes += bytes;
+  g_prof.launches += 1;
+  g_prof.open = true;
+}
+void bsed_prof_end(int cls, cudaStream_t st) {
+  if (cls != g_prof.cls || !g_prof.open) return;
+  cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+  g_prof.used += 2;
+  g_prof.open = false;
+}
+
+extern "C" uint64_t bsed_launch_count(void) { return g_launches.load(); }
+
+extern "C" int bsed_profile_begin(int kernel_class) {
+  g_prof.cls = kernel_class;
+  g_prof.used = 0;
+  g_prof.flops = g_prof.bytes = 0;
+  g_prof.launches = 0;
+  g_prof.open = false;
+  return BSED_OK;
+}
+
+extern "C" int bsed_profile_end(double* total_ms, double* total_flops, double* total_bytes, int* n_launches) {
+  double ms = 0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[i + 1]);
+    if (e != cudaSuccess) {
+      bsed_set_error("profile_end: %s", cudaGetErrorString(e));
+      return BSED_E_CUDA;
+    }
+    float t = 0;
+    cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = g_prof.flops;
+  if (total_bytes) *total_bytes = g_prof.bytes;
+  if (n_launches) *n_launches = g_prof.launches;
+  g_prof.cls = PROF_NONE;
+  return BSED_OK;
+}
+
 extern "C" int bsed_version(void) { return BSED_ABI_VERSION; }
 extern "C" const char* bsed_last_error(void) { return g_err; }
 

@@ -11,6 +11,19 @@
 // error plumbing (thread-local message, no exceptions across the ABI)
 // ----------------------------------------------------------------------------------------------
 void bsed_set_error(const char* fmt, ...);
+void bsed_count_launch();  // every kernel launch of this library passes through BSED_CHECK_LAUNCH
+
+// optional per-class device timing (CUDA events on the launching stream), see api.cu
+enum { PROF_NONE = 0, PROF_CONV = 1, PROF_WGRAD = 2, PROF_GEMM = 3, PROF_GEMM_TN = 4, PROF_MELSPEC = 5, PROF_GRU = 6,
+       PROF_ELEMENTWISE = 7 };
+void bsed_prof_begin(int cls, double flops, double bytes, cudaStream_t st);
+void bsed_prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  ProfScope(int c, double flops, double bytes, cudaStream_t s) : cls(c), st(s) { bsed_prof_begin(c, flops, bytes, s); }
+  ~ProfScope() { bsed_prof_end(cls, st); }
+};
 
 #define BSED_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \
@@ -23,6 +36,7 @@ void bsed_set_error(const char* fmt, ...);
 
 #define BSED_CHECK_LAUNCH()                                                                    \
   do {                                                                                         \
+    bsed_count_launch();                                                                       \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) {                                                                   \
       bsed_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

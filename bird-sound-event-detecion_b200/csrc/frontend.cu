@@ -213,6 +213,8 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
   int n_frames = 1 + n_samples / kHop;
   FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_w, h->mel_start, h->mel_len, h->mel_off, h->mel_nnz};
   dim3 grid(ceil_div(n_frames, FE_FPC), B);
+  // algorithmic bytes: audio in + mel out; flops: rFFT-2048 + magnitude + sparse mel
+  ProfScope prof(PROF_MELSPEC, (double)B * n_frames * 70000.0, 4.0 * B * ((double)n_samples + (double)n_frames * kNMels), st);
   melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, mel, tb);
   BSED_CHECK_LAUNCH();
   return BSED_OK;

@@ -38,6 +38,7 @@ int gemm_nn(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc
   BSED_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, "gemm_nn: leading dims must be multiples of 4");
   PlainRows a{A, lda, M};
   NNEpilogue epi{C, ldc, bias, accumulate};
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
   return launch_nn(a, Bm, ldb, M, N, K, epi, st);
 }
 
@@ -48,6 +49,7 @@ int conv3x3_nn(const float* X, const float* Wp, float* Y, int B, int T, int F, i
   BSED_REQUIRE(M < (1ll << 31), "conv3x3: too many pixels");
   ConvRows a{X, T, F, Cin, (int)M, Cin / GEMM_BK};
   NNEpilogue epi{Y, Cout, bias, accumulate};
+  ProfScope prof(PROF_CONV, 2.0 * M * Cout * 9.0 * Cin, 4.0 * ((double)M * Cin + (double)M * Cout + 9.0 * Cin * Cout), st);
   return launch_nn(a, Wp, Cout, (int)M, Cout, 9 * Cin, epi, st);
 }
 
@@ -88,6 +90,7 @@ static int launch_tn(ALoad a, BLoad b, float* C, long long rs, long long cs, int
 int gemm_tn(const float* A, int lda, const float* Bm, int ldb, float* C, long long rs, long long cs, int M,
             int N, long long K, int target_ctas, cudaStream_t st) {
   PlainK a{A, lda}, b{Bm, ldb};
+  ProfScope prof(PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * M + (double)K * N + (double)M * N), st);
   return launch_tn(a, b, C, rs, cs, M, N, K, target_ctas, st);
 }
 
@@ -95,6 +98,7 @@ int gemm_tn(const float* A, int lda, const float* Bm, int ldb, float* C, long lo
 int conv3x3_wgrad(const float* X, const float* dY, float* dW, int B, int T, int F, int Cin, int Cout,
                   int target_ctas, cudaStream_t st) {
   long long K = (long long)B * T * F;
+  ProfScope prof(PROF_WGRAD, 2.0 * K * Cout * 9.0 * Cin, 4.0 * ((double)K * Cin + (double)K * Cout + 9.0 * Cin * Cout), st);
   for (int tap = 0; tap < 9; ++tap) {
     PlainK a{dY, Cout};
     ShiftedPixelK b{X, T, F, Cin, tap / 3 - 1, tap % 3 - 1};

@@ -102,6 +102,7 @@ int gru_forward(const float* xg, const Groups& g, const FloatPtrs& whhT, const F
   int B = 0;
   for (int i = 0; i < g.n; ++i) B += g.count[i];
   dim3 grid(B, 2);
+  ProfScope prof(PROF_GRU, 2.0 * B * 2 * T * kG * kH, 4.0 * B * T * (2.0 * kG + 2 * kH), st);
   gru_fwd_kernel<<<grid, kG, 0, st>>>(xg, g, whhT, bhh, out, enc, saved, T, key, thresh, inv_keep);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
 int gru_backward(const float* dout, const float* saved, const float* out, const float* whh, float* dxg,
                  float* dgh, int T, int first_clip, int n_clips, cudaStream_t st) {
   dim3 grid(n_clips, 2);
+  ProfScope prof(PROF_GRU, 2.0 * n_clips * 2 * T * kG * kH, 4.0 * n_clips * T * (4.0 * kG + 8 * kH), st);
   gru_bwd_kernel<<<grid, kG, 0, st>>>(dout, saved, out, whh, dxg, dgh, T, first_clip);
   BSED_CHECK_LAUNCH();
   return BSED_OK;

@@ -219,6 +219,18 @@ int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffe
                      int64_t ema_step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py).
+ *   bsed_launch_count: kernels this library has launched in this process.
+ *   bsed_profile_begin(cls) .. bsed_profile_end: CUDA-event time, summed over the launches of one
+ *   kernel class on their launching stream, with the algorithmic flops / bytes of those launches.
+ *   classes: 1 implicit-GEMM conv (fwd + dgrad), 2 conv weight gradient, 3 plain GEMM, 4 split-K
+ *   reduction GEMM, 5 log-mel frontend (STFT+mel), 6 GRU recurrence.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bsed_launch_count(void);
+int bsed_profile_begin(int kernel_class);
+int bsed_profile_end(double* total_ms, double* total_flops, double* total_bytes, int* n_launches);
+
+/* ------------------------------------------------------------------------------------------
  * Generic kernels exported for unit tests (row-major fp32).
  *   gemm_nn: C[M][N] (ldc) = A[M][K] (lda) * Bm[K][N] (ldb) (+ bias[N]) (+ C if accumulate)
  *            K % 16 == 0, N % 16 == 0
