@@ -293,3 +293,25 @@ extern "C" int bsed_conv3x3(bsed_handle h, const float* x, const float* weight, 
   BSED_TRY(run_prep(tb, as_stream(stream)));
   return conv3x3_nn(x, wpack, y, B, T, F, Cin, Cout, bias, 0, as_stream(stream));
 }
+
+// tensor-core variants of the unit-test entry points (kind::tf32, so ~1e-3 relative to fp32)
+extern "C" int bsed_conv3x3_tc(bsed_handle h, const float* x, const float* weight, const float* bias, float* y, int B,
+                               int T, int F, int Cin, int Cout, float* wpack, void* stream) {
+  BSED_REQUIRE(h && x && weight && y && wpack, "bsed_conv3x3_tc: null argument");
+  PrepTable tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.n = 1;
+  tb.ops[0].type = PREP_CONV_KMAJOR;
+  tb.ops[0].src = weight;
+  tb.ops[0].dst = wpack;
+  tb.ops[0].d0 = Cout;
+  tb.ops[0].d1 = Cin;
+  BSED_TRY(run_prep(tb, as_stream(stream)));
+  return tc_conv3x3(x, wpack, y, B, T, F, Cin, Cout, bias, 0, h->num_sms, as_stream(stream));
+}
+
+extern "C" int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
+                               int M, int N, int K, const float* bias, int accumulate, void* stream) {
+  BSED_REQUIRE(h && A && Bk && C, "bsed_gemm_nt_tc: null argument");
+  return tc_gemm_nt(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, h->num_sms, as_stream(stream));
+}

@@ -80,7 +80,7 @@ struct PrepOp {
   float* dst;
   float* dst2;
 };
-enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6 };
+enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8 };
 constexpr int kMaxPrepOps = 56;
 struct PrepTable {
   int n;
@@ -114,6 +114,12 @@ int opt_ema_step(float* params, const float* grads, float* m, float* v, float* e
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
                 int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st);
 int add_f32(float* dst, const float* src, long long n, cudaStream_t st);
+
+// ---- tc_gemm.cu (tcgen05 / TMA)
+int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+               int accumulate, int sms, cudaStream_t st);
+int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
+               const float* bias, int accumulate, int sms, cudaStream_t st);
 
 // ---- frontend.cu
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st);

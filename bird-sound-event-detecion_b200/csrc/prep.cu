@@ -31,6 +31,22 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
         op.dst[i] = op.src[((size_t)co * Cin + ci) * 9 + (8 - tap)];
       }
     } break;
+    case PREP_CONV_KMAJOR: {  // dst [co][tap][ci]  (tensor-core forward: B operand [N = co][K = tap*Cin + ci])
+      int Cout = op.d0, Cin = op.d1;
+      int n = Cout * Cin * 9;
+      for (int i = tid; i < n; i += nth) {
+        int ci = i % Cin, tap = (i / Cin) % 9, co = i / (Cin * 9);
+        op.dst[i] = op.src[((size_t)co * Cin + ci) * 9 + tap];
+      }
+    } break;
+    case PREP_CONV_KMAJOR_FLIP: {  // dst [ci][tap][co] = W[co][ci][8-tap]  (data gradient: N = ci, K = tap*Cout + co)
+      int Cout = op.d0, Cin = op.d1;
+      int n = Cout * Cin * 9;
+      for (int i = tid; i < n; i += nth) {
+        int co = i % Cout, tap = (i / Cout) % 9, ci = i / (Cout * 9);
+        op.dst[i] = op.src[((size_t)co * Cin + ci) * 9 + (8 - tap)];
+      }
+    } break;
     case PREP_GLU_FOLD: {
       int C = op.d0;
       for (int i = tid; i < C * C; i += nth) {  // dst [c][c']

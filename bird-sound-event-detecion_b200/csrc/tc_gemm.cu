@@ -1,0 +1,482 @@
+// tc_gemm.cu -- tcgen05 (5th-gen tensor core) GEMM family for sm_100a, operands fed by TMA.
+//
+//   D[128 x N] (fp32, TMEM) += A[128 x 8] * B[8 x N]      tcgen05.mma.cta_group::1.kind::tf32
+//
+// K-major kernel (tc_kmajor_kernel): implicit-GEMM 3x3 convolution forward / data gradient over
+// channels-last activations, and plain row-major GEMMs (GLU linears).  One M-tile is 128 output
+// pixels forming a th x tw rectangle of one clip; the A operand of tap (dt, df), channels
+// [c, c+KCH) is ONE TMA box load of the 4-D activation tensor (C, F, T, B) at coordinates
+// (c, df, t0 + dt, b): the box lands in shared memory as [128 pixels][KCH floats], i.e. exactly the
+// K-major SWIZZLE_128B (KCH = 32) / SWIZZLE_64B (KCH = 16) operand tile the MMA wants, and the
+// zero padding of the convolution is the TMA's out-of-bounds fill.  B is the [N][K] K-major packed
+// weight matrix (2-D box).  Persistent CTAs, warp-specialised:
+//   warp 0    TMA producer (one elected lane), STAGES-deep mbarrier ring
+//   warp 1    TMEM allocation + MMA issue (one elected lane), double-buffered accumulators
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> + bias -> global fp32
+#include <cuda.h>
+
+#include "launch.h"
+
+namespace bsed {
+namespace tc {
+
+constexpr int kBM = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 26;   // bounded mbarrier waits: trap instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, void* dst, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, swizzled rows of ROWB bytes (128 or 64):
+//   start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 8 rows | version 1 | layout type
+template <int ROWB>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
+  constexpr uint64_t sbo = (8 * ROWB) >> 4;
+  constexpr uint64_t layout = ROWB == 128 ? 2 : 4;   // SWIZZLE_128B : SWIZZLE_64B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct KArgs {
+  int plain;           // 0: conv (4-D activation map), 1: plain GEMM (2-D row map)
+  int n_tiles, tiles_per_clip, th;
+  int T, F;            // conv geometry (tw == F)
+  long long rows;      // plain: number of rows
+  int ntaps, cpt;      // taps (9 or 1), k-chunks per tap
+  int ldc;
+  int accumulate;
+};
+
+template <int N, int KCH, int STAGES>
+struct KSmem {
+  static constexpr int A_BYTES = kBM * KCH * 4;
+  static constexpr int B_BYTES = N * KCH * 4;
+  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE = A_BYTES + B_STRIDE;
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int N, int KCH, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 float* __restrict__ Y, const float* __restrict__ bias, KArgs a) {
+  using S = KSmem<N, KCH, STAGES>;
+  constexpr int ROWB = KCH * 4;
+  constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nk = a.ntaps * a.cpt;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int b = 0, t0 = 0;
+        if (!a.plain) {
+          b = tile / a.tiles_per_clip;
+          t0 = (tile - b * a.tiles_per_clip) * a.th;
+        }
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          const int dt = a.ntaps == 9 ? tap / 3 - 1 : 0, df = a.ntaps == 9 ? tap % 3 - 1 : 0;
+          for (int ch = 0; ch < a.cpt; ++ch) {
+            mbar_wait(&empty[s], ph ^ 1);
+            unsigned char* sa = smem + s * S::STAGE;
+            unsigned char* sb = sa + S::A_BYTES;
+            mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+            if (a.plain) tma_load_2d(&mapA, sa, &full[s], ch * KCH, tile * kBM);
+            else tma_load_4d(&mapA, sa, &full[s], ch * KCH, df, t0 + dt, b);
+            tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, 0);
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        __syncwarp();
+        if (lane == 0) {   // one fixed lane issues the MMAs and their commits (commit tracks the issuing thread)
+          const uint32_t sa = smem_u32(smem + s * S::STAGE);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KCH / 8; ++k) {
+            uint64_t da = kmajor_desc<ROWB>(sa + k * 32);
+            uint64_t db = kmajor_desc<ROWB>(sb + k * 32);
+            umma_tf32(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);                      // frees the stage once these MMAs have read it
+          if (kc == nk - 1) umma_commit(&tfull[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // row of the 128-row tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      long long grow;                       // global output row
+      bool valid;
+      if (a.plain) {
+        grow = (long long)tile * kBM + row;
+        valid = grow < a.rows;
+      } else {
+        int b = tile / a.tiles_per_clip;
+        int t0 = (tile - b * a.tiles_per_clip) * a.th;
+        long long in_clip = (long long)t0 * a.F + row;
+        valid = in_clip < (long long)a.T * a.F;
+        grow = (long long)b * a.T * a.F + in_clip;
+      }
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * N + ((uint32_t)(q * 32) << 16);
+      float* yrow = Y + grow * a.ldc;
+      if constexpr (N >= 32) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (bias) {
+                float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              float4* dst = reinterpret_cast<float4*>(yrow + c0 + j);
+              if (a.accumulate) {
+                float4 c = *dst;
+                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+              }
+              *dst = o;
+            }
+          }
+        }
+      } else {
+        float v[16];
+        tmem_ld16(taddr, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (bias) {
+              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(yrow + j);
+            if (a.accumulate) {
+              float4 c = *dst;
+              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            }
+            *dst = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rank-R fp32 map; dims/strides innermost first (strides in bytes for dims 1..R-1)
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box, int row_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    bsed_set_error("cuTensorMapEncodeTiled entry point not available");
+    return BSED_E_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    bsed_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return BSED_E_CUDA;
+  }
+  return BSED_OK;
+}
+
+template <int N, int KCH>
+static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, float* Y, const float* bias, const KArgs& a, int sms,
+                    cudaStream_t st) {
+  constexpr int STAGES = (N >= 128 && KCH == 32) ? 6 : 8;
+  using S = KSmem<N, KCH, STAGES>;
+  auto kern = tc_kmajor_kernel<N, KCH, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, Y, bias, a);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+template <int KCH>
+static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, float* Y, const float* bias, const KArgs& a,
+                      int sms, cudaStream_t st) {
+  switch (N) {
+    case 16: return launch_k<16, KCH>(mA, mB, Y, bias, a, sms, st);
+    case 32: return launch_k<32, KCH>(mA, mB, Y, bias, a, sms, st);
+    case 64: return launch_k<64, KCH>(mA, mB, Y, bias, a, sms, st);
+    case 128: return launch_k<128, KCH>(mA, mB, Y, bias, a, sms, st);
+  }
+  bsed_set_error("tc gemm: N=%d unsupported (16/32/64/128)", N);
+  return BSED_E_INVALID;
+}
+
+}  // namespace tc
+
+// Y[B][T][F][Cout] (+)= conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin]
+// (k = tap*Cin + ci).  Requires F in {2..128} dividing 128.
+int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+               int accumulate, int sms, cudaStream_t st) {
+  BSED_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128, "tc_conv3x3: Cin=%d Cout=%d", Cin, Cout);
+  BSED_REQUIRE(F >= 1 && F <= 128 && 128 % F == 0, "tc_conv3x3: F=%d must divide 128", F);
+  const int KCH = Cin % 32 == 0 ? 32 : 16;
+  const int th = 128 / F;
+  CUtensorMap mA, mB;
+  cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sA[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
+  cuuint32_t bA[4] = {(cuuint32_t)KCH, (cuuint32_t)F, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, KCH * 4));
+  cuuint64_t dB[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+  cuuint64_t sB[1] = {(cuuint64_t)9 * Cin * 4};
+  cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)Cout};
+  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, KCH * 4));
+  tc::KArgs a;
+  a.plain = 0;
+  a.tiles_per_clip = (T + th - 1) / th;
+  a.n_tiles = a.tiles_per_clip * B;
+  a.th = th;
+  a.T = T;
+  a.F = F;
+  a.rows = 0;
+  a.ntaps = 9;
+  a.cpt = Cin / KCH;
+  a.ldc = Cout;
+  a.accumulate = accumulate;
+  ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
+                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
+  if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, Y, bias, a, sms, st);
+  return tc::dispatch_n<16>(Cout, mA, mB, Y, bias, a, sms, st);
+}
+
+// C[M][N] (+)= A[M][K] * Bk^T + bias ; Bk = [N][K] K-major
+int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
+               const float* bias, int accumulate, int sms, cudaStream_t st) {
+  BSED_REQUIRE(K % 16 == 0 && N % 16 == 0 && N <= 128 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
+               "tc_gemm_nt: M=%lld N=%d K=%d", M, N, K);
+  const int KCH = K % 32 == 0 ? 32 : 16;
+  CUtensorMap mA, mB;
+  cuuint64_t dA[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
+  cuuint32_t bA[2] = {(cuuint32_t)KCH, 128};
+  BSED_TRY(tc::make_map(&mA, A, 2, dA, sA, bA, KCH * 4));
+  cuuint64_t dB[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t sB[1] = {(cuuint64_t)ldb * 4};
+  cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)N};
+  BSED_TRY(tc::make_map(&mB, Bk, 2, dB, sB, bB, KCH * 4));
+  tc::KArgs a;
+  a.plain = 1;
+  a.n_tiles = (int)((M + 127) / 128);
+  a.tiles_per_clip = 1;
+  a.th = 1;
+  a.T = 1;
+  a.F = 128;
+  a.rows = M;
+  a.ntaps = 1;
+  a.cpt = K / KCH;
+  a.ldc = ldc;
+  a.accumulate = accumulate;
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
+  if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, C, bias, a, sms, st);
+  return tc::dispatch_n<16>(N, mA, mB, C, bias, a, sms, st);
+}
+
+}  // namespace bsed

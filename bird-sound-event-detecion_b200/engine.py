@@ -261,7 +261,20 @@ def gemm_tn(a, b, out):
     return out
 
 
-def conv3x3(x, weight, bias=None):
+def gemm_nt_tc(a, bk, bias=None, out=None, accumulate=False):
+    """tcgen05: out[M][N] (+)= a[M][K] @ bk[N][K]^T (+ bias)."""
+    lib = _lib.load()
+    h = _lib.handle(a.device.index)
+    M, K = a.shape
+    N = bk.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    check(lib.bsed_gemm_nt_tc(h, _rows(a), a.stride(0), _rows(bk), bk.stride(0), _rows(out), out.stride(0), M, N, K,
+                              ptr(bias), int(bool(accumulate)), stream_ptr()), "bsed_gemm_nt_tc")
+    return out
+
+
+def conv3x3(x, weight, bias=None, tensor_cores=False):
     """channels-last x (B, T, F, Cin), weight (Cout, Cin, 3, 3) -> (B, T, F, Cout)."""
     lib = _lib.load()
     h = _lib.handle(x.device.index)
@@ -269,6 +282,7 @@ def conv3x3(x, weight, bias=None):
     Cout = weight.shape[0]
     y = torch.empty(B, T, F, Cout, dtype=torch.float32, device=x.device)
     wpack = torch.empty(9 * Cin * Cout, dtype=torch.float32, device=x.device)
-    check(lib.bsed_conv3x3(h, ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(y), B, T, F, Cin, Cout,
-                           ptr(wpack), stream_ptr()), "bsed_conv3x3")
+    fn = lib.bsed_conv3x3_tc if tensor_cores else lib.bsed_conv3x3
+    check(fn(h, ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(y), B, T, F, Cin, Cout, ptr(wpack),
+             stream_ptr()), "bsed_conv3x3")
     return y

@@ -245,6 +245,12 @@ int bsed_gemm_tn(bsed_handle h, const float* A, int lda, const float* Bm, int ld
                  int M, int N, int K, void* stream);
 int bsed_conv3x3(bsed_handle h, const float* x, const float* weight, const float* bias, float* y,
                  int B, int T, int F, int Cin, int Cout, float* wpack, void* stream);
+/* tcgen05 (kind::tf32) + TMA variants: conv3x3_tc needs F dividing 128 and Cout <= 128;
+ * gemm_nt_tc: C[M][N] (+)= A[M][K] * Bk[N][K]^T (+ bias), N <= 128, K % 16 == 0. */
+int bsed_conv3x3_tc(bsed_handle h, const float* x, const float* weight, const float* bias, float* y,
+                    int B, int T, int F, int Cin, int Cout, float* wpack, void* stream);
+int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
+                    int M, int N, int K, const float* bias, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -144,3 +144,39 @@ def test_mt_loss_matches_torch():
     assert rel_l2(ds.cpu().numpy(), st.grad.numpy()) < 1e-5
     assert rel_l2(dw.cpu().numpy(), wk.grad.numpy()) < 1e-5
     assert float(ds[5].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 (kind::tf32) + TMA kernels: same contracts, tf32 input rounding (10-bit mantissa)
+# ---------------------------------------------------------------------------------------------
+TF32_REL = 2e-3
+
+
+@pytest.mark.parametrize("B,T,Fq,Cin,Cout", [(2, 37, 16, 32, 32), (1, 20, 8, 64, 128), (3, 11, 2, 128, 128),
+                                             (2, 9, 4, 32, 16), (1, 313, 1, 128, 128), (2, 5, 64, 16, 16),
+                                             (1, 627, 64, 16, 32), (2, 313, 32, 32, 64), (2, 40, 128, 16, 32)])
+def test_conv3x3_tensor_cores(B, T, Fq, Cin, Cout):
+    from bsed_b200 import engine
+    x = _rand(B, Cin, T, Fq, seed=10)
+    w = _rand(Cout, Cin, 3, 3, seed=11, scale=0.2)
+    b = _rand(Cout, seed=12)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    got = engine.conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), b.cuda(), tensor_cores=True)
+    torch.cuda.synchronize()
+    assert rel_l2(got.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < TF32_REL
+
+
+@pytest.mark.parametrize("M,K,N,bias,acc", [(1000, 128, 128, False, False), (300, 16, 16, True, False),
+                                            (777, 256, 64, True, False), (513, 768, 128, False, True),
+                                            (129, 64, 64, True, True), (5, 32, 32, False, False),
+                                            (40000, 32, 32, True, False)])
+def test_gemm_nt_tensor_cores(M, K, N, bias, acc):
+    from bsed_b200 import engine
+    a, bk = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    bi = _rand(N, seed=3) if bias else None
+    c0 = _rand(M, N, seed=4)
+    ref = a.double() @ bk.double().T + (bi.double() if bias else 0) + (c0.double() if acc else 0)
+    out = c0.clone().cuda() if acc else None
+    got = engine.gemm_nt_tc(a.cuda(), bk.cuda(), bi.cuda() if bias else None, out=out, accumulate=acc)
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu().numpy(), ref.numpy()) < TF32_REL
