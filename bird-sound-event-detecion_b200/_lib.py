@@ -23,7 +23,7 @@ SYMBOLS = [
     "bsed_predictor_ldl", "bsed_predictor_workspace_bytes", "bsed_predictor_forward", "bsed_predictor_backward",
     "bsed_plan_debug_tensor", "bsed_mt_loss", "bsed_opt_ema_step", "bsed_ema_buffers", "bsed_gemm_nn",
     "bsed_gemm_tn", "bsed_conv3x3", "bsed_launch_count", "bsed_profile_begin", "bsed_profile_end",
-    "bsed_conv3x3_tc", "bsed_gemm_nt_tc",
+    "bsed_conv3x3_tc", "bsed_gemm_nt_tc", "bsed_conv3x3_wgrad", "bsed_conv3x3_wgrad_workspace_bytes",
 ]
 
 
@@ -105,6 +105,8 @@ def load():
         proto("bsed_launch_count", u64)
         proto("bsed_profile_begin", i32, i32)
         proto("bsed_profile_end", i32, P(C.c_double), P(C.c_double), P(C.c_double), P(i32))
+        proto("bsed_conv3x3_wgrad_workspace_bytes", sz, vp)
+        proto("bsed_conv3x3_wgrad", i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp)
         proto("bsed_conv3x3_tc", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
         proto("bsed_gemm_nt_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)
         proto("bsed_conv3x3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)

@@ -315,3 +315,14 @@ extern "C" int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const flo
   BSED_REQUIRE(h && A && Bk && C, "bsed_gemm_nt_tc: null argument");
   return tc_gemm_nt(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, h->num_sms, as_stream(stream));
 }
+
+// conv weight gradient: dw (Cout,Cin,3,3) += ...; unit-test entry (tensor_cores = 0 -> fp32 SIMT split-K)
+extern "C" int bsed_conv3x3_wgrad(bsed_handle h, const float* x, const float* dy, float* dw, int B, int T, int F, int Cin,
+                                  int Cout, int tensor_cores, float* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(h && x && dy && dw, "bsed_conv3x3_wgrad: null argument");
+  if (!tensor_cores) return conv3x3_wgrad(x, dy, dw, B, T, F, Cin, Cout, h->num_sms * 4, as_stream(stream));
+  BSED_REQUIRE(workspace, "bsed_conv3x3_wgrad: workspace required for the tensor-core path");
+  return tc_wgrad(x, dy, dw, (long long)Cin * 9, 9, 1, B, T, F, Cin, Cout, 9, workspace, workspace_bytes, h->num_sms,
+                  as_stream(stream));
+}
+extern "C" size_t bsed_conv3x3_wgrad_workspace_bytes(bsed_handle h) { return h ? tc_wgrad_workspace_bytes(h->num_sms) : 0; }

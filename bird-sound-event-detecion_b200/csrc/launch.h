@@ -121,6 +121,10 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 
+size_t tc_wgrad_workspace_bytes(int sms);
+int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long cs, long long ts, int B, int T, int F,
+             int Cin, int Cout, int ntaps, float* part, size_t part_bytes, int sms, cudaStream_t st);
+
 // ---- frontend.cu
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st);
 int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_in, int frames,

@@ -14,6 +14,7 @@
 //   warp 1    TMEM allocation + MMA issue (one elected lane), double-buffered accumulators
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> + bias -> global fp32
 #include <cuda.h>
+#include <cstdlib>
 
 #include "launch.h"
 
@@ -368,7 +369,9 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return BSED_E_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = row_bytes == 128   ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : row_bytes == 132 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B   // 128 B rows, 32 B swizzle atoms
+                                             : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -385,6 +388,7 @@ static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, float* Y, cons
                     cudaStream_t st) {
   constexpr int STAGES = (N >= 128 && KCH == 32) ? 6 : 8;
   using S = KSmem<N, KCH, STAGES>;
+  static_assert(S::TOTAL <= 227 * 1024, "stage ring exceeds shared memory");
   auto kern = tc_kmajor_kernel<N, KCH, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -408,6 +412,186 @@ static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, float
   }
   bsed_set_error("tc gemm: N=%d unsupported (16/32/64/128)", N);
   return BSED_E_INVALID;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// MN-major kernel: weight gradients.  dW[co][ci] (per tap) = sum_pixels dY[p][co] * X[p + tap][ci]
+// Both operands are "[pixels][channels]" tiles, i.e. MN-major for this product (the reduction runs
+// over the rows): A = dY tile (M = co), B = shifted X tile (N = ci).  Same TMA boxes as the forward
+// kernel, only the descriptors differ.  One CTA = (pixel range, tap); the accumulator stays in TMEM
+// for the whole range; partial results go to a workspace [split][tap][128][N] reduced afterwards.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWP = 64;   // pixels per stage
+
+struct WArgs {
+  int n_tiles, tiles_per_clip, th;   // 64-pixel tiles
+  int T, F;
+  int ntaps;
+  int a_chunks;                      // Cout / 32
+  int tiles_per_split;
+  int layout, sbo;                   // shared-memory descriptor layout type and stride-byte-offset
+};
+
+// MN-major descriptor for 32-bit operands.  tcgen05 accepts exactly one shared-memory layout for MN-major
+// tf32: 128-byte rows (32 floats along M/N) whose 32-byte chunks are XOR-swizzled with the row index mod 4
+// (layout type 1, SWIZZLE_128B_BASE32B <-> CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  One swizzle atom is
+// 4 k-rows x 128 B; a K = 8 instruction spans two atoms (SBO = 512 B apart); the next 32 floats along M/N
+// live LBO bytes further (one TMA box each).
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint32_t layout) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+template <int N, int STAGES>
+struct WSmem {
+  static constexpr int NCH = 32;                           // floats per B row (128 B)
+  static constexpr int A_CHUNK = kWP * 128;                // [64 px][32 co] fp32
+  static constexpr int A_BYTES = 4 * A_CHUNK;              // room for M = 128 (4 chunks)
+  static constexpr int B_CHUNK = kWP * NCH * 4;
+  static constexpr int B_BYTES = (N / NCH) * B_CHUNK;
+  static constexpr int STAGE = A_BYTES + (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int TOTAL = STAGES * STAGE + 1024 + 256;
+};
+
+template <int N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                float* __restrict__ part, WArgs a) {
+  using S = WSmem<N, STAGES>;
+  constexpr int NCH = S::NCH;
+  constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : 128;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int split = blockIdx.x, tap = blockIdx.y;
+  const int tile_beg = split * a.tiles_per_split;
+  int tile_end = tile_beg + a.tiles_per_split;
+  if (tile_end > a.n_tiles) tile_end = a.n_tiles;
+  const int my_tiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int dt = a.ntaps == 9 ? tap / 3 - 1 : 0, df = a.ntaps == 9 ? tap % 3 - 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = a.a_chunks * S::A_CHUNK + S::B_BYTES;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        int b = tile / a.tiles_per_clip;
+        int t0 = (tile - b * a.tiles_per_clip) * a.th;
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* sa = smem + s * S::STAGE;
+        unsigned char* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full[s], tx);
+        for (int c = 0; c < a.a_chunks; ++c) tma_load_4d(&mapA, sa + c * S::A_CHUNK, &full[s], c * 32, 0, t0, b);
+#pragma unroll
+        for (int c = 0; c < N / NCH; ++c) tma_load_4d(&mapB, sb + c * S::B_CHUNK, &full[s], c * NCH, df, t0 + dt, b);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_tf32(N, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < kWP / 8; ++k) {
+          uint64_t da = mnmajor_desc(sa + k * 1024, S::A_CHUNK, a.sbo, a.layout);
+          uint64_t db = mnmajor_desc(sb + k * 1024, S::B_CHUNK, a.sbo, a.layout);
+          umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (i == my_tiles - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;   // co
+    float* out = part + (((size_t)split * a.ntaps + tap) * kBM + row) * N;
+    if (my_tiles > 0) {
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    } else {
+      for (int j = 0; j < N; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// dW[co*rs + ci*cs + tap*ts] += sum_split part[split][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int ntaps, int Cout, int N, float* dW,
+                                    long long rs, long long cs, long long ts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntaps * Cout * N) return;
+  int ci = i % N, co = (i / N) % Cout, tap = i / (N * Cout);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[(((size_t)s * ntaps + tap) * kBM + co) * N + ci];
+  dW[co * rs + ci * cs + tap * ts] += acc;
+}
+
+template <int N>
+static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, const WArgs& a, int splits, int ntaps,
+                    cudaStream_t st) {
+  constexpr int STAGES = N >= 128 ? 3 : 4;
+  using S = WSmem<N, STAGES>;
+  static_assert(S::TOTAL <= 227 * 1024, "wgrad stage ring exceeds shared memory");
+  auto kern = tc_wgrad_kernel<N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  dim3 grid(splits, ntaps);
+  kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, part, a);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
 }
 
 }  // namespace tc
@@ -479,4 +663,68 @@ int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int 
   return tc::dispatch_n<16>(N, mA, mB, C, bias, a, sms, st);
 }
 
+}  // namespace bsed
+
+namespace bsed {
+size_t tc_wgrad_workspace_bytes(int sms) { return (size_t)(sms / 9 + 1) * 9 * 128 * 128 * sizeof(float); }
+
+// dW (+)= sum_p dY[p][co] * X[p + tap][ci] for the 9 taps (ntaps = 9) or the plain product (ntaps = 1).
+// dW element (co, ci, tap) at dW[co*rs + ci*cs + tap*ts].  X [B][T][F][Cin], dY [B][T][F][Cout].
+int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long cs, long long ts, int B, int T, int F,
+             int Cin, int Cout, int ntaps, float* part, size_t part_bytes, int sms, cudaStream_t st) {
+  BSED_REQUIRE(Cin % 32 == 0 && Cin <= 128 && Cout % 32 == 0 && Cout <= 128, "tc_wgrad: Cin=%d Cout=%d", Cin, Cout);
+  BSED_REQUIRE(F >= 1 && F <= 64 && 64 % F == 0, "tc_wgrad: F=%d must divide 64", F);
+  BSED_REQUIRE(ntaps == 9 || ntaps == 1, "tc_wgrad: ntaps=%d", ntaps);
+  const int th = tc::kWP / F;
+  const int NCH = 32;
+  static int variant = -1;   // BSED_WGRAD_VARIANT=0: plain 128B swizzle (debug only; not a legal tf32 MN-major layout)
+  if (variant < 0) {
+    const char* e = getenv("BSED_WGRAD_VARIANT");
+    variant = e ? atoi(e) : 1;
+  }
+  const int sw = variant == 0 ? 128 : 132;
+  CUtensorMap mA, mB;
+  cuuint64_t dA[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sA[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
+  cuuint32_t bA[4] = {32, (cuuint32_t)F, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mA, dY, 4, dA, sA, bA, sw));
+  cuuint64_t dB[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sB[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
+  cuuint32_t bB[4] = {(cuuint32_t)NCH, (cuuint32_t)F, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mB, X, 4, dB, sB, bB, sw));
+  tc::WArgs a;
+  a.layout = variant == 0 ? 2 : 1;
+  a.sbo = variant == 0 ? 1024 : 512;
+  a.tiles_per_clip = (T + th - 1) / th;
+  a.n_tiles = a.tiles_per_clip * B;
+  a.th = th;
+  a.T = T;
+  a.F = F;
+  a.ntaps = ntaps;
+  a.a_chunks = Cout / 32;
+  int splits = sms / ntaps;
+  if (splits < 1) splits = 1;
+  if (splits > a.n_tiles) splits = a.n_tiles;
+  a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
+  splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  size_t need = (size_t)splits * ntaps * 128 * Cin * sizeof(float);
+  if (part_bytes < need) {
+    bsed_set_error("tc_wgrad: workspace %zu < %zu", part_bytes, need);
+    return BSED_E_WORKSPACE;
+  }
+  ProfScope prof(PROF_WGRAD, 2.0 * B * T * F * Cout * (double)ntaps * Cin,
+                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + (double)ntaps * Cin * Cout), st);
+  int r;
+  switch (Cin) {
+    case 32: r = tc::launch_w<32>(mA, mB, part, a, splits, ntaps, st); break;
+    case 64: r = tc::launch_w<64>(mA, mB, part, a, splits, ntaps, st); break;
+    case 128: r = tc::launch_w<128>(mA, mB, part, a, splits, ntaps, st); break;
+    default: bsed_set_error("tc_wgrad: Cin=%d unsupported", Cin); return BSED_E_INVALID;
+  }
+  BSED_TRY(r);
+  int n = ntaps * Cout * Cin;
+  tc::wgrad_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(part, splits, ntaps, Cout, Cin, dW, rs, cs, ts);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
 }  // namespace bsed

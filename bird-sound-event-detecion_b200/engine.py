@@ -286,3 +286,17 @@ def conv3x3(x, weight, bias=None, tensor_cores=False):
     check(fn(h, ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(y), B, T, F, Cin, Cout, ptr(wpack),
              stream_ptr()), "bsed_conv3x3")
     return y
+
+
+def conv3x3_wgrad(x, dy, tensor_cores=False):
+    """channels-last x (B,T,F,Cin), dy (B,T,F,Cout) -> dw (Cout,Cin,3,3)."""
+    lib = _lib.load()
+    h = _lib.handle(x.device.index)
+    B, T, F, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float32, device=x.device)
+    wsb = int(lib.bsed_conv3x3_wgrad_workspace_bytes(h))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    check(lib.bsed_conv3x3_wgrad(h, ptr(x.contiguous()), ptr(dy.contiguous()), ptr(dw), B, T, F, Cin, Cout,
+                                 int(bool(tensor_cores)), ptr(ws), wsb, stream_ptr()), "bsed_conv3x3_wgrad")
+    return dw

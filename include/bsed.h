@@ -249,6 +249,11 @@ int bsed_conv3x3(bsed_handle h, const float* x, const float* weight, const float
  * gemm_nt_tc: C[M][N] (+)= A[M][K] * Bk[N][K]^T (+ bias), N <= 128, K % 16 == 0. */
 int bsed_conv3x3_tc(bsed_handle h, const float* x, const float* weight, const float* bias, float* y,
                     int B, int T, int F, int Cin, int Cout, float* wpack, void* stream);
+/* dw (Cout,Cin,3,3) += sum_pixels dy[p][co] * x[p + tap][ci]; tensor_cores != 0 needs F dividing 64,
+ * Cout % 32 == 0 and a workspace of bsed_conv3x3_wgrad_workspace_bytes(h). */
+size_t bsed_conv3x3_wgrad_workspace_bytes(bsed_handle h);
+int bsed_conv3x3_wgrad(bsed_handle h, const float* x, const float* dy, float* dw, int B, int T, int F, int Cin,
+                       int Cout, int tensor_cores, float* workspace, size_t workspace_bytes, void* stream);
 int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
                     int M, int N, int K, const float* bias, int accumulate, void* stream);
 

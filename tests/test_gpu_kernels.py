@@ -180,3 +180,19 @@ def test_gemm_nt_tensor_cores(M, K, N, bias, acc):
     got = engine.gemm_nt_tc(a.cuda(), bk.cuda(), bi.cuda() if bias else None, out=out, accumulate=acc)
     torch.cuda.synchronize()
     assert rel_l2(got.cpu().numpy(), ref.numpy()) < TF32_REL
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("B,T,Fq,Cin,Cout", [(2, 37, 16, 32, 32), (1, 20, 8, 64, 128), (3, 11, 2, 128, 128),
+                                             (2, 313, 1, 128, 128), (2, 50, 64, 16, 32), (1, 313, 32, 32, 64),
+                                             (2, 100, 4, 128, 128)])
+def test_conv3x3_weight_gradient(B, T, Fq, Cin, Cout, tensor_cores):
+    from bsed_b200 import engine
+    x = _rand(B, Cin, T, Fq, seed=20).double().requires_grad_(False)
+    dy = _rand(B, Cout, T, Fq, seed=21).double()
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w, None, padding=1).backward(dy)
+    got = engine.conv3x3_wgrad(x.float().permute(0, 2, 3, 1).contiguous().cuda(),
+                               dy.float().permute(0, 2, 3, 1).contiguous().cuda(), tensor_cores=tensor_cores)
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu().numpy(), w.grad.numpy()) < (TF32_REL if tensor_cores else 1e-5)
