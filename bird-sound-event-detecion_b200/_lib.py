@@ -24,7 +24,9 @@ SYMBOLS = [
     "bsed_plan_debug_tensor", "bsed_mt_loss", "bsed_opt_ema_step", "bsed_ema_buffers", "bsed_gemm_nn",
     "bsed_gemm_tn", "bsed_conv3x3", "bsed_launch_count", "bsed_profile_begin", "bsed_profile_end",
     "bsed_conv3x3_tc", "bsed_gemm_nt_tc", "bsed_conv3x3_wgrad", "bsed_conv3x3_wgrad_workspace_bytes",
+    "bsed_plan_set_precision", "bsed_plan_get_precision",
 ]
+PRECISIONS = {"fp32": 0, "tf32": 1}
 
 
 class CrnnCfg(C.Structure):
@@ -83,6 +85,8 @@ def load():
         proto("bsed_median_decode", i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp, vp)
         proto("bsed_plan_create", i32, vp, P(CrnnCfg), i32, P(vp))
         proto("bsed_plan_destroy", i32, vp)
+        proto("bsed_plan_set_precision", i32, vp, i32)
+        proto("bsed_plan_get_precision", i32, vp)
         proto("bsed_plan_param_count", i64, vp)
         proto("bsed_plan_bn_buffer_count", i64, vp)
         proto("bsed_plan_out_frames", i32, vp)

@@ -32,7 +32,7 @@ struct ParamLayout {
 
 struct PackedLayout {
   long long wp[BSED_MAX_CNN_LAYERS], wd[BSED_MAX_CNN_LAYERS], glu_wT[BSED_MAX_CNN_LAYERS],
-      glu_bf[BSED_MAX_CNN_LAYERS];
+      glu_bf[BSED_MAX_CNN_LAYERS], glu_wgT[BSED_MAX_CNN_LAYERS];
   long long wihT[4], bih[4], whhT[4], whh[4], bhh[4], wih_cat[4];
   long long total;
   long long wcatT, bcat, wcat, pred_total;  // Predictor operands (own region)
@@ -56,8 +56,10 @@ struct bsed_crnn_plan {
   size_t off_stats, off_stats2, off_meanrstd;
   size_t off_xg, off_gru_out[4], off_gru_saved[4], off_enc;
   size_t off_dxn, off_dpool[2], off_denc, off_dx1, off_dxg, off_dgh;
-  size_t off_G, off_dscratch;
+  size_t off_G, off_dscratch, off_wgpart;
+  size_t wgpart_bytes;
   size_t ws_bytes;
+  int precision;  // BSED_PRECISION_FP32 (SIMT fp32) or BSED_PRECISION_TF32 (tcgen05 kind::tf32)
   // state of the last forward
   bool saved_valid;
   int n_groups, B;
@@ -170,6 +172,7 @@ int build_layouts(bsed_crnn_plan* p) {
     pk.wd[i] = ptake((long long)g.Cout * g.Cin * 9);
     pk.glu_wT[i] = ptake((long long)g.Cout * g.Cout);
     pk.glu_bf[i] = ptake(g.Cout);
+    pk.glu_wgT[i] = ptake((long long)g.Cout * g.Cout);
   }
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
@@ -228,6 +231,8 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_dgh = takeb(sizeof(float) * BT * 768);
   p->off_G = takeb(sizeof(float) * 128 * 128);
   p->off_dscratch = takeb(sizeof(double) * 2 * 768);
+  p->wgpart_bytes = tc_wgrad_workspace_bytes(p->ctx->num_sms);
+  p->off_wgpart = takeb(p->wgpart_bytes);
   p->ws_bytes = o;
 }
 
@@ -240,6 +245,7 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
   const bsed_crnn_cfg& c = p->cfg;
   const ParamLayout& pl = p->pl;
   const PackedLayout& pk = p->pk;
+  const bool tc = p->precision == BSED_PRECISION_TF32;
   tb->n = 0;
   auto add = [&](int type, const float* src, float* dst, int d0, int d1 = 0, int d2 = 0, int d3 = 0,
                  const float* a0 = nullptr, const float* a1 = nullptr, const float* a2 = nullptr,
@@ -260,11 +266,14 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
   for (int i = 0; i < c.n_cnn; ++i) {
     const LayerGeom& g = p->L[i];
     if (i > 0) {
-      add(PREP_CONV_PACK, params + pl.conv_w[i], packed + pk.wp[i], g.Cout, g.Cin);
-      if (need_bwd) add(PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
+      add(tc ? PREP_CONV_KMAJOR : PREP_CONV_PACK, params + pl.conv_w[i], packed + pk.wp[i], g.Cout, g.Cin);
+      if (need_bwd)
+        add(tc ? PREP_CONV_KMAJOR_FLIP : PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
     }
-    add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, 0, 0, 0, params + pl.bn_w[i],
+    // d1 != 0: K-major folded matrix [c'][c] for the tensor-core GEMM (B operand [N][K])
+    add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, tc ? 1 : 0, 0, 0, params + pl.bn_w[i],
         params + pl.bn_b[i], params + pl.glu_b[i], packed + pk.glu_bf[i]);
+    if (tc && need_bwd) add(PREP_TRANSPOSE, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, g.Cout, g.Cout, 0);
   }
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
@@ -275,10 +284,8 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
       // W_hh [384][128] -> whhT [d][128][384]
       add(PREP_TRANSPOSE, params + pl.whh[l][d], packed + pk.whhT[l] + (long long)d * 128 * 384, 384, 128, 384, 0);
       add(PREP_COPY, params + pl.bhh[l][d], packed + pk.bhh[l] + d * 384, 384);
-      if (need_bwd) {
-        add(PREP_COPY, params + pl.whh[l][d], packed + pk.whh[l] + (long long)d * 384 * 128, 384 * 128);
-        add(PREP_COPY, params + pl.wih[l][d], packed + pk.wih_cat[l] + (long long)d * 384 * In, 384 * In);
-      }
+      if (need_bwd) add(PREP_COPY, params + pl.whh[l][d], packed + pk.whh[l] + (long long)d * 384 * 128, 384 * 128);
+      if (need_bwd || tc) add(PREP_COPY, params + pl.wih[l][d], packed + pk.wih_cat[l] + (long long)d * 384 * In, 384 * In);
     }
   }
 }
@@ -340,6 +347,7 @@ extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max
   p->cfg = *cfg;
   p->max_clips = max_clips;
   p->saved_valid = false;
+  p->precision = BSED_PRECISION_TF32;
   int r = build_layouts(p);
   if (r != BSED_OK) {
     delete p;
@@ -354,6 +362,15 @@ extern "C" int bsed_plan_destroy(bsed_plan p) {
   delete p;
   return BSED_OK;
 }
+
+extern "C" int bsed_plan_set_precision(bsed_plan p, int precision) {
+  BSED_REQUIRE(p, "plan_set_precision: null plan");
+  BSED_REQUIRE(precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32, "plan_set_precision: mode %d", precision);
+  p->precision = precision;
+  p->saved_valid = false;
+  return BSED_OK;
+}
+extern "C" int bsed_plan_get_precision(bsed_plan p) { return p ? p->precision : -1; }
 
 extern "C" int64_t bsed_plan_param_count(bsed_plan p) { return p ? p->pl.total : -1; }
 extern "C" int64_t bsed_plan_bn_buffer_count(bsed_plan p) { return p ? p->pl.bn_total : -1; }
@@ -385,6 +402,8 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
   cudaStream_t st = as_stream(stream);
   const bsed_crnn_cfg& c = p->cfg;
   void* ws = workspace;
+  const bool tc = p->precision == BSED_PRECISION_TF32;
+  const int sms = p->ctx->num_sms;
 
   // groups must tile [0, B)
   Groups g;
@@ -463,9 +482,11 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]);
       for (int r = 0; r < n_runs; ++r) {
         const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
-        BSED_TRY(conv3x3_nn(xin + (size_t)runs[r].first * L.rows * L.Cin, packed + p->pk.wp[i],
-                            y + (size_t)runs[r].first * L.rows * L.Cout, runs[r].count, L.T, L.F, L.Cin, L.Cout,
-                            p->pset_params[runs[r].pset] + p->pl.conv_b[i], 0, st));
+        const float* xr = xin + (size_t)runs[r].first * L.rows * L.Cin;
+        float* yr = y + (size_t)runs[r].first * L.rows * L.Cout;
+        const float* cb = p->pset_params[runs[r].pset] + p->pl.conv_b[i];
+        if (tc) BSED_TRY(tc_conv3x3(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, sms, st));
+        else BSED_TRY(conv3x3_nn(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st));
       }
     }
     BNPtrs bn = make_bn_ptrs(p, ws, i, all_ids, n_groups);
@@ -492,8 +513,12 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       size_t off = (size_t)runs[r].first * L.rows * L.Cout;
       long long M = (long long)runs[r].count * L.rows;
       BSED_REQUIRE(M < (1ll << 31), "crnn_forward: too many pixels");
-      BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
-                       packed + p->pk.glu_bf[i], 0, st));
+      if (tc)
+        BSED_TRY(tc_gemm_nt(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, M, L.Cout, L.Cout,
+                            packed + p->pk.glu_bf[i], 0, sms, st));
+      else
+        BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
+                         packed + p->pk.glu_bf[i], 0, st));
     }
     BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
                                p->inv_keep, st));
@@ -508,9 +533,16 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     const float* X = l == 0 ? wsp<float>(ws, p->off_pool[c.n_cnn - 1]) : wsp<float>(ws, p->off_gru_out[l - 1]);
     for (int r = 0; r < n_runs; ++r) {
       const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
-      BSED_TRY(gemm_nn(X + (size_t)runs[r].first * T * In, In, packed + p->pk.wihT[l], 768,
-                       xg + (size_t)runs[r].first * T * 768, 768, runs[r].count * T, 768, In, packed + p->pk.bih[l],
-                       0, st));
+      const float* Xr = X + (size_t)runs[r].first * T * In;
+      float* xgr = xg + (size_t)runs[r].first * T * 768;
+      if (tc) {
+        for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
+          BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[l] + (size_t)n0 * In, In, xgr + n0, 768,
+                              (long long)runs[r].count * T, 128, In, packed + p->pk.bih[l] + n0, 0, sms, st));
+      } else {
+        BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[l], 768, xgr, 768, runs[r].count * T, 768, In, packed + p->pk.bih[l],
+                         0, st));
+      }
     }
     FloatPtrs whhT, bhh;
     for (int k = 0; k < kMaxGroups; ++k) {
@@ -571,6 +603,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
   const int T = p->Tout;
   const int sms = p->ctx->num_sms;
   const int target = sms * 4;
+  const bool tc = p->precision == BSED_PRECISION_TF32;
+  float* wgpart = wsp<float>(ws, p->off_wgpart);
   double* dscr = wsp<double>(ws, p->off_dscratch);
 
   if (!accumulate) BSED_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * pl.total, st));
@@ -617,7 +651,13 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bhh[l][0], 384, st));
     BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bhh[l][1], 384, st));
     float* dX = l == 0 ? dpool_cur + ro * 128 : dxin + ro * 256;
-    BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[l], In, dX, In, (int)BTn, In, 768, nullptr, 0, st));
+    if (tc) {
+      for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
+        BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[l] + (size_t)n0 * 768, 768, dX + n0, In, BTn, 128,
+                            768, nullptr, 0, sms, st));
+    } else {
+      BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[l], In, dX, In, (int)BTn, In, 768, nullptr, 0, st));
+    }
   }
 
   // ---- CNN blocks
@@ -635,11 +675,20 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
                                p->inv_keep, st));
     // dxn += d_lin * Wg        (Wg [c'][c] is already K-major for this product)
-    BSED_TRY(gemm_nn(lin + off, L.Cout, params + pl.glu_w[i], L.Cout, dxn + off, L.Cout, (int)M, L.Cout, L.Cout,
-                     nullptr, 1, st));
+    if (tc)
+      BSED_TRY(tc_gemm_nt(lin + off, L.Cout, packed + p->pk.glu_wgT[i], L.Cout, dxn + off, L.Cout, M, L.Cout, L.Cout,
+                          nullptr, 1, sms, st));
+    else
+      BSED_TRY(gemm_nn(lin + off, L.Cout, params + pl.glu_w[i], L.Cout, dxn + off, L.Cout, (int)M, L.Cout, L.Cout,
+                       nullptr, 1, st));
     // G = d_lin^T xhat ; dbg = colsum(d_lin)
     BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.Cout * L.Cout, st));
-    BSED_TRY(gemm_tn(lin + off, L.Cout, xhat + off, L.Cout, G, L.Cout, 1, L.Cout, L.Cout, M, target, st));
+    const bool tc_red = tc && L.Cout % 32 == 0 && L.F <= 64 && 64 % L.F == 0;
+    if (tc_red)
+      BSED_TRY(tc_wgrad(xhat + off, lin + off, G, L.Cout, 1, 0, nb, L.T, L.F, L.Cout, L.Cout, 1, wgpart, p->wgpart_bytes,
+                        sms, st));
+    else
+      BSED_TRY(gemm_tn(lin + off, L.Cout, xhat + off, L.Cout, G, L.Cout, 1, L.Cout, L.Cout, M, target, st));
     Groups one;
     one.n = 1;
     one.first[0] = 0;
@@ -656,11 +705,19 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(col_sum_to(dxn + off, M, L.Cout, grads + pl.conv_b[i], dscr, sms, st));
     if (i > 0) {
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]) + (size_t)first * L.rows * L.Cin;
-      BSED_TRY(conv3x3_wgrad(xin, dxn + off, grads + pl.conv_w[i], nb, L.T, L.F, L.Cin, L.Cout, target, st));
+      if (tc && L.Cin % 32 == 0 && L.F <= 64 && 64 % L.F == 0)
+        BSED_TRY(tc_wgrad(xin, dxn + off, grads + pl.conv_w[i], (long long)L.Cin * 9, 9, 1, nb, L.T, L.F, L.Cin, L.Cout, 9,
+                          wgpart, p->wgpart_bytes, sms, st));
+      else
+        BSED_TRY(conv3x3_wgrad(xin, dxn + off, grads + pl.conv_w[i], nb, L.T, L.F, L.Cin, L.Cout, target, st));
       cur ^= 1;
       float* dnext = wsp<float>(ws, p->off_dpool[cur]);
-      BSED_TRY(conv3x3_nn(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
-                          L.Cin, nullptr, 0, st));
+      if (tc)
+        BSED_TRY(tc_conv3x3(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
+                            L.Cin, nullptr, 0, sms, st));
+      else
+        BSED_TRY(conv3x3_nn(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
+                            L.Cin, nullptr, 0, st));
       dpool_cur = dnext;
     } else {
       BSED_TRY(conv0_wgrad(p->x_in, dxn, grads + pl.conv_w[0], first, nb, L.T, L.F, L.Cout, sms, st));

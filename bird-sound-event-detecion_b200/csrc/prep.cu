@@ -49,9 +49,13 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
     } break;
     case PREP_GLU_FOLD: {
       int C = op.d0;
-      for (int i = tid; i < C * C; i += nth) {  // dst [c][c']
-        int cp = i % C, c = i / C;
-        op.dst[i] = op.aux0[c] * op.src[(size_t)cp * C + c];
+      if (op.d1) {
+        for (int i = tid; i < C * C; i += nth) op.dst[i] = op.aux0[i % C] * op.src[i];  // dst [c'][c] (K-major)
+      } else {
+        for (int i = tid; i < C * C; i += nth) {  // dst [c][c']
+          int cp = i % C, c = i / C;
+          op.dst[i] = op.aux0[c] * op.src[(size_t)cp * C + c];
+        }
       }
       for (int cp = tid; cp < C; cp += nth) {
         float a = op.aux2[cp];

@@ -33,6 +33,12 @@ def make_cfg(nclass=20, dropout=0.5, nb_filters=(16, 32, 64, 128, 128, 128, 128)
     return cfg
 
 
+def default_precision():
+    """"tf32" (tcgen05 tensor cores; what cuDNN gives the reference on a GPU) unless BSED_PRECISION=fp32."""
+    import os
+    return os.environ.get("BSED_PRECISION", "tf32").lower()
+
+
 def _dev_index(device):
     device = torch.device(device)
     if device.type != "cuda":
@@ -44,14 +50,18 @@ class Plan:
     """bsed_plan + its workspace.  One saved forward at a time (see models/CRNN.py for the slot pool).
     `with_workspace=False` builds a plan that only serves the Predictor calls."""
 
-    def __init__(self, cfg, max_clips, device, with_workspace=True):
+    def __init__(self, cfg, max_clips, device, with_workspace=True, precision=None):
         self.lib = _lib.load()
+        self.precision = (precision or default_precision()).lower()
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.device = torch.device("cuda", _dev_index(device))
         self.h = _lib.handle(self.device.index)
         self.cfg = cfg
         self.max_clips = int(max_clips)
         self.p = C.c_void_p()
         check(self.lib.bsed_plan_create(self.h, C.byref(cfg), self.max_clips, C.byref(self.p)), "bsed_plan_create")
+        check(self.lib.bsed_plan_set_precision(self.p, _lib.PRECISIONS[self.precision]), "bsed_plan_set_precision")
         self.n_params = int(self.lib.bsed_plan_param_count(self.p))
         self.n_pred_params = int(self.lib.bsed_predictor_param_count(self.p))
         self.n_bn = int(self.lib.bsed_plan_bn_buffer_count(self.p))

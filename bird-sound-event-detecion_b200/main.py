@@ -83,7 +83,7 @@ class MeanTeacherTrainer:
 
     def __init__(self, model, predictor, ema_model=None, ema_predictor=None, lr=cfg.default_learning_rate,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, n_syn=cfg.batch_size, n_real=cfg.batch_size,
-                 ema_flavour="state_dict", dropout_seed=2023, process_group=None):
+                 ema_flavour="state_dict", dropout_seed=2023, process_group=None, precision=None):
         assert isinstance(model, CRNN) and isinstance(predictor, Predictor)
         self.model, self.predictor, self.ema_model, self.ema_predictor = model, predictor, ema_model, ema_predictor
         dev = model._flat.device
@@ -108,7 +108,8 @@ class MeanTeacherTrainer:
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         B = n_syn + n_real + (n_real if self.has_teacher else 0)
         self.B = B
-        self.plan = engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev)
+        self.plan = engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev,
+                                precision=precision or model.precision)
         assert self.plan.n_params == self.n_crnn and self.plan.n_pred_params == self.n_pred
         self.x = torch.empty(B, 1, cfg.max_frames, cfg.n_mels, dtype=torch.float32, device=dev)
         self.enc = torch.empty(B, self.plan.t_out, 256, dtype=torch.float32, device=dev)

@@ -209,6 +209,8 @@ class CRNN(_FlatModule):
         self._counter_mods = cm
         self._build(ps, bs, len(cm))
         self._slots, self._free = [], []
+        # "tf32" (tensor cores) / "fp32" (CUDA cores); None = engine.default_precision()
+        self.precision = kwargs.get("precision", None)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -235,12 +237,13 @@ class CRNN(_FlatModule):
 
     # ---- plan slots: each train-mode forward keeps its activations until its backward
     def _acquire_slot(self, B, save):
+        prec = (self.precision or engine.default_precision()).lower()
         for s in self._free:
-            if s.max_clips >= B and s.device == self._flat.device:
+            if s.max_clips >= B and s.device == self._flat.device and s.precision == prec:
                 self._free.remove(s)
                 return s
         cfg = engine.make_cfg(**self.cfg_kwargs)
-        s = engine.Plan(cfg, max_clips=B, device=self._flat.device)
+        s = engine.Plan(cfg, max_clips=B, device=self._flat.device, precision=prec)
         if s.n_params != self._flat.numel():
             raise RuntimeError(f"layout mismatch: library expects {s.n_params} parameters, module has {self._flat.numel()}")
         self._slots.append(s)

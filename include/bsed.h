@@ -117,6 +117,17 @@ typedef struct bsed_crnn_plan* bsed_plan;
 int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max_clips, bsed_plan* out);
 int bsed_plan_destroy(bsed_plan p);
 
+/* Arithmetic of the dense contractions (3x3 convolutions, GLU / GRU-input linears and their gradients):
+ *   BSED_PRECISION_TF32 (default)  tcgen05.mma kind::tf32 fed by TMA, fp32 accumulation in TMEM -- what
+ *                                  the reference gets from cuDNN on a GPU (torch.backends.cudnn.allow_tf32
+ *                                  defaults to True);
+ *   BSED_PRECISION_FP32            fp32 FMA on the CUDA cores (the tight-parity mode of the tests).
+ * Everything else (BatchNorm, gates, pooling, GRU recurrence, head, losses, optimiser) is fp32 in both. */
+#define BSED_PRECISION_FP32 0
+#define BSED_PRECISION_TF32 1
+int bsed_plan_set_precision(bsed_plan p, int precision);
+int bsed_plan_get_precision(bsed_plan p);
+
 int64_t bsed_plan_param_count(bsed_plan p);       /* floats in the flat parameter buffer  */
 int64_t bsed_plan_bn_buffer_count(bsed_plan p);   /* floats in the flat BN running-stat buffer */
 int bsed_plan_out_frames(bsed_plan p);            /* 313 */
