@@ -633,10 +633,19 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(gru_backward(dout, wsp<float>(ws, p->off_gru_saved[l]), out_l, packed + p->pk.whh[l], dxg, dgh, T, first,
                           nb, st));
     for (int d = 0; d < 2; ++d) {
-      BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
-                            grads + pl.whh[l][d], T, BTn, target, st));
-      BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[l][d], In, 1, 384, In, BTn,
-                       target, st));
+      if (tc) {
+        // dW_hh[j][i] += sum_{b,t} dgh[b][t][j] * h[b][t -/+ 1][i] ; dW_ih[j][i] += sum_{b,t} dxg[b][t][j] * x[b][t][i]
+        TcOperand Ah{dgh + ro * 768, 768, d * 384, 384}, Bh{out_l + ro * 256, 256, d * 128, 128};
+        BSED_TRY(tc_wgrad_ex(Ah, Bh, nb, T, 1, 1, d == 0 ? -1 : 1, grads + pl.whh[l][d], 128, 1, 0, wgpart,
+                             p->wgpart_bytes, sms, st));
+        TcOperand Ai{dxg + ro * 768, 768, d * 384, 384}, Bi{X + ro * In, In, 0, In};
+        BSED_TRY(tc_wgrad_ex(Ai, Bi, nb, T, 1, 1, 0, grads + pl.wih[l][d], In, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+      } else {
+        BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
+                              grads + pl.whh[l][d], T, BTn, target, st));
+        BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[l][d], In, 1, 384, In, BTn,
+                         target, st));
+      }
     }
     Groups one;
     one.n = 1;
@@ -683,11 +692,14 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
                        nullptr, 1, st));
     // G = d_lin^T xhat ; dbg = colsum(d_lin)
     BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.Cout * L.Cout, st));
-    const bool tc_red = tc && L.Cout % 32 == 0 && L.F <= 64 && 64 % L.F == 0;
-    if (tc_red)
+    if (tc && L.Cout % 32 == 0 && L.F <= 64 && 64 % L.F == 0) {
       BSED_TRY(tc_wgrad(xhat + off, lin + off, G, L.Cout, 1, 0, nb, L.T, L.F, L.Cout, L.Cout, 1, wgpart, p->wgpart_bytes,
                         sms, st));
-    else
+    } else if (tc && L.Cout == 16 && L.F % 2 == 0 && L.F <= 128 && 64 % (L.F / 2) == 0) {
+      // 16-channel block: both operands viewed two pixels per row (32 floats)
+      TcOperand Ag{lin + off, 32, 0, 32}, Bg{xhat + off, 32, 0, 32};
+      BSED_TRY(tc_wgrad_ex(Ag, Bg, nb, L.T, L.F / 2, 3, 0, G, L.Cout, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+    } else
       BSED_TRY(gemm_tn(lin + off, L.Cout, xhat + off, L.Cout, G, L.Cout, 1, L.Cout, L.Cout, M, target, st));
     Groups one;
     one.n = 1;
@@ -705,7 +717,9 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(col_sum_to(dxn + off, M, L.Cout, grads + pl.conv_b[i], dscr, sms, st));
     if (i > 0) {
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]) + (size_t)first * L.rows * L.Cin;
-      if (tc && L.Cin % 32 == 0 && L.F <= 64 && 64 % L.F == 0)
+      const bool tc_w32 = L.Cin % 32 == 0 && L.F <= 64 && 64 % L.F == 0;
+      const bool tc_w16 = L.Cin == 16 && L.F % 2 == 0 && L.F <= 128 && 64 % (L.F / 2) == 0;
+      if (tc && L.Cout % 32 == 0 && (tc_w32 || tc_w16))
         BSED_TRY(tc_wgrad(xin, dxn + off, grads + pl.conv_w[i], (long long)L.Cin * 9, 9, 1, nb, L.T, L.F, L.Cin, L.Cout, 9,
                           wgpart, p->wgpart_bytes, sms, st));
       else

@@ -122,6 +122,13 @@ int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int 
                const float* bias, int accumulate, int sms, cudaStream_t st);
 
 size_t tc_wgrad_workspace_bytes(int sms);
+// [rows][ld] fp32 tensor, channels [c0, c0 + C) of every row take part
+struct TcOperand {
+  const float* p;
+  int ld, c0, C;
+};
+int tc_wgrad_ex(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int mode, int dt0, float* dW, long long rs,
+                long long cs, long long ts, float* part, size_t part_bytes, int sms, cudaStream_t st);
 int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long cs, long long ts, int B, int T, int F,
              int Cin, int Cout, int ntaps, float* part, size_t part_bytes, int sms, cudaStream_t st);
 

@@ -416,21 +416,35 @@ static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, float
 
 
 // ---------------------------------------------------------------------------------------------
-// MN-major kernel: weight gradients.  dW[co][ci] (per tap) = sum_pixels dY[p][co] * X[p + tap][ci]
-// Both operands are "[pixels][channels]" tiles, i.e. MN-major for this product (the reduction runs
-// over the rows): A = dY tile (M = co), B = shifted X tile (N = ci).  Same TMA boxes as the forward
-// kernel, only the descriptors differ.  One CTA = (pixel range, tap); the accumulator stays in TMEM
-// for the whole range; partial results go to a workspace [split][tap][128][N] reduced afterwards.
+// MN-major kernel: reductions over rows ("weight gradients").
+//     D[m][n] (per tap) = sum_rows A[row][m] * Bm[row + shift(tap)][n]
+// Both operands are "[rows][channels]" tensors, i.e. MN-major for this product (the reduction runs over
+// the rows): A = dY tile (M = channels of A), B = shifted X tile (N = channels of B).  Same 4-D TMA boxes as
+// the forward kernel -- (channel, f, t, clip) with zero fill outside the clip = the convolution's padding
+// -- only the descriptors differ.  One CTA = (row range, tap, M/N tile); the accumulator stays in TMEM for
+// the whole range; partial results go to a workspace [split][tap][tile][128][N] reduced afterwards.
+// Modes:
+//   W_CONV9   9 taps (dt, df) in {-1,0,1}^2                      conv weight gradient, Cin % 32 == 0
+//   W_SINGLE  one tap (dt0, 0)                                   GLU / GRU reductions (dt0 = -1/+1: W_hh)
+//   W_PAIR    operands viewed two pixels per row (rows of 2*C floats) for C = 16 channel tensors, whose
+//             64-byte rows cannot be MN-major tf32 operands: 12 virtual taps (dt, j) with
+//             j = 0: A even pixels, B pair g      -> cols 0..15 = tap df 0,  cols 16..31 = tap df +1
+//             j = 1: A even pixels, B pair g - 1  ->                         cols 16..31 = tap df -1
+//             j = 2: A odd pixels,  B pair g      -> cols 0..15 = tap df -1, cols 16..31 = tap df 0
+//             j = 3: A odd pixels,  B pair g + 1  -> cols 0..15 = tap df +1
 // ---------------------------------------------------------------------------------------------
-constexpr int kWP = 64;   // pixels per stage
+constexpr int kWP = 64;   // rows per stage
+enum { W_CONV9 = 0, W_SINGLE = 1, W_PAIR = 2 };
 
 struct WArgs {
-  int n_tiles, tiles_per_clip, th;   // 64-pixel tiles
+  int n_tiles, tiles_per_clip, th;   // 64-row tiles
   int T, F;
-  int ntaps;
-  int a_chunks;                      // Cout / 32
+  int mode, dt0;
+  int a_c0, b_c0;                    // first channel of A / B
+  int m_total;                       // channels of A (multiple of 32); M tiles of 128
+  int n_tiles_n;                     // N tiles (each N channels of B)
+  int pair_stride;                   // W_PAIR: channel offset of the odd pixel inside an A row (= Cout)
   int tiles_per_split;
-  int layout, sbo;                   // shared-memory descriptor layout type and stride-byte-offset
 };
 
 // MN-major descriptor for 32-bit operands.  tcgen05 accepts exactly one shared-memory layout for MN-major
@@ -438,16 +452,15 @@ struct WArgs {
 // (layout type 1, SWIZZLE_128B_BASE32B <-> CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  One swizzle atom is
 // 4 k-rows x 128 B; a K = 8 instruction spans two atoms (SBO = 512 B apart); the next 32 floats along M/N
 // live LBO bytes further (one TMA box each).
-__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                 uint32_t layout) {
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+         ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
 template <int N, int STAGES>
 struct WSmem {
   static constexpr int NCH = 32;                           // floats per B row (128 B)
-  static constexpr int A_CHUNK = kWP * 128;                // [64 px][32 co] fp32
+  static constexpr int A_CHUNK = kWP * 128;                // [64 rows][32 channels] fp32
   static constexpr int A_BYTES = 4 * A_CHUNK;              // room for M = 128 (4 chunks)
   static constexpr int B_CHUNK = kWP * NCH * 4;
   static constexpr int B_BYTES = (N / NCH) * B_CHUNK;
@@ -472,10 +485,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int split = blockIdx.x, tap = blockIdx.y;
+  const int mt = blockIdx.z / a.n_tiles_n, nt = blockIdx.z % a.n_tiles_n;
   const int tile_beg = split * a.tiles_per_split;
   int tile_end = tile_beg + a.tiles_per_split;
   if (tile_end > a.n_tiles) tile_end = a.n_tiles;
   const int my_tiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+  int a_chunks = (a.m_total - mt * kBM) / 32;
+  if (a_chunks > 4) a_chunks = 4;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
@@ -492,13 +508,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int dt = a.ntaps == 9 ? tap / 3 - 1 : 0, df = a.ntaps == 9 ? tap % 3 - 1 : 0;
+  int dt, df, a_ch = a.a_c0 + mt * kBM;
+  const int b_ch = a.b_c0 + nt * N;
+  if (a.mode == W_CONV9) {
+    dt = tap / 3 - 1;
+    df = tap % 3 - 1;
+  } else if (a.mode == W_SINGLE) {
+    dt = a.dt0;
+    df = 0;
+  } else {
+    const int j = tap & 3;
+    dt = (tap >> 2) - 1;
+    df = j == 1 ? -1 : j == 3 ? 1 : 0;
+    if (j >= 2) a_ch += a.pair_stride;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = a.a_chunks * S::A_CHUNK + S::B_BYTES;
+      const uint32_t tx = a_chunks * S::A_CHUNK + S::B_BYTES;
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         int b = tile / a.tiles_per_clip;
         int t0 = (tile - b * a.tiles_per_clip) * a.th;
@@ -506,9 +535,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         unsigned char* sa = smem + s * S::STAGE;
         unsigned char* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full[s], tx);
-        for (int c = 0; c < a.a_chunks; ++c) tma_load_4d(&mapA, sa + c * S::A_CHUNK, &full[s], c * 32, 0, t0, b);
+        for (int c = 0; c < a_chunks; ++c) tma_load_4d(&mapA, sa + c * S::A_CHUNK, &full[s], a_ch + c * 32, 0, t0, b);
 #pragma unroll
-        for (int c = 0; c < N / NCH; ++c) tma_load_4d(&mapB, sb + c * S::B_CHUNK, &full[s], c * NCH, df, t0 + dt, b);
+        for (int c = 0; c < N / NCH; ++c) tma_load_4d(&mapB, sb + c * S::B_CHUNK, &full[s], b_ch + c * NCH, df, t0 + dt, b);
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
@@ -528,8 +557,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < kWP / 8; ++k) {
-          uint64_t da = mnmajor_desc(sa + k * 1024, S::A_CHUNK, a.sbo, a.layout);
-          uint64_t db = mnmajor_desc(sb + k * 1024, S::B_CHUNK, a.sbo, a.layout);
+          uint64_t da = mnmajor_desc(sa + k * 1024, S::A_CHUNK);
+          uint64_t db = mnmajor_desc(sb + k * 1024, S::B_CHUNK);
           umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -543,8 +572,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   } else {
     const int q = warp & 3;
-    const int row = q * 32 + lane;   // co
-    float* out = part + (((size_t)split * a.ntaps + tap) * kBM + row) * N;
+    const int row = q * 32 + lane;   // channel of A inside this M tile
+    float* out = part + ((((size_t)split * gridDim.y + tap) * gridDim.z + blockIdx.z) * kBM + row) * N;
     if (my_tiles > 0) {
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
@@ -553,10 +582,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int c0 = 0; c0 < N; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + c0, v);
+        if (row < a_chunks * 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
       }
-    } else {
+    } else if (row < a_chunks * 32) {
       for (int j = 0; j < N; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -565,20 +596,47 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// dW[co*rs + ci*cs + tap*ts] += sum_split part[split][tap][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int ntaps, int Cout, int N, float* dW,
-                                    long long rs, long long cs, long long ts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ntaps * Cout * N) return;
-  int ci = i % N, co = (i / N) % Cout, tap = i / (N * Cout);
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += part[(((size_t)s * ntaps + tap) * kBM + co) * N + ci];
-  dW[co * rs + ci * cs + tap * ts] += acc;
+struct RArgs {
+  int splits, ntaps, ztiles, n_tiles_n, N;
+  int m_total, n_total;
+  int mode;
+  long long rs, cs, ts;
+};
+
+// part [split][tap][z][128][N] -> dW.  W_CONV9 / W_SINGLE: dW[m*rs + n*cs + tap*ts] += sum_split.
+// W_PAIR (C = 16 input channels, see the table above): dW[m*rs + ci*cs + (3*(dt+1) + df+1)*ts].
+// mode 3 (GLU of a 16-channel block, both operands in pair view): dW[m*rs + n*cs] += P[m][n] + P[16+m][16+n].
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, RArgs r, float* dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  auto P = [&](int tap, int m, int n) {
+    const int z = (m / kBM) * r.n_tiles_n + n / r.N;
+    float acc = 0.f;
+    for (int s = 0; s < r.splits; ++s)
+      acc += part[((((size_t)s * r.ntaps + tap) * r.ztiles + z) * kBM + m % kBM) * r.N + n % r.N];
+    return acc;
+  };
+  if (r.mode == W_PAIR) {
+    if (i >= 9 * r.m_total * 16) return;
+    const int ci = i % 16, m = (i / 16) % r.m_total, tap = i / (16 * r.m_total);
+    const int dt = tap / 3, df = tap % 3 - 1;
+    float acc;
+    if (df == 0) acc = P(dt * 4 + 0, m, ci) + P(dt * 4 + 2, m, 16 + ci);
+    else if (df == 1) acc = P(dt * 4 + 0, m, 16 + ci) + P(dt * 4 + 3, m, ci);
+    else acc = P(dt * 4 + 1, m, 16 + ci) + P(dt * 4 + 2, m, ci);
+    dW[m * r.rs + ci * r.cs + tap * r.ts] += acc;
+  } else if (r.mode == 3) {
+    if (i >= 16 * 16) return;
+    const int n = i % 16, m = i / 16;
+    dW[m * r.rs + n * r.cs] += P(0, m, n) + P(0, 16 + m, 16 + n);
+  } else {
+    if (i >= r.ntaps * r.m_total * r.n_total) return;
+    const int n = i % r.n_total, m = (i / r.n_total) % r.m_total, tap = i / (r.n_total * r.m_total);
+    dW[m * r.rs + n * r.cs + tap * r.ts] += P(tap, m, n);
+  }
 }
 
 template <int N>
-static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, const WArgs& a, int splits, int ntaps,
-                    cudaStream_t st) {
+static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, const WArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = N >= 128 ? 3 : 4;
   using S = WSmem<N, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "wgrad stage ring exceeds shared memory");
@@ -588,7 +646,6 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid(splits, ntaps);
   kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, part, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
@@ -666,65 +723,100 @@ int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int 
 }  // namespace bsed
 
 namespace bsed {
-size_t tc_wgrad_workspace_bytes(int sms) { return (size_t)(sms / 9 + 1) * 9 * 128 * 128 * sizeof(float); }
+size_t tc_wgrad_workspace_bytes(int sms) { return (size_t)(sms + 16) * 128 * 128 * sizeof(float); }
 
-// dW (+)= sum_p dY[p][co] * X[p + tap][ci] for the 9 taps (ntaps = 9) or the plain product (ntaps = 1).
-// dW element (co, ci, tap) at dW[co*rs + ci*cs + tap*ts].  X [B][T][F][Cin], dY [B][T][F][Cout].
-int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long cs, long long ts, int B, int T, int F,
-             int Cin, int Cout, int ntaps, float* part, size_t part_bytes, int sms, cudaStream_t st) {
-  BSED_REQUIRE(Cin % 32 == 0 && Cin <= 128 && Cout % 32 == 0 && Cout <= 128, "tc_wgrad: Cin=%d Cout=%d", Cin, Cout);
-  BSED_REQUIRE(F >= 1 && F <= 64 && 64 % F == 0, "tc_wgrad: F=%d must divide 64", F);
-  BSED_REQUIRE(ntaps == 9 || ntaps == 1, "tc_wgrad: ntaps=%d", ntaps);
-  const int th = tc::kWP / F;
-  const int NCH = 32;
-  static int variant = -1;   // BSED_WGRAD_VARIANT=0: plain 128B swizzle (debug only; not a legal tf32 MN-major layout)
-  if (variant < 0) {
-    const char* e = getenv("BSED_WGRAD_VARIANT");
-    variant = e ? atoi(e) : 1;
-  }
-  const int sw = variant == 0 ? 128 : 132;
+// D[m][n][tap] (+)= sum_rows A[row][a.c0 + m] * Bm[row + shift(tap)][b.c0 + n]; element (m, n, tap) lands at
+// dW[m*rs + n*cs + tap*ts].  Rows are the pixels of a (Bn, T, Fv) grid, row stride ld floats.
+// mode: 0 = 9 conv taps, 1 = one tap (dt0), 2 = pixel-pair view of a 16-channel B operand (A.C = Cout,
+// operands passed in their pair views: A.ld = 2*Cout, Bm.ld = 32, Fv = F/2), 3 = 16-channel GLU reduction
+// (both operands in pair view, A.C = Bm.C = 32; dW is the 16 x 16 matrix).
+int tc_wgrad_ex(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int mode, int dt0, float* dW, long long rs,
+                long long cs, long long ts, float* part, size_t part_bytes, int sms, cudaStream_t st) {
+  BSED_REQUIRE(A.C % 32 == 0 && A.C >= 32 && Bm.C % 32 == 0 && Bm.C >= 32, "tc_wgrad: channels A=%d B=%d", A.C, Bm.C);
+  BSED_REQUIRE(Fv >= 1 && Fv <= 64 && 64 % Fv == 0, "tc_wgrad: F=%d must divide 64", Fv);
+  BSED_REQUIRE(A.ld % 4 == 0 && Bm.ld % 4 == 0, "tc_wgrad: leading dimensions must be multiples of 4");
+  const int kmode = mode == 3 ? tc::W_SINGLE : mode;
+  const int N = Bm.C >= 128 ? 128 : Bm.C;
+  BSED_REQUIRE(Bm.C % N == 0 && (N == 32 || N == 64 || N == 128), "tc_wgrad: B channels %d", Bm.C);
+  const int n_tiles_n = Bm.C / N, m_tiles = (A.C + 127) / 128;
+  const int ntaps = kmode == tc::W_CONV9 ? 9 : kmode == tc::W_PAIR ? 12 : 1;
+  const int th = tc::kWP / Fv;
   CUtensorMap mA, mB;
-  cuuint64_t dA[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t sA[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
-  cuuint32_t bA[4] = {32, (cuuint32_t)F, (cuuint32_t)th, 1};
-  BSED_TRY(tc::make_map(&mA, dY, 4, dA, sA, bA, sw));
-  cuuint64_t dB[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t sB[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
-  cuuint32_t bB[4] = {(cuuint32_t)NCH, (cuuint32_t)F, (cuuint32_t)th, 1};
-  BSED_TRY(tc::make_map(&mB, X, 4, dB, sB, bB, sw));
+  const int a_width = mode == 2 ? 2 * A.C : A.c0 + A.C;   // channels the A map must cover
+  cuuint64_t dA[4] = {(cuuint64_t)a_width, (cuuint64_t)Fv, (cuuint64_t)T, (cuuint64_t)Bn};
+  cuuint64_t sA[3] = {(cuuint64_t)A.ld * 4, (cuuint64_t)Fv * A.ld * 4, (cuuint64_t)T * Fv * A.ld * 4};
+  cuuint32_t bA[4] = {32, (cuuint32_t)Fv, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mA, A.p, 4, dA, sA, bA, 132));
+  cuuint64_t dB[4] = {(cuuint64_t)(Bm.c0 + Bm.C), (cuuint64_t)Fv, (cuuint64_t)T, (cuuint64_t)Bn};
+  cuuint64_t sB[3] = {(cuuint64_t)Bm.ld * 4, (cuuint64_t)Fv * Bm.ld * 4, (cuuint64_t)T * Fv * Bm.ld * 4};
+  cuuint32_t bB[4] = {32, (cuuint32_t)Fv, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mB, Bm.p, 4, dB, sB, bB, 132));
   tc::WArgs a;
-  a.layout = variant == 0 ? 2 : 1;
-  a.sbo = variant == 0 ? 1024 : 512;
   a.tiles_per_clip = (T + th - 1) / th;
-  a.n_tiles = a.tiles_per_clip * B;
+  a.n_tiles = a.tiles_per_clip * Bn;
   a.th = th;
   a.T = T;
-  a.F = F;
-  a.ntaps = ntaps;
-  a.a_chunks = Cout / 32;
-  int splits = sms / ntaps;
+  a.F = Fv;
+  a.mode = kmode;
+  a.dt0 = dt0;
+  a.a_c0 = A.c0;
+  a.b_c0 = Bm.c0;
+  a.m_total = A.C;
+  a.n_tiles_n = n_tiles_n;
+  a.pair_stride = A.C;
+  const int z = m_tiles * n_tiles_n;
+  int splits = sms / (ntaps * z);
   if (splits < 1) splits = 1;
   if (splits > a.n_tiles) splits = a.n_tiles;
   a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
   splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
-  size_t need = (size_t)splits * ntaps * 128 * Cin * sizeof(float);
+  size_t need = (size_t)splits * ntaps * z * 128 * N * sizeof(float);
   if (part_bytes < need) {
     bsed_set_error("tc_wgrad: workspace %zu < %zu", part_bytes, need);
     return BSED_E_WORKSPACE;
   }
-  ProfScope prof(PROF_WGRAD, 2.0 * B * T * F * Cout * (double)ntaps * Cin,
-                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + (double)ntaps * Cin * Cout), st);
+  const double rows = (double)Bn * T * Fv;
+  ProfScope prof(PROF_WGRAD, 2.0 * rows * A.C * (double)ntaps * Bm.C,
+                 4.0 * (rows * A.C + rows * Bm.C + (double)ntaps * A.C * Bm.C), st);
+  dim3 grid(splits, ntaps, z);
   int r;
-  switch (Cin) {
-    case 32: r = tc::launch_w<32>(mA, mB, part, a, splits, ntaps, st); break;
-    case 64: r = tc::launch_w<64>(mA, mB, part, a, splits, ntaps, st); break;
-    case 128: r = tc::launch_w<128>(mA, mB, part, a, splits, ntaps, st); break;
-    default: bsed_set_error("tc_wgrad: Cin=%d unsupported", Cin); return BSED_E_INVALID;
+  switch (N) {
+    case 32: r = tc::launch_w<32>(mA, mB, part, a, grid, st); break;
+    case 64: r = tc::launch_w<64>(mA, mB, part, a, grid, st); break;
+    default: r = tc::launch_w<128>(mA, mB, part, a, grid, st); break;
   }
   BSED_TRY(r);
-  int n = ntaps * Cout * Cin;
-  tc::wgrad_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(part, splits, ntaps, Cout, Cin, dW, rs, cs, ts);
+  tc::RArgs ra;
+  ra.splits = splits;
+  ra.ntaps = ntaps;
+  ra.ztiles = z;
+  ra.n_tiles_n = n_tiles_n;
+  ra.N = N;
+  ra.m_total = A.C;
+  ra.n_total = Bm.C;
+  ra.mode = mode;
+  ra.rs = rs;
+  ra.cs = cs;
+  ra.ts = ts;
+  const int n = mode == 2 ? 9 * A.C * 16 : mode == 3 ? 256 : ntaps * A.C * Bm.C;
+  tc::wgrad_reduce_kernel<<<ceil_div(n, 128), 128, 0, st>>>(part, ra, dW);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
+}
+
+// conv weight gradient: dW (+)= sum_p dY[p][co] * X[p + tap][ci] for the 9 taps (ntaps = 9) or the plain
+// product (ntaps = 1).  X [B][T][F][Cin], dY [B][T][F][Cout].  Cin = 16 goes through the pixel-pair view.
+int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long cs, long long ts, int B, int T, int F,
+             int Cin, int Cout, int ntaps, float* part, size_t part_bytes, int sms, cudaStream_t st) {
+  BSED_REQUIRE(ntaps == 9 || ntaps == 1, "tc_wgrad: ntaps=%d", ntaps);
+  BSED_REQUIRE(Cout % 32 == 0 && Cout <= 128 && Cin <= 128, "tc_wgrad: Cin=%d Cout=%d", Cin, Cout);
+  if (Cin == 16 && ntaps == 9) {
+    BSED_REQUIRE(F % 2 == 0, "tc_wgrad: pair view needs an even F (got %d)", F);
+    TcOperand A{dY, 2 * Cout, 0, Cout}, Bm{X, 32, 0, 32};
+    return tc_wgrad_ex(A, Bm, B, T, F / 2, 2, 0, dW, rs, cs, ts, part, part_bytes, sms, st);
+  }
+  BSED_REQUIRE(Cin % 32 == 0, "tc_wgrad: Cin=%d", Cin);
+  TcOperand A{dY, Cout, 0, Cout}, Bm{X, Cin, 0, Cin};
+  return tc_wgrad_ex(A, Bm, B, T, F, ntaps == 9 ? 0 : 1, 0, dW, rs, cs, ts, part, part_bytes, sms, st);
 }
 }  // namespace bsed
