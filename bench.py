@@ -249,21 +249,27 @@ def run_b200(args):
         cps_cpu, sec_cpu, threads = cpu_mean_teacher(2, 2, 2, 1)
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if trainer.plan.precision == "tf32" else "f32",
             "data": "synthetic",
             "config": {"workload": "mean-teacher CRNN training step (src/main.py:train_mt, pretrain -mt): per GPU 12 synthetic + "
                                    "12 real clips student fwd+bwd, 12 clips teacher fwd (train mode), BCE+MSE, Adam lr 5e-4, "
                                    "state-dict EMA; log-mel features 1255x128 resident in HBM",
+                       "precision": trainer.plan.precision + (" (tcgen05 kind::tf32 contractions, fp32 accumulate; everything "
+                                                              "else fp32)" if trainer.plan.precision == "tf32" else ""),
                        "clips_per_step_per_gpu": 24, "parallelism": f"dp{world} (NCCL sum all-reduce of the 4.47 MB flat gradient)",
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",
                        "step_gflop_algorithmic": STEP_FLOP / 1e9},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_timed),
-            "roofline": {"kernel": "gemm_nn_kernel<ConvRows> (implicit-GEMM 3x3 conv forward + data gradient, fp32 SIMT)",
+            "roofline": {"kernel": ("tc_kmajor_kernel (tcgen05 tf32 implicit-GEMM 3x3 conv forward + data gradient, TMA-fed)"
+                                    if trainer.plan.precision == "tf32" else
+                                    "gemm_nn_kernel<ConvRows> (implicit-GEMM 3x3 conv forward + data gradient, fp32 SIMT)"),
                          "bound": "tensor", "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None, "traffic": None,
-                         "peak_source": peaks["source"] + " bf16 sustained", "launches": pn.value,
+                         "peak_source": peaks["source"] + " bf16 sustained (tf32 nominal dense peak is half of bf16)",
+                         "launches": pn.value,
                          "share_of_step": pm.value / ms if ms else None,
                          "step_tflops": STEP_FLOP * args.steps / (ms * 1e-3) / 1e12},
             "frontend": {"metric": "log-mel frontend", "clips_per_s": fe_cps, "algorithmic_GBps": fe_cps * CLIP_BYTES_FRONTEND / 1e9,
