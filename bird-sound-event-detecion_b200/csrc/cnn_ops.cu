@@ -165,17 +165,27 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   if (rend > rows_per_clip) rend = rows_per_clip;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   if (r0 < rstep) {
-    for (long long r = rbeg + r0; r < rend; r += rstep) {
-      size_t off = ((size_t)clip * rows_per_clip + r) * C + q * 4;
-      float4 av = *reinterpret_cast<const float4*>(a + off);
-      s1.x += av.x; s1.y += av.y; s1.z += av.z; s1.w += av.w;
-      if (MODE == 0) {
-        s2.x = fmaf(av.x, av.x, s2.x); s2.y = fmaf(av.y, av.y, s2.y);
-        s2.z = fmaf(av.z, av.z, s2.z); s2.w = fmaf(av.w, av.w, s2.w);
-      } else if (MODE == 1) {
-        float4 bv = *reinterpret_cast<const float4*>(b + off);
-        s2.x = fmaf(av.x, bv.x, s2.x); s2.y = fmaf(av.y, bv.y, s2.y);
-        s2.z = fmaf(av.z, bv.z, s2.z); s2.w = fmaf(av.w, bv.w, s2.w);
+    constexpr int U = 4;   // rows in flight per thread
+    const float* abase = a + (size_t)clip * rows_per_clip * C + q * 4;
+    const float* bbase = MODE == 1 ? b + (size_t)clip * rows_per_clip * C + q * 4 : nullptr;
+    for (long long r = rbeg + r0; r < rend; r += (long long)U * rstep) {
+      float4 av[U], bv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        long long rr = r + (long long)u * rstep;
+        av[u] = rr < rend ? *reinterpret_cast<const float4*>(abase + (size_t)rr * C) : make_float4(0, 0, 0, 0);
+        if (MODE == 1) bv[u] = rr < rend ? *reinterpret_cast<const float4*>(bbase + (size_t)rr * C) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s1.x += av[u].x; s1.y += av[u].y; s1.z += av[u].z; s1.w += av[u].w;
+        if (MODE == 0) {
+          s2.x = fmaf(av[u].x, av[u].x, s2.x); s2.y = fmaf(av[u].y, av[u].y, s2.y);
+          s2.z = fmaf(av[u].z, av[u].z, s2.z); s2.w = fmaf(av[u].w, av[u].w, s2.w);
+        } else if (MODE == 1) {
+          s2.x = fmaf(av[u].x, bv[u].x, s2.x); s2.y = fmaf(av[u].y, bv[u].y, s2.y);
+          s2.z = fmaf(av[u].z, bv[u].z, s2.z); s2.w = fmaf(av[u].w, bv[u].w, s2.w);
+        }
       }
     }
   }
@@ -303,23 +313,34 @@ int bn_prepare_eval(const Groups& g, int C, float eps, const BNPtrs& bn, float* 
   return BSED_OK;
 }
 
-// in place y -> xhat = (y - mean) * rstd ; grid (chunks, clip)
+// in place y -> xhat = (y - mean) * rstd ; grid (chunks, clip); kEltU float4 per thread, loads issued first
+constexpr int kEltU = 4;
 __global__ void __launch_bounds__(256) bn_normalize_kernel(float* __restrict__ y, Groups g, long long elems_per_clip,
                                                            int C, BNPtrs bn) {
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
-  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 * 4 >= elems_per_clip) return;
-  int c = (int)((i4 * 4) % C);
-  float4* p = reinterpret_cast<float4*>(y + (size_t)clip * elems_per_clip) + i4;
-  float4 v = *p;
-  const float* mu = bn.mean[grp] + c;
-  const float* rs = bn.rstd[grp] + c;
-  v.x = (v.x - mu[0]) * rs[0];
-  v.y = (v.y - mu[1]) * rs[1];
-  v.z = (v.z - mu[2]) * rs[2];
-  v.w = (v.w - mu[3]) * rs[3];
-  *p = v;
+  const long long n4 = elems_per_clip / 4;
+  const long long base = (long long)blockIdx.x * (256 * kEltU) + threadIdx.x;
+  float4* p = reinterpret_cast<float4*>(y + (size_t)clip * elems_per_clip);
+  float4 v[kEltU];
+#pragma unroll
+  for (int u = 0; u < kEltU; ++u) {
+    long long i4 = base + u * 256;
+    if (i4 < n4) v[u] = p[i4];
+  }
+#pragma unroll
+  for (int u = 0; u < kEltU; ++u) {
+    long long i4 = base + u * 256;
+    if (i4 >= n4) continue;
+    int c = (int)((i4 * 4) % C);
+    const float4 mu = *reinterpret_cast<const float4*>(bn.mean[grp] + c);
+    const float4 rs = *reinterpret_cast<const float4*>(bn.rstd[grp] + c);
+    v[u].x = (v[u].x - mu.x) * rs.x;
+    v[u].y = (v[u].y - mu.y) * rs.y;
+    v[u].z = (v[u].z - mu.z) * rs.z;
+    v[u].w = (v[u].w - mu.w) * rs.w;
+    p[i4] = v[u];
+  }
 }
 
 static int total_clips(const Groups& g) {
@@ -331,7 +352,7 @@ static int total_clips(const Groups& g) {
 int bn_normalize(float* y, const Groups& g, long long rows_per_clip, int C, const BNPtrs& bn,
                  cudaStream_t st) {
   long long elems = rows_per_clip * C;
-  dim3 grid(ceil_div(elems / 4, 256), total_clips(g));
+  dim3 grid(ceil_div(elems / 4, 256 * kEltU), total_clips(g));
   bn_normalize_kernel<<<grid, 256, 0, st>>>(y, g, elems, C, bn);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
@@ -341,11 +362,13 @@ int bn_normalize(float* y, const Groups& g, long long rows_per_clip, int C, cons
 // GLU gate + dropout + average pool
 //   out = lin * sigmoid(gamma * xhat + beta) * keep / (1 - p), averaged over the pt x pf window
 // ---------------------------------------------------------------------------------------------
+template <int PT, int PF>
 __global__ void __launch_bounds__(256) glu_gate_pool_fwd_kernel(const float* __restrict__ xhat,
                                                                 const float* __restrict__ lin,
                                                                 float* __restrict__ pooled, Groups g, BNPtrs bn,
-                                                                int T, int F, int C, int pt, int pf, int To, int Fo,
+                                                                int T, int F, int C, int pt_rt, int pf_rt, int To, int Fo,
                                                                 uint32_t key, uint32_t thresh, float inv_keep) {
+  const int pt = PT ? PT : pt_rt, pf = PF ? PF : pf_rt;
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
   const int nq = C / 4;
@@ -355,29 +378,41 @@ __global__ void __launch_bounds__(256) glu_gate_pool_fwd_kernel(const float* __r
   int opix = (int)(id / nq);
   int fo = opix % Fo, to = opix / Fo;
   int c = q * 4;
-  float ga[4], be[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    ga[j] = bn.gamma[grp][c + j];
-    be[j] = bn.beta[grp][c + j];
-  }
+  const float4 ga4 = *reinterpret_cast<const float4*>(bn.gamma[grp] + c);
+  const float4 be4 = *reinterpret_cast<const float4*>(bn.beta[grp] + c);
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int dt = 0; dt < pt; ++dt)
-    for (int df = 0; df < pf; ++df) {
-      int t = to * pt + dt, f = fo * pf + df;
-      size_t e = (((size_t)clip * T + t) * F + f) * C + c;
-      float4 xv = *reinterpret_cast<const float4*>(xhat + e);
-      float4 lv = *reinterpret_cast<const float4*>(lin + e);
-      float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      float ls[4] = {lv.x, lv.y, lv.z, lv.w};
+  auto body = [&](size_t e, const float4& xv, const float4& lv) {
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float ls[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float s = sigmoidf_(fmaf(ga[j], xs[j], be[j]));
-        float o = ls[j] * s;
-        if (thresh) o = bsed_keep((uint32_t)(e + j), key, thresh) ? o * inv_keep : 0.f;
-        acc[j] += o;
-      }
+    for (int j = 0; j < 4; ++j) {
+      float s = sigmoidf_(fmaf(ga[j], xs[j], be[j]));
+      float o = ls[j] * s;
+      if (thresh) o = bsed_keep((uint32_t)(e + j), key, thresh) ? o * inv_keep : 0.f;
+      acc[j] += o;
     }
+  };
+  if (PT && PF) {
+    float4 xv[PT ? PT * PF : 1], lv[PT ? PT * PF : 1];
+#pragma unroll
+    for (int w = 0; w < PT * PF; ++w) {
+      size_t e = (((size_t)clip * T + to * PT + w / (PF ? PF : 1)) * F + fo * PF + w % (PF ? PF : 1)) * C + c;
+      xv[w] = *reinterpret_cast<const float4*>(xhat + e);
+      lv[w] = *reinterpret_cast<const float4*>(lin + e);
+    }
+#pragma unroll
+    for (int w = 0; w < PT * PF; ++w) {
+      size_t e = (((size_t)clip * T + to * PT + w / (PF ? PF : 1)) * F + fo * PF + w % (PF ? PF : 1)) * C + c;
+      body(e, xv[w], lv[w]);
+    }
+  } else {
+    for (int dt = 0; dt < pt; ++dt)
+      for (int df = 0; df < pf; ++df) {
+        size_t e = (((size_t)clip * T + to * pt + dt) * F + fo * pf + df) * C + c;
+        body(e, *reinterpret_cast<const float4*>(xhat + e), *reinterpret_cast<const float4*>(lin + e));
+      }
+  }
   float inv = 1.0f / (float)(pt * pf);
   float4 o = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
   *reinterpret_cast<float4*>(pooled + (((size_t)clip * To + to) * Fo + fo) * C + c) = o;
@@ -389,8 +424,12 @@ int glu_gate_pool_fwd(const float* xhat, const float* lin, float* pooled, const 
   int To = T / pt, Fo = F / pf;
   long long work = (long long)To * Fo * (C / 4);
   dim3 grid(ceil_div(work, 256), total_clips(g));
-  glu_gate_pool_fwd_kernel<<<grid, 256, 0, st>>>(xhat, lin, pooled, g, bn, T, F, C, pt, pf, To, Fo, key, thresh,
-                                                 inv_keep);
+  if (pt == 2 && pf == 2)
+    glu_gate_pool_fwd_kernel<2, 2><<<grid, 256, 0, st>>>(xhat, lin, pooled, g, bn, T, F, C, pt, pf, To, Fo, key, thresh, inv_keep);
+  else if (pt == 1 && pf == 2)
+    glu_gate_pool_fwd_kernel<1, 2><<<grid, 256, 0, st>>>(xhat, lin, pooled, g, bn, T, F, C, pt, pf, To, Fo, key, thresh, inv_keep);
+  else
+    glu_gate_pool_fwd_kernel<0, 0><<<grid, 256, 0, st>>>(xhat, lin, pooled, g, bn, T, F, C, pt, pf, To, Fo, key, thresh, inv_keep);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -405,36 +444,52 @@ __global__ void __launch_bounds__(256) glu_gate_pool_bwd_kernel(const float* __r
                                                                 float* __restrict__ dxn, Groups g, BNPtrs bn, int T,
                                                                 int F, int C, int pt, int pf, int To, int Fo,
                                                                 uint32_t key, uint32_t thresh, float inv_keep) {
+  constexpr int U = 2;   // quads per thread, loads issued first
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
   const int nq = C / 4;
-  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= (long long)T * F * nq) return;
-  int q = (int)(id % nq);
-  int pix = (int)(id / nq);
-  int f = pix % F, t = pix / F;
-  int c = q * 4;
-  size_t e = (((size_t)clip * T + t) * F + f) * C + c;
-  int to = t / pt, fo = f / pf;
-  float4 gv = make_float4(0, 0, 0, 0);
-  if (to < To && fo < Fo) gv = *reinterpret_cast<const float4*>(dpooled + (((size_t)clip * To + to) * Fo + fo) * C + c);
-  float4 xv = *reinterpret_cast<const float4*>(xhat + e);
-  float4 lv = *reinterpret_cast<const float4*>(lin_dlin + e);
-  float gs[4] = {gv.x, gv.y, gv.z, gv.w};
-  float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-  float ls[4] = {lv.x, lv.y, lv.z, lv.w};
-  float inv = 1.0f / (float)(pt * pf);
-  float dl[4], dx[4];
+  const long long total = (long long)T * F * nq;
+  const long long base = (long long)blockIdx.x * (256 * U) + threadIdx.x;
+  const float inv = 1.0f / (float)(pt * pf);
+  float4 gv[U], xv[U], lv[U];
+  size_t e[U];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float gg = gs[j] * inv;
-    if (thresh) gg = bsed_keep((uint32_t)(e + j), key, thresh) ? gg * inv_keep : 0.f;
-    float s = sigmoidf_(fmaf(bn.gamma[grp][c + j], xs[j], bn.beta[grp][c + j]));
-    dl[j] = gg * s;
-    dx[j] = gg * ls[j] * s * (1.f - s);
+  for (int u = 0; u < U; ++u) {
+    long long id = base + u * 256;
+    if (id >= total) continue;
+    int q = (int)(id % nq);
+    int pix = (int)(id / nq);
+    int f = pix % F, t = pix / F;
+    e[u] = (((size_t)clip * T + t) * F + f) * C + q * 4;
+    int to = t / pt, fo = f / pf;
+    gv[u] = make_float4(0, 0, 0, 0);
+    if (to < To && fo < Fo) gv[u] = *reinterpret_cast<const float4*>(dpooled + (((size_t)clip * To + to) * Fo + fo) * C + q * 4);
+    xv[u] = *reinterpret_cast<const float4*>(xhat + e[u]);
+    lv[u] = *reinterpret_cast<const float4*>(lin_dlin + e[u]);
   }
-  *reinterpret_cast<float4*>(lin_dlin + e) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-  *reinterpret_cast<float4*>(dxn + e) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    long long id = base + u * 256;
+    if (id >= total) continue;
+    const int c = (int)(id % nq) * 4;
+    const float4 ga4 = *reinterpret_cast<const float4*>(bn.gamma[grp] + c);
+    const float4 be4 = *reinterpret_cast<const float4*>(bn.beta[grp] + c);
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    float gs[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+    float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+    float ls[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+    float dl[4], dx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gg = gs[j] * inv;
+      if (thresh) gg = bsed_keep((uint32_t)(e[u] + j), key, thresh) ? gg * inv_keep : 0.f;
+      float s = sigmoidf_(fmaf(ga[j], xs[j], be[j]));
+      dl[j] = gg * s;
+      dx[j] = gg * ls[j] * s * (1.f - s);
+    }
+    *reinterpret_cast<float4*>(lin_dlin + e[u]) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+    *reinterpret_cast<float4*>(dxn + e[u]) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+  }
 }
 
 int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
@@ -442,7 +497,7 @@ int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, 
                       float inv_keep, cudaStream_t st) {
   int To = T / pt, Fo = F / pf;
   long long work = (long long)T * F * (C / 4);
-  dim3 grid(ceil_div(work, 256), total_clips(g));
+  dim3 grid(ceil_div(work, 256 * 2), total_clips(g));
   glu_gate_pool_bwd_kernel<<<grid, 256, 0, st>>>(xhat, lin_dlin, dpooled, dxn, g, bn, T, F, C, pt, pf, To, Fo,
                                                  key, thresh, inv_keep);
   BSED_CHECK_LAUNCH();
@@ -456,29 +511,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            BNPtrs bn) {
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
-  long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 * 4 >= elems_per_clip) return;
-  int c = (int)((i4 * 4) % C);
-  float invn = 1.0f / ((float)g.count[grp] * (float)rows_per_clip);
-  size_t off = (size_t)clip * elems_per_clip + i4 * 4;
-  float4 d = *reinterpret_cast<float4*>(dxn + off);
-  float4 xh = *reinterpret_cast<const float4*>(xhat + off);
-  float dv[4] = {d.x, d.y, d.z, d.w};
-  float xs[4] = {xh.x, xh.y, xh.z, xh.w};
+  const long long n4 = elems_per_clip / 4;
+  const long long base = (long long)blockIdx.x * (256 * kEltU) + threadIdx.x;
+  const float invn = 1.0f / ((float)g.count[grp] * (float)rows_per_clip);
+  float4* pd = reinterpret_cast<float4*>(dxn + (size_t)clip * elems_per_clip);
+  const float4* px = reinterpret_cast<const float4*>(xhat + (size_t)clip * elems_per_clip);
+  float4 d[kEltU], xh[kEltU];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float s1 = (float)stats2[((size_t)grp * C + c + j) * 2] * invn;
-    float s2 = (float)stats2[((size_t)grp * C + c + j) * 2 + 1] * invn;
-    float k = bn.gamma[grp][c + j] * bn.rstd[grp][c + j];
-    dv[j] = k * (dv[j] - s1 - xs[j] * s2);
+  for (int u = 0; u < kEltU; ++u) {
+    long long i4 = base + u * 256;
+    if (i4 < n4) {
+      d[u] = pd[i4];
+      xh[u] = px[i4];
+    }
   }
-  *reinterpret_cast<float4*>(dxn + off) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+#pragma unroll
+  for (int u = 0; u < kEltU; ++u) {
+    long long i4 = base + u * 256;
+    if (i4 >= n4) continue;
+    int c = (int)((i4 * 4) % C);
+    float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+    float xs[4] = {xh[u].x, xh[u].y, xh[u].z, xh[u].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s1 = (float)stats2[((size_t)grp * C + c + j) * 2] * invn;
+      float s2 = (float)stats2[((size_t)grp * C + c + j) * 2 + 1] * invn;
+      float k = bn.gamma[grp][c + j] * bn.rstd[grp][c + j];
+      dv[j] = k * (dv[j] - s1 - xs[j] * s2);
+    }
+    pd[i4] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  }
 }
 
 int bn_bwd_apply(float* dxn_dy, const float* xhat, const double* stats2, const Groups& g,
                  long long rows_per_clip, int C, const BNPtrs& bn, cudaStream_t st) {
   long long elems = rows_per_clip * C;
-  dim3 grid(ceil_div(elems / 4, 256), total_clips(g));
+  dim3 grid(ceil_div(elems / 4, 256 * kEltU), total_clips(g));
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dxn_dy, xhat, stats2, g, elems, rows_per_clip, C, bn);
   BSED_CHECK_LAUNCH();
   return BSED_OK;

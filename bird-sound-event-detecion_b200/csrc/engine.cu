@@ -713,8 +713,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(bn_glu_param_grads(stats2, n, L.Cout, params + pl.bn_w[i], params + pl.bn_b[i], G, dscr,
                                 grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i], grads + pl.glu_b[i], st));
     BSED_TRY(bn_bwd_apply(dxn, xhat, stats2, gb, L.rows, L.Cout, bn, st));
-    // conv bias gradient
-    BSED_TRY(col_sum_to(dxn + off, M, L.Cout, grads + pl.conv_b[i], dscr, sms, st));
+    // conv bias gradient: sum_p dY = gamma*rstd*(sum dxn - n*mean(dxn) - mean(dxn*xhat) * sum xhat) = 0 exactly behind a
+    // train-mode BatchNorm (the reference computes rounding noise here); grads[conv_b] keeps its zero / accumulated value
     if (i > 0) {
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]) + (size_t)first * L.rows * L.Cin;
       const bool tc_w32 = L.Cin % 32 == 0 && L.F <= 64 && 64 % L.F == 0;

@@ -40,23 +40,33 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
   for (int k = 0; k < kH; ++k) w[k] = WT[(size_t)k * kG + j];
   const float bj = bhh.p[grp][dir * kG + j];
 
-  __shared__ __align__(16) float h_s[kH];
+  __shared__ __align__(16) float h_s[2][kH];   // double-buffered hidden state: two barriers per step
   __shared__ float gates_s[kG];
-  if (j < kH) h_s[j] = 0.f;
+  if (j < kH) h_s[0][j] = 0.f;
   __syncthreads();
 
+  // the input projections of step s + 1 are fetched while step s computes (their latency would otherwise sit on
+  // the 313-step critical path)
+  auto xrow = [&](int step) { return (size_t)clip * T + (dir == 0 ? step : T - 1 - step); };
+  float nxr = 0.f, nxz = 0.f, nxn = 0.f;
+  if (j < kH) {
+    const float* xb = xg + xrow(0) * (2 * kG) + dir * kG;
+    nxr = xb[j];
+    nxz = xb[kH + j];
+    nxn = xb[2 * kH + j];
+  }
+  int buf = 0;
   for (int step = 0; step < T; ++step) {
-    const int t = dir == 0 ? step : T - 1 - step;
-    const size_t row = (size_t)clip * T + t;
-    float xr = 0.f, xz = 0.f, xn = 0.f;
-    if (j < kH) {
-      const float* xb = xg + row * (2 * kG) + dir * kG;
-      xr = xb[j];
-      xz = xb[kH + j];
-      xn = xb[2 * kH + j];
+    const size_t row = xrow(step);
+    const float xr = nxr, xz = nxz, xn = nxn;
+    if (j < kH && step + 1 < T) {
+      const float* xb = xg + xrow(step + 1) * (2 * kG) + dir * kG;
+      nxr = xb[j];
+      nxz = xb[kH + j];
+      nxn = xb[2 * kH + j];
     }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float4* h4 = reinterpret_cast<const float4*>(h_s);
+    const float4* h4 = reinterpret_cast<const float4*>(h_s[buf]);
 #pragma unroll
     for (int k4 = 0; k4 < kH / 4; ++k4) {
       float4 hv = h4[k4];
@@ -67,14 +77,14 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
     }
     gates_s[j] = (a0 + a1) + (a2 + a3) + bj;
     __syncthreads();
-    float hnew = 0.f;
     if (j < kH) {
       float r = sigmoid_acc(xr + gates_s[j]);
       float z = sigmoid_acc(xz + gates_s[kH + j]);
       float hn = gates_s[2 * kH + j];
       float n = tanhf(fmaf(r, hn, xn));
-      float hold = h_s[j];
-      hnew = (1.f - z) * n + z * hold;
+      float hold = h_s[buf][j];
+      float hnew = (1.f - z) * n + z * hold;
+      h_s[buf ^ 1][j] = hnew;
       size_t o = row * (2 * kH) + dir * kH + j;
       out[o] = hnew;
       if (enc) {
@@ -91,8 +101,7 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
       }
     }
     __syncthreads();
-    if (j < kH) h_s[j] = hnew;
-    __syncthreads();
+    buf ^= 1;
   }
 }
 
@@ -130,19 +139,40 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
   __shared__ float part_s[3][kH];
   float dh_carry = 0.f;
 
+  // operands of the next step are fetched one step ahead (see gru_fwd_kernel)
+  struct StepIn {
+    float dout, r, z, n, hn, hprev;
+  };
+  auto fetch = [&](int step) {
+    StepIn v;
+    const int s = T - 1 - step;
+    const int t = dir == 0 ? s : T - 1 - s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    const size_t row = (size_t)clip * T + t;
+    v.dout = dout[row * (2 * kH) + dir * kH + i];
+    const float* sv = saved + (row * 2 + dir) * (4 * kH);
+    v.r = sv[i];
+    v.z = sv[kH + i];
+    v.n = sv[2 * kH + i];
+    v.hn = sv[3 * kH + i];
+    v.hprev = s > 0 ? out[((size_t)clip * T + tp) * (2 * kH) + dir * kH + i] : 0.f;
+    return v;
+  };
+  StepIn nxt = {};
+  if (gs == 0) nxt = fetch(0);
+
   for (int step = 0; step < T; ++step) {
     const int s = T - 1 - step;                 // forward step being undone
     const int t = dir == 0 ? s : T - 1 - s;
-    const int tp = dir == 0 ? t - 1 : t + 1;    // time index of h_{prev}
     const size_t row = (size_t)clip * T + t;
     float dh_z = 0.f;
     if (gs == 0) {
-      float dh = dh_carry + dout[row * (2 * kH) + dir * kH + i];
-      const float* sv = saved + (row * 2 + dir) * (4 * kH);
-      float r = sv[i], z = sv[kH + i], n = sv[2 * kH + i], hn = sv[3 * kH + i];
-      float hprev = s > 0 ? out[((size_t)clip * T + tp) * (2 * kH) + dir * kH + i] : 0.f;
+      const StepIn c = nxt;
+      if (step + 1 < T) nxt = fetch(step + 1);
+      float dh = dh_carry + c.dout;
+      float r = c.r, z = c.z, n = c.n, hn = c.hn;
       float dn = dh * (1.f - z);
-      float dz = dh * (hprev - n);
+      float dz = dh * (c.hprev - n);
       float dnp = dn * (1.f - n * n);
       float drp = dnp * hn * r * (1.f - r);
       float dzp = dz * z * (1.f - z);
