@@ -41,30 +41,21 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
   const float bj = bhh.p[grp][dir * kG + j];
 
   __shared__ __align__(16) float h_s[2][kH];   // double-buffered hidden state: two barriers per step
-  __shared__ float gates_s[kG];
+  __shared__ float gates_s[kG];                // r, z (after the sigmoid) and W_hn h + b_hn
   if (j < kH) h_s[0][j] = 0.f;
   __syncthreads();
 
-  // the input projections of step s + 1 are fetched while step s computes (their latency would otherwise sit on
-  // the 313-step critical path)
+  // Thread j owns gate row j end to end: its input projection x_j (fetched one step ahead, so the load latency is
+  // off the 313-step critical path), its recurrent dot product, and -- for the r and z rows -- the sigmoid, so that
+  // after the barrier only tanh and the blend remain (done by the 128 threads of the n rows).
   auto xrow = [&](int step) { return (size_t)clip * T + (dir == 0 ? step : T - 1 - step); };
-  float nxr = 0.f, nxz = 0.f, nxn = 0.f;
-  if (j < kH) {
-    const float* xb = xg + xrow(0) * (2 * kG) + dir * kG;
-    nxr = xb[j];
-    nxz = xb[kH + j];
-    nxn = xb[2 * kH + j];
-  }
+  float nx = xg[xrow(0) * (2 * kG) + dir * kG + j];
+  const int u = j - 2 * kH;                    // hidden unit of an n-row thread
   int buf = 0;
   for (int step = 0; step < T; ++step) {
     const size_t row = xrow(step);
-    const float xr = nxr, xz = nxz, xn = nxn;
-    if (j < kH && step + 1 < T) {
-      const float* xb = xg + xrow(step + 1) * (2 * kG) + dir * kG;
-      nxr = xb[j];
-      nxz = xb[kH + j];
-      nxn = xb[2 * kH + j];
-    }
+    const float x = nx;
+    if (step + 1 < T) nx = xg[xrow(step + 1) * (2 * kG) + dir * kG + j];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float4* h4 = reinterpret_cast<const float4*>(h_s[buf]);
 #pragma unroll
@@ -75,29 +66,30 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
       a2 = fmaf(w[4 * k4 + 2], hv.z, a2);
       a3 = fmaf(w[4 * k4 + 3], hv.w, a3);
     }
-    gates_s[j] = (a0 + a1) + (a2 + a3) + bj;
+    const float acc = (a0 + a1) + (a2 + a3) + bj;
+    float* sv = saved ? saved + (row * 2 + dir) * (4 * kH) : nullptr;
+    if (j < 2 * kH) {
+      const float sg = sigmoid_acc(x + acc);
+      gates_s[j] = sg;
+      if (sv) sv[j] = sg;                      // r at [0,128), z at [128,256)
+    }
     __syncthreads();
-    if (j < kH) {
-      float r = sigmoid_acc(xr + gates_s[j]);
-      float z = sigmoid_acc(xz + gates_s[kH + j]);
-      float hn = gates_s[2 * kH + j];
-      float n = tanhf(fmaf(r, hn, xn));
-      float hold = h_s[buf][j];
-      float hnew = (1.f - z) * n + z * hold;
-      h_s[buf ^ 1][j] = hnew;
-      size_t o = row * (2 * kH) + dir * kH + j;
+    if (j >= 2 * kH) {
+      const float r = gates_s[u], z = gates_s[kH + u];
+      const float n = tanhf(fmaf(r, acc, x));
+      const float hold = h_s[buf][u];
+      const float hnew = (1.f - z) * n + z * hold;
+      h_s[buf ^ 1][u] = hnew;
+      size_t o = row * (2 * kH) + dir * kH + u;
       out[o] = hnew;
       if (enc) {
         float e = hnew;
         if (thresh) e = bsed_keep((uint32_t)o, key, thresh) ? e * inv_keep : 0.f;
         enc[o] = e;
       }
-      if (saved) {
-        float* sv = saved + (row * 2 + dir) * (4 * kH);
-        sv[j] = r;
-        sv[kH + j] = z;
-        sv[2 * kH + j] = n;
-        sv[3 * kH + j] = hn;
+      if (sv) {
+        sv[2 * kH + u] = n;
+        sv[3 * kH + u] = acc;
       }
     }
     __syncthreads();
@@ -137,29 +129,37 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
 
   __shared__ __align__(16) float dg_s[kG];
   __shared__ float part_s[3][kH];
+  // operands of the coming steps (r, z, n, W_hn h + b_hn, d_out, h_prev: 6 x 128 floats = 192 16-byte chunks per
+  // step) are staged through shared memory kRing - 1 steps ahead with cp.async: the DRAM latency of these cold
+  // tensors (~1 us, longer than one step) stays off the critical path without spending registers
+  constexpr int kRing = 8;
+  __shared__ __align__(16) float ring[kRing][6 * kH];
   float dh_carry = 0.f;
+  const int tid = threadIdx.x;
 
-  // operands of the next step are fetched one step ahead (see gru_fwd_kernel)
-  struct StepIn {
-    float dout, r, z, n, hn, hprev;
+  auto issue = [&](int step) {
+    if (step < T && tid < 192) {
+      const int s = T - 1 - step;
+      const int t = dir == 0 ? s : T - 1 - s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const size_t row = (size_t)clip * T + t;
+      const float* src;
+      bool valid = true;
+      if (tid < 128) {
+        src = saved + (row * 2 + dir) * (4 * kH) + tid * 4;
+      } else if (tid < 160) {
+        src = dout + row * (2 * kH) + dir * kH + (tid - 128) * 4;
+      } else {
+        valid = s > 0;
+        src = valid ? out + ((size_t)clip * T + tp) * (2 * kH) + dir * kH + (tid - 160) * 4 : out;
+      }
+      cp_async16(&ring[step % kRing][tid * 4], src, valid);
+    }
+    cp_async_commit();
   };
-  auto fetch = [&](int step) {
-    StepIn v;
-    const int s = T - 1 - step;
-    const int t = dir == 0 ? s : T - 1 - s;
-    const int tp = dir == 0 ? t - 1 : t + 1;
-    const size_t row = (size_t)clip * T + t;
-    v.dout = dout[row * (2 * kH) + dir * kH + i];
-    const float* sv = saved + (row * 2 + dir) * (4 * kH);
-    v.r = sv[i];
-    v.z = sv[kH + i];
-    v.n = sv[2 * kH + i];
-    v.hn = sv[3 * kH + i];
-    v.hprev = s > 0 ? out[((size_t)clip * T + tp) * (2 * kH) + dir * kH + i] : 0.f;
-    return v;
-  };
-  StepIn nxt = {};
-  if (gs == 0) nxt = fetch(0);
+  for (int p = 0; p < kRing - 1; ++p) issue(p);
+  cp_async_wait<kRing - 2>();
+  __syncthreads();
 
   for (int step = 0; step < T; ++step) {
     const int s = T - 1 - step;                 // forward step being undone
@@ -167,12 +167,11 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
     const size_t row = (size_t)clip * T + t;
     float dh_z = 0.f;
     if (gs == 0) {
-      const StepIn c = nxt;
-      if (step + 1 < T) nxt = fetch(step + 1);
-      float dh = dh_carry + c.dout;
-      float r = c.r, z = c.z, n = c.n, hn = c.hn;
+      const float* c = ring[step % kRing];
+      float dh = dh_carry + c[4 * kH + i];
+      float r = c[i], z = c[kH + i], n = c[2 * kH + i], hn = c[3 * kH + i];
       float dn = dh * (1.f - z);
-      float dz = dh * (c.hprev - n);
+      float dz = dh * (c[5 * kH + i] - n);
       float dnp = dn * (1.f - n * n);
       float drp = dnp * hn * r * (1.f - r);
       float dzp = dz * z * (1.f - z);
@@ -191,6 +190,7 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
       dh_z = dh * z;
     }
     __syncthreads();
+    issue(step + kRing - 1);                    // refills the slot consumed in the previous step
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float4* d4 = reinterpret_cast<const float4*>(dg_s + gs * kH);
 #pragma unroll
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
       a3 = fmaf(w[4 * k4 + 3], dv.w, a3);
     }
     part_s[gs][i] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
+    cp_async_wait<kRing - 2>();                 // the group of step + 1 has landed (for this thread) ...
+    __syncthreads();                            // ... and for every thread
     if (gs == 0) dh_carry = dh_z + part_s[0][i] + part_s[1][i] + part_s[2][i];
   }
 }
