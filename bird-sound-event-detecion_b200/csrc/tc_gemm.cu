@@ -55,6 +55,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();
   }
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {   // explicit shared-space load (a generic LD costs a long scoreboard)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -153,6 +158,7 @@ struct KArgs {
   int ntaps, cpt;      // taps (9 or 1), k-chunks per tap
   int ldc;
   int accumulate;
+  int debug;           // BSED_TC_DEBUG (measurement experiments only): 1 = skip the epilogue's global stores
 };
 
 template <int N, int KCH, int STAGES>
@@ -161,7 +167,9 @@ struct KSmem {
   static constexpr int B_BYTES = N * KCH * 4;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE = A_BYTES + B_STRIDE;
-  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 4 mbarriers + the TMEM slot
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/;
+  static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
 template <int N, int KCH, int STAGES>
@@ -179,6 +187,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(smem + STAGES * S::STAGE + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -194,6 +203,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     fence_barrier_init();
   }
+  if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -285,49 +295,40 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         valid = in_clip < (long long)a.T * a.F;
         grow = (long long)b * a.T * a.F + in_clip;
       }
+      // C values of the upcoming column chunk (accumulate mode) are requested before the accumulator is awaited, and
+      // the next chunk's while the current one is combined: their latency overlaps the MMAs / the TMEM loads
+      constexpr int CW = N >= 32 ? 32 : 16;       // columns per chunk
+      const uint32_t sbias_addr = smem_u32(sbias);
+      float* yrow = Y + grow * a.ldc;
+      const bool acc_rd = a.accumulate && valid;
+      float4 cpre[CW / 4];
+      if (acc_rd) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+      }
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * N + ((uint32_t)(q * 32) << 16);
-      float* yrow = Y + grow * a.ldc;
-      if constexpr (N >= 32) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          if (valid) {
+      for (int c0 = 0; c0 < N; c0 += CW) {
+        float v[CW];
+        if constexpr (CW == 32) tmem_ld32(taddr + c0, v);
+        else tmem_ld16(taddr + c0, v);
+        float4 ccur[CW / 4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (bias) {
-                float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              }
-              float4* dst = reinterpret_cast<float4*>(yrow + c0 + j);
-              if (a.accumulate) {
-                float4 c = *dst;
-                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-              }
-              *dst = o;
-            }
-          }
+        for (int j = 0; j < CW / 4; ++j) ccur[j] = acc_rd ? cpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (acc_rd && c0 + CW < N) {
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
         }
-      } else {
-        float v[16];
-        tmem_ld16(taddr, v);
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (bias) {
-              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            }
-            float4* dst = reinterpret_cast<float4*>(yrow + j);
-            if (a.accumulate) {
-              float4 c = *dst;
-              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-            }
-            *dst = o;
+          for (int j = 0; j < CW; j += 4) {
+            const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
+            const float4 cv = ccur[j / 4];
+            float4 o = make_float4(v[j] + bv.x + cv.x, v[j + 1] + bv.y + cv.y, v[j + 2] + bv.z + cv.z,
+                                   v[j + 3] + bv.w + cv.w);
+            if (a.debug != 1 || o.x == 12345.678f) *reinterpret_cast<float4*>(yrow + c0 + j) = o;
           }
         }
       }
@@ -386,7 +387,10 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 template <int N, int KCH>
 static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, float* Y, const float* bias, const KArgs& a, int sms,
                     cudaStream_t st) {
-  constexpr int STAGES = (N >= 128 && KCH == 32) ? 6 : 8;
+  // as many stages as fit ~200 KB (max 24): the small-tile GEMMs (GLU, block 1) are streaming kernels that need
+  // tens of KB of loads in flight per SM to cover the HBM latency
+  constexpr int STAGE_BYTES = KSmem<N, KCH, 1>::STAGE;
+  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 24 ? 24 : (200 * 1024 / STAGE_BYTES);
   using S = KSmem<N, KCH, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "stage ring exceeds shared memory");
   auto kern = tc_kmajor_kernel<N, KCH, STAGES>;
@@ -653,6 +657,15 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
 
 }  // namespace tc
 
+static int tc_debug() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BSED_TC_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 // Y[B][T][F][Cout] (+)= conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin]
 // (k = tap*Cin + ci).  Requires F in {2..128} dividing 128.
 int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
@@ -682,6 +695,7 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
   a.cpt = Cin / KCH;
   a.ldc = Cout;
   a.accumulate = accumulate;
+  a.debug = tc_debug();
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
   if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, Y, bias, a, sms, st);
@@ -715,6 +729,7 @@ int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int 
   a.cpt = K / KCH;
   a.ldc = ldc;
   a.accumulate = accumulate;
+  a.debug = tc_debug();
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
   if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, C, bias, a, sms, st);
   return tc::dispatch_n<16>(N, mA, mB, C, bias, a, sms, st);
