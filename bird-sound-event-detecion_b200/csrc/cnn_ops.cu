@@ -504,6 +504,168 @@ int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, 
   return BSED_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused variant used by the tensor-core path: the gate / dropout / pool backward of glu_gate_pool_bwd plus, per
+// group and channel, the three column sums every later BatchNorm-backward statistic can be derived from:
+//   A1[c] = sum d_lin[p][c]      A2[c] = sum dxd[p][c]      A3[c] = sum dxd[p][c] * xhat[p][c]
+// (dxd = the direct gate path of dxn).  With G = d_lin^T xhat of the same group (one weight-gradient GEMM),
+//   s1[c] = sum_p dxn = A2[c] + sum_c' A1[c'] Wg[c'][c]
+//   s2[c] = sum_p dxn * xhat = A3[c] + sum_c' Wg[c'][c] G[c'][c]
+// so no pass over d_lin / dxn is needed for them.  Each CTA owns a row range of one clip (few, long-lived CTAs:
+// one fp64 atomic per channel and sum per CTA).  sums: double [group][C][4].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) glu_gate_pool_bwd_sums_kernel(const float* __restrict__ xhat,
+                                                                     float* __restrict__ lin_dlin,
+                                                                     const float* __restrict__ dpooled,
+                                                                     float* __restrict__ dxn, Groups g, BNPtrs bn,
+                                                                     int T, int F, int C, int pt, int pf, int To,
+                                                                     int Fo, uint32_t key, uint32_t thresh,
+                                                                     float inv_keep, long long rows_per_cta,
+                                                                     double* __restrict__ sums) {
+  constexpr int U = 2;
+  const int clip = g.first[0] + blockIdx.y;
+  const int grp = group_of(g, clip);
+  const int nq = C / 4;
+  const int q = threadIdx.x % nq;
+  const int r0 = threadIdx.x / nq;
+  const int rstep = 256 / nq;
+  const long long rows = (long long)T * F;
+  const long long rbeg = (long long)blockIdx.x * rows_per_cta;
+  long long rend = rbeg + rows_per_cta;
+  if (rend > rows) rend = rows;
+  const int c = q * 4;
+  const float4 ga4 = *reinterpret_cast<const float4*>(bn.gamma[grp] + c);
+  const float4 be4 = *reinterpret_cast<const float4*>(bn.beta[grp] + c);
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+  const float inv = 1.0f / (float)(pt * pf);
+  float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
+  for (long long r = rbeg + r0; r < rend; r += (long long)U * rstep) {
+    float4 gv[U], xv[U], lv[U];
+    size_t e[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * rstep;
+      ok[u] = rr < rend;
+      if (!ok[u]) continue;
+      const int f = (int)(rr % F), t = (int)(rr / F);
+      e[u] = (((size_t)clip * T + t) * F + f) * C + c;
+      const int to = t / pt, fo = f / pf;
+      gv[u] = make_float4(0, 0, 0, 0);
+      if (to < To && fo < Fo) gv[u] = *reinterpret_cast<const float4*>(dpooled + (((size_t)clip * To + to) * Fo + fo) * C + c);
+      xv[u] = *reinterpret_cast<const float4*>(xhat + e[u]);
+      lv[u] = *reinterpret_cast<const float4*>(lin_dlin + e[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const float gs[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const float ls[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+      float dl[4], dx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gg = gs[j] * inv;
+        if (thresh) gg = bsed_keep((uint32_t)(e[u] + j), key, thresh) ? gg * inv_keep : 0.f;
+        const float sg = sigmoidf_(fmaf(ga[j], xs[j], be[j]));
+        dl[j] = gg * sg;
+        dx[j] = gg * ls[j] * sg * (1.f - sg);
+        a1[j] += dl[j];
+        a2[j] += dx[j];
+        a3[j] = fmaf(dx[j], xs[j], a3[j]);
+      }
+      *reinterpret_cast<float4*>(lin_dlin + e[u]) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+      *reinterpret_cast<float4*>(dxn + e[u]) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    }
+  }
+  __shared__ float red[3][256][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = a1[j];
+    red[1][threadIdx.x][j] = a2[j];
+    red[2][threadIdx.x][j] = a3[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int k = i / C, ch = i % C;
+    const int cq = ch / 4, cj = ch % 4;
+    float t = 0.f;
+    for (int r = 0; r < rstep; ++r) t += red[k][r * nq + cq][cj];
+    atomicAdd(sums + ((size_t)grp * C + ch) * 4 + k, (double)t);
+  }
+}
+
+int glu_gate_pool_bwd_sums(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
+                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                           float inv_keep, double* sums, int num_sms, cudaStream_t st) {
+  BSED_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "glu_gate_pool_bwd_sums: C=%d", C);
+  const int To = T / pt, Fo = F / pf;
+  const int nclips = total_clips(g);
+  const long long rows = (long long)T * F;
+  long long want = (long long)num_sms * 8 / nclips + 1;       // ~8 CTAs per SM overall
+  long long rows_per_cta = (rows + want - 1) / want;
+  const long long gran = 2LL * (256 / (C / 4));                 // rows one CTA pass covers
+  rows_per_cta = (rows_per_cta + gran - 1) / gran * gran;
+  dim3 grid(ceil_div(rows, rows_per_cta), nclips);
+  glu_gate_pool_bwd_sums_kernel<<<grid, 256, 0, st>>>(xhat, lin_dlin, dpooled, dxn, g, bn, T, F, C, pt, pf, To, Fo, key,
+                                                      thresh, inv_keep, rows_per_cta, sums);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// BatchNorm / GLU backward bookkeeping of the tensor-core path, one launch per block (C <= 128 threads of work):
+//   s1, s2 (see above) per group -> table for the fused GEMM epilogue, PACK times replicated:
+//       tab[g][0][j] = gamma*rstd, tab[g][1][j] = s1/n, tab[g][2][j] = s2/n      (j = p*C + c)
+//   parameter gradients: d_beta += sum_g s1, d_gamma += sum_g s2, d_bg += sum_g A1,
+//                        d_Wg[c'][c] += gamma[c] * sum_g G[g][c'][c] + beta[c] * sum_g A1[g][c']
+__global__ void bn_bwd_prepare_kernel(const double* __restrict__ sums, const float* __restrict__ G, int n_groups, int C,
+                                      Groups g, long long rows_per_clip, BNPtrs bn, const float* __restrict__ wg,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int pack,
+                                      float* __restrict__ tab, float* d_gamma, float* d_beta, float* d_wg, float* d_bg) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double s1_all = 0.0, s2_all = 0.0, a1_all = 0.0;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const double* sg = sums + (size_t)gi * C * 4;
+    const float* Gg = G + (size_t)gi * C * C;
+    double s1 = sg[c * 4 + 1], s2 = sg[c * 4 + 2];
+    for (int cp = 0; cp < C; ++cp) {
+      const double w = (double)wg[(size_t)cp * C + c];
+      s1 += sg[cp * 4 + 0] * w;
+      s2 += w * (double)Gg[(size_t)cp * C + c];
+    }
+    const double n = (double)g.count[gi] * (double)rows_per_clip;
+    const float k = bn.gamma[gi][c] * bn.rstd[gi][c];
+    for (int p = 0; p < pack; ++p) {
+      float* t = tab + (size_t)gi * 3 * C * pack + p * C + c;
+      t[0] = k;
+      t[(size_t)C * pack] = (float)(s1 / n);
+      t[(size_t)2 * C * pack] = (float)(s2 / n);
+    }
+    s1_all += s1;
+    s2_all += s2;
+    a1_all += sg[c * 4 + 0];
+  }
+  d_beta[c] += (float)s1_all;
+  d_gamma[c] += (float)s2_all;
+  d_bg[c] += (float)a1_all;
+  // row c of d_Wg: thread c handles c' = c (all columns)
+  for (int col = 0; col < C; ++col) {
+    float gsum = 0.f;
+    for (int gi = 0; gi < n_groups; ++gi) gsum += G[(size_t)gi * C * C + (size_t)c * C + col];
+    d_wg[(size_t)c * C + col] += gamma[col] * gsum + beta[col] * (float)a1_all;
+  }
+}
+
+int bn_bwd_prepare(const double* sums, const float* G, int n_groups, int C, const Groups& g, long long rows_per_clip,
+                   const BNPtrs& bn, const float* wg, const float* gamma, const float* beta, int pack, float* tab,
+                   float* d_gamma, float* d_beta, float* d_wg, float* d_bg, cudaStream_t st) {
+  bn_bwd_prepare_kernel<<<1, 128, 0, st>>>(sums, G, n_groups, C, g, rows_per_clip, bn, wg, gamma, beta, pack, tab, d_gamma,
+                                           d_beta, d_wg, d_bg);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
 // dY = gamma * rstd * (dxn - s1/n - xhat * s2/n), in place on dxn
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dxn, const float* __restrict__ xhat,
                                                            const double* __restrict__ stats2, Groups g,

@@ -56,7 +56,7 @@ struct bsed_crnn_plan {
   size_t off_stats, off_stats2, off_meanrstd;
   size_t off_xg, off_gru_out[4], off_gru_saved[4], off_enc;
   size_t off_dxn, off_dpool[2], off_denc, off_dx1, off_dxg, off_dgh;
-  size_t off_G, off_dscratch, off_wgpart;
+  size_t off_G, off_dscratch, off_wgpart, off_bsums, off_bntab;
   size_t wgpart_bytes;
   size_t ws_bytes;
   int precision;  // BSED_PRECISION_FP32 (SIMT fp32) or BSED_PRECISION_TF32 (tcgen05 kind::tf32)
@@ -229,7 +229,9 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_dx1 = takeb(sizeof(float) * BT * 256);
   p->off_dxg = takeb(sizeof(float) * BT * 768);
   p->off_dgh = takeb(sizeof(float) * BT * 768);
-  p->off_G = takeb(sizeof(float) * 128 * 128);
+  p->off_G = takeb(sizeof(float) * kMaxGroups * 128 * 128);
+  p->off_bsums = takeb(sizeof(double) * kMaxGroups * 128 * 4);
+  p->off_bntab = takeb(sizeof(float) * kMaxGroups * 3 * 128);
   p->off_dscratch = takeb(sizeof(double) * 2 * 768);
   p->wgpart_bytes = tc_wgrad_workspace_bytes(p->ctx->num_sms);
   p->off_wgpart = takeb(p->wgpart_bytes);
@@ -680,6 +682,38 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BNPtrs bn = make_bn_ptrs(p, ws, i, ids, n);
     const size_t off = (size_t)first * L.rows * L.Cout;
     const long long M = (long long)nb * L.rows;
+    if (tc) {
+      // ---- tensor-core path: every BatchNorm-backward statistic comes from column sums taken inside the gate
+      // kernel plus the per-group GLU weight-gradient GEMM (cnn_ops.cu: glu_gate_pool_bwd_sums), and the BatchNorm
+      // backward itself is the epilogue of the GEMM that adds the GLU linear path to dxn.
+      double* bsums = wsp<double>(ws, p->off_bsums);
+      float* tab = wsp<float>(ws, p->off_bntab);
+      BSED_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * kMaxGroups * 128 * 4, st));
+      BSED_TRY(glu_gate_pool_bwd_sums(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i],
+                                      p->thresh, p->inv_keep, bsums, sms, st));
+      BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * n * L.Cout * L.Cout, st));
+      int gfirst_rel[kMaxGroups] = {0, 0, 0, 0};
+      for (int k = 0; k < n; ++k) {
+        gfirst_rel[k] = gb.first[k] - first;
+        const size_t goff = (size_t)gb.first[k] * L.rows * L.Cout;
+        float* Gk = G + (size_t)k * L.Cout * L.Cout;
+        if (L.Cout % 32 == 0 && L.F <= 64 && 64 % L.F == 0) {
+          BSED_TRY(tc_wgrad(xhat + goff, lin + goff, Gk, L.Cout, 1, 0, gb.count[k], L.T, L.F, L.Cout, L.Cout, 1, wgpart,
+                            p->wgpart_bytes, sms, st));
+        } else if (L.Cout == 16 && L.F % 2 == 0 && L.F <= 128 && 64 % (L.F / 2) == 0) {
+          TcOperand Ag{lin + goff, 32, 0, 32}, Bg{xhat + goff, 32, 0, 32};   // two pixels per row (32 floats)
+          BSED_TRY(tc_wgrad_ex(Ag, Bg, gb.count[k], L.T, L.F / 2, 3, 0, Gk, L.Cout, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+        } else {
+          BSED_TRY(gemm_tn(lin + goff, L.Cout, xhat + goff, L.Cout, Gk, L.Cout, 1, L.Cout, L.Cout,
+                           (long long)gb.count[k] * L.rows, target, st));
+        }
+      }
+      BSED_TRY(bn_bwd_prepare(bsums, G, n, L.Cout, gb, L.rows, bn, params + pl.glu_w[i], params + pl.bn_w[i],
+                              params + pl.bn_b[i], 1, tab, grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i],
+                              grads + pl.glu_b[i], st));
+      BSED_TRY(tc_gemm_nt_bnbwd(lin + off, packed + p->pk.glu_wgT[i], dxn + off, xhat + off, M, L.Cout, L.Cout, tab, n,
+                                L.rows, gfirst_rel, sms, st));
+    } else {
     // gate / dropout / pool backward: lin -> d_lin (in place), dxn <- direct gate path
     BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
                                p->inv_keep, st));
@@ -713,6 +747,7 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     BSED_TRY(bn_glu_param_grads(stats2, n, L.Cout, params + pl.bn_w[i], params + pl.bn_b[i], G, dscr,
                                 grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i], grads + pl.glu_b[i], st));
     BSED_TRY(bn_bwd_apply(dxn, xhat, stats2, gb, L.rows, L.Cout, bn, st));
+    }
     // conv bias gradient: sum_p dY = gamma*rstd*(sum dxn - n*mean(dxn) - mean(dxn*xhat) * sum xhat) = 0 exactly behind a
     // train-mode BatchNorm (the reference computes rounding noise here); grads[conv_b] keeps its zero / accumulated value
     if (i > 0) {

@@ -58,6 +58,12 @@ int glu_gate_pool_fwd(const float* xhat, const float* lin, float* pooled, const 
 int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
                       const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
                       float inv_keep, cudaStream_t st);
+int glu_gate_pool_bwd_sums(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
+                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                           float inv_keep, double* sums, int num_sms, cudaStream_t st);
+int bn_bwd_prepare(const double* sums, const float* G, int n_groups, int C, const Groups& g, long long rows_per_clip,
+                   const BNPtrs& bn, const float* wg, const float* gamma, const float* beta, int pack, float* tab,
+                   float* d_gamma, float* d_beta, float* d_wg, float* d_bg, cudaStream_t st);
 int bn_bwd_apply(float* dxn_dy, const float* xhat, const double* stats2, const Groups& g,
                  long long rows_per_clip, int C, const BNPtrs& bn, cudaStream_t st);
 // dgamma += sum_g s2, dbeta += sum_g s1; dWg += gamma[c] * G[c'][c] + beta[c] * dbg[c']; dbg_out += dbg
@@ -121,6 +127,8 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 
+int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xhat, long long M, int N, int K,
+                     const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(int sms);
 // [rows][ld] fp32 tensor, channels [c0, c0 + C) of every row take part
 struct TcOperand {

@@ -159,6 +159,14 @@ struct KArgs {
   int ldc;
   int accumulate;
   int debug;           // BSED_TC_DEBUG (measurement experiments only): 1 = skip the epilogue's global stores
+  // epi == 1: BatchNorm-backward epilogue (plain mode): C holds the direct gate path dxd on entry and
+  //   dY = k * (dxd + acc - m1 - xhat * m2) on exit; (k, m1, m2) per group and column from `tab` [groups][3][N]
+  int epi;
+  const float* xh;           // xhat, same shape / leading dimension as C
+  const float* tab;
+  int tab_groups;
+  long long rows_per_clip;   // rows of one clip (row -> clip -> group)
+  int gfirst[kMaxGroups];    // first clip of each group, relative to row 0
 };
 
 template <int N, int KCH, int STAGES>
@@ -168,7 +176,8 @@ struct KSmem {
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE = A_BYTES + B_STRIDE;
   static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 4 mbarriers + the TMEM slot
-  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/;
+  static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
   static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
@@ -204,6 +213,9 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     fence_barrier_init();
   }
   if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  float* stab = sbias + 128;
+  if (a.epi == 1)
+    for (int i = threadIdx.x; i < a.tab_groups * 3 * N; i += kThreads) stab[i] = a.tab[i];
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -300,11 +312,26 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       constexpr int CW = N >= 32 ? 32 : 16;       // columns per chunk
       const uint32_t sbias_addr = smem_u32(sbias);
       float* yrow = Y + grow * a.ldc;
-      const bool acc_rd = a.accumulate && valid;
-      float4 cpre[CW / 4];
+      const bool acc_rd = (a.accumulate || a.epi == 1) && valid;
+      const bool bn_rd = a.epi == 1 && valid;
+      const float* xrow = a.xh + grow * a.ldc;
+      uint32_t tab_addr = 0;
+      if (a.epi == 1) {
+        const int clip = (int)(grow / a.rows_per_clip);
+        int gi = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxGroups; ++k)
+          if (k < a.tab_groups && clip >= a.gfirst[k]) gi = k;
+        tab_addr = smem_u32(stab) + gi * 3 * N * 4;
+      }
+      float4 cpre[CW / 4], xpre[CW / 4];
       if (acc_rd) {
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+      }
+      if (bn_rd) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) xpre[j] = *reinterpret_cast<const float4*>(xrow + 4 * j);
       }
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
@@ -314,20 +341,38 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         float v[CW];
         if constexpr (CW == 32) tmem_ld32(taddr + c0, v);
         else tmem_ld16(taddr + c0, v);
-        float4 ccur[CW / 4];
+        float4 ccur[CW / 4], xcur[CW / 4];
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) ccur[j] = acc_rd ? cpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (acc_rd && c0 + CW < N) {
+        for (int j = 0; j < CW / 4; ++j) {
+          ccur[j] = acc_rd ? cpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          xcur[j] = bn_rd ? xpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (c0 + CW < N) {
+          if (acc_rd) {
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
+            for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
+          }
+          if (bn_rd) {
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) xpre[j] = *reinterpret_cast<const float4*>(xrow + c0 + CW + 4 * j);
+          }
         }
         if (valid) {
 #pragma unroll
           for (int j = 0; j < CW; j += 4) {
-            const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
             const float4 cv = ccur[j / 4];
-            float4 o = make_float4(v[j] + bv.x + cv.x, v[j + 1] + bv.y + cv.y, v[j + 2] + bv.z + cv.z,
-                                   v[j + 3] + bv.w + cv.w);
+            float4 o;
+            if (a.epi == 1) {
+              const float4 kk = lds128(tab_addr + (c0 + j) * 4);
+              const float4 m1 = lds128(tab_addr + (N + c0 + j) * 4);
+              const float4 m2 = lds128(tab_addr + (2 * N + c0 + j) * 4);
+              const float4 xv = xcur[j / 4];
+              o = make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
+                              kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w));
+            } else {
+              const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
+              o = make_float4(v[j] + bv.x + cv.x, v[j + 1] + bv.y + cv.y, v[j + 2] + bv.z + cv.z, v[j + 3] + bv.w + cv.w);
+            }
             if (a.debug != 1 || o.x == 12345.678f) *reinterpret_cast<float4*>(yrow + c0 + j) = o;
           }
         }
@@ -696,15 +741,28 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
   a.ldc = Cout;
   a.accumulate = accumulate;
   a.debug = tc_debug();
+  a.epi = 0;
+  a.xh = nullptr;
+  a.tab = nullptr;
+  a.tab_groups = 0;
+  a.rows_per_clip = 1;
+  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = 0;
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
   if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, Y, bias, a, sms, st);
   return tc::dispatch_n<16>(Cout, mA, mB, Y, bias, a, sms, st);
 }
 
-// C[M][N] (+)= A[M][K] * Bk^T + bias ; Bk = [N][K] K-major
-int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
-               const float* bias, int accumulate, int sms, cudaStream_t st) {
+// C[M][N] (+)= A[M][K] * Bk^T + bias ; Bk = [N][K] K-major.  bnb != nullptr selects the BatchNorm-backward epilogue.
+struct BnBwdEpi {
+  const float* xhat;
+  const float* tab;
+  int groups;
+  long long rows_per_clip;
+  int gfirst[kMaxGroups];
+};
+static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
+                           const float* bias, int accumulate, const BnBwdEpi* bnb, int sms, cudaStream_t st) {
   BSED_REQUIRE(K % 16 == 0 && N % 16 == 0 && N <= 128 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
                "tc_gemm_nt: M=%lld N=%d K=%d", M, N, K);
   const int KCH = K % 32 == 0 ? 32 : 16;
@@ -730,9 +788,32 @@ int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int 
   a.ldc = ldc;
   a.accumulate = accumulate;
   a.debug = tc_debug();
+  a.epi = bnb ? 1 : 0;
+  a.xh = bnb ? bnb->xhat : nullptr;
+  a.tab = bnb ? bnb->tab : nullptr;
+  a.tab_groups = bnb ? bnb->groups : 0;
+  a.rows_per_clip = bnb ? bnb->rows_per_clip : 1;
+  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = bnb ? bnb->gfirst[k] : 0;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
   if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, C, bias, a, sms, st);
   return tc::dispatch_n<16>(N, mA, mB, C, bias, a, sms, st);
+}
+
+int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
+               const float* bias, int accumulate, int sms, cudaStream_t st) {
+  return tc_gemm_nt_impl(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, nullptr, sms, st);
+}
+
+// dY = k * (dxd + A * Bk^T - m1 - xhat * m2), in place on C (= dxd on entry); see KArgs::epi
+int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xhat, long long M, int N, int K,
+                     const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st) {
+  BnBwdEpi e;
+  e.xhat = xhat;
+  e.tab = tab;
+  e.groups = groups;
+  e.rows_per_clip = rows_per_clip;
+  for (int k = 0; k < kMaxGroups; ++k) e.gfirst[k] = k < groups ? gfirst[k] : 0;
+  return tc_gemm_nt_impl(A, K, Bk, K, C, N, M, N, K, nullptr, 0, &e, sms, st);
 }
 
 }  // namespace bsed
