@@ -487,8 +487,20 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         const float* xr = xin + (size_t)runs[r].first * L.rows * L.Cin;
         float* yr = y + (size_t)runs[r].first * L.rows * L.Cout;
         const float* cb = p->pset_params[runs[r].pset] + p->pl.conv_b[i];
-        if (tc) BSED_TRY(tc_conv3x3(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, sms, st));
-        else BSED_TRY(conv3x3_nn(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st));
+        if (tc) {
+          // batch statistics of the conv output are accumulated by the GEMM epilogue (train mode)
+          int gfirst_rel[kMaxGroups] = {0, 0, 0, 0}, gbase = -1, ng = 0;
+          for (int k = 0; k < n_groups; ++k)
+            if (p->gpset[k] == runs[r].pset) {
+              if (gbase < 0) gbase = k;
+              gfirst_rel[ng++] = g.first[k] - runs[r].first;
+            }
+          double* st_run = train ? stats + (size_t)i * kMaxGroups * 128 * 2 + (size_t)gbase * L.Cout * 2 : nullptr;
+          BSED_TRY(tc_conv3x3_stats(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st_run, ng,
+                                    gfirst_rel, sms, st));
+        } else {
+          BSED_TRY(conv3x3_nn(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st));
+        }
       }
     }
     BNPtrs bn = make_bn_ptrs(p, ws, i, all_ids, n_groups);
@@ -503,7 +515,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     }
     if (train) {
       double* st_i = stats + (size_t)i * kMaxGroups * 128 * 2;
-      BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
+      if (!tc || i == 0) BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
       // stats rows are indexed [group][C]: col_stats uses stride C, finalize too
       BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, rmean, rvar, nbt, st));
     } else {

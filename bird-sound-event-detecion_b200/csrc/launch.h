@@ -124,6 +124,10 @@ int add_f32(float* dst, const float* src, long long n, cudaStream_t st);
 // ---- tc_gemm.cu (tcgen05 / TMA)
 int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
                int accumulate, int sms, cudaStream_t st);
+// stats != nullptr: also accumulates the per-channel sum / sum of squares of the output per group
+// (stats[(group * Cout + c) * 2 + {0,1}], group = last k with clip >= gfirst[k], clips relative to X)
+int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+                     int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 

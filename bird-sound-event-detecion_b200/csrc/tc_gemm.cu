@@ -82,6 +82,35 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, void* dst, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
@@ -166,42 +195,57 @@ struct KArgs {
   const float* tab;
   int tab_groups;
   long long rows_per_clip;   // rows of one clip (row -> clip -> group)
-  int gfirst[kMaxGroups];    // first clip of each group, relative to row 0
+  int gfirst[kMaxGroups];    // first clip of each group, relative to row 0 (epi == 1) / to clip 0 (stats)
+  // per-channel batch statistics of the output (conv mode): stats[(group * N + c) * 2 + {0,1}] += sum, sum of squares
+  double* stats;
+  int stats_groups;
 };
 
-template <int N, int KCH, int STAGES>
+// RB ("resident B"): the whole [N][K] weight matrix (<= kRbBytes) is loaded once per CTA and stays in shared
+// memory; the ring then carries A tiles only.  Without it every 128-pixel tile re-fetches the weights from L2, which
+// for the GLU linears and blocks 1-2 is 20-50 % of the L2 -> SM traffic these kernels are bound by.
+constexpr int kRbBytes = 72 * 1024;
+
+template <int N, int KCH, int STAGES, bool RB>
 struct KSmem {
   static constexpr int A_BYTES = kBM * KCH * 4;
   static constexpr int B_BYTES = N * KCH * 4;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE = A_BYTES + B_STRIDE;
-  static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 4 mbarriers + the TMEM slot
+  static constexpr int STAGE = A_BYTES + (RB ? 0 : B_STRIDE);
+  static constexpr int RB_BYTES = RB ? kRbBytes : 0;
+  static constexpr int STG_BYTES = kBM * N * 4;   // output tile staged for the TMA store
+  static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 5 mbarriers + the TMEM slot
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
-  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
-  static_assert((2 * STAGES + 5) * 8 <= BAR_BYTES, "barrier region too small");
+  static constexpr int TOTAL =
+      STAGES * STAGE + RB_BYTES + STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
+  static_assert((2 * STAGES + 6) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
-template <int N, int KCH, int STAGES>
+template <int N, int KCH, int STAGES, bool RB>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 float* __restrict__ Y, const float* __restrict__ bias, KArgs a) {
-  using S = KSmem<N, KCH, STAGES>;
+                 const __grid_constant__ CUtensorMap mapC, float* __restrict__ Y, const float* __restrict__ bias, KArgs a) {
+  using S = KSmem<N, KCH, STAGES, RB>;
   constexpr int ROWB = KCH * 4;
   constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE);
+  unsigned char* rb = smem + STAGES * S::STAGE;   // resident weights (RB)
+  unsigned char* stg = rb + S::RB_BYTES;          // output staging (1024-byte aligned: STAGE and kRbBytes are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + S::STG_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* sbias = reinterpret_cast<float*>(smem + STAGES * S::STAGE + S::BAR_BYTES);   // bias staged once per CTA
+  uint64_t* rbfull = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  float* sbias = reinterpret_cast<float*>(stg + S::STG_BYTES + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
+    prefetch_tmap(&mapC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -210,6 +254,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
     }
+    mbar_init(rbfull, 1);
     fence_barrier_init();
   }
   if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
@@ -228,6 +273,10 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      if (RB) {
+        mbar_expect_tx(rbfull, nk * S::B_BYTES);
+        for (int i = 0; i < nk; ++i) tma_load_2d(&mapB, rb + i * S::B_STRIDE, rbfull, i * KCH, 0);
+      }
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         int b = 0, t0 = 0;
         if (!a.plain) {
@@ -240,10 +289,10 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_wait(&empty[s], ph ^ 1);
             unsigned char* sa = smem + s * S::STAGE;
             unsigned char* sb = sa + S::A_BYTES;
-            mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+            mbar_expect_tx(&full[s], S::A_BYTES + (RB ? 0 : S::B_BYTES));
             if (a.plain) tma_load_2d(&mapA, sa, &full[s], ch * KCH, tile * kBM);
             else tma_load_4d(&mapA, sa, &full[s], ch * KCH, df, t0 + dt, b);
-            tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, 0);
+            if (!RB) tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, 0);
             if (++s == STAGES) {
               s = 0;
               ph ^= 1;
@@ -258,6 +307,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
+    if (RB) mbar_wait(rbfull, 0);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
@@ -270,7 +320,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
         if (lane == 0) {   // one fixed lane issues the MMAs and their commits (commit tracks the issuing thread)
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
-          const uint32_t sb = sa + S::A_BYTES;
+          const uint32_t sb = RB ? smem_u32(rb + kc * S::B_STRIDE) : sa + S::A_BYTES;
 #pragma unroll
           for (int k = 0; k < KCH / 8; ++k) {
             uint64_t da = kmajor_desc<ROWB>(sa + k * 32);
@@ -289,31 +339,52 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;          // row of the 128-row tile
+    // TMEM -> registers -> (+ bias | BatchNorm backward) -> swizzled staging tile in shared memory -> TMA store
+    // (TMA reduce-add in accumulate mode: C is never read by the SM).  Column statistics of the tile (conv forward in
+    // train mode) are taken from the staged tile: thread c owns column c.
+    constexpr int CW = N >= 32 ? 32 : 16;       // columns per TMEM load / per TMA store box
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;              // row of the 128-row tile
+    const bool leader = threadIdx.x == 64;
+    const uint32_t sbias_addr = smem_u32(sbias);
+    const uint32_t stg_addr = smem_u32(stg);
+    // swizzled position of 16-byte chunk c4 of this thread's row inside one [128][CW] staging sub-tile
+    auto chunk_addr = [&](int r, int c4) -> uint32_t {
+      if (CW == 32) return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4));
+      return (uint32_t)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
+    };
+    double st_sum = 0.0, st_sq = 0.0;           // running column statistics (thread = column `row`)
+    int st_grp = -1;
+    auto flush_stats = [&]() {
+      if (st_grp >= 0 && row < N) {
+        atomicAdd(a.stats + ((size_t)st_grp * N + row) * 2 + 0, st_sum);
+        atomicAdd(a.stats + ((size_t)st_grp * N + row) * 2 + 1, st_sq);
+      }
+      st_sum = st_sq = 0.0;
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       long long grow;                       // global output row
       bool valid;
+      int b = 0, t0 = 0, valid_rows = kBM;
       if (a.plain) {
         grow = (long long)tile * kBM + row;
         valid = grow < a.rows;
+        if (a.rows - (long long)tile * kBM < kBM) valid_rows = (int)(a.rows - (long long)tile * kBM);
       } else {
-        int b = tile / a.tiles_per_clip;
-        int t0 = (tile - b * a.tiles_per_clip) * a.th;
+        b = tile / a.tiles_per_clip;
+        t0 = (tile - b * a.tiles_per_clip) * a.th;
         long long in_clip = (long long)t0 * a.F + row;
         valid = in_clip < (long long)a.T * a.F;
         grow = (long long)b * a.T * a.F + in_clip;
+        if ((long long)a.T * a.F - (long long)t0 * a.F < kBM) valid_rows = (int)((long long)a.T * a.F - (long long)t0 * a.F);
       }
-      // C values of the upcoming column chunk (accumulate mode) are requested before the accumulator is awaited, and
-      // the next chunk's while the current one is combined: their latency overlaps the MMAs / the TMEM loads
-      constexpr int CW = N >= 32 ? 32 : 16;       // columns per chunk
-      const uint32_t sbias_addr = smem_u32(sbias);
-      float* yrow = Y + grow * a.ldc;
-      const bool acc_rd = (a.accumulate || a.epi == 1) && valid;
+      // operands of the BatchNorm-backward epilogue: requested before the accumulator is awaited, next chunk's while
+      // the current one is combined
       const bool bn_rd = a.epi == 1 && valid;
+      const float* yrow = Y + grow * a.ldc;
       const float* xrow = a.xh + grow * a.ldc;
       uint32_t tab_addr = 0;
       if (a.epi == 1) {
@@ -325,16 +396,21 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tab_addr = smem_u32(stab) + gi * 3 * N * 4;
       }
       float4 cpre[CW / 4], xpre[CW / 4];
-      if (acc_rd) {
-#pragma unroll
-        for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
-      }
       if (bn_rd) {
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) xpre[j] = *reinterpret_cast<const float4*>(xrow + 4 * j);
+        for (int j = 0; j < CW / 4; ++j) {
+          cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+          xpre[j] = *reinterpret_cast<const float4*>(xrow + 4 * j);
+        }
       }
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
+      // the staging tile is free once the previous tile's TMA stores have read it (and every thread is done with its
+      // statistics pass)
+      if (it > 0) {
+        if (leader) bulk_wait_read0();
+        epi_barrier();
+      }
       const uint32_t taddr = tmem_base + acc * N + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += CW) {
@@ -344,43 +420,74 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         float4 ccur[CW / 4], xcur[CW / 4];
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
-          ccur[j] = acc_rd ? cpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          ccur[j] = bn_rd ? cpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
           xcur[j] = bn_rd ? xpre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (c0 + CW < N) {
-          if (acc_rd) {
+        if (bn_rd && c0 + CW < N) {
 #pragma unroll
-            for (int j = 0; j < CW / 4; ++j) cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
-          }
-          if (bn_rd) {
-#pragma unroll
-            for (int j = 0; j < CW / 4; ++j) xpre[j] = *reinterpret_cast<const float4*>(xrow + c0 + CW + 4 * j);
+          for (int j = 0; j < CW / 4; ++j) {
+            cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
+            xpre[j] = *reinterpret_cast<const float4*>(xrow + c0 + CW + 4 * j);
           }
         }
-        if (valid) {
+        const uint32_t sub = stg_addr + (c0 / CW) * (kBM * CW * 4);
 #pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            const float4 cv = ccur[j / 4];
-            float4 o;
-            if (a.epi == 1) {
-              const float4 kk = lds128(tab_addr + (c0 + j) * 4);
-              const float4 m1 = lds128(tab_addr + (N + c0 + j) * 4);
-              const float4 m2 = lds128(tab_addr + (2 * N + c0 + j) * 4);
-              const float4 xv = xcur[j / 4];
-              o = make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
-                              kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w));
-            } else {
-              const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
-              o = make_float4(v[j] + bv.x + cv.x, v[j + 1] + bv.y + cv.y, v[j + 2] + bv.z + cv.z, v[j + 3] + bv.w + cv.w);
-            }
-            if (a.debug != 1 || o.x == 12345.678f) *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+        for (int j = 0; j < CW; j += 4) {
+          float4 o;
+          if (a.epi == 1) {
+            const float4 kk = lds128(tab_addr + (c0 + j) * 4);
+            const float4 m1 = lds128(tab_addr + (N + c0 + j) * 4);
+            const float4 m2 = lds128(tab_addr + (2 * N + c0 + j) * 4);
+            const float4 cv = ccur[j / 4], xv = xcur[j / 4];
+            o = make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
+                            kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w));
+          } else {
+            const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
+            o = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
           }
+          sts128(sub + chunk_addr(row, j / 4), o);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: the next MMAs may overwrite it
+      fence_proxy_async();                         // staged tile visible to the TMA (async proxy)
+      epi_barrier();
+      if (leader && a.debug != 1) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += CW) {
+          const void* src = stg + (c0 / CW) * (kBM * CW * 4);
+          if (a.plain) tma_store_2d(&mapC, src, c0, tile * kBM, a.accumulate != 0);
+          else tma_store_4d(&mapC, src, c0, 0, t0, b, a.accumulate != 0);
+        }
+        bulk_commit();
+      }
+      if (a.stats) {
+        int gi = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxGroups; ++k)
+          if (k < a.stats_groups && b >= a.gfirst[k]) gi = k;
+        if (gi != st_grp) {
+          flush_stats();
+          st_grp = gi;
+        }
+        if (row < N) {
+          const int c = row;
+          const uint32_t cbase = stg_addr + (c / CW) * (kBM * CW * 4) + (c & 3) * 4;
+          const int c4 = (c % CW) >> 2;
+          float s1 = 0.f, s2 = 0.f;
+          for (int r = 0; r < valid_rows; ++r) {
+            const float x = lds32(cbase + chunk_addr(r, c4));
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          st_sum += (double)s1;
+          st_sq += (double)s2;
+        }
+      }
     }
+    if (a.stats) flush_stats();
+    if (leader) bulk_wait0();                      // shared memory must outlive the TMA reads
   }
   tc_fence_before();
   __syncthreads();
@@ -408,7 +515,7 @@ static EncodeTiledFn encode_fn() {
 
 // rank-R fp32 map; dims/strides innermost first (strides in bytes for dims 1..R-1)
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                    const cuuint32_t* box, int row_bytes) {
+                    const cuuint32_t* box, int row_bytes, bool store = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     bsed_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -418,7 +525,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   CUtensorMapSwizzle sw = row_bytes == 128   ? CU_TENSOR_MAP_SWIZZLE_128B
                           : row_bytes == 132 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B   // 128 B rows, 32 B swizzle atoms
                                              : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+  CUresult r = fn(m, store ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -429,35 +536,44 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return BSED_OK;
 }
 
-template <int N, int KCH>
-static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, float* Y, const float* bias, const KArgs& a, int sms,
-                    cudaStream_t st) {
+template <int N, int KCH, bool RB>
+static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
+                     const KArgs& a, int sms, cudaStream_t st) {
   // as many stages as fit ~200 KB (max 24): the small-tile GEMMs (GLU, block 1) are streaming kernels that need
   // tens of KB of loads in flight per SM to cover the HBM latency
-  constexpr int STAGE_BYTES = KSmem<N, KCH, 1>::STAGE;
-  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 24 ? 24 : (200 * 1024 / STAGE_BYTES);
-  using S = KSmem<N, KCH, STAGES>;
+  constexpr int STAGE_BYTES = KSmem<N, KCH, 1, RB>::STAGE;
+  constexpr int BUDGET = 200 * 1024 - (RB ? kRbBytes : 0) - kBM * N * 4;
+  constexpr int STAGES = (BUDGET / STAGE_BYTES) > 24 ? 24 : (BUDGET / STAGE_BYTES);
+  using S = KSmem<N, KCH, STAGES, RB>;
   static_assert(S::TOTAL <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = tc_kmajor_kernel<N, KCH, STAGES>;
+  auto kern = tc_kmajor_kernel<N, KCH, STAGES, RB>;
   static bool configured = false;
   if (!configured) {
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, Y, bias, a);
+  kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, mC, Y, bias, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
 
+template <int N, int KCH>
+static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
+                    const KArgs& a, int sms, cudaStream_t st) {
+  const bool rb = (long long)a.ntaps * a.cpt * KSmem<N, KCH, 1, true>::B_STRIDE <= kRbBytes;
+  if (rb) return launch_k2<N, KCH, true>(mA, mB, mC, Y, bias, a, sms, st);
+  return launch_k2<N, KCH, false>(mA, mB, mC, Y, bias, a, sms, st);
+}
+
 template <int KCH>
-static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, float* Y, const float* bias, const KArgs& a,
-                      int sms, cudaStream_t st) {
+static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
+                      const KArgs& a, int sms, cudaStream_t st) {
   switch (N) {
-    case 16: return launch_k<16, KCH>(mA, mB, Y, bias, a, sms, st);
-    case 32: return launch_k<32, KCH>(mA, mB, Y, bias, a, sms, st);
-    case 64: return launch_k<64, KCH>(mA, mB, Y, bias, a, sms, st);
-    case 128: return launch_k<128, KCH>(mA, mB, Y, bias, a, sms, st);
+    case 16: return launch_k<16, KCH>(mA, mB, mC, Y, bias, a, sms, st);
+    case 32: return launch_k<32, KCH>(mA, mB, mC, Y, bias, a, sms, st);
+    case 64: return launch_k<64, KCH>(mA, mB, mC, Y, bias, a, sms, st);
+    case 128: return launch_k<128, KCH>(mA, mB, mC, Y, bias, a, sms, st);
   }
   bsed_set_error("tc gemm: N=%d unsupported (16/32/64/128)", N);
   return BSED_E_INVALID;
@@ -659,10 +775,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, RArgs r, flo
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   auto P = [&](int tap, int m, int n) {
     const int z = (m / kBM) * r.n_tiles_n + n / r.N;
-    float acc = 0.f;
-    for (int s = 0; s < r.splits; ++s)
-      acc += part[((((size_t)s * r.ntaps + tap) * r.ztiles + z) * kBM + m % kBM) * r.N + n % r.N];
-    return acc;
+    const float* p0 = part + (((size_t)tap * r.ztiles + z) * kBM + m % kBM) * r.N + n % r.N;
+    const size_t stride = (size_t)r.ntaps * r.ztiles * kBM * r.N;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 8 independent loads in flight
+    int s = 0;
+    for (; s + 8 <= r.splits; s += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += p0[(size_t)(s + u) * stride];
+    }
+    for (; s < r.splits; ++s) a[0] += p0[(size_t)s * stride];
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   };
   if (r.mode == W_PAIR) {
     if (i >= 9 * r.m_total * 16) return;
@@ -713,13 +835,14 @@ static int tc_debug() {
 
 // Y[B][T][F][Cout] (+)= conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin]
 // (k = tap*Cin + ci).  Requires F in {2..128} dividing 128.
-int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-               int accumulate, int sms, cudaStream_t st) {
+int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+                     int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st) {
   BSED_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128, "tc_conv3x3: Cin=%d Cout=%d", Cin, Cout);
   BSED_REQUIRE(F >= 1 && F <= 128 && 128 % F == 0, "tc_conv3x3: F=%d must divide 128", F);
   const int KCH = Cin % 32 == 0 ? 32 : 16;
   const int th = 128 / F;
-  CUtensorMap mA, mB;
+  const int CW = Cout >= 32 ? 32 : 16;
+  CUtensorMap mA, mB, mC;
   cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t sA[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
   cuuint32_t bA[4] = {(cuuint32_t)KCH, (cuuint32_t)F, (cuuint32_t)th, 1};
@@ -728,6 +851,10 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
   cuuint64_t sB[1] = {(cuuint64_t)9 * Cin * 4};
   cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)Cout};
   BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, KCH * 4));
+  cuuint64_t dC[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sC[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
+  cuuint32_t bC[4] = {(cuuint32_t)CW, (cuuint32_t)F, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mC, Y, 4, dC, sC, bC, CW * 4, true));
   tc::KArgs a;
   a.plain = 0;
   a.tiles_per_clip = (T + th - 1) / th;
@@ -746,11 +873,18 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
   a.tab = nullptr;
   a.tab_groups = 0;
   a.rows_per_clip = 1;
-  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = 0;
+  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = stats && k < stats_groups ? gfirst[k] : 0;
+  a.stats = stats;
+  a.stats_groups = stats ? stats_groups : 0;
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
-  if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, Y, bias, a, sms, st);
-  return tc::dispatch_n<16>(Cout, mA, mB, Y, bias, a, sms, st);
+  if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, mC, Y, bias, a, sms, st);
+  return tc::dispatch_n<16>(Cout, mA, mB, mC, Y, bias, a, sms, st);
+}
+
+int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+               int accumulate, int sms, cudaStream_t st) {
+  return tc_conv3x3_stats(X, Wk, Y, B, T, F, Cin, Cout, bias, accumulate, nullptr, 0, nullptr, sms, st);
 }
 
 // C[M][N] (+)= A[M][K] * Bk^T + bias ; Bk = [N][K] K-major.  bnb != nullptr selects the BatchNorm-backward epilogue.
@@ -775,6 +909,12 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, fl
   cuuint64_t sB[1] = {(cuuint64_t)ldb * 4};
   cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)N};
   BSED_TRY(tc::make_map(&mB, Bk, 2, dB, sB, bB, KCH * 4));
+  const int CW = N >= 32 ? 32 : 16;
+  CUtensorMap mC;
+  cuuint64_t dC[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t sC[1] = {(cuuint64_t)ldc * 4};
+  cuuint32_t bC[2] = {(cuuint32_t)CW, 128};
+  BSED_TRY(tc::make_map(&mC, C, 2, dC, sC, bC, CW * 4, true));
   tc::KArgs a;
   a.plain = 1;
   a.n_tiles = (int)((M + 127) / 128);
@@ -794,9 +934,11 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, fl
   a.tab_groups = bnb ? bnb->groups : 0;
   a.rows_per_clip = bnb ? bnb->rows_per_clip : 1;
   for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = bnb ? bnb->gfirst[k] : 0;
+  a.stats = nullptr;
+  a.stats_groups = 0;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
-  if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, C, bias, a, sms, st);
-  return tc::dispatch_n<16>(N, mA, mB, C, bias, a, sms, st);
+  if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, mC, C, bias, a, sms, st);
+  return tc::dispatch_n<16>(N, mA, mB, mC, C, bias, a, sms, st);
 }
 
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
