@@ -38,6 +38,10 @@ struct PackedLayout {
   long long wcatT, bcat, wcat, pred_total;  // Predictor operands (own region)
 };
 
+// pixels packed per GEMM row for the GLU linears of narrow blocks (tensor-core path): 16 / 32 channels are viewed as
+// rows of 64 floats with block-diagonal weights -- 64-byte TMA rows move at a fraction of the 128-byte row rate
+inline int glu_pack(int C) { return C == 16 ? 4 : C == 32 ? 2 : 1; }
+
 constexpr int kLdl = 48;  // padded logits row: [0,20) dense, [20,40) dense_softmax, rest zero
 
 }  // namespace
@@ -99,6 +103,7 @@ int build_layouts(bsed_crnn_plan* p) {
     g.To = T / g.pt;
     g.Fo = F / g.pf;
     BSED_REQUIRE(g.To >= 1 && g.Fo >= 1, "plan: layer %d pools to nothing", i);
+    BSED_REQUIRE(((long long)T * F) % glu_pack(g.Cout) == 0, "plan: layer %d: T*F must be a multiple of %d", i, glu_pack(g.Cout));
     g.rows = (long long)T * F;
     g.prows = (long long)g.To * g.Fo;
     T = g.To;
@@ -170,9 +175,10 @@ int build_layouts(bsed_crnn_plan* p) {
     const LayerGeom& g = p->L[i];
     pk.wp[i] = ptake((long long)g.Cout * g.Cin * 9);
     pk.wd[i] = ptake((long long)g.Cout * g.Cin * 9);
-    pk.glu_wT[i] = ptake((long long)g.Cout * g.Cout);
-    pk.glu_bf[i] = ptake(g.Cout);
-    pk.glu_wgT[i] = ptake((long long)g.Cout * g.Cout);
+    const long long cp = (long long)g.Cout * glu_pack(g.Cout);
+    pk.glu_wT[i] = ptake(cp * cp);
+    pk.glu_bf[i] = ptake(cp);
+    pk.glu_wgT[i] = ptake(cp * cp);
   }
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
@@ -273,9 +279,9 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
         add(tc ? PREP_CONV_KMAJOR_FLIP : PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
     }
     // d1 != 0: K-major folded matrix [c'][c] for the tensor-core GEMM (B operand [N][K])
-    add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, tc ? 1 : 0, 0, 0, params + pl.bn_w[i],
-        params + pl.bn_b[i], params + pl.glu_b[i], packed + pk.glu_bf[i]);
-    if (tc && need_bwd) add(PREP_TRANSPOSE, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, g.Cout, g.Cout, 0);
+    add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, tc ? 1 : 0, glu_pack(g.Cout), 0,
+        params + pl.bn_w[i], params + pl.bn_b[i], params + pl.glu_b[i], packed + pk.glu_bf[i]);
+    if (tc && need_bwd) add(PREP_TRANSPOSE_BD, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, glu_pack(g.Cout));
   }
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
@@ -527,9 +533,11 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       size_t off = (size_t)runs[r].first * L.rows * L.Cout;
       long long M = (long long)runs[r].count * L.rows;
       BSED_REQUIRE(M < (1ll << 31), "crnn_forward: too many pixels");
-      if (tc)
-        BSED_TRY(tc_gemm_nt(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, M, L.Cout, L.Cout,
+      if (tc) {
+        const int pack = glu_pack(L.Cout), CP = L.Cout * pack;   // L.rows is a multiple of 4 (F is even twice over)
+        BSED_TRY(tc_gemm_nt(y + off, CP, packed + p->pk.glu_wT[i], CP, lin + off, CP, M / pack, CP, CP,
                             packed + p->pk.glu_bf[i], 0, sms, st));
+      }
       else
         BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
                          packed + p->pk.glu_bf[i], 0, st));
@@ -720,11 +728,12 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
                            (long long)gb.count[k] * L.rows, target, st));
         }
       }
+      const int pack = glu_pack(L.Cout), CP = L.Cout * pack;
       BSED_TRY(bn_bwd_prepare(bsums, G, n, L.Cout, gb, L.rows, bn, params + pl.glu_w[i], params + pl.bn_w[i],
-                              params + pl.bn_b[i], 1, tab, grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i],
+                              params + pl.bn_b[i], pack, tab, grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i],
                               grads + pl.glu_b[i], st));
-      BSED_TRY(tc_gemm_nt_bnbwd(lin + off, packed + p->pk.glu_wgT[i], dxn + off, xhat + off, M, L.Cout, L.Cout, tab, n,
-                                L.rows, gfirst_rel, sms, st));
+      BSED_TRY(tc_gemm_nt_bnbwd(lin + off, packed + p->pk.glu_wgT[i], dxn + off, xhat + off, M / pack, CP, CP, tab, n,
+                                L.rows / pack, gfirst_rel, sms, st));
     } else {
     // gate / dropout / pool backward: lin -> d_lin (in place), dxn <- direct gate path
     BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,

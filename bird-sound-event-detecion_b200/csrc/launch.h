@@ -86,7 +86,7 @@ struct PrepOp {
   float* dst;
   float* dst2;
 };
-enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8 };
+enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8, PREP_TRANSPOSE_BD = 9 };
 constexpr int kMaxPrepOps = 64;
 struct PrepTable {
   int n;

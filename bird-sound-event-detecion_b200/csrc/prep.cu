@@ -50,17 +50,38 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
     case PREP_GLU_FOLD: {
       int C = op.d0;
       if (op.d1) {
-        for (int i = tid; i < C * C; i += nth) op.dst[i] = op.aux0[i % C] * op.src[i];  // dst [c'][c] (K-major)
+        // K-major folded matrix for the tensor-core GEMM, block-diagonal over `pack` pixels per row:
+        // dst[(p*C + c')][(q*C + c)] = (p == q) * gamma[c] * Wg[c'][c]
+        const int pack = op.d2 > 0 ? op.d2 : 1, CP = C * pack;
+        for (int i = tid; i < CP * CP; i += nth) {
+          int col = i % CP, rowi = i / CP;
+          int p = rowi / C, cp = rowi % C, q = col / C, c = col % C;
+          op.dst[i] = p == q ? op.aux0[c] * op.src[(size_t)cp * C + c] : 0.f;
+        }
+        for (int j = tid; j < CP; j += nth) {
+          int cp = j % C;
+          float a = op.aux2[cp];
+          for (int c = 0; c < C; ++c) a = fmaf(op.src[(size_t)cp * C + c], op.aux1[c], a);
+          op.dst2[j] = a;
+        }
       } else {
         for (int i = tid; i < C * C; i += nth) {  // dst [c][c']
           int cp = i % C, c = i / C;
           op.dst[i] = op.aux0[c] * op.src[(size_t)cp * C + c];
         }
+        for (int cp = tid; cp < C; cp += nth) {
+          float a = op.aux2[cp];
+          for (int c = 0; c < C; ++c) a = fmaf(op.src[(size_t)cp * C + c], op.aux1[c], a);
+          op.dst2[cp] = a;
+        }
       }
-      for (int cp = tid; cp < C; cp += nth) {
-        float a = op.aux2[cp];
-        for (int c = 0; c < C; ++c) a = fmaf(op.src[(size_t)cp * C + c], op.aux1[c], a);
-        op.dst2[cp] = a;
+    } break;
+    case PREP_TRANSPOSE_BD: {  // dst[(p*C + c)][(q*C + c')] = (p == q) * src[c'][c]   (src [C][C], pack = d1)
+      const int C = op.d0, pack = op.d1, CP = C * pack;
+      for (int i = tid; i < CP * CP; i += nth) {
+        int col = i % CP, rowi = i / CP;
+        int p = rowi / C, c = rowi % C, q = col / C, cp = col % C;
+        op.dst[i] = p == q ? op.src[(size_t)cp * C + c] : 0.f;
       }
     } break;
     case PREP_TRANSPOSE: {
