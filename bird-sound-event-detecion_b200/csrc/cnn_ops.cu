@@ -20,50 +20,78 @@ __device__ __forceinline__ int group_of(const Groups& g, int clip) {
 // conv0: x [B][T][F] -> y [B][T][F][16], weights in the reference's (16,1,3,3) layout
 // grid (chunks, clip); thread -> (pixel, channel quad)
 // ---------------------------------------------------------------------------------------------
+// Each CTA owns a contiguous pixel range of one clip; a thread keeps the 36 weights of its channel quad in registers
+// and walks the range with stride 256 / nq pixels (a warp writes 512 contiguous bytes per step).  With stats != nullptr
+// the per-channel sum / sum of squares of the output (BatchNorm batch statistics) are accumulated on the way:
+// stats[(group * Cout + c) * 2 + {0, 1}].
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, Groups g, FloatPtrs w,
                                                         FloatPtrs bias, float* __restrict__ y, int T, int F,
-                                                        int Cout) {
-  __shared__ float ws[128 * 9];
-  __shared__ float bs[128];
+                                                        int Cout, long long pix_per_cta, double* __restrict__ stats) {
   const int clip = blockIdx.y;
   const int grp = group_of(g, clip);
-  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i] = w.p[grp][i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias.p[grp][i];
-  __syncthreads();
   const int nq = Cout / 4;
-  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long npix = (long long)T * F;
-  if (id >= npix * nq) return;
-  int q = (int)(id % nq);
-  int pix = (int)(id / nq);
-  int f = pix % F, t = pix / F;
-  const float* xc = x + (size_t)clip * npix;
-  float v[9];
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
-    v[tap] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
-  }
-  float o[4];
+  const int q = threadIdx.x % nq;
+  const int pstep = 256 / nq;
+  const long long npix = (long long)T * F;
+  float wr[4][9], br[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    int co = q * 4 + j;
-    float a = bs[co];
+    br[j] = bias.p[grp][q * 4 + j];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) a = fmaf(v[tap], ws[co * 9 + tap], a);
-    o[j] = a;
+    for (int tap = 0; tap < 9; ++tap) wr[j][tap] = w.p[grp][(q * 4 + j) * 9 + tap];
   }
-  float4* dst = reinterpret_cast<float4*>(y + ((size_t)clip * npix + pix) * Cout + q * 4);
-  *dst = make_float4(o[0], o[1], o[2], o[3]);
+  const float* xc = x + (size_t)clip * npix;
+  const long long pbeg = (long long)blockIdx.x * pix_per_cta;
+  long long pend = pbeg + pix_per_cta;
+  if (pend > npix) pend = npix;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long pix = pbeg + threadIdx.x / nq; pix < pend; pix += pstep) {
+    const int f = (int)(pix % F), t = (int)(pix / F);
+    float v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
+      v[tap] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = br[j];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) a = fmaf(v[tap], wr[j][tap], a);
+      o[j] = a;
+      s1[j] += a;
+      s2[j] = fmaf(a, a, s2[j]);
+    }
+    *reinterpret_cast<float4*>(y + ((size_t)clip * npix + pix) * Cout + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (!stats) return;
+  __shared__ float red[2][256][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = s1[j];
+    red[1][threadIdx.x][j] = s2[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Cout; i += 256) {
+    const int k = i / Cout, c = i % Cout;
+    float tsum = 0.f;
+    for (int r = 0; r < pstep; ++r) tsum += red[k][r * nq + c / 4][c % 4];
+    atomicAdd(stats + ((size_t)grp * Cout + c) * 2 + k, (double)tsum);
+  }
 }
 
 int conv0_fwd(const float* x, const Groups& g, const FloatPtrs& w, const FloatPtrs& bias, float* y, int T,
-              int F, int Cout, cudaStream_t st) {
-  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128, "conv0: Cout=%d", Cout);
+              int F, int Cout, double* stats, int num_sms, cudaStream_t st) {
+  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128 && 256 % (Cout / 4) == 0, "conv0: Cout=%d", Cout);
   int B = g.first[g.n - 1] + g.count[g.n - 1];
-  long long work = (long long)T * F * (Cout / 4);
-  dim3 grid(ceil_div(work, 256), B);
-  conv0_fwd_kernel<<<grid, 256, 0, st>>>(x, g, w, bias, y, T, F, Cout);
+  const long long npix = (long long)T * F;
+  long long want = (long long)num_sms * 8 / B + 1;            // ~8 CTAs per SM overall
+  long long pix_per_cta = (npix + want - 1) / want;
+  const long long gran = 256 / (Cout / 4);
+  pix_per_cta = (pix_per_cta + gran - 1) / gran * gran;
+  dim3 grid(ceil_div(npix, pix_per_cta), B);
+  conv0_fwd_kernel<<<grid, 256, 0, st>>>(x, g, w, bias, y, T, F, Cout, pix_per_cta, stats);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -127,7 +155,7 @@ int conv0_wgrad(const float* x, const float* dY, float* dW, int first_clip, int 
   BSED_REQUIRE(Cout % 4 == 0 && Cout <= 32 && (32 % (Cout / 4)) == 0 && (256 % (Cout / 4)) == 0,
                "conv0_wgrad: Cout=%d unsupported", Cout);
   long long work = (long long)T * F * (Cout / 4);
-  int iters = 16;
+  int iters = 128;   // pixels per thread between block reductions
   dim3 grid(ceil_div(work, 256LL * iters), n_clips);
   conv0_wgrad_kernel<<<grid, 256, 0, st>>>(x, dY, dW, first_clip, T, F, Cout, iters);
   BSED_CHECK_LAUNCH();

@@ -485,7 +485,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         w.p[k] = p->gparams[gi] + p->pl.conv_w[0];
         bias.p[k] = p->gparams[gi] + p->pl.conv_b[0];
       }
-      BSED_TRY(conv0_fwd(x, g, w, bias, y, L.T, L.F, L.Cout, st));
+      BSED_TRY(conv0_fwd(x, g, w, bias, y, L.T, L.F, L.Cout, train ? stats : nullptr, sms, st));   // + batch statistics
     } else {
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]);
       for (int r = 0; r < n_runs; ++r) {
@@ -521,7 +521,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     }
     if (train) {
       double* st_i = stats + (size_t)i * kMaxGroups * 128 * 2;
-      if (!tc || i == 0) BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
+      if (!tc && i > 0) BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
       // stats rows are indexed [group][C]: col_stats uses stride C, finalize too
       BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, rmean, rvar, nbt, st));
     } else {

@@ -39,7 +39,7 @@ int gru_whh_grad(const float* dG, int ldg, const float* H, int ldh, int dt, floa
 
 // ---- cnn_ops.cu
 int conv0_fwd(const float* x, const Groups& g, const FloatPtrs& w, const FloatPtrs& bias, float* y, int T,
-              int F, int Cout, cudaStream_t st);
+              int F, int Cout, double* stats, int num_sms, cudaStream_t st);
 int conv0_wgrad(const float* x, const float* dY, float* dW, int first_clip, int n_clips, int T, int F,
                 int Cout, int num_sms, cudaStream_t st);
 // mode 0: (sum a, sum a^2); mode 1: (sum a, sum a*b); out: double [group][C][2], accumulated
