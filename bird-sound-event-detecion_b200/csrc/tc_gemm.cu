@@ -761,6 +761,152 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// All-taps variant for the 3x3 weight gradient (W_CONV9 / W_PAIR).  The per-tap kernel above re-reads dY and X
+// from L2 once per tap (9-12x), which is what bounds it; here ONE CTA owns a row range and a 32-channel slice of X
+// for ALL taps: per 32-row stage it loads the dY tile once (both pixel parities in pair mode) plus the 9 shifted
+// X tiles, and keeps 9 (12) accumulators of 32 columns in TMEM (288 / 384 of the 512 columns).
+//   grid = (splits, 1, N tiles of 32 channels);   partial layout identical to tc_wgrad_kernel's with N = 32.
+// ---------------------------------------------------------------------------------------------
+constexpr int kW9Rows = 32;    // rows per stage
+constexpr int kW9Stages = 3;
+struct W9Smem {
+  static constexpr int CHUNK = kW9Rows * 128;          // [32 rows][32 channels] fp32 = 4 KB
+  static constexpr int A_BYTES = 8 * CHUNK;            // up to 4 chunks (M = 128) x 2 pixel parities
+  static constexpr int B_BYTES = 9 * CHUNK;            // 9 shifted X tiles
+  static constexpr int STAGE = (A_BYTES + B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int TOTAL = kW9Stages * STAGE + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 float* __restrict__ part, WArgs a) {
+  using S = W9Smem;
+  constexpr int N = 32;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kW9Stages * S::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kW9Stages;
+  uint64_t* tfull = bars + 2 * kW9Stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kW9Stages + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int split = blockIdx.x, nt = blockIdx.z;
+  const bool pair = a.mode == W_PAIR;
+  const int ntaps = pair ? 12 : 9;
+  const int tile_beg = split * a.tiles_per_split;
+  int tile_end = tile_beg + a.tiles_per_split;
+  if (tile_end > a.n_tiles) tile_end = a.n_tiles;
+  const int my_tiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+  int a_chunks = a.m_total / 32;
+  if (a_chunks > 4) a_chunks = 4;
+  const int a_sets = pair ? 2 : 1;                      // pixel parities
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < kW9Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int b_ch = a.b_c0 + nt * N;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (a_sets * a_chunks + 9) * S::CHUNK;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        int b = tile / a.tiles_per_clip;
+        int t0 = (tile - b * a.tiles_per_clip) * a.th;
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* sa = smem + s * S::STAGE;
+        unsigned char* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full[s], tx);
+        for (int ps = 0; ps < a_sets; ++ps)
+          for (int c = 0; c < a_chunks; ++c)
+            tma_load_4d(&mapA, sa + (ps * 4 + c) * S::CHUNK, &full[s], a.a_c0 + ps * a.pair_stride + c * 32, 0, t0, b);
+#pragma unroll
+        for (int i = 0; i < 9; ++i)   // shift (dt, d) = (i / 3 - 1, i % 3 - 1) along (t, f) [pair mode: (t, pixel pair)]
+          tma_load_4d(&mapB, sb + i * S::CHUNK, &full[s], b_ch, i % 3 - 1, t0 + i / 3 - 1, b);
+        if (++s == kW9Stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_tf32(N, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint32_t sb = sa + S::A_BYTES;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          int aset = 0, bidx = tap;
+          if (pair) {   // virtual tap (dt, j): see the table above
+            const int j = tap & 3, dt = tap >> 2;
+            aset = j >> 1;
+            bidx = dt * 3 + (j == 1 ? 0 : j == 3 ? 2 : 1);
+          }
+          const uint32_t abase = sa + aset * 4 * S::CHUNK, bbase = sb + bidx * S::CHUNK;
+#pragma unroll
+          for (int k = 0; k < kW9Rows / 8; ++k) {
+            uint64_t da = mnmajor_desc(abase + k * 1024, S::CHUNK);
+            uint64_t db = mnmajor_desc(bbase + k * 1024, S::CHUNK);
+            umma_tf32(tmem_base + tap * N, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (i == my_tiles - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      if (++s == kW9Stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;   // channel of A
+    if (my_tiles > 0) {
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+    }
+    for (int tap = 0; tap < ntaps; ++tap) {
+      float* out = part + ((((size_t)split * ntaps + tap) * gridDim.z + blockIdx.z) * kBM + row) * N;
+      float v[32];
+      if (my_tiles > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tap * N, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (row < a_chunks * 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 struct RArgs {
   int splits, ntaps, ztiles, n_tiles_n, N;
   int m_total, n_total;
@@ -771,38 +917,57 @@ struct RArgs {
 // part [split][tap][z][128][N] -> dW.  W_CONV9 / W_SINGLE: dW[m*rs + n*cs + tap*ts] += sum_split.
 // W_PAIR (C = 16 input channels, see the table above): dW[m*rs + ci*cs + (3*(dt+1) + df+1)*ts].
 // mode 3 (GLU of a 16-channel block, both operands in pair view): dW[m*rs + n*cs] += P[m][n] + P[16+m][16+n].
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, RArgs r, float* dW) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, RArgs r, float* dW) {
+  // 32 output elements per CTA; the splits are spread over 8 thread groups (lane = element, warp = split group)
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sg = threadIdx.x >> 5;
   auto P = [&](int tap, int m, int n) {
     const int z = (m / kBM) * r.n_tiles_n + n / r.N;
     const float* p0 = part + (((size_t)tap * r.ztiles + z) * kBM + m % kBM) * r.N + n % r.N;
     const size_t stride = (size_t)r.ntaps * r.ztiles * kBM * r.N;
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 8 independent loads in flight
-    int s = 0;
-    for (; s + 8 <= r.splits; s += 8) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};   // independent loads in flight
+    int s = sg;
+    for (; s + 24 < r.splits; s += 32) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += p0[(size_t)(s + u) * stride];
+      for (int u = 0; u < 4; ++u) a[u] += p0[(size_t)(s + 8 * u) * stride];
     }
-    for (; s < r.splits; ++s) a[0] += p0[(size_t)s * stride];
-    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (; s < r.splits; s += 8) a[0] += p0[(size_t)s * stride];
+    return (a[0] + a[1]) + (a[2] + a[3]);
   };
+  float acc = 0.f;
+  size_t dst = 0;
+  bool live = false;
   if (r.mode == W_PAIR) {
-    if (i >= 9 * r.m_total * 16) return;
-    const int ci = i % 16, m = (i / 16) % r.m_total, tap = i / (16 * r.m_total);
-    const int dt = tap / 3, df = tap % 3 - 1;
-    float acc;
-    if (df == 0) acc = P(dt * 4 + 0, m, ci) + P(dt * 4 + 2, m, 16 + ci);
-    else if (df == 1) acc = P(dt * 4 + 0, m, 16 + ci) + P(dt * 4 + 3, m, ci);
-    else acc = P(dt * 4 + 1, m, 16 + ci) + P(dt * 4 + 2, m, ci);
-    dW[m * r.rs + ci * r.cs + tap * r.ts] += acc;
+    if (i < 9 * r.m_total * 16) {
+      const int ci = i % 16, m = (i / 16) % r.m_total, tap = i / (16 * r.m_total);
+      const int dt = tap / 3, df = tap % 3 - 1;
+      if (df == 0) acc = P(dt * 4 + 0, m, ci) + P(dt * 4 + 2, m, 16 + ci);
+      else if (df == 1) acc = P(dt * 4 + 0, m, 16 + ci) + P(dt * 4 + 3, m, ci);
+      else acc = P(dt * 4 + 1, m, 16 + ci) + P(dt * 4 + 2, m, ci);
+      dst = m * r.rs + ci * r.cs + tap * r.ts;
+      live = true;
+    }
   } else if (r.mode == 3) {
-    if (i >= 16 * 16) return;
-    const int n = i % 16, m = i / 16;
-    dW[m * r.rs + n * r.cs] += P(0, m, n) + P(0, 16 + m, 16 + n);
-  } else {
-    if (i >= r.ntaps * r.m_total * r.n_total) return;
+    if (i < 16 * 16) {
+      const int n = i % 16, m = i / 16;
+      acc = P(0, m, n) + P(0, 16 + m, 16 + n);
+      dst = m * r.rs + n * r.cs;
+      live = true;
+    }
+  } else if (i < r.ntaps * r.m_total * r.n_total) {
     const int n = i % r.n_total, m = (i / r.n_total) % r.m_total, tap = i / (r.n_total * r.m_total);
-    dW[m * r.rs + n * r.cs + tap * r.ts] += P(tap, m, n);
+    acc = P(tap, m, n);
+    dst = m * r.rs + n * r.cs + tap * r.ts;
+    live = true;
+  }
+  __shared__ float red[8][32];
+  red[sg][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (sg == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    dW[dst] += t;
   }
 }
 
@@ -961,7 +1126,77 @@ int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xha
 }  // namespace bsed
 
 namespace bsed {
-size_t tc_wgrad_workspace_bytes(int sms) { return (size_t)(sms + 16) * 128 * 128 * sizeof(float); }
+// split-K partials: per-tap kernel <= (sms + 16) tiles of 128 x 128; all-taps kernel <= (sms + 16) x 12 taps x 128 x 32
+size_t tc_wgrad_workspace_bytes(int sms) { return (size_t)(sms + 16) * 12 * 128 * 32 * sizeof(float); }
+
+static int tc_wgrad9(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int kmode, float* dW, long long rs, long long cs,
+                     long long ts, float* part, size_t part_bytes, int sms, cudaStream_t st) {
+  const int ntaps = kmode == tc::W_PAIR ? 12 : 9;
+  const int th = tc::kW9Rows / Fv;
+  const int z = Bm.C / 32;
+  CUtensorMap mA, mB;
+  const int a_width = kmode == tc::W_PAIR ? 2 * A.C : A.c0 + A.C;
+  cuuint64_t dA[4] = {(cuuint64_t)a_width, (cuuint64_t)Fv, (cuuint64_t)T, (cuuint64_t)Bn};
+  cuuint64_t sA[3] = {(cuuint64_t)A.ld * 4, (cuuint64_t)Fv * A.ld * 4, (cuuint64_t)T * Fv * A.ld * 4};
+  cuuint32_t bA[4] = {32, (cuuint32_t)Fv, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mA, A.p, 4, dA, sA, bA, 132));
+  cuuint64_t dB[4] = {(cuuint64_t)(Bm.c0 + Bm.C), (cuuint64_t)Fv, (cuuint64_t)T, (cuuint64_t)Bn};
+  cuuint64_t sB[3] = {(cuuint64_t)Bm.ld * 4, (cuuint64_t)Fv * Bm.ld * 4, (cuuint64_t)T * Fv * Bm.ld * 4};
+  cuuint32_t bB[4] = {32, (cuuint32_t)Fv, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mB, Bm.p, 4, dB, sB, bB, 132));
+  tc::WArgs a;
+  a.tiles_per_clip = (T + th - 1) / th;
+  a.n_tiles = a.tiles_per_clip * Bn;
+  a.th = th;
+  a.T = T;
+  a.F = Fv;
+  a.mode = kmode;
+  a.dt0 = 0;
+  a.a_c0 = A.c0;
+  a.b_c0 = Bm.c0;
+  a.m_total = A.C;
+  a.n_tiles_n = z;
+  a.pair_stride = A.C;
+  int splits = sms / z;
+  if (splits < 1) splits = 1;
+  if (splits > a.n_tiles) splits = a.n_tiles;
+  a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
+  splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  size_t need = (size_t)splits * ntaps * z * 128 * 32 * sizeof(float);
+  if (part_bytes < need) {
+    bsed_set_error("tc_wgrad9: workspace %zu < %zu", part_bytes, need);
+    return BSED_E_WORKSPACE;
+  }
+  static bool configured = false;
+  if (!configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(tc::tc_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::W9Smem::TOTAL));
+    configured = true;
+  }
+  const double rows = (double)Bn * T * Fv;
+  const double taps_real = 9.0;
+  const double cin = kmode == tc::W_PAIR ? 16.0 : Bm.C;
+  ProfScope prof(PROF_WGRAD, 2.0 * rows * (kmode == tc::W_PAIR ? 2.0 : 1.0) * A.C * taps_real * cin,
+                 4.0 * (rows * A.C + rows * Bm.C + 9.0 * A.C * cin), st);
+  dim3 grid(splits, 1, z);
+  tc::tc_wgrad9_kernel<<<grid, tc::kThreads, tc::W9Smem::TOTAL, st>>>(mA, mB, part, a);
+  BSED_CHECK_LAUNCH();
+  tc::RArgs ra;
+  ra.splits = splits;
+  ra.ntaps = ntaps;
+  ra.ztiles = z;
+  ra.n_tiles_n = z;
+  ra.N = 32;
+  ra.m_total = A.C;
+  ra.n_total = Bm.C;
+  ra.mode = kmode;
+  ra.rs = rs;
+  ra.cs = cs;
+  ra.ts = ts;
+  const int n = kmode == tc::W_PAIR ? 9 * A.C * 16 : 9 * A.C * Bm.C;
+  tc::wgrad_reduce_kernel<<<ceil_div(n, 32), 256, 0, st>>>(part, ra, dW);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
 
 // D[m][n][tap] (+)= sum_rows A[row][a.c0 + m] * Bm[row + shift(tap)][b.c0 + n]; element (m, n, tap) lands at
 // dW[m*rs + n*cs + tap*ts].  Rows are the pixels of a (Bn, T, Fv) grid, row stride ld floats.
@@ -974,6 +1209,11 @@ int tc_wgrad_ex(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int mode, int 
   BSED_REQUIRE(Fv >= 1 && Fv <= 64 && 64 % Fv == 0, "tc_wgrad: F=%d must divide 64", Fv);
   BSED_REQUIRE(A.ld % 4 == 0 && Bm.ld % 4 == 0, "tc_wgrad: leading dimensions must be multiples of 4");
   const int kmode = mode == 3 ? tc::W_SINGLE : mode;
+  // all-taps kernel only where X is narrow (one 32-channel tile): every tcgen05.mma re-reads its 128 x 8 A tile from
+  // shared memory whatever N is, so splitting wide X into 32-column MMAs costs more than the L2 traffic it saves
+  if ((kmode == tc::W_CONV9 || kmode == tc::W_PAIR) && A.C <= 128 && Bm.C == 32 && 32 % Fv == 0 &&
+      !getenv("BSED_WGRAD_PER_TAP"))
+    return tc_wgrad9(A, Bm, Bn, T, Fv, kmode, dW, rs, cs, ts, part, part_bytes, sms, st);
   const int N = Bm.C >= 128 ? 128 : Bm.C;
   BSED_REQUIRE(Bm.C % N == 0 && (N == 32 || N == 64 || N == 128), "tc_wgrad: B channels %d", Bm.C);
   const int n_tiles_n = Bm.C / N, m_tiles = (A.C + 127) / 128;
@@ -1037,7 +1277,7 @@ int tc_wgrad_ex(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int mode, int 
   ra.cs = cs;
   ra.ts = ts;
   const int n = mode == 2 ? 9 * A.C * 16 : mode == 3 ? 256 : ntaps * A.C * Bm.C;
-  tc::wgrad_reduce_kernel<<<ceil_div(n, 128), 128, 0, st>>>(part, ra, dW);
+  tc::wgrad_reduce_kernel<<<ceil_div(n, 32), 256, 0, st>>>(part, ra, dW);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

@@ -23,7 +23,8 @@ def load(path):
 
 def main():
     rows = load(sys.argv[1])
-    which = int(sys.argv[2]) if len(sys.argv) > 2 else -1
+    nums = [a for a in sys.argv[2:] if a.lstrip("-").isdigit()]
+    which = int(nums[0]) if nums else -1
     idx = [i for i, r in enumerate(rows) if "opt_ema" in r[0]]
     a, b = idx[which - 1] + 1, idx[which] + 1
     step = rows[a:b]
