@@ -212,23 +212,43 @@ def run_b200(args):
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     value = (N_SYN + N_REAL) * world * args.steps / (ms * 1e-3)
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the losses, every step
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the losses, every step.  The copies of step i+1 are
+    # issued on a copy stream while step i computes (double-buffered device inputs), as a training loop's prefetcher
+    # does; every step still moves its own inputs host -> device and its losses device -> host inside the timed region.
     hx, hxe, hxs, hts = [t.cpu().pin_memory() for t in (x, x_ema, xs, ts)]
-    dx, dxe, dxs, dts = [torch.empty_like(t) for t in (x, x_ema, xs, ts)]
+    dbuf = [[torch.empty_like(t) for t in (x, x_ema, xs, ts)] for _ in range(2)]
     hloss = torch.empty(4).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])                     # the step that last read this slot is done
+            for d, h in zip(dbuf[slot], (hx, hxe, hxs, hts)):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    for sl in (0, 1):
+        freed[sl].record(torch.cuda.current_stream())
+    e2e_state = {"primed": False}
 
     def e2e_step(i):
-        dx.copy_(hx, non_blocking=True)
-        dxe.copy_(hxe, non_blocking=True)
-        dxs.copy_(hxs, non_blocking=True)
-        dts.copy_(hts, non_blocking=True)
+        slot = i & 1
+        if not e2e_state["primed"]:
+            h2d(slot)
+            e2e_state["primed"] = True
+        h2d(slot ^ 1)                                               # next step's inputs, overlapping this step
+        torch.cuda.current_stream().wait_event(ready[slot])
+        dx, dxe, dxs, dts = dbuf[slot]
         losses = trainer.step(dx, dxe, dxs, dts, 1000 + i, rampup_len)
+        freed[slot].record(torch.cuda.current_stream())
         hloss.copy_(losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss (reference: loss.item())
 
     ms_e2e = timed(e2e_step, args.steps, 1)
     e2e = (N_SYN + N_REAL) * world * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(t.numel() * 4 for t in (hx, hxe, hxs, hts))
+    h2d_bytes = sum(t.numel() * 4 for t in (hx, hxe, hxs, hts))
 
     # ---- frontend: audio resident in HBM -> log-mel (second half of the metric)
     fe_clips = clips.repeat(16, 1)[:256].contiguous()                 # 256 clips = 328 MB > L2
@@ -260,7 +280,7 @@ def run_b200(args):
                        "clips_per_step_per_gpu": 24, "parallelism": f"dp{world} (NCCL sum all-reduce of the 4.47 MB flat gradient)",
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",
                        "step_gflop_algorithmic": STEP_FLOP / 1e9},
-            "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+            "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_timed),
             "roofline": {"kernel": ("tc_kmajor_kernel (tcgen05 tf32 implicit-GEMM 3x3 conv forward + data gradient, TMA-fed)"
