@@ -128,6 +128,10 @@ int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, i
 // (stats[(group * Cout + c) * 2 + {0,1}], group = last k with clip >= gfirst[k], clips relative to X)
 int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
                      int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
+// column-tiled variant with shared-memory halo reuse (tc_conv.cu); no accumulate mode
+bool tc_conv_col_supported(int F, int Cin, int Cout);
+int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 

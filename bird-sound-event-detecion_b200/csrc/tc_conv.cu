@@ -1,0 +1,389 @@
+// tc_conv.cu -- column-tiled implicit-GEMM 3x3 convolution (forward / data gradient) on tcgen05 tf32 with the nine
+// taps served from ONE shared-memory copy of the input halo.
+//
+// The row-tiled kernel of tc_gemm.cu fetches every activation tile from L2 once per tap (9x), and with it the layer's
+// weights once per 128 pixels: it is bound by the L2 -> SM TMA bandwidth (~8 TB/s chip-wide, profiles/r01_*), not by
+// the tensor pipe.  Here a tile is a COLUMN segment: 128 consecutive time steps t at one frequency bin f, G = 2
+// neighbouring bins per CTA step.  Per 32-channel chunk the producer loads the G + 2 columns f0-1 .. f0+G as boxes of
+// 130 rows (t0-1 .. t0+128; out-of-range rows / columns are the TMA's zero fill = the convolution's padding).  A tap
+// (dt, df) of bin f0+g is then just a descriptor into column copy g+df+1, starting (dt+1) rows in: 4 boxes of 130 rows
+// replace 2 x 9 boxes of 128 rows (0.23x the activation traffic), and each weight tile feeds both bins (0.5x).
+// Shifting a K-major SWIZZLE_128B operand by whole 128-byte rows needs nothing but the new start address: the tensor
+// core applies the swizzle XOR to absolute shared-memory address bits (measured on B200: the descriptor's base-offset
+// field must stay 0; setting it to (address >> 7) & 7 gives wrong products).
+//
+// Warp roles, pipelines and the epilogue (TMEM -> swizzled staging -> TMA store, batch statistics from the staged
+// tile) follow tc_kmajor_kernel.
+#include "tc_common.cuh"
+
+namespace bsed {
+namespace tc {
+
+constexpr int kG = 2;               // frequency bins per CTA step
+constexpr int kHaloRows = 130;      // t0-1 .. t0+128
+constexpr int kACopy = 17 * 1024;   // one column copy: 130 rows x 128 B, padded to the 1024-byte swizzle repeat
+constexpr int kAStages = 2;
+
+struct CArgs {
+  int n_tiles, fgroups, tblocks;   // tile = (clip, f group, t block)
+  int T, F;
+  int cpt;                         // 32-channel chunks of the input
+  int rb;                          // weights resident in shared memory (all 9 * cpt tiles)
+  int bstages;                     // weight ring depth (rb == 0)
+  int debug;
+  double* stats;
+  int stats_groups;
+  int gfirst[kMaxGroups];
+};
+
+// K-major SWIZZLE_128B descriptor whose start may sit on any 128-byte row of the 1024-byte swizzle repeat
+__device__ __forceinline__ uint64_t kmajor_desc_rows(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int N>
+struct CSmem {
+  static constexpr int KCH = 32;
+  static constexpr int A_STAGE = (kG + 2) * kACopy;
+  static constexpr int B_TILE = N * KCH * 4;                          // one tap, one chunk
+  static constexpr int B_STRIDE = (B_TILE + 1023) / 1024 * 1024;
+  static constexpr int HW = N < 64 ? N : 64;                          // columns staged per pass
+  static constexpr int STG_BYTES = kBM * HW * 4;
+  static constexpr int BAR_BYTES = 512;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapC, const float* __restrict__ bias, CArgs a) {
+  using S = CSmem<N>;
+  constexpr int KCH = S::KCH;
+  constexpr uint32_t TMEM_COLS = (2 * kG * N <= 64) ? 64 : (2 * kG * N <= 128) ? 128 : (2 * kG * N <= 256) ? 256 : 512;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nk = 9 * a.cpt;
+  const int nb = a.rb ? nk : a.bstages;                               // weight tiles held in shared memory
+  unsigned char* sB = smem + kAStages * S::A_STAGE;
+  unsigned char* stg = sB + nb * S::B_STRIDE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + S::STG_BYTES);
+  uint64_t* afull = bars;
+  uint64_t* aempty = bars + kAStages;
+  uint64_t* bfull = bars + 2 * kAStages;          // up to 16 weight stages
+  uint64_t* bempty = bfull + 16;
+  uint64_t* tfull = bempty + 16;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* rbfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbfull + 1);
+  float* sbias = reinterpret_cast<float*>(stg + S::STG_BYTES + S::BAR_BYTES);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    prefetch_tmap(&mapC);
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < 16; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(rbfull, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_clip = a.fgroups * a.tblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      if (a.rb) {
+        mbar_expect_tx(rbfull, nk * S::B_TILE);
+        for (int i = 0; i < nk; ++i) tma_load_2d(&mapB, sB + i * S::B_STRIDE, rbfull, i * KCH, 0);
+      }
+      // flat sequence of (tile, chunk) steps; the activation columns of step i + 1 are requested BEFORE the nine weight
+      // tiles of step i (which are paced by the MMAs through the weight ring), so they land while step i computes
+      const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int steps = my_tiles * a.cpt;
+      auto issue_a = [&](int step) {
+        const int tile = blockIdx.x + (step / a.cpt) * gridDim.x, ch = step % a.cpt;
+        const int b = tile / per_clip, r = tile - b * per_clip;
+        const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
+        mbar_wait(&aempty[sa], pha ^ 1);
+        unsigned char* dst = smem + sa * S::A_STAGE;
+        mbar_expect_tx(&afull[sa], (kG + 2) * kHaloRows * KCH * 4);
+#pragma unroll
+        for (int j = 0; j < kG + 2; ++j) tma_load_4d(&mapA, dst + j * kACopy, &afull[sa], ch * KCH, f0 - 1 + j, t0 - 1, b);
+        if (++sa == kAStages) {
+          sa = 0;
+          pha ^= 1;
+        }
+      };
+      if (steps > 0) issue_a(0);
+      for (int step = 0; step < steps; ++step) {
+        if (step + 1 < steps) issue_a(step + 1);
+        if (!a.rb) {
+          const int ch = step % a.cpt;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bempty[sb], phb ^ 1);
+            mbar_expect_tx(&bfull[sb], S::B_TILE);
+            tma_load_2d(&mapB, sB + sb * S::B_STRIDE, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
+            if (++sb == a.bstages) {
+              sb = 0;
+              phb ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    int it = 0;
+    if (a.rb) mbar_wait(rbfull, 0);
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t ab_ph = (it >> 1) & 1;
+      mbar_wait(&tempty[ab], ab_ph ^ 1);
+      tc_fence_after();
+      for (int ch = 0; ch < a.cpt; ++ch) {
+        mbar_wait(&afull[sa], pha);
+        tc_fence_after();
+        const uint32_t abase = smem_u32(smem + sa * S::A_STAGE);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dt = tap / 3 - 1, df = tap % 3 - 1;
+          uint32_t bbase;
+          if (a.rb) {
+            bbase = smem_u32(sB + (tap * a.cpt + ch) * S::B_STRIDE);
+          } else {
+            mbar_wait(&bfull[sb], phb);
+            tc_fence_after();
+            bbase = smem_u32(sB + sb * S::B_STRIDE);
+          }
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+              const uint32_t arow = abase + (g + df + 1) * kACopy + (dt + 1) * 128;
+              const uint32_t d_tmem = tmem_base + (ab * kG + g) * N;
+#pragma unroll
+              for (int k = 0; k < KCH / 8; ++k) {
+                const uint64_t da = kmajor_desc_rows(arow + k * 32);
+                const uint64_t db = kmajor_desc<128>(bbase + k * 32);
+                umma_tf32(d_tmem, da, db, idesc, (ch | tap | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (!a.rb) umma_commit(&bempty[sb]);
+            if (tap == 8) {
+              umma_commit(&aempty[sa]);
+              if (ch == a.cpt - 1) umma_commit(&tfull[ab]);
+            }
+          }
+          __syncwarp();
+          if (!a.rb && ++sb == a.bstages) {
+            sb = 0;
+            phb ^= 1;
+          }
+        }
+        if (++sa == kAStages) {
+          sa = 0;
+          pha ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    constexpr int HW = S::HW;
+    constexpr int CW = N >= 32 ? 32 : 16;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    const uint32_t sbias_addr = smem_u32(sbias);
+    const uint32_t stg_addr = smem_u32(stg);
+    auto chunk_addr = [&](int r, int c4) -> uint32_t {
+      if (CW == 32) return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4));
+      return (uint32_t)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
+    };
+    // thread `row` owns output channels row (pass 0) and 64 + row (pass 1) for the statistics
+    double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
+    int st_grp = -1;
+    auto flush_stats = [&]() {
+      if (st_grp >= 0) {
+#pragma unroll
+        for (int h = 0; h < N / HW; ++h)
+          if (row < HW) {
+            atomicAdd(a.stats + ((size_t)st_grp * N + h * HW + row) * 2 + 0, st_sum[h]);
+            atomicAdd(a.stats + ((size_t)st_grp * N + h * HW + row) * 2 + 1, st_sq[h]);
+          }
+      }
+      st_sum[0] = st_sum[1] = st_sq[0] = st_sq[1] = 0.0;
+    };
+    int it = 0, pass_no = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t ab_ph = (it >> 1) & 1;
+      const int b = tile / per_clip, r = tile - b * per_clip;
+      const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
+      const int valid_rows = a.T - t0 < kBM ? a.T - t0 : kBM;
+      if (a.stats) {
+        int gi = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxGroups; ++k)
+          if (k < a.stats_groups && b >= a.gfirst[k]) gi = k;
+        if (gi != st_grp) {
+          flush_stats();
+          st_grp = gi;
+        }
+      }
+      mbar_wait(&tfull[ab], ab_ph);
+      tc_fence_after();
+      for (int g = 0; g < kG; ++g) {
+        const uint32_t taddr = tmem_base + (ab * kG + g) * N + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int h = 0; h < N / HW; ++h, ++pass_no) {
+          if (pass_no > 0) {      // staging free: previous TMA stores have read it, statistics pass finished
+            if (leader) bulk_wait_read0();
+            epi_barrier();
+          }
+#pragma unroll 1
+          for (int c0 = 0; c0 < HW; c0 += CW) {
+            float v[CW];
+            if constexpr (CW == 32) tmem_ld32(taddr + h * HW + c0, v);
+            else tmem_ld16(taddr + h * HW + c0, v);
+            const uint32_t sub = stg_addr + (c0 / CW) * (kBM * CW * 4);
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+              const float4 bv = lds128(sbias_addr + (h * HW + c0 + j) * 4);
+              sts128(sub + chunk_addr(row, j / 4), make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w));
+            }
+          }
+          if (g == kG - 1 && h == N / HW - 1) {   // accumulators of this step fully read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[ab]);
+          }
+          fence_proxy_async();
+          epi_barrier();
+          if (leader && a.debug != 1) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < HW; c0 += CW)
+              tma_store_4d(&mapC, stg + (c0 / CW) * (kBM * CW * 4), h * HW + c0, f0 + g, t0, b, false);
+            bulk_commit();
+          }
+          if (a.stats && row < HW) {
+            const int c = row;
+            const uint32_t cbase = stg_addr + (c / CW) * (kBM * CW * 4) + (c & 3) * 4;
+            const int c4 = (c % CW) >> 2;
+            float s1 = 0.f, s2 = 0.f;
+            for (int rr = 0; rr < valid_rows; ++rr) {
+              const float x = lds32(cbase + chunk_addr(rr, c4));
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            st_sum[h] += (double)s1;
+            st_sq[h] += (double)s2;
+          }
+        }
+      }
+    }
+    if (a.stats) flush_stats();
+    if (leader) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int N>
+static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const float* bias, CArgs& a,
+                      int sms, cudaStream_t st) {
+  using S = CSmem<N>;
+  const int nk = 9 * a.cpt;
+  const long long fixed = (long long)kAStages * S::A_STAGE + S::STG_BYTES + S::BAR_BYTES + 512 + 1024;
+  const long long budget = 227 * 1024 - fixed;
+  if ((long long)nk * S::B_STRIDE <= budget && (long long)nk * S::B_STRIDE <= 24 * 1024) {
+    a.rb = 1;
+    a.bstages = 0;
+  } else {
+    a.rb = 0;
+    long long bs = budget / S::B_STRIDE;
+    a.bstages = (int)(bs > 9 ? 9 : bs);
+    if (a.bstages < 2) {
+      bsed_set_error("tc_conv_col: no room for the weight ring (N=%d)", N);
+      return BSED_E_INVALID;
+    }
+  }
+  const size_t smem_bytes = (size_t)(fixed + (long long)(a.rb ? nk : a.bstages) * S::B_STRIDE);
+  auto kern = tc_conv_col_kernel<N>;
+  static size_t configured = 0;
+  if (smem_bytes > configured) {
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    configured = smem_bytes;
+  }
+  int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  kern<<<grid, kThreads, smem_bytes, st>>>(mA, mB, mC, bias, a);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+}  // namespace tc
+
+bool tc_conv_col_supported(int F, int Cin, int Cout) {
+  return F >= 8 && F % tc::kG == 0 && Cin % 32 == 0 && (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) &&
+         !getenv("BSED_CONV_ROW_TILES");
+}
+
+// Y[B][T][F][Cout] = conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin] (k = tap*Cin + ci)
+int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
+                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st) {
+  BSED_REQUIRE(tc_conv_col_supported(F, Cin, Cout), "tc_conv3x3_col: F=%d Cin=%d Cout=%d", F, Cin, Cout);
+  const int CW = Cout >= 32 ? 32 : 16;
+  CUtensorMap mA, mB, mC;
+  cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sA[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
+  cuuint32_t bA[4] = {32, 1, (cuuint32_t)tc::kHaloRows, 1};
+  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, 128));
+  cuuint64_t dB[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+  cuuint64_t sB[1] = {(cuuint64_t)9 * Cin * 4};
+  cuuint32_t bB[2] = {32, (cuuint32_t)Cout};
+  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, 128));
+  cuuint64_t dC[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sC[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
+  cuuint32_t bC[4] = {(cuuint32_t)CW, 1, 128, 1};
+  BSED_TRY(tc::make_map(&mC, Y, 4, dC, sC, bC, CW * 4, true));
+  tc::CArgs a;
+  a.fgroups = F / tc::kG;
+  a.tblocks = (T + 127) / 128;
+  a.n_tiles = B * a.fgroups * a.tblocks;
+  a.T = T;
+  a.F = F;
+  a.cpt = Cin / 32;
+  a.debug = tc_debug();
+  a.stats = stats;
+  a.stats_groups = stats ? stats_groups : 0;
+  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = stats && k < stats_groups ? gfirst[k] : 0;
+  ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
+                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
+  switch (Cout) {
+    case 16: return tc::launch_col<16>(mA, mB, mC, bias, a, sms, st);
+    case 32: return tc::launch_col<32>(mA, mB, mC, bias, a, sms, st);
+    case 64: return tc::launch_col<64>(mA, mB, mC, bias, a, sms, st);
+    default: return tc::launch_col<128>(mA, mB, mC, bias, a, sms, st);
+  }
+}
+
+}  // namespace bsed

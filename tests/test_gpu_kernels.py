@@ -154,7 +154,11 @@ TF32_REL = 2e-3
 
 @pytest.mark.parametrize("B,T,Fq,Cin,Cout", [(2, 37, 16, 32, 32), (1, 20, 8, 64, 128), (3, 11, 2, 128, 128),
                                              (2, 9, 4, 32, 16), (1, 313, 1, 128, 128), (2, 5, 64, 16, 16),
-                                             (1, 627, 64, 16, 32), (2, 313, 32, 32, 64), (2, 40, 128, 16, 32)])
+                                             (1, 627, 64, 16, 32), (2, 313, 32, 32, 64), (2, 40, 128, 16, 32),
+                                             # column-tiled halo kernel (F >= 8, Cin % 32 == 0): partial t blocks,
+                                             # every output width, weights resident / ringed
+                                             (2, 313, 16, 64, 128), (1, 130, 8, 128, 128), (3, 129, 64, 32, 16),
+                                             (1, 257, 32, 64, 32), (2, 128, 8, 128, 64), (1, 1, 8, 32, 32)])
 def test_conv3x3_tensor_cores(B, T, Fq, Cin, Cout):
     from bsed_b200 import engine
     x = _rand(B, Cin, T, Fq, seed=10)
