@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   if (rend > rows_per_clip) rend = rows_per_clip;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   if (r0 < rstep) {
-    constexpr int U = 4;   // rows in flight per thread
+    constexpr int U = 2;   // rows in flight per thread
     const float* abase = a + (size_t)clip * rows_per_clip * C + q * 4;
     const float* bbase = MODE == 1 ? b + (size_t)clip * rows_per_clip * C + q * 4 : nullptr;
     for (long long r = rbeg + r0; r < rend; r += (long long)U * rstep) {
