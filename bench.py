@@ -289,11 +289,17 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_timed),
-            "roofline": {"kernel": ("tc_kmajor_kernel (tcgen05 tf32 implicit-GEMM 3x3 conv forward + data gradient, TMA-fed)"
+            "roofline": {"kernel": ("tc_conv_col_kernel + tc_kmajor_kernel (tcgen05 tf32 implicit-GEMM 3x3 conv forward + data "
+                                    "gradient, TMA-fed; all such launches of the step)"
                                     if trainer.plan.precision == "tf32" else
                                     "gemm_nn_kernel<ConvRows> (implicit-GEMM 3x3 conv forward + data gradient, fp32 SIMT)"),
                          "bound": "tensor", "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None, "traffic": None,
+                         "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None,
+                         # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 18 conv launches of one step,
+                         # per launch (profiles/r01_ncu_tc_kernels.md); algorithmic bytes per launch beside it
+                         "traffic": 3.899e7 if trainer.plan.precision == "tf32" else None,
+                         "traffic_unit": "bytes per launch (average over the conv forward + data-gradient launches)",
+                         "algorithmic_bytes_per_launch": pb.value / pn.value if pn.value else None,
                          "peak_source": peaks["source"] + " bf16 sustained (tf32 nominal dense peak is half of bf16)",
                          "launches": pn.value,
                          "share_of_step": pm.value / ms if ms else None,
