@@ -32,7 +32,7 @@ struct ParamLayout {
 
 struct PackedLayout {
   long long wp[BSED_MAX_CNN_LAYERS], wd[BSED_MAX_CNN_LAYERS], glu_wT[BSED_MAX_CNN_LAYERS],
-      glu_bf[BSED_MAX_CNN_LAYERS], glu_wgT[BSED_MAX_CNN_LAYERS];
+      glu_bf[BSED_MAX_CNN_LAYERS], glu_wgT[BSED_MAX_CNN_LAYERS], wpair[BSED_MAX_CNN_LAYERS], bpair[BSED_MAX_CNN_LAYERS];
   long long wihT[4], bih[4], whhT[4], whh[4], bhh[4], wih_cat[4];
   long long total;
   long long wcatT, bcat, wcat, pred_total;  // Predictor operands (own region)
@@ -41,6 +41,11 @@ struct PackedLayout {
 // pixels packed per GEMM row for the GLU linears of narrow blocks (tensor-core path): 16 / 32 channels are viewed as
 // rows of 64 floats with block-diagonal weights -- 64-byte TMA rows move at a fraction of the 128-byte row rate
 inline int glu_pack(int C) { return C == 16 ? 4 : C == 32 ? 2 : 1; }
+
+// forward conv of a 16-input-channel block on the column-tiled kernel: two pixels per row (32 floats in, 2*Cout out)
+inline bool conv_pair_ok(const LayerGeom& g) {
+  return g.Cin == 16 && g.F % 2 == 0 && 2 * g.Cout <= 128 && tc_conv_col_supported(g.F / 2, 32, 2 * g.Cout);
+}
 
 constexpr int kLdl = 48;  // padded logits row: [0,20) dense, [20,40) dense_softmax, rest zero
 
@@ -175,6 +180,8 @@ int build_layouts(bsed_crnn_plan* p) {
     const LayerGeom& g = p->L[i];
     pk.wp[i] = ptake((long long)g.Cout * g.Cin * 9);
     pk.wd[i] = ptake((long long)g.Cout * g.Cin * 9);
+    pk.wpair[i] = ptake(g.Cin == 16 ? 36LL * g.Cin * g.Cout : 0);   // pixel-pair conv weights (16-channel input)
+    pk.bpair[i] = ptake(g.Cin == 16 ? 2LL * g.Cout : 0);
     const long long cp = (long long)g.Cout * glu_pack(g.Cout);
     pk.glu_wT[i] = ptake(cp * cp);
     pk.glu_bf[i] = ptake(cp);
@@ -274,6 +281,9 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
   for (int i = 0; i < c.n_cnn; ++i) {
     const LayerGeom& g = p->L[i];
     if (i > 0) {
+      if (tc && conv_pair_ok(g))
+        add(PREP_CONV_PAIR, params + pl.conv_w[i], packed + pk.wpair[i], g.Cout, g.Cin, 0, 0, params + pl.conv_b[i], nullptr,
+            nullptr, packed + pk.bpair[i]);
       add(tc ? PREP_CONV_KMAJOR : PREP_CONV_PACK, params + pl.conv_w[i], packed + pk.wp[i], g.Cout, g.Cin);
       if (need_bwd)
         add(tc ? PREP_CONV_KMAJOR_FLIP : PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
@@ -502,8 +512,12 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
               gfirst_rel[ng++] = g.first[k] - runs[r].first;
             }
           double* st_run = train ? stats + (size_t)i * kMaxGroups * 128 * 2 + (size_t)gbase * L.Cout * 2 : nullptr;
-          BSED_TRY(tc_conv3x3_stats(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st_run, ng,
-                                    gfirst_rel, sms, st));
+          if (conv_pair_ok(L))
+            BSED_TRY(tc_conv3x3_col(xr, packed + p->pk.wpair[i], yr, runs[r].count, L.T, L.F / 2, 32, 2 * L.Cout,
+                                    packed + p->pk.bpair[i], st_run, ng, gfirst_rel, sms, st, L.Cout));
+          else
+            BSED_TRY(tc_conv3x3_stats(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st_run, ng,
+                                      gfirst_rel, sms, st));
         } else {
           BSED_TRY(conv3x3_nn(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st));
         }

@@ -86,7 +86,7 @@ struct PrepOp {
   float* dst;
   float* dst2;
 };
-enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8, PREP_TRANSPOSE_BD = 9 };
+enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8, PREP_TRANSPOSE_BD = 9, PREP_CONV_PAIR = 10 };
 constexpr int kMaxPrepOps = 64;
 struct PrepTable {
   int n;
@@ -130,8 +130,9 @@ int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, in
                      int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
 // column-tiled variant with shared-memory halo reuse (tc_conv.cu); no accumulate mode
 bool tc_conv_col_supported(int F, int Cin, int Cout);
+// stats_c: number of true channels the statistics fold onto (output column c counts for channel c % stats_c)
 int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
+                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st, int stats_c = 0);
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 

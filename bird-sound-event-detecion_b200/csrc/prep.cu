@@ -76,6 +76,23 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
         }
       }
     } break;
+    case PREP_CONV_PAIR: {
+      // 16-input-channel block viewed two pixels per row: K-major weights of the equivalent 3x3 convolution over
+      // pixel PAIRS, dst [(par, co)][tap' = (dt, dg)][(p', ci)] = W[co][ci][dt][df], df = 2*dg + p' - par (0 if |df| > 1);
+      // dst2 [(par, co)] = bias[co]
+      const int Cout = op.d0, Cin = op.d1;
+      const int K = 9 * 2 * Cin, n = 2 * Cout * K;
+      for (int i = tid; i < n; i += nth) {
+        const int k = i % K, rowi = i / K;
+        const int par = rowi / Cout, co = rowi % Cout;
+        const int tap = k / (2 * Cin), pc = k % (2 * Cin);
+        const int pp = pc / Cin, ci = pc % Cin;
+        const int dt = tap / 3, dg = tap % 3 - 1;
+        const int df = 2 * dg + pp - par;
+        op.dst[i] = (df >= -1 && df <= 1) ? op.src[((size_t)co * Cin + ci) * 9 + dt * 3 + (df + 1)] : 0.f;
+      }
+      for (int j = tid; j < 2 * Cout; j += nth) op.dst2[j] = op.aux0[j % Cout];
+    } break;
     case PREP_TRANSPOSE_BD: {  // dst[(p*C + c)][(q*C + c')] = (p == q) * src[c'][c]   (src [C][C], pack = d1)
       const int C = op.d0, pack = op.d1, CP = C * pack;
       for (int i = tid; i < CP * CP; i += nth) {

@@ -32,7 +32,7 @@ struct CArgs {
   int bstages;                     // weight ring depth (rb == 0)
   int debug;
   double* stats;
-  int stats_groups;
+  int stats_groups, stats_c;       // statistics fold output column c onto channel c % stats_c
   int gfirst[kMaxGroups];
 };
 
@@ -107,8 +107,8 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
+      int sb = 0;
+      uint32_t phb = 0;
       if (a.rb) {
         mbar_expect_tx(rbfull, nk * S::B_TILE);
         for (int i = 0; i < nk; ++i) tma_load_2d(&mapB, sB + i * S::B_STRIDE, rbfull, i * KCH, 0);
@@ -117,26 +117,26 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       // tiles of step i (which are paced by the MMAs through the weight ring), so they land while step i computes
       const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const int steps = my_tiles * a.cpt;
-      auto issue_a = [&](int step) {
+      // The column copies of step i + 1 are interleaved one by one with the weight tiles of step i: a 68 KB burst of
+      // activation boxes ahead of them in the TMA queue would add its whole service time to the weight tiles' latency.
+      auto issue_a = [&](int step, int j) {   // column copy j of step `step`
         const int tile = blockIdx.x + (step / a.cpt) * gridDim.x, ch = step % a.cpt;
         const int b = tile / per_clip, r = tile - b * per_clip;
         const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
-        mbar_wait(&aempty[sa], pha ^ 1);
-        unsigned char* dst = smem + sa * S::A_STAGE;
-        mbar_expect_tx(&afull[sa], (kG + 2) * kHaloRows * KCH * 4);
-#pragma unroll
-        for (int j = 0; j < kG + 2; ++j) tma_load_4d(&mapA, dst + j * kACopy, &afull[sa], ch * KCH, f0 - 1 + j, t0 - 1, b);
-        if (++sa == kAStages) {
-          sa = 0;
-          pha ^= 1;
+        const int stage = step % kAStages;
+        if (j == 0) {
+          mbar_wait(&aempty[stage], ((step / kAStages) & 1) ^ 1);
+          mbar_expect_tx(&afull[stage], (kG + 2) * kHaloRows * KCH * 4);
         }
+        tma_load_4d(&mapA, smem + stage * S::A_STAGE + j * kACopy, &afull[stage], ch * KCH, f0 - 1 + j, t0 - 1, b);
       };
-      if (steps > 0) issue_a(0);
+      if (steps > 0)
+        for (int j = 0; j < kG + 2; ++j) issue_a(0, j);
       for (int step = 0; step < steps; ++step) {
-        if (step + 1 < steps) issue_a(step + 1);
-        if (!a.rb) {
-          const int ch = step % a.cpt;
-          for (int tap = 0; tap < 9; ++tap) {
+        const int ch = step % a.cpt;
+        for (int tap = 0; tap < 9; ++tap) {
+          if (step + 1 < steps && (tap & 1) == 0 && tap / 2 < kG + 2) issue_a(step + 1, tap / 2);
+          if (!a.rb) {
             mbar_wait(&bempty[sb], phb ^ 1);
             mbar_expect_tx(&bfull[sb], S::B_TILE);
             tma_load_2d(&mapB, sB + sb * S::B_STRIDE, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
@@ -226,8 +226,9 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int h = 0; h < N / HW; ++h)
           if (row < HW) {
-            atomicAdd(a.stats + ((size_t)st_grp * N + h * HW + row) * 2 + 0, st_sum[h]);
-            atomicAdd(a.stats + ((size_t)st_grp * N + h * HW + row) * 2 + 1, st_sq[h]);
+            const int c = (h * HW + row) % a.stats_c;
+            atomicAdd(a.stats + ((size_t)st_grp * a.stats_c + c) * 2 + 0, st_sum[h]);
+            atomicAdd(a.stats + ((size_t)st_grp * a.stats_c + c) * 2 + 1, st_sq[h]);
           }
       }
       st_sum[0] = st_sum[1] = st_sq[0] = st_sq[1] = 0.0;
@@ -349,7 +350,7 @@ bool tc_conv_col_supported(int F, int Cin, int Cout) {
 
 // Y[B][T][F][Cout] = conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin] (k = tap*Cin + ci)
 int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st) {
+                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st, int stats_c) {
   BSED_REQUIRE(tc_conv_col_supported(F, Cin, Cout), "tc_conv3x3_col: F=%d Cin=%d Cout=%d", F, Cin, Cout);
   const int CW = Cout >= 32 ? 32 : 16;
   CUtensorMap mA, mB, mC;
@@ -375,6 +376,7 @@ int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int 
   a.debug = tc_debug();
   a.stats = stats;
   a.stats_groups = stats ? stats_groups : 0;
+  a.stats_c = stats_c > 0 ? stats_c : Cout;
   for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = stats && k < stats_groups ? gfirst[k] : 0;
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
