@@ -86,7 +86,7 @@ struct PrepOp {
   float* dst;
   float* dst2;
 };
-enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8, PREP_TRANSPOSE_BD = 9, PREP_CONV_PAIR = 10 };
+enum { PREP_CONV_PACK = 0, PREP_CONV_PACK_FLIP = 1, PREP_GLU_FOLD = 2, PREP_TRANSPOSE = 3, PREP_COPY = 4, PREP_ZERO = 5, PREP_ZERO_COLS = 6, PREP_CONV_KMAJOR = 7, PREP_CONV_KMAJOR_FLIP = 8, PREP_TRANSPOSE_BD = 9, PREP_CONV_PAIR = 10, PREP_GATE_TAB = 11 };
 constexpr int kMaxPrepOps = 64;
 struct PrepTable {
   int n;
@@ -136,6 +136,9 @@ int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int 
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st);
 
+int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const float* tab, float* lin, float* pooled,
+                    int B, int T, int F, int C, int pack, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
+                    uint32_t drop_base, int store_lin, int sms, cudaStream_t st);
 int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xhat, long long M, int N, int K,
                      const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(int sms);

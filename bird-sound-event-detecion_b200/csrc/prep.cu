@@ -93,6 +93,13 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
       }
       for (int j = tid; j < 2 * Cout; j += nth) op.dst2[j] = op.aux0[j % Cout];
     } break;
+    case PREP_GATE_TAB: {  // dst [gamma x pack | beta x pack], C = d0, pack = d1
+      const int C = op.d0, CP = C * op.d1;
+      for (int j = tid; j < CP; j += nth) {
+        op.dst[j] = op.src[j % C];
+        op.dst[CP + j] = op.aux0[j % C];
+      }
+    } break;
     case PREP_TRANSPOSE_BD: {  // dst[(p*C + c)][(q*C + c')] = (p == q) * src[c'][c]   (src [C][C], pack = d1)
       const int C = op.d0, pack = op.d1, CP = C * pack;
       for (int i = tid; i < CP * CP; i += nth) {

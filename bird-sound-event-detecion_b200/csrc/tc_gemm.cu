@@ -38,6 +38,13 @@ struct KArgs {
   // per-channel batch statistics of the output (conv mode): stats[(group * N + c) * 2 + {0,1}] += sum, sum of squares
   double* stats;
   int stats_groups;
+  // epi == 2: GLU forward with the gate, dropout and average pool fused (4-D tiles, N = pack * C <= 64):
+  //   lin = acc + bias (stored unless store_lin == 0);  o = lin * sigmoid(gamma * xhat + beta) * keep / (1 - p);
+  //   pooled[to][fo][c] = mean of o over the pt x pf window.  tab = [gamma | beta], each replicated pack times.
+  float* pooled;
+  int pt, pf, pack, gC, To, Fo, store_lin;
+  uint32_t drop_key, drop_thresh, drop_base;   // drop_base: element index of row 0 (the mask is keyed on absolute indices)
+  float inv_keep;
 };
 
 // RB ("resident B"): the whole [N][K] weight matrix (<= kRbBytes) is loaded once per CTA and stays in shared
@@ -53,10 +60,11 @@ struct KSmem {
   static constexpr int STAGE = A_BYTES + (RB ? 0 : B_STRIDE);
   static constexpr int RB_BYTES = RB ? kRbBytes : 0;
   static constexpr int STG_BYTES = kBM * N * 4;   // output tile staged for the TMA store
+  static constexpr int STG2_BYTES = N <= 64 ? kBM * N * 4 : 0;   // gated tile of the fused GLU epilogue (epi == 2)
   static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 5 mbarriers + the TMEM slot
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
   static constexpr int TOTAL =
-      STAGES * STAGE + RB_BYTES + STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
+      STAGES * STAGE + RB_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
   static_assert((2 * STAGES + 6) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
@@ -71,14 +79,15 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* rb = smem + STAGES * S::STAGE;   // resident weights (RB)
   unsigned char* stg = rb + S::RB_BYTES;          // output staging (1024-byte aligned: STAGE and kRbBytes are)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + S::STG_BYTES);
+  unsigned char* stg2 = stg + S::STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg2 + S::STG2_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* rbfull = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
-  float* sbias = reinterpret_cast<float*>(stg + S::STG_BYTES + S::BAR_BYTES);   // bias staged once per CTA
+  float* sbias = reinterpret_cast<float*>(stg2 + S::STG2_BYTES + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -100,6 +109,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   float* stab = sbias + 128;
   if (a.epi == 1)
     for (int i = threadIdx.x; i < a.tab_groups * 3 * N; i += kThreads) stab[i] = a.tab[i];
+  if (a.epi == 2)
+    for (int i = threadIdx.x; i < 2 * N; i += kThreads) stab[i] = a.tab[i];
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -222,7 +233,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       // operands of the BatchNorm-backward epilogue: requested before the accumulator is awaited, next chunk's while
       // the current one is combined
-      const bool bn_rd = a.epi == 1 && valid;
+      const bool bn_rd = (a.epi == 1 || a.epi == 2) && valid;   // operands read per element: (dxd, xhat) / xhat
       const float* yrow = Y + grow * a.ldc;
       const float* xrow = a.xh + grow * a.ldc;
       uint32_t tab_addr = 0;
@@ -238,7 +249,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (bn_rd) {
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
-          cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+          if (a.epi == 1) cpre[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
           xpre[j] = *reinterpret_cast<const float4*>(xrow + 4 * j);
         }
       }
@@ -265,7 +276,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (bn_rd && c0 + CW < N) {
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
+            if (a.epi == 1) cpre[j] = *reinterpret_cast<const float4*>(yrow + c0 + CW + 4 * j);
             xpre[j] = *reinterpret_cast<const float4*>(xrow + c0 + CW + 4 * j);
           }
         }
@@ -285,6 +296,20 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             o = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
           }
           sts128(sub + chunk_addr(row, j / 4), o);
+          if (S::STG2_BYTES > 0 && a.epi == 2) {   // gated value into the second staging tile
+            const float4 ga = lds128(smem_u32(stab) + (c0 + j) * 4);
+            const float4 be = lds128(smem_u32(stab) + (N + c0 + j) * 4);
+            const float4 xv = xcur[j / 4];
+            float gv[4] = {o.x * sigmoidf_(fmaf(ga.x, xv.x, be.x)), o.y * sigmoidf_(fmaf(ga.y, xv.y, be.y)),
+                           o.z * sigmoidf_(fmaf(ga.z, xv.z, be.z)), o.w * sigmoidf_(fmaf(ga.w, xv.w, be.w))};
+            if (a.drop_thresh) {
+              const uint32_t e0 = a.drop_base + (uint32_t)(grow * N + c0 + j);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) gv[u] = bsed_keep(e0 + u, a.drop_key, a.drop_thresh) ? gv[u] * a.inv_keep : 0.f;
+            }
+            if (!valid) gv[0] = gv[1] = gv[2] = gv[3] = 0.f;
+            sts128(smem_u32(stg2) + (c0 / CW) * (kBM * CW * 4) + chunk_addr(row, j / 4), make_float4(gv[0], gv[1], gv[2], gv[3]));
+          }
         }
       }
       tc_fence_before();
@@ -292,7 +317,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: the next MMAs may overwrite it
       fence_proxy_async();                         // staged tile visible to the TMA (async proxy)
       epi_barrier();
-      if (leader && a.debug != 1) {
+      if (leader && a.debug != 1 && !(a.epi == 2 && !a.store_lin)) {
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += CW) {
           const void* src = stg + (c0 / CW) * (kBM * CW * 4);
@@ -300,6 +325,29 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           else tma_store_4d(&mapC, src, c0, 0, t0, b, a.accumulate != 0);
         }
         bulk_commit();
+      }
+      if (S::STG2_BYTES > 0 && a.epi == 2) {
+        // average pool from the gated tile: pooled float4 i = (tol, fo, c4); sources are pt x pf packed pixels
+        const int c4n = a.gC / 4;
+        const int n4 = (a.th / a.pt) * a.Fo * c4n;
+        const float inv = 1.0f / (float)(a.pt * a.pf);
+        const uint32_t s2 = smem_u32(stg2);
+        for (int i = row; i < n4; i += kBM) {
+          const int c4 = i % c4n, fo = (i / c4n) % a.Fo, tol = i / (c4n * a.Fo);
+          const int to = t0 / a.pt + tol;
+          if (to >= a.To) continue;
+          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int dt = 0; dt < a.pt; ++dt)
+            for (int df = 0; df < a.pf; ++df) {
+              const int f = fo * a.pf + df;
+              const int r = (tol * a.pt + dt) * a.F + f / a.pack;
+              const int col = (f % a.pack) * a.gC + c4 * 4;
+              const float4 x4 = lds128(s2 + (col / CW) * (kBM * CW * 4) + chunk_addr(r, (col % CW) >> 2));
+              acc4.x += x4.x; acc4.y += x4.y; acc4.z += x4.z; acc4.w += x4.w;
+            }
+          acc4.x *= inv; acc4.y *= inv; acc4.z *= inv; acc4.w *= inv;
+          *reinterpret_cast<float4*>(a.pooled + (((size_t)b * a.To + to) * a.Fo + fo) * a.gC + c4 * 4) = acc4;
+        }
       }
       if (a.stats) {
         int gi = 0;
@@ -342,7 +390,7 @@ static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
   // as many stages as fit ~200 KB (max 24): the small-tile GEMMs (GLU, block 1) are streaming kernels that need
   // tens of KB of loads in flight per SM to cover the HBM latency
   constexpr int STAGE_BYTES = KSmem<N, KCH, 1, RB>::STAGE;
-  constexpr int BUDGET = 200 * 1024 - (RB ? kRbBytes : 0) - kBM * N * 4;
+  constexpr int BUDGET = 200 * 1024 - (RB ? kRbBytes : 0) - kBM * N * 4 - (N <= 64 ? kBM * N * 4 : 0);
   constexpr int STAGES = (BUDGET / STAGE_BYTES) > 24 ? 24 : (BUDGET / STAGE_BYTES);
   using S = KSmem<N, KCH, STAGES, RB>;
   static_assert(S::TOTAL <= 227 * 1024, "stage ring exceeds shared memory");
@@ -834,6 +882,12 @@ int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, in
   for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = stats && k < stats_groups ? gfirst[k] : 0;
   a.stats = stats;
   a.stats_groups = stats ? stats_groups : 0;
+  a.pooled = nullptr;
+  a.pt = a.pf = a.pack = 1;
+  a.gC = a.To = a.Fo = 0;
+  a.store_lin = 1;
+  a.drop_key = a.drop_thresh = a.drop_base = 0;
+  a.inv_keep = 1.f;
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
   if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, mC, Y, bias, a, sms, st);
@@ -894,6 +948,12 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, fl
   for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = bnb ? bnb->gfirst[k] : 0;
   a.stats = nullptr;
   a.stats_groups = 0;
+  a.pooled = nullptr;
+  a.pt = a.pf = a.pack = 1;
+  a.gC = a.To = a.Fo = 0;
+  a.store_lin = 1;
+  a.drop_key = a.drop_thresh = a.drop_base = 0;
+  a.inv_keep = 1.f;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
   if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, mC, C, bias, a, sms, st);
   return tc::dispatch_n<16>(N, mA, mB, mC, C, bias, a, sms, st);
@@ -902,6 +962,64 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, fl
 int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
                const float* bias, int accumulate, int sms, cudaStream_t st) {
   return tc_gemm_nt_impl(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, nullptr, sms, st);
+}
+
+// GLU forward of one block with gate, dropout and average pool fused (KArgs::epi == 2).  xhat / lin are the
+// [B][T][F][C] tensors viewed as rows of CP = pack * C floats ([B][T][F/pack][CP]); Wk = block-diagonal folded weights
+// [CP][CP] (K-major), bias [CP], tab = [gamma x pack | beta x pack]; pooled [B][T/pt][F/pf][C].
+int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const float* tab, float* lin, float* pooled,
+                    int B, int T, int F, int C, int pack, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
+                    uint32_t drop_base, int store_lin, int sms, cudaStream_t st) {
+  const int CP = C * pack, Fp = F / pack;
+  BSED_REQUIRE(CP == 64 && F % pack == 0 && Fp <= 128 && 128 % Fp == 0, "tc_glu_gate_fwd: C=%d pack=%d F=%d", C, pack, F);
+  const int th = 128 / Fp;
+  BSED_REQUIRE(th % pt == 0 && F % pf == 0 && pf % 1 == 0, "tc_glu_gate_fwd: pooling %dx%d does not tile (th=%d)", pt, pf, th);
+  CUtensorMap mA, mB, mC;
+  cuuint64_t dA[4] = {(cuuint64_t)CP, (cuuint64_t)Fp, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t sA[3] = {(cuuint64_t)CP * 4, (cuuint64_t)Fp * CP * 4, (cuuint64_t)T * Fp * CP * 4};
+  cuuint32_t bA[4] = {32, (cuuint32_t)Fp, (cuuint32_t)th, 1};
+  BSED_TRY(tc::make_map(&mA, xhat, 4, dA, sA, bA, 128));
+  cuuint64_t dB[2] = {(cuuint64_t)CP, (cuuint64_t)CP};
+  cuuint64_t sB[1] = {(cuuint64_t)CP * 4};
+  cuuint32_t bB[2] = {32, (cuuint32_t)CP};
+  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, 128));
+  BSED_TRY(tc::make_map(&mC, lin, 4, dA, sA, bA, 128, true));
+  tc::KArgs a;
+  a.plain = 0;
+  a.tiles_per_clip = (T + th - 1) / th;
+  a.n_tiles = a.tiles_per_clip * B;
+  a.th = th;
+  a.T = T;
+  a.F = Fp;
+  a.rows = 0;
+  a.ntaps = 1;
+  a.cpt = CP / 32;
+  a.ldc = CP;
+  a.accumulate = 0;
+  a.debug = tc_debug();
+  a.epi = 2;
+  a.xh = xhat;
+  a.tab = tab;
+  a.tab_groups = 0;
+  a.rows_per_clip = 1;
+  for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = 0;
+  a.stats = nullptr;
+  a.stats_groups = 0;
+  a.pooled = pooled;
+  a.pt = pt;
+  a.pf = pf;
+  a.pack = pack;
+  a.gC = C;
+  a.To = T / pt;
+  a.Fo = F / pf;
+  a.store_lin = store_lin;
+  a.drop_key = key;
+  a.drop_thresh = thresh;
+  a.drop_base = drop_base;
+  a.inv_keep = inv_keep;
+  const double M = (double)B * T * Fp;
+  ProfScope prof(PROF_GEMM, 2.0 * M * CP * CP, 4.0 * (2.0 * M * CP + (double)CP * CP), st);
+  return tc::dispatch_n<32>(CP, mA, mB, mC, lin, bias, a, sms, st);
 }
 
 // dY = k * (dxd + A * Bk^T - m1 - xhat * m2), in place on C (= dxd on entry); see KArgs::epi
