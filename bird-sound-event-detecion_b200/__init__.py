@@ -13,4 +13,4 @@ not a Python identifier).
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "engine", "models", "data", "utilities", "evaluation_measures", "main"]
+__all__ = ["_lib", "engine", "models", "data", "utilities", "evaluation_measures", "main", "pseudo_labeling"]
