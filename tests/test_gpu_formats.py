@@ -29,7 +29,7 @@ def test_write_cache_then_read_through_dataset(tmp_path):
     assert list(a1.columns) == ["onset", "offset", "event_label"] and a1["event_label"].tolist() == ["WOTH"]
     assert abs(a1["onset"][0] - 2.5) < 1e-9                                          # shifted into clip time; 9.5-10.5 crosses -> dropped
     enc = ManyHotEncoder(cfg.bird_list, n_frames=313)
-    ds = dataload.ENA_Dataset(str(tmp_path), enc.encode_strong_df, get_transforms(cfg.max_frames, None, 0))
+    ds = dataload.ENA_Dataset(str(tmp_path), enc.encode_strong_df, get_transforms(cfg.max_frames, None, 0, noise_dict_params={"mean": 0., "snr": cfg.noise_snr}))
     ((clean, noisy), target), path = ds[0]
     assert tuple(clean.shape) == (1, 1255, 128) and tuple(target.shape) == (313, 20) and path == paths[0]
     assert float(target[:, 0].sum()) > 0
