@@ -326,3 +326,105 @@ class Predictor(_FlatModule):
         if not x.is_cuda or not self._flat.is_cuda:
             raise RuntimeError("libbsed Predictor runs on CUDA tensors only (no CPU fallback)")
         return _PredictorFunction.apply(self, x, bool(inference), *self.param_list())
+
+
+class _DiscFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        import ctypes as C
+        from .. import _lib
+        from .._lib import check, ptr, stream_ptr
+        lib = _lib.load()
+        flat, bn, nbt = module.flat_tensors()
+        B = x.shape[0]
+        h = _lib.handle(flat.device.index)
+        xin = x.detach().contiguous().float()
+        ws, wsb = module._workspace(B)
+        prob = torch.empty(B, dtype=torch.float32, device=flat.device)
+        check(lib.bsed_disc_forward(h, ptr(flat), ptr(bn), ptr(nbt), ptr(xin), B, int(module.training), ptr(prob), ptr(ws), wsb,
+                                    stream_ptr()), "bsed_disc_forward")
+        ctx.module, ctx.B, ctx.train = module, B, module.training
+        ctx.save_for_backward(prob)
+        ctx.need_dx = x.requires_grad
+        return prob.reshape(B, 1)
+
+    @staticmethod
+    def backward(ctx, d_prob):
+        from .. import _lib
+        from .._lib import check, ptr, stream_ptr
+        module = ctx.module
+        if not ctx.train:
+            raise RuntimeError("Clip_Discriminator backward needs a forward in train() mode (batch statistics)")
+        lib = _lib.load()
+        flat, _, _ = module.flat_tensors()
+        (prob,) = ctx.saved_tensors
+        h = _lib.handle(flat.device.index)
+        ws, wsb = module._workspace(ctx.B)
+        grads = torch.empty_like(flat)
+        dx = torch.empty(ctx.B, 313, 256, dtype=torch.float32, device=flat.device) if ctx.need_dx else None
+        check(lib.bsed_disc_backward(h, ptr(flat), ptr(prob), ptr(d_prob.contiguous().float().reshape(-1)), ctx.B, ptr(grads), 0,
+                                     ptr(dx), ptr(ws), wsb, stream_ptr()), "bsed_disc_backward")
+        out, o = [], 0
+        for _, _, shape in module._param_specs:
+            k = math.prod(shape)
+            out.append(grads[o:o + k].view(shape))
+            o += k
+        return (None, dx, *out)
+
+
+class Clip_Discriminator(_FlatModule):
+    """src/models/CRNN_GRL.py:16-52 -- forward(x: (B, 313, 256)) -> (B, 1) domain probability, in libbsed kernels
+    (csrc/disc.cu).  State-dict keys equal the reference's (conv_1.weight ... bn_5.num_batches_tracked, dense_d.*)."""
+
+    def __init__(self, input_dim=256, dropout=0):
+        super().__init__()
+        chans = [1, 128, 64, 32, 16, 8]
+        ps, bs, cm = [], [], []
+        convs, bns = [], []
+        for l in range(5):
+            conv, bnm = nn.Module(), nn.Module()
+            setattr(self, f"conv_{l + 1}", conv)
+            convs.append(conv)
+            ps += [(conv, "weight", (chans[l + 1], chans[l], 3, 3)), (conv, "bias", (chans[l + 1],))]
+        self.dense_d = nn.Module()
+        ps += [(self.dense_d, "weight", (1, 16)), (self.dense_d, "bias", (1,))]
+        for l in range(5):
+            bnm = nn.Module()
+            setattr(self, f"bn_{l + 1}", bnm)
+            bns.append(bnm)
+            ps += [(bnm, "weight", (chans[l + 1],)), (bnm, "bias", (chans[l + 1],))]
+            bs += [(bnm, "running_mean", (chans[l + 1],)), (bnm, "running_var", (chans[l + 1],))]
+            cm.append(bnm)
+        self._counter_mods = cm
+        self._build(ps, bs, len(cm))
+        self._ws = {}
+        with torch.no_grad():   # PyTorch's default initialisation of Conv2d / Linear / BatchNorm2d
+            for mod, name, shape in self._param_specs:
+                p = getattr(mod, name)
+                if name == "weight" and len(shape) == 4:
+                    nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+                    nn.init.uniform_(mod.bias, -1 / math.sqrt(shape[1] * 9), 1 / math.sqrt(shape[1] * 9))
+                elif name == "weight" and len(shape) == 2:
+                    nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+                    nn.init.uniform_(mod.bias, -0.25, 0.25)
+                elif name == "weight" and len(shape) == 1:
+                    p.fill_(1.0)
+                    mod.bias.zero_()
+            for mod, name, _ in self._buffer_specs:
+                getattr(mod, name).fill_(0.0 if name == "running_mean" else 1.0)
+            self._flat_nbt.zero_()
+
+    def _workspace(self, B):
+        from .. import _lib
+        key = (B, self._flat.device)
+        if key not in self._ws:
+            nb = int(_lib.load().bsed_disc_workspace_bytes(B))
+            self._ws = {key: (torch.empty(nb, dtype=torch.uint8, device=self._flat.device), nb)}
+        return self._ws[key]
+
+    def forward(self, x):
+        if not x.is_cuda or not self._flat.is_cuda:
+            raise RuntimeError("libbsed Clip_Discriminator runs on CUDA tensors only (no CPU fallback)")
+        if tuple(x.shape[1:]) != (313, 256):
+            raise ValueError(f"Clip_Discriminator expects (B, 313, 256), got {tuple(x.shape)}")
+        return _DiscFunction.apply(self, x, *self.param_list())

@@ -230,6 +230,26 @@ int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffe
                      int64_t ema_step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Adversarial domain-adaptation branch.      src/models/CRNN_GRL.py:16-52, src/DA/cdan_frame.py:89-119
+ * Clip_Discriminator: d_input [B][313][256] -> 5 x [conv3x3 stride 2 -> BatchNorm2d -> LeakyReLU(.2)]
+ * (channels 128, 64, 32, 16, 8) -> AdaptiveAvgPool2d((2,1)) -> Linear(16,1) -> sigmoid -> prob [B].
+ * Parameters: one flat fp32 buffer in the reference's named_parameters() order (conv_1..5 weight/bias, dense_d
+ * weight/bias, bn_1..5 weight/bias; bsed_disc_param_count floats); BatchNorm running stats: flat fp32
+ * (running_mean_l, running_var_l per layer) + int64 num_batches_tracked[5].
+ * bsed_disc_backward undoes the last train-mode bsed_disc_forward on the same workspace; d_dinput (may be NULL) is
+ * the gradient handed to the gradient-reversal layer.  bsed_disc_bce: mean BCE against the domain labels + gradient.
+ * ------------------------------------------------------------------------------------------ */
+int64_t bsed_disc_param_count(void);
+int64_t bsed_disc_bn_buffer_count(void);
+size_t bsed_disc_workspace_bytes(int B);
+int bsed_disc_forward(bsed_handle h, const float* params, float* bn_buffers, int64_t* num_batches_tracked,
+                      const float* d_input, int B, int train, float* prob, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int bsed_disc_backward(bsed_handle h, const float* params, const float* prob, const float* d_prob, int B, float* grads,
+                       int accumulate, float* d_dinput, void* workspace, size_t workspace_bytes, void* stream);
+int bsed_disc_bce(bsed_handle h, const float* prob, const float* label, int B, float* loss, float* d_prob, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).
  *   bsed_launch_count: kernels this library has launched in this process.
  *   bsed_profile_begin(cls) .. bsed_profile_end: CUDA-event time, summed over the launches of one
