@@ -13,7 +13,10 @@ Two execution paths, both entirely in libbsed.so kernels:
     buffers without host synchronisation.
   * generic (any torch.optim optimizer): the reference's statement order through the autograd
     wrappers of models/CRNN.py.
-Out of scope here: the ISP/ICT branches and the discriminator updates.
+With `discriminator` (a DA.cdan_frame.ConditionalDomainAdversarialLoss around a Clip_Discriminator), `optimizer_d` and
+`optimizer_crnn`, every iteration first runs the adversarial update of src/main_scmt_ada_weak_seperate.py:314-335
+(student forward on both domains -> gradient reversal -> discriminator -> BCE -> backward -> both optimisers step).
+Out of scope here: the ISP/ICT shift-consistency branches.
 """
 import logging
 import time
@@ -185,13 +188,30 @@ def _generic_step(model, predictor, ema_model, ema_predictor, optimizer, batch, 
     return losses
 
 
+def adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_d, batch_input, syn_batch_input):
+    """src/main_scmt_ada_weak_seperate.py:314-335.  Returns the domain loss (device scalar)."""
+    syn_encoded_x, syn_d_input = model(syn_batch_input)
+    syn_strong_pred, _ = predictor(syn_encoded_x)
+    encoded_x, d_input = model(batch_input)
+    strong_pred, _ = predictor(encoded_x)
+    optimizer_crnn.zero_grad()
+    optimizer_d.zero_grad()
+    domain_loss = discriminator(syn_strong_pred, syn_d_input, strong_pred, d_input)
+    domain_loss.backward()
+    optimizer_crnn.step()
+    optimizer_d.step()
+    return domain_loss.detach()
+
+
 def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None, ema_predictor=None, mask_weak=None,
              mask_strong=None, adjust_lr=False, discriminator=None, optimizer_d=None, predictor=None,
              optimizer_crnn=None, ISP=False):
     """One epoch of the mean-teacher model; same arguments as the reference (src/main.py:163).
     Loaders yield (((student_input, teacher_input), target), filename)."""
-    if ISP or discriminator is not None or mask_weak is not None or mask_strong is not None:
-        raise NotImplementedError("ISP / discriminator / masked-real-label branches are outside this round's hot path")
+    if ISP or mask_weak is not None or mask_strong is not None:
+        raise NotImplementedError("ISP / masked-real-label branches are outside this round's hot path")
+    if discriminator is not None and (optimizer_d is None or optimizer_crnn is None):
+        raise ValueError("the adversarial update needs optimizer_d and optimizer_crnn (as in the reference)")
     if predictor is None:
         raise ValueError("train_mt needs the Predictor module (the reference passes it as `predictor`)")
     start = time.time()
@@ -218,6 +238,8 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
         x_ema = ema_batch_input.to(dev, non_blocking=True)
         xs = syn_batch_input.to(dev, non_blocking=True)
         ts = syn_target.to(dev, non_blocking=True)
+        if discriminator is not None:
+            domain_loss = adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_d, x, xs)
         if fused:
             tr = optimizer._trainer
             if tr is None:

@@ -110,3 +110,29 @@ def test_discriminator_behind_the_crnn_encoder():
     assert all(np.isfinite(losses)) and 0.1 < losses[0] < 3.0
     assert not torch.equal(before_c, m.flat_tensors()[0]) and not torch.equal(before_d, d.flat_tensors()[0])
     assert m.cnn.conv3.weight.grad is not None and float(m.cnn.conv3.weight.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_train_mt_with_the_adaptation_branch(fused):
+    """train_mt(..., discriminator, optimizer_d, optimizer_crnn) as src/main_scmt_ada_weak_seperate.py drives it."""
+    from bsed_b200 import main as bmain
+    from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
+    from test_gpu_train import _inputs, _models
+    m, p, em, ep = _models(0.5)
+    _, d = _disc()
+    d.train()
+    crit = ConditionalDomainAdversarialLoss(d)
+    crit.grl.iter_num = 300
+    xs, xr, xr_ema, ts = _inputs()
+    real = [(((xr, xr_ema), torch.zeros(2, 313, 20)), ["r0", "r1"])] * 2
+    syn = [(((xs, xs), ts), ["s0", "s1"])]
+    params = list(m.parameters()) + list(p.parameters())
+    opt = bmain.FusedAdam(params, lr=5e-4, betas=(0.9, 0.999)) if fused else torch.optim.Adam(params, lr=5e-4)
+    opt_c = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    opt_d = torch.optim.SGD(d.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    d0 = d._flat.clone()
+    loss = bmain.train_mt(real, syn, m, opt, 0, ema_model=em, ema_predictor=ep, predictor=p, discriminator=crit,
+                          optimizer_d=opt_d, optimizer_crnn=opt_c)
+    assert torch.isfinite(loss) and float(loss) > 0
+    assert crit.grl.iter_num == 302 and not torch.equal(d0, d.flat_tensors()[0])
+    assert int(d.bn_1.num_batches_tracked) == 2
