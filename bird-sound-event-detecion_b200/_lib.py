@@ -26,7 +26,7 @@ SYMBOLS = [
     "bsed_conv3x3_tc", "bsed_gemm_nt_tc", "bsed_conv3x3_wgrad", "bsed_conv3x3_wgrad_workspace_bytes",
     "bsed_plan_set_precision", "bsed_plan_get_precision",
     "bsed_disc_param_count", "bsed_disc_bn_buffer_count", "bsed_disc_workspace_bytes", "bsed_disc_forward",
-    "bsed_disc_backward", "bsed_disc_bce",
+    "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -116,6 +116,7 @@ def load():
         proto("bsed_conv3x3_tc", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
         proto("bsed_gemm_nt_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)
         proto("bsed_conv3x3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+        proto("bsed_disc_set_precision", i32, vp, i32)
         proto("bsed_disc_param_count", i64)
         proto("bsed_disc_bn_buffer_count", i64)
         proto("bsed_disc_workspace_bytes", sz, i32)

@@ -186,6 +186,7 @@ extern "C" int bsed_create(int device, bsed_handle* out) {
   memset(h, 0, sizeof(*h));
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  h->disc_precision = BSED_PRECISION_FP32;
   int r = build_tables(h);
   if (r != BSED_OK) {
     delete h;

@@ -79,6 +79,7 @@ struct bsed_context {
   int* mel_len;         // [128] number of bins of band m
   int* mel_off;         // [128] offset of band m inside mel_w
   int mel_nnz;
+  int disc_precision;   // BSED_PRECISION_* of the Clip_Discriminator GEMMs (default FP32, see bsed_disc_set_precision)
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

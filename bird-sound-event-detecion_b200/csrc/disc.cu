@@ -66,7 +66,8 @@ DiscGeom disc_geom() {
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct DiscWs {
-  size_t col[kDL], y[kDL], act[kDL], wt[kDL], wk[kDL], bp[kDL], dwt[kDL], ypad, mr, stats, stats2, feat, dscr, total;
+  size_t col[kDL], y[kDL], act[kDL], wt[kDL], wk[kDL], bp[kDL], dwt[kDL], ypad, mr, stats, stats2, feat, dscr, wgpart;
+  size_t wgpart_bytes, total;
 };
 
 DiscWs disc_ws(const DiscGeom& g, int B) {
@@ -95,6 +96,8 @@ DiscWs disc_ws(const DiscGeom& g, int B) {
   w.stats2 = take(sizeof(double) * 128 * 2);
   w.feat = take(sizeof(float) * (size_t)B * 16);
   w.dscr = take(sizeof(double) * 64);
+  w.wgpart_bytes = tc_wgrad_workspace_bytes(148);
+  w.wgpart = take(w.wgpart_bytes);
   w.total = o;
   return w;
 }
@@ -276,6 +279,11 @@ int grid_for(long long n) {
 
 using namespace bsed;
 
+extern "C" int bsed_disc_set_precision(bsed_handle h, int precision) {
+  BSED_REQUIRE(h && (precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32), "disc_set_precision: bad argument");
+  h->disc_precision = precision;
+  return BSED_OK;
+}
 extern "C" int64_t bsed_disc_param_count(void) { return disc_geom().n_params; }
 extern "C" int64_t bsed_disc_bn_buffer_count(void) { return disc_geom().n_bn; }
 extern "C" size_t bsed_disc_workspace_bytes(int B) { return B > 0 ? disc_ws(disc_geom(), B).total : 0; }
@@ -308,8 +316,13 @@ extern "C" int bsed_disc_forward(bsed_handle h, const float* params, float* bn_b
     disc_im2col_kernel<<<grid_for(M * g.Kp[l]), 256, 0, st>>>(x, col, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], l == 0);
     BSED_CHECK_LAUNCH();
     BSED_REQUIRE(M < (1ll << 31), "disc_forward: too many rows");
+    const bool tc = h->disc_precision == BSED_PRECISION_TF32;
     if (g.Np[l] == Cout) {
-      BSED_TRY(gemm_nn(col, g.Kp[l], wsp<float>(ws, w.wt[l]), g.Np[l], y, Cout, (int)M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0, st));
+      if (tc)   // y = col * Wk^T on tcgen05 (Wk [Np][Kp] is the K-major B operand)
+        BSED_TRY(tc_gemm_nt(col, g.Kp[l], wsp<float>(ws, w.wk[l]), g.Kp[l], y, Cout, M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0,
+                            h->num_sms, st));
+      else
+        BSED_TRY(gemm_nn(col, g.Kp[l], wsp<float>(ws, w.wt[l]), g.Np[l], y, Cout, (int)M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0, st));
     } else {
       float* ypad = wsp<float>(ws, w.ypad);
       BSED_TRY(gemm_nn(col, g.Kp[l], wsp<float>(ws, w.wt[l]), g.Np[l], ypad, g.Np[l], (int)M, g.Np[l], g.Kp[l],
@@ -414,13 +427,31 @@ extern "C" int bsed_disc_backward(bsed_handle h, const float* params, const floa
     // weight gradient: dWt [Kp][Np] = col^T dy
     float* dwt = wsp<float>(ws, w.dwt[l]);
     BSED_CHECK_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * g.Kp[l] * g.Np[l], st));
-    BSED_TRY(gemm_tn(col, g.Kp[l], dy, ldy, dwt, g.Np[l], 1, g.Kp[l], g.Np[l], M, h->num_sms * 4, st));
+    const bool tc = h->disc_precision == BSED_PRECISION_TF32;
+    if (tc && g.Kp[l] % 32 == 0 && g.Np[l] % 32 == 0 && g.Np[l] == Cout) {
+      TcOperand Aop{col, g.Kp[l], 0, g.Kp[l]}, Bop{dy, ldy, 0, g.Np[l]};   // rows = im2col rows, as a (1, M, 1) grid
+      BSED_TRY(tc_wgrad_ex(Aop, Bop, 1, (int)M, 1, 1, 0, dwt, g.Np[l], 1, 0, wsp<float>(ws, w.wgpart), w.wgpart_bytes,
+                           h->num_sms, st));
+    } else {
+      BSED_TRY(gemm_tn(col, g.Kp[l], dy, ldy, dwt, g.Np[l], 1, g.Kp[l], g.Np[l], M, h->num_sms * 4, st));
+    }
     disc_unpack_dw_kernel<<<grid_for(9LL * Cin * Cout), 256, 0, st>>>(dwt, grads + g.w_off[l], Cin, Cout, g.Np[l]);
     BSED_CHECK_LAUNCH();
     // data gradient: dcol = dy Wk (overwrites col), then scatter
     float* dx = l > 0 ? wsp<float>(ws, w.act[l - 1]) : d_dinput;
     if (dx) {
-      BSED_TRY(gemm_nn(dy, ldy, wsp<float>(ws, w.wk[l]), g.Kp[l], col, g.Kp[l], (int)M, g.Kp[l], g.Np[l], nullptr, 0, st));
+      if (tc && g.Np[l] == Cout) {
+        // dcol = dy * Wk on tcgen05: B operand [N = k][K = co] = Wt, in column slices of <= 128
+        for (int n0 = 0; n0 < g.Kp[l];) {
+          const int rem = g.Kp[l] - n0;
+          const int nw = rem >= 128 ? 128 : rem >= 64 ? 64 : rem >= 32 ? 32 : 16;
+          BSED_TRY(tc_gemm_nt(dy, ldy, wsp<float>(ws, w.wt[l]) + (size_t)n0 * g.Np[l], g.Np[l], col + n0, g.Kp[l], M, nw, g.Np[l],
+                              nullptr, 0, h->num_sms, st));
+          n0 += nw;
+        }
+      } else {
+        BSED_TRY(gemm_nn(dy, ldy, wsp<float>(ws, w.wk[l]), g.Kp[l], col, g.Kp[l], (int)M, g.Kp[l], g.Np[l], nullptr, 0, st));
+      }
       const long long nin = (long long)B * g.H[l] * g.W[l] * Cin;
       BSED_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * nin, st));
       disc_col2im_kernel<<<grid_for(M * 9 * Cin), 256, 0, st>>>(col, dx, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], l == 0);

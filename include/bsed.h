@@ -239,6 +239,7 @@ int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffe
  * bsed_disc_backward undoes the last train-mode bsed_disc_forward on the same workspace; d_dinput (may be NULL) is
  * the gradient handed to the gradient-reversal layer.  bsed_disc_bce: mean BCE against the domain labels + gradient.
  * ------------------------------------------------------------------------------------------ */
+int bsed_disc_set_precision(bsed_handle h, int precision);   /* BSED_PRECISION_FP32 (default) | BSED_PRECISION_TF32 */
 int64_t bsed_disc_param_count(void);
 int64_t bsed_disc_bn_buffer_count(void);
 size_t bsed_disc_workspace_bytes(int B);

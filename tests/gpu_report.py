@@ -108,9 +108,46 @@ def train_step_timing():
     say("workspace GB", tr.plan.ws_bytes / 1e9)
 
 
+def ada_step_timing():
+    from bsed_b200 import main as bmain
+    from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
+    from bsed_b200.models.CRNN import Clip_Discriminator
+    oc, op = oracle_models(seed=5, linear_std=0.2)
+    m, p = bsed_models(oc, op, dropout=0.5)
+    m.train(); p.train()
+    d = Clip_Discriminator(256).cuda().train()
+    crit = ConditionalDomainAdversarialLoss(d)
+    crit.grl.iter_num = 500
+    opt_c = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    opt_d = torch.optim.SGD(d.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    x = torch.from_numpy(synth.make_logmel_like(12, seed=1)).cuda()
+    xs = torch.from_numpy(synth.make_logmel_like(12, seed=2)).cuda()
+    for _ in range(3):
+        bmain.adversarial_step(m, p, crit, opt_c, opt_d, x, xs)
+    torch.cuda.synchronize()
+    t = time.time()
+    n = 5
+    for _ in range(n):
+        l = bmain.adversarial_step(m, p, crit, opt_c, opt_d, x, xs)
+    torch.cuda.synchronize()
+    dt = (time.time() - t) / n
+    # discriminator alone
+    f = torch.randn(24, 313, 256, device="cuda").tanh().requires_grad_(True)
+    for _ in range(3):
+        crit(None, f[:12], None, f[12:]).backward()
+    torch.cuda.synchronize()
+    t = time.time()
+    for _ in range(n):
+        crit(None, f[:12], None, f[12:]).backward()
+    torch.cuda.synchronize()
+    dd = (time.time() - t) / n
+    say("adversarial step (12 syn + 12 real clips, student fwd+bwd, D fwd+bwd, 2 x SGD): %.2f ms; discriminator fwd+bwd alone "
+        "(24 clips): %.2f ms; domain loss %.4f" % (dt * 1e3, dd * 1e3, float(l)))
+
+
 if __name__ == "__main__":
     say(torch.cuda.get_device_name(0))
-    for fn in (frontend, crnn_eval, train_step_timing):
+    for fn in (frontend, crnn_eval, train_step_timing, ada_step_timing):
         section(fn)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "report.txt"), "w") as fh:

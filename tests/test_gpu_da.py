@@ -136,3 +136,31 @@ def test_train_mt_with_the_adaptation_branch(fused):
     assert torch.isfinite(loss) and float(loss) > 0
     assert crit.grl.iter_num == 302 and not torch.equal(d0, d.flat_tensors()[0])
     assert int(d.bn_1.num_batches_tracked) == 2
+
+
+def test_tensor_core_discriminator_within_stated_tolerance(monkeypatch):
+    """Opt-in tf32 tcgen05 GEMMs for the discriminator's convolutions (Clip_Discriminator.precision = "tf32"): loss 2e-3
+    relative, gradients 5e-2 relative L2 (measured 2e-2: five BatchNorms over a 5-clip batch amplify the rounding)."""
+    from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
+    g = golden("ada.npz")
+    _, d = _disc()
+    d.train()
+    d.precision = "tf32"
+    f_s = oda.seeded_features(2, 31).cuda().requires_grad_(True)
+    f_t = oda.seeded_features(3, 32).cuda().requires_grad_(True)
+    crit = ConditionalDomainAdversarialLoss(d)
+    crit.grl.iter_num = 500
+    loss = crit(None, f_s, None, f_t)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g["loss"])) < 2e-3 * float(g["loss"])
+    assert rel_l2(f_s.grad.cpu().numpy()[:, ::7, ::5], g["df_s"]) < 5e-2
+    worst = 0.0
+    for name, p in d.named_parameters():
+        if name.startswith("conv_") and name.endswith(".bias"):
+            continue
+        got = p.grad.reshape(-1).cpu().numpy()
+        got = got[:: max(1, got.size // 2048)][:2048]
+        worst = max(worst, rel_l2(got, g["g_" + name]))
+    print("[tf32] discriminator worst gradient rel_l2 %.3e" % worst)
+    assert worst < 5e-2
