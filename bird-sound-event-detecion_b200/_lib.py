@@ -36,7 +36,7 @@ class CrnnCfg(C.Structure):
                 ("filters", C.c_int * MAX_CNN_LAYERS), ("pool_t", C.c_int * MAX_CNN_LAYERS),
                 ("pool_f", C.c_int * MAX_CNN_LAYERS), ("rnn_hidden", C.c_int), ("rnn_layers", C.c_int),
                 ("n_class", C.c_int), ("dropout", C.c_float), ("bn_eps", C.c_float),
-                ("bn_momentum", C.c_float)]
+                ("bn_momentum", C.c_float), ("fpn", C.c_int)]
 
 
 class Group(C.Structure):

@@ -19,22 +19,31 @@ struct LayerGeom {
   long long rows, prows;  // T*F and To*Fo per clip
 };
 
+// A "block" is one Conv3x3 -> BatchNorm -> GLU -> dropout -> AvgPool application: the n_cnn trunk blocks, then (fpn) the
+// two applications of the shared-weight stage cnn_fcn / bn_fcn / glu (src/models/CNN_FPN.py:85-98), which are blocks
+// n_cnn and n_cnn + 1 with identical parameter / packed-operand / running-stat offsets and their own activations.
+constexpr int kMaxBlocks = BSED_MAX_CNN_LAYERS + 2;
+// A "stack" is one BidirectionalGRU: rnn, and (fpn) rnn_2, rnn_4 on the 156- and 78-frame scales.
+constexpr int kMaxStacks = 3;
+
 struct ParamLayout {
-  long long conv_w[BSED_MAX_CNN_LAYERS], conv_b[BSED_MAX_CNN_LAYERS], bn_w[BSED_MAX_CNN_LAYERS],
-      bn_b[BSED_MAX_CNN_LAYERS], glu_w[BSED_MAX_CNN_LAYERS], glu_b[BSED_MAX_CNN_LAYERS];
-  long long wih[4][2], whh[4][2], bih[4][2], bhh[4][2];
+  long long conv_w[kMaxBlocks], conv_b[kMaxBlocks], bn_w[kMaxBlocks], bn_b[kMaxBlocks], glu_w[kMaxBlocks], glu_b[kMaxBlocks];
+  long long wih[kMaxStacks][4][2], whh[kMaxStacks][4][2], bih[kMaxStacks][4][2], bhh[kMaxStacks][4][2];
+  long long c1_w, c1_b;        // cnn.conv1x1 of CNN_FPN: registered by the reference, never used in forward
+  long long m_w[2], m_b[2];    // [0] conv1x1_2 (156-frame merge), [1] conv1x1_4 (313-frame merge): [256][512], [256]
   long long total;
   long long dense_w, dense_b, sm_w, sm_b, pred_total;  // Predictor: its own flat buffer
   std::vector<long long> pred_order;
-  long long rm[BSED_MAX_CNN_LAYERS], rv[BSED_MAX_CNN_LAYERS], bn_total;
+  long long rm[kMaxBlocks], rv[kMaxBlocks], bn_total;
   std::vector<long long> order;
 };
 
 struct PackedLayout {
-  long long wp[BSED_MAX_CNN_LAYERS], wd[BSED_MAX_CNN_LAYERS], glu_wT[BSED_MAX_CNN_LAYERS],
-      glu_bf[BSED_MAX_CNN_LAYERS], glu_wgT[BSED_MAX_CNN_LAYERS], wpair[BSED_MAX_CNN_LAYERS], bpair[BSED_MAX_CNN_LAYERS],
-      gate_tab[BSED_MAX_CNN_LAYERS];
-  long long wihT[4], bih[4], whhT[4], whh[4], bhh[4], wih_cat[4];
+  long long wp[kMaxBlocks], wd[kMaxBlocks], glu_wT[kMaxBlocks], glu_bf[kMaxBlocks], glu_wgT[kMaxBlocks], wpair[kMaxBlocks],
+      bpair[kMaxBlocks], gate_tab[kMaxBlocks];
+  long long wihT[kMaxStacks][4], bih[kMaxStacks][4], whhT[kMaxStacks][4], whh[kMaxStacks][4], bhh[kMaxStacks][4],
+      wih_cat[kMaxStacks][4];
+  long long m_w[2], m_wT[2];   // merge convolutions: [256][512] copy and its [512][256] transpose
   long long total;
   long long wcatT, bcat, wcat, pred_total;  // Predictor operands (own region)
 };
@@ -65,15 +74,21 @@ struct bsed_crnn_plan {
   bsed_crnn_cfg cfg;
   int max_clips;
   int Tout;
-  LayerGeom L[BSED_MAX_CNN_LAYERS];
+  int n_blocks;                 // n_cnn (+ 2 with fpn)
+  int bn_slot[kMaxBlocks];      // index of a block's BatchNorm in num_batches_tracked
+  int n_stacks;                 // 1 (+ 2 with fpn)
+  int stackT[kMaxStacks];       // frames of each GRU stack: 313, 156, 78
+  int stack_src[kMaxStacks];    // block whose pooled output feeds the stack
+  LayerGeom L[kMaxBlocks];
   ParamLayout pl;
   PackedLayout pk;
   // workspace offsets (bytes)
   size_t off_packed[2];
-  size_t off_xhat[BSED_MAX_CNN_LAYERS], off_lin[BSED_MAX_CNN_LAYERS], off_pool[BSED_MAX_CNN_LAYERS];
+  size_t off_xhat[kMaxBlocks], off_lin[kMaxBlocks], off_pool[kMaxBlocks];
   size_t off_stats, off_stats2, off_meanrstd;
-  size_t off_xg, off_gru_out[4], off_gru_saved[4], off_enc;
-  size_t off_dxn, off_dpool[2], off_denc, off_dx1, off_dxg, off_dgh;
+  size_t off_xg, off_gru_out[kMaxStacks][4], off_gru_saved[kMaxStacks][4], off_enc[kMaxStacks];
+  size_t off_dxn, off_dpool[2], off_denc[kMaxStacks], off_dx1, off_dxg, off_dgh;
+  size_t off_cat[2], off_y2, off_dcat, off_dy2;   // fpn merge: cat[0] (B,156,512), cat[1] (B,313,512), y2 (B,156,256)
   size_t off_G, off_dscratch, off_wgpart, off_bsums, off_bntab;
   size_t wgpart_bytes;
   size_t ws_bytes;
@@ -87,9 +102,12 @@ struct bsed_crnn_plan {
   const float* pset_params[2];
   int n_psets;
   const float* x_in;
-  uint32_t keys[BSED_MAX_CNN_LAYERS + 1];
-  uint32_t thresh;
+  uint32_t bkeys[kMaxBlocks];   // dropout keys of the blocks
+  uint32_t skeys[kMaxStacks];   // dropout keys of the stack outputs
+  uint32_t thresh;              // encoder-output and trunk-block dropout (cfg.dropout)
   float inv_keep;
+  uint32_t bthresh[kMaxBlocks]; // per block: the fpn stage drops with p = 0.5 whatever cfg.dropout is
+  float binv[kMaxBlocks];       // (CNN_FPN.__init__: self.dropout = nn.Dropout(0.5), src/models/CNN_FPN.py:79)
 };
 
 namespace {
@@ -126,7 +144,36 @@ int build_layouts(bsed_crnn_plan* p) {
   }
   BSED_REQUIRE(F == 1, "plan: frequency axis must pool to 1 (got %d)", F);
   BSED_REQUIRE(Cin == 128, "plan: last CNN block must have 128 channels (GRU input), got %d", Cin);
+  BSED_REQUIRE(c.fpn == 0 || c.fpn == 1, "plan: fpn=%d", c.fpn);
   p->Tout = T;
+  p->n_blocks = c.n_cnn;
+  p->n_stacks = 1;
+  p->stackT[0] = T;
+  p->stack_src[0] = c.n_cnn - 1;
+  for (int i = 0; i < c.n_cnn; ++i) p->bn_slot[i] = i;
+  if (c.fpn) {
+    // CNN_FPN.forward (src/models/CNN_FPN.py:82-100): two applications of cnn_fcn -> bn_fcn -> glu -> dropout -> pool_fcn
+    BSED_REQUIRE(c.n_cnn + 2 <= kMaxBlocks, "plan: too many CNN blocks for fpn");
+    BSED_REQUIRE(T >= 4, "plan: fpn needs at least 4 output frames (got %d)", T);
+    for (int j = 0; j < 2; ++j) {
+      LayerGeom& g = p->L[c.n_cnn + j];
+      g.Cin = g.Cout = 128;
+      g.T = T;
+      g.F = 1;
+      g.pt = 2;
+      g.pf = 1;
+      g.To = T / 2;
+      g.Fo = 1;
+      g.rows = T;
+      g.prows = g.To;
+      T = g.To;
+      p->bn_slot[c.n_cnn + j] = c.n_cnn;
+      p->stackT[1 + j] = T;
+      p->stack_src[1 + j] = c.n_cnn + j;
+    }
+    p->n_blocks = c.n_cnn + 2;
+    p->n_stacks = 3;
+  }
   // flat parameter layout == reference named_parameters() order
   ParamLayout& pl = p->pl;
   long long o = 0;
@@ -145,15 +192,38 @@ int build_layouts(bsed_crnn_plan* p) {
     pl.glu_w[i] = take((long long)g.Cout * g.Cout);
     pl.glu_b[i] = take(g.Cout);
   }
-  for (int l = 0; l < c.rnn_layers; ++l) {
-    int In = l == 0 ? 128 : 256;
-    for (int d = 0; d < 2; ++d) {
-      pl.wih[l][d] = take(384LL * In);
-      pl.whh[l][d] = take(384LL * 128);
-      pl.bih[l][d] = take(384);
-      pl.bhh[l][d] = take(384);
-    }
+  if (c.fpn) {
+    const int i = c.n_cnn;   // registration order of CNN_FPN.__init__: cnn_fcn, glu, bn_fcn, conv1x1
+    pl.conv_w[i] = take(128LL * 128 * 9);
+    pl.conv_b[i] = take(128);
+    pl.glu_w[i] = take(128LL * 128);
+    pl.glu_b[i] = take(128);
+    pl.bn_w[i] = take(128);
+    pl.bn_b[i] = take(128);
+    pl.c1_w = take(128LL * 256);
+    pl.c1_b = take(128);
+    pl.conv_w[i + 1] = pl.conv_w[i];
+    pl.conv_b[i + 1] = pl.conv_b[i];
+    pl.glu_w[i + 1] = pl.glu_w[i];
+    pl.glu_b[i + 1] = pl.glu_b[i];
+    pl.bn_w[i + 1] = pl.bn_w[i];
+    pl.bn_b[i + 1] = pl.bn_b[i];
   }
+  for (int s = 0; s < p->n_stacks; ++s)
+    for (int l = 0; l < c.rnn_layers; ++l) {
+      int In = l == 0 ? 128 : 256;
+      for (int d = 0; d < 2; ++d) {
+        pl.wih[s][l][d] = take(384LL * In);
+        pl.whh[s][l][d] = take(384LL * 128);
+        pl.bih[s][l][d] = take(384);
+        pl.bhh[s][l][d] = take(384);
+      }
+    }
+  if (c.fpn)
+    for (int j = 0; j < 2; ++j) {
+      pl.m_w[j] = take(256LL * 512);
+      pl.m_b[j] = take(256);
+    }
   pl.total = o;
   {
     long long po = 0;
@@ -170,11 +240,15 @@ int build_layouts(bsed_crnn_plan* p) {
     pl.pred_total = po;
   }
   long long bo = 0;
-  for (int i = 0; i < c.n_cnn; ++i) {
+  for (int i = 0; i < c.n_cnn + (c.fpn ? 1 : 0); ++i) {
     pl.rm[i] = bo;
     bo += p->L[i].Cout;
     pl.rv[i] = bo;
     bo += p->L[i].Cout;
+  }
+  if (c.fpn) {
+    pl.rm[c.n_cnn + 1] = pl.rm[c.n_cnn];
+    pl.rv[c.n_cnn + 1] = pl.rv[c.n_cnn];
   }
   pl.bn_total = bo;
   // packed operand layout (per parameter set)
@@ -185,7 +259,7 @@ int build_layouts(bsed_crnn_plan* p) {
     q += (n + 3) / 4 * 4;
     return r;
   };
-  for (int i = 0; i < c.n_cnn; ++i) {
+  for (int i = 0; i < c.n_cnn + (c.fpn ? 1 : 0); ++i) {
     const LayerGeom& g = p->L[i];
     pk.wp[i] = ptake((long long)g.Cout * g.Cin * 9);
     pk.wd[i] = ptake((long long)g.Cout * g.Cin * 9);
@@ -197,15 +271,32 @@ int build_layouts(bsed_crnn_plan* p) {
     pk.glu_wgT[i] = ptake(cp * cp);
     pk.gate_tab[i] = ptake(2 * cp);
   }
-  for (int l = 0; l < c.rnn_layers; ++l) {
-    int In = l == 0 ? 128 : 256;
-    pk.wihT[l] = ptake(768LL * In);
-    pk.bih[l] = ptake(768);
-    pk.whhT[l] = ptake(2LL * 128 * 384);
-    pk.whh[l] = ptake(2LL * 384 * 128);
-    pk.bhh[l] = ptake(768);
-    pk.wih_cat[l] = ptake(768LL * In);
+  if (c.fpn) {
+    const int i = c.n_cnn;
+    pk.wp[i + 1] = pk.wp[i];
+    pk.wd[i + 1] = pk.wd[i];
+    pk.wpair[i + 1] = pk.wpair[i];
+    pk.bpair[i + 1] = pk.bpair[i];
+    pk.glu_wT[i + 1] = pk.glu_wT[i];
+    pk.glu_bf[i + 1] = pk.glu_bf[i];
+    pk.glu_wgT[i + 1] = pk.glu_wgT[i];
+    pk.gate_tab[i + 1] = pk.gate_tab[i];
   }
+  for (int s = 0; s < p->n_stacks; ++s)
+    for (int l = 0; l < c.rnn_layers; ++l) {
+      int In = l == 0 ? 128 : 256;
+      pk.wihT[s][l] = ptake(768LL * In);
+      pk.bih[s][l] = ptake(768);
+      pk.whhT[s][l] = ptake(2LL * 128 * 384);
+      pk.whh[s][l] = ptake(2LL * 384 * 128);
+      pk.bhh[s][l] = ptake(768);
+      pk.wih_cat[s][l] = ptake(768LL * In);
+    }
+  if (c.fpn)
+    for (int j = 0; j < 2; ++j) {
+      pk.m_w[j] = ptake(256LL * 512);
+      pk.m_wT[j] = ptake(512LL * 256);
+    }
   pk.total = q;
   q = 0;
   pk.wcatT = ptake(256LL * kLdl);
@@ -226,7 +317,7 @@ void carve_workspace(bsed_crnn_plan* p) {
   };
   for (int s = 0; s < 2; ++s) p->off_packed[s] = takeb(sizeof(float) * p->pk.total);
   long long max_full = 0, max_pool = 0;
-  for (int i = 0; i < c.n_cnn; ++i) {
+  for (int i = 0; i < p->n_blocks; ++i) {
     const LayerGeom& g = p->L[i];
     long long full = Bm * g.rows * g.Cout, pool = Bm * g.prows * g.Cout;
     p->off_xhat[i] = takeb(sizeof(float) * full);
@@ -235,23 +326,33 @@ void carve_workspace(bsed_crnn_plan* p) {
     if (full > max_full) max_full = full;
     if (pool > max_pool) max_pool = pool;
   }
-  p->off_stats = takeb(sizeof(double) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2);
+  p->off_stats = takeb(sizeof(double) * kMaxBlocks * kMaxGroups * 128 * 2);
   p->off_stats2 = takeb(sizeof(double) * kMaxGroups * 128 * 2);
-  p->off_meanrstd = takeb(sizeof(float) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2);
-  const long long BT = Bm * p->Tout;
+  p->off_meanrstd = takeb(sizeof(float) * kMaxBlocks * kMaxGroups * 128 * 2);
+  const long long BT = Bm * p->Tout;   // the longest stack
   p->off_xg = takeb(sizeof(float) * BT * 768);
-  for (int l = 0; l < c.rnn_layers; ++l) {
-    p->off_gru_out[l] = takeb(sizeof(float) * BT * 256);
-    p->off_gru_saved[l] = takeb(sizeof(float) * BT * 2 * 4 * 128);
+  for (int s = 0; s < p->n_stacks; ++s) {
+    const long long BTs = Bm * p->stackT[s];
+    for (int l = 0; l < c.rnn_layers; ++l) {
+      p->off_gru_out[s][l] = takeb(sizeof(float) * BTs * 256);
+      p->off_gru_saved[s][l] = takeb(sizeof(float) * BTs * 2 * 4 * 128);
+    }
+    p->off_enc[s] = takeb(sizeof(float) * BTs * 256);
+    p->off_denc[s] = takeb(sizeof(float) * BTs * 256);
   }
-  p->off_enc = takeb(sizeof(float) * BT * 256);
   p->off_dxn = takeb(sizeof(float) * max_full);
   p->off_dpool[0] = takeb(sizeof(float) * max_pool);
   p->off_dpool[1] = takeb(sizeof(float) * max_pool);
-  p->off_denc = takeb(sizeof(float) * BT * 256);
   p->off_dx1 = takeb(sizeof(float) * BT * 256);
   p->off_dxg = takeb(sizeof(float) * BT * 768);
   p->off_dgh = takeb(sizeof(float) * BT * 768);
+  if (c.fpn) {
+    p->off_cat[0] = takeb(sizeof(float) * Bm * p->stackT[1] * 512);
+    p->off_cat[1] = takeb(sizeof(float) * BT * 512);
+    p->off_y2 = takeb(sizeof(float) * Bm * p->stackT[1] * 256);
+    p->off_dcat = takeb(sizeof(float) * BT * 512);
+    p->off_dy2 = takeb(sizeof(float) * Bm * p->stackT[1] * 256);
+  }
   p->off_G = takeb(sizeof(float) * kMaxGroups * 128 * 128);
   p->off_bsums = takeb(sizeof(double) * kMaxGroups * 128 * 4);
   p->off_bntab = takeb(sizeof(float) * kMaxGroups * 3 * 128);
@@ -266,15 +367,11 @@ T* wsp(void* ws, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ws) + off);
 }
 
-void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
-  const bsed_crnn_cfg& c = p->cfg;
-  const ParamLayout& pl = p->pl;
-  const PackedLayout& pk = p->pk;
-  const bool tc = p->precision == BSED_PRECISION_TF32;
-  tb->n = 0;
-  auto add = [&](int type, const float* src, float* dst, int d0, int d1 = 0, int d2 = 0, int d3 = 0,
-                 const float* a0 = nullptr, const float* a1 = nullptr, const float* a2 = nullptr,
-                 float* dst2 = nullptr) {
+struct PrepAdder {
+  PrepTable* tb;
+  void operator()(int type, const float* src, float* dst, int d0, int d1 = 0, int d2 = 0, int d3 = 0,
+                  const float* a0 = nullptr, const float* a1 = nullptr, const float* a2 = nullptr,
+                  float* dst2 = nullptr) const {
     PrepOp& op = tb->ops[tb->n++];
     op.type = type;
     op.src = src;
@@ -287,8 +384,18 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
     op.d1 = d1;
     op.d2 = d2;
     op.d3 = d3;
-  };
-  for (int i = 0; i < c.n_cnn; ++i) {
+  }
+};
+
+// conv / BatchNorm / GLU operands of the trunk blocks and (fpn) of the shared stage, prepared once for both applications
+void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
+  const bsed_crnn_cfg& c = p->cfg;
+  const ParamLayout& pl = p->pl;
+  const PackedLayout& pk = p->pk;
+  const bool tc = p->precision == BSED_PRECISION_TF32;
+  tb->n = 0;
+  PrepAdder add{tb};
+  for (int i = 0; i < c.n_cnn + (c.fpn ? 1 : 0); ++i) {
     const LayerGeom& g = p->L[i];
     if (i > 0) {
       if (tc && conv_pair_ok(g))
@@ -304,19 +411,34 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
     if (tc) add(PREP_GATE_TAB, params + pl.bn_w[i], packed + pk.gate_tab[i], g.Cout, glu_pack(g.Cout), 0, 0, params + pl.bn_b[i]);
     if (tc && need_bwd) add(PREP_TRANSPOSE_BD, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, glu_pack(g.Cout));
   }
+}
+
+// recurrent operands of GRU stack s (and, with s == 0 and fpn, the two merge convolutions)
+void build_prep_table_stack(const bsed_crnn_plan* p, int s, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
+  const bsed_crnn_cfg& c = p->cfg;
+  const ParamLayout& pl = p->pl;
+  const PackedLayout& pk = p->pk;
+  const bool tc = p->precision == BSED_PRECISION_TF32;
+  tb->n = 0;
+  PrepAdder add{tb};
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
     for (int d = 0; d < 2; ++d) {
       // W_ih [384][In] -> wihT [In][768] columns d*384..
-      add(PREP_TRANSPOSE, params + pl.wih[l][d], packed + pk.wihT[l], 384, In, 768, d * 384);
-      add(PREP_COPY, params + pl.bih[l][d], packed + pk.bih[l] + d * 384, 384);
+      add(PREP_TRANSPOSE, params + pl.wih[s][l][d], packed + pk.wihT[s][l], 384, In, 768, d * 384);
+      add(PREP_COPY, params + pl.bih[s][l][d], packed + pk.bih[s][l] + d * 384, 384);
       // W_hh [384][128] -> whhT [d][128][384]
-      add(PREP_TRANSPOSE, params + pl.whh[l][d], packed + pk.whhT[l] + (long long)d * 128 * 384, 384, 128, 384, 0);
-      add(PREP_COPY, params + pl.bhh[l][d], packed + pk.bhh[l] + d * 384, 384);
-      if (need_bwd) add(PREP_COPY, params + pl.whh[l][d], packed + pk.whh[l] + (long long)d * 384 * 128, 384 * 128);
-      if (need_bwd || tc) add(PREP_COPY, params + pl.wih[l][d], packed + pk.wih_cat[l] + (long long)d * 384 * In, 384 * In);
+      add(PREP_TRANSPOSE, params + pl.whh[s][l][d], packed + pk.whhT[s][l] + (long long)d * 128 * 384, 384, 128, 384, 0);
+      add(PREP_COPY, params + pl.bhh[s][l][d], packed + pk.bhh[s][l] + d * 384, 384);
+      if (need_bwd) add(PREP_COPY, params + pl.whh[s][l][d], packed + pk.whh[s][l] + (long long)d * 384 * 128, 384 * 128);
+      if (need_bwd || tc) add(PREP_COPY, params + pl.wih[s][l][d], packed + pk.wih_cat[s][l] + (long long)d * 384 * In, 384 * In);
     }
   }
+  if (c.fpn && s == 0)
+    for (int j = 0; j < 2; ++j) {
+      add(PREP_COPY, params + pl.m_w[j], packed + pk.m_w[j], 256 * 512);
+      add(PREP_TRANSPOSE, params + pl.m_w[j], packed + pk.m_wT[j], 256, 512, 256, 0);   // [256][512] -> [512][256]
+    }
 }
 
 void build_prep_table_head(const bsed_crnn_plan* p, const float* params, float* packed, PrepTable* tb) {
@@ -470,7 +592,15 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
   p->saved_valid = false;
   p->thresh = train ? bsed_drop_thresh(c.dropout) : 0u;
   p->inv_keep = train && c.dropout > 0.f ? 1.0f / (1.0f - c.dropout) : 1.0f;
-  for (int i = 0; i <= c.n_cnn; ++i) p->keys[i] = bsed_mix_key(dropout_seed, dropout_step, i == c.n_cnn ? 7 : i);
+  for (int i = 0; i < p->n_blocks; ++i) {
+    const bool stage = i >= c.n_cnn;
+    p->bthresh[i] = stage ? (train ? bsed_drop_thresh(0.5f) : 0u) : p->thresh;
+    p->binv[i] = stage ? (train ? 2.0f : 1.0f) : p->inv_keep;
+  }
+  // dropout streams (restated in oracle/crnn.py): trunk block i -> i, encoder output -> 7, fpn stage applications -> 8, 9,
+  // rnn_2 / rnn_4 outputs -> 10, 11
+  for (int i = 0; i < p->n_blocks; ++i) p->bkeys[i] = bsed_mix_key(dropout_seed, dropout_step, i < c.n_cnn ? i : 8 + (i - c.n_cnn));
+  for (int s = 0; s < p->n_stacks; ++s) p->skeys[s] = bsed_mix_key(dropout_seed, dropout_step, s == 0 ? 7 : 9 + s);
 
   // runs of clips sharing a parameter set
   struct Run {
@@ -488,13 +618,17 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     float* packed = wsp<float>(ws, p->off_packed[s]);
     build_prep_table(p, p->pset_params[s], packed, save, &tb);
     BSED_TRY(run_prep(tb, st));
+    for (int k = 0; k < p->n_stacks; ++k) {
+      build_prep_table_stack(p, k, p->pset_params[s], packed, save, &tb);
+      BSED_TRY(run_prep(tb, st));
+    }
   }
 
   int all_ids[kMaxGroups] = {0, 1, 2, 3};
   double* stats = wsp<double>(ws, p->off_stats);
-  if (train) BSED_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * BSED_MAX_CNN_LAYERS * kMaxGroups * 128 * 2, st));
+  if (train) BSED_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * kMaxBlocks * kMaxGroups * 128 * 2, st));
 
-  for (int i = 0; i < c.n_cnn; ++i) {
+  for (int i = 0; i < p->n_blocks; ++i) {
     const LayerGeom& L = p->L[i];
     float* y = wsp<float>(ws, p->off_xhat[i]);
     float* lin = wsp<float>(ws, p->off_lin[i]);
@@ -542,7 +676,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       int gi = k < n_groups ? k : 0;
       rmean[k] = groups[gi].bn_buffers + p->pl.rm[i];
       rvar[k] = groups[gi].bn_buffers + p->pl.rv[i];
-      nbt[k] = groups[gi].num_batches_tracked ? groups[gi].num_batches_tracked + i : nullptr;
+      nbt[k] = groups[gi].num_batches_tracked ? groups[gi].num_batches_tracked + p->bn_slot[i] : nullptr;
     }
     if (train) {
       double* st_i = stats + (size_t)i * kMaxGroups * 128 * 2;
@@ -564,7 +698,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
           // GEMM + gate + dropout + average pool in one kernel; lin is stored only when backward will need it
           BSED_TRY(tc_glu_gate_fwd(y + off, packed + p->pk.glu_wT[i], packed + p->pk.glu_bf[i], packed + p->pk.gate_tab[i],
                                    lin + off, pool + (size_t)runs[r].first * L.prows * L.Cout, runs[r].count, L.T, L.F,
-                                   L.Cout, pack, L.pt, L.pf, p->keys[i], p->thresh, p->inv_keep, (uint32_t)off, save ? 1 : 0,
+                                   L.Cout, pack, L.pt, L.pf, p->bkeys[i], p->bthresh[i], p->binv[i], (uint32_t)off, save ? 1 : 0,
                                    sms, st));
         } else {
           BSED_TRY(tc_gemm_nt(y + off, CP, packed + p->pk.glu_wT[i], CP, lin + off, CP, M / pack, CP, CP,
@@ -576,44 +710,73 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
                          packed + p->pk.glu_bf[i], 0, st));
     }
     if (!(tc && glu_fused(L)))
-      BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
-                                 p->inv_keep, st));
+      BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
+                                 p->binv[i], st));
   }
 
-  // GRU stack
-  const int T = p->Tout;
+  // GRU stacks: rnn on the trunk output, (fpn) rnn_2 / rnn_4 on the two coarser scales; each followed by dropout
   float* xg = wsp<float>(ws, p->off_xg);
-  float* enc_i = wsp<float>(ws, p->off_enc);
-  for (int l = 0; l < c.rnn_layers; ++l) {
-    const int In = l == 0 ? 128 : 256;
-    const float* X = l == 0 ? wsp<float>(ws, p->off_pool[c.n_cnn - 1]) : wsp<float>(ws, p->off_gru_out[l - 1]);
-    for (int r = 0; r < n_runs; ++r) {
-      const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
-      const float* Xr = X + (size_t)runs[r].first * T * In;
-      float* xgr = xg + (size_t)runs[r].first * T * 768;
-      if (tc) {
-        for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
-          BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[l] + (size_t)n0 * In, In, xgr + n0, 768,
-                              (long long)runs[r].count * T, 128, In, packed + p->pk.bih[l] + n0, 0, sms, st));
-      } else {
-        BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[l], 768, xgr, 768, runs[r].count * T, 768, In, packed + p->pk.bih[l],
-                         0, st));
+  for (int s = 0; s < p->n_stacks; ++s) {
+    const int T = p->stackT[s];
+    for (int l = 0; l < c.rnn_layers; ++l) {
+      const int In = l == 0 ? 128 : 256;
+      const float* X = l == 0 ? wsp<float>(ws, p->off_pool[p->stack_src[s]]) : wsp<float>(ws, p->off_gru_out[s][l - 1]);
+      for (int r = 0; r < n_runs; ++r) {
+        const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+        const float* Xr = X + (size_t)runs[r].first * T * In;
+        float* xgr = xg + (size_t)runs[r].first * T * 768;
+        if (tc) {
+          for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
+            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In, In, xgr + n0, 768,
+                                (long long)runs[r].count * T, 128, In, packed + p->pk.bih[s][l] + n0, 0, sms, st));
+        } else {
+          BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[s][l], 768, xgr, 768, runs[r].count * T, 768, In,
+                           packed + p->pk.bih[s][l], 0, st));
+        }
+      }
+      FloatPtrs whhT, bhh;
+      for (int k = 0; k < kMaxGroups; ++k) {
+        int gi = k < n_groups ? k : 0;
+        const float* packed = wsp<float>(ws, p->off_packed[p->gpset[gi]]);
+        whhT.p[k] = packed + p->pk.whhT[s][l];
+        bhh.p[k] = packed + p->pk.bhh[s][l];
+      }
+      const bool last = l == c.rnn_layers - 1;
+      BSED_TRY(gru_forward(xg, g, whhT, bhh, wsp<float>(ws, p->off_gru_out[s][l]), last ? wsp<float>(ws, p->off_enc[s]) : nullptr,
+                           save ? wsp<float>(ws, p->off_gru_saved[s][l]) : nullptr, T, p->skeys[s], p->thresh,
+                           p->inv_keep, st));
+    }
+  }
+
+  if (!c.fpn) {
+    BSED_CHECK_CUDA(cudaMemcpyAsync(enc, wsp<float>(ws, p->off_enc[0]), sizeof(float) * (size_t)B * p->Tout * 256,
+                                    cudaMemcpyDeviceToDevice, st));
+  } else {
+    // feature pyramid merge (src/models/CRNN.py:323-328):
+    //   x_2 = conv1x1_2(cat(x_2, upsample_4(x_4)))  (156 frames) ; x = conv1x1_4(cat(x, upsample_2(x_2)))  (313 frames)
+    const float* lo[2] = {wsp<float>(ws, p->off_enc[2]), wsp<float>(ws, p->off_y2)};
+    const float* hi[2] = {wsp<float>(ws, p->off_enc[1]), wsp<float>(ws, p->off_enc[0])};
+    float* outs[2] = {wsp<float>(ws, p->off_y2), enc};
+    for (int j = 0; j < 2; ++j) {
+      const int Ta = p->stackT[1 - j], Tb = p->stackT[2 - j];
+      float* cat = wsp<float>(ws, p->off_cat[j]);
+      BSED_TRY(fpn_cat_upsample_fwd(hi[j], lo[j], cat, B, Ta, Tb, st));
+      for (int r = 0; r < n_runs; ++r) {
+        const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+        const float* bias = p->pset_params[runs[r].pset] + p->pl.m_b[j];
+        const float* A = cat + (size_t)runs[r].first * Ta * 512;
+        float* Y = outs[j] + (size_t)runs[r].first * Ta * 256;
+        const long long M = (long long)runs[r].count * Ta;
+        if (tc) {
+          for (int n0 = 0; n0 < 256; n0 += 128)   // B operand rows = output channels n0.., K-major as the reference stores them
+            BSED_TRY(tc_gemm_nt(A, 512, packed + p->pk.m_w[j] + (size_t)n0 * 512, 512, Y + n0, 256, M, 128, 512, bias + n0, 0,
+                                sms, st));
+        } else {
+          BSED_TRY(gemm_nn(A, 512, packed + p->pk.m_wT[j], 256, Y, 256, (int)M, 256, 512, bias, 0, st));
+        }
       }
     }
-    FloatPtrs whhT, bhh;
-    for (int k = 0; k < kMaxGroups; ++k) {
-      int gi = k < n_groups ? k : 0;
-      const float* packed = wsp<float>(ws, p->off_packed[p->gpset[gi]]);
-      whhT.p[k] = packed + p->pk.whhT[l];
-      bhh.p[k] = packed + p->pk.bhh[l];
-    }
-    const bool last = l == c.rnn_layers - 1;
-    BSED_TRY(gru_forward(xg, g, whhT, bhh, wsp<float>(ws, p->off_gru_out[l]), last ? enc_i : nullptr,
-                         save ? wsp<float>(ws, p->off_gru_saved[l]) : nullptr, T, p->keys[c.n_cnn], p->thresh,
-                         p->inv_keep, st));
   }
-
-  BSED_CHECK_CUDA(cudaMemcpyAsync(enc, enc_i, sizeof(float) * (size_t)B * T * 256, cudaMemcpyDeviceToDevice, st));
   p->saved_valid = save;
   return BSED_OK;
 }
@@ -665,71 +828,112 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
 
   if (!accumulate) BSED_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * pl.total, st));
 
-  // ---- gradient w.r.t. the encoder output, through the final dropout
-  float* denc = wsp<float>(ws, p->off_denc);
-  const size_t ro = (size_t)first * T;  // row offset of the first masked clip in (B*T)-row matrices
-  const long long BTn = (long long)nb * T;
-  BSED_CHECK_CUDA(cudaMemcpyAsync(denc + ro * 256, d_enc + ro * 256, sizeof(float) * BTn * 256, cudaMemcpyDeviceToDevice, st));
-  BSED_TRY(dropout_bwd_mask(denc + ro * 256, nullptr, (long long)ro * 256, BTn * 256, p->keys[c.n_cnn], p->thresh,
-                            p->inv_keep, st));
-
-  // ---- GRU stack
+  // ---- gradient w.r.t. the dropout output of every GRU stack
   float* dxg = wsp<float>(ws, p->off_dxg);
   float* dgh = wsp<float>(ws, p->off_dgh);
   float* dx1 = wsp<float>(ws, p->off_dx1);
-  int cur = 0;
-  float* dpool_cur = wsp<float>(ws, p->off_dpool[cur]);
-  for (int l = c.rnn_layers - 1; l >= 0; --l) {
-    const int In = l == 0 ? 128 : 256;
-    const float* X = l == 0 ? wsp<float>(ws, p->off_pool[c.n_cnn - 1]) : wsp<float>(ws, p->off_gru_out[l - 1]);
-    const float* out_l = wsp<float>(ws, p->off_gru_out[l]);
-    // gradient w.r.t. this layer's output: denc for the top layer, dx1 (ping-pong with denc) below
-    float* dout = ((c.rnn_layers - 1 - l) % 2 == 0) ? denc : dx1;
-    float* dxin = ((c.rnn_layers - 1 - l) % 2 == 0) ? dx1 : denc;
-    BSED_TRY(gru_backward(dout, wsp<float>(ws, p->off_gru_saved[l]), out_l, packed + p->pk.whh[l], dxg, dgh, T, first,
-                          nb, st));
-    for (int d = 0; d < 2; ++d) {
+  Groups one;
+  one.n = 1;
+  for (int k = 0; k < kMaxGroups; ++k) one.first[k] = 0, one.count[k] = k == 0 ? 1 : 0;
+  if (!c.fpn) {
+    const size_t ro = (size_t)first * p->Tout;  // row offset of the first masked clip in (B*T)-row matrices
+    BSED_CHECK_CUDA(cudaMemcpyAsync(wsp<float>(ws, p->off_denc[0]) + ro * 256, d_enc + ro * 256,
+                                    sizeof(float) * (size_t)nb * p->Tout * 256, cudaMemcpyDeviceToDevice, st));
+  } else {
+    // backward of the feature-pyramid merge, fine scale first (forward: src/models/CRNN.py:323-328)
+    float* dcat = wsp<float>(ws, p->off_dcat);
+    const float* dY[2] = {wsp<float>(ws, p->off_dy2), d_enc};                 // gradient of the merge output of level j
+    float* d_hi[2] = {wsp<float>(ws, p->off_denc[1]), wsp<float>(ws, p->off_denc[0])};
+    float* d_lo[2] = {wsp<float>(ws, p->off_denc[2]), wsp<float>(ws, p->off_dy2)};
+    for (int j = 1; j >= 0; --j) {
+      const int Ta = p->stackT[1 - j], Tb = p->stackT[2 - j];
+      const size_t roa = (size_t)first * Ta, rob = (size_t)first * Tb;
+      const long long M = (long long)nb * Ta;
+      const float* dy = dY[j] + roa * 256;
+      const float* cat = wsp<float>(ws, p->off_cat[j]) + roa * 512;
+      // dW[co][k] += sum_rows dy[row][co] * cat[row][k] ; db += column sums of dy
       if (tc) {
-        // dW_hh[j][i] += sum_{b,t} dgh[b][t][j] * h[b][t -/+ 1][i] ; dW_ih[j][i] += sum_{b,t} dxg[b][t][j] * x[b][t][i]
-        TcOperand Ah{dgh + ro * 768, 768, d * 384, 384}, Bh{out_l + ro * 256, 256, d * 128, 128};
-        BSED_TRY(tc_wgrad_ex(Ah, Bh, nb, T, 1, 1, d == 0 ? -1 : 1, grads + pl.whh[l][d], 128, 1, 0, wgpart,
-                             p->wgpart_bytes, sms, st));
-        TcOperand Ai{dxg + ro * 768, 768, d * 384, 384}, Bi{X + ro * In, In, 0, In};
-        BSED_TRY(tc_wgrad_ex(Ai, Bi, nb, T, 1, 1, 0, grads + pl.wih[l][d], In, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+        TcOperand Aw{dy, 256, 0, 256}, Bw{cat, 512, 0, 512};
+        BSED_TRY(tc_wgrad_ex(Aw, Bw, nb, Ta, 1, 1, 0, grads + pl.m_w[j], 512, 1, 0, wgpart, p->wgpart_bytes, sms, st));
       } else {
-        BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
-                              grads + pl.whh[l][d], T, BTn, target, st));
-        BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[l][d], In, 1, 384, In, BTn,
-                         target, st));
+        BSED_TRY(gemm_tn(dy, 256, cat, 512, grads + pl.m_w[j], 512, 1, 256, 512, M, target, st));
       }
-    }
-    Groups one;
-    one.n = 1;
-    one.first[0] = 0;
-    one.count[0] = 1;
-    BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
-    BSED_TRY(col_stats(dxg + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
-    BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bih[l][0], 384, st));
-    BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bih[l][1], 384, st));
-    BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
-    BSED_TRY(col_stats(dgh + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
-    BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bhh[l][0], 384, st));
-    BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bhh[l][1], 384, st));
-    float* dX = l == 0 ? dpool_cur + ro * 128 : dxin + ro * 256;
-    if (tc) {
-      for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
-        BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[l] + (size_t)n0 * 768, 768, dX + n0, In, BTn, 128,
-                            768, nullptr, 0, sms, st));
-    } else {
-      BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[l], In, dX, In, (int)BTn, In, 768, nullptr, 0, st));
+      BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
+      BSED_TRY(col_stats(dy, nullptr, 2, one, M, 256, dscr, sms, st));
+      BSED_TRY(add_double_to_float(dscr, 2, grads + pl.m_b[j], 256, st));
+      // dcat = dy * W   ([M][256] x [256][512])
+      if (tc) {
+        for (int n0 = 0; n0 < 512; n0 += 128)
+          BSED_TRY(tc_gemm_nt(dy, 256, packed + p->pk.m_wT[j] + (size_t)n0 * 256, 256, dcat + roa * 512 + n0, 512, M, 128, 256,
+                              nullptr, 0, sms, st));
+      } else {
+        BSED_TRY(gemm_nn(dy, 256, packed + p->pk.m_w[j], 512, dcat + roa * 512, 512, (int)M, 512, 256, nullptr, 0, st));
+      }
+      BSED_TRY(fpn_cat_upsample_bwd(dcat + roa * 512, d_hi[j] + roa * 256, d_lo[j] + rob * 256, nb, Ta, Tb, st));
     }
   }
 
-  // ---- CNN blocks
+  // ---- one GRU stack: dropout mask, layers top-down; dX of layer 0 goes to (or is added to) the gradient of the
+  // pooled block output that fed the stack
+  int cur = 0;
+  float* dpool_cur = wsp<float>(ws, p->off_dpool[cur]);
+  auto stack_backward = [&](int s, int accumulate_dx) -> int {
+    const int T = p->stackT[s];
+    const size_t ro = (size_t)first * T;
+    const long long BTn = (long long)nb * T;
+    float* denc = wsp<float>(ws, p->off_denc[s]);
+    BSED_TRY(dropout_bwd_mask(denc + ro * 256, nullptr, (long long)ro * 256, BTn * 256, p->skeys[s], p->thresh,
+                              p->inv_keep, st));
+    for (int l = c.rnn_layers - 1; l >= 0; --l) {
+      const int In = l == 0 ? 128 : 256;
+      const float* X = l == 0 ? wsp<float>(ws, p->off_pool[p->stack_src[s]]) : wsp<float>(ws, p->off_gru_out[s][l - 1]);
+      const float* out_l = wsp<float>(ws, p->off_gru_out[s][l]);
+      // gradient w.r.t. this layer's output: denc for the top layer, dx1 (ping-pong with denc) below
+      float* dout = ((c.rnn_layers - 1 - l) % 2 == 0) ? denc : dx1;
+      float* dxin = ((c.rnn_layers - 1 - l) % 2 == 0) ? dx1 : denc;
+      BSED_TRY(gru_backward(dout, wsp<float>(ws, p->off_gru_saved[s][l]), out_l, packed + p->pk.whh[s][l], dxg, dgh, T, first,
+                            nb, st));
+      for (int d = 0; d < 2; ++d) {
+        if (tc) {
+          // dW_hh[j][i] += sum_{b,t} dgh[b][t][j] * h[b][t -/+ 1][i] ; dW_ih[j][i] += sum_{b,t} dxg[b][t][j] * x[b][t][i]
+          TcOperand Ah{dgh + ro * 768, 768, d * 384, 384}, Bh{out_l + ro * 256, 256, d * 128, 128};
+          BSED_TRY(tc_wgrad_ex(Ah, Bh, nb, T, 1, 1, d == 0 ? -1 : 1, grads + pl.whh[s][l][d], 128, 1, 0, wgpart,
+                               p->wgpart_bytes, sms, st));
+          TcOperand Ai{dxg + ro * 768, 768, d * 384, 384}, Bi{X + ro * In, In, 0, In};
+          BSED_TRY(tc_wgrad_ex(Ai, Bi, nb, T, 1, 1, 0, grads + pl.wih[s][l][d], In, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+        } else {
+          BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
+                                grads + pl.whh[s][l][d], T, BTn, target, st));
+          BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[s][l][d], In, 1, 384, In, BTn,
+                           target, st));
+        }
+      }
+      BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
+      BSED_TRY(col_stats(dxg + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
+      BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bih[s][l][0], 384, st));
+      BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bih[s][l][1], 384, st));
+      BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
+      BSED_TRY(col_stats(dgh + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
+      BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bhh[s][l][0], 384, st));
+      BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bhh[s][l][1], 384, st));
+      float* dX = l == 0 ? dpool_cur + ro * 128 : dxin + ro * 256;
+      const int acc = l == 0 ? accumulate_dx : 0;
+      if (tc) {
+        for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
+          BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l] + (size_t)n0 * 768, 768, dX + n0, In, BTn, 128,
+                              768, nullptr, acc, sms, st));
+      } else {
+        BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[s][l], In, dX, In, (int)BTn, In, 768, nullptr, acc, st));
+      }
+    }
+    return BSED_OK;
+  };
+
+  // ---- one conv block: consumes dpool_cur (gradient of its pooled output), leaves the gradient of its input there
   float* dxn = wsp<float>(ws, p->off_dxn);
   double* stats2 = wsp<double>(ws, p->off_stats2);
   float* G = wsp<float>(ws, p->off_G);
-  for (int i = c.n_cnn - 1; i >= 0; --i) {
+  auto block_backward = [&](int i) -> int {
     const LayerGeom& L = p->L[i];
     float* xhat = wsp<float>(ws, p->off_xhat[i]);
     float* lin = wsp<float>(ws, p->off_lin[i]);
@@ -743,8 +947,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       double* bsums = wsp<double>(ws, p->off_bsums);
       float* tab = wsp<float>(ws, p->off_bntab);
       BSED_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * kMaxGroups * 128 * 4, st));
-      BSED_TRY(glu_gate_pool_bwd_sums(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i],
-                                      p->thresh, p->inv_keep, bsums, sms, st));
+      BSED_TRY(glu_gate_pool_bwd_sums(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i],
+                                      p->bthresh[i], p->binv[i], bsums, sms, st));
       BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * n * L.Cout * L.Cout, st));
       int gfirst_rel[kMaxGroups] = {0, 0, 0, 0};
       for (int k = 0; k < n; ++k) {
@@ -770,8 +974,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
                                 L.rows / pack, gfirst_rel, sms, st));
     } else {
     // gate / dropout / pool backward: lin -> d_lin (in place), dxn <- direct gate path
-    BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->keys[i], p->thresh,
-                               p->inv_keep, st));
+    BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
+                               p->binv[i], st));
     // dxn += d_lin * Wg        (Wg [c'][c] is already K-major for this product)
     if (tc)
       BSED_TRY(tc_gemm_nt(lin + off, L.Cout, packed + p->pk.glu_wgT[i], L.Cout, dxn + off, L.Cout, M, L.Cout, L.Cout,
@@ -826,7 +1030,16 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     } else {
       BSED_TRY(conv0_wgrad(p->x_in, dxn, grads + pl.conv_w[0], first, nb, L.T, L.F, L.Cout, sms, st));
     }
+    return BSED_OK;
+  };
+
+  // coarse scales first: rnn_4 -> second stage application -> (+ rnn_2) -> first application -> (+ rnn) -> trunk
+  for (int s = p->n_stacks - 1; s >= 1; --s) {
+    BSED_TRY(stack_backward(s, s != p->n_stacks - 1));
+    BSED_TRY(block_backward(p->stack_src[s]));
   }
+  BSED_TRY(stack_backward(0, p->n_stacks > 1));
+  for (int i = c.n_cnn - 1; i >= 0; --i) BSED_TRY(block_backward(i));
   p->saved_valid = false;  // lin buffers now hold gradients
   return BSED_OK;
 }
@@ -845,39 +1058,52 @@ extern "C" int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* 
     return *idx >= 0;
   };
   int i;
-  if (layer_of("xhat", &i) && i < p->cfg.n_cnn) {
+  if (layer_of("xhat", &i) && i < p->n_blocks) {
     *ptr = wsp<float>(workspace, p->off_xhat[i]);
     *numel = Bm * p->L[i].rows * p->L[i].Cout;
     return BSED_OK;
   }
-  if (layer_of("lin", &i) && i < p->cfg.n_cnn) {
+  if (layer_of("lin", &i) && i < p->n_blocks) {
     *ptr = wsp<float>(workspace, p->off_lin[i]);
     *numel = Bm * p->L[i].rows * p->L[i].Cout;
     return BSED_OK;
   }
-  if (layer_of("pool", &i) && i < p->cfg.n_cnn) {
+  if (layer_of("pool", &i) && i < p->n_blocks) {
     *ptr = wsp<float>(workspace, p->off_pool[i]);
     *numel = Bm * p->L[i].prows * p->L[i].Cout;
     return BSED_OK;
   }
   if (layer_of("gru", &i) && i < p->cfg.rnn_layers) {
-    *ptr = wsp<float>(workspace, p->off_gru_out[i]);
+    *ptr = wsp<float>(workspace, p->off_gru_out[0][i]);
     *numel = Bm * p->Tout * 256;
     return BSED_OK;
   }
   struct Tap { const char* n; size_t off; long long numel; } taps[] = {
-      {"denc", p->off_denc, Bm * p->Tout * 256}, {"dx1", p->off_dx1, Bm * p->Tout * 256},
+      {"denc", p->off_denc[0], Bm * p->Tout * 256}, {"dx1", p->off_dx1, Bm * p->Tout * 256},
       {"dxg", p->off_dxg, Bm * p->Tout * 768},   {"dgh", p->off_dgh, Bm * p->Tout * 768},
-      {"xg", p->off_xg, Bm * p->Tout * 768},     {"enc", p->off_enc, Bm * p->Tout * 256},
+      {"xg", p->off_xg, Bm * p->Tout * 768},     {"enc", p->off_enc[0], Bm * p->Tout * 256},
       {"dpool0", p->off_dpool[0], Bm * p->L[0].prows * p->L[0].Cout},
       {"dpool1", p->off_dpool[1], Bm * p->L[0].prows * p->L[0].Cout},
-      {"saved0", p->off_gru_saved[0], Bm * p->Tout * 1024}, {"saved1", p->off_gru_saved[1], Bm * p->Tout * 1024}};
+      {"saved0", p->off_gru_saved[0][0], Bm * p->Tout * 1024}, {"saved1", p->off_gru_saved[0][1], Bm * p->Tout * 1024}};
   for (const Tap& t : taps)
     if (s == t.n) {
       *ptr = wsp<float>(workspace, t.off);
       *numel = t.numel;
       return BSED_OK;
     }
+  if (p->cfg.fpn) {
+    struct Tap { const char* n; size_t off; long long numel; } ftaps[] = {
+        {"enc1", p->off_enc[1], Bm * p->stackT[1] * 256}, {"enc2", p->off_enc[2], Bm * p->stackT[2] * 256},
+        {"y2", p->off_y2, Bm * p->stackT[1] * 256},       {"cat0", p->off_cat[0], Bm * p->stackT[1] * 512},
+        {"cat1", p->off_cat[1], Bm * p->Tout * 512},      {"denc1", p->off_denc[1], Bm * p->stackT[1] * 256},
+        {"denc2", p->off_denc[2], Bm * p->stackT[2] * 256}, {"dy2", p->off_dy2, Bm * p->stackT[1] * 256}};
+    for (const Tap& t : ftaps)
+      if (s == t.n) {
+        *ptr = wsp<float>(workspace, t.off);
+        *numel = t.numel;
+        return BSED_OK;
+      }
+  }
   if (s == "dxn") {
     *ptr = wsp<float>(workspace, p->off_dxn);
     *numel = Bm * p->L[0].rows * p->L[0].Cout;

@@ -180,6 +180,107 @@ int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long lo
 }
 
 // ---------------------------------------------------------------------------------------------
+// feature-pyramid merge of CRNN_fpn (src/models/CRNN.py:323-328):  torch.cat((x, nn.Upsample((Ta,1), mode='bilinear',
+// align_corners=True)(y)), 1) on (B, 256, T, 1) tensors, here time-major (B, T, 256).  Along time (the width axis
+// has one element): src = t * (Tb-1)/(Ta-1), i0 = floor(src), i1 = min(i0+1, Tb-1), w1 = src - i0, all in fp32 as
+// ATen's upsample_bilinear2d does for float inputs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fpn_src(int t, float scale, int Tb, int* i0, int* i1, float* w1) {
+  const float src = scale * (float)t;
+  const int k = (int)src;
+  *i0 = k;
+  *i1 = k + (k < Tb - 1 ? 1 : 0);
+  *w1 = src - (float)k;
+}
+
+__global__ void __launch_bounds__(256) fpn_cat_upsample_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                   float* __restrict__ cat, int Ta, int Tb, float scale,
+                                                                   long long total) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of cat
+  if (id >= total) return;
+  const int q = (int)(id % 128);
+  const long long row = id / 128;
+  const int t = (int)(row % Ta);
+  const long long clip = row / Ta;
+  float4 v;
+  if (q < 64) {
+    v = *reinterpret_cast<const float4*>(a + row * 256 + q * 4);
+  } else {
+    int i0, i1;
+    float w1;
+    fpn_src(t, scale, Tb, &i0, &i1, &w1);
+    const float w0 = 1.f - w1;
+    const float4 x0 = *reinterpret_cast<const float4*>(b + (clip * Tb + i0) * 256 + (q - 64) * 4);
+    const float4 x1 = *reinterpret_cast<const float4*>(b + (clip * Tb + i1) * 256 + (q - 64) * 4);
+    v = make_float4(w0 * x0.x + w1 * x1.x, w0 * x0.y + w1 * x1.y, w0 * x0.z + w1 * x1.z, w0 * x0.w + w1 * x1.w);
+  }
+  *reinterpret_cast<float4*>(cat + row * 512 + q * 4) = v;
+}
+
+int fpn_cat_upsample_fwd(const float* a, const float* b, float* cat, int B, int Ta, int Tb, cudaStream_t st) {
+  BSED_REQUIRE(Ta >= 2 && Tb >= 1, "fpn_cat_upsample: Ta=%d Tb=%d", Ta, Tb);
+  const long long total = (long long)B * Ta * 128;
+  const float scale = (float)(Tb - 1) / (float)(Ta - 1);
+  fpn_cat_upsample_fwd_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a, b, cat, Ta, Tb, scale, total);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// da[b][t][c] = dcat[b][t][c] ; db[b][u][c] = sum_t w(t -> u) * dcat[b][t][256 + c]   (gather over the few t that read u)
+__global__ void __launch_bounds__(256) fpn_cat_upsample_bwd_kernel(const float* __restrict__ dcat, float* __restrict__ da,
+                                                                   float* __restrict__ db, int Ta, int Tb, float scale,
+                                                                   long long total_a, long long total) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  if (id < total_a) {   // float4 of da
+    const int q = (int)(id % 64);
+    const long long row = id / 64;
+    *reinterpret_cast<float4*>(da + row * 256 + q * 4) = *reinterpret_cast<const float4*>(dcat + row * 512 + q * 4);
+    return;
+  }
+  const long long jd = id - total_a;   // float4 of db
+  const int q = (int)(jd % 64);
+  const long long row = jd / 64;
+  const int u = (int)(row % Tb);
+  const long long clip = row / Tb;
+  // candidates: every t whose source interval [i0, i1] can contain u, i.e. src in (u - 1, u + 1)
+  int t_lo = 0, t_hi = Ta - 1;
+  if (scale > 0.f) {
+    t_lo = (int)floorf((float)(u - 1) / scale) - 1;
+    t_hi = (int)ceilf((float)(u + 1) / scale) + 1;
+    if (t_lo < 0) t_lo = 0;
+    if (t_hi > Ta - 1) t_hi = Ta - 1;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = t_lo; t <= t_hi; ++t) {
+    int i0, i1;
+    float w1;
+    fpn_src(t, scale, Tb, &i0, &i1, &w1);
+    float w = 0.f;
+    if (i0 == u) w += 1.f - w1;
+    if (i1 == u) w += w1;
+    if (w != 0.f) {
+      const float4 g = *reinterpret_cast<const float4*>(dcat + (clip * Ta + t) * 512 + 256 + q * 4);
+      acc.x += w * g.x;
+      acc.y += w * g.y;
+      acc.z += w * g.z;
+      acc.w += w * g.w;
+    }
+  }
+  *reinterpret_cast<float4*>(db + row * 256 + q * 4) = acc;
+}
+
+int fpn_cat_upsample_bwd(const float* dcat, float* da, float* db, int B, int Ta, int Tb, cudaStream_t st) {
+  BSED_REQUIRE(Ta >= 2 && Tb >= 1, "fpn_cat_upsample: Ta=%d Tb=%d", Ta, Tb);
+  const long long total_a = (long long)B * Ta * 64, total_b = (long long)B * Tb * 64;
+  const float scale = (float)(Tb - 1) / (float)(Ta - 1);
+  fpn_cat_upsample_bwd_kernel<<<ceil_div(total_a + total_b, 256), 256, 0, st>>>(dcat, da, db, Ta, Tb, scale, total_a,
+                                                                                total_a + total_b);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mean-teacher losses (src/main.py:376,405,434,439-449) and their gradients
 //   BCELoss: -(y log x + (1-y) log(1-x)), logs clamped at -100, mean; grad (x-y)/max(x(1-x),1e-12)/N
 //   MSELoss: mean (a-b)^2; grad 2(a-b)/N

@@ -120,6 +120,10 @@ int opt_ema_step(float* params, const float* grads, float* m, float* v, float* e
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
                 int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st);
 int add_f32(float* dst, const float* src, long long n, cudaStream_t st);
+// feature-pyramid merge (src/models/CRNN.py:323-328): cat[b][t][0:256] = a[b][t], cat[b][t][256:512] = bilinear
+// (align_corners=True) upsampling of b from Tb to Ta frames; backward splits dcat into da and the transposed upsampling db
+int fpn_cat_upsample_fwd(const float* a, const float* b, float* cat, int B, int Ta, int Tb, cudaStream_t st);
+int fpn_cat_upsample_bwd(const float* dcat, float* da, float* db, int B, int Ta, int Tb, cudaStream_t st);
 
 // ---- tc_gemm.cu (tcgen05 / TMA)
 int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,

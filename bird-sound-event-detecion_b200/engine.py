@@ -21,7 +21,7 @@ REFERENCE_PREDICTOR_KWARGS = dict(nclass=20, attention=True, n_RNN_cell=128)
 
 def make_cfg(nclass=20, dropout=0.5, nb_filters=(16, 32, 64, 128, 128, 128, 128),
              pooling=((2, 2), (2, 2), (1, 2), (1, 2), (1, 2), (1, 2), (1, 2)), n_RNN_cell=128,
-             n_layers_RNN=2, n_frames=1255, n_mels=128, bn_eps=1e-3, bn_momentum=0.99):
+             n_layers_RNN=2, n_frames=1255, n_mels=128, bn_eps=1e-3, bn_momentum=0.99, fpn=False):
     cfg = CrnnCfg()
     cfg.n_frames, cfg.n_mels, cfg.n_cnn = int(n_frames), int(n_mels), len(nb_filters)
     for i, (c, p) in enumerate(zip(nb_filters, pooling)):
@@ -30,6 +30,7 @@ def make_cfg(nclass=20, dropout=0.5, nb_filters=(16, 32, 64, 128, 128, 128, 128)
         cfg.pool_f[i] = int(p[1])
     cfg.rnn_hidden, cfg.rnn_layers, cfg.n_class = int(n_RNN_cell), int(n_layers_RNN), int(nclass)
     cfg.dropout, cfg.bn_eps, cfg.bn_momentum = float(dropout), float(bn_eps), float(bn_momentum)
+    cfg.fpn = int(bool(fpn))   # CRNN_fpn (src/models/CRNN.py:243-337)
     return cfg
 
 
@@ -69,6 +70,7 @@ class Plan:
         self.ldl = int(self.lib.bsed_predictor_ldl())
         self.n_class = int(cfg.n_class)
         self.n_cnn = int(cfg.n_cnn)
+        self.n_bn_layers = self.n_cnn + (1 if cfg.fpn else 0)   # entries of num_batches_tracked
         self.ws_bytes = int(self.lib.bsed_plan_workspace_bytes(self.p))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device) if with_workspace else None
         self._pred_ws = {}

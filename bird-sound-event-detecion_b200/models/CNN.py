@@ -27,3 +27,19 @@ class CNN(_Holder):
             self.add_module(f"conv{i}", conv)
             self.add_module(f"batchnorm{i}", bn)
             self.add_module(f"glu{i}", glu)
+
+
+class CNN_FPN(_Holder):
+    """Parameter holder of src/models/CNN_FPN.py:33-100: `cnn` (the 7 blocks) plus the shared stage `cnn_fcn`, `glu`,
+    `bn_fcn` that CNN_FPN.forward applies twice, and `conv1x1`, which the reference registers but never calls (it stays in
+    the state dict and receives no gradient)."""
+
+    def __init__(self, n_in_channel, nb_filters, pooling):
+        super().__init__()
+        self.nb_filters = list(nb_filters)
+        self.cnn = CNN(n_in_channel, nb_filters, pooling)
+        self.cnn_fcn = _Holder()
+        self.glu = _Holder()
+        self.glu.linear = _Holder()
+        self.bn_fcn = _Holder()
+        self.conv1x1 = _Holder()

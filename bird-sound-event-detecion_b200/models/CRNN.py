@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from .. import engine
-from .CNN import CNN
+from .CNN import CNN, CNN_FPN
 from .RNN import BidirectionalGRU
 
 _dropout_state = {"seed": 2023, "step": 0}
@@ -161,6 +161,8 @@ class _CRNNFunction(torch.autograd.Function):
 
 
 class CRNN(_FlatModule):
+    _fpn = False
+
     def __init__(self, n_in_channel, nclass, attention=False, activation="Relu", dropout=0, train_cnn=True,
                  rnn_type='BGRU', n_RNN_cell=64, n_layers_RNN=1, dropout_recurrent=0, cnn_integration=False,
                  learned_post=False, **kwargs):
@@ -187,25 +189,50 @@ class CRNN(_FlatModule):
         self.rnn_type, self.train_cnn = rnn_type, train_cnn
         self.dropout_p = float(dropout)
         self.cfg_kwargs = dict(nclass=nclass, dropout=float(dropout), nb_filters=nb_filters, pooling=pooling,
-                               n_RNN_cell=n_RNN_cell, n_layers_RNN=n_layers_RNN)
-        self.cnn = CNN(1, nb_filters, pooling)
+                               n_RNN_cell=n_RNN_cell, n_layers_RNN=n_layers_RNN, fpn=self._fpn)
+        if self._fpn:
+            if nb_filters[-1] != 128:
+                raise NotImplementedError("CRNN_fpn: the shared stage cnn_fcn is Conv2d(128, 128) (src/models/CNN_FPN.py:72)")
+            self.cnn = CNN_FPN(1, nb_filters, pooling)
+            trunk = self.cnn.cnn
+        else:
+            self.cnn = CNN(1, nb_filters, pooling)
+            trunk = self.cnn
         self.rnn = BidirectionalGRU(nb_filters[-1], n_RNN_cell, dropout=dropout_recurrent, num_layers=n_layers_RNN)
+        rnns = [self.rnn]
+        if self._fpn:
+            self.rnn_2 = BidirectionalGRU(nb_filters[-1], n_RNN_cell, dropout=dropout_recurrent, num_layers=n_layers_RNN)
+            self.rnn_4 = BidirectionalGRU(nb_filters[-1], n_RNN_cell, dropout=dropout_recurrent, num_layers=n_layers_RNN)
+            rnns += [self.rnn_2, self.rnn_4]
         self.dropout = nn.Dropout(dropout)   # placeholder with the reference's name; the mask is applied in-kernel
         ps, bs, cm = [], [], []
         cin = 1
         for i, c in enumerate(nb_filters):
-            conv, bnm, glu = getattr(self.cnn, f"conv{i}"), getattr(self.cnn, f"batchnorm{i}"), getattr(self.cnn, f"glu{i}")
+            conv, bnm, glu = getattr(trunk, f"conv{i}"), getattr(trunk, f"batchnorm{i}"), getattr(trunk, f"glu{i}")
             ps += [(conv, "weight", (c, cin, 3, 3)), (conv, "bias", (c,)), (bnm, "weight", (c,)), (bnm, "bias", (c,)),
                    (glu.linear, "weight", (c, c)), (glu.linear, "bias", (c,))]
             bs += [(bnm, "running_mean", (c,)), (bnm, "running_var", (c,))]
             cm.append(bnm)
             cin = c
+        if self._fpn:   # registration order of CNN_FPN.__init__ (src/models/CNN_FPN.py:71-79)
+            f = self.cnn
+            ps += [(f.cnn_fcn, "weight", (128, 128, 3, 3)), (f.cnn_fcn, "bias", (128,)),
+                   (f.glu.linear, "weight", (128, 128)), (f.glu.linear, "bias", (128,)),
+                   (f.bn_fcn, "weight", (128,)), (f.bn_fcn, "bias", (128,)),
+                   (f.conv1x1, "weight", (128, 256, 1, 1)), (f.conv1x1, "bias", (128,))]
+            bs += [(f.bn_fcn, "running_mean", (128,)), (f.bn_fcn, "running_var", (128,))]
+            cm.append(f.bn_fcn)
         H = n_RNN_cell
-        for l in range(n_layers_RNN):
-            n_in = cin if l == 0 else 2 * H
-            for suf in ("", "_reverse"):
-                ps += [(self.rnn.rnn, f"weight_ih_l{l}{suf}", (3 * H, n_in)), (self.rnn.rnn, f"weight_hh_l{l}{suf}", (3 * H, H)),
-                       (self.rnn.rnn, f"bias_ih_l{l}{suf}", (3 * H,)), (self.rnn.rnn, f"bias_hh_l{l}{suf}", (3 * H,))]
+        for rnn in rnns:
+            for l in range(n_layers_RNN):
+                n_in = cin if l == 0 else 2 * H
+                for suf in ("", "_reverse"):
+                    ps += [(rnn.rnn, f"weight_ih_l{l}{suf}", (3 * H, n_in)), (rnn.rnn, f"weight_hh_l{l}{suf}", (3 * H, H)),
+                           (rnn.rnn, f"bias_ih_l{l}{suf}", (3 * H,)), (rnn.rnn, f"bias_hh_l{l}{suf}", (3 * H,))]
+        if self._fpn:   # src/models/CRNN.py:281-282
+            self.conv1x1_2, self.conv1x1_4 = nn.Module(), nn.Module()
+            for m in (self.conv1x1_2, self.conv1x1_4):
+                ps += [(m, "weight", (256, 512, 1, 1)), (m, "bias", (256,))]
         self._counter_mods = cm
         self._build(ps, bs, len(cm))
         self._slots, self._free = [], []
@@ -221,7 +248,7 @@ class CRNN(_FlatModule):
                 p = getattr(mod, name)
                 if name == "weight" and len(shape) == 4:
                     nn.init.kaiming_uniform_(p, a=math.sqrt(5))
-                    bound = 1 / math.sqrt(shape[1] * 9)
+                    bound = 1 / math.sqrt(shape[1] * shape[2] * shape[3])
                     nn.init.uniform_(getattr(mod, "bias"), -bound, bound)
                 elif name == "weight" and len(shape) == 2:
                     nn.init.kaiming_uniform_(p, a=math.sqrt(5))
@@ -253,8 +280,9 @@ class CRNN(_FlatModule):
         if s not in self._free:
             self._free.append(s)
 
-    def forward(self, x):
-        # input size : (batch_size, n_channels, n_frames, n_freq)
+    def forward(self, x, inference=False):
+        # input size : (batch_size, n_channels, n_frames, n_freq); `inference` is accepted as CRNN_fpn.forward does
+        # (src/models/CRNN.py:285) and, as there, has no effect on the encoder
         if not x.is_cuda:
             raise RuntimeError("libbsed CRNN runs on CUDA tensors only (no CPU fallback)")
         if not self._flat.is_cuda:
@@ -264,6 +292,15 @@ class CRNN(_FlatModule):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # grad mode is off inside Function.forward
         enc = _CRNNFunction.apply(self, x, seed, step, need_grad, *params)
         return enc, enc
+
+
+class CRNN_fpn(CRNN):
+    """src/models/CRNN.py:243-337 -- feature-pyramid CRNN: the CNN_FPN trunk yields three time scales (313 / 156 / 78
+    frames), each with its own BidirectionalGRU (`rnn`, `rnn_2`, `rnn_4`); the scales are merged top-down with
+    bilinear upsampling and the 1x1 convolutions `conv1x1_2`, `conv1x1_4`.  Same constructor and
+    forward(x, inference=False) -> (x, d_input) as the reference; state-dict keys `cnn.cnn.conv0.weight` ...
+    `cnn.cnn_fcn.*`, `cnn.glu.linear.*`, `cnn.bn_fcn.*`, `cnn.conv1x1.*`, `rnn*.rnn.*`, `conv1x1_2.*`, `conv1x1_4.*`."""
+    _fpn = True
 
 
 class _PredictorFunction(torch.autograd.Function):

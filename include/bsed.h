@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BSED_ABI_VERSION 1
+#define BSED_ABI_VERSION 2
 
 #define BSED_OK 0
 #define BSED_E_INVALID (-1) /* bad argument / shape / alignment */
@@ -96,6 +96,16 @@ int bsed_median_decode(bsed_handle h, const float* strong, int B, int T, int C, 
  * ------------------------------------------------------------------------------------------ */
 #define BSED_MAX_CNN_LAYERS 8
 
+/* fpn = 1 selects CRNN_fpn / CNN_FPN (src/models/CRNN.py:243-337, src/models/CNN_FPN.py:33-100): after the CNN trunk
+ * the shared-weight stage cnn_fcn (Conv3x3 128->128) -> bn_fcn -> glu -> dropout -> AvgPool[2,1] is applied twice
+ * (313 -> 156 -> 78 frames); rnn / rnn_2 / rnn_4 run on the three time scales; after dropout the scales are merged
+ * top-down: x_2 = conv1x1_2(cat(x_2, up(x_4))), x = conv1x1_4(cat(x, up(x_2))) with bilinear align_corners=True
+ * upsampling along time.  The flat parameter buffer follows CRNN_fpn.named_parameters(): cnn.cnn.* (7 blocks),
+ * cnn.cnn_fcn.{weight,bias}, cnn.glu.linear.{weight,bias}, cnn.bn_fcn.{weight,bias}, cnn.conv1x1.{weight,bias}
+ * (registered but unused by the reference's forward: its gradient stays zero), rnn.rnn.*, rnn_2.rnn.*, rnn_4.rnn.*,
+ * conv1x1_2.{weight,bias}, conv1x1_4.{weight,bias}.  BatchNorm buffers: the 7 blocks then bn_fcn
+ * (num_batches_tracked[8]; bn_fcn is updated twice per train-mode forward, as in the reference). */
+
 typedef struct {
   int n_frames;                        /* 1255 */
   int n_mels;                          /* 128  */
@@ -109,6 +119,7 @@ typedef struct {
   float dropout;                       /* 0.5 */
   float bn_eps;                        /* 1e-3 */
   float bn_momentum;                   /* 0.99 */
+  int fpn;                             /* 0 = CRNN (src/models/CRNN.py:178-240); 1 = CRNN_fpn (:243-337), see below */
 } bsed_crnn_cfg;
 
 typedef struct bsed_crnn_plan* bsed_plan;

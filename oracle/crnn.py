@@ -13,6 +13,7 @@ Follows:
   * src/models/CRNN.py:178-240   CRNN.forward -> (x, d_input)
   * src/models/CRNN.py:548-577   Predictor.forward -> (strong, weak)
   * src/main.py:632-641       crnn_kwargs / predictor_kwargs
+  * src/models/CNN_FPN.py:33-100, src/models/CRNN.py:243-337   CNN_FPN / CRNN_fpn (OracleCRNNfpn below)
 State-dict key names equal the reference's (79 CRNN keys `cnn.conv0.weight` ...
 `rnn.rnn.bias_hh_l1_reverse`; Predictor `dense.*`, `dense_softmax.*`).
 
@@ -32,8 +33,11 @@ CRNN_KWARGS = dict(
     pooling=[[2, 2], [2, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2]])
 PREDICTOR_KWARGS = dict(nclass=20, attention=True, n_RNN_cell=128)
 
-# dropout streams: one per CNN block, then the post-RNN dropout
+# dropout streams: one per CNN block, then the post-RNN dropout; CRNN_fpn adds the two applications of the shared
+# stage (8, 9) and the rnn_2 / rnn_4 outputs (10, 11)   (csrc/engine.cu: bkeys / skeys)
 STREAM_RNN_OUT = 7
+STREAM_FCN = (8, 9)
+STREAM_RNN_OUT_FPN = (7, 10, 11)
 
 
 def mix_key(seed, step, stream):
@@ -137,6 +141,115 @@ class OracleCRNN(nn.Module):
         x = x.squeeze(-1).permute(0, 2, 1)    # (B, 313, 128)
         x = self.rnn(x)                       # (B, 313, 256)
         x = self.dropout(x)
+        return x, x
+
+
+class CycleHashDropout(nn.Module):
+    """One dropout MODULE called several times per forward (CNN_FPN.dropout twice, CRNN_fpn.dropout three times): call k
+    uses streams[k].  `layout` "BCT" = the (B, C, T) tensors CRNN_fpn.forward drops (src/models/CRNN.py:318-322); the
+    mask index is always the time-major element index ((b*T + t)*C + c) the kernels use."""
+
+    def __init__(self, p, streams, layout="NCHW"):
+        super().__init__()
+        self.p, self.streams, self.layout = float(p), tuple(streams), layout
+        self.keys = None
+        self.batch_offset = 0
+        self.calls = 0
+
+    def set(self, seed, step, batch_offset=0):
+        self.keys = [mix_key(seed, step, s) for s in self.streams]
+        self.batch_offset = batch_offset
+        self.calls = 0
+
+    def forward(self, x):
+        if not self.training or self.p == 0.0 or self.keys is None:
+            return x
+        key = self.keys[self.calls % len(self.keys)]
+        self.calls += 1
+        if self.layout == "BCT":
+            B, C, T = x.shape
+            b = np.arange(B)[:, None, None] + self.batch_offset
+            idx = (b * T + np.arange(T)[None, None, :]) * C + np.arange(C)[None, :, None]
+        else:
+            B, C, T, F = x.shape
+            b = np.arange(B)[:, None, None, None] + self.batch_offset
+            c = np.arange(C)[None, :, None, None]
+            t = np.arange(T)[None, None, :, None]
+            f = np.arange(F)[None, None, None, :]
+            idx = ((b * T + t) * F + f) * C + c
+        keep = torch.from_numpy(keep_mask(idx, key, self.p)).to(x.dtype)
+        return x * keep * (1.0 / (1.0 - self.p))
+
+
+class _CNNFPN(nn.Module):
+    """src/models/CNN_FPN.py:33-100.  Note `self.dropout = nn.Dropout(0.5)` (:79): the shared stage drops with p = 0.5
+    whatever `conv_dropout` is."""
+
+    def __init__(self, n_in_channel, dropout, kernel_size, padding, stride, nb_filters, pooling):
+        super().__init__()
+        seq = nn.Sequential()
+        cin = n_in_channel
+        for i, cout in enumerate(nb_filters):
+            seq.add_module(f"conv{i}", nn.Conv2d(cin, cout, kernel_size[i], stride[i], padding[i]))
+            seq.add_module(f"batchnorm{i}", nn.BatchNorm2d(cout, eps=0.001, momentum=0.99))
+            seq.add_module(f"glu{i}", _Gate(cout))
+            seq.add_module(f"dropout{i}", HashDropout(dropout, i))
+            seq.add_module(f"pooling{i}", nn.AvgPool2d(tuple(pooling[i])))
+            cin = cout
+        self.cnn = seq
+        self.cnn_fcn = nn.Conv2d(128, 128, 3, 1, 1)
+        self.glu = _Gate(128)
+        self.pool_fcn = nn.AvgPool2d([2, 1])
+        self.bn_fcn = nn.BatchNorm2d(128, eps=0.001, momentum=0.99)
+        self.conv1x1 = nn.Conv2d(256, 128, 1)          # registered, never called (as in the reference)
+        self.dropout = CycleHashDropout(0.5, STREAM_FCN)
+
+    def forward(self, x):
+        x = self.cnn(x)
+        outs = [x]
+        for _ in range(2):
+            x = self.pool_fcn(self.dropout(self.glu(self.bn_fcn(self.cnn_fcn(x)))))
+            outs.append(x)
+        return outs
+
+
+class OracleCRNNfpn(nn.Module):
+    """src/models/CRNN.py:243-337 (CRNN_fpn) with the hash dropout; state-dict keys equal the reference's."""
+
+    def __init__(self, n_in_channel=1, nclass=20, attention=True, activation="glu", dropout=0.0,
+                 n_RNN_cell=128, n_layers_RNN=2, kernel_size=None, padding=None, stride=None,
+                 nb_filters=None, pooling=None, n_frames_out=313, **_):
+        super().__init__()
+        assert activation.lower() == "glu"
+        self.cnn = _CNNFPN(n_in_channel, dropout, kernel_size, padding, stride, nb_filters, pooling)
+        self.rnn = _BiGRU(nb_filters[-1], n_RNN_cell, n_layers_RNN)
+        self.rnn_2 = _BiGRU(nb_filters[-1], n_RNN_cell, n_layers_RNN)
+        self.rnn_4 = _BiGRU(nb_filters[-1], n_RNN_cell, n_layers_RNN)
+        self.dropout = CycleHashDropout(dropout, STREAM_RNN_OUT_FPN, layout="BCT")
+        self.upsample_2 = nn.Upsample((n_frames_out, 1), mode='bilinear', align_corners=True)
+        self.upsample_4 = nn.Upsample((n_frames_out // 2, 1), mode='bilinear', align_corners=True)
+        self.conv1x1_2 = nn.Conv2d(512, 256, 1)
+        self.conv1x1_4 = nn.Conv2d(512, 256, 1)
+
+    def set_dropout_keys(self, seed, step, batch_offset=0):
+        for m in self.modules():
+            if isinstance(m, HashDropout):
+                m.key = mix_key(seed, step, m.stream)
+                m.batch_offset = batch_offset
+            elif isinstance(m, CycleHashDropout):
+                m.set(seed, step, batch_offset)
+
+    def forward(self, x, inference=False):
+        x, x_2, x_4 = self.cnn(x)
+        x = self.rnn(x.squeeze(-1).permute(0, 2, 1)).permute(0, 2, 1)          # (B, 256, 313)
+        x_2 = self.rnn_2(x_2.squeeze(-1).permute(0, 2, 1)).permute(0, 2, 1)
+        x_4 = self.rnn_4(x_4.squeeze(-1).permute(0, 2, 1)).permute(0, 2, 1)
+        x = self.dropout(x).unsqueeze(-1)
+        x_2 = self.dropout(x_2).unsqueeze(-1)
+        x_4 = self.dropout(x_4).unsqueeze(-1)
+        x_2 = self.conv1x1_2(torch.cat((x_2, self.upsample_4(x_4)), 1))
+        x = self.conv1x1_4(torch.cat((x, self.upsample_2(x_2)), 1)).squeeze(-1)
+        x = x.permute(0, 2, 1)
         return x, x
 
 

@@ -106,7 +106,7 @@ def mt_step(model, predictor, ema_model, ema_predictor, optimizer, x, x_ema, xs,
     grads = {}
     for prefix, mod in (("crnn.", model), ("pred.", predictor)):
         for n, p in mod.named_parameters():
-            grads[prefix + n] = p.grad.detach().clone()
+            grads[prefix + n] = p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)
     optimizer.step()
 
     gs = global_step + 1

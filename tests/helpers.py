@@ -22,6 +22,28 @@ def oracle_models(seed=5, linear_std=0.2, dropout=0.0, train=False):
     return oc, op
 
 
+def oracle_fpn_models(seed=5, linear_std=0.2, dropout=0.0, train=False):
+    oc = ocrnn.OracleCRNNfpn(**{**ocrnn.CRNN_KWARGS, "dropout": dropout})
+    op = ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
+    ocrnn.reference_style_init(oc, op, seed, linear_std)
+    oc.train(train)
+    op.train(train)
+    return oc, op
+
+
+def bsed_fpn_models(oc, op, dropout=0.0, device="cuda", precision=None):
+    """Our CRNN_fpn / Predictor carrying the oracle's weights (state-dict keys are identical to the reference's)."""
+    from bsed_b200 import engine
+    from bsed_b200.models import CRNN_fpn, Predictor
+    kw = dict(engine.REFERENCE_CRNN_KWARGS)
+    kw["dropout"] = dropout
+    m = CRNN_fpn(**kw, precision=precision)
+    p = Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+    m.load_state_dict(oc.state_dict())
+    p.load_state_dict(op.state_dict())
+    return m.to(device), p.to(device)
+
+
 def bsed_models(oc, op, dropout=0.0, device="cuda"):
     """Our CRNN/Predictor carrying the oracle's weights (state-dict keys are identical)."""
     from bsed_b200 import engine

@@ -1,0 +1,168 @@
+"""CRNN_fpn (src/models/CRNN.py:243-337, src/models/CNN_FPN.py) on the GPU through the C ABI, against the CPU oracle and
+the fixtures produced by the reference's own modules (tests/golden/fpn_*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bsed_fpn_models, golden, max_abs, oracle_fpn_models, rel_l2
+from bsed_b200.utilities import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sub(v, n=4096):
+    v = v.reshape(-1)
+    return v if v.size <= n else v[:: max(1, v.size // n)][:n]
+
+
+def test_fpn_layout_matches_reference():
+    from bsed_b200 import engine
+    from bsed_b200.models import CRNN_fpn
+    g = golden("fpn_state_dict_keys.npz")
+    m = CRNN_fpn(**engine.REFERENCE_CRNN_KWARGS)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    assert [str(tuple(v.shape)) for v in m.state_dict().values()] == [str(s) for s in g["shapes"]]
+    assert [n for n, _ in m.named_parameters()] == [str(k) for k in g["param_keys"]]
+    plan = engine.Plan(engine.make_cfg(**m.cfg_kwargs), max_clips=1, device="cuda", with_workspace=False)
+    assert plan.n_params == m._flat.numel() == int(g["n_params"]) == 2556368
+    # the library's tensor offsets equal the module's named_parameters() layout
+    offs, o = [], 0
+    for _, _, shape in m._param_specs:
+        offs.append(o)
+        o += int(np.prod(shape))
+    assert plan.param_offsets() == offs
+    assert plan.n_bn == m._flat_bn.numel() == 2 * (16 + 32 + 64 + 4 * 128 + 128) and plan.n_bn_layers == 8
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 2e-2)])
+def test_fpn_eval_forward(precision, tol):
+    g = golden("fpn_eval.npz")
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=11))
+    oc, op = oracle_fpn_models(seed=5, linear_std=0.2)
+    m, p = bsed_fpn_models(oc, op, precision=precision)
+    m.eval(); p.eval()
+    with torch.no_grad():
+        enc, d_in = m(x.cuda())
+        strong, weak = p(enc)
+        strong_inf, _ = p(enc, inference=True)
+    assert enc.shape == (2, 313, 256) and d_in is enc
+    es, ew = max_abs(strong.cpu().numpy(), g["strong"]), max_abs(weak.cpu().numpy(), g["weak"])
+    print(f"fpn eval {precision}: enc rel_l2 {rel_l2(enc.cpu().numpy()[:, ::8], g['enc']):.2e} strong {es:.2e} weak {ew:.2e}")
+    # fp32: north-star 1e-3 on probabilities; tf32: stated tolerance (the random-init fixture network amplifies rounding)
+    assert es < tol and ew < tol
+    # weak-gated strong predictions (Predictor.forward(inference=True), src/models/CRNN.py:570-574)
+    gate = (weak > 0.5).float().unsqueeze(1)
+    assert torch.equal(strong_inf, strong * gate)
+
+
+@pytest.mark.parametrize("precision,tol_p,tol_g", [("fp32", 1e-3, 3e-3), ("tf32", 5e-3, 2e-2)])
+def test_fpn_train_forward_backward(precision, tol_p, tol_g):
+    from bsed_b200.models import set_dropout_seed
+    g = golden("fpn_train.npz")
+    x = torch.from_numpy(synth.make_logmel_like(2, seed=11))
+    oc, op = oracle_fpn_models(seed=5, linear_std=0.2)
+    m, p = bsed_fpn_models(oc, op, dropout=0.5, precision=precision)
+    m.train(); p.train()
+    set_dropout_seed(2023, 2)     # the next forward uses step 3, as the fixture
+    enc, _ = m(x.cuda())
+    strong, weak = p(enc)
+    w = torch.from_numpy(np.random.default_rng(7).standard_normal(tuple(strong.shape)).astype(np.float32)).cuda()
+    ((strong * w).mean() + weak.mean()).backward()
+    es, ew = max_abs(strong.detach().cpu().numpy(), g["strong"]), max_abs(weak.detach().cpu().numpy(), g["weak"])
+    assert es < tol_p and ew < tol_p, (es, ew)
+    assert int(m.cnn.bn_fcn.num_batches_tracked) == 2 and int(m.cnn.cnn.batchnorm0.num_batches_tracked) == 1
+    assert max_abs(m.cnn.bn_fcn.running_mean.cpu().numpy(), g["rm_fcn"]) < 1e-3
+    assert rel_l2(m.cnn.bn_fcn.running_var.cpu().numpy(), g["rv_fcn"]) < 5e-3
+    bad, worst = [], 0.0
+    for n, prm in m.named_parameters():
+        if n.startswith("cnn.conv1x1."):
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0    # unused by the reference forward
+            continue
+        gn = float(g["gn_" + n])
+        if gn < 1e-5:
+            continue                  # conv biases in front of a train-mode BatchNorm: rounding noise only
+        e = rel_l2(_sub(prm.grad.cpu().numpy()), g["g_" + n])
+        worst = max(worst, e)
+        if e > tol_g:
+            bad.append((n, e))
+    print(f"fpn train {precision}: strong {es:.2e} weak {ew:.2e} worst grad rel_l2 {worst:.2e}")
+    assert not bad, bad
+
+
+def test_fpn_fused_trainer_matches_reference_fixture():
+    from bsed_b200.main import MeanTeacherTrainer
+    g = golden("fpn_mt_step_drop.npz")
+    oc, op = oracle_fpn_models(seed=5, linear_std=0.2)
+    tc, tp = oracle_fpn_models(seed=6, linear_std=0.2)
+    m, p = bsed_fpn_models(oc, op, dropout=0.5)
+    em, ep = bsed_fpn_models(tc, tp, dropout=0.5)
+    for mod in (m, p, em, ep):
+        mod.train()
+    for prm in list(em.parameters()) + list(ep.parameters()):
+        prm.detach_()
+    xs = torch.from_numpy(synth.make_logmel_like(2, seed=21)).cuda()
+    xr = torch.from_numpy(synth.make_logmel_like(2, seed=22))
+    xr_ema = (xr + 0.5 * torch.from_numpy(synth.make_logmel_like(2, seed=23)) * 0.1).cuda()
+    xr = xr.cuda()
+    ts = torch.from_numpy(synth.make_targets(2, seed=24)).cuda()
+    tr = MeanTeacherTrainer(m, p, em, ep, lr=5e-4, n_syn=2, n_real=2, dropout_seed=2023)
+    for it in range(2):
+        l = tr.step(xr, xr_ema, xs, ts, global_step=100 + it, rampup_length=500)
+        lv = [float(v) for v in l.cpu()]
+        ref = [float(g[f"strong_class{it}"]), float(g[f"weak_class{it}"]), float(g[f"cons_strong{it}"]),
+               float(g[f"cons_weak{it}"])]
+        for a, b in zip(lv, ref):
+            assert a == pytest.approx(b, rel=3e-3, abs=2e-6), (it, lv, ref)
+        if it == 0:
+            o, bad = 0, []
+            for (mod, pname, shape), (fullname, _) in zip(m._param_specs + p._param_specs,
+                                                          list(m.named_parameters()) + list(p.named_parameters())):
+                k = int(np.prod(shape))
+                got = tr.grads[o:o + k].cpu().numpy()
+                o += k
+                key = ("g_crnn." if o <= tr.n_crnn else "g_pred.") + fullname
+                if float(g[key.replace("g_", "gn_", 1)]) < 1e-4:
+                    continue
+                e = rel_l2(_sub(got), g[key])
+                if e > 3e-3:
+                    bad.append((fullname, e))
+            assert not bad, bad
+            assert max_abs(tr.last["strong"][2:].cpu().numpy(), g["strong0"]) < 1e-3
+    ssd, tsd = m.state_dict(), em.state_dict()
+    for k in ("cnn.cnn.conv0.weight", "cnn.cnn.glu4.linear.weight", "cnn.cnn_fcn.weight", "cnn.glu.linear.weight",
+              "cnn.bn_fcn.weight", "cnn.conv1x1.weight", "rnn.rnn.weight_hh_l0", "rnn_2.rnn.weight_ih_l1_reverse",
+              "rnn_4.rnn.bias_hh_l0", "conv1x1_2.weight", "conv1x1_4.bias", "cnn.bn_fcn.running_var"):
+        d = np.abs(ssd[k].cpu().numpy().reshape(-1)[:2048].astype(np.float64) - g["s_" + k])
+        assert d.max() < 1.1e-3 and d.mean() < 2e-5, (k, d.max(), d.mean())       # two Adam steps of lr 5e-4
+        assert max_abs(tsd[k].cpu().numpy().reshape(-1)[:2048], g["t_" + k]) < 1e-4, k
+    assert int(tsd["cnn.bn_fcn.num_batches_tracked"]) == int(g["t_nbt_fcn"]) == 4
+    assert int(ssd["cnn.bn_fcn.num_batches_tracked"]) == int(g["s_nbt_fcn"]) == 8
+    assert int(ssd["cnn.cnn.batchnorm0.num_batches_tracked"]) == int(g["s_nbt0"]) == 4
+
+
+def test_fpn_step_timing_report(capsys):
+    """Not a parity test: prints the 24 + 12-clip CRNN_fpn mean-teacher step time (tf32) for the round notes."""
+    from bsed_b200 import engine
+    from bsed_b200.main import MeanTeacherTrainer
+    from bsed_b200.models import CRNN_fpn, Predictor
+    torch.manual_seed(0)
+    mk = lambda: (CRNN_fpn(**engine.REFERENCE_CRNN_KWARGS, precision="tf32").cuda().train(),
+                  Predictor(**engine.REFERENCE_PREDICTOR_KWARGS).cuda().train())
+    (m, p), (em, ep) = mk(), mk()
+    tr = MeanTeacherTrainer(m, p, em, ep, lr=5e-4, n_syn=12, n_real=12, precision="tf32")
+    x = torch.from_numpy(synth.make_logmel_like(12, seed=1)).cuda()
+    ts = torch.from_numpy(synth.make_targets(12, seed=2)).cuda()
+    for i in range(3):
+        tr.step(x, x, x, ts, i, 500)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(10):
+        l = tr.step(x, x, x, ts, 3 + i, 500)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    with capsys.disabled():
+        print(f"\nCRNN_fpn mean-teacher step (24 student + 12 teacher clips, tf32): {ms:.2f} ms -> {24e3 / ms:.0f} clips/s; "
+              f"losses {[round(float(v), 4) for v in l.cpu()]}")
+    assert torch.isfinite(l).all()
