@@ -319,6 +319,45 @@ int bn_finalize_train(const double* stats, const Groups& g, long long rows_per_c
   return BSED_OK;
 }
 
+// Running-statistics update of a BatchNorm that one forward applies twice (bn_fcn of CNN_FPN, src/models/CNN_FPN.py:86-96):
+// per group (= reference model call) the first application's batch statistics are blended in, then the second's, in the
+// reference's order; num_batches_tracked += 2.  statsA / statsB: double [group][C][2] = (sum, sum of squares).
+__global__ void bn_running_update2_kernel(const double* __restrict__ statsA, long long rowsA,
+                                          const double* __restrict__ statsB, long long rowsB, Groups g, int C,
+                                          float momentum, RunPtrs run) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int i = 0; i < g.n; ++i) {
+    if (!run.mean[i]) continue;
+    for (int a = 0; a < 2; ++a) {
+      const double* stats = a == 0 ? statsA : statsB;
+      const double n = (double)g.count[i] * (double)(a == 0 ? rowsA : rowsB);
+      const double s = stats[((size_t)i * C + c) * 2], ss = stats[((size_t)i * C + c) * 2 + 1];
+      const double mean = s / n;
+      double var = ss / n - mean * mean;
+      if (var < 0) var = 0;
+      const double unb = n > 1 ? var * n / (n - 1) : var;
+      run.mean[i][c] = (1.f - momentum) * run.mean[i][c] + momentum * (float)mean;
+      run.var[i][c] = (1.f - momentum) * run.var[i][c] + momentum * (float)unb;
+    }
+    if (c == 0 && run.nbt[i]) *run.nbt[i] += 2;
+  }
+}
+
+int bn_running_update2(const double* statsA, long long rowsA, const double* statsB, long long rowsB, const Groups& g, int C,
+                       float momentum, float* const* run_mean, float* const* run_var, int64_t* const* nbt,
+                       cudaStream_t st) {
+  RunPtrs run;
+  for (int i = 0; i < kMaxGroups; ++i) {
+    run.mean[i] = i < g.n ? run_mean[i] : nullptr;
+    run.var[i] = i < g.n ? run_var[i] : nullptr;
+    run.nbt[i] = i < g.n ? nbt[i] : nullptr;
+  }
+  bn_running_update2_kernel<<<ceil_div(C, 128), 128, 0, st>>>(statsA, rowsA, statsB, rowsB, g, C, momentum, run);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
 __global__ void bn_prepare_eval_kernel(Groups g, int C, float eps, BNPtrs bn, RunPtrs run) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;

@@ -682,7 +682,18 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       double* st_i = stats + (size_t)i * kMaxGroups * 128 * 2;
       if (!tc && i > 0) BSED_TRY(col_stats(y, nullptr, 0, g, L.rows, L.Cout, st_i, p->ctx->num_sms, st));
       // stats rows are indexed [group][C]: col_stats uses stride C, finalize too
-      BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, rmean, rvar, nbt, st));
+      if (i < c.n_cnn) {
+        BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, rmean, rvar, nbt, st));
+      } else {
+        // shared bn_fcn: batch mean / rstd per application now; its running statistics are updated after the second
+        // application, group by group, in the reference's order (application 1 then 2 of each model call)
+        float* no_f[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+        int64_t* no_i[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+        BSED_TRY(bn_finalize_train(st_i, g, L.rows, L.Cout, c.bn_eps, c.bn_momentum, bn, no_f, no_f, no_i, st));
+        if (i == c.n_cnn + 1)
+          BSED_TRY(bn_running_update2(stats + (size_t)c.n_cnn * kMaxGroups * 128 * 2, p->L[c.n_cnn].rows, st_i, L.rows, g,
+                                      L.Cout, c.bn_momentum, rmean, rvar, nbt, st));
+      }
     } else {
       BSED_TRY(bn_prepare_eval(g, L.Cout, c.bn_eps, bn, rmean, rvar, st));
     }

@@ -48,6 +48,9 @@ int col_stats(const float* a, const float* b, int mode, const Groups& g, long lo
 int bn_finalize_train(const double* stats, const Groups& g, long long rows_per_clip, int C, float eps,
                       float momentum, const BNPtrs& bn, float* const* run_mean, float* const* run_var,
                       int64_t* const* nbt, cudaStream_t st);
+int bn_running_update2(const double* statsA, long long rowsA, const double* statsB, long long rowsB, const Groups& g, int C,
+                       float momentum, float* const* run_mean, float* const* run_var, int64_t* const* nbt,
+                       cudaStream_t st);
 int bn_prepare_eval(const Groups& g, int C, float eps, const BNPtrs& bn, float* const* run_mean,
                     float* const* run_var, cudaStream_t st);
 int bn_normalize(float* y, const Groups& g, long long rows_per_clip, int C, const BNPtrs& bn,
