@@ -6,7 +6,7 @@
 // src/data/Transforms.py:74-139,155-197,304-322 (AugmentGaussianNoise, ApplyLog, PadOrTrunc,
 // Normalize).
 //
-// K1/K2 design: one CTA stages the audio of 16 consecutive frames (2048 + 15*255 samples) in
+// K1/K2 design: one CTA stages the audio of 32 consecutive frames (2048 + 31*255 samples) in
 // shared memory with one coalesced pass (reflect padding resolved at load time), so the 8x frame
 // overlap is served from SMEM, not HBM.  Each warp then owns whole frames: the 2048-point real FFT
 // is a 1024-point complex FFT (even/odd packing) done as 32 x 32 -- two in-register 32-point FFTs
@@ -17,11 +17,10 @@
 
 namespace bsed {
 
-constexpr int FE_FPC = 16;                                  // frames per CTA
-constexpr int FE_WARPS = 8;
+constexpr int FE_FPC = 32;                                  // frames per CTA
+constexpr int FE_WARPS = 16;                                // 4 warps per scheduler: the kernel is latency-bound below that
 constexpr int FE_AUD = ((kNFFT + (FE_FPC - 1) * kHop) + 15) / 16 * 16;  // 5888 staged samples
 constexpr int FE_BUF = 33 * 32;                             // padded transpose buffer (float2)
-constexpr int FE_MAG = 1028;
 constexpr int FE_MELW = 2048;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -98,7 +97,6 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
   int* mlen_s = mstart_s + kNMels;
   int* moff_s = mlen_s + kNMels;
   float2* bufs = reinterpret_cast<float2*>(moff_s + kNMels);
-  float* mags = reinterpret_cast<float*>(bufs + FE_WARPS * FE_BUF);
 
   const int tid = threadIdx.x;
   const int lane = tid % 32, warp = tid / 32;
@@ -132,7 +130,9 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
   __syncthreads();
 
   float2* buf = bufs + warp * FE_BUF;
-  float* mag = mags + warp * FE_MAG;
+  // magnitudes overwrite the spectrum in place: |X[k]| lives in the real slot of buf[k] (float index 2k); the lane that
+  // untangles the pair (k, 1024 - k) is the only one that touches those two slots
+  float* mag = reinterpret_cast<float*>(buf);
 
   for (int fi = warp; fi < FE_FPC; fi += FE_WARPS) {
     const int t = frame0 + fi;
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 #pragma unroll
     for (int a = 0; a < 32; ++a) {
       int n0 = 64 * a + 2 * lane;
-      v[a] = make_float2(fr[n0] * win_s[n0], fr[n0 + 1] * win_s[n0 + 1]);
+      const float2 w2 = *reinterpret_cast<const float2*>(win_s + n0);
+      v[a] = make_float2(fr[n0] * w2.x, fr[n0 + 1] * w2.y);
     }
     fft32(v);
 #pragma unroll
@@ -167,10 +168,10 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
       int k = lane + 32 * jj;
       if (k == 0) {
         float2 z0 = buf[0];
-        mag[0] = fabsf(z0.x + z0.y);
-        mag[1024] = fabsf(z0.x - z0.y);
         float2 zh = buf[512];
-        mag[512] = sqrtf(zh.x * zh.x + zh.y * zh.y);
+        mag[0] = fabsf(z0.x + z0.y);
+        mag[2 * 1024] = fabsf(z0.x - z0.y);
+        mag[2 * 512] = sqrtf(zh.x * zh.x + zh.y * zh.y);
       } else {
         float2 zk = buf[k], zm = buf[1024 - k];
         float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
         float2 P = cmul(tw2048_s[k], O);
         float xr = E.x + P.y, xi = E.y - P.x;
         float yr = E.x - P.y, yi = -E.y - P.x;
-        mag[k] = sqrtf(xr * xr + xi * xi);
-        mag[1024 - k] = sqrtf(yr * yr + yi * yi);
+        mag[2 * k] = sqrtf(xr * xr + xi * xi);
+        mag[2 * (1024 - k)] = sqrtf(yr * yr + yi * yi);
       }
     }
     __syncwarp();
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
       int m = lane + 32 * r;
       int s = mstart_s[m], len = mlen_s[m], off = moff_s[m];
       float acc = 0.f;
-      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[s + j], acc);
+      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[2 * (s + j)], acc);
       out[m] = acc;
     }
     __syncwarp();
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 
 constexpr size_t FE_SMEM_BYTES = sizeof(float) * (FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516) +
                                  sizeof(float) * FE_MELW + sizeof(int) * 3 * kNMels +
-                                 sizeof(float2) * FE_WARPS * FE_BUF + sizeof(float) * FE_WARPS * FE_MAG;
+                                 sizeof(float2) * FE_WARPS * FE_BUF;
 
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st) {
   BSED_REQUIRE(n_samples >= kNFFT / 2 + 1, "melspec: n_samples=%d < 1025 (reflect padding)", n_samples);
@@ -221,76 +222,116 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
 }
 
 // ---------------------------------------------------------------------------------------------
-// amplitude_to_db (+ noise, pad/trunc, normalise).  Two kernels:
-//   1. per clip: [std_m = sqrt(mean_t(mel^2) * 10^(-snr/10))], max |x| with x = mel (+ std_m * noise)
-//   2. elementwise: max(20 log10(max(1e-5,|x|)), maxdb - 80), rows >= t_in -> 0, (v - mean_m)/std_m
-// Arithmetic in double: the reference evaluates the noisy branch in float64.
-// workspace per clip: 128 doubles (std) + 1 double (max)
+// amplitude_to_db (+ noise, pad/trunc, normalise): HBM-bound, float4 accesses, grid = (row chunks, clips).
+//   1. (noise only) per clip and mel bin: sum_t mel^2  -> std_m = sqrt(mean_t(mel^2) * 10^(-snr/10))   [fp64 atomics]
+//   2. per clip: max |x|, x = mel (+ std_m * noise)                                  [atomicMax on the float bits]
+//   3. elementwise: max(20 log10(max(1e-5,|x|)), maxdb - 80), rows >= t_in -> 0, (v - mean_m)/std_m
+// The noisy sample x is formed in double (the reference evaluates that branch in float64; a float add would lose the
+// small |x| left after cancellation); the logarithm is fp32, as numpy's is on the reference's float32 path.
+// workspace per clip: 128 doubles (sum of squares) + 1 slot (max bits)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) db_stats_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
-                                                        double snr_scale, int t_in, double* ws) {
-  const int b = blockIdx.x;
-  const int m = threadIdx.x % kNMels, r = threadIdx.x / kNMels;  // 8 row lanes
+constexpr int DB_CHUNKS = 16;   // row chunks per clip in the reduction passes
+
+__global__ void __launch_bounds__(256) db_sumsq_kernel(const float* __restrict__ mel, int t_in, double* __restrict__ ws) {
+  const int b = blockIdx.y;
+  const int q = threadIdx.x % 32, r = threadIdx.x / 32;   // 4 mel bins per thread, 8 row lanes
+  const int rows = (t_in + DB_CHUNKS - 1) / DB_CHUNKS;
+  const int t0 = blockIdx.x * rows;
+  const int t1 = min(t_in, t0 + rows);
   const float* x = mel + (size_t)b * t_in * kNMels;
-  double* std_out = ws + (size_t)b * (kNMels + 1);
+  double s[4] = {0, 0, 0, 0};
+  for (int t = t0 + r; t < t1; t += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)t * kNMels + q * 4);
+    s[0] += (double)v.x * (double)v.x;
+    s[1] += (double)v.y * (double)v.y;
+    s[2] += (double)v.z * (double)v.z;
+    s[3] += (double)v.w * (double)v.w;
+  }
   __shared__ double red[8][kNMels];
-  __shared__ double std_s[kNMels];
-  if (noise) {
-    double s = 0;
-    for (int t = r; t < t_in; t += 8) {
-      double v = (double)x[(size_t)t * kNMels + m];
-      s += v * v * snr_scale;
-    }
-    red[r][m] = s;
-    __syncthreads();
-    if (r == 0) {
-      double tot = 0;
-      for (int i = 0; i < 8; ++i) tot += red[i][m];
-      std_s[m] = sqrt(tot / (double)t_in);
-      std_out[m] = std_s[m];
-    }
-    __syncthreads();
-  }
-  double mx = 0;
-  const float* nz = noise ? noise + (size_t)b * t_in * kNMels : nullptr;
-  for (int t = r; t < t_in; t += 8) {
-    double v = (double)x[(size_t)t * kNMels + m];
-    if (nz) v += std_s[m] * (double)nz[(size_t)t * kNMels + m];
-    mx = fmax(mx, fabs(v));
-  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[r][q * 4 + j] = s[j];
   __syncthreads();
-  red[r][m] = mx;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = 0;
-    for (int i = threadIdx.x; i < 8 * kNMels; i += 32) v = fmax(v, (&red[0][0])[i]);
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (threadIdx.x == 0) std_out[kNMels] = v;
+  if (threadIdx.x < kNMels) {
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+    atomicAdd(ws + (size_t)b * (kNMels + 1) + threadIdx.x, tot);
   }
 }
 
-__global__ void __launch_bounds__(256) db_apply_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
-                                                       int t_in, int frames, const float* __restrict__ sc_mean,
-                                                       const float* __restrict__ sc_std, const double* __restrict__ ws,
-                                                       float* __restrict__ out) {
+__device__ __forceinline__ float db_sample(float m, float nz, double std_m) { return (float)fabs((double)m + std_m * (double)nz); }
+
+template <bool NOISE>
+__global__ void __launch_bounds__(256) db_max_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
+                                                     double snr_scale, int t_in, double* __restrict__ ws) {
   const int b = blockIdx.y;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)frames * kNMels) return;
-  int m = (int)(i % kNMels), t = (int)(i / kNMels);
+  const int q = threadIdx.x % 32, r = threadIdx.x / 32;
+  const int rows = (t_in + DB_CHUNKS - 1) / DB_CHUNKS;
+  const int t0 = blockIdx.x * rows;
+  const int t1 = min(t_in, t0 + rows);
+  const float* x = mel + (size_t)b * t_in * kNMels;
+  const float* nz = NOISE ? noise + (size_t)b * t_in * kNMels : nullptr;
+  double* w = ws + (size_t)b * (kNMels + 1);
+  double sd[4] = {0, 0, 0, 0};
+  if (NOISE) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sd[j] = sqrt(w[q * 4 + j] * snr_scale / (double)t_in);
+  }
+  float mx = 0.f;
+  for (int t = t0 + r; t < t1; t += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)t * kNMels + q * 4);
+    if (NOISE) {
+      const float4 n = *reinterpret_cast<const float4*>(nz + (size_t)t * kNMels + q * 4);
+      mx = fmaxf(mx, fmaxf(fmaxf(db_sample(v.x, n.x, sd[0]), db_sample(v.y, n.y, sd[1])),
+                           fmaxf(db_sample(v.z, n.z, sd[2]), db_sample(v.w, n.w, sd[3]))));
+    } else {
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  }
+  mx = warp_max(mx);
+  __shared__ float red[8];
+  if (q == 0) red[r] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    atomicMax(reinterpret_cast<unsigned int*>(w + kNMels), __float_as_uint(mx));   // mx >= 0: bit order == value order
+  }
+}
+
+template <bool NOISE>
+__global__ void __launch_bounds__(256) db_apply_kernel(const float* __restrict__ mel, const float* __restrict__ noise,
+                                                       double snr_scale, int t_in, int frames,
+                                                       const float* __restrict__ sc_mean, const float* __restrict__ sc_std,
+                                                       const double* __restrict__ ws, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4
+  if (i >= (long long)frames * (kNMels / 4)) return;
+  const int q = (int)(i % (kNMels / 4)), t = (int)(i / (kNMels / 4));
   const double* w = ws + (size_t)b * (kNMels + 1);
-  double v = 0.0;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
   if (t < t_in) {
-    size_t e = ((size_t)b * t_in + t) * kNMels + m;
-    double x = (double)mel[e];
-    if (noise) x += w[m] * (double)noise[e];
-    double db = 20.0 * log10(fmax(1e-5, fabs(x)));
-    double mdb = 20.0 * log10(fmax(1e-5, w[kNMels]));
-    v = fmax(db, mdb - 80.0);
+    const size_t e = ((size_t)b * t_in + t) * kNMels + q * 4;
+    const float4 v = *reinterpret_cast<const float4*>(mel + e);
+    float xs[4] = {fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w)};
+    if (NOISE) {
+      const float4 n = *reinterpret_cast<const float4*>(noise + e);
+      const float ms[4] = {v.x, v.y, v.z, v.w}, ns[4] = {n.x, n.y, n.z, n.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xs[j] = db_sample(ms[j], ns[j], sqrt(w[q * 4 + j] * snr_scale / (double)t_in));
+    }
+    const float mxv = __uint_as_float(*reinterpret_cast<const unsigned int*>(w + kNMels));
+    const float floor_db = 20.0f * log10f(fmaxf(1e-5f, mxv)) - 80.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(20.0f * log10f(fmaxf(1e-5f, xs[j])), floor_db);
   }
   // ApplyLog / PadOrTrunc produce float32 (ToTensor().float()) before Normalize
-  float vf = (float)v;
-  if (sc_mean) vf = (float)(((double)vf - (double)sc_mean[m]) / (double)sc_std[m]);
-  out[((size_t)b * frames + t) * kNMels + m] = vf;
+  if (sc_mean) {
+    const float4 mu = *reinterpret_cast<const float4*>(sc_mean + q * 4), sg = *reinterpret_cast<const float4*>(sc_std + q * 4);
+    o[0] = (o[0] - mu.x) / sg.x;
+    o[1] = (o[1] - mu.y) / sg.y;
+    o[2] = (o[2] - mu.z) / sg.z;
+    o[3] = (o[3] - mu.w) / sg.w;
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)b * frames + t) * kNMels + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_in, int frames,
@@ -298,17 +339,30 @@ int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_i
               cudaStream_t st) {
   BSED_REQUIRE(B > 0 && t_in > 0 && frames > 0, "amp_to_db: B=%d t_in=%d frames=%d", B, t_in, frames);
   BSED_REQUIRE((sc_mean == nullptr) == (sc_std == nullptr), "amp_to_db: scaler mean/std must come together");
-  if (ws_bytes < sizeof(double) * (size_t)B * (kNMels + 1)) {
-    bsed_set_error("amp_to_db: workspace %zu < %zu", ws_bytes, sizeof(double) * (size_t)B * (kNMels + 1));
+  const size_t need = sizeof(double) * (size_t)B * (kNMels + 1);
+  if (ws_bytes < need) {
+    bsed_set_error("amp_to_db: workspace %zu < %zu", ws_bytes, need);
     return BSED_E_WORKSPACE;
   }
-  double snr_scale = pow(10.0, -(double)snr_db / 10.0);
-  db_stats_kernel<<<B, 1024, 0, st>>>(mel, noise, snr_scale, t_in, (double*)ws);
+  const double snr_scale = pow(10.0, -(double)snr_db / 10.0);
+  double* w = (double*)ws;
+  // algorithmic bytes: mel (and noise) read once + log-mel written once; the reductions re-read mel (and noise)
+  ProfScope prof(PROF_ELEMENTWISE, 0.0, 4.0 * B * kNMels * ((noise ? 2.0 : 1.0) * t_in + (double)frames), st);
+  BSED_CHECK_CUDA(cudaMemsetAsync(w, 0, need, st));
+  dim3 rgrid(DB_CHUNKS, B);
+  if (noise) {
+    db_sumsq_kernel<<<rgrid, 256, 0, st>>>(mel, t_in, w);
+    BSED_CHECK_LAUNCH();
+    db_max_kernel<true><<<rgrid, 256, 0, st>>>(mel, noise, snr_scale, t_in, w);
+  } else {
+    db_max_kernel<false><<<rgrid, 256, 0, st>>>(mel, nullptr, snr_scale, t_in, w);
+  }
   BSED_CHECK_LAUNCH();
-  int t_used = t_in < frames ? t_in : frames;
-  (void)t_used;
-  dim3 grid(ceil_div((long long)frames * kNMels, 256), B);
-  db_apply_kernel<<<grid, 256, 0, st>>>(mel, noise, t_in, frames, sc_mean, sc_std, (const double*)ws, out);
+  dim3 grid(ceil_div((long long)frames * (kNMels / 4), 256), B);
+  if (noise)
+    db_apply_kernel<true><<<grid, 256, 0, st>>>(mel, noise, snr_scale, t_in, frames, sc_mean, sc_std, w, out);
+  else
+    db_apply_kernel<false><<<grid, 256, 0, st>>>(mel, nullptr, snr_scale, t_in, frames, sc_mean, sc_std, w, out);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
