@@ -116,7 +116,12 @@ int build_tables(bsed_context* h) {
   std::vector<float> win(kNFFT);
   for (int n = 0; n < kNFFT; ++n) win[n] = (float)(0.54 - 0.46 * cos(2.0 * PI * n / (kNFFT - 1)));
   std::vector<float2> t1(1024), t2(513);
-  for (int j = 0; j < 1024; ++j) t1[j] = make_float2((float)cos(2.0 * PI * j / 1024), (float)(-sin(2.0 * PI * j / 1024)));
+  // inter-pass twiddles of the 32 x 32 decomposition, [c][lane] = e^{-2 pi i lane c / 1024} (conflict-free per c)
+  for (int c = 0; c < 32; ++c)
+    for (int l = 0; l < 32; ++l) {
+      const int j = l * c;
+      t1[c * 32 + l] = make_float2((float)cos(2.0 * PI * j / 1024), (float)(-sin(2.0 * PI * j / 1024)));
+    }
   for (int k = 0; k <= 512; ++k) t2[k] = make_float2((float)cos(2.0 * PI * k / 2048), (float)(-sin(2.0 * PI * k / 2048)));
   // Slaney filterbank, librosa.filters.mel(sr=32000, n_fft=2048, n_mels=128, fmin=0, fmax=16000,
   // htk=False, norm=None): float64 ramps stored as float32

@@ -72,7 +72,7 @@ struct bsed_context {
   int num_sms;
   // frontend tables (device)
   float* window;        // [2048] symmetric Hamming
-  float2* tw1024;       // [1024] e^{-2 pi i j / 1024}
+  float2* tw1024;       // [32][32] e^{-2 pi i lane c / 1024} at [c][lane]
   float2* tw2048;       // [513]  e^{-2 pi i k / 2048}
   float* mel_w;         // packed non-zero filterbank weights
   int* mel_start;       // [128] first bin of band m

@@ -6,19 +6,20 @@
 // src/data/Transforms.py:74-139,155-197,304-322 (AugmentGaussianNoise, ApplyLog, PadOrTrunc,
 // Normalize).
 //
-// K1/K2 design: one CTA stages the audio of 32 consecutive frames (2048 + 31*255 samples) in
-// shared memory with one coalesced pass (reflect padding resolved at load time), so the 8x frame
-// overlap is served from SMEM, not HBM.  Each warp then owns whole frames: the 2048-point real FFT
-// is a 1024-point complex FFT (even/odd packing) done as 32 x 32 -- two in-register 32-point FFTs
-// per lane with one padded shared-memory transpose in between -- followed by the real-FFT
-// untangling, the magnitude, and the sparse mel projection (2016 non-zero weights, <= 60 bins per
-// band), all without leaving the SM.  Only the 128 mel values per frame go back to HBM.
+// K1/K2 design: persistent CTAs (one per SM, 16 warps = 4 per scheduler; below that the kernel is latency-bound).  A
+// tile is 16 consecutive frames of one clip; its audio (2048 + 15*255 samples, reflect padding resolved per element)
+// is staged in shared memory with cp.async while the previous tile is being transformed (double buffer), so the 8x
+// frame overlap is served from SMEM, not HBM, and the staging latency is hidden.  Each warp owns one frame of the
+// tile: the 2048-point real FFT is a 1024-point complex FFT (even/odd packing) done as 32 x 32 -- two in-register
+// 32-point FFTs per lane with one padded shared-memory transpose in between -- followed by the real-FFT untangling,
+// the magnitude (written back compactly over the spectrum), and the sparse mel projection (2016 non-zero weights,
+// <= 60 bins per band), all without leaving the SM.  Only the 128 mel values per frame go back to HBM.
 #include "launch.h"
 
 namespace bsed {
 
-constexpr int FE_FPC = 32;                                  // frames per CTA
-constexpr int FE_WARPS = 16;                                // 4 warps per scheduler: the kernel is latency-bound below that
+constexpr int FE_FPC = 16;                                  // frames per tile (one per warp)
+constexpr int FE_WARPS = 16;
 constexpr int FE_AUD = ((kNFFT + (FE_FPC - 1) * kHop) + 15) / 16 * 16;  // 5888 staged samples
 constexpr int FE_BUF = 33 * 32;                             // padded transpose buffer (float2)
 constexpr int FE_MELW = 2048;
@@ -84,13 +85,18 @@ struct FrontendTables {
   int mel_nnz;
 };
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src));
+}
+
 __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* __restrict__ audio, int n_samples,
-                                                                   int n_frames, float* __restrict__ mel,
-                                                                   FrontendTables tb) {
+                                                                   int n_frames, int tiles_per_clip, int n_tiles,
+                                                                   float* __restrict__ mel, FrontendTables tb) {
   extern __shared__ __align__(16) unsigned char fe_smem[];
-  float* audio_s = reinterpret_cast<float*>(fe_smem);
-  float* win_s = audio_s + FE_AUD;
-  float2* tw1024_s = reinterpret_cast<float2*>(win_s + kNFFT);
+  float* audio_s = reinterpret_cast<float*>(fe_smem);          // 2 x FE_AUD (double buffer)
+  float* win_s = audio_s + 2 * FE_AUD;
+  float2* tw1024_s = reinterpret_cast<float2*>(win_s + kNFFT);  // [c][lane] = e^{-2 pi i lane c / 1024}
   float2* tw2048_s = tw1024_s + 1024;
   float* melw_s = reinterpret_cast<float*>(tw2048_s + 516);
   int* mstart_s = reinterpret_cast<int*>(melw_s + FE_MELW);
@@ -100,24 +106,29 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 
   const int tid = threadIdx.x;
   const int lane = tid % 32, warp = tid / 32;
-  const int b = blockIdx.y;
-  const int frame0 = blockIdx.x * FE_FPC;
-  const float* y = audio + (size_t)b * n_samples;
-
-  // stage audio (reflect padding: ypad[p] = y[reflect(p - 1024)])
-  const long long p0 = (long long)frame0 * kHop;
   const long long padded = (long long)n_samples + kNFFT;
-  for (int i = tid; i < FE_AUD; i += blockDim.x) {
-    long long p = p0 + i;
-    float v = 0.f;
-    if (p < padded) {
-      long long j = p - kNFFT / 2;
-      if (j < 0) j = -j;
-      if (j >= n_samples) j = 2LL * (n_samples - 1) - j;
-      v = __ldg(y + j);
+
+  // stage the audio of one tile (reflect padding: ypad[p] = y[reflect(p - 1024)])
+  auto stage = [&](int tile, float* dst) {
+    const int b = tile / tiles_per_clip;
+    const long long p0 = (long long)(tile % tiles_per_clip) * FE_FPC * kHop;
+    const float* y = audio + (size_t)b * n_samples;
+    for (int i = tid; i < FE_AUD; i += FE_WARPS * 32) {
+      const long long p = p0 + i;
+      if (p < padded) {
+        long long j = p - kNFFT / 2;
+        if (j < 0) j = -j;
+        if (j >= n_samples) j = 2LL * (n_samples - 1) - j;
+        cp_async4(dst + i, y + j);
+      } else {
+        dst[i] = 0.f;
+      }
     }
-    audio_s[i] = v;
-  }
+  };
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) stage(tile, audio_s);
+  cp_async_commit();
   for (int i = tid; i < kNFFT; i += blockDim.x) win_s[i] = tb.window[i];
   for (int i = tid; i < 1024; i += blockDim.x) tw1024_s[i] = tb.tw1024[i];
   for (int i = tid; i < 513; i += blockDim.x) tw2048_s[i] = tb.tw2048[i];
@@ -127,17 +138,23 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
     mlen_s[i] = tb.mel_len[i];
     moff_s[i] = tb.mel_off[i];
   }
-  __syncthreads();
 
   float2* buf = bufs + warp * FE_BUF;
-  // magnitudes overwrite the spectrum in place: |X[k]| lives in the real slot of buf[k] (float index 2k); the lane that
-  // untangles the pair (k, 1024 - k) is the only one that touches those two slots
+  // magnitudes overwrite the spectrum once every lane holds its share in registers
   float* mag = reinterpret_cast<float*>(buf);
 
-  for (int fi = warp; fi < FE_FPC; fi += FE_WARPS) {
-    const int t = frame0 + fi;
-    if (t >= n_frames) break;
-    const float* fr = audio_s + fi * kHop;
+  int cur = 0;
+  for (; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();   // this tile's audio has landed; every warp is done with the other buffer
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) stage(next, audio_s + (cur ^ 1) * FE_AUD);
+    cp_async_commit();
+
+    const int b = tile / tiles_per_clip;
+    const int t = (tile % tiles_per_clip) * FE_FPC + warp;
+    if (t >= n_frames) continue;
+    const float* fr = audio_s + cur * FE_AUD + warp * kHop;
     float2 v[32];
     // pass 1: lane = b0; z[32 a + b0] = (x[64a + 2b0] w, x[64a + 2b0 + 1] w)
 #pragma unroll
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       float2 yv = v[bitrev5(c)];
-      if (c > 0) yv = cmul(yv, tw1024_s[lane * c]);
+      if (c > 0) yv = cmul(yv, tw1024_s[c * 32 + lane]);
       buf[c * 33 + lane] = yv;
     }
     __syncwarp();
@@ -162,16 +179,17 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 #pragma unroll
     for (int d = 0; d < 32; ++d) buf[lane + 32 * d] = v[bitrev5(d)];
     __syncwarp();
-    // real-FFT untangling + magnitude
-#pragma unroll 4
+    // real-FFT untangling + magnitude: lane holds |X[k]|, |X[1024-k]| for k = lane + 32 jj
+    float mlo[16], mhi[16], m512 = 0.f;
+#pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
       int k = lane + 32 * jj;
       if (k == 0) {
         float2 z0 = buf[0];
         float2 zh = buf[512];
-        mag[0] = fabsf(z0.x + z0.y);
-        mag[2 * 1024] = fabsf(z0.x - z0.y);
-        mag[2 * 512] = sqrtf(zh.x * zh.x + zh.y * zh.y);
+        mlo[jj] = fabsf(z0.x + z0.y);
+        mhi[jj] = fabsf(z0.x - z0.y);
+        m512 = sqrtf(zh.x * zh.x + zh.y * zh.y);
       } else {
         float2 zk = buf[k], zm = buf[1024 - k];
         float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
@@ -179,10 +197,18 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
         float2 P = cmul(tw2048_s[k], O);
         float xr = E.x + P.y, xi = E.y - P.x;
         float yr = E.x - P.y, yi = -E.y - P.x;
-        mag[2 * k] = sqrtf(xr * xr + xi * xi);
-        mag[2 * (1024 - k)] = sqrtf(yr * yr + yi * yi);
+        mlo[jj] = sqrtf(xr * xr + xi * xi);
+        mhi[jj] = sqrtf(yr * yr + yi * yi);
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      int k = lane + 32 * jj;
+      mag[k] = mlo[jj];
+      mag[1024 - k] = mhi[jj];
+    }
+    if (lane == 0) mag[512] = m512;
     __syncwarp();
     // sparse mel projection: lane -> bands lane, lane+32, lane+64, lane+96
     float* out = mel + ((size_t)b * n_frames + t) * kNMels;
@@ -191,14 +217,15 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
       int m = lane + 32 * r;
       int s = mstart_s[m], len = mlen_s[m], off = moff_s[m];
       float acc = 0.f;
-      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[2 * (s + j)], acc);
+      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[s + j], acc);
       out[m] = acc;
     }
     __syncwarp();
   }
+  cp_async_wait<0>();
 }
 
-constexpr size_t FE_SMEM_BYTES = sizeof(float) * (FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516) +
+constexpr size_t FE_SMEM_BYTES = sizeof(float) * (2 * FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516) +
                                  sizeof(float) * FE_MELW + sizeof(int) * 3 * kNMels +
                                  sizeof(float2) * FE_WARPS * FE_BUF;
 
@@ -213,10 +240,13 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
   }
   int n_frames = 1 + n_samples / kHop;
   FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_w, h->mel_start, h->mel_len, h->mel_off, h->mel_nnz};
-  dim3 grid(ceil_div(n_frames, FE_FPC), B);
+  const int tiles_per_clip = ceil_div(n_frames, FE_FPC);
+  const long long n_tiles = (long long)tiles_per_clip * B;
+  BSED_REQUIRE(n_tiles < (1ll << 31), "melspec: too many frames");
+  const int grid = (int)(n_tiles < h->num_sms ? n_tiles : h->num_sms);
   // algorithmic bytes: audio in + mel out; flops: rFFT-2048 + magnitude + sparse mel
   ProfScope prof(PROF_MELSPEC, (double)B * n_frames * 70000.0, 4.0 * B * ((double)n_samples + (double)n_frames * kNMels), st);
-  melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, mel, tb);
+  melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, tiles_per_clip, (int)n_tiles, mel, tb);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
