@@ -31,6 +31,9 @@ N_SYN = N_REAL = 12
 CLIP_BYTES_FRONTEND = 320000 * 4 + 1255 * 128 * 4
 FLOP_PER_CLIP_FWD = 3.684e9
 STEP_FLOP = (24 * 3 + 12) * FLOP_PER_CLIP_FWD             # 309.5 GFLOP
+# CRNN_fpn adds per clip: the shared stage twice (conv 3x3 + GLU on 313 + 156 frames, 77 MMAC), rnn_2 / rnn_4
+# ((156 + 78) / 313 of the GRU's 154 MMAC) and the two 512 -> 256 merges (61 MMAC): + 0.507 GFLOP forward
+FLOP_PER_CLIP_FWD_FPN = FLOP_PER_CLIP_FWD + 0.507e9
 
 
 def load_peaks():
@@ -71,7 +74,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_mean_teacher(n_syn, n_real, steps, warmup, threads=None):
+def cpu_mean_teacher(n_syn, n_real, steps, warmup, threads=None, fpn=False):
     """The oracle port of the reference step (torch.nn Conv2d / BatchNorm2d / GRU on the host cores)."""
     import torch
     from oracle import crnn as ocrnn
@@ -79,9 +82,10 @@ def cpu_mean_teacher(n_syn, n_real, steps, warmup, threads=None):
     from bsed_b200.utilities import synth
     # all host cores (torchrun exports OMP_NUM_THREADS=1; the baseline runs on rank 0 alone)
     torch.set_num_threads(threads or os.cpu_count() or 1)
-    oc = ocrnn.OracleCRNN(**ocrnn.CRNN_KWARGS)
+    cls = ocrnn.OracleCRNNfpn if fpn else ocrnn.OracleCRNN
+    oc = cls(**ocrnn.CRNN_KWARGS)
     op = ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
-    tc = ocrnn.OracleCRNN(**ocrnn.CRNN_KWARGS)
+    tc = cls(**ocrnn.CRNN_KWARGS)
     tp = ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
     ocrnn.reference_style_init(oc, op, 1)
     ocrnn.reference_style_init(tc, tp, 2)
@@ -112,13 +116,15 @@ def run_reference(args):
     ns = nr = 2
     steps = max(1, min(args.steps, 20))
     warmup = max(1, min(args.warmup, 2))
-    cps, sec, threads = cpu_mean_teacher(ns, nr, steps, warmup)
+    fpn = args.model == "crnn_fpn"
+    cps, sec, threads = cpu_mean_teacher(ns, nr, steps, warmup, fpn=fpn)
     line = {
         "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "mean-teacher CRNN training step (main.py shapes), CPU sample of 2 synthetic + 2 real clips "
-                               "per step instead of 12 + 12 (clips/s is per clip)", "parallelism": "cpu threads"},
+                               "per step instead of 12 + 12 (clips/s is per clip)", "model": args.model,
+                   "parallelism": "cpu threads"},
         "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} steps x (2 syn + 2 real student clips, 2 teacher clips), oracle port of "
                                    "src/main.py:train_mt with the reference's torch.nn layers"},
@@ -144,17 +150,20 @@ def run_b200(args):
         ge.build()
     from bsed_b200 import _lib, engine
     from bsed_b200.main import MeanTeacherTrainer
-    from bsed_b200.models import CRNN, Predictor
+    from bsed_b200.models import CRNN, CRNN_fpn, Predictor
     from bsed_b200.utilities import synth
     from bsed_b200.utilities.utils import weights_init
     lib = _lib.load()
     peaks = load_peaks()
+    fpn = args.model == "crnn_fpn"
+    model_cls = CRNN_fpn if fpn else CRNN
+    step_flop = (24 * 3 + 12) * (FLOP_PER_CLIP_FWD_FPN if fpn else FLOP_PER_CLIP_FWD)
     dev = torch.device("cuda", local)
 
     torch.manual_seed(2023 + rank)
 
     def make():
-        m, p = CRNN(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+        m, p = model_cls(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
         weights_init(m)
         weights_init(p)
         return m.to(dev).train(), p.to(dev).train()
@@ -202,6 +211,14 @@ def run_b200(args):
         sampler.start()
 
     # ---- device-resident run (value) with the dominant kernel class timed by CUDA events
+    # host time to enqueue one step (no synchronisation inside): must stay below the device time or the GPU starves
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(3):
+        trainer.step(x, x_ema, xs, ts, i, rampup_len)
+    host_enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
+
     launches0 = lib.bsed_launch_count()
     lib.bsed_profile_begin(1)
     ms = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup)
@@ -259,6 +276,14 @@ def run_b200(args):
     _lib.check(lib.bsed_profile_end(C.byref(fm), None, None, C.byref(fn_)), "profile_end")
     fe_steps = max(3, args.steps // 2)
     fe_cps = 256 * world * fe_steps / (ms_fe * 1e-3)
+    # the dB transform alone (the HBM-bound elementwise half of the frontend): algorithmic bytes = mel in + log-mel out
+    fe_mel = engine.melspec(fe_clips)
+    fe_out = torch.empty(256, 1255, 128, device=dev)
+    lib.bsed_profile_begin(7)
+    timed(lambda i: engine.amp_to_db(fe_mel, 1255, out=fe_out), fe_steps, 3)
+    dm, db_, dn = C.c_double(), C.c_double(), C.c_int()
+    _lib.check(lib.bsed_profile_end(C.byref(dm), None, C.byref(db_), C.byref(dn)), "profile_end")
+    db_gbps = db_.value / (dm.value * 1e-3) / 1e9 if dm.value > 0 else None
 
     if rank == 0:
         sampler.stop_flag = True
@@ -267,10 +292,10 @@ def run_b200(args):
         conv_tflops = pf.value / (pm.value * 1e-3) / 1e12 if pm.value > 0 else None
         # the CPU port on this box's host cores, bounded sample
         if world == 1:
-            cps_cpu, sec_cpu, threads = cpu_mean_teacher(2, 2, 2, 1)
+            cps_cpu, sec_cpu, threads = cpu_mean_teacher(2, 2, 12, 1, fpn=fpn)
             cpu_baseline = {"value": cps_cpu, "unit": "clips/s", "cores": threads, "kind": "port",
-                            "sample": "2 steps of 2 synthetic + 2 real clips (oracle port of src/main.py:train_mt, "
-                                      "torch.nn on host cores)"}
+                            "sample": "12 steps of 2 synthetic + 2 real clips (oracle port of src/main.py:train_mt, "
+                                      "torch.nn on host cores, %.1f s of CPU work)" % (sec_cpu * 12)}
         else:
             cpu_baseline = None     # reported at N = 1 only
         line = {
@@ -283,9 +308,12 @@ def run_b200(args):
                                    "state-dict EMA; log-mel features 1255x128 resident in HBM",
                        "precision": trainer.plan.precision + (" (tcgen05 kind::tf32 contractions, fp32 accumulate; everything "
                                                               "else fp32)" if trainer.plan.precision == "tf32" else ""),
-                       "clips_per_step_per_gpu": 24, "parallelism": f"dp{world} (NCCL sum all-reduce of the 4.47 MB flat gradient)",
+                       "model": args.model + (" (src/models/CRNN.py:243-337)" if fpn else " (src/models/CRNN.py:178-240)"),
+                       "clips_per_step_per_gpu": 24,
+                       "parallelism": f"dp{world} (NCCL sum all-reduce of the %.2f MB flat gradient)" % (trainer.grads.numel() * 4 / 1e6),
+                       "host_enqueue_ms_per_step": host_enqueue_ms,
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",
-                       "step_gflop_algorithmic": STEP_FLOP / 1e9},
+                       "step_gflop_algorithmic": step_flop / 1e9},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_timed),
@@ -303,10 +331,16 @@ def run_b200(args):
                          "peak_source": peaks["source"] + " bf16 sustained (tf32 nominal dense peak is half of bf16)",
                          "launches": pn.value,
                          "share_of_step": pm.value / ms if ms else None,
-                         "step_tflops": STEP_FLOP * args.steps / (ms * 1e-3) / 1e12},
+                         "step_tflops": step_flop * args.steps / (ms * 1e-3) / 1e12},
             "frontend": {"metric": "log-mel frontend", "clips_per_s": fe_cps, "algorithmic_GBps": fe_cps * CLIP_BYTES_FRONTEND / 1e9,
                          "hbm_frac": fe_cps * CLIP_BYTES_FRONTEND / 1e9 / peaks["hbm"] / world,
-                         "stft_mel_kernel_ms_per_256_clips": fm.value / max(1, fn_.value)},
+                         "stft_mel_kernel_ms_per_256_clips": fm.value / max(1, fn_.value),
+                         "stft_mel_fp32_tflops": 256 * 1255 * 70000.0 / (fm.value / max(1, fn_.value) * 1e-3) / 1e12,
+                         "db_transform": {"bound": "hbm", "achieved_GBps": db_gbps, "peak_GBps": peaks["hbm"],
+                                          "frac": db_gbps / peaks["hbm"] if db_gbps else None,
+                                          "ms_per_256_clips": dm.value / max(1, dn.value),
+                                          "note": "algorithmic bytes (amplitude-mel read once + log-mel written once); the per-clip "
+                                                  "80 dB clamp needs the clip maximum first, so the kernel pair reads the mel twice"}},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }
@@ -376,6 +410,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="crnn", choices=["crnn", "crnn_fpn"],
+                    help="crnn = src/models/CRNN.py:CRNN (default, the headline); crnn_fpn = CRNN_fpn (SURVEY 8f-1)")
     ap.add_argument("--workload", default="train", choices=["train", "pseudo_label"],
                     help="train = the headline mean-teacher step (default); pseudo_label = configs[4] inference pipeline")
     args = ap.parse_args()

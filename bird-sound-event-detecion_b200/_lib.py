@@ -26,7 +26,7 @@ SYMBOLS = [
     "bsed_conv3x3_tc", "bsed_gemm_nt_tc", "bsed_conv3x3_wgrad", "bsed_conv3x3_wgrad_workspace_bytes",
     "bsed_plan_set_precision", "bsed_plan_get_precision",
     "bsed_disc_param_count", "bsed_disc_bn_buffer_count", "bsed_disc_workspace_bytes", "bsed_disc_forward",
-    "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision",
+    "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision", "bsed_loss_terms", "bsed_roll_clips",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -50,6 +50,14 @@ class OptCfg(C.Structure):
                 ("grad_scale", C.c_float), ("ema_alpha", C.c_float), ("step", C.c_int64),
                 ("ema_step", C.c_int64)]
 
+
+class LossTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("pred_first", C.c_int), ("n_clips", C.c_int), ("ref", C.c_void_p),
+                ("roll", C.c_void_p), ("ref_is_strong", C.c_int), ("weight", C.c_float), ("grad_weight", C.c_float),
+                ("slot", C.c_int)]
+
+
+LOSS_BCE_STRONG, LOSS_BCE_WEAK, LOSS_MSE_STRONG, LOSS_MSE_WEAK = 0, 1, 2, 3
 
 _lib = None
 _lock = threading.Lock()
@@ -104,6 +112,8 @@ def load():
         proto("bsed_predictor_backward", i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, sz, vp)
         proto("bsed_plan_debug_tensor", i32, vp, vp, C.c_char_p, P(vp), P(i64))
         proto("bsed_mt_loss", i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, f32, vp, vp, vp, vp)
+        proto("bsed_loss_terms", i32, vp, vp, vp, i32, i32, i32, P(LossTerm), i32, vp, i32, vp, vp, vp)
+        proto("bsed_roll_clips", i32, vp, vp, vp, vp, vp, i32, i32, i32, vp)
         proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
         proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)

@@ -256,6 +256,22 @@ extern "C" int bsed_mt_loss(bsed_handle h, const float* strong, const float* wea
                  losses, d_strong, d_weak, as_stream(stream));
 }
 
+extern "C" int bsed_loss_terms(bsed_handle h, const float* strong, const float* weak, int B, int T, int C,
+                               const bsed_loss_term* terms, int n_terms, float* losses, int n_slots, float* d_strong,
+                               float* d_weak, void* stream) {
+  BSED_REQUIRE(h && strong && weak && terms && losses && d_strong && d_weak, "bsed_loss_terms: null argument");
+  BSED_REQUIRE(B >= 1 && T >= 1 && n_terms >= 1 && n_slots >= 1, "bsed_loss_terms: B=%d T=%d terms=%d slots=%d", B, T, n_terms,
+               n_slots);
+  return loss_terms(strong, weak, B, T, C, terms, n_terms, losses, n_slots, d_strong, d_weak, as_stream(stream));
+}
+
+extern "C" int bsed_roll_clips(bsed_handle h, const float* x, const int32_t* shift_t, const int32_t* shift_f, float* out,
+                               int B, int T, int F, void* stream) {
+  BSED_REQUIRE(h && x && out && x != out, "bsed_roll_clips: null or aliased argument");
+  BSED_REQUIRE(B >= 1 && T >= 1 && F >= 1, "bsed_roll_clips: B=%d T=%d F=%d", B, T, F);
+  return roll_clips(x, shift_t, shift_f, out, B, T, F, as_stream(stream));
+}
+
 extern "C" int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m, float* v, float* ema,
                                  int64_t n, const bsed_opt_cfg* cfg, void* stream) {
   BSED_REQUIRE(h && params && grads && m && cfg, "bsed_opt_ema_step: null argument");

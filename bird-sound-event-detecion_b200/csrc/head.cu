@@ -379,6 +379,117 @@ int mt_loss(const float* strong, const float* weak, int B, int T, int C, int syn
 }
 
 // ---------------------------------------------------------------------------------------------
+// generic loss terms (shift-consistency training, src/main_baseline.py:372-529): one launch per term, so the
+// gradient accumulation order is fixed.  grid = clips of the term.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_term_kernel(const float* __restrict__ strong, const float* __restrict__ weak,
+                                                        int T, int C, bsed_loss_term tm, float* losses,
+                                                        float* __restrict__ d_strong, float* __restrict__ d_weak) {
+  const int b = blockIdx.x;
+  const int pb = tm.pred_first + b;
+  const int TC = T * C;
+  const bool is_bce = tm.kind == BSED_LOSS_BCE_STRONG || tm.kind == BSED_LOSS_BCE_WEAK;
+  float acc = 0.f;
+  __shared__ float tmax[kMaxC];
+  __shared__ float red[8];
+  if (tm.kind == BSED_LOSS_BCE_STRONG || tm.kind == BSED_LOSS_MSE_STRONG) {
+    const int roll = tm.roll ? tm.roll[b] : 0;
+    const float* ref = tm.ref + (size_t)b * TC;
+    const float gscale = tm.grad_weight / ((float)tm.n_clips * (float)TC);
+    for (int i = threadIdx.x; i < TC; i += blockDim.x) {
+      const int t = i / C, c = i - t * C;
+      int ts = (t - roll) % T;                 // torch.roll(ref, roll, 0)[t] = ref[(t - roll) mod T]
+      if (ts < 0) ts += T;
+      const float x = strong[(size_t)pb * TC + i], y = ref[(size_t)ts * C + c];
+      float g;
+      if (is_bce) {
+        acc += bce_term(x, y);
+        g = bce_grad(x, y);
+      } else {
+        const float d = x - y;
+        acc += d * d;
+        g = 2.f * d;
+      }
+      if (tm.grad_weight != 0.f) d_strong[(size_t)pb * TC + i] += g * gscale;
+    }
+  } else {
+    if (tm.ref_is_strong) {                    // weak target = max over time of a strong target (syn_target.max(-2)[0])
+      if (threadIdx.x < kMaxC) tmax[threadIdx.x] = 0.f;
+      __syncthreads();
+      const float* ref = tm.ref + (size_t)b * TC;
+      for (int i = threadIdx.x; i < TC; i += blockDim.x) {
+        const float y = ref[i];
+        if (y > 0.f) atomicMax(reinterpret_cast<int*>(&tmax[i % C]), __float_as_int(y));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < C) {
+      const float x = weak[(size_t)pb * C + threadIdx.x];
+      const float y = tm.ref_is_strong ? tmax[threadIdx.x] : tm.ref[(size_t)b * C + threadIdx.x];
+      const float gscale = tm.grad_weight / ((float)tm.n_clips * (float)C);
+      float g;
+      if (is_bce) {
+        acc = bce_term(x, y);
+        g = bce_grad(x, y);
+      } else {
+        const float d = x - y;
+        acc = d * d;
+        g = 2.f * d;
+      }
+      if (tm.grad_weight != 0.f) d_weak[(size_t)pb * C + threadIdx.x] += g * gscale;
+    }
+  }
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  const float s = warp_sum(acc);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float n = (float)tm.n_clips * (float)((tm.kind == BSED_LOSS_BCE_STRONG || tm.kind == BSED_LOSS_MSE_STRONG) ? TC : C);
+    atomicAdd(&losses[tm.slot], tm.weight * tot / n);
+  }
+}
+
+int loss_terms(const float* strong, const float* weak, int B, int T, int C, const bsed_loss_term* terms, int n_terms,
+               float* losses, int n_slots, float* d_strong, float* d_weak, cudaStream_t st) {
+  BSED_REQUIRE(C <= kMaxC, "loss_terms: C=%d", C);
+  BSED_CHECK_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * n_slots, st));
+  BSED_CHECK_CUDA(cudaMemsetAsync(d_strong, 0, sizeof(float) * (size_t)B * T * C, st));
+  BSED_CHECK_CUDA(cudaMemsetAsync(d_weak, 0, sizeof(float) * (size_t)B * C, st));
+  for (int i = 0; i < n_terms; ++i) {
+    const bsed_loss_term& tm = terms[i];
+    BSED_REQUIRE(tm.kind >= 0 && tm.kind <= 3 && tm.ref && tm.n_clips >= 1 && tm.pred_first >= 0 &&
+                     tm.pred_first + tm.n_clips <= B && tm.slot >= 0 && tm.slot < n_slots,
+                 "loss_terms: term %d is malformed", i);
+    loss_term_kernel<<<tm.n_clips, 256, 0, st>>>(strong, weak, T, C, tm, losses, d_strong, d_weak);
+    BSED_CHECK_LAUNCH();
+  }
+  return BSED_OK;
+}
+
+// out[b][t][f] = x[b][(t - shift_t[b]) mod T][(f - shift_f[b]) mod F]   (torch.roll along time, then frequency)
+__global__ void __launch_bounds__(256) roll_clips_kernel(const float* __restrict__ x, const int* __restrict__ shift_t,
+                                                         const int* __restrict__ shift_f, float* __restrict__ out, int T,
+                                                         int F) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * F) return;
+  const int t = (int)(i / F), f = (int)(i - (long long)t * F);
+  int ts = (t - (shift_t ? shift_t[b] : 0)) % T, fs = (f - (shift_f ? shift_f[b] : 0)) % F;
+  if (ts < 0) ts += T;
+  if (fs < 0) fs += F;
+  out[(size_t)b * T * F + i] = x[((size_t)b * T + ts) * F + fs];
+}
+
+int roll_clips(const float* x, const int* shift_t, const int* shift_f, float* out, int B, int T, int F, cudaStream_t st) {
+  dim3 grid(ceil_div((long long)T * F, 256), B);
+  roll_clips_kernel<<<grid, 256, 0, st>>>(x, shift_t, shift_f, out, T, F);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // optimiser + EMA over flat buffers
 // ---------------------------------------------------------------------------------------------
 struct OptScalars {

@@ -118,6 +118,9 @@ int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long lo
 int mt_loss(const float* strong, const float* weak, int B, int T, int C, int syn_first, int syn_n,
             const float* syn_target, int real_first, int real_n, const float* strong_ema, const float* weak_ema,
             float cons_w, float* losses, float* d_strong, float* d_weak, cudaStream_t st);
+int loss_terms(const float* strong, const float* weak, int B, int T, int C, const bsed_loss_term* terms, int n_terms,
+               float* losses, int n_slots, float* d_strong, float* d_weak, cudaStream_t st);
+int roll_clips(const float* x, const int* shift_t, const int* shift_f, float* out, int B, int T, int F, cudaStream_t st);
 int opt_ema_step(float* params, const float* grads, float* m, float* v, float* ema, long long n,
                  const bsed_opt_cfg* cfg, cudaStream_t st);
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,

@@ -129,13 +129,17 @@ class Plan:
             self._pred_ws[n] = (torch.empty(nb, dtype=torch.uint8, device=self.device), nb)
         return self._pred_ws[n]
 
-    def predictor_forward(self, pred_params, enc, inference=False):
+    def predictor_forward(self, pred_params, enc, inference=False, out=None):
+        """out: optional (logits, strong, weak) buffers of n clips (views into larger tensors are fine)."""
         n = enc.shape[0]
         ws, wsb = self._pws(n)
         enc = enc.contiguous()
-        logits = torch.empty(n, self.t_out, self.ldl, dtype=torch.float32, device=self.device)
-        strong = torch.empty(n, self.t_out, self.n_class, dtype=torch.float32, device=self.device)
-        weak = torch.empty(n, self.n_class, dtype=torch.float32, device=self.device)
+        if out is not None:
+            logits, strong, weak = out
+        else:
+            logits = torch.empty(n, self.t_out, self.ldl, dtype=torch.float32, device=self.device)
+            strong = torch.empty(n, self.t_out, self.n_class, dtype=torch.float32, device=self.device)
+            weak = torch.empty(n, self.n_class, dtype=torch.float32, device=self.device)
         check(self.lib.bsed_predictor_forward(self.p, ptr(pred_params), ptr(enc), n, int(bool(inference)), ptr(logits),
                                               ptr(strong), ptr(weak), ptr(ws), wsb, stream_ptr()),
               "bsed_predictor_forward")
@@ -177,6 +181,50 @@ def mt_loss(strong, weak, syn_first, syn_n, syn_target, real_first, real_n, stro
                            ptr(strong_ema), ptr(weak_ema), float(cons_w), ptr(losses), ptr(d_strong), ptr(d_weak),
                            stream_ptr()), "bsed_mt_loss")
     return losses, d_strong, d_weak
+
+
+def loss_terms(strong, weak, terms, n_slots):
+    """Generic BCE / MSE terms (include/bsed.h: bsed_loss_terms).  terms: list of dicts(kind, pred_first, n, ref, roll=None,
+    ref_is_strong=False, weight=1.0, grad_weight=None (= weight), slot).  Returns (losses [n_slots], d_strong, d_weak)."""
+    lib = _lib.load()
+    h = _lib.handle(strong.device.index)
+    B, T, Cn = strong.shape
+    arr = (_lib.LossTerm * len(terms))()
+    keep = []
+    for i, t in enumerate(terms):
+        ref = t["ref"]
+        assert ref.is_contiguous() and ref.dtype == torch.float32 and ref.is_cuda
+        arr[i].kind, arr[i].pred_first, arr[i].n_clips = int(t["kind"]), int(t["pred_first"]), int(t["n"])
+        arr[i].ref = ref.data_ptr()
+        roll = t.get("roll")
+        if roll is not None:
+            assert roll.dtype == torch.int32 and roll.is_cuda and roll.numel() >= t["n"]
+        arr[i].roll = roll.data_ptr() if roll is not None else None
+        arr[i].ref_is_strong = int(bool(t.get("ref_is_strong", False)))
+        arr[i].weight = float(t.get("weight", 1.0))
+        gw = t.get("grad_weight")
+        arr[i].grad_weight = float(arr[i].weight if gw is None else gw)
+        arr[i].slot = int(t["slot"])
+        keep.append((ref, roll))
+    losses = torch.empty(n_slots, dtype=torch.float32, device=strong.device)
+    d_strong = torch.empty_like(strong)
+    d_weak = torch.empty_like(weak)
+    check(lib.bsed_loss_terms(h, ptr(strong), ptr(weak), B, T, Cn, arr, len(terms), ptr(losses), n_slots, ptr(d_strong),
+                              ptr(d_weak), stream_ptr()), "bsed_loss_terms")
+    return losses, d_strong, d_weak
+
+
+def roll_clips(x, shift_t=None, shift_f=None, out=None):
+    """out[b] = roll(roll(x[b], shift_t[b], time), shift_f[b], frequency); x (B, T, F) or (B, 1, T, F) fp32 cuda,
+    shifts int32 device tensors (or None)."""
+    lib = _lib.load()
+    h = _lib.handle(x.device.index)
+    x = x.contiguous()
+    B, T, F = x.shape[0], x.shape[-2], x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.bsed_roll_clips(h, ptr(x), ptr(shift_t), ptr(shift_f), ptr(out), B, T, F, stream_ptr()), "bsed_roll_clips")
+    return out
 
 
 def opt_ema_step(params, grads, m, v, ema, step, ema_step=None, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,

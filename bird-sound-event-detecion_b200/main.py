@@ -16,9 +16,13 @@ Two execution paths, both entirely in libbsed.so kernels:
 With `discriminator` (a DA.cdan_frame.ConditionalDomainAdversarialLoss around a Clip_Discriminator), `optimizer_d` and
 `optimizer_crnn`, every iteration first runs the adversarial update of src/main_scmt_ada_weak_seperate.py:314-335
 (student forward on both domains -> gradient reversal -> discriminator -> BCE -> backward -> both optimisers step).
-Out of scope here: the ISP/ICT shift-consistency branches.
+With ISP=True (the shift-consistency / SCT branch of src/main_baseline.py:229-277,372-529) `ShiftConsistencyTrainer.step`
+runs the nine model calls of one iteration (student: synthetic, real, time-shifted and frequency-shifted real and
+synthetic; teacher: real, time-shifted real, frequency-shifted real), the twelve loss terms and one optimiser + EMA
+update, all in libbsed.so kernels.
 """
 import logging
+import random
 import time
 
 import torch
@@ -158,6 +162,153 @@ class MeanTeacherTrainer:
         return losses
 
 
+ISP_SLOTS = ("strong_class", "weak_class", "cons_strong", "cons_weak", "weak_freq_shift_class", "strong_shift_class",
+             "strong_freq_shift_class", "cons_shift", "cons_strong_shift", "cons_strong_freq_shift", "cons_weak_shift",
+             "cons_weak_freq_shift")
+
+
+class ShiftConsistencyTrainer:
+    """One fused iteration of train_mt(ISP=True) with a teacher (src/main_baseline.py:229-277, 337-584).
+
+    Model calls (each its own BatchNorm batch statistics, in the reference's order per network):
+      plan A  [synthetic | real]                         student   + [real]                        teacher
+      plan B  [real>>t | real>>f | synthetic>>t | synthetic>>f]     student
+      plan C  [real>>t | real>>f]                                   teacher
+    (>>t: per-clip roll along time by shift_list[k]; >>f: along frequency by freq_shift_list[k]).  Student predictions
+    live in one (6n, T, C) tensor, teacher predictions in one (3n, T, C) tensor, and the loss is the term list of
+    bsed_loss_terms; the rolled targets / rolled detached predictions are references with a per-clip roll."""
+
+    def __init__(self, model, predictor, ema_model, ema_predictor, lr=cfg.default_learning_rate, betas=(0.9, 0.999),
+                 eps=1e-8, weight_decay=0.0, n=cfg.batch_size, dropout_seed=2023, process_group=None, precision=None,
+                 pooling_time_ratio=cfg.pooling_time_ratio):
+        assert isinstance(model, CRNN) and isinstance(predictor, Predictor)
+        assert ema_model is not None and ema_predictor is not None, "the ISP step needs the teacher"
+        self.model, self.predictor, self.ema_model, self.ema_predictor = model, predictor, ema_model, ema_predictor
+        dev = model._flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("move the models to the GPU before building the trainer")
+        self.device, self.n = dev, n
+        self.params, sizes = _rehome([model, predictor], dev)
+        self.n_crnn, self.n_pred = sizes
+        self.ema_params, _ = _rehome([ema_model, ema_predictor], dev)
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.dropout_seed, self.opt_step, self.pg = dropout_seed, 0, process_group
+        self.ptr = int(pooling_time_ratio)
+        mk = lambda B: engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev,
+                                   precision=precision or model.precision)
+        self.planA, self.planB, self.planC = mk(3 * n), mk(4 * n), mk(2 * n)
+        T, F, To = cfg.max_frames, cfg.n_mels, self.planA.t_out
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.xA = torch.empty(3 * n, 1, T, F, **f32)
+        self.xB = torch.empty(4 * n, 1, T, F, **f32)
+        self.xC = torch.empty(2 * n, 1, T, F, **f32)
+        # encoder outputs / gradients: [A: syn, real, teacher | B: 4n | C: 2n]
+        self.enc = torch.empty(9 * n, To, 256, **f32)
+        self.d_enc = torch.zeros(9 * n, To, 256, **f32)
+        C, ldl = self.planA.n_class, self.planA.ldl
+        self.s_logits, self.s_strong, self.s_weak = (torch.empty(6 * n, To, ldl, **f32), torch.empty(6 * n, To, C, **f32),
+                                                     torch.empty(6 * n, C, **f32))
+        self.t_logits, self.t_strong, self.t_weak = (torch.empty(3 * n, To, ldl, **f32), torch.empty(3 * n, To, C, **f32),
+                                                     torch.empty(3 * n, C, **f32))
+        self.last = {}
+
+    def step(self, x, x_ema, target_weak, xs, ts, shift_list, freq_shift_list, global_step, rampup_value,
+             max_consistency_cost=cfg.max_consistency_cost):
+        """x / x_ema (n,1,T,F): real batch, student / teacher inputs; target_weak (n,C): its weak labels; xs / ts: synthetic
+        batch and strong targets; shift_list (frames, multiples of pooling_time_ratio) / freq_shift_list (bins): per-clip
+        shifts.  Returns the 12 loss terms (ISP_SLOTS order, device tensor, no host sync)."""
+        n, dev = self.n, self.device
+        T, F = cfg.max_frames, cfg.n_mels
+        st = torch.tensor([int(v) for v in shift_list], dtype=torch.int32, device=dev)
+        sf = torch.tensor([int(v) for v in freq_shift_list], dtype=torch.int32, device=dev)
+        pool_shift = torch.tensor([int(v / self.ptr) for v in shift_list], dtype=torch.int32, device=dev)
+        xr = x.reshape(n, 1, T, F).float().contiguous()
+        xe = x_ema.reshape(n, 1, T, F).float().contiguous()
+        xsy = xs.reshape(n, 1, T, F).float().contiguous()
+        self.xA[:n].copy_(xsy)
+        self.xA[n:2 * n].copy_(xr)
+        self.xA[2 * n:].copy_(xe)
+        engine.roll_clips(xr, st, None, out=self.xB[:n])
+        engine.roll_clips(xr, None, sf, out=self.xB[n:2 * n])
+        engine.roll_clips(xsy, st, None, out=self.xB[2 * n:3 * n])
+        engine.roll_clips(xsy, None, sf, out=self.xB[3 * n:])
+        engine.roll_clips(xe, st, None, out=self.xC[:n])
+        engine.roll_clips(xe, None, sf, out=self.xC[n:])
+        sp, sbn, snbt = self.model.flat_tensors()
+        tp, tbn, tnbt = self.ema_model.flat_tensors()
+        S = lambda k: dict(params=sp, bn=sbn, nbt=snbt, n=k)
+        Tg = lambda k: dict(params=tp, bn=tbn, nbt=tnbt, n=k)
+        seed = self.dropout_seed
+        encA, encB, encC = self.enc[:3 * n], self.enc[3 * n:7 * n], self.enc[7 * n:]
+        self.planA.forward([S(n), S(n), Tg(n)], self.xA, train=True, save=True, seed=seed, step=3 * global_step, enc=encA)
+        self.planB.forward([S(n), S(n), S(n), S(n)], self.xB, train=True, save=True, seed=seed, step=3 * global_step + 1,
+                           enc=encB)
+        self.planC.forward([Tg(n), Tg(n)], self.xC, train=True, save=False, seed=seed, step=3 * global_step + 2, enc=encC)
+        pp, tpp = self.params[self.n_crnn:], self.ema_params[self.n_crnn:]
+        sl = lambda t, a, b: t[a:b]
+        outS = lambda a, b: (sl(self.s_logits, a, b), sl(self.s_strong, a, b), sl(self.s_weak, a, b))
+        outT = lambda a, b: (sl(self.t_logits, a, b), sl(self.t_strong, a, b), sl(self.t_weak, a, b))
+        self.planA.predictor_forward(pp, encA[:2 * n], out=outS(0, 2 * n))
+        self.planA.predictor_forward(pp, encB, out=outS(2 * n, 6 * n))
+        self.planA.predictor_forward(tpp, encA[2 * n:], out=outT(0, n))
+        self.planA.predictor_forward(tpp, encC, out=outT(n, 3 * n))
+
+        # student clips: syn [0,n) real [n,2n) real>>t [2n,3n) real>>f [3n,4n) syn>>t [4n,5n) syn>>f [5n,6n)
+        # teacher clips: real [0,n) real>>t [n,2n) real>>f [2n,3n)
+        from ._lib import LOSS_BCE_STRONG as BS, LOSS_BCE_WEAK as BW, LOSS_MSE_STRONG as MS, LOSS_MSE_WEAK as MW
+        cc = float(max_consistency_cost * rampup_value)
+        widx = n // 2
+        ts = ts.float().contiguous()
+        tw = target_weak.float().contiguous()
+        Ss, Sw, Ts, Tw = self.s_strong, self.s_weak, self.t_strong, self.t_weak
+        terms = [
+            dict(kind=BS, pred_first=0, n=n, ref=ts, slot=0),                                            # :475
+            dict(kind=BW, pred_first=0, n=n, ref=ts, ref_is_strong=True, slot=1),                        # :433-434
+            dict(kind=BW, pred_first=n, n=n, ref=tw, slot=1),                                            # :437
+            dict(kind=MS, pred_first=n, n=n, ref=Ts[:n], weight=cc, slot=2),                             # :489
+            dict(kind=MW, pred_first=n, n=n, ref=Tw[:n], weight=cc, slot=3),                             # :494
+            dict(kind=BW, pred_first=5 * n, n=n, ref=ts, ref_is_strong=True, slot=4),                    # :448
+            dict(kind=BS, pred_first=4 * n, n=n, ref=ts, roll=pool_shift, slot=5),                       # :481
+            dict(kind=BS, pred_first=5 * n, n=n, ref=ts, slot=6),                                        # :482
+            dict(kind=MS, pred_first=4 * n, n=n, ref=Ss[:n], roll=pool_shift, weight=cc / 2, slot=7),    # :523
+            dict(kind=MS, pred_first=2 * n, n=n, ref=Ss[n:2 * n], roll=pool_shift, weight=cc / 2, slot=7),
+            dict(kind=MS, pred_first=2 * n, n=n, ref=Ts[n:2 * n], weight=cc, grad_weight=cc / 2, slot=8),   # :500, :529
+            dict(kind=MS, pred_first=3 * n, n=n, ref=Ts[2 * n:], weight=cc, grad_weight=cc / 2, slot=9),    # :508, :529
+        ]
+        if widx > 0:
+            terms.insert(6, dict(kind=BW, pred_first=3 * n, n=widx, ref=tw[:widx], slot=4))              # :448 (real half)
+        if n - widx > 0:   # logged only (:504, :512)
+            terms += [dict(kind=MW, pred_first=2 * n + widx, n=n - widx, ref=Tw[n + widx:2 * n], weight=cc, grad_weight=0.0, slot=10),
+                      dict(kind=MW, pred_first=3 * n + widx, n=n - widx, ref=Tw[2 * n + widx:], weight=cc, grad_weight=0.0, slot=11)]
+        losses, d_strong, d_weak = engine.loss_terms(Ss, Sw, terms, len(ISP_SLOTS))
+
+        gp = self.grads[self.n_crnn:]
+        dA, dB = self.d_enc[:3 * n], self.d_enc[3 * n:7 * n]
+        self.planA.predictor_backward(pp, encA[:2 * n], self.s_logits[:2 * n], Ss[:2 * n], Sw[:2 * n], d_strong[:2 * n],
+                                      d_weak[:2 * n], gp, accumulate=False, d_enc=dA[:2 * n])
+        self.planA.predictor_backward(pp, encB, self.s_logits[2 * n:], Ss[2 * n:], Sw[2 * n:], d_strong[2 * n:],
+                                      d_weak[2 * n:], gp, accumulate=True, d_enc=dB)
+        gc = self.grads[:self.n_crnn]
+        self.planA.backward(0b011, dA, gc, accumulate=False)
+        self.planB.backward(0b1111, dB, gc, accumulate=True)
+        grad_scale = shard.allreduce_gradients(self.grads, self.pg)
+        self.opt_step += 1
+        engine.opt_ema_step(self.params, self.grads, self.m, self.v, self.ema_params, step=self.opt_step,
+                            ema_step=global_step + 1, kind="adam", lr=self.lr, betas=self.betas, eps=self.eps,
+                            weight_decay=self.weight_decay, grad_scale=grad_scale)
+        engine.ema_buffers(sbn, tbn, snbt, tnbt, global_step + 1)
+        self.last = dict(strong=Ss, weak=Sw, losses=losses)
+        return losses
+
+    @staticmethod
+    def total(losses):
+        """loss of src/main_baseline.py:517-529 from the 12 terms."""
+        return losses[:8].sum() + 0.5 * (losses[8] + losses[9])
+
+
 def _generic_step(model, predictor, ema_model, ema_predictor, optimizer, batch, syn_batch, global_step,
                   rampup_value):
     """The reference's statement order (src/main.py:250-254, 335-343, 376-477, 517-523) on the autograd
@@ -208,8 +359,10 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
              optimizer_crnn=None, ISP=False):
     """One epoch of the mean-teacher model; same arguments as the reference (src/main.py:163).
     Loaders yield (((student_input, teacher_input), target), filename)."""
-    if ISP or mask_weak is not None or mask_strong is not None:
-        raise NotImplementedError("ISP / masked-real-label branches are outside this round's hot path")
+    if mask_weak is not None or mask_strong is not None:
+        raise NotImplementedError("masked-real-label branches are outside this round's hot path")
+    if ISP and (ema_model is None or not isinstance(optimizer, FusedAdam)):
+        raise ValueError("ISP=True runs the fused shift-consistency step: it needs the teacher and a FusedAdam optimizer")
     if discriminator is not None and (optimizer_d is None or optimizer_crnn is None):
         raise ValueError("the adversarial update needs optimizer_d and optimizer_crnn (as in the reference)")
     if predictor is None:
@@ -240,7 +393,23 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
         ts = syn_target.to(dev, non_blocking=True)
         if discriminator is not None:
             domain_loss = adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_d, x, xs)
-        if fused:
+        if ISP:
+            tr = optimizer._trainer
+            if tr is None:
+                g = optimizer.param_groups[0]
+                tr = ShiftConsistencyTrainer(model, predictor, ema_model, ema_predictor, lr=g['lr'], betas=g['betas'],
+                                             eps=g['eps'], weight_decay=g['weight_decay'], n=x.shape[0],
+                                             dropout_seed=_dropout_state["seed"])
+                optimizer._trainer = tr
+            tr.lr = optimizer.param_groups[0]['lr']
+            # src/main_baseline.py:232-233: per-clip random shifts, +-64 pooled frames in time, +-4 mel bins
+            shift_list = [random.randint(-64, 64) * cfg.pooling_time_ratio for _ in range(x.shape[0])]
+            freq_shift_list = [random.randint(-4, 4) for _ in range(x.shape[0])]
+            tgt = target.to(dev, non_blocking=True).float()
+            target_weak = tgt if tgt.dim() == 2 else tgt.max(-2)[0]
+            losses12 = tr.step(x, x_ema, target_weak, xs, ts, shift_list, freq_shift_list, global_step, rampup_value)
+            losses = torch.cat([losses12[:8], 0.5 * losses12[8:10]])    # the terms that make up the loss (:517-529)
+        elif fused:
             tr = optimizer._trainer
             if tr is None:
                 g = optimizer.param_groups[0]
@@ -258,6 +427,6 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
     if losses is not None:
         lv = losses.tolist()   # the only host sync of the epoch
         log.info("Epoch: %d\t Time %.2f\t strong %.4f weak %.4f cons_strong %.4f cons_weak %.4f", c_epoch,
-                 time.time() - start, *lv)
+                 time.time() - start, *lv[:4])
         assert not (sum(lv) != sum(lv) or sum(lv) > 1e5), 'Loss explosion: {}'.format(sum(lv))
     return loss

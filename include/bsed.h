@@ -213,6 +213,41 @@ int bsed_mt_loss(bsed_handle h, const float* strong, const float* weak, int B, i
                  float* d_strong, float* d_weak, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Shift-consistency training (the ISP / SCT branch).           src/main_baseline.py:229-277,372-529
+ * bsed_roll_clips: out[b] = torch.roll(torch.roll(x[b], shift_t[b], time), shift_f[b], frequency) for clips
+ * x [B][T][F] (shift arrays on the device, either may be NULL = no shift along that axis); out must not alias x.
+ * bsed_loss_terms: a list of BCELoss / MSELoss terms over clip ranges of strong [B][T][C] / weak [B][C]:
+ *   kind BCE_STRONG / MSE_STRONG: pred = strong[pred_first .. +n_clips), ref [n_clips][T][C], optionally rolled per clip
+ *        along time (ref'[k] = torch.roll(ref[k], roll[k], 0), roll on the device) -- the rolled targets and rolled
+ *        (detached) predictions of the reference;
+ *   kind BCE_WEAK / MSE_WEAK: pred = weak[pred_first .. +n_clips), ref [n_clips][C], or with ref_is_strong a strong
+ *        target [n_clips][T][C] whose maximum over time is the weak target (syn_target.max(-2)[0]).
+ * Every term is a mean over its own elements (torch reduction='mean'); losses[slot] += weight * mean and
+ * d_strong / d_weak += grad_weight * d(mean)/d(pred) (grad_weight 0: value only, e.g. terms the reference only logs).
+ * `terms` is a HOST array; losses [n_slots], d_strong [B][T][C], d_weak [B][C] are device buffers, zeroed here first.
+ * Terms run as consecutive launches in array order, so the accumulation order is fixed.
+ * ------------------------------------------------------------------------------------------ */
+#define BSED_LOSS_BCE_STRONG 0
+#define BSED_LOSS_BCE_WEAK 1
+#define BSED_LOSS_MSE_STRONG 2
+#define BSED_LOSS_MSE_WEAK 3
+typedef struct {
+  int kind;
+  int pred_first, n_clips;
+  const float* ref;
+  const int32_t* roll;
+  int ref_is_strong;
+  float weight;
+  float grad_weight;
+  int slot;
+} bsed_loss_term;
+int bsed_loss_terms(bsed_handle h, const float* strong, const float* weak, int B, int T, int C,
+                    const bsed_loss_term* terms, int n_terms, float* losses, int n_slots, float* d_strong,
+                    float* d_weak, void* stream);
+int bsed_roll_clips(bsed_handle h, const float* x, const int32_t* shift_t, const int32_t* shift_f, float* out, int B,
+                    int T, int F, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser + EMA in one pass over the flat buffers.
  *   Adam   torch.optim.Adam(lr, betas=(.9,.999), eps=1e-8, weight_decay=0)   src/main.py:823-828
  *   SGD    torch.optim.SGD(momentum=.9, weight_decay=1e-4, nesterov=True)

@@ -121,3 +121,92 @@ def mt_step(model, predictor, ema_model, ema_predictor, optimizer, x, x_ema, xs,
     outs = dict(strong_ema=strong_ema, weak_ema=weak_ema, syn_strong=syn_strong.detach(),
                 syn_weak=syn_weak.detach(), strong=strong.detach(), weak=weak.detach(), grads=grads)
     return loss.detach(), {k: v.detach() for k, v in parts.items()}, outs
+
+
+def isp_step(model, predictor, ema_model, ema_predictor, optimizer, x, x_ema, target_weak, xs, ts, shift_list,
+             freq_shift_list, global_step, rampup_value, max_consistency_cost=1.0, pooling_time_ratio=4,
+             dropout_hook=None):
+    """One iteration of the shift-consistency (ISP / SCT) step of src/main_baseline.py:train_mt with ISP=True, a teacher
+    and no discriminator update.  PARITY UNPINNED for the step assembly (the script imports librosa / tensorboardX and
+    cannot be executed here); the modules it drives are the pinned ones.
+
+      * :229-277   per clip k: inputs rolled by shift_list[k] frames (time) and by freq_shift_list[k] bins (frequency),
+                   the same shifts for the real, teacher and synthetic batches
+      * :337-341   student forward: synthetic, real
+      * :352-370   teacher forward (detached): real, time-shifted real, frequency-shifted real
+      * :375-408   rolled (detached) student predictions and rolled synthetic targets, roll = shift / pooling_time_ratio
+      * :412-422   student forward: shifted real, freq-shifted real, shifted synthetic, freq-shifted synthetic
+      * :433-452   weak BCE (synthetic + real weak targets), SCT weak term on the freq-shifted batches (real: first half)
+      * :475-482   strong BCE; strong BCE of the shifted / freq-shifted synthetic batch
+      * :485-512   teacher-student consistency (MSE) incl. the shifted variants (the weak shifted ones are only logged)
+      * :517-529   loss assembly
+      * :571-584   backward, optimizer step, state-dict EMA with global_step + 1
+    x / x_ema / xs: (B,1,T,128); target_weak (B,20); ts (B,313,20); shift_list multiples of pooling_time_ratio.
+    dropout_hook(tag) is called before each forward with tag in {'syn','real','teacher','teacher_shift',
+    'teacher_fshift','real_shift','real_fshift','syn_shift','syn_fshift'}."""
+    hook = dropout_hook or (lambda tag: None)
+    B = x.shape[0]
+
+    def roll_batch(t, shifts, dim):
+        return torch.stack([torch.roll(t[k], int(shifts[k]), dims=dim) for k in range(t.shape[0])])
+
+    x_shift, x_fshift = roll_batch(x, shift_list, 1), roll_batch(x, freq_shift_list, 2)
+    xe_shift, xe_fshift = roll_batch(x_ema, shift_list, 1), roll_batch(x_ema, freq_shift_list, 2)
+    xs_shift, xs_fshift = roll_batch(xs, shift_list, 1), roll_batch(xs, freq_shift_list, 2)
+
+    def run(m, p, inp, tag):
+        hook(tag)
+        enc, _ = m(inp)
+        return p(enc)
+
+    syn_strong, syn_weak = run(model, predictor, xs, "syn")
+    strong, weak = run(model, predictor, x, "real")
+    strong_ema, weak_ema = [t.detach() for t in run(ema_model, ema_predictor, x_ema, "teacher")]
+    strong_shift_ema, weak_shift_ema = [t.detach() for t in run(ema_model, ema_predictor, xe_shift, "teacher_shift")]
+    strong_fshift_ema, weak_fshift_ema = [t.detach() for t in run(ema_model, ema_predictor, xe_fshift, "teacher_fshift")]
+
+    pool_shift = [int(s / pooling_time_ratio) for s in shift_list]
+    strong_pred_shift = roll_batch(strong, pool_shift, 0).detach()
+    syn_strong_pred_shift = roll_batch(syn_strong, pool_shift, 0).detach()
+    syn_target_shift = roll_batch(ts, pool_shift, 0)
+
+    strong_shift, weak_shift = run(model, predictor, x_shift, "real_shift")
+    strong_fshift, weak_fshift = run(model, predictor, x_fshift, "real_fshift")
+    syn_strong_shift, syn_weak_shift = run(model, predictor, xs_shift, "syn_shift")
+    syn_strong_fshift, syn_weak_fshift = run(model, predictor, xs_fshift, "syn_fshift")
+
+    bce, mse = nn.BCELoss(), nn.MSELoss()
+    syn_target_weak = ts.max(-2)[0]
+    widx = target_weak.shape[0] // 2
+    cc = max_consistency_cost * rampup_value
+    parts = dict(
+        strong_class=bce(syn_strong, ts),
+        weak_class=bce(syn_weak, syn_target_weak) + bce(weak, target_weak),
+        cons_strong=cc * mse(strong, strong_ema),
+        cons_weak=cc * mse(weak, weak_ema),
+        weak_freq_shift_class=bce(syn_weak_fshift, syn_target_weak) + bce(weak_fshift[:widx], target_weak[:widx]),
+        strong_shift_class=bce(syn_strong_shift, syn_target_shift),
+        strong_freq_shift_class=bce(syn_strong_fshift, ts),
+        cons_shift=cc / 2 * (mse(syn_strong_shift, syn_strong_pred_shift) + mse(strong_shift, strong_pred_shift)),
+        cons_strong_shift=cc * mse(strong_shift, strong_shift_ema),
+        cons_strong_freq_shift=cc * mse(strong_fshift, strong_fshift_ema),
+        cons_weak_shift=cc * mse(weak_shift[widx:], weak_shift_ema[widx:]),            # logged only
+        cons_weak_freq_shift=cc * mse(weak_fshift[widx:], weak_fshift_ema[widx:]))     # logged only
+    loss = parts["strong_class"] + parts["weak_class"]
+    loss = loss + (parts["cons_weak"] + parts["cons_strong"])
+    loss = loss + (parts["weak_freq_shift_class"] + parts["strong_shift_class"] + parts["strong_freq_shift_class"]
+                   + parts["cons_shift"])
+    loss = loss + 1 / 2 * (parts["cons_strong_shift"] + parts["cons_strong_freq_shift"])
+    optimizer.zero_grad()
+    loss.backward()
+    grads = {}
+    for prefix, mod in (("crnn.", model), ("pred.", predictor)):
+        for n, p in mod.named_parameters():
+            grads[prefix + n] = p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)
+    optimizer.step()
+    gs = global_step + 1
+    update_ema_state_dict(model, ema_model, 0.999, gs)
+    update_ema_state_dict(predictor, ema_predictor, 0.999, gs)
+    outs = dict(strong=strong.detach(), weak=weak.detach(), syn_strong=syn_strong.detach(),
+                strong_shift=strong_shift.detach(), syn_strong_fshift=syn_strong_fshift.detach(), grads=grads)
+    return loss.detach(), {k: v.detach() for k, v in parts.items()}, outs
