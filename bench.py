@@ -310,7 +310,9 @@ def run_b200(args):
                                                               "else fp32)" if trainer.plan.precision == "tf32" else ""),
                        "model": args.model + (" (src/models/CRNN.py:243-337)" if fpn else " (src/models/CRNN.py:178-240)"),
                        "clips_per_step_per_gpu": 24,
-                       "parallelism": f"dp{world} (NCCL sum all-reduce of the %.2f MB flat gradient)" % (trainer.grads.numel() * 4 / 1e6),
+                       "parallelism": f"dp{world} (%s of the %.2f MB flat gradient)" % (
+                           "one kernel per rank: all-reduce over NVLink peer memory + Adam + EMA" if trainer.dp is not None
+                           else "NCCL sum all-reduce", trainer.grads.numel() * 4 / 1e6),
                        "host_enqueue_ms_per_step": host_enqueue_ms,
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",
                        "step_gflop_algorithmic": step_flop / 1e9},

@@ -27,6 +27,7 @@ SYMBOLS = [
     "bsed_plan_set_precision", "bsed_plan_get_precision",
     "bsed_disc_param_count", "bsed_disc_bn_buffer_count", "bsed_disc_workspace_bytes", "bsed_disc_forward",
     "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision", "bsed_loss_terms", "bsed_roll_clips",
+    "bsed_ipc_export", "bsed_ipc_open", "bsed_ipc_close", "bsed_dp_opt_ema_step",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -114,6 +115,10 @@ def load():
         proto("bsed_mt_loss", i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, f32, vp, vp, vp, vp)
         proto("bsed_loss_terms", i32, vp, vp, vp, i32, i32, i32, P(LossTerm), i32, vp, i32, vp, vp, vp)
         proto("bsed_roll_clips", i32, vp, vp, vp, vp, vp, i32, i32, i32, vp)
+        proto("bsed_ipc_export", i32, vp, vp, C.c_char_p, P(u64))
+        proto("bsed_ipc_open", i32, vp, C.c_char_p, u64, P(vp))
+        proto("bsed_ipc_close", i32, vp, vp, u64)
+        proto("bsed_dp_opt_ema_step", i32, vp, i32, i32, P(vp), P(vp), i64, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
         proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)

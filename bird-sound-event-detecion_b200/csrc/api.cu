@@ -279,6 +279,53 @@ extern "C" int bsed_opt_ema_step(bsed_handle h, float* params, const float* grad
   return opt_ema_step(params, grads, m, v, ema, n, cfg, as_stream(stream));
 }
 
+// ---------------------------------------------------------------------------------------------
+// peer memory (CUDA IPC) for the fused data-parallel step
+// ---------------------------------------------------------------------------------------------
+extern "C" int bsed_ipc_export(bsed_handle h, const void* dev_ptr, unsigned char* handle, uint64_t* offset) {
+  BSED_REQUIRE(h && dev_ptr && handle && offset, "bsed_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == BSED_IPC_HANDLE_BYTES, "IPC handle size");
+  typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  BSED_CHECK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+  BSED_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "bsed_ipc_export: cuMemGetAddressRange not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  int r = reinterpret_cast<GetRange>(fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+  BSED_REQUIRE(r == 0, "bsed_ipc_export: cuMemGetAddressRange failed (%d)", r);
+  cudaIpcMemHandle_t hd;
+  BSED_CHECK_CUDA(cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>((uintptr_t)base)));
+  memcpy(handle, &hd, sizeof(hd));
+  *offset = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return BSED_OK;
+}
+
+extern "C" int bsed_ipc_open(bsed_handle h, const unsigned char* handle, uint64_t offset, void** mapped) {
+  BSED_REQUIRE(h && handle && mapped, "bsed_ipc_open: null argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, sizeof(hd));
+  void* base = nullptr;
+  BSED_CHECK_CUDA(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  *mapped = reinterpret_cast<unsigned char*>(base) + offset;
+  return BSED_OK;
+}
+
+extern "C" int bsed_ipc_close(bsed_handle h, void* mapped, uint64_t offset) {
+  BSED_REQUIRE(h && mapped, "bsed_ipc_close: null argument");
+  BSED_CHECK_CUDA(cudaIpcCloseMemHandle(reinterpret_cast<unsigned char*>(mapped) - offset));
+  return BSED_OK;
+}
+
+extern "C" int bsed_dp_opt_ema_step(bsed_handle h, int rank, int world, const float* const* peer_grads,
+                                    int32_t* const* peer_flags, int64_t epoch, float* params, float* m, float* v, float* ema,
+                                    int64_t n, const bsed_opt_cfg* cfg, void* stream) {
+  BSED_REQUIRE(h && peer_grads && peer_flags && params && m && cfg, "bsed_dp_opt_ema_step: null argument");
+  BSED_REQUIRE(cfg->kind != 0 || v, "bsed_dp_opt_ema_step: Adam needs v");
+  return dp_opt_ema_step(rank, world, peer_grads, reinterpret_cast<int* const*>(peer_flags), epoch, params, m, v, ema, n, cfg,
+                         h->num_sms, as_stream(stream));
+}
+
 extern "C" int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffers, int64_t n,
                                 const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float ema_alpha, int64_t ema_step,
                                 void* stream) {

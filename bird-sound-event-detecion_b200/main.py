@@ -22,6 +22,7 @@ synthetic; teacher: real, time-shifted real, frequency-shifted real), the twelve
 update, all in libbsed.so kernels.
 """
 import logging
+import os
 import random
 import time
 
@@ -113,6 +114,11 @@ class MeanTeacherTrainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        # N > 1: the gradient exchange is fused with the optimiser + EMA in one kernel over NVLink peer memory
+        # (utilities/shard.py: FusedDataParallel); BSED_DP=nccl keeps the NCCL all-reduce + separate optimiser kernel
+        self.dp = None
+        if self.world > 1 and os.environ.get("BSED_DP", "fused").lower() == "fused":
+            self.dp = shard.FusedDataParallel.create(self.grads, process_group)
         B = n_syn + n_real + (n_real if self.has_teacher else 0)
         self.B = B
         self.plan = engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev,
@@ -151,11 +157,16 @@ class MeanTeacherTrainer:
         self.plan.predictor_backward(pp, self.enc[:nst], logits, strong, weak, d_strong, d_weak,
                                      self.grads[self.n_crnn:], accumulate=False, d_enc=self.d_enc[:nst])
         self.plan.backward(0b011, self.d_enc, self.grads[:self.n_crnn], accumulate=False)
-        grad_scale = shard.allreduce_gradients(self.grads, self.pg)   # NCCL sum over NVLink; 1/N folded below
         self.opt_step += 1
-        engine.opt_ema_step(self.params, self.grads, self.m, self.v, self.ema_params if self.has_teacher else None,
-                            step=self.opt_step, ema_step=global_step + 1, kind="adam", lr=self.lr, betas=self.betas,
-                            eps=self.eps, weight_decay=self.weight_decay, grad_scale=grad_scale)
+        ema = self.ema_params if self.has_teacher else None
+        if self.dp is not None:    # all-reduce over peer memory + Adam + EMA in one kernel
+            self.dp.opt_ema_step(self.params, self.m, self.v, ema, step=self.opt_step, ema_step=global_step + 1, kind="adam",
+                                 lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        else:
+            grad_scale = shard.allreduce_gradients(self.grads, self.pg)   # NCCL sum over NVLink; 1/N folded below
+            engine.opt_ema_step(self.params, self.grads, self.m, self.v, ema, step=self.opt_step, ema_step=global_step + 1,
+                                kind="adam", lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay,
+                                grad_scale=grad_scale)
         if self.has_teacher and self.ema_flavour == "state_dict":
             engine.ema_buffers(sbn, tbn, snbt, tnbt, global_step + 1)
         self.last = dict(strong=strong, weak=weak, losses=losses)

@@ -2,8 +2,14 @@
 needs no data-path collective (contiguous blocks per rank, rank-ordered concatenation of results on
 the host); training is data-parallel with ONE sum all-reduce of the flat gradient buffer per step
 (4.47 MB), the 1/N average folded into the optimiser kernel's grad_scale."""
+import ctypes as C
+import logging
+import os
+
 import torch
 import torch.distributed as dist
+
+log = logging.getLogger("bsed_b200.shard")
 
 
 def clip_shard(n_clips, rank, world):
@@ -33,3 +39,89 @@ def gather_in_rank_order(obj, group=None):
     parts = [None] * n
     dist.all_gather_object(parts, obj, group=group)
     return [x for p in parts for x in p]
+
+
+class FusedDataParallel:
+    """Gradient exchange + optimiser + EMA in ONE kernel over NVLink peer memory (include/bsed.h: bsed_dp_opt_ema_step).
+
+    Every rank exports its flat gradient buffer and a flag block through CUDA IPC, maps its peers', and each step one
+    kernel per rank waits for the peers' gradients, sums them in rank order out of peer memory and updates the local
+    parameters / optimiser state / EMA teacher.  `FusedDataParallel.create` returns None (every rank alike) when peer
+    mapping is unavailable, and the caller keeps the NCCL all-reduce path."""
+
+    def __init__(self, grads, group=None):
+        from .. import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("fused data-parallel step supports up to 8 ranks")
+        self.device = grads.device
+        self.h = _lib.handle(self.device.index)
+        self.grads = grads
+        self.flags = torch.zeros(64, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+
+        def export(t):
+            buf = C.create_string_buffer(64)
+            off = C.c_uint64()
+            _lib.check(self.lib.bsed_ipc_export(self.h, C.c_void_p(t.data_ptr()), buf, C.byref(off)), "bsed_ipc_export")
+            return buf.raw, int(off.value)
+
+        mine = dict(pid=os.getpid(), grads=export(grads), flags=export(self.flags), n=grads.numel())
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine, group=group)
+        if any(i["n"] != grads.numel() for i in infos):
+            raise RuntimeError("ranks disagree on the gradient buffer size")
+        self._opened = {}
+        self.peer_grads = (C.c_void_p * self.world)()
+        self.peer_flags = (C.c_void_p * self.world)()
+        for r, info in enumerate(infos):
+            if r == self.rank:
+                self.peer_grads[r], self.peer_flags[r] = grads.data_ptr(), self.flags.data_ptr()
+            else:
+                self.peer_grads[r] = self._open(r, *info["grads"])
+                self.peer_flags[r] = self._open(r, *info["flags"])
+        self.epoch = 0
+
+    def _open(self, r, handle, offset):
+        key = (r, handle)
+        if key not in self._opened:       # one mapping per peer allocation
+            base = C.c_void_p()
+            from .. import _lib
+            _lib.check(self.lib.bsed_ipc_open(self.h, handle, 0, C.byref(base)), "bsed_ipc_open")
+            self._opened[key] = base.value
+        return self._opened[key] + offset
+
+    @classmethod
+    def create(cls, grads, group=None):
+        """Collective: every rank calls it; all get an instance or all get None."""
+        ok, obj = 1, None
+        try:
+            obj = cls(grads, group)
+        except Exception as e:   # noqa: BLE001 -- any failure means 'use NCCL', decided jointly below
+            log.warning("fused data-parallel step unavailable on rank %s: %s", dist.get_rank(group), e)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=grads.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        torch.cuda.synchronize(grads.device)
+        return obj if int(flag.item()) == 1 else None
+
+    def opt_ema_step(self, params, m, v, ema, step, ema_step, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
+                     weight_decay=0.0, momentum=0.9, ema_alpha=0.999):
+        from .. import _lib
+        from .._lib import OptCfg, check, ptr, stream_ptr
+        cfg = OptCfg()
+        cfg.kind = 0 if kind == "adam" else 1
+        cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        cfg.weight_decay, cfg.momentum, cfg.ema_alpha = float(weight_decay), float(momentum), float(ema_alpha)
+        cfg.grad_scale = 1.0 / self.world
+        cfg.step, cfg.ema_step = int(step), int(ema_step)
+        self.epoch += 1
+        check(self.lib.bsed_dp_opt_ema_step(self.h, self.rank, self.world, self.peer_grads, self.peer_flags, self.epoch,
+                                            ptr(params), ptr(m), ptr(v), ptr(ema), params.numel(), C.byref(cfg), stream_ptr()),
+              "bsed_dp_opt_ema_step")
+
+    def timed_out(self):
+        """True if a spin gave up (a peer never arrived); host sync."""
+        return bool(int(self.flags[33].item()))

@@ -1,0 +1,80 @@
+"""2+-GPU check of the fused data-parallel step (run under torchrun on a multi-GPU box):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dp_fused_check.py
+Each rank holds different gradients; the fused kernel (all-reduce over NVLink peer memory + Adam + EMA) must give the
+same parameters / moments / EMA as NCCL all-reduce + bsed_opt_ema_step, and bit-identical replicas across ranks."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from bsed_b200 import engine
+    from bsed_b200.utilities import shard
+    dev = torch.device("cuda", local)
+    n = 1117560
+    g0 = torch.Generator(device=dev).manual_seed(1)
+    p0 = torch.randn(n, device=dev, generator=g0)           # same parameters on every rank
+    e0 = torch.randn(n, device=dev, generator=g0)
+    grads = torch.empty(n, device=dev)
+    dp = shard.FusedDataParallel.create(grads, None)
+    if dp is None:
+        if rank == 0:
+            print("FUSED-DP UNAVAILABLE (peer mapping failed); NCCL path stays in use")
+        dist.destroy_process_group()
+        return
+    pa, ma, va, ea = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), e0.clone()
+    pb, mb, vb, eb = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), e0.clone()
+    worst = 0.0
+    for step in range(1, 6):
+        gr = torch.Generator(device=dev).manual_seed(100 * step + rank)
+        grads.copy_(torch.randn(n, device=dev, generator=gr) * 0.01)      # rank-specific gradients
+        ref = grads.clone()
+        dp.opt_ema_step(pa, ma, va, ea, step=step, ema_step=step, lr=5e-4)
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        engine.opt_ema_step(pb, ref, mb, vb, eb, step=step, ema_step=step, lr=5e-4, grad_scale=1.0 / world)
+        torch.cuda.synchronize()
+        for a, b in ((pa, pb), (ma, mb), (va, vb), (ea, eb)):
+            worst = max(worst, float((a - b).abs().max()))
+    assert not dp.timed_out(), "a spin timed out"
+    # replicas bit-identical across ranks
+    cs = torch.stack([pa.double().sum(), ea.double().sum(), ma.double().sum()])
+    all_cs = [torch.empty_like(cs) for _ in range(world)]
+    dist.all_gather(all_cs, cs)
+    same = all(torch.equal(all_cs[0], c) for c in all_cs)
+    # timing: fused kernel vs NCCL + optimiser kernel
+    def timeit(fn, k=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / k * 1e3
+    st = [10]
+    def fused():
+        st[0] += 1
+        dp.opt_ema_step(pa, ma, va, ea, step=st[0], ema_step=st[0], lr=5e-4)
+    def nccl():
+        st[0] += 1
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        engine.opt_ema_step(pb, grads, mb, vb, eb, step=st[0], ema_step=st[0], lr=5e-4, grad_scale=1.0 / world)
+    us_f, us_n = timeit(fused), timeit(nccl)
+    if rank == 0:
+        print(f"fused-dp world={world}: max |fused - (nccl + opt)| = {worst:.3e}; replicas bit-identical: {same}; "
+              f"fused kernel {us_f:.1f} us/step vs NCCL all-reduce + optimiser {us_n:.1f} us/step")
+    assert worst < 1e-6 and same
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
