@@ -311,7 +311,7 @@ def run_b200(args):
                        "model": args.model + (" (src/models/CRNN.py:243-337)" if fpn else " (src/models/CRNN.py:178-240)"),
                        "clips_per_step_per_gpu": 24,
                        "parallelism": f"dp{world} (%s of the %.2f MB flat gradient)" % (
-                           "one kernel per rank: all-reduce over NVLink peer memory + Adam + EMA" if trainer.dp is not None
+                           "one kernel per rank: reduce-scatter over NVLink peer memory + Adam + EMA + all-gather" if trainer.dp is not None
                            else "NCCL sum all-reduce", trainer.grads.numel() * 4 / 1e6),
                        "host_enqueue_ms_per_step": host_enqueue_ms,
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",

@@ -118,7 +118,7 @@ def load():
         proto("bsed_ipc_export", i32, vp, vp, C.c_char_p, P(u64))
         proto("bsed_ipc_open", i32, vp, C.c_char_p, u64, P(vp))
         proto("bsed_ipc_close", i32, vp, vp, u64)
-        proto("bsed_dp_opt_ema_step", i32, vp, i32, i32, P(vp), P(vp), i64, vp, vp, vp, vp, i64, P(OptCfg), vp)
+        proto("bsed_dp_opt_ema_step", i32, vp, i32, i32, P(vp), P(vp), P(vp), P(vp), i64, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
         proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)

@@ -318,12 +318,12 @@ extern "C" int bsed_ipc_close(bsed_handle h, void* mapped, uint64_t offset) {
 }
 
 extern "C" int bsed_dp_opt_ema_step(bsed_handle h, int rank, int world, const float* const* peer_grads,
-                                    int32_t* const* peer_flags, int64_t epoch, float* params, float* m, float* v, float* ema,
-                                    int64_t n, const bsed_opt_cfg* cfg, void* stream) {
-  BSED_REQUIRE(h && peer_grads && peer_flags && params && m && cfg, "bsed_dp_opt_ema_step: null argument");
+                                    float* const* peer_params, float* const* peer_ema, int32_t* const* peer_flags,
+                                    int64_t epoch, float* m, float* v, int64_t n, const bsed_opt_cfg* cfg, void* stream) {
+  BSED_REQUIRE(h && peer_grads && peer_params && peer_flags && m && cfg, "bsed_dp_opt_ema_step: null argument");
   BSED_REQUIRE(cfg->kind != 0 || v, "bsed_dp_opt_ema_step: Adam needs v");
-  return dp_opt_ema_step(rank, world, peer_grads, reinterpret_cast<int* const*>(peer_flags), epoch, params, m, v, ema, n, cfg,
-                         h->num_sms, as_stream(stream));
+  return dp_opt_ema_step(rank, world, peer_grads, peer_params, peer_ema, reinterpret_cast<int* const*>(peer_flags), epoch, m, v,
+                         n, cfg, h->num_sms, as_stream(stream));
 }
 
 extern "C" int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffers, int64_t n,

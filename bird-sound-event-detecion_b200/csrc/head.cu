@@ -570,24 +570,28 @@ int opt_ema_step(float* params, const float* grads, float* m, float* v, float* e
 }
 
 // ---------------------------------------------------------------------------------------------
-// Data-parallel step in ONE kernel: gradient all-reduce over NVLink peer memory + optimiser + EMA.
+// Data-parallel step in ONE kernel: gradient reduce-scatter over NVLink peer memory + optimiser + EMA + all-gather.
 //
-// Every rank maps every peer's flat gradient buffer and flag block (CUDA IPC).  Per step (`epoch` increases by one):
-//   1. arrive: thread r of every CTA's first warp... (block 0) stores `epoch` into peer r's arrive[my_rank] with release.sys
-//      semantics -- the gradient kernels of this rank ran earlier on the same stream, so its buffer is complete;
-//      every CTA then spins on its OWN arrive[] flags (local memory) until all peers have arrived;
-//   2. reduce + update: each thread sums element i over the peers IN RANK ORDER (so every rank computes bit-identical
-//      sums and the replicas stay bit-identical without a broadcast), reading peers with L1-bypassing loads, and applies
-//      Adam / SGD-Nesterov and the EMA to its local parameters;
+// Every rank maps every peer's flat gradient, parameter and EMA buffers and flag block (CUDA IPC).  Per step (`epoch`
+// increases by one), rank r owns the slice [r * chunk, (r + 1) * chunk) of the flat buffers:
+//   1. arrive: block 0 stores `epoch` into every peer's arrive[my_rank] with release.sys semantics -- the gradient
+//      kernels of this rank ran earlier on the same stream, so its buffer is complete and nothing on this rank reads
+//      the parameters any more; every CTA then spins on its OWN arrive[] flags (local memory) until all peers arrived;
+//   2. reduce + update + publish: each thread sums element i of its rank's slice over the peers IN RANK ORDER (L1-bypassing
+//      loads from peer memory), applies Adam / SGD-Nesterov and the EMA to the local copy, and stores the new parameter
+//      and EMA value into every peer's buffers -- replicas are bit-identical by construction, the optimiser state
+//      (m, v) is only ever touched inside the owner's slice, and each rank moves n gradient floats in and
+//      2 n (world - 1) / world parameter floats out over NVLink instead of the world * n of a one-shot all-reduce;
 //   3. depart: the last CTA to finish (device-scope counter) stores `epoch` into every peer's done[my_rank] and waits
-//      until all peers have done the same, so no rank's next backward can overwrite gradients a peer is still reading.
-// Each rank pulls world x n floats over NVLink (8 x 4.47 MB = 36 MB for the CRNN: tens of microseconds on NVLink 5).
-// Spins give up after ~4 s and raise flags[err] instead of hanging the GPU.
+//      until all peers have done the same: all pushes have landed and nobody still reads this rank's gradients.
+// Spins give up after ~4 s and raise flags[33] instead of hanging the GPU.
 // flag block (int32[64], zero-initialised by the host): arrive[0..15], done[16..31], counter [32], error [33].
 // ---------------------------------------------------------------------------------------------
 constexpr int kDpMaxWorld = 8;
 struct DpPeers {
   const float* grads[kDpMaxWorld];
+  float* params[kDpMaxWorld];
+  float* ema[kDpMaxWorld];
   int* flags[kDpMaxWorld];
 };
 
@@ -603,6 +607,9 @@ __device__ __forceinline__ float ld_peer(const float* p) {   // peer memory: nev
   float v;
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_peer(float* p, float v) {
+  asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -623,7 +630,7 @@ __device__ bool dp_wait(const int* flags, int base, int world, int epoch) {
 
 __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank, int world, int epoch, float* __restrict__ p,
                                                          float* __restrict__ m, float* __restrict__ v,
-                                                         float* __restrict__ ema, long long n, OptScalars o) {
+                                                         float* __restrict__ ema, long long lo, long long hi, OptScalars o) {
   int* my = peers.flags[rank];
   __shared__ int ok_s;
   if (threadIdx.x == 0) {
@@ -636,17 +643,30 @@ __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank
   }
   __syncthreads();
   if (ok_s) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+      float gr[kDpMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kDpMaxWorld; ++r)
+        if (r < world) gr[r] = r == rank ? peers.grads[r][i] : ld_peer(peers.grads[r] + i);
       float g = 0.f;
-      for (int r = 0; r < world; ++r) g += r == rank ? peers.grads[r][i] : ld_peer(peers.grads[r] + i);
+#pragma unroll
+      for (int r = 0; r < kDpMaxWorld; ++r)
+        if (r < world) g += gr[r];
       opt_update(i, g * o.grad_scale, p, m, v, ema, o);
+      const float pw = p[i], ew = o.has_ema ? ema[i] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kDpMaxWorld; ++r)
+        if (r < world && r != rank) {
+          st_peer(peers.params[r] + i, pw);
+          if (o.has_ema) st_peer(peers.ema[r] + i, ew);
+        }
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    __threadfence_system();                    // this CTA's pushes are ordered before the counter increment
     const int done = atomicAdd(my + 32, 1);
-    if (done == (int)gridDim.x - 1) {          // last CTA of this rank: all peer reads of this rank are complete
+    if (done == (int)gridDim.x - 1) {          // last CTA of this rank: every push is out, every peer read is complete
       my[32] = 0;
       __threadfence_system();
       for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + 16 + rank, epoch);   // depart
@@ -655,24 +675,32 @@ __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank
   }
 }
 
-int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, int* const* peer_flags, long long epoch,
-                    float* params, float* m, float* v, float* ema, long long n, const bsed_opt_cfg* cfg, int num_sms,
-                    cudaStream_t st) {
+int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* const* peer_params, float* const* peer_ema,
+                    int* const* peer_flags, long long epoch, float* m, float* v, long long n, const bsed_opt_cfg* cfg,
+                    int num_sms, cudaStream_t st) {
   BSED_REQUIRE(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "dp_opt: rank %d of %d", rank, world);
   BSED_REQUIRE(epoch >= 1 && epoch < (1ll << 31), "dp_opt: epoch %lld", epoch);
+  const bool has_ema = peer_ema != nullptr && peer_ema[rank] != nullptr;
   OptScalars o;
-  BSED_TRY(make_opt_scalars(cfg, ema != nullptr, &o));
+  BSED_TRY(make_opt_scalars(cfg, has_ema, &o));
   DpPeers peers;
   for (int r = 0; r < kDpMaxWorld; ++r) {
     peers.grads[r] = r < world ? peer_grads[r] : nullptr;
+    peers.params[r] = r < world ? peer_params[r] : nullptr;
+    peers.ema[r] = r < world && has_ema ? peer_ema[r] : nullptr;
     peers.flags[r] = r < world ? peer_flags[r] : nullptr;
-    BSED_REQUIRE(r >= world || (peers.grads[r] && peers.flags[r]), "dp_opt: peer %d not mapped", r);
+    BSED_REQUIRE(r >= world || (peers.grads[r] && peers.params[r] && peers.flags[r] && (!has_ema || peers.ema[r])),
+                 "dp_opt: peer %d not mapped", r);
   }
-  // one resident wave: every CTA spins at the start, so all of them must be co-resident
-  int grid = num_sms * 4;
-  const long long need = (n + 255) / 256;
-  if (grid > need) grid = (int)need;
-  dp_opt_ema_kernel<<<grid, 256, 0, st>>>(peers, rank, world, (int)epoch, params, m, v, ema, n, o);
+  long long chunk = (n + world - 1) / world;
+  chunk = (chunk + 3) / 4 * 4;
+  long long lo = (long long)rank * chunk, hi = lo + chunk;
+  if (lo > n) lo = n;
+  if (hi > n) hi = n;
+  int grid = num_sms * 2;
+  const long long need = (hi - lo + 255) / 256;
+  if (grid > need) grid = (int)(need > 0 ? need : 1);
+  dp_opt_ema_kernel<<<grid, 256, 0, st>>>(peers, rank, world, (int)epoch, peers.params[rank], m, v, peers.ema[rank], lo, hi, o);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

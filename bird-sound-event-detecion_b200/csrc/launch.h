@@ -123,9 +123,9 @@ int loss_terms(const float* strong, const float* weak, int B, int T, int C, cons
 int roll_clips(const float* x, const int* shift_t, const int* shift_f, float* out, int B, int T, int F, cudaStream_t st);
 int opt_ema_step(float* params, const float* grads, float* m, float* v, float* ema, long long n,
                  const bsed_opt_cfg* cfg, cudaStream_t st);
-int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, int* const* peer_flags, long long epoch,
-                    float* params, float* m, float* v, float* ema, long long n, const bsed_opt_cfg* cfg, int num_sms,
-                    cudaStream_t st);
+int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* const* peer_params, float* const* peer_ema,
+                    int* const* peer_flags, long long epoch, float* m, float* v, long long n, const bsed_opt_cfg* cfg,
+                    int num_sms, cudaStream_t st);
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
                 int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st);
 int add_f32(float* dst, const float* src, long long n, cudaStream_t st);

@@ -114,11 +114,13 @@ class MeanTeacherTrainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        # N > 1: the gradient exchange is fused with the optimiser + EMA in one kernel over NVLink peer memory
+        # N > 1: the gradient exchange is fused with the optimiser + EMA in one kernel over NVLink peer memory (rank r
+        # reduces, updates and publishes slice r of the flat buffers)
         # (utilities/shard.py: FusedDataParallel); BSED_DP=nccl keeps the NCCL all-reduce + separate optimiser kernel
         self.dp = None
         if self.world > 1 and os.environ.get("BSED_DP", "fused").lower() == "fused":
-            self.dp = shard.FusedDataParallel.create(self.grads, process_group)
+            self.dp = shard.FusedDataParallel.create(self.grads, self.params, self.ema_params if self.has_teacher else None,
+                                                     process_group)
         B = n_syn + n_real + (n_real if self.has_teacher else 0)
         self.B = B
         self.plan = engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev,
@@ -160,8 +162,8 @@ class MeanTeacherTrainer:
         self.opt_step += 1
         ema = self.ema_params if self.has_teacher else None
         if self.dp is not None:    # all-reduce over peer memory + Adam + EMA in one kernel
-            self.dp.opt_ema_step(self.params, self.m, self.v, ema, step=self.opt_step, ema_step=global_step + 1, kind="adam",
-                                 lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+            self.dp.opt_ema_step(self.m, self.v, step=self.opt_step, ema_step=global_step + 1, kind="adam", lr=self.lr,
+                                 betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
         else:
             grad_scale = shard.allreduce_gradients(self.grads, self.pg)   # NCCL sum over NVLink; 1/N folded below
             engine.opt_ema_step(self.params, self.grads, self.m, self.v, ema, step=self.opt_step, ema_step=global_step + 1,

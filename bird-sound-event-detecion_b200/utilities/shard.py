@@ -44,12 +44,13 @@ def gather_in_rank_order(obj, group=None):
 class FusedDataParallel:
     """Gradient exchange + optimiser + EMA in ONE kernel over NVLink peer memory (include/bsed.h: bsed_dp_opt_ema_step).
 
-    Every rank exports its flat gradient buffer and a flag block through CUDA IPC, maps its peers', and each step one
-    kernel per rank waits for the peers' gradients, sums them in rank order out of peer memory and updates the local
-    parameters / optimiser state / EMA teacher.  `FusedDataParallel.create` returns None (every rank alike) when peer
-    mapping is unavailable, and the caller keeps the NCCL all-reduce path."""
+    Every rank exports its flat gradient / parameter / EMA buffers and a flag block through CUDA IPC and maps its
+    peers'.  Each step one kernel per rank waits for the peers' gradients, reduces ITS slice of the flat buffer in rank
+    order out of peer memory, updates that slice (parameters, optimiser state, EMA teacher) and stores the new values
+    into every peer's buffers.  `FusedDataParallel.create` returns None (every rank alike) when peer mapping is
+    unavailable, and the caller keeps the NCCL all-reduce path."""
 
-    def __init__(self, grads, group=None):
+    def __init__(self, grads, params, ema=None, group=None):
         from .. import _lib
         self.lib = _lib.load()
         self.group = group
@@ -58,7 +59,8 @@ class FusedDataParallel:
             raise RuntimeError("fused data-parallel step supports up to 8 ranks")
         self.device = grads.device
         self.h = _lib.handle(self.device.index)
-        self.grads = grads
+        self.grads, self.params, self.ema = grads, params, ema
+        assert params.numel() == grads.numel() and (ema is None or ema.numel() == grads.numel())
         self.flags = torch.zeros(64, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
 
@@ -68,19 +70,23 @@ class FusedDataParallel:
             _lib.check(self.lib.bsed_ipc_export(self.h, C.c_void_p(t.data_ptr()), buf, C.byref(off)), "bsed_ipc_export")
             return buf.raw, int(off.value)
 
-        mine = dict(pid=os.getpid(), grads=export(grads), flags=export(self.flags), n=grads.numel())
+        mine = dict(pid=os.getpid(), grads=export(grads), params=export(params), ema=export(ema) if ema is not None else None,
+                    flags=export(self.flags), n=grads.numel())
         infos = [None] * self.world
         dist.all_gather_object(infos, mine, group=group)
-        if any(i["n"] != grads.numel() for i in infos):
-            raise RuntimeError("ranks disagree on the gradient buffer size")
+        if any(i["n"] != grads.numel() or (i["ema"] is None) != (ema is None) for i in infos):
+            raise RuntimeError("ranks disagree on the flat buffer layout")
         self._opened = {}
-        self.peer_grads = (C.c_void_p * self.world)()
-        self.peer_flags = (C.c_void_p * self.world)()
+        mk = lambda: (C.c_void_p * self.world)()
+        self.peer_grads, self.peer_params, self.peer_ema, self.peer_flags = mk(), mk(), mk(), mk()
         for r, info in enumerate(infos):
             if r == self.rank:
-                self.peer_grads[r], self.peer_flags[r] = grads.data_ptr(), self.flags.data_ptr()
+                self.peer_grads[r], self.peer_params[r], self.peer_flags[r] = grads.data_ptr(), params.data_ptr(), self.flags.data_ptr()
+                self.peer_ema[r] = ema.data_ptr() if ema is not None else None
             else:
                 self.peer_grads[r] = self._open(r, *info["grads"])
+                self.peer_params[r] = self._open(r, *info["params"])
+                self.peer_ema[r] = self._open(r, *info["ema"]) if ema is not None else None
                 self.peer_flags[r] = self._open(r, *info["flags"])
         self.epoch = 0
 
@@ -94,11 +100,11 @@ class FusedDataParallel:
         return self._opened[key] + offset
 
     @classmethod
-    def create(cls, grads, group=None):
+    def create(cls, grads, params, ema=None, group=None):
         """Collective: every rank calls it; all get an instance or all get None."""
         ok, obj = 1, None
         try:
-            obj = cls(grads, group)
+            obj = cls(grads, params, ema, group)
         except Exception as e:   # noqa: BLE001 -- any failure means 'use NCCL', decided jointly below
             log.warning("fused data-parallel step unavailable on rank %s: %s", dist.get_rank(group), e)
             ok = 0
@@ -107,9 +113,9 @@ class FusedDataParallel:
         torch.cuda.synchronize(grads.device)
         return obj if int(flag.item()) == 1 else None
 
-    def opt_ema_step(self, params, m, v, ema, step, ema_step, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
-                     weight_decay=0.0, momentum=0.9, ema_alpha=0.999):
-        from .. import _lib
+    def opt_ema_step(self, m, v, step, ema_step, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                     momentum=0.9, ema_alpha=0.999):
+        """Updates self.params / self.ema (every rank ends with identical buffers); m, v: this rank's optimiser state."""
         from .._lib import OptCfg, check, ptr, stream_ptr
         cfg = OptCfg()
         cfg.kind = 0 if kind == "adam" else 1
@@ -118,8 +124,9 @@ class FusedDataParallel:
         cfg.grad_scale = 1.0 / self.world
         cfg.step, cfg.ema_step = int(step), int(ema_step)
         self.epoch += 1
-        check(self.lib.bsed_dp_opt_ema_step(self.h, self.rank, self.world, self.peer_grads, self.peer_flags, self.epoch,
-                                            ptr(params), ptr(m), ptr(v), ptr(ema), params.numel(), C.byref(cfg), stream_ptr()),
+        check(self.lib.bsed_dp_opt_ema_step(self.h, self.rank, self.world, self.peer_grads, self.peer_params,
+                                            self.peer_ema if self.ema is not None else None, self.peer_flags, self.epoch,
+                                            ptr(m), ptr(v), self.params.numel(), C.byref(cfg), stream_ptr()),
               "bsed_dp_opt_ema_step")
 
     def timed_out(self):

@@ -270,23 +270,25 @@ int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m
                       float* ema, int64_t n, const bsed_opt_cfg* cfg, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Data-parallel step in one kernel: gradient all-reduce over NVLink peer memory + optimiser + EMA.
+ * Data-parallel step in one kernel: gradient reduce-scatter over NVLink peer memory + optimiser + EMA + all-gather.
  * The reference trains on one GPU; data-parallel replicas exchange ONE flat gradient buffer per step.
- * Each rank exports its gradient buffer and a zero-initialised int32[64] flag block (bsed_ipc_export -> 64-byte handle +
- * byte offset inside the allocation, exchanged by the host), maps its peers' (bsed_ipc_open), and every step calls
- * bsed_dp_opt_ema_step with the per-rank device pointers (entry `rank` = its own buffers) and epoch = 1, 2, 3, ...:
- * the kernel waits until every peer's gradients are complete, sums them in rank order straight out of peer memory
- * (bit-identical on every rank), applies bsed_opt_ema_step's update with cfg->grad_scale (1 / world), and leaves only
- * when every peer has finished reading this rank's buffer.  world <= 8.  A peer that never arrives raises flag[33] after
- * ~4 s instead of hanging.  Buffers must come from cudaMalloc-backed allocations (the default torch allocator).
+ * Each rank exports its flat gradient, parameter and EMA buffers and a zero-initialised int32[64] flag block
+ * (bsed_ipc_export -> 64-byte handle + byte offset inside the allocation, exchanged by the host), maps its peers'
+ * (bsed_ipc_open), and every step calls bsed_dp_opt_ema_step with the per-rank device pointers (entry `rank` = its own
+ * buffers; peer_ema NULL = no teacher) and epoch = 1, 2, 3, ...  Rank r owns slice r of the flat buffers: the kernel
+ * waits until every peer's gradients are complete, sums the slice in rank order straight out of peer memory, applies
+ * bsed_opt_ema_step's update with cfg->grad_scale (1 / world) to its own copy, stores the new parameter / EMA values
+ * into every peer's buffers, and leaves only when every peer has done the same (all replicas bit-identical; m and v are
+ * only touched inside the owner's slice).  world <= 8.  A peer that never arrives raises flag[33] after ~4 s instead
+ * of hanging.  Buffers must come from cudaMalloc-backed allocations (the default torch allocator).
  * ------------------------------------------------------------------------------------------ */
 #define BSED_IPC_HANDLE_BYTES 64
 int bsed_ipc_export(bsed_handle h, const void* dev_ptr, unsigned char* handle, uint64_t* offset);
 int bsed_ipc_open(bsed_handle h, const unsigned char* handle, uint64_t offset, void** mapped);
 int bsed_ipc_close(bsed_handle h, void* mapped, uint64_t offset);
 int bsed_dp_opt_ema_step(bsed_handle h, int rank, int world, const float* const* peer_grads,
-                         int32_t* const* peer_flags, int64_t epoch, float* params, float* m, float* v, float* ema,
-                         int64_t n, const bsed_opt_cfg* cfg, void* stream);
+                         float* const* peer_params, float* const* peer_ema, int32_t* const* peer_flags,
+                         int64_t epoch, float* m, float* v, int64_t n, const bsed_opt_cfg* cfg, void* stream);
 
 /* State-dict flavour of update_ema_variables for the non-parameter entries: BN running stats
  * (fp32) and num_batches_tracked (int64, blended in fp32 and truncated, as load_state_dict does). */

@@ -1,6 +1,6 @@
 """2+-GPU check of the fused data-parallel step (run under torchrun on a multi-GPU box):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dp_fused_check.py
-Each rank holds different gradients; the fused kernel (all-reduce over NVLink peer memory + Adam + EMA) must give the
+Each rank holds different gradients; the fused kernel (reduce-scatter over NVLink peer memory + Adam + EMA + all-gather) must give the
 same parameters / moments / EMA as NCCL all-reduce + bsed_opt_ema_step, and bit-identical replicas across ranks."""
 import os
 import sys
@@ -24,28 +24,32 @@ def main():
     p0 = torch.randn(n, device=dev, generator=g0)           # same parameters on every rank
     e0 = torch.randn(n, device=dev, generator=g0)
     grads = torch.empty(n, device=dev)
-    dp = shard.FusedDataParallel.create(grads, None)
+    pa, ea = p0.clone(), e0.clone()
+    dp = shard.FusedDataParallel.create(grads, pa, ea, None)
     if dp is None:
         if rank == 0:
             print("FUSED-DP UNAVAILABLE (peer mapping failed); NCCL path stays in use")
         dist.destroy_process_group()
         return
-    pa, ma, va, ea = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), e0.clone()
+    ma, va = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    chunk = (-(-n // world) + 3) // 4 * 4
+    lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)      # this rank's slice (optimiser state lives there only)
     pb, mb, vb, eb = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), e0.clone()
     worst = 0.0
     for step in range(1, 6):
         gr = torch.Generator(device=dev).manual_seed(100 * step + rank)
         grads.copy_(torch.randn(n, device=dev, generator=gr) * 0.01)      # rank-specific gradients
         ref = grads.clone()
-        dp.opt_ema_step(pa, ma, va, ea, step=step, ema_step=step, lr=5e-4)
+        dp.opt_ema_step(ma, va, step=step, ema_step=step, lr=5e-4)
         dist.all_reduce(ref, op=dist.ReduceOp.SUM)
         engine.opt_ema_step(pb, ref, mb, vb, eb, step=step, ema_step=step, lr=5e-4, grad_scale=1.0 / world)
         torch.cuda.synchronize()
-        for a, b in ((pa, pb), (ma, mb), (va, vb), (ea, eb)):
+        dist.barrier()
+        for a, b in ((pa, pb), (ea, eb), (ma[lo:hi], mb[lo:hi]), (va[lo:hi], vb[lo:hi])):
             worst = max(worst, float((a - b).abs().max()))
     assert not dp.timed_out(), "a spin timed out"
     # replicas bit-identical across ranks
-    cs = torch.stack([pa.double().sum(), ea.double().sum(), ma.double().sum()])
+    cs = torch.stack([pa.double().sum(), ea.double().sum(), pa.double().square().sum()])
     all_cs = [torch.empty_like(cs) for _ in range(world)]
     dist.all_gather(all_cs, cs)
     same = all(torch.equal(all_cs[0], c) for c in all_cs)
@@ -63,7 +67,7 @@ def main():
     st = [10]
     def fused():
         st[0] += 1
-        dp.opt_ema_step(pa, ma, va, ea, step=st[0], ema_step=st[0], lr=5e-4)
+        dp.opt_ema_step(ma, va, step=st[0], ema_step=st[0], lr=5e-4)
     def nccl():
         st[0] += 1
         dist.all_reduce(grads, op=dist.ReduceOp.SUM)
@@ -72,7 +76,9 @@ def main():
     if rank == 0:
         print(f"fused-dp world={world}: max |fused - (nccl + opt)| = {worst:.3e}; replicas bit-identical: {same}; "
               f"fused kernel {us_f:.1f} us/step vs NCCL all-reduce + optimiser {us_n:.1f} us/step")
-    assert worst < 1e-6 and same
+    # NCCL sums in another order than rank order: a gradient sum that nearly cancels can change its last bits, and Adam's
+    # m / sqrt(v) turns that into up to a fraction of lr on single elements (measured 2.7e-6 at world = 8)
+    assert worst < 5e-5 and same
     dist.destroy_process_group()
 
 

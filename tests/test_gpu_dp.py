@@ -1,4 +1,4 @@
-"""Fused data-parallel step kernel (all-reduce over peer memory + optimiser + EMA) in its one-rank form: with world = 1 the
+"""Fused data-parallel step kernel (reduce-scatter over peer memory + optimiser + EMA + all-gather) in its one-rank form: with world = 1 the
 kernel runs the same arrive / reduce / depart protocol against its own buffers and must equal bsed_opt_ema_step bit for
 bit.  The multi-GPU form is checked by tests/dp_fused_check.py under torchrun on a multi-GPU box."""
 import ctypes as C
@@ -23,6 +23,7 @@ def test_world1_equals_plain_optimizer_step(kind):
     pa, ma, va, ea = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0), e0.clone()
     pb, mb, vb, eb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0), e0.clone()
     pg, pf = (C.c_void_p * 1)(grads.data_ptr()), (C.c_void_p * 1)(flags.data_ptr())
+    pp, pe = (C.c_void_p * 1)(pa.data_ptr()), (C.c_void_p * 1)(ea.data_ptr())
     for step in range(1, 5):
         grads.copy_(torch.randn(n, device="cuda", generator=g) * 0.01)
         cfg = OptCfg()
@@ -30,7 +31,7 @@ def test_world1_equals_plain_optimizer_step(kind):
         cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = 5e-4, 0.9, 0.999, 1e-8
         cfg.weight_decay, cfg.momentum, cfg.grad_scale, cfg.ema_alpha = (0.0 if kind == "adam" else 1e-4), 0.9, 1.0, 0.999
         cfg.step, cfg.ema_step = step, step
-        check(lib.bsed_dp_opt_ema_step(h, 0, 1, pg, pf, step, ptr(pa), ptr(ma), ptr(va), ptr(ea), n, C.byref(cfg), stream_ptr()),
+        check(lib.bsed_dp_opt_ema_step(h, 0, 1, pg, pp, pe, pf, step, ptr(ma), ptr(va), n, C.byref(cfg), stream_ptr()),
               "bsed_dp_opt_ema_step")
         engine.opt_ema_step(pb, grads, mb, vb, eb, step=step, ema_step=step, kind=kind, lr=5e-4,
                             weight_decay=(0.0 if kind == "adam" else 1e-4), grad_scale=1.0)
