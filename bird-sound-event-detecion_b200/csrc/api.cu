@@ -157,6 +157,48 @@ int build_tables(bsed_context* h) {
   h->mel_nnz = (int)w.size();
   BSED_REQUIRE(h->mel_nnz <= 2048, "mel filterbank has %d weights (> 2048)", h->mel_nnz);
   if (w.empty()) w.push_back(0.f);
+  // The same filterbank by INTERVALS between consecutive band edges: a bin in [e_j, e_j+1) lies on the rising slope of
+  // band j and on the falling slope of band j - 1 and on no other band, so one magnitude load serves both:
+  //   U_j = sum_k up[k] |X[k]|,  D_j = sum_k down[k] |X[k]|  over the bins of interval j;  mel[m] = U_m + D_(m+1).
+  // iv_w[k] = (W[j][k], W[j-1][k]) for the bins in interval order (= bin order), iv_start / iv_len per interval j = 0..128.
+  {
+    std::vector<float2> ivw;
+    std::vector<int> ivs(nm + 1), ivl(nm + 1);
+    int nnz = 0;
+    int k = 0;
+    auto weight = [&](int m, int kk) -> float {
+      if (m < 0 || m >= nm) return 0.f;
+      double f = (double)kk * kSampleRate / kNFFT;
+      double lower = (f - edges[m]) / (edges[m + 1] - edges[m]);
+      double upper = (edges[m + 2] - f) / (edges[m + 2] - edges[m + 1]);
+      return (float)fmax(0.0, fmin(lower, upper));
+    };
+    for (int j = 0; j <= nm; ++j) {
+      while (k < kNBins && (double)k * kSampleRate / kNFFT < edges[j]) ++k;
+      ivs[j] = (int)ivw.size();
+      int kk = k;
+      while (kk < kNBins && (double)kk * kSampleRate / kNFFT < edges[j + 1]) {
+        float2 w2 = make_float2(weight(j, kk), weight(j - 1, kk));
+        nnz += (w2.x != 0.f) + (w2.y != 0.f);
+        ivw.push_back(w2);
+        ++kk;
+      }
+      ivl[j] = kk - k;
+      // bins of interval j are k .. kk-1; their position in iv_w equals (bin - first bin of interval 0)
+      k = kk;
+    }
+    BSED_REQUIRE(nnz == h->mel_nnz, "mel interval tables hold %d non-zero weights, the filterbank %d", nnz, h->mel_nnz);
+    BSED_REQUIRE(ivl[nm] <= 32 && (int)ivw.size() <= 1028, "mel interval tables: top interval %d bins, %zu entries", ivl[nm], ivw.size());
+    // first bin of interval 0 (bins below e_0 = 0 Hz: none) -- iv_w index i corresponds to bin iv_bin0 + i
+    int bin0 = 0;
+    while (bin0 < kNBins && (double)bin0 * kSampleRate / kNFFT < edges[0]) ++bin0;
+    h->mel_iv_bin0 = bin0;
+    h->mel_iv_n = (int)ivw.size();
+    if (ivw.empty()) ivw.push_back(make_float2(0.f, 0.f));
+    BSED_TRY(upload(&h->mel_iv_w, ivw));
+    BSED_TRY(upload(&h->mel_iv_start, ivs));
+    BSED_TRY(upload(&h->mel_iv_len, ivl));
+  }
   BSED_TRY(upload(&h->window, win));
   BSED_TRY(upload(&h->tw1024, t1));
   BSED_TRY(upload(&h->tw2048, t2));
@@ -208,6 +250,9 @@ extern "C" int bsed_destroy(bsed_handle h) {
   cudaFree(h->tw2048);
   cudaFree(h->mel_w);
   cudaFree(h->mel_start);
+  cudaFree(h->mel_iv_w);
+  cudaFree(h->mel_iv_start);
+  cudaFree(h->mel_iv_len);
   cudaFree(h->mel_len);
   cudaFree(h->mel_off);
   delete h;

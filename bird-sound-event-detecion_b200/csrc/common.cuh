@@ -79,6 +79,11 @@ struct bsed_context {
   int* mel_len;         // [128] number of bins of band m
   int* mel_off;         // [128] offset of band m inside mel_w
   int mel_nnz;
+  float2* mel_iv_w;     // interval form of the filterbank: (rising weight of band j, falling weight of band j-1) per bin
+  int* mel_iv_start;    // [129] first entry of interval j in mel_iv_w
+  int* mel_iv_len;      // [129] bins in interval j
+  int mel_iv_bin0;      // bin of entry 0
+  int mel_iv_n;         // entries
   int disc_precision;   // BSED_PRECISION_* of the Clip_Discriminator GEMMs (default FP32, see bsed_disc_set_precision)
 };
 

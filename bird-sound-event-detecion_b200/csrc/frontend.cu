@@ -22,7 +22,8 @@ constexpr int FE_FPC = 16;                                  // frames per tile (
 constexpr int FE_WARPS = 16;
 constexpr int FE_AUD = ((kNFFT + (FE_FPC - 1) * kHop) + 15) / 16 * 16;  // 5888 staged samples
 constexpr int FE_BUF = 33 * 32;                             // padded transpose buffer (float2)
-constexpr int FE_MELW = 2048;
+constexpr int FE_IVW = 1028;                                // float2 entries of the interval filterbank
+constexpr int FE_NIV = kNMels + 1;                          // intervals between the 130 band edges
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -78,11 +79,10 @@ struct FrontendTables {
   const float* window;
   const float2* tw1024;
   const float2* tw2048;
-  const float* mel_w;
-  const int* mel_start;
-  const int* mel_len;
-  const int* mel_off;
-  int mel_nnz;
+  const float2* iv_w;     // interval form of the mel filterbank (api.cu: build_tables)
+  const int* iv_start;
+  const int* iv_len;
+  int iv_bin0, iv_n;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -98,11 +98,10 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
   float* win_s = audio_s + 2 * FE_AUD;
   float2* tw1024_s = reinterpret_cast<float2*>(win_s + kNFFT);  // [c][lane] = e^{-2 pi i lane c / 1024}
   float2* tw2048_s = tw1024_s + 1024;
-  float* melw_s = reinterpret_cast<float*>(tw2048_s + 516);
-  int* mstart_s = reinterpret_cast<int*>(melw_s + FE_MELW);
-  int* mlen_s = mstart_s + kNMels;
-  int* moff_s = mlen_s + kNMels;
-  float2* bufs = reinterpret_cast<float2*>(moff_s + kNMels);
+  float2* ivw_s = tw2048_s + 516;
+  int* ivs_s = reinterpret_cast<int*>(ivw_s + FE_IVW);
+  int* ivl_s = ivs_s + FE_NIV + 3;
+  float2* bufs = reinterpret_cast<float2*>(ivl_s + FE_NIV + 3);
 
   const int tid = threadIdx.x;
   const int lane = tid % 32, warp = tid / 32;
@@ -132,11 +131,10 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
   for (int i = tid; i < kNFFT; i += blockDim.x) win_s[i] = tb.window[i];
   for (int i = tid; i < 1024; i += blockDim.x) tw1024_s[i] = tb.tw1024[i];
   for (int i = tid; i < 513; i += blockDim.x) tw2048_s[i] = tb.tw2048[i];
-  for (int i = tid; i < tb.mel_nnz; i += blockDim.x) melw_s[i] = tb.mel_w[i];
-  for (int i = tid; i < kNMels; i += blockDim.x) {
-    mstart_s[i] = tb.mel_start[i];
-    mlen_s[i] = tb.mel_len[i];
-    moff_s[i] = tb.mel_off[i];
+  for (int i = tid; i < tb.iv_n; i += blockDim.x) ivw_s[i] = tb.iv_w[i];
+  for (int i = tid; i < FE_NIV; i += blockDim.x) {
+    ivs_s[i] = tb.iv_start[i];
+    ivl_s[i] = tb.iv_len[i];
   }
 
   float2* buf = bufs + warp * FE_BUF;
@@ -210,24 +208,46 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
     }
     if (lane == 0) mag[512] = m512;
     __syncwarp();
-    // sparse mel projection: lane -> bands lane, lane+32, lane+64, lane+96
+    // sparse mel projection by intervals between band edges: lane -> intervals lane, lane+32, lane+64, lane+96; one
+    // magnitude load feeds the rising slope of band j (U) and the falling slope of band j-1 (D); mel[m] = U_m + D_(m+1)
     float* out = mel + ((size_t)b * n_frames + t) * kNMels;
+    const float* magb = mag + tb.iv_bin0;
+    float U[4], D[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      int m = lane + 32 * r;
-      int s = mstart_s[m], len = mlen_s[m], off = moff_s[m];
-      float acc = 0.f;
-      for (int j = 0; j < len; ++j) acc = fmaf(melw_s[off + j], mag[s + j], acc);
-      out[m] = acc;
+      const int j = lane + 32 * r;
+      const int s = ivs_s[j], len = ivl_s[j];
+      float u = 0.f, d = 0.f;
+      for (int i = 0; i < len; ++i) {
+        const float2 w2 = ivw_s[s + i];
+        const float a = magb[s + i];
+        u = fmaf(w2.x, a, u);
+        d = fmaf(w2.y, a, d);
+      }
+      U[r] = u;
+      D[r] = d;
+    }
+    // top interval (above the centre of band 127, <= 32 bins): one bin per lane
+    float dtop = 0.f;
+    {
+      const int s = ivs_s[kNMels], len = ivl_s[kNMels];
+      if (lane < len) dtop = ivw_s[s + lane].y * magb[s + lane];
+      dtop = warp_sum(dtop);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float dn = __shfl_down_sync(0xffffffffu, D[r], 1);                       // D of interval j + 1 (same pass)
+      const float dnext = r < 3 ? __shfl_sync(0xffffffffu, D[r < 3 ? r + 1 : r], 0) : dtop;   // lane 31: first interval of the next pass
+      if (lane == 31) dn = dnext;
+      out[lane + 32 * r] = U[r] + dn;
     }
     __syncwarp();
   }
   cp_async_wait<0>();
 }
 
-constexpr size_t FE_SMEM_BYTES = sizeof(float) * (2 * FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516) +
-                                 sizeof(float) * FE_MELW + sizeof(int) * 3 * kNMels +
-                                 sizeof(float2) * FE_WARPS * FE_BUF;
+constexpr size_t FE_SMEM_BYTES = sizeof(float) * (2 * FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516 + FE_IVW) +
+                                 sizeof(int) * 2 * (FE_NIV + 3) + sizeof(float2) * FE_WARPS * FE_BUF;
 
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st) {
   BSED_REQUIRE(n_samples >= kNFFT / 2 + 1, "melspec: n_samples=%d < 1025 (reflect padding)", n_samples);
@@ -239,7 +259,7 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
     configured = true;
   }
   int n_frames = 1 + n_samples / kHop;
-  FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_w, h->mel_start, h->mel_len, h->mel_off, h->mel_nnz};
+  FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_iv_w, h->mel_iv_start, h->mel_iv_len, h->mel_iv_bin0, h->mel_iv_n};
   const int tiles_per_clip = ceil_div(n_frames, FE_FPC);
   const long long n_tiles = (long long)tiles_per_clip * B;
   BSED_REQUIRE(n_tiles < (1ll << 31), "melspec: too many frames");
@@ -349,9 +369,12 @@ __global__ void __launch_bounds__(256) db_apply_kernel(const float* __restrict__
       for (int j = 0; j < 4; ++j) xs[j] = db_sample(ms[j], ns[j], sqrt(w[q * 4 + j] * snr_scale / (double)t_in));
     }
     const float mxv = __uint_as_float(*reinterpret_cast<const unsigned int*>(w + kNMels));
-    const float floor_db = 20.0f * log10f(fmaxf(1e-5f, mxv)) - 80.0f;
+    // 20 log10(x) = 20 log10(2) * log2(x); __log2f (MUFU.LG2, <= 2 ulp: < 3e-5 dB over [1e-5, 1e4]) keeps the pass
+    // HBM-bound -- log10f made it issue-bound (ncu: 78 % issue slots, 52 % DRAM)
+    constexpr float kDbPerLog2 = 6.02059991327962390f;
+    const float floor_db = kDbPerLog2 * __log2f(fmaxf(1e-5f, mxv)) - 80.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = fmaxf(20.0f * log10f(fmaxf(1e-5f, xs[j])), floor_db);
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(kDbPerLog2 * __log2f(fmaxf(1e-5f, xs[j])), floor_db);
   }
   // ApplyLog / PadOrTrunc produce float32 (ToTensor().float()) before Normalize
   if (sc_mean) {

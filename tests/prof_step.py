@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 
 from bsed_b200 import engine  # noqa: E402
 from bsed_b200.main import MeanTeacherTrainer  # noqa: E402
-from bsed_b200.models import CRNN, Predictor  # noqa: E402
+from bsed_b200.models import CRNN, CRNN_fpn, Predictor  # noqa: E402
 from bsed_b200.utilities import synth  # noqa: E402
 from bsed_b200.utilities.utils import weights_init  # noqa: E402
 
@@ -22,12 +22,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frontend", action="store_true")
     ap.add_argument("--precision", default=None)
+    ap.add_argument("--model", default="crnn", choices=["crnn", "crnn_fpn"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(2023)
 
     def make():
-        m, p = CRNN(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+        cls = CRNN_fpn if a.model == "crnn_fpn" else CRNN
+        m, p = cls(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
         weights_init(m)
         weights_init(p)
         return m.to(dev).train(), p.to(dev).train()
