@@ -17,22 +17,28 @@ __device__ __forceinline__ int group_of(const Groups& g, int clip) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv0: x [B][T][F] -> y [B][T][F][16], weights in the reference's (16,1,3,3) layout
-// grid (chunks, clip); thread -> (pixel, channel quad)
+// conv0: x [B][T][F] -> y [B][T][F][Cout], weights in the reference's (Cout,1,3,3) layout.
+// A thread owns one (column, channel quad) and walks down a strip of rows with the 3 x 3 input window sliding through
+// registers: three new loads per output pixel instead of nine, no per-pixel index arithmetic, the next row's loads
+// issued before the current row's FMAs.  Lanes = 8 consecutive columns x 4 quads (Cout = 16), so a warp writes 512
+// contiguous bytes per row.  With stats != nullptr the per-channel sum / sum of squares of the output (BatchNorm batch
+// statistics) are accumulated on the way: stats[(group * Cout + c) * 2 + {0, 1}].
+// grid (column blocks x row strips, clip); block = 256 threads = (256 / nq) columns x nq quads.
 // ---------------------------------------------------------------------------------------------
-// Each CTA owns a contiguous pixel range of one clip; a thread keeps the 36 weights of its channel quad in registers
-// and walks the range with stride 256 / nq pixels (a warp writes 512 contiguous bytes per step).  With stats != nullptr
-// the per-channel sum / sum of squares of the output (BatchNorm batch statistics) are accumulated on the way:
-// stats[(group * Cout + c) * 2 + {0, 1}].
+constexpr int kConv0Rows = 32;   // rows per strip
+
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, Groups g, FloatPtrs w,
                                                         FloatPtrs bias, float* __restrict__ y, int T, int F,
-                                                        int Cout, long long pix_per_cta, double* __restrict__ stats) {
+                                                        int Cout, int col_blocks, double* __restrict__ stats) {
   const int clip = blockIdx.y;
   const int grp = group_of(g, clip);
   const int nq = Cout / 4;
   const int q = threadIdx.x % nq;
-  const int pstep = 256 / nq;
-  const long long npix = (long long)T * F;
+  const int cols_per_cta = 256 / nq;
+  const int cb = blockIdx.x % col_blocks, strip = blockIdx.x / col_blocks;
+  const int col = cb * cols_per_cta + threadIdx.x / nq;
+  const int t0 = strip * kConv0Rows;
+  const int t1 = min(T, t0 + kConv0Rows);
   float wr[4][9], br[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -40,30 +46,48 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) wr[j][tap] = w.p[grp][(q * 4 + j) * 9 + tap];
   }
-  const float* xc = x + (size_t)clip * npix;
-  const long long pbeg = (long long)blockIdx.x * pix_per_cta;
-  long long pend = pbeg + pix_per_cta;
-  if (pend > npix) pend = npix;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long pix = pbeg + threadIdx.x / nq; pix < pend; pix += pstep) {
-    const int f = (int)(pix % F), t = (int)(pix / F);
-    float v[9];
+  if (col < F) {
+    const float* xc = x + (size_t)clip * T * F;
+    const bool has_l = col > 0, has_r = col + 1 < F;
+    auto load_row = [&](int t, float (&r)[3]) {
+      if (t >= 0 && t < T) {
+        const float* p = xc + (size_t)t * F + col;
+        r[0] = has_l ? __ldg(p - 1) : 0.f;
+        r[1] = __ldg(p);
+        r[2] = has_r ? __ldg(p + 1) : 0.f;
+      } else {
+        r[0] = r[1] = r[2] = 0.f;
+      }
+    };
+    float r0[3], r1[3], r2[3];
+    load_row(t0 - 1, r0);
+    load_row(t0, r1);
+    float* yp = y + (((size_t)clip * T + t0) * F + col) * Cout + q * 4;
+    for (int t = t0; t < t1; ++t) {
+      load_row(t + 1, r2);
+      float o[4];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
-      v[tap] = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        float a = br[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a = fmaf(r0[k], wr[j][k], a);        // taps in the reference's (kh, kw) order
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a = fmaf(r1[k], wr[j][3 + k], a);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a = fmaf(r2[k], wr[j][6 + k], a);
+        o[j] = a;
+        s1[j] += a;
+        s2[j] = fmaf(a, a, s2[j]);
+      }
+      *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+      yp += (size_t)F * Cout;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r0[k] = r1[k];
+        r1[k] = r2[k];
+      }
     }
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = br[j];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) a = fmaf(v[tap], wr[j][tap], a);
-      o[j] = a;
-      s1[j] += a;
-      s2[j] = fmaf(a, a, s2[j]);
-    }
-    *reinterpret_cast<float4*>(y + ((size_t)clip * npix + pix) * Cout + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
   if (!stats) return;
   __shared__ float red[2][256][4];
@@ -76,7 +100,7 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < 2 * Cout; i += 256) {
     const int k = i / Cout, c = i % Cout;
     float tsum = 0.f;
-    for (int r = 0; r < pstep; ++r) tsum += red[k][r * nq + c / 4][c % 4];
+    for (int r = 0; r < cols_per_cta; ++r) tsum += red[k][r * nq + c / 4][c % 4];
     atomicAdd(stats + ((size_t)grp * Cout + c) * 2 + k, (double)tsum);
   }
 }
@@ -84,49 +108,74 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
 int conv0_fwd(const float* x, const Groups& g, const FloatPtrs& w, const FloatPtrs& bias, float* y, int T,
               int F, int Cout, double* stats, int num_sms, cudaStream_t st) {
   BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128 && 256 % (Cout / 4) == 0, "conv0: Cout=%d", Cout);
+  (void)num_sms;
   int B = g.first[g.n - 1] + g.count[g.n - 1];
-  const long long npix = (long long)T * F;
-  long long want = (long long)num_sms * 8 / B + 1;            // ~8 CTAs per SM overall
-  long long pix_per_cta = (npix + want - 1) / want;
-  const long long gran = 256 / (Cout / 4);
-  pix_per_cta = (pix_per_cta + gran - 1) / gran * gran;
-  dim3 grid(ceil_div(npix, pix_per_cta), B);
-  conv0_fwd_kernel<<<grid, 256, 0, st>>>(x, g, w, bias, y, T, F, Cout, pix_per_cta, stats);
+  const int cols_per_cta = 256 / (Cout / 4);
+  const int col_blocks = ceil_div(F, cols_per_cta);
+  dim3 grid(col_blocks * ceil_div(T, kConv0Rows), B);
+  conv0_fwd_kernel<<<grid, 256, 0, st>>>(x, g, w, bias, y, T, F, Cout, col_blocks, stats);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
 
-// dW[co][tap] += sum_p dY[p][co] * x[p + tap]; Cout == 16 (4 quads): thread -> (pixel, quad)
+// dW[co][tap] += sum_p dY[p][co] * x[p + tap]: same strip walk as the forward (thread = column x channel quad, sliding
+// 3 x 3 window of x), 36 accumulators per thread, reduced over the CTA's columns through shared memory.
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x,
                                                           const float* __restrict__ dY, float* dW, int first_clip,
-                                                          int T, int F, int Cout, int iters) {
+                                                          int T, int F, int Cout, int col_blocks) {
   const int clip = first_clip + blockIdx.y;
   const int nq = Cout / 4;
-  const long long npix = (long long)T * F;
-  const float* xc = x + (size_t)clip * npix;
+  const int q = threadIdx.x % nq;
+  const int cols_per_cta = 256 / nq;
+  const int cb = blockIdx.x % col_blocks, strip = blockIdx.x / col_blocks;
+  const int col = cb * cols_per_cta + threadIdx.x / nq;
+  const int t0 = strip * kConv0Rows;
+  const int t1 = min(T, t0 + kConv0Rows);
   float acc[4][9];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) acc[j][tap] = 0.f;
-  const int q = threadIdx.x % nq;
-  for (int it = 0; it < iters; ++it) {
-    long long id = ((long long)blockIdx.x * iters + it) * blockDim.x + threadIdx.x;
-    long long pix = id / nq;
-    if (pix >= npix) break;
-    int f = (int)(pix % F), t = (int)(pix / F);
-    float4 d = *reinterpret_cast<const float4*>(dY + ((size_t)clip * npix + pix) * Cout + q * 4);
-    float dv[4] = {d.x, d.y, d.z, d.w};
+  if (col < F) {
+    const float* xc = x + (size_t)clip * T * F;
+    const bool has_l = col > 0, has_r = col + 1 < F;
+    auto load_row = [&](int t, float (&r)[3]) {
+      if (t >= 0 && t < T) {
+        const float* p = xc + (size_t)t * F + col;
+        r[0] = has_l ? __ldg(p - 1) : 0.f;
+        r[1] = __ldg(p);
+        r[2] = has_r ? __ldg(p + 1) : 0.f;
+      } else {
+        r[0] = r[1] = r[2] = 0.f;
+      }
+    };
+    float r0[3], r1[3], r2[3];
+    load_row(t0 - 1, r0);
+    load_row(t0, r1);
+    const float* dp = dY + (((size_t)clip * T + t0) * F + col) * Cout + q * 4;
+    float4 d = *reinterpret_cast<const float4*>(dp);
+    for (int t = t0; t < t1; ++t) {
+      load_row(t + 1, r2);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+      dp += (size_t)F * Cout;
+      if (t + 1 < t1) d = *reinterpret_cast<const float4*>(dp);     // next row's gradient, ahead of this row's FMAs
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      int tt = t + tap / 3 - 1, ff = f + tap % 3 - 1;
-      float xv = (tt >= 0 && tt < T && ff >= 0 && ff < F) ? __ldg(xc + (size_t)tt * F + ff) : 0.f;
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j][tap] = fmaf(dv[j], xv, acc[j][tap]);
+        for (int k = 0; k < 3; ++k) {
+          acc[j][k] = fmaf(dv[j], r0[k], acc[j][k]);
+          acc[j][3 + k] = fmaf(dv[j], r1[k], acc[j][3 + k]);
+          acc[j][6 + k] = fmaf(dv[j], r2[k], acc[j][6 + k]);
+        }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        r0[k] = r1[k];
+        r1[k] = r2[k];
+      }
     }
   }
-  // reduce over threads with equal q: first inside the warp (lanes l, l + nq, ...), then via smem
-  __shared__ float red[8][32 * 9 * 4 / 4];  // [warp][nq(<=32)*... ] sized for nq <= 8 below
+  // reduce over the threads with equal q: lanes l, l + nq, ... inside the warp, then the 8 warps through smem
+  __shared__ float red[8][32 * 9];   // [warp][(q * 4 + j) * 9 + tap], Cout <= 32
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -154,10 +203,11 @@ int conv0_wgrad(const float* x, const float* dY, float* dW, int first_clip, int 
                 int Cout, int num_sms, cudaStream_t st) {
   BSED_REQUIRE(Cout % 4 == 0 && Cout <= 32 && (32 % (Cout / 4)) == 0 && (256 % (Cout / 4)) == 0,
                "conv0_wgrad: Cout=%d unsupported", Cout);
-  long long work = (long long)T * F * (Cout / 4);
-  int iters = 128;   // pixels per thread between block reductions
-  dim3 grid(ceil_div(work, 256LL * iters), n_clips);
-  conv0_wgrad_kernel<<<grid, 256, 0, st>>>(x, dY, dW, first_clip, T, F, Cout, iters);
+  (void)num_sms;
+  const int cols_per_cta = 256 / (Cout / 4);
+  const int col_blocks = ceil_div(F, cols_per_cta);
+  dim3 grid(col_blocks * ceil_div(T, kConv0Rows), n_clips);
+  conv0_wgrad_kernel<<<grid, 256, 0, st>>>(x, dY, dW, first_clip, T, F, Cout, col_blocks);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
