@@ -86,10 +86,16 @@ struct bsed_crnn_plan {
   size_t off_packed[2];
   size_t off_xhat[kMaxBlocks], off_lin[kMaxBlocks], off_pool[kMaxBlocks];
   size_t off_stats, off_stats2, off_meanrstd;
-  size_t off_xg, off_gru_out[kMaxStacks][4], off_gru_saved[kMaxStacks][4], off_enc[kMaxStacks];
-  size_t off_dxn, off_dpool[2], off_denc[kMaxStacks], off_dx1, off_dxg, off_dgh;
+  // per BRANCH scratch: branch 0 runs on the caller's stream; with fpn, rnn and rnn_2 (forward and backward) run on two
+  // plan-owned streams forked from / joined to it, so the three independent recurrences overlap
+  size_t off_xg[kMaxStacks], off_gru_out[kMaxStacks][4], off_gru_saved[kMaxStacks][4], off_enc[kMaxStacks];
+  size_t off_dxn, off_dpool[2], off_denc[kMaxStacks], off_dx1[kMaxStacks], off_dxg[kMaxStacks], off_dgh[kMaxStacks];
+  size_t off_dx0[kMaxStacks];   // aux branches: gradient w.r.t. the stack input, added to the block gradient after the join
+  int n_branches;
+  cudaStream_t aux[2];
+  cudaEvent_t ev_fork[2], ev_join[2];
   size_t off_cat[2], off_y2, off_dcat, off_dy2;   // fpn merge: cat[0] (B,156,512), cat[1] (B,313,512), y2 (B,156,256)
-  size_t off_G, off_dscratch, off_wgpart, off_bsums, off_bntab;
+  size_t off_G, off_dscratch[kMaxStacks], off_wgpart[kMaxStacks], off_bsums, off_bntab;
   size_t wgpart_bytes;
   size_t ws_bytes;
   int precision;  // BSED_PRECISION_FP32 (SIMT fp32) or BSED_PRECISION_TF32 (tcgen05 kind::tf32)
@@ -330,7 +336,8 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_stats2 = takeb(sizeof(double) * kMaxGroups * 128 * 2);
   p->off_meanrstd = takeb(sizeof(float) * kMaxBlocks * kMaxGroups * 128 * 2);
   const long long BT = Bm * p->Tout;   // the longest stack
-  p->off_xg = takeb(sizeof(float) * BT * 768);
+  p->n_branches = p->n_stacks;
+  for (int b = 0; b < p->n_branches; ++b) p->off_xg[b] = takeb(sizeof(float) * BT * 768);
   for (int s = 0; s < p->n_stacks; ++s) {
     const long long BTs = Bm * p->stackT[s];
     for (int l = 0; l < c.rnn_layers; ++l) {
@@ -343,9 +350,12 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_dxn = takeb(sizeof(float) * max_full);
   p->off_dpool[0] = takeb(sizeof(float) * max_pool);
   p->off_dpool[1] = takeb(sizeof(float) * max_pool);
-  p->off_dx1 = takeb(sizeof(float) * BT * 256);
-  p->off_dxg = takeb(sizeof(float) * BT * 768);
-  p->off_dgh = takeb(sizeof(float) * BT * 768);
+  for (int b = 0; b < p->n_branches; ++b) {
+    p->off_dx1[b] = takeb(sizeof(float) * BT * 256);
+    p->off_dxg[b] = takeb(sizeof(float) * BT * 768);
+    p->off_dgh[b] = takeb(sizeof(float) * BT * 768);
+    p->off_dx0[b] = b > 0 ? takeb(sizeof(float) * BT * 128) : 0;
+  }
   if (c.fpn) {
     p->off_cat[0] = takeb(sizeof(float) * Bm * p->stackT[1] * 512);
     p->off_cat[1] = takeb(sizeof(float) * BT * 512);
@@ -356,9 +366,11 @@ void carve_workspace(bsed_crnn_plan* p) {
   p->off_G = takeb(sizeof(float) * kMaxGroups * 128 * 128);
   p->off_bsums = takeb(sizeof(double) * kMaxGroups * 128 * 4);
   p->off_bntab = takeb(sizeof(float) * kMaxGroups * 3 * 128);
-  p->off_dscratch = takeb(sizeof(double) * 2 * 768);
   p->wgpart_bytes = tc_wgrad_workspace_bytes(p->ctx->num_sms);
-  p->off_wgpart = takeb(p->wgpart_bytes);
+  for (int b = 0; b < p->n_branches; ++b) {
+    p->off_dscratch[b] = takeb(sizeof(double) * 2 * 768);
+    p->off_wgpart[b] = takeb(p->wgpart_bytes);
+  }
   p->ws_bytes = o;
 }
 
@@ -490,6 +502,7 @@ BNPtrs make_bn_ptrs(const bsed_crnn_plan* p, void* ws, int layer, const int* gro
 // =================================================================================================
 // C ABI: plan
 // =================================================================================================
+extern "C" int bsed_plan_destroy(bsed_plan p);
 extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max_clips, bsed_plan* out) {
   BSED_REQUIRE(h && cfg && out, "plan_create: null argument");
   BSED_REQUIRE(max_clips >= 1 && max_clips <= 4096, "plan_create: max_clips=%d", max_clips);
@@ -505,11 +518,32 @@ extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max
     return r;
   }
   carve_workspace(p);
+  for (int i = 0; i < 2; ++i) {
+    p->aux[i] = nullptr;
+    p->ev_fork[i] = p->ev_join[i] = nullptr;
+  }
+  if (p->n_branches > 1 && !getenv("BSED_FPN_SERIAL")) {
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+        bsed_set_error("plan_create: cannot create the fpn branch streams: %s", cudaGetErrorString(cudaGetLastError()));
+        bsed_plan_destroy(p);
+        return BSED_E_CUDA;
+      }
+    }
+  }
   *out = p;
   return BSED_OK;
 }
 
 extern "C" int bsed_plan_destroy(bsed_plan p) {
+  if (!p) return BSED_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
+    if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
+    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  }
   delete p;
   return BSED_OK;
 }
@@ -624,6 +658,58 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     }
   }
 
+  // GRU stacks: rnn on the trunk output, (fpn) rnn_2 / rnn_4 on the two coarser scales; each followed by dropout.
+  // branch of a stack: its scratch set and its stream (0 = the caller's stream)
+  const bool forked = p->n_stacks > 1 && p->aux[0] != nullptr;
+  auto branch_of = [&](int s) { return p->n_stacks == 1 ? 0 : (s == p->n_stacks - 1 ? 0 : s + 1); };
+  auto stream_of = [&](int b) { return b == 0 || !forked ? st : p->aux[b - 1]; };
+  auto stack_forward = [&](int s) -> int {
+    const int T = p->stackT[s];
+    const int br = branch_of(s);
+    cudaStream_t ss = stream_of(br);
+    float* xg = wsp<float>(ws, p->off_xg[br]);
+    for (int l = 0; l < c.rnn_layers; ++l) {
+      const int In = l == 0 ? 128 : 256;
+      const float* X = l == 0 ? wsp<float>(ws, p->off_pool[p->stack_src[s]]) : wsp<float>(ws, p->off_gru_out[s][l - 1]);
+      for (int r = 0; r < n_runs; ++r) {
+        const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
+        const float* Xr = X + (size_t)runs[r].first * T * In;
+        float* xgr = xg + (size_t)runs[r].first * T * 768;
+        if (tc) {
+          for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
+            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In, In, xgr + n0, 768,
+                                (long long)runs[r].count * T, 128, In, packed + p->pk.bih[s][l] + n0, 0, sms, ss));
+        } else {
+          BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[s][l], 768, xgr, 768, runs[r].count * T, 768, In,
+                           packed + p->pk.bih[s][l], 0, ss));
+        }
+      }
+      FloatPtrs whhT, bhh;
+      for (int k = 0; k < kMaxGroups; ++k) {
+        int gi = k < n_groups ? k : 0;
+        const float* packed = wsp<float>(ws, p->off_packed[p->gpset[gi]]);
+        whhT.p[k] = packed + p->pk.whhT[s][l];
+        bhh.p[k] = packed + p->pk.bhh[s][l];
+      }
+      const bool last = l == c.rnn_layers - 1;
+      BSED_TRY(gru_forward(xg, g, whhT, bhh, wsp<float>(ws, p->off_gru_out[s][l]), last ? wsp<float>(ws, p->off_enc[s]) : nullptr,
+                           save ? wsp<float>(ws, p->off_gru_saved[s][l]) : nullptr, T, p->skeys[s], p->thresh,
+                           p->inv_keep, ss));
+    }
+    return BSED_OK;
+  };
+  // fork: a stack may start as soon as the block that feeds it is done
+  auto fork_stack = [&](int s) -> int {
+    const int br = branch_of(s);
+    if (forked && br > 0) {
+      BSED_CHECK_CUDA(cudaEventRecord(p->ev_fork[br - 1], st));
+      BSED_CHECK_CUDA(cudaStreamWaitEvent(p->aux[br - 1], p->ev_fork[br - 1], 0));
+    }
+    BSED_TRY(stack_forward(s));
+    if (forked && br > 0) BSED_CHECK_CUDA(cudaEventRecord(p->ev_join[br - 1], p->aux[br - 1]));
+    return BSED_OK;
+  };
+
   int all_ids[kMaxGroups] = {0, 1, 2, 3};
   double* stats = wsp<double>(ws, p->off_stats);
   if (train) BSED_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * kMaxBlocks * kMaxGroups * 128 * 2, st));
@@ -723,41 +809,13 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
     if (!(tc && glu_fused(L)))
       BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
                                  p->binv[i], st));
+    for (int s = 0; s < p->n_stacks; ++s)
+      if (p->stack_src[s] == i) BSED_TRY(fork_stack(s));
   }
 
-  // GRU stacks: rnn on the trunk output, (fpn) rnn_2 / rnn_4 on the two coarser scales; each followed by dropout
-  float* xg = wsp<float>(ws, p->off_xg);
-  for (int s = 0; s < p->n_stacks; ++s) {
-    const int T = p->stackT[s];
-    for (int l = 0; l < c.rnn_layers; ++l) {
-      const int In = l == 0 ? 128 : 256;
-      const float* X = l == 0 ? wsp<float>(ws, p->off_pool[p->stack_src[s]]) : wsp<float>(ws, p->off_gru_out[s][l - 1]);
-      for (int r = 0; r < n_runs; ++r) {
-        const float* packed = wsp<float>(ws, p->off_packed[runs[r].pset]);
-        const float* Xr = X + (size_t)runs[r].first * T * In;
-        float* xgr = xg + (size_t)runs[r].first * T * 768;
-        if (tc) {
-          for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
-            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In, In, xgr + n0, 768,
-                                (long long)runs[r].count * T, 128, In, packed + p->pk.bih[s][l] + n0, 0, sms, st));
-        } else {
-          BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[s][l], 768, xgr, 768, runs[r].count * T, 768, In,
-                           packed + p->pk.bih[s][l], 0, st));
-        }
-      }
-      FloatPtrs whhT, bhh;
-      for (int k = 0; k < kMaxGroups; ++k) {
-        int gi = k < n_groups ? k : 0;
-        const float* packed = wsp<float>(ws, p->off_packed[p->gpset[gi]]);
-        whhT.p[k] = packed + p->pk.whhT[s][l];
-        bhh.p[k] = packed + p->pk.bhh[s][l];
-      }
-      const bool last = l == c.rnn_layers - 1;
-      BSED_TRY(gru_forward(xg, g, whhT, bhh, wsp<float>(ws, p->off_gru_out[s][l]), last ? wsp<float>(ws, p->off_enc[s]) : nullptr,
-                           save ? wsp<float>(ws, p->off_gru_saved[s][l]) : nullptr, T, p->skeys[s], p->thresh,
-                           p->inv_keep, st));
-    }
-  }
+  // join the forked stacks before anything reads their outputs
+  if (forked)
+    for (int i = 0; i < 2; ++i) BSED_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_join[i], 0));
 
   if (!c.fpn) {
     BSED_CHECK_CUDA(cudaMemcpyAsync(enc, wsp<float>(ws, p->off_enc[0]), sizeof(float) * (size_t)B * p->Tout * 256,
@@ -834,15 +892,12 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
   const int sms = p->ctx->num_sms;
   const int target = sms * 4;
   const bool tc = p->precision == BSED_PRECISION_TF32;
-  float* wgpart = wsp<float>(ws, p->off_wgpart);
-  double* dscr = wsp<double>(ws, p->off_dscratch);
+  float* wgpart = wsp<float>(ws, p->off_wgpart[0]);
+  double* dscr = wsp<double>(ws, p->off_dscratch[0]);
 
   if (!accumulate) BSED_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * pl.total, st));
 
   // ---- gradient w.r.t. the dropout output of every GRU stack
-  float* dxg = wsp<float>(ws, p->off_dxg);
-  float* dgh = wsp<float>(ws, p->off_dgh);
-  float* dx1 = wsp<float>(ws, p->off_dx1);
   Groups one;
   one.n = 1;
   for (int k = 0; k < kMaxGroups; ++k) one.first[k] = 0, one.count[k] = k == 0 ? 1 : 0;
@@ -884,17 +939,23 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     }
   }
 
-  // ---- one GRU stack: dropout mask, layers top-down; dX of layer 0 goes to (or is added to) the gradient of the
-  // pooled block output that fed the stack
+  // ---- one GRU stack: dropout mask, layers top-down; dX of layer 0 goes to `dx_target` (= or +=).  `br` selects the
+  // scratch set, `ss` the stream (the caller's, or a plan-owned branch stream)
   int cur = 0;
   float* dpool_cur = wsp<float>(ws, p->off_dpool[cur]);
-  auto stack_backward = [&](int s, int accumulate_dx) -> int {
+  const bool forked = p->n_stacks > 1 && p->aux[0] != nullptr;
+  auto stack_backward = [&](int s, int br, cudaStream_t ss, float* dx_target, int accumulate_dx) -> int {
     const int T = p->stackT[s];
     const size_t ro = (size_t)first * T;
     const long long BTn = (long long)nb * T;
     float* denc = wsp<float>(ws, p->off_denc[s]);
+    float* dxg = wsp<float>(ws, p->off_dxg[br]);
+    float* dgh = wsp<float>(ws, p->off_dgh[br]);
+    float* dx1 = wsp<float>(ws, p->off_dx1[br]);
+    float* wgp = wsp<float>(ws, p->off_wgpart[br]);
+    double* dsc = wsp<double>(ws, p->off_dscratch[br]);
     BSED_TRY(dropout_bwd_mask(denc + ro * 256, nullptr, (long long)ro * 256, BTn * 256, p->skeys[s], p->thresh,
-                              p->inv_keep, st));
+                              p->inv_keep, ss));
     for (int l = c.rnn_layers - 1; l >= 0; --l) {
       const int In = l == 0 ? 128 : 256;
       const float* X = l == 0 ? wsp<float>(ws, p->off_pool[p->stack_src[s]]) : wsp<float>(ws, p->off_gru_out[s][l - 1]);
@@ -903,38 +964,38 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       float* dout = ((c.rnn_layers - 1 - l) % 2 == 0) ? denc : dx1;
       float* dxin = ((c.rnn_layers - 1 - l) % 2 == 0) ? dx1 : denc;
       BSED_TRY(gru_backward(dout, wsp<float>(ws, p->off_gru_saved[s][l]), out_l, packed + p->pk.whh[s][l], dxg, dgh, T, first,
-                            nb, st));
+                            nb, ss));
       for (int d = 0; d < 2; ++d) {
         if (tc) {
           // dW_hh[j][i] += sum_{b,t} dgh[b][t][j] * h[b][t -/+ 1][i] ; dW_ih[j][i] += sum_{b,t} dxg[b][t][j] * x[b][t][i]
           TcOperand Ah{dgh + ro * 768, 768, d * 384, 384}, Bh{out_l + ro * 256, 256, d * 128, 128};
-          BSED_TRY(tc_wgrad_ex(Ah, Bh, nb, T, 1, 1, d == 0 ? -1 : 1, grads + pl.whh[s][l][d], 128, 1, 0, wgpart,
-                               p->wgpart_bytes, sms, st));
+          BSED_TRY(tc_wgrad_ex(Ah, Bh, nb, T, 1, 1, d == 0 ? -1 : 1, grads + pl.whh[s][l][d], 128, 1, 0, wgp,
+                               p->wgpart_bytes, sms, ss));
           TcOperand Ai{dxg + ro * 768, 768, d * 384, 384}, Bi{X + ro * In, In, 0, In};
-          BSED_TRY(tc_wgrad_ex(Ai, Bi, nb, T, 1, 1, 0, grads + pl.wih[s][l][d], In, 1, 0, wgpart, p->wgpart_bytes, sms, st));
+          BSED_TRY(tc_wgrad_ex(Ai, Bi, nb, T, 1, 1, 0, grads + pl.wih[s][l][d], In, 1, 0, wgp, p->wgpart_bytes, sms, ss));
         } else {
           BSED_TRY(gru_whh_grad(dgh + ro * 768 + d * 384, 768, out_l + ro * 256 + d * 128, 256, d == 0 ? -1 : 1,
-                                grads + pl.whh[s][l][d], T, BTn, target, st));
+                                grads + pl.whh[s][l][d], T, BTn, target, ss));
           BSED_TRY(gemm_tn(dxg + ro * 768 + d * 384, 768, X + ro * In, In, grads + pl.wih[s][l][d], In, 1, 384, In, BTn,
-                           target, st));
+                           target, ss));
         }
       }
-      BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
-      BSED_TRY(col_stats(dxg + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
-      BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bih[s][l][0], 384, st));
-      BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bih[s][l][1], 384, st));
-      BSED_CHECK_CUDA(cudaMemsetAsync(dscr, 0, sizeof(double) * 2 * 768, st));
-      BSED_TRY(col_stats(dgh + ro * 768, nullptr, 2, one, BTn, 768, dscr, sms, st));
-      BSED_TRY(add_double_to_float(dscr, 2, grads + pl.bhh[s][l][0], 384, st));
-      BSED_TRY(add_double_to_float(dscr + 2 * 384, 2, grads + pl.bhh[s][l][1], 384, st));
-      float* dX = l == 0 ? dpool_cur + ro * 128 : dxin + ro * 256;
+      BSED_CHECK_CUDA(cudaMemsetAsync(dsc, 0, sizeof(double) * 2 * 768, ss));
+      BSED_TRY(col_stats(dxg + ro * 768, nullptr, 2, one, BTn, 768, dsc, sms, ss));
+      BSED_TRY(add_double_to_float(dsc, 2, grads + pl.bih[s][l][0], 384, ss));
+      BSED_TRY(add_double_to_float(dsc + 2 * 384, 2, grads + pl.bih[s][l][1], 384, ss));
+      BSED_CHECK_CUDA(cudaMemsetAsync(dsc, 0, sizeof(double) * 2 * 768, ss));
+      BSED_TRY(col_stats(dgh + ro * 768, nullptr, 2, one, BTn, 768, dsc, sms, ss));
+      BSED_TRY(add_double_to_float(dsc, 2, grads + pl.bhh[s][l][0], 384, ss));
+      BSED_TRY(add_double_to_float(dsc + 2 * 384, 2, grads + pl.bhh[s][l][1], 384, ss));
+      float* dX = l == 0 ? dx_target + ro * 128 : dxin + ro * 256;
       const int acc = l == 0 ? accumulate_dx : 0;
       if (tc) {
         for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
           BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l] + (size_t)n0 * 768, 768, dX + n0, In, BTn, 128,
-                              768, nullptr, acc, sms, st));
+                              768, nullptr, acc, sms, ss));
       } else {
-        BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[s][l], In, dX, In, (int)BTn, In, 768, nullptr, acc, st));
+        BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[s][l], In, dX, In, (int)BTn, In, 768, nullptr, acc, ss));
       }
     }
     return BSED_OK;
@@ -1044,12 +1105,32 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     return BSED_OK;
   };
 
-  // coarse scales first: rnn_4 -> second stage application -> (+ rnn_2) -> first application -> (+ rnn) -> trunk
-  for (int s = p->n_stacks - 1; s >= 1; --s) {
-    BSED_TRY(stack_backward(s, s != p->n_stacks - 1));
-    BSED_TRY(block_backward(p->stack_src[s]));
+  // coarse scales first: rnn_4 -> second stage application -> (+ rnn_2) -> first application -> (+ rnn) -> trunk.
+  // With branch streams, rnn and rnn_2 run their backward concurrently with that chain into their own dX buffers, which
+  // are added to the block gradients after the join.
+  if (p->n_stacks == 1) {
+    BSED_TRY(stack_backward(0, 0, st, dpool_cur, 0));
+  } else if (!forked) {
+    for (int s = p->n_stacks - 1; s >= 1; --s) {
+      BSED_TRY(stack_backward(s, 0, st, dpool_cur, s != p->n_stacks - 1));
+      BSED_TRY(block_backward(p->stack_src[s]));
+    }
+    BSED_TRY(stack_backward(0, 0, st, dpool_cur, 1));
+  } else {
+    for (int s = 0; s < p->n_stacks - 1; ++s) {   // stack s on branch s + 1
+      BSED_CHECK_CUDA(cudaEventRecord(p->ev_fork[s], st));
+      BSED_CHECK_CUDA(cudaStreamWaitEvent(p->aux[s], p->ev_fork[s], 0));
+      BSED_TRY(stack_backward(s, s + 1, p->aux[s], wsp<float>(ws, p->off_dx0[s + 1]), 0));
+      BSED_CHECK_CUDA(cudaEventRecord(p->ev_join[s], p->aux[s]));
+    }
+    BSED_TRY(stack_backward(p->n_stacks - 1, 0, st, dpool_cur, 0));
+    for (int s = p->n_stacks - 1; s >= 1; --s) {
+      BSED_TRY(block_backward(p->stack_src[s]));                        // leaves the gradient of pool[stack_src[s - 1]]
+      BSED_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_join[s - 1], 0));
+      const size_t ro = (size_t)first * p->stackT[s - 1] * 128;
+      BSED_TRY(add_f32(dpool_cur + ro, wsp<float>(ws, p->off_dx0[s]) + ro, (long long)nb * p->stackT[s - 1] * 128, st));
+    }
   }
-  BSED_TRY(stack_backward(0, p->n_stacks > 1));
   for (int i = c.n_cnn - 1; i >= 0; --i) BSED_TRY(block_backward(i));
   p->saved_valid = false;  // lin buffers now hold gradients
   return BSED_OK;
@@ -1090,9 +1171,9 @@ extern "C" int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* 
     return BSED_OK;
   }
   struct Tap { const char* n; size_t off; long long numel; } taps[] = {
-      {"denc", p->off_denc[0], Bm * p->Tout * 256}, {"dx1", p->off_dx1, Bm * p->Tout * 256},
-      {"dxg", p->off_dxg, Bm * p->Tout * 768},   {"dgh", p->off_dgh, Bm * p->Tout * 768},
-      {"xg", p->off_xg, Bm * p->Tout * 768},     {"enc", p->off_enc[0], Bm * p->Tout * 256},
+      {"denc", p->off_denc[0], Bm * p->Tout * 256}, {"dx1", p->off_dx1[0], Bm * p->Tout * 256},
+      {"dxg", p->off_dxg[0], Bm * p->Tout * 768},   {"dgh", p->off_dgh[0], Bm * p->Tout * 768},
+      {"xg", p->off_xg[0], Bm * p->Tout * 768},     {"enc", p->off_enc[0], Bm * p->Tout * 256},
       {"dpool0", p->off_dpool[0], Bm * p->L[0].prows * p->L[0].Cout},
       {"dpool1", p->off_dpool[1], Bm * p->L[0].prows * p->L[0].Cout},
       {"saved0", p->off_gru_saved[0][0], Bm * p->Tout * 1024}, {"saved1", p->off_gru_saved[0][1], Bm * p->Tout * 1024}};
