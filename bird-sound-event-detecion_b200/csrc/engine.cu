@@ -94,6 +94,12 @@ struct bsed_crnn_plan {
   int n_branches;
   cudaStream_t aux[2];
   cudaEvent_t ev_fork[2], ev_join[2];
+  // conv weight gradients are off the backward critical path (only the optimiser needs them): they run on a plan-owned
+  // side stream, reading a double-buffered dY, while the caller's stream continues with the data gradient and the
+  // next block's HBM-bound gate / BatchNorm kernels
+  cudaStream_t side;
+  cudaEvent_t ev_dy[2], ev_wg[2];
+  size_t off_dxn2, off_wgpart_side;
   size_t off_cat[2], off_y2, off_dcat, off_dy2;   // fpn merge: cat[0] (B,156,512), cat[1] (B,313,512), y2 (B,156,256)
   size_t off_G, off_dscratch[kMaxStacks], off_wgpart[kMaxStacks], off_bsums, off_bntab;
   size_t wgpart_bytes;
@@ -348,6 +354,7 @@ void carve_workspace(bsed_crnn_plan* p) {
     p->off_denc[s] = takeb(sizeof(float) * BTs * 256);
   }
   p->off_dxn = takeb(sizeof(float) * max_full);
+  p->off_dxn2 = takeb(sizeof(float) * max_full);
   p->off_dpool[0] = takeb(sizeof(float) * max_pool);
   p->off_dpool[1] = takeb(sizeof(float) * max_pool);
   for (int b = 0; b < p->n_branches; ++b) {
@@ -371,6 +378,7 @@ void carve_workspace(bsed_crnn_plan* p) {
     p->off_dscratch[b] = takeb(sizeof(double) * 2 * 768);
     p->off_wgpart[b] = takeb(p->wgpart_bytes);
   }
+  p->off_wgpart_side = takeb(p->wgpart_bytes);
   p->ws_bytes = o;
 }
 
@@ -520,7 +528,19 @@ extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max
   carve_workspace(p);
   for (int i = 0; i < 2; ++i) {
     p->aux[i] = nullptr;
-    p->ev_fork[i] = p->ev_join[i] = nullptr;
+    p->ev_fork[i] = p->ev_join[i] = p->ev_dy[i] = p->ev_wg[i] = nullptr;
+  }
+  p->side = nullptr;
+  if (!getenv("BSED_WGRAD_INLINE")) {
+    bool ok = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&p->ev_dy[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p->ev_wg[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      bsed_set_error("plan_create: cannot create the weight-gradient side stream: %s", cudaGetErrorString(cudaGetLastError()));
+      bsed_plan_destroy(p);
+      return BSED_E_CUDA;
+    }
   }
   if (p->n_branches > 1 && !getenv("BSED_FPN_SERIAL")) {
     for (int i = 0; i < 2; ++i) {
@@ -543,7 +563,10 @@ extern "C" int bsed_plan_destroy(bsed_plan p) {
     if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
     if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+    if (p->ev_dy[i]) cudaEventDestroy(p->ev_dy[i]);
+    if (p->ev_wg[i]) cudaEventDestroy(p->ev_wg[i]);
   }
+  if (p->side) cudaStreamDestroy(p->side);
   delete p;
   return BSED_OK;
 }
@@ -1002,11 +1025,20 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
   };
 
   // ---- one conv block: consumes dpool_cur (gradient of its pooled output), leaves the gradient of its input there
-  float* dxn = wsp<float>(ws, p->off_dxn);
+  float* dxn_buf[2] = {wsp<float>(ws, p->off_dxn), wsp<float>(ws, p->off_dxn2)};
+  float* wgpart_side = wsp<float>(ws, p->off_wgpart_side);
+  bool side_pending[2] = {false, false};
+  const bool use_side = p->side != nullptr;
   double* stats2 = wsp<double>(ws, p->off_stats2);
   float* G = wsp<float>(ws, p->off_G);
   auto block_backward = [&](int i) -> int {
     const LayerGeom& L = p->L[i];
+    const int kb = use_side ? (i & 1) : 0;      // dY buffer of this block
+    float* dxn = dxn_buf[kb];
+    if (side_pending[kb]) {                     // the weight gradient that last read this buffer must be done
+      BSED_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_wg[kb], 0));
+      side_pending[kb] = false;
+    }
     float* xhat = wsp<float>(ws, p->off_xhat[i]);
     float* lin = wsp<float>(ws, p->off_lin[i]);
     BNPtrs bn = make_bn_ptrs(p, ws, i, ids, n);
@@ -1081,15 +1113,26 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     }
     // conv bias gradient: sum_p dY = gamma*rstd*(sum dxn - n*mean(dxn) - mean(dxn*xhat) * sum xhat) = 0 exactly behind a
     // train-mode BatchNorm (the reference computes rounding noise here); grads[conv_b] keeps its zero / accumulated value
+    // the conv weight gradient of this block: on the side stream once dY is final
+    cudaStream_t wst = use_side ? p->side : st;
+    float* wgp = use_side ? wgpart_side : wgpart;
+    if (use_side) {
+      BSED_CHECK_CUDA(cudaEventRecord(p->ev_dy[kb], st));
+      BSED_CHECK_CUDA(cudaStreamWaitEvent(p->side, p->ev_dy[kb], 0));
+    }
     if (i > 0) {
       const float* xin = wsp<float>(ws, p->off_pool[i - 1]) + (size_t)first * L.rows * L.Cin;
       const bool tc_w32 = L.Cin % 32 == 0 && L.F <= 64 && 64 % L.F == 0;
       const bool tc_w16 = L.Cin == 16 && L.F % 2 == 0 && L.F <= 128 && 64 % (L.F / 2) == 0;
       if (tc && L.Cout % 32 == 0 && (tc_w32 || tc_w16))
         BSED_TRY(tc_wgrad(xin, dxn + off, grads + pl.conv_w[i], (long long)L.Cin * 9, 9, 1, nb, L.T, L.F, L.Cin, L.Cout, 9,
-                          wgpart, p->wgpart_bytes, sms, st));
+                          wgp, p->wgpart_bytes, sms, wst));
       else
-        BSED_TRY(conv3x3_wgrad(xin, dxn + off, grads + pl.conv_w[i], nb, L.T, L.F, L.Cin, L.Cout, target, st));
+        BSED_TRY(conv3x3_wgrad(xin, dxn + off, grads + pl.conv_w[i], nb, L.T, L.F, L.Cin, L.Cout, target, wst));
+      if (use_side) {
+        BSED_CHECK_CUDA(cudaEventRecord(p->ev_wg[kb], p->side));
+        side_pending[kb] = true;
+      }
       cur ^= 1;
       float* dnext = wsp<float>(ws, p->off_dpool[cur]);
       if (tc)
@@ -1100,7 +1143,11 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
                             L.Cin, nullptr, 0, st));
       dpool_cur = dnext;
     } else {
-      BSED_TRY(conv0_wgrad(p->x_in, dxn, grads + pl.conv_w[0], first, nb, L.T, L.F, L.Cout, sms, st));
+      BSED_TRY(conv0_wgrad(p->x_in, dxn, grads + pl.conv_w[0], first, nb, L.T, L.F, L.Cout, sms, wst));
+      if (use_side) {
+        BSED_CHECK_CUDA(cudaEventRecord(p->ev_wg[kb], p->side));
+        side_pending[kb] = true;
+      }
     }
     return BSED_OK;
   };
@@ -1132,6 +1179,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
     }
   }
   for (int i = c.n_cnn - 1; i >= 0; --i) BSED_TRY(block_backward(i));
+  for (int k = 0; k < 2; ++k)   // join: the gradient buffer is complete when the caller's stream gets here
+    if (side_pending[k]) BSED_CHECK_CUDA(cudaStreamWaitEvent(st, p->ev_wg[k], 0));
   p->saved_valid = false;  // lin buffers now hold gradients
   return BSED_OK;
 }
@@ -1196,7 +1245,7 @@ extern "C" int bsed_plan_debug_tensor(bsed_plan p, void* workspace, const char* 
         return BSED_OK;
       }
   }
-  if (s == "dxn") {
+  if (s == "dxn") {   // dY of block 0 (even blocks use the first buffer)
     *ptr = wsp<float>(workspace, p->off_dxn);
     *numel = Bm * p->L[0].rows * p->L[0].Cout;
     return BSED_OK;
