@@ -60,32 +60,39 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
         r[0] = r[1] = r[2] = 0.f;
       }
     };
-    float r0[3], r1[3], r2[3];
-    load_row(t0 - 1, r0);
-    load_row(t0, r1);
+    // rows t-1 .. t+4 of the window: the loads of four output rows are issued together, ahead of their FMAs
+    float rw[6][3];
+    load_row(t0 - 1, rw[0]);
+    load_row(t0, rw[1]);
     float* yp = y + (((size_t)clip * T + t0) * F + col) * Cout + q * 4;
-    for (int t = t0; t < t1; ++t) {
-      load_row(t + 1, r2);
-      float o[4];
+    for (int t = t0; t < t1; t += 4) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a = br[j];
+      for (int u = 0; u < 4; ++u) load_row(t + 1 + u, rw[2 + u]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a = fmaf(r0[k], wr[j][k], a);        // taps in the reference's (kh, kw) order
+      for (int u = 0; u < 4; ++u) {
+        if (t + u < t1) {
+          float o[4];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a = fmaf(r1[k], wr[j][3 + k], a);
+          for (int j = 0; j < 4; ++j) {
+            float a = br[j];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a = fmaf(r2[k], wr[j][6 + k], a);
-        o[j] = a;
-        s1[j] += a;
-        s2[j] = fmaf(a, a, s2[j]);
+            for (int k = 0; k < 3; ++k) a = fmaf(rw[u][k], wr[j][k], a);        // taps in the reference's (kh, kw) order
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a = fmaf(rw[u + 1][k], wr[j][3 + k], a);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a = fmaf(rw[u + 2][k], wr[j][6 + k], a);
+            o[j] = a;
+            s1[j] += a;
+            s2[j] = fmaf(a, a, s2[j]);
+          }
+          *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+          yp += (size_t)F * Cout;
+        }
       }
-      *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
-      yp += (size_t)F * Cout;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        r0[k] = r1[k];
-        r1[k] = r2[k];
+        rw[0][k] = rw[4][k];
+        rw[1][k] = rw[5][k];
       }
     }
   }
@@ -149,28 +156,34 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
         r[0] = r[1] = r[2] = 0.f;
       }
     };
-    float r0[3], r1[3], r2[3];
-    load_row(t0 - 1, r0);
-    load_row(t0, r1);
+    float rw[6][3];
+    load_row(t0 - 1, rw[0]);
+    load_row(t0, rw[1]);
     const float* dp = dY + (((size_t)clip * T + t0) * F + col) * Cout + q * 4;
-    float4 d = *reinterpret_cast<const float4*>(dp);
-    for (int t = t0; t < t1; ++t) {
-      load_row(t + 1, r2);
-      const float dv[4] = {d.x, d.y, d.z, d.w};
-      dp += (size_t)F * Cout;
-      if (t + 1 < t1) d = *reinterpret_cast<const float4*>(dp);     // next row's gradient, ahead of this row's FMAs
+    for (int t = t0; t < t1; t += 4) {
+      float4 d[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int u = 0; u < 4; ++u) {     // four rows of gradient and of input in flight before the FMAs
+        load_row(t + 1 + u, rw[2 + u]);
+        d[u] = t + u < t1 ? *reinterpret_cast<const float4*>(dp + (size_t)u * F * Cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      dp += (size_t)4 * F * Cout;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          acc[j][k] = fmaf(dv[j], r0[k], acc[j][k]);
-          acc[j][3 + k] = fmaf(dv[j], r1[k], acc[j][3 + k]);
-          acc[j][6 + k] = fmaf(dv[j], r2[k], acc[j][6 + k]);
-        }
+      for (int u = 0; u < 4; ++u) {
+        const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            acc[j][k] = fmaf(dv[j], rw[u][k], acc[j][k]);
+            acc[j][3 + k] = fmaf(dv[j], rw[u + 1][k], acc[j][3 + k]);
+            acc[j][6 + k] = fmaf(dv[j], rw[u + 2][k], acc[j][6 + k]);
+          }
+      }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        r0[k] = r1[k];
-        r1[k] = r2[k];
+        rw[0][k] = rw[4][k];
+        rw[1][k] = rw[5][k];
       }
     }
   }
