@@ -210,6 +210,11 @@ class ShiftConsistencyTrainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.dropout_seed, self.opt_step, self.pg = dropout_seed, 0, process_group
         self.ptr = int(pooling_time_ratio)
+        self.world = torch.distributed.get_world_size(process_group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self.dp = None
+        if self.world > 1 and os.environ.get("BSED_DP", "fused").lower() == "fused":
+            self.dp = shard.FusedDataParallel.create(self.grads, self.params, self.ema_params, process_group)
         mk = lambda B: engine.Plan(engine.make_cfg(**model.cfg_kwargs), max_clips=B, device=dev,
                                    precision=precision or model.precision)
         self.planA, self.planB, self.planC = mk(3 * n), mk(4 * n), mk(2 * n)
@@ -307,11 +312,15 @@ class ShiftConsistencyTrainer:
         gc = self.grads[:self.n_crnn]
         self.planA.backward(0b011, dA, gc, accumulate=False)
         self.planB.backward(0b1111, dB, gc, accumulate=True)
-        grad_scale = shard.allreduce_gradients(self.grads, self.pg)
         self.opt_step += 1
-        engine.opt_ema_step(self.params, self.grads, self.m, self.v, self.ema_params, step=self.opt_step,
-                            ema_step=global_step + 1, kind="adam", lr=self.lr, betas=self.betas, eps=self.eps,
-                            weight_decay=self.weight_decay, grad_scale=grad_scale)
+        if self.dp is not None:    # reduce-scatter over peer memory + Adam + EMA + all-gather in one kernel
+            self.dp.opt_ema_step(self.m, self.v, step=self.opt_step, ema_step=global_step + 1, kind="adam", lr=self.lr,
+                                 betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        else:
+            grad_scale = shard.allreduce_gradients(self.grads, self.pg)
+            engine.opt_ema_step(self.params, self.grads, self.m, self.v, self.ema_params, step=self.opt_step,
+                                ema_step=global_step + 1, kind="adam", lr=self.lr, betas=self.betas, eps=self.eps,
+                                weight_decay=self.weight_decay, grad_scale=grad_scale)
         engine.ema_buffers(sbn, tbn, snbt, tnbt, global_step + 1)
         self.last = dict(strong=Ss, weak=Sw, losses=losses)
         return losses
