@@ -44,7 +44,8 @@ def test_workspace_and_call_order_are_checked():
 
 def test_bad_configurations_are_rejected_at_plan_creation():
     from bsed_b200 import _lib, engine
-    for kw, frag in ((dict(nb_filters=(16, 32, 64, 128, 128, 128, 96)), "filters"),
+    for kw, frag in ((dict(nb_filters=(16, 32, 64, 128, 128, 128, 96)), "128 channels"),
+                     (dict(nb_filters=(16, 32, 64, 128, 128, 128, 200)), "filters"),
                      (dict(n_RNN_cell=64), "rnn_hidden"),
                      (dict(pooling=((2, 2), (2, 2), (1, 2), (1, 2), (1, 2), (1, 2), (1, 1))), "frequency axis"),
                      (dict(nclass=21), "n_class")):
