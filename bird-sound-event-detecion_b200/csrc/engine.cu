@@ -94,9 +94,10 @@ struct bsed_crnn_plan {
   int n_branches;
   cudaStream_t aux[2];
   cudaEvent_t ev_fork[2], ev_join[2];
-  // conv weight gradients are off the backward critical path (only the optimiser needs them): they run on a plan-owned
-  // side stream, reading a double-buffered dY, while the caller's stream continues with the data gradient and the
-  // next block's HBM-bound gate / BatchNorm kernels
+  // conv weight gradients are off the backward critical path (only the optimiser needs them): with BSED_WGRAD_ASIDE=1
+  // they run on a plan-owned side stream, reading a double-buffered dY, while the caller's stream continues with the
+  // data gradient and the next block's gate / BatchNorm kernels.  Opt-in: both sides fill the GPU, the step gains 0.6 %
+  // (CRNN) to 2 % (CRNN_fpn), and kernels timed on the caller's stream slow down under the sharing
   cudaStream_t side;
   cudaEvent_t ev_dy[2], ev_wg[2];
   size_t off_dxn2, off_wgpart_side;
@@ -531,7 +532,7 @@ extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max
     p->ev_fork[i] = p->ev_join[i] = p->ev_dy[i] = p->ev_wg[i] = nullptr;
   }
   p->side = nullptr;
-  if (!getenv("BSED_WGRAD_INLINE")) {
+  if (getenv("BSED_WGRAD_ASIDE")) {
     bool ok = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
       ok = cudaEventCreateWithFlags(&p->ev_dy[i], cudaEventDisableTiming) == cudaSuccess &&
