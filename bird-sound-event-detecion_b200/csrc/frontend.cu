@@ -392,6 +392,9 @@ int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_i
               cudaStream_t st) {
   BSED_REQUIRE(B > 0 && t_in > 0 && frames > 0, "amp_to_db: B=%d t_in=%d frames=%d", B, t_in, frames);
   BSED_REQUIRE((sc_mean == nullptr) == (sc_std == nullptr), "amp_to_db: scaler mean/std must come together");
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  BSED_REQUIRE(aligned16(mel) && aligned16(noise) && aligned16(out) && aligned16(sc_mean) && aligned16(sc_std) && aligned16(ws),
+               "amp_to_db: buffers must be 16-byte aligned (float4 accesses)");
   const size_t need = sizeof(double) * (size_t)B * (kNMels + 1);
   if (ws_bytes < need) {
     bsed_set_error("amp_to_db: workspace %zu < %zu", ws_bytes, need);
