@@ -58,6 +58,8 @@ class FusedDataParallel:
         if self.world > 8:
             raise RuntimeError("fused data-parallel step supports up to 8 ranks")
         self.device = grads.device
+        if self.device.type != "cuda":
+            raise RuntimeError("peer-memory exchange needs CUDA buffers")
         self.h = _lib.handle(self.device.index)
         self.grads, self.params, self.ema = grads, params, ema
         assert params.numel() == grads.numel() and (ema is None or ema.numel() == grads.numel())
@@ -110,7 +112,8 @@ class FusedDataParallel:
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=grads.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        torch.cuda.synchronize(grads.device)
+        if grads.is_cuda:
+            torch.cuda.synchronize(grads.device)
         return obj if int(flag.item()) == 1 else None
 
     def opt_ema_step(self, m, v, step, ema_step, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,

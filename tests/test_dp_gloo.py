@@ -34,6 +34,11 @@ def _worker(rank, world, port, out):
         ev = [(rank, i, i + 1) for i in range(rank + 1)]
         allev = shard.gather_in_rank_order(ev)
         torch.save(allev, os.path.join(out, f"e{rank}.pt"))
+        # the fused peer-memory step cannot be set up without GPUs: every rank must get None (and none may hang), so the
+        # trainers fall back to the all-reduce path together
+        buf = torch.zeros(16)
+        dp = shard.FusedDataParallel.create(buf, buf.clone(), None, None)
+        torch.save(dp is None, os.path.join(out, f"d{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -47,3 +52,4 @@ def test_gradient_exchange_and_gather_world2(tmp_path):
         assert torch.allclose(g, torch.arange(10, dtype=torch.float32) * 1.5)
         ev = torch.load(os.path.join(str(tmp_path), f"e{r}.pt"))
         assert ev == [(0, 0, 1), (1, 0, 1), (1, 1, 2)]
+        assert torch.load(os.path.join(str(tmp_path), f"d{r}.pt")) is True
