@@ -912,7 +912,6 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
   for (int k = 0; k < n; ++k) nb += gb.count[k];
   const float* params = p->gparams[ids[0]];
   const float* packed = wsp<float>(ws, p->off_packed[p->gpset[ids[0]]]);
-  const int T = p->Tout;
   const int sms = p->ctx->num_sms;
   const int target = sms * 4;
   const bool tc = p->precision == BSED_PRECISION_TF32;
