@@ -28,6 +28,7 @@ SYMBOLS = [
     "bsed_disc_param_count", "bsed_disc_bn_buffer_count", "bsed_disc_workspace_bytes", "bsed_disc_forward",
     "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision", "bsed_loss_terms", "bsed_roll_clips",
     "bsed_ipc_export", "bsed_ipc_open", "bsed_ipc_close", "bsed_dp_opt_ema_step",
+    "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -119,6 +120,11 @@ def load():
         proto("bsed_ipc_open", i32, vp, C.c_char_p, u64, P(vp))
         proto("bsed_ipc_close", i32, vp, vp, u64)
         proto("bsed_dp_opt_ema_step", i32, vp, i32, i32, P(vp), P(vp), P(vp), P(vp), i64, vp, vp, i64, P(OptCfg), vp)
+        proto("bsed_im2col_nhwc", i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp)
+        proto("bsed_add_relu", i32, vp, vp, vp, i64, vp)
+        proto("bsed_maxpool_nhwc", i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp)
+        proto("bsed_avgpool_nhwc", i32, vp, vp, vp, i32, i32, i32, vp)
+        proto("bsed_sigmoid_rows", i32, vp, vp, i32, vp, i32, i32, vp)
         proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
         proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)

@@ -360,3 +360,55 @@ def conv3x3_wgrad(x, dy, tensor_cores=False):
     check(lib.bsed_conv3x3_wgrad(h, ptr(x.contiguous()), ptr(dy.contiguous()), ptr(dw), B, T, F, Cin, Cout,
                                  int(bool(tensor_cores)), ptr(ws), wsb, stream_ptr()), "bsed_conv3x3_wgrad")
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# channels-last building blocks of the ResNet-18 tagger's inference path (csrc/resnet.cu)
+# ------------------------------------------------------------------------------------------------
+def im2col_nhwc(x, kh, kw, sh, sw, ph, pw, k_pad):
+    """x (B, H, W, Cin) -> (col (B*Ho*Wo, k_pad), Ho, Wo); column order (ky, kx, ci), zero-filled up to k_pad."""
+    lib = _lib.load()
+    h = _lib.handle(x.device.index)
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    col = torch.empty(B * Ho * Wo, k_pad, dtype=torch.float32, device=x.device)
+    check(lib.bsed_im2col_nhwc(h, ptr(x), ptr(col), B, H, W, Cin, kh, kw, sh, sw, ph, pw, Ho, Wo, k_pad, stream_ptr()),
+          "bsed_im2col_nhwc")
+    return col, Ho, Wo
+
+
+def add_relu(y, residual=None):
+    lib = _lib.load()
+    check(lib.bsed_add_relu(_lib.handle(y.device.index), ptr(y), ptr(residual), y.numel(), stream_ptr()), "bsed_add_relu")
+    return y
+
+
+def maxpool_nhwc(x, k, s, p):
+    lib = _lib.load()
+    x = x.contiguous()
+    B, H, W, Cn = x.shape
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    y = torch.empty(B, Ho, Wo, Cn, dtype=torch.float32, device=x.device)
+    check(lib.bsed_maxpool_nhwc(_lib.handle(x.device.index), ptr(x), ptr(y), B, H, W, Cn, k, s, p, Ho, Wo, stream_ptr()),
+          "bsed_maxpool_nhwc")
+    return y
+
+
+def avgpool_nhwc(x):
+    """(B, H, W, C) -> (B, C) mean over the pixels."""
+    lib = _lib.load()
+    x = x.contiguous()
+    B, H, W, Cn = x.shape
+    y = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
+    check(lib.bsed_avgpool_nhwc(_lib.handle(x.device.index), ptr(x), ptr(y), B, H * W, Cn, stream_ptr()), "bsed_avgpool_nhwc")
+    return y
+
+
+def sigmoid_rows(logits, n_cols):
+    lib = _lib.load()
+    rows, ld = logits.shape
+    out = torch.empty(rows, n_cols, dtype=torch.float32, device=logits.device)
+    check(lib.bsed_sigmoid_rows(_lib.handle(logits.device.index), ptr(logits), ld, ptr(out), rows, n_cols, stream_ptr()),
+          "bsed_sigmoid_rows")
+    return out

@@ -318,6 +318,26 @@ int bsed_disc_backward(bsed_handle h, const float* params, const float* prob, co
 int bsed_disc_bce(bsed_handle h, const float* prob, const float* label, int B, float* loss, float* d_prob, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ResNet-18 weak tagger, inference path.    src/audio_tagging_system_cnn.py:50-64 (Net_resnet = torchvision resnet18,
+ * conv1 -> Conv2d(1,64,7,2,3,bias=False), fc -> Linear(512,20), sigmoid), src/audio_tagging_inference.py:123-133,289-316
+ * In eval mode each BatchNorm folds into the preceding convolution (host, at load time); a stage then is
+ *   bsed_im2col_nhwc -> bsed_gemm_nt_tc / bsed_gemm_nn (+ bias) -> bsed_add_relu (with the residual for a block's
+ * second convolution), plus the stem's max-pool, the global average pool and the sigmoid.  Tensors are channels-last.
+ *   im2col: col[(b*Ho+ho)*Wo+wo][(ky*kw+kx)*Cin+ci] = x[b][ho*sh-ph+ky][wo*sw-pw+kx][ci] (0 outside), columns up to
+ *           Kpad (a multiple of 4, >= kh*kw*Cin) zero-filled; Ho = (H+2ph-kh)/sh+1, Wo likewise.
+ *   add_relu: y = relu(y + residual) in place, residual may be NULL, n % 4 == 0.
+ *   maxpool: nn.MaxPool2d(k, s, p); avgpool: AdaptiveAvgPool2d(1) over the HW pixels; sigmoid_rows: out[r][c] =
+ *           sigmoid(logits[r*ld + c]), c < C.
+ * ------------------------------------------------------------------------------------------ */
+int bsed_im2col_nhwc(bsed_handle h, const float* x, float* col, int B, int H, int W, int Cin, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int Ho, int Wo, int Kpad, void* stream);
+int bsed_add_relu(bsed_handle h, float* y, const float* residual, int64_t n, void* stream);
+int bsed_maxpool_nhwc(bsed_handle h, const float* x, float* y, int B, int H, int W, int C, int k, int s, int p, int Ho,
+                      int Wo, void* stream);
+int bsed_avgpool_nhwc(bsed_handle h, const float* x, float* y, int B, int HW, int C, void* stream);
+int bsed_sigmoid_rows(bsed_handle h, const float* logits, int ld, float* out, int rows, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).
  *   bsed_launch_count: kernels this library has launched in this process.
  *   bsed_profile_begin(cls) .. bsed_profile_end: CUDA-event time, summed over the launches of one
