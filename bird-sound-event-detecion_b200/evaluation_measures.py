@@ -101,15 +101,19 @@ def get_predictions(model, dataloader, decoder, pooling_time_ratio=1, thresholds
 
 
 def get_weak_predictions(model, predictor, dataloader, labels=None, threshold=0.5):
-    """Weak pseudo-labelling loop of src/audio_tagging.py:256-283: weak >= threshold -> comma-joined
-    labels per file (rows only for files with at least one label)."""
+    """Weak pseudo-labelling loop of src/audio_tagging.py:256-283 (CRNN + Predictor) and of
+    src/audio_tagging_inference.py:289-316 (Net_resnet, `predictor=None`: the model returns the weak probabilities
+    itself): weak >= threshold -> comma-joined labels per file (rows only for files with at least one label)."""
     labels = labels or cfg.bird_list
     rows = []
-    dev = model._flat.device
+    dev = next(model.parameters()).device
     for (((input_data, _e), _t), paths) in dataloader:
         with torch.no_grad():
-            enc, _ = model(input_data.to(dev, non_blocking=True))
-            _, weak = predictor(enc)
+            if predictor is None:
+                weak = model(input_data.to(dev, non_blocking=True))
+            else:
+                enc, _ = model(input_data.to(dev, non_blocking=True))
+                _, weak = predictor(enc)
         mask = (weak >= threshold).cpu().numpy()
         for j, p in enumerate(paths):
             names = [labels[c] for c in np.nonzero(mask[j])[0]]

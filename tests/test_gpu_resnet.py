@@ -72,3 +72,10 @@ def test_weak_label_rows_from_the_tagger():
     assert np.array_equal((p >= 0.5)[safe], (q >= 0.5)[safe])
     rows = [",".join(cfg.bird_list[c] for c in np.nonzero(pi >= 0.5)[0]) for pi in p]
     assert len(rows) == 3
+    # the reference-facing loop: loader of (((x, x_ema), target), paths) -> DataFrame(filename, event_labels)
+    from bsed_b200.evaluation_measures import get_weak_predictions
+    loader = [(((x[:2], x[:2]), None), ["a.wav", "b.wav"]), (((x[2:], x[2:]), None), ["c.wav"])]
+    df = get_weak_predictions(m, None, loader)
+    assert list(df.columns) == ["filename", "event_labels"]
+    want = {f: r for f, r in zip(["a.wav", "b.wav", "c.wav"], rows) if r}
+    assert dict(zip(df["filename"], df["event_labels"])) == want
