@@ -29,6 +29,8 @@ SYMBOLS = [
     "bsed_disc_backward", "bsed_disc_bce", "bsed_disc_set_precision", "bsed_loss_terms", "bsed_roll_clips",
     "bsed_ipc_export", "bsed_ipc_open", "bsed_ipc_close", "bsed_dp_opt_ema_step",
     "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
+    "bsed_bn_rows_workspace_bytes", "bsed_bn_rows_train", "bsed_bn_rows_backward", "bsed_col2im_nhwc",
+    "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -125,6 +127,13 @@ def load():
         proto("bsed_maxpool_nhwc", i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp)
         proto("bsed_avgpool_nhwc", i32, vp, vp, vp, i32, i32, i32, vp)
         proto("bsed_sigmoid_rows", i32, vp, vp, i32, vp, i32, i32, vp)
+        proto("bsed_bn_rows_workspace_bytes", sz, i32)
+        proto("bsed_bn_rows_train", i32, vp, vp, i64, i32, vp, vp, f32, f32, vp, vp, vp, vp, i32, vp, vp, vp, sz, vp)
+        proto("bsed_bn_rows_backward", i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, sz, vp)
+        proto("bsed_col2im_nhwc", i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp)
+        proto("bsed_maxpool_nhwc_backward", i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp)
+        proto("bsed_avgpool_nhwc_backward", i32, vp, vp, vp, i32, i32, i32, vp)
+        proto("bsed_sigmoid_rows_backward", i32, vp, vp, vp, vp, i32, i32, i32, vp)
         proto("bsed_opt_ema_step", i32, vp, vp, vp, vp, vp, vp, i64, P(OptCfg), vp)
         proto("bsed_ema_buffers", i32, vp, vp, vp, i64, vp, vp, i32, f32, i64, vp)
         proto("bsed_gemm_nn", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)

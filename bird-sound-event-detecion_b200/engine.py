@@ -412,3 +412,72 @@ def sigmoid_rows(logits, n_cols):
     check(lib.bsed_sigmoid_rows(_lib.handle(logits.device.index), ptr(logits), ld, ptr(out), rows, n_cols, stream_ptr()),
           "bsed_sigmoid_rows")
     return out
+
+
+def bn_rows_train(x, gamma, beta, run_mean, run_var, nbt, residual=None, relu=True, eps=1e-5, momentum=0.1):
+    """Train-mode BatchNorm over the rows of x [M][C] (x becomes xhat in place) -> (y, mean_rstd [2][C])."""
+    lib = _lib.load()
+    h = _lib.handle(x.device.index)
+    M, Cn = x.shape
+    y = torch.empty_like(x)
+    mr = torch.empty(2, Cn, dtype=torch.float32, device=x.device)
+    wsb = int(lib.bsed_bn_rows_workspace_bytes(Cn))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    check(lib.bsed_bn_rows_train(h, ptr(x), M, Cn, ptr(gamma), ptr(beta), float(eps), float(momentum), ptr(run_mean), ptr(run_var),
+                                 ptr(nbt), ptr(residual), int(bool(relu)), ptr(y), ptr(mr), ptr(ws), wsb, stream_ptr()),
+          "bsed_bn_rows_train")
+    return y, mr
+
+
+def bn_rows_backward(dy, y, xhat, gamma, mean_rstd, d_gamma, d_beta, want_residual_grad=False):
+    """dy [M][C] becomes the gradient w.r.t. the BatchNorm input (in place); returns the residual-branch gradient or None."""
+    lib = _lib.load()
+    h = _lib.handle(dy.device.index)
+    M, Cn = dy.shape
+    d_res = torch.empty_like(dy) if want_residual_grad else None
+    wsb = int(lib.bsed_bn_rows_workspace_bytes(Cn))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
+    check(lib.bsed_bn_rows_backward(h, ptr(dy), ptr(y), ptr(xhat), M, Cn, ptr(gamma), ptr(mean_rstd), ptr(d_gamma), ptr(d_beta),
+                                    ptr(d_res), ptr(ws), wsb, stream_ptr()), "bsed_bn_rows_backward")
+    return d_res
+
+
+def col2im_nhwc(dcol, shape, kh, kw, sh, sw, ph, pw, k_pad, out=None):
+    """Transpose of im2col_nhwc: dcol (B*Ho*Wo, k_pad) -> dx (B, H, W, Cin); `out` given: accumulate into it."""
+    lib = _lib.load()
+    B, H, W, Cin = shape
+    Ho, Wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    acc = out is not None
+    if out is None:
+        out = torch.empty(B, H, W, Cin, dtype=torch.float32, device=dcol.device)
+    check(lib.bsed_col2im_nhwc(_lib.handle(dcol.device.index), ptr(dcol), ptr(out), B, H, W, Cin, kh, kw, sh, sw, ph, pw, Ho, Wo,
+                               k_pad, int(acc), stream_ptr()), "bsed_col2im_nhwc")
+    return out
+
+
+def maxpool_nhwc_backward(x, dy, k, s, p):
+    lib = _lib.load()
+    B, H, W, Cn = x.shape
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    dx = torch.empty_like(x)
+    check(lib.bsed_maxpool_nhwc_backward(_lib.handle(x.device.index), ptr(x), ptr(dy.contiguous()), ptr(dx), B, H, W, Cn, k, s, p,
+                                         Ho, Wo, stream_ptr()), "bsed_maxpool_nhwc_backward")
+    return dx
+
+
+def avgpool_nhwc_backward(dy, shape):
+    lib = _lib.load()
+    B, H, W, Cn = shape
+    dx = torch.empty(B, H, W, Cn, dtype=torch.float32, device=dy.device)
+    check(lib.bsed_avgpool_nhwc_backward(_lib.handle(dy.device.index), ptr(dy.contiguous()), ptr(dx), B, H * W, Cn, stream_ptr()),
+          "bsed_avgpool_nhwc_backward")
+    return dx
+
+
+def sigmoid_rows_backward(p, dp, ld):
+    lib = _lib.load()
+    rows, Cn = p.shape
+    dl = torch.empty(rows, ld, dtype=torch.float32, device=p.device)
+    check(lib.bsed_sigmoid_rows_backward(_lib.handle(p.device.index), ptr(p.contiguous()), ptr(dp.contiguous()), ptr(dl), rows, Cn,
+                                         ld, stream_ptr()), "bsed_sigmoid_rows_backward")
+    return dl

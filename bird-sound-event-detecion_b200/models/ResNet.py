@@ -4,12 +4,17 @@
     model = Net_resnet(pretrained=False); model.load_state_dict(state["model"]["state_dict"]); model.eval()
     pred_weak = model(x)            x: (B, 1, 1255, 128) -> (B, 20)            (src/audio_tagging_inference.py:123-133, 295)
 
-INFERENCE path only (what audio_tagging_inference.py runs to write the pseudo-label TSV): in eval mode every BatchNorm is
-an affine map, folded here into the preceding convolution when the weights are (re)loaded; each convolution then runs in
-libbsed.so as im2col -> GEMM (+ bias) -> [+ residual] -> ReLU on channels-last tensors.  State-dict keys equal the
-reference's (`resnet.conv1.weight`, `resnet.bn1.running_mean`, `resnet.layer2.0.downsample.0.weight`, `resnet.fc.bias`, ...),
-so its checkpoints load.  Training this model is not built (forward in train() mode raises); `pretrained=True` needs
-torchvision's ImageNet weights, which are not reachable from here, and raises as well.
+Every convolution runs in libbsed.so as im2col -> GEMM on channels-last tensors (csrc/resnet.cu):
+  * eval mode (the inference script): each BatchNorm is an affine map, folded into the preceding convolution when the
+    weights are (re)loaded; conv = im2col -> GEMM + bias -> [+ residual] -> ReLU;
+  * train mode (src/audio_tagging_system_cnn.py:199-416): conv -> train-mode BatchNorm over the GEMM rows (batch statistics,
+    running statistics with momentum 0.1) -> [+ residual] -> ReLU, with the backward pass (BatchNorm / ReLU / residual,
+    weight gradient = GEMM on the recomputed im2col matrix, data gradient = GEMM + col2im, max-pool and average-pool
+    backward) behind one torch.autograd.Function; `TaggerTrainer` fuses the two model calls of an iteration, the BCE terms
+    and Adam over the flat parameter buffer.
+State-dict keys equal the reference's (`resnet.conv1.weight`, `resnet.bn1.running_mean`,
+`resnet.layer2.0.downsample.0.weight`, `resnet.fc.bias`, ...), so its checkpoints load.  `pretrained=True` needs torchvision's
+ImageNet weights, which are not reachable from here, and raises.
 """
 import math
 
@@ -17,63 +22,103 @@ import torch
 from torch import nn
 
 from .. import engine
+from .CRNN import _FlatModule
 
 
-class _BN(nn.Module):
-    def __init__(self, c):
-        super().__init__()
-        self.weight = nn.Parameter(torch.ones(c))
-        self.bias = nn.Parameter(torch.zeros(c))
-        self.register_buffer("running_mean", torch.zeros(c))
-        self.register_buffer("running_var", torch.ones(c))
-        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
-        self.eps = 1e-5
+class _Holder(nn.Module):
+    pass
 
 
-class _Conv(nn.Module):
-    def __init__(self, cin, cout, k, stride, pad):
-        super().__init__()
-        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
-        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")     # torchvision's resnet init
-        self.k, self.stride, self.pad = k, stride, pad
+def _conv_holder(cin, cout, k, stride, pad):
+    m = _Holder()
+    m.cin, m.cout, m.k, m.stride, m.pad = cin, cout, k, stride, pad
+    return m
 
 
-class _Block(nn.Module):
+def _block(cin, cout, stride):
     """torchvision BasicBlock: conv1-bn1-relu-conv2-bn2 (+ downsample(x)) - relu."""
-
-    def __init__(self, cin, cout, stride):
-        super().__init__()
-        self.conv1, self.bn1 = _Conv(cin, cout, 3, stride, 1), _BN(cout)
-        self.conv2, self.bn2 = _Conv(cout, cout, 3, 1, 1), _BN(cout)
-        if stride != 1 or cin != cout:
-            self.downsample = nn.Sequential(_Conv(cin, cout, 1, stride, 0), _BN(cout))
-        else:
-            self.downsample = None
+    b = _Holder()
+    b.conv1, b.bn1 = _conv_holder(cin, cout, 3, stride, 1), _Holder()
+    b.conv2, b.bn2 = _conv_holder(cout, cout, 3, 1, 1), _Holder()
+    b.downsample = nn.Sequential(_conv_holder(cin, cout, 1, stride, 0), _Holder()) if (stride != 1 or cin != cout) else None
+    return b
 
 
-class _ResNet18(nn.Module):
-    def __init__(self, n_class):
-        super().__init__()
-        self.conv1, self.bn1 = _Conv(1, 64, 7, 2, 3), _BN(64)
-        cin = 64
-        for li, (cout, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
-            setattr(self, f"layer{li}", nn.Sequential(_Block(cin, cout, stride), _Block(cout, cout, 1)))
-            cin = cout
-        self.fc = nn.Linear(512, n_class)
+class _ResNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        p, tape = module._forward_train(x)
+        ctx.module, ctx.tape = module, tape
+        return p
+
+    @staticmethod
+    def backward(ctx, d_p):
+        module = ctx.module
+        grads = torch.zeros_like(module._flat)
+        module._backward_train(ctx.tape, d_p.contiguous().float(), grads)
+        out, o = [], 0
+        for _, _, shape in module._param_specs:
+            k = math.prod(shape)
+            out.append(grads[o:o + k].view(shape))
+            o += k
+        return (None, None, *out)
 
 
-class Net_resnet(nn.Module):
+class Net_resnet(_FlatModule):
+    BN_EPS, BN_MOMENTUM = 1e-5, 0.1          # torchvision's BatchNorm2d defaults
+
     def __init__(self, pretrained=True, n_class=20, precision=None):
         super().__init__()
         if pretrained:
             raise NotImplementedError("Net_resnet(pretrained=True) needs torchvision's ImageNet checkpoint (no network here); "
                                       "build with pretrained=False and load a state dict")
-        self.resnet = _ResNet18(n_class)
         self.n_class = n_class
-        self.precision = precision          # "tf32" (tcgen05 GEMMs) / "fp32"; None = engine.default_precision()
-        self._packed = None
+        self.precision = precision          # forward GEMMs: "tf32" (tcgen05) / "fp32"; None = engine.default_precision()
+        r = self.resnet = _Holder()
+        r.conv1, r.bn1 = _conv_holder(1, 64, 7, 2, 3), _Holder()
+        cin = 64
+        for li, (cout, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+            setattr(r, f"layer{li}", nn.Sequential(_block(cin, cout, stride), _block(cout, cout, 1)))
+            cin = cout
+        r.fc = _Holder()
+        # (conv, bn) units in forward order, parameter / buffer specs in torchvision's state-dict order
+        self._units = [(r.conv1, r.bn1)]
+        ps, bs, cm = [], [], []
 
-    # ---- folded / packed operands (rebuilt whenever the weights may have changed)
+        def add_unit(conv, bn):
+            ps.extend([(conv, "weight", (conv.cout, conv.cin, conv.k, conv.k)), (bn, "weight", (conv.cout,)), (bn, "bias", (conv.cout,))])
+            bs.extend([(bn, "running_mean", (conv.cout,)), (bn, "running_var", (conv.cout,))])
+            cm.append(bn)
+
+        add_unit(r.conv1, r.bn1)
+        for li in range(1, 5):
+            for blk in getattr(r, f"layer{li}"):
+                add_unit(blk.conv1, blk.bn1)
+                add_unit(blk.conv2, blk.bn2)
+                if blk.downsample is not None:
+                    add_unit(blk.downsample[0], blk.downsample[1])
+        ps += [(r.fc, "weight", (n_class, 512)), (r.fc, "bias", (n_class,))]
+        self._counter_mods = cm
+        self._build(ps, bs, len(cm))
+        self._packed = None
+        with torch.no_grad():                                   # torchvision's resnet initialisation
+            for mod, name, shape in self._param_specs:
+                prm = getattr(mod, name)
+                if len(shape) == 4:
+                    nn.init.kaiming_normal_(prm, mode="fan_out", nonlinearity="relu")
+                elif mod is r.fc and name == "weight":
+                    nn.init.kaiming_uniform_(prm, a=math.sqrt(5))
+                elif mod is r.fc:
+                    nn.init.uniform_(prm, -1 / math.sqrt(512), 1 / math.sqrt(512))
+                elif name == "weight":
+                    prm.fill_(1.0)
+                else:
+                    prm.zero_()
+            for mod, name, _ in self._buffer_specs:
+                getattr(mod, name).fill_(0.0 if name == "running_mean" else 1.0)
+            self._flat_nbt.zero_()
+
+    # ---- folded / packed operands of the eval path (rebuilt whenever the weights may have changed)
     def load_state_dict(self, *a, **k):
         self._packed = None
         return super().load_state_dict(*a, **k)
@@ -82,70 +127,235 @@ class Net_resnet(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **k)
 
-    @staticmethod
-    def _fold(conv, bn):
-        """eval-mode BatchNorm folded into the convolution: (Wk [Cout][Kpad] in (ky, kx, ci) order, bias [Cout])."""
-        with torch.no_grad():
-            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-            w = conv.weight * scale[:, None, None, None]
-            bias = bn.bias - bn.running_mean * scale
-            cout, cin, kh, kw = w.shape
-            K = kh * kw * cin
-            kpad = (K + 31) // 32 * 32
-            wk = torch.zeros(cout, kpad, dtype=torch.float32, device=w.device)
-            wk[:, :K] = w.permute(0, 2, 3, 1).reshape(cout, K)
-            return dict(wk=wk.contiguous(), wkT=wk.t().contiguous(), bias=bias.float().contiguous(), k=kh, stride=conv.stride,
-                        pad=conv.pad, kpad=kpad, cout=cout)
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
 
-    def _prepare(self):
+    @staticmethod
+    def _pack(w):
+        """(Cout, Cin, kh, kw) -> [Cout][Kpad] in (ky, kx, ci) order, zero padded to a multiple of 32."""
+        cout, cin, kh, kw = w.shape
+        K = kh * kw * cin
+        kpad = (K + 31) // 32 * 32
+        wk = torch.zeros(cout, kpad, dtype=torch.float32, device=w.device)
+        wk[:, :K] = w.permute(0, 2, 3, 1).reshape(cout, K)
+        return wk, K, kpad
+
+    def _fold(self, conv, bn):
+        """eval-mode BatchNorm folded into the convolution."""
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + self.BN_EPS)
+            wk, K, kpad = self._pack(conv.weight * scale[:, None, None, None])
+            bias = (bn.bias - bn.running_mean * scale).float().contiguous()
+            return dict(wk=wk, wkT=wk.t().contiguous(), bias=bias, kpad=kpad)
+
+    def _fc_operands(self):
         r = self.resnet
-        ops = {"stem": self._fold(r.conv1, r.bn1), "blocks": []}
-        for li in range(1, 5):
-            for blk in getattr(r, f"layer{li}"):
-                ops["blocks"].append(dict(c1=self._fold(blk.conv1, blk.bn1), c2=self._fold(blk.conv2, blk.bn2),
-                                          ds=self._fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None))
         with torch.no_grad():
             npad = (self.n_class + 15) // 16 * 16
             fcT = torch.zeros(512, npad, dtype=torch.float32, device=r.fc.weight.device)
             fcT[:, :self.n_class] = r.fc.weight.t()
             fb = torch.zeros(npad, dtype=torch.float32, device=r.fc.weight.device)
             fb[:self.n_class] = r.fc.bias
-        ops["fcT"], ops["fb"] = fcT.contiguous(), fb
-        self._packed = ops
+        return fcT.contiguous(), fb, npad
 
-    def _conv(self, x, op, tc):
-        """x (B, H, W, Cin) channels-last -> (B, Ho, Wo, Cout) = conv + folded BatchNorm (no activation)."""
-        B = x.shape[0]
-        col, Ho, Wo = engine.im2col_nhwc(x, op["k"], op["k"], op["stride"], op["stride"], op["pad"], op["pad"], op["kpad"])
-        cout = op["cout"]
-        y = torch.empty(B * Ho * Wo, cout, dtype=torch.float32, device=x.device)
+    def _blocks(self):
+        r = self.resnet
+        return [blk for li in range(1, 5) for blk in getattr(r, f"layer{li}")]
+
+    def _gemm(self, col, wk, wkT, bias, tc):
+        M, cout = col.shape[0], wk.shape[0]
+        y = torch.empty(M, cout, dtype=torch.float32, device=col.device)
         if tc:
             for n0 in range(0, cout, 128):
                 n1 = min(cout, n0 + 128)
-                engine.gemm_nt_tc(col, op["wk"][n0:n1], op["bias"][n0:n1].contiguous(), out=y[:, n0:n1])
+                engine.gemm_nt_tc(col, wk[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=y[:, n0:n1])
         else:
-            engine.gemm_nn(col, op["wkT"], op["bias"], out=y)
-        return y.view(B, Ho, Wo, cout)
+            engine.gemm_nn(col, wkT, bias, out=y)
+        return y
 
-    def forward(self, x):
-        if self.training:
-            raise NotImplementedError("libbsed Net_resnet implements the inference path (model.eval()); training it is not built")
-        if not x.is_cuda or not self.resnet.fc.weight.is_cuda:
-            raise RuntimeError("libbsed Net_resnet runs on CUDA tensors only (no CPU fallback)")
+    def _use_tc(self):
+        return (self.precision or engine.default_precision()).lower() == "tf32"
+
+    # ------------------------------------------------------------------------------------------ eval
+    def _forward_eval(self, x):
+        r = self.resnet
         if self._packed is None:
-            self._prepare()
-        ops = self._packed
-        tc = (self.precision or engine.default_precision()).lower() == "tf32"
-        with torch.no_grad():
-            B = x.shape[0]
-            h = x.detach().float().reshape(B, x.shape[-2], x.shape[-1], 1).contiguous()       # (B,1,T,F) -> (B,T,F,1)
-            h = engine.add_relu(self._conv(h, ops["stem"], tc))
-            h = engine.maxpool_nhwc(h, 3, 2, 1)
-            for blk in ops["blocks"]:
-                identity = h if blk["ds"] is None else self._conv(h, blk["ds"], tc)
-                o = engine.add_relu(self._conv(h, blk["c1"], tc))
-                o = self._conv(o, blk["c2"], tc)
-                h = engine.add_relu(o, identity.contiguous())
-            feat = engine.avgpool_nhwc(h)                                                       # (B, 512)
-            logits = engine.gemm_nn(feat, ops["fcT"], ops["fb"])                                # (B, 32)
-            return engine.sigmoid_rows(logits, self.n_class)
+            ops = {id(conv): self._fold(conv, bn) for conv, bn in self._all_units()}
+            ops["fc"] = self._fc_operands()
+            self._packed = ops
+        ops, tc = self._packed, self._use_tc()
+
+        def conv(h, c):
+            op = ops[id(c)]
+            col, Ho, Wo = engine.im2col_nhwc(h, c.k, c.k, c.stride, c.stride, c.pad, c.pad, op["kpad"])
+            return self._gemm(col, op["wk"], op["wkT"], op["bias"], tc).view(h.shape[0], Ho, Wo, c.cout)
+
+        B = x.shape[0]
+        h = x.detach().float().reshape(B, x.shape[-2], x.shape[-1], 1).contiguous()       # (B,1,T,F) -> (B,T,F,1)
+        h = engine.add_relu(conv(h, r.conv1))
+        h = engine.maxpool_nhwc(h, 3, 2, 1)
+        for blk in self._blocks():
+            identity = h if blk.downsample is None else conv(h, blk.downsample[0])
+            o = engine.add_relu(conv(h, blk.conv1))
+            h = engine.add_relu(conv(o, blk.conv2), identity.contiguous())
+        feat = engine.avgpool_nhwc(h)                                                       # (B, 512)
+        fcT, fb, _ = ops["fc"]
+        return engine.sigmoid_rows(engine.gemm_nn(feat, fcT, fb), self.n_class)
+
+    def _all_units(self):
+        r = self.resnet
+        units = [(r.conv1, r.bn1)]
+        for blk in self._blocks():
+            units += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
+            if blk.downsample is not None:
+                units.append((blk.downsample[0], blk.downsample[1]))
+        return units
+
+    # ------------------------------------------------------------------------------------------ train
+    def _unit_forward(self, h, conv, bn, relu, residual, tape, tc):
+        """conv -> train-mode BatchNorm -> [+ residual] -> [ReLU] on channels-last h; records what backward needs."""
+        B = h.shape[0]
+        wk, K, kpad = self._pack(conv.weight.detach())
+        col, Ho, Wo = engine.im2col_nhwc(h, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, kpad)
+        z = self._gemm(col, wk, None if tc else wk.t().contiguous(), None, tc)              # (M, Cout), becomes xhat
+        del col
+        nbt = self._flat_nbt[self._counter_mods.index(bn):][:1]
+        res = residual.reshape(-1, conv.cout) if residual is not None else None
+        y, mr = engine.bn_rows_train(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, nbt, res, relu,
+                                     self.BN_EPS, self.BN_MOMENTUM)
+        tape.append(dict(conv=conv, bn=bn, inp=h, xhat=z, y=y if relu else None, mr=mr, wk=wk, K=K, kpad=kpad,
+                         has_res=residual is not None))
+        return y.view(B, Ho, Wo, conv.cout)
+
+    def _forward_train(self, x):
+        r, tc = self.resnet, self._use_tc()
+        tape = []
+        B = x.shape[0]
+        h0 = x.detach().float().reshape(B, x.shape[-2], x.shape[-1], 1).contiguous()
+        s = self._unit_forward(h0, r.conv1, r.bn1, True, None, tape, tc)
+        h = engine.maxpool_nhwc(s, 3, 2, 1)
+        for blk in self._blocks():
+            identity = h if blk.downsample is None else self._unit_forward(h, blk.downsample[0], blk.downsample[1], False, None, tape, tc)
+            o = self._unit_forward(h, blk.conv1, blk.bn1, True, None, tape, tc)
+            h = self._unit_forward(o, blk.conv2, blk.bn2, True, identity, tape, tc)
+        feat = engine.avgpool_nhwc(h)
+        fcT, fb, npad = self._fc_operands()
+        p = engine.sigmoid_rows(engine.gemm_nn(feat, fcT, fb), self.n_class)
+        return p, dict(units=tape, stem_out=s, last_shape=tuple(h.shape), feat=feat, p=p, npad=npad, B=B)
+
+    def _grad_view(self, grads, mod, name):
+        o = 0
+        for m, n, shape in self._param_specs:
+            k = math.prod(shape)
+            if m is mod and n == name:
+                return grads[o:o + k].view(shape)
+            o += k
+        raise KeyError(name)
+
+    def _unit_backward(self, rec, dy, grads, need_dx, dx_out=None):
+        """dy (M, Cout): gradient w.r.t. the unit's output.  Adds the unit's parameter gradients into `grads`; returns
+        (dx or None, residual-branch gradient or None).  dx_out given: the input gradient is accumulated into it."""
+        conv, bn = rec["conv"], rec["bn"]
+        d_res = engine.bn_rows_backward(dy, rec["y"], rec["xhat"], bn.weight.detach(), rec["mr"],
+                                        self._grad_view(grads, bn, "weight"), self._grad_view(grads, bn, "bias"), rec["has_res"])
+        inp = rec["inp"]
+        col, _, _ = engine.im2col_nhwc(inp, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, rec["kpad"])
+        dwk = torch.zeros(conv.cout, rec["kpad"], dtype=torch.float32, device=dy.device)
+        engine.gemm_tn(dy, col, dwk)                                     # dWk[co][k] = sum_rows dconv[row][co] * col[row][k]
+        del col
+        self._grad_view(grads, conv, "weight").add_(dwk[:, :rec["K"]].view(conv.cout, conv.k, conv.k, conv.cin).permute(0, 3, 1, 2))
+        dx = None
+        if need_dx:
+            dcol = engine.gemm_nn(dy, rec["wk"])                         # (M, Kpad) = dconv * Wk
+            dx = engine.col2im_nhwc(dcol, tuple(inp.shape), conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad,
+                                    rec["kpad"], out=dx_out)
+        return dx, d_res
+
+    def _backward_train(self, tape, d_p, grads):
+        r = self.resnet
+        B, npad = tape["B"], tape["npad"]
+        dev = d_p.device
+        # head: sigmoid -> fc -> global average pool
+        dl = engine.sigmoid_rows_backward(tape["p"], d_p, npad)                                # (B, npad)
+        dfc = torch.zeros(npad, 512, dtype=torch.float32, device=dev)
+        engine.gemm_tn(dl, tape["feat"], dfc)
+        self._grad_view(grads, r.fc, "weight").add_(dfc[:self.n_class])
+        dbs = torch.zeros(npad, 16, dtype=torch.float32, device=dev)
+        engine.gemm_tn(dl, torch.ones(B, 16, dtype=torch.float32, device=dev), dbs)            # column sums of d_logits
+        self._grad_view(grads, r.fc, "bias").add_(dbs[:self.n_class, 0])
+        fc_pad = torch.zeros(npad, 512, dtype=torch.float32, device=dev)
+        fc_pad[:self.n_class] = r.fc.weight.detach()
+        dfeat = engine.gemm_nn(dl, fc_pad)                                                     # (B, 512)
+        dh = engine.avgpool_nhwc_backward(dfeat, tape["last_shape"])
+        # residual blocks, last to first
+        units = list(tape["units"])
+        for blk in reversed(self._blocks()):
+            rec2 = units.pop()
+            rec1 = units.pop()
+            recd = units.pop() if blk.downsample is not None else None
+            d_o1, d_id = self._unit_backward(rec2, dh.reshape(-1, blk.conv2.cout), grads, True)
+            if recd is None:
+                # identity branch: the block input's gradient starts as the masked output gradient
+                dx0 = d_id.view(rec1["inp"].shape)
+                dh, _ = self._unit_backward(rec1, d_o1.reshape(-1, blk.conv1.cout), grads, True, dx_out=dx0)
+            else:
+                dx0, _ = self._unit_backward(recd, d_id, grads, True)
+                dh, _ = self._unit_backward(rec1, d_o1.reshape(-1, blk.conv1.cout), grads, True, dx_out=dx0)
+        # stem: max-pool -> (conv1, bn1, relu)
+        stem = units.pop()
+        ds = engine.maxpool_nhwc_backward(tape["stem_out"], dh, 3, 2, 1)
+        self._unit_backward(stem, ds.reshape(-1, 64), grads, False)
+        assert not units
+
+    # ------------------------------------------------------------------------------------------ entry point
+    def forward(self, x):
+        if not x.is_cuda or not self._flat.is_cuda:
+            raise RuntimeError("libbsed Net_resnet runs on CUDA tensors only (no CPU fallback)")
+        if not self.training:
+            with torch.no_grad():
+                return self._forward_eval(x)
+        params = self.param_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _ResNetFunction.apply(self, x, *params)
+        return self._forward_train(x)[0]
+
+
+class TaggerTrainer:
+    """One fused iteration of the tagger's train_mt (src/audio_tagging_system_cnn.py:340-406): two model calls (synthetic
+    batch, weak / unlabeled batch; BatchNorm statistics per call), loss = BCE(syn_weak, max_t syn_target) +
+    BCE(weak[:half], target_weak[:half]), backward, Adam over the flat parameter buffer (csrc/head.cu: opt_ema_kernel)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        assert isinstance(model, Net_resnet) and model._flat.is_cuda
+        self.model = model
+        self.params = model.flat_tensors()[0]
+        self.grads = torch.zeros_like(self.params)
+        self.m, self.v = torch.zeros_like(self.params), torch.zeros_like(self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.opt_step = 0
+
+    def step(self, syn_batch_input, syn_target, batch_input, target_weak):
+        """syn_target: (n, 313, C) strong or (n, C) weak targets; target_weak (n, C).  Returns the loss (device scalar)."""
+        from .._lib import LOSS_BCE_WEAK
+        m = self.model
+        m.train()
+        ps, ts = m._forward_train(syn_batch_input)
+        pr, tr = m._forward_train(batch_input)
+        n, widx = pr.shape[0], target_weak.shape[0] // 2
+        weak = torch.cat([ps, pr]).contiguous()
+        tgt = syn_target.float().contiguous()
+        strong_dummy = torch.zeros(weak.shape[0], 1, weak.shape[1], dtype=torch.float32, device=weak.device)
+        terms = [dict(kind=LOSS_BCE_WEAK, pred_first=0, n=ps.shape[0], ref=tgt, ref_is_strong=tgt.dim() == 3, slot=0)]
+        if widx > 0:
+            terms.append(dict(kind=LOSS_BCE_WEAK, pred_first=ps.shape[0], n=widx, ref=target_weak[:widx].float().contiguous(), slot=0))
+        if tgt.dim() == 3:   # the loss kernel indexes strong references with the T of its `strong` argument
+            strong_dummy = torch.zeros(weak.shape[0], tgt.shape[1], weak.shape[1], dtype=torch.float32, device=weak.device)
+        losses, _, d_weak = engine.loss_terms(strong_dummy, weak, terms, 1)
+        self.grads.zero_()
+        m._backward_train(tr, d_weak[ps.shape[0]:].contiguous(), self.grads)
+        m._backward_train(ts, d_weak[:ps.shape[0]].contiguous(), self.grads)
+        self.opt_step += 1
+        engine.opt_ema_step(self.params, self.grads, self.m, self.v, None, step=self.opt_step, kind="adam", lr=self.lr,
+                            betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        return losses[0]

@@ -337,6 +337,32 @@ int bsed_maxpool_nhwc(bsed_handle h, const float* x, float* y, int B, int H, int
 int bsed_avgpool_nhwc(bsed_handle h, const float* x, float* y, int B, int HW, int C, void* stream);
 int bsed_sigmoid_rows(bsed_handle h, const float* logits, int ld, float* out, int rows, int C, void* stream);
 
+/* Training path of the tagger (src/audio_tagging_system_cnn.py:199-416): every convolution is bias-free and followed by a
+ * train-mode BatchNorm2d (eps 1e-5, momentum 0.1) over the rows [M][C] of the GEMM output.
+ *   bsed_bn_rows_train: batch statistics -> running statistics (unbiased variance) and num_batches_tracked -> x becomes
+ *       xhat in place, y = gamma*xhat + beta [+ residual] [ReLU]; mean_rstd [2][C] is kept for the backward.
+ *   bsed_bn_rows_backward: dy (in: gradient w.r.t. y; out: gradient w.r.t. the convolution output); y != NULL applies the
+ *       ReLU mask first; d_residual (may be NULL) receives the masked gradient (the identity branch); d_gamma / d_beta +=.
+ *   bsed_col2im_nhwc: transpose of bsed_im2col_nhwc (gather, fixed summation order), dx = or += (accumulate).
+ *   bsed_maxpool_nhwc_backward: gradient to the first maximum of each window (ATen's rule).
+ *   bsed_sigmoid_rows_backward: d_logits [rows][ld] = d_p * p (1-p), padding columns zero.
+ * workspace: bsed_bn_rows_workspace_bytes(C).  Weight gradients and data gradients of the convolutions are GEMMs
+ * (bsed_gemm_tn on the recomputed im2col matrix, bsed_gemm_nn with the packed weights).  C % 4 == 0, C <= 1024. */
+size_t bsed_bn_rows_workspace_bytes(int C);
+int bsed_bn_rows_train(bsed_handle h, float* x, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* run_mean, float* run_var, int64_t* nbt, const float* residual, int relu,
+                       float* y, float* mean_rstd, void* workspace, size_t workspace_bytes, void* stream);
+int bsed_bn_rows_backward(bsed_handle h, float* dy, const float* y, const float* xhat, int64_t M, int C,
+                          const float* gamma, const float* mean_rstd, float* d_gamma, float* d_beta, float* d_residual,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int bsed_col2im_nhwc(bsed_handle h, const float* dcol, float* dx, int B, int H, int W, int Cin, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int Ho, int Wo, int Kpad, int accumulate, void* stream);
+int bsed_maxpool_nhwc_backward(bsed_handle h, const float* x, const float* dy, float* dx, int B, int H, int W, int C, int k,
+                               int s, int p, int Ho, int Wo, void* stream);
+int bsed_avgpool_nhwc_backward(bsed_handle h, const float* dy, float* dx, int B, int HW, int C, void* stream);
+int bsed_sigmoid_rows_backward(bsed_handle h, const float* p, const float* dp, float* d_logits, int rows, int C, int ld,
+                               void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).
  *   bsed_launch_count: kernels this library has launched in this process.

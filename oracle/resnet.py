@@ -53,3 +53,16 @@ def seeded_init(model, seed, fc_std=0.0015):
                 m.weight.copy_(t(rng.normal(0.0, fc_std, m.weight.shape)))
                 m.bias.copy_(t(rng.normal(0.0, 0.1, m.bias.shape)))
     return model
+
+
+def tagger_step_loss(model, syn_batch_input, syn_target, batch_input, target_weak):
+    """Loss of one iteration of the tagger's train_mt (src/audio_tagging_system_cnn.py:340-352): two model calls in the
+    order of the reference (synthetic batch, then the weak / unlabeled batch), BCELoss on the weak outputs; of the real
+    batch only the weakly labelled first half counts.  Returns (loss, None)."""
+    bce = nn.BCELoss()
+    syn_weak_pred = model(syn_batch_input)
+    weak_pred = model(batch_input)
+    syn_target_weak = syn_target.max(-2)[0]
+    widx = target_weak.shape[0] // 2
+    loss = bce(syn_weak_pred, syn_target_weak) + bce(weak_pred[:widx], target_weak[:widx])
+    return loss, None

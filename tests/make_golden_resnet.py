@@ -33,5 +33,34 @@ def main():
     print("resnet golden written; out range", float(out.min()), float(out.max()), "shape", tuple(out.shape))
 
 
+def train_fixture():
+    """One iteration of the tagger's train_mt (src/audio_tagging_system_cnn.py:340-406) with the torchvision-based model:
+    two model calls in train mode, BCE on the weak outputs, backward, Adam(lr 1e-3)."""
+    torch.set_num_threads(8)
+    m = ores.seeded_init(ores.OracleNetResnet(20), seed=17).train()
+    xs = torch.from_numpy(synth.make_logmel_like(2, seed=61))
+    xr = torch.from_numpy(synth.make_logmel_like(2, seed=62))
+    ts = torch.from_numpy(synth.make_targets(2, seed=63))
+    tw = (torch.from_numpy(synth.make_targets(2, seed=64)).max(-2)[0] > 0).float()
+    loss, grads = ores.tagger_step_loss(m, xs, ts, xr, tw)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt.zero_grad()
+    loss.backward()
+    rec = {"loss": float(loss)}
+    for n, p in m.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        rec["g_" + n] = g if g.size <= 4096 else g[:: max(1, g.size // 4096)][:4096]
+        rec["gn_" + n] = float(np.sqrt((g.astype(np.float64) ** 2).sum()))
+    opt.step()
+    sd = m.state_dict()
+    for k in ("resnet.conv1.weight", "resnet.layer1.0.bn1.weight", "resnet.layer2.0.downsample.0.weight", "resnet.layer4.1.conv2.weight",
+              "resnet.fc.bias", "resnet.bn1.running_mean", "resnet.layer3.0.downsample.1.running_var", "resnet.layer4.1.bn2.running_var"):
+        rec["s_" + k] = sd[k].numpy().reshape(-1)[:2048]
+    rec["nbt"] = int(sd["resnet.bn1.num_batches_tracked"])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "resnet_train.npz"), **rec)
+    print("resnet train fixture: loss", rec["loss"], "nbt", rec["nbt"])
+
+
 if __name__ == "__main__":
     main()
+    train_fixture()

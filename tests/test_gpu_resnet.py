@@ -52,8 +52,6 @@ def test_eval_forward_matches_oracle_and_fixture(precision, tol):
     # clips are independent of their batch
     one = m(x[1:2].cuda())
     assert max_abs(one.cpu().numpy(), out[1:2].cpu().numpy()) < 1e-6
-    with pytest.raises(NotImplementedError):
-        m.train()(x.cuda())
 
 
 def test_weak_label_rows_from_the_tagger():
@@ -79,3 +77,73 @@ def test_weak_label_rows_from_the_tagger():
     assert list(df.columns) == ["filename", "event_labels"]
     want = {f: r for f, r in zip(["a.wav", "b.wav", "c.wav"], rows) if r}
     assert dict(zip(df["filename"], df["event_labels"])) == want
+
+
+def _train_inputs():
+    xs = torch.from_numpy(synth.make_logmel_like(2, seed=61))
+    xr = torch.from_numpy(synth.make_logmel_like(2, seed=62))
+    ts = torch.from_numpy(synth.make_targets(2, seed=63))
+    tw = (torch.from_numpy(synth.make_targets(2, seed=64)).max(-2)[0] > 0).float()
+    return xs, xr, ts, tw
+
+
+def _check_grads(g, named_grads, tol):
+    bad, worst = [], 0.0
+    for n, got in named_grads:
+        gn = float(g["gn_" + n])
+        if gn < 1e-6:
+            continue
+        got = got.cpu().numpy().reshape(-1)
+        got = got if got.size <= 4096 else got[:: max(1, got.size // 4096)][:4096]
+        e = float(np.linalg.norm(got.astype(np.float64) - g["g_" + n]) / max(np.linalg.norm(g["g_" + n]), 1e-30))
+        worst = max(worst, e)
+        if e > tol:
+            bad.append((n, e))
+    return bad, worst
+
+
+def test_training_step_through_autograd_matches_fixture():
+    """Reference statement order (src/audio_tagging_system_cnn.py:340-406): two model calls, BCELoss, loss.backward()."""
+    from bsed_b200.models.ResNet import Net_resnet
+    g = golden("resnet_train.npz")
+    oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
+    m = Net_resnet(pretrained=False, precision="fp32")
+    m.load_state_dict(oc.state_dict())
+    m = m.cuda().train()
+    xs, xr, ts, tw = [t.cuda() for t in _train_inputs()]
+    loss, _ = ores.tagger_step_loss(m, xs, ts, xr, tw)                   # the oracle's loss assembly on the CUDA model
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-4)
+    loss.backward()
+    bad, worst = _check_grads(g, [(n, p.grad) for n, p in m.named_parameters()], 3e-3)
+    print(f"resnet train (autograd): loss {float(loss):.6f}, worst gradient rel_l2 {worst:.2e}")
+    assert not bad, bad
+    assert int(m.resnet.bn1.num_batches_tracked) == int(g["nbt"]) == 2
+    for k in ("resnet.bn1.running_mean", "resnet.layer3.0.downsample.1.running_var", "resnet.layer4.1.bn2.running_var"):
+        assert max_abs(m.state_dict()[k].cpu().numpy().reshape(-1)[:2048], g["s_" + k]) < 1e-3, k
+
+
+def test_fused_tagger_trainer_matches_fixture():
+    from bsed_b200.models.ResNet import Net_resnet, TaggerTrainer
+    g = golden("resnet_train.npz")
+    oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
+    m = Net_resnet(pretrained=False, precision="fp32")
+    m.load_state_dict(oc.state_dict())
+    m = m.cuda().train()
+    xs, xr, ts, tw = [t.cuda() for t in _train_inputs()]
+    tr = TaggerTrainer(m, lr=1e-3)
+    loss = tr.step(xs, ts, xr, tw)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-4)
+    o, named = 0, []
+    names = [n for n, _ in m.named_parameters()]
+    for (mod, pname, shape), n in zip(m._param_specs, names):
+        k = int(np.prod(shape))
+        named.append((n, tr.grads[o:o + k]))
+        o += k
+    bad, worst = _check_grads(g, named, 3e-3)
+    print(f"resnet train (fused): worst gradient rel_l2 {worst:.2e}")
+    assert not bad, bad
+    sd = m.state_dict()
+    for k in ("resnet.conv1.weight", "resnet.layer1.0.bn1.weight", "resnet.layer2.0.downsample.0.weight",
+              "resnet.layer4.1.conv2.weight", "resnet.fc.bias"):
+        d = np.abs(sd[k].cpu().numpy().reshape(-1)[:2048].astype(np.float64) - g["s_" + k])
+        assert d.max() < 2.2e-3 and d.mean() < 5e-5, (k, d.max(), d.mean())      # one Adam step of lr 1e-3
