@@ -30,7 +30,7 @@ SYMBOLS = [
     "bsed_ipc_export", "bsed_ipc_open", "bsed_ipc_close", "bsed_dp_opt_ema_step",
     "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
     "bsed_bn_rows_workspace_bytes", "bsed_bn_rows_train", "bsed_bn_rows_backward", "bsed_col2im_nhwc",
-    "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward",
+    "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward", "bsed_gemm_tn_tc",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -144,6 +144,7 @@ def load():
         proto("bsed_conv3x3_wgrad_workspace_bytes", sz, vp)
         proto("bsed_conv3x3_wgrad", i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp)
         proto("bsed_conv3x3_tc", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+        proto("bsed_gemm_tn_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i64, vp, sz, vp)
         proto("bsed_gemm_nt_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)
         proto("bsed_conv3x3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
         proto("bsed_disc_set_precision", i32, vp, i32)

@@ -424,6 +424,16 @@ extern "C" int bsed_conv3x3_tc(bsed_handle h, const float* x, const float* weigh
   return tc_conv3x3(x, wpack, y, B, T, F, Cin, Cout, bias, 0, h->num_sms, as_stream(stream));
 }
 
+// C[M][N] += sum_k A[k][M]^T Bm[k][N] on tcgen05 (kind::tf32): the weight-gradient kernel with one tap and rows = k
+extern "C" int bsed_gemm_tn_tc(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N,
+                               int64_t K, float* workspace, size_t workspace_bytes, void* stream) {
+  BSED_REQUIRE(h && A && Bm && C && workspace, "bsed_gemm_tn_tc: null argument");
+  BSED_REQUIRE(M % 32 == 0 && M >= 32 && N % 32 == 0 && N >= 32 && (N < 128 || N % 128 == 0), "bsed_gemm_tn_tc: M=%d N=%d", M, N);
+  BSED_REQUIRE(K >= 1 && K < (1ll << 31), "bsed_gemm_tn_tc: K=%lld", (long long)K);
+  TcOperand a{A, lda, 0, M}, b{Bm, ldb, 0, N};
+  return tc_wgrad_ex(a, b, 1, (int)K, 1, 1, 0, C, ldc, 1, 0, workspace, workspace_bytes, h->num_sms, as_stream(stream));
+}
+
 extern "C" int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
                                int M, int N, int K, const float* bias, int accumulate, void* stream) {
   BSED_REQUIRE(h && A && Bk && C, "bsed_gemm_nt_tc: null argument");

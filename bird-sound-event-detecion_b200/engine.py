@@ -321,6 +321,24 @@ def gemm_tn(a, b, out):
     return out
 
 
+_tn_ws = {}
+
+
+def gemm_tn_tc(a, b, out):
+    """tcgen05: out[M][N] += a[K][M]^T @ b[K][N]  (M % 32 == 0; N % 32 == 0 and N % 128 == 0 from 128 up)."""
+    lib = _lib.load()
+    h = _lib.handle(a.device.index)
+    K, M = a.shape
+    N = b.shape[1]
+    if a.device not in _tn_ws:
+        nb = int(lib.bsed_conv3x3_wgrad_workspace_bytes(h))
+        _tn_ws[a.device] = (torch.empty(nb, dtype=torch.uint8, device=a.device), nb)
+    ws, nb = _tn_ws[a.device]
+    check(lib.bsed_gemm_tn_tc(h, _rows(a), a.stride(0), _rows(b), b.stride(0), _rows(out), out.stride(0), M, N, K, ptr(ws), nb,
+                              stream_ptr()), "bsed_gemm_tn_tc")
+    return out
+
+
 def gemm_nt_tc(a, bk, bias=None, out=None, accumulate=False):
     """tcgen05: out[M][N] (+)= a[M][K] @ bk[N][K]^T (+ bias)."""
     lib = _lib.load()

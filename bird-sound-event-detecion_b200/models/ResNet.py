@@ -10,7 +10,7 @@ Every convolution runs in libbsed.so as im2col -> GEMM on channels-last tensors 
   * train mode (src/audio_tagging_system_cnn.py:199-416): conv -> train-mode BatchNorm over the GEMM rows (batch statistics,
     running statistics with momentum 0.1) -> [+ residual] -> ReLU, with the backward pass (BatchNorm / ReLU / residual,
     weight gradient = GEMM on the recomputed im2col matrix, data gradient = GEMM + col2im, max-pool and average-pool
-    backward) behind one torch.autograd.Function; `TaggerTrainer` fuses the two model calls of an iteration, the BCE terms
+    backward; the GEMMs on tcgen05 tf32 or, with precision="fp32", on the CUDA cores) behind one torch.autograd.Function; `TaggerTrainer` fuses the two model calls of an iteration, the BCE terms
     and Adam over the flat parameter buffer.
 State-dict keys equal the reference's (`resnet.conv1.weight`, `resnet.bn1.running_mean`,
 `resnet.layer2.0.downsample.0.weight`, `resnet.fc.bias`, ...), so its checkpoints load.  `pretrained=True` needs torchvision's
@@ -133,10 +133,11 @@ class Net_resnet(_FlatModule):
 
     @staticmethod
     def _pack(w):
-        """(Cout, Cin, kh, kw) -> [Cout][Kpad] in (ky, kx, ci) order, zero padded to a multiple of 32."""
+        """(Cout, Cin, kh, kw) -> [Cout][Kpad] in (ky, kx, ci) order, zero padded to a multiple of 32 (of 128 above 128: the
+        tensor-core weight-gradient GEMM tiles its N = Kpad by 128)."""
         cout, cin, kh, kw = w.shape
         K = kh * kw * cin
-        kpad = (K + 31) // 32 * 32
+        kpad = (K + 31) // 32 * 32 if K <= 128 else (K + 127) // 128 * 128
         wk = torch.zeros(cout, kpad, dtype=torch.float32, device=w.device)
         wk[:, :K] = w.permute(0, 2, 3, 1).reshape(cout, K)
         return wk, K, kpad
@@ -225,7 +226,7 @@ class Net_resnet(_FlatModule):
         y, mr = engine.bn_rows_train(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, nbt, res, relu,
                                      self.BN_EPS, self.BN_MOMENTUM)
         tape.append(dict(conv=conv, bn=bn, inp=h, xhat=z, y=y if relu else None, mr=mr, wk=wk, K=K, kpad=kpad,
-                         has_res=residual is not None))
+                         has_res=residual is not None, tc=tc))
         return y.view(B, Ho, Wo, conv.cout)
 
     def _forward_train(self, x):
@@ -262,12 +263,20 @@ class Net_resnet(_FlatModule):
         inp = rec["inp"]
         col, _, _ = engine.im2col_nhwc(inp, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, rec["kpad"])
         dwk = torch.zeros(conv.cout, rec["kpad"], dtype=torch.float32, device=dy.device)
-        engine.gemm_tn(dy, col, dwk)                                     # dWk[co][k] = sum_rows dconv[row][co] * col[row][k]
+        tc = rec["tc"]
+        (engine.gemm_tn_tc if tc else engine.gemm_tn)(dy, col, dwk)      # dWk[co][k] = sum_rows dconv[row][co] * col[row][k]
         del col
         self._grad_view(grads, conv, "weight").add_(dwk[:, :rec["K"]].view(conv.cout, conv.k, conv.k, conv.cin).permute(0, 3, 1, 2))
         dx = None
         if need_dx:
-            dcol = engine.gemm_nn(dy, rec["wk"])                         # (M, Kpad) = dconv * Wk
+            if tc:                                                       # (M, Kpad) = dconv * Wk, 128 columns per launch
+                wkT = rec["wk"].t().contiguous()
+                dcol = torch.empty(dy.shape[0], rec["kpad"], dtype=torch.float32, device=dy.device)
+                for n0 in range(0, rec["kpad"], 128):
+                    n1 = min(rec["kpad"], n0 + 128)
+                    engine.gemm_nt_tc(dy, wkT[n0:n1], None, out=dcol[:, n0:n1])
+            else:
+                dcol = engine.gemm_nn(dy, rec["wk"])
             dx = engine.col2im_nhwc(dcol, tuple(inp.shape), conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad,
                                     rec["kpad"], out=dx_out)
         return dx, d_res

@@ -401,6 +401,10 @@ int bsed_conv3x3_wgrad(bsed_handle h, const float* x, const float* dy, float* dw
                        int Cout, int tensor_cores, float* workspace, size_t workspace_bytes, void* stream);
 int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
                     int M, int N, int K, const float* bias, int accumulate, void* stream);
+/* gemm_tn_tc: C[M][N] += sum_k A[k][M] * Bm[k][N] on tcgen05 (the weight-gradient kernel, rows = k); M % 32 == 0,
+ * N % 32 == 0 and, from 128 up, N % 128 == 0; workspace of bsed_conv3x3_wgrad_workspace_bytes(h). */
+int bsed_gemm_tn_tc(bsed_handle h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N,
+                    int64_t K, float* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -223,3 +223,37 @@ def test_fused_tagger_trainer_matches_fixture():
         # one Adam step moves every weight by ~lr = 1e-3 whatever the gradient size: elements whose gradient is rounding
         # noise may move the other way
         assert d.max() < 2.2e-3 and d.mean() < 2e-4, (k, d.max(), d.mean())
+
+
+@pytest.mark.parametrize("K,M,N", [(1000, 64, 64), (20096, 64, 640), (320, 512, 4608), (640, 256, 128)])
+def test_gemm_tn_tensor_cores(K, M, N):
+    from bsed_b200 import engine
+    g = torch.Generator().manual_seed(K + M + N)
+    a, b = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    out = torch.zeros(M, N, device="cuda")
+    engine.gemm_tn_tc(a.cuda(), b.cuda(), out)
+    ref = a.double().t() @ b.double()
+    assert _rel(out.cpu().double(), ref) < 2e-3           # tf32 operands, fp32 accumulation
+
+
+def test_tf32_training_step_gradients():
+    """tcgen05 tf32 GEMMs in the forward and backward of the tagger against the fp32 fixture: stated tolerance 6e-2 on
+    the gradients (the fp32 kernels already sit at 1.7e-2 on this ill-conditioned 2-clip problem), loss 1e-3."""
+    from bsed_b200.models.ResNet import Net_resnet, TaggerTrainer
+    g = golden("resnet_train.npz")
+    oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
+    m = Net_resnet(pretrained=False, precision="tf32")
+    m.load_state_dict(oc.state_dict())
+    m = m.cuda().train()
+    xs, xr, ts, tw = [t.cuda() for t in _train_inputs()]
+    tr = TaggerTrainer(m, lr=1e-3)
+    loss = tr.step(xs, ts, xr, tw)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-3)
+    o, named = 0, []
+    for (mod, pname, shape), n in zip(m._param_specs, [n for n, _ in m.named_parameters()]):
+        k = int(np.prod(shape))
+        named.append((n, tr.grads[o:o + k]))
+        o += k
+    bad, worst = _check_grads(g, named, 6e-2)
+    print(f"resnet train (fused, tf32): loss {float(loss):.6f}, worst gradient rel_l2 {worst:.2e}")
+    assert not bad, bad
