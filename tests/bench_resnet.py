@@ -43,5 +43,5 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print(f"Net_resnet training step, 12 + 12 clips (tf32 forward GEMMs, {m.backward_precision} backward GEMMs): {ms:.1f} ms -> {24e3 / ms:.0f} clips/s; "
+print(f"Net_resnet training step, 12 + 12 clips (tf32 forward GEMMs, {m.backward_precision or "tf32"} backward GEMMs): {ms:.1f} ms -> {24e3 / ms:.0f} clips/s; "
       f"loss {float(loss):.4f}; peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")

@@ -264,7 +264,7 @@ def test_tf32_training_step_gradients(bwd):
 
 def test_tf32_against_fp32_on_a_larger_batch():
     """The same comparison between this implementation's two precisions on 6 + 6 clips: with more rows per BatchNorm the
-    backward is better conditioned and the tf32 deviation shrinks (printed; stated bound 0.3)."""
+    backward is better conditioned and the tf32 deviation shrinks to 3.3e-3 (measured; stated bound 2e-2)."""
     from bsed_b200.models.ResNet import Net_resnet, TaggerTrainer
     oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
     xs = torch.from_numpy(synth.make_logmel_like(6, seed=71)).cuda()
@@ -281,4 +281,4 @@ def test_tf32_against_fp32_on_a_larger_batch():
         grads[prec] = tr.grads.clone()
     e = _rel(grads["tf32"], grads["fp32"])
     print(f"resnet train 6 + 6 clips: tf32 vs fp32 whole-gradient rel_l2 {e:.2e}, losses {losses}")
-    assert losses["tf32"] == pytest.approx(losses["fp32"], rel=1e-3) and e < 0.3
+    assert losses["tf32"] == pytest.approx(losses["fp32"], rel=1e-3) and e < 2e-2
