@@ -282,3 +282,32 @@ def test_tf32_against_fp32_on_a_larger_batch():
     e = _rel(grads["tf32"], grads["fp32"])
     print(f"resnet train 6 + 6 clips: tf32 vs fp32 whole-gradient rel_l2 {e:.2e}, losses {losses}")
     assert losses["tf32"] == pytest.approx(losses["fp32"], rel=1e-3) and e < 2e-2
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_tagger_train_mt_entry_point(fused):
+    """train_mt of src/audio_tagging_system_cnn.py:199 with the reference's three loaders, through the fused trainer and
+    through a stock torch optimizer + the autograd function; a teacher copy follows by parameter EMA."""
+    from bsed_b200 import audio_tagging_system_cnn as ats
+    from bsed_b200.main import FusedAdam
+    oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
+    m = ats.Net_resnet(pretrained=False, precision="fp32")
+    m.load_state_dict(oc.state_dict())
+    em = ats.Net_resnet(pretrained=False, precision="fp32")
+    em.load_state_dict(oc.state_dict())
+    m, em = m.cuda().train(), em.cuda().train()
+    for prm in em.parameters():
+        prm.detach_()
+    xs, xr, ts, tw = _train_inputs()
+    syn = [(((xs, xs), ts), ["s0", "s1"])]
+    weak = [(((xr[:1], xr[:1]), torch.from_numpy(synth.make_targets(1, seed=65))), ["w0"])]
+    unl = [(((xr[1:], xr[1:]), tw[1:]), ["u0"])]
+    opt = (FusedAdam if fused else torch.optim.Adam)(m.parameters(), lr=1e-3)
+    before = m._flat.clone()
+    loss = ats.train_mt(unl, weak, syn, m, opt, 0, ema_model=em)
+    assert torch.isfinite(loss) and float(loss) > 0
+    moved = (m.flat_tensors()[0] - before).abs()
+    assert float(moved.max()) > 5e-4 and float(moved.max()) < 1.1e-3            # one Adam step of lr 1e-3
+    assert int(m.resnet.bn1.num_batches_tracked) == 2
+    # global_step = 1: alpha = min(1 - 1/2, 0.999) = 0.5
+    assert torch.allclose(em.flat_tensors()[0], 0.5 * before + 0.5 * m.flat_tensors()[0], atol=1e-7)
