@@ -31,6 +31,7 @@ SYMBOLS = [
     "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
     "bsed_bn_rows_workspace_bytes", "bsed_bn_rows_train", "bsed_bn_rows_backward", "bsed_col2im_nhwc",
     "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward", "bsed_gemm_tn_tc",
+    "bsed_logmel",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1}
 
@@ -96,6 +97,7 @@ def load():
         proto("bsed_melspec", i32, vp, vp, i32, i32, vp, vp)
         proto("bsed_amp_to_db_workspace_bytes", sz, i32)
         proto("bsed_amp_to_db", i32, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, sz, vp)
+        proto("bsed_logmel", i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp)
         proto("bsed_median_decode", i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp, vp)
         proto("bsed_plan_create", i32, vp, P(CrnnCfg), i32, P(vp))
         proto("bsed_plan_destroy", i32, vp)

@@ -271,6 +271,14 @@ extern "C" int bsed_melspec(bsed_handle h, const float* audio, int B, int n_samp
 
 extern "C" size_t bsed_amp_to_db_workspace_bytes(int B) { return B > 0 ? sizeof(double) * (size_t)B * (kNMels + 1) : 0; }
 
+extern "C" int bsed_logmel(bsed_handle h, const float* audio, int B, int n_samples, int frames, const float* scaler_mean,
+                           const float* scaler_std, float* mel, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  BSED_REQUIRE(h && audio && mel && out && workspace, "bsed_logmel: null argument");
+  BSED_REQUIRE(B > 0 && n_samples >= kNFFT / 2 + 1, "bsed_logmel: B=%d n_samples=%d", B, n_samples);
+  return logmel(h, audio, B, n_samples, frames, scaler_mean, scaler_std, mel, out, workspace, workspace_bytes, as_stream(stream));
+}
+
 extern "C" int bsed_amp_to_db(bsed_handle h, const float* mel, const float* unit_noise, float snr_db, int B, int t_in,
                               int frames, const float* scaler_mean, const float* scaler_std, float* out,
                               void* workspace, size_t workspace_bytes, void* stream) {

@@ -92,7 +92,8 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 
 __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* __restrict__ audio, int n_samples,
                                                                    int n_frames, int tiles_per_clip, int n_tiles,
-                                                                   float* __restrict__ mel, FrontendTables tb) {
+                                                                   float* __restrict__ mel, FrontendTables tb,
+                                                                   double* __restrict__ clip_max_ws) {
   extern __shared__ __align__(16) unsigned char fe_smem[];
   float* audio_s = reinterpret_cast<float*>(fe_smem);          // 2 x FE_AUD (double buffer)
   float* win_s = audio_s + 2 * FE_AUD;
@@ -234,12 +235,19 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
       if (lane < len) dtop = ivw_s[s + lane].y * magb[s + lane];
       dtop = warp_sum(dtop);
     }
+    float fmx = 0.f;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       float dn = __shfl_down_sync(0xffffffffu, D[r], 1);                       // D of interval j + 1 (same pass)
       const float dnext = r < 3 ? __shfl_sync(0xffffffffu, D[r < 3 ? r + 1 : r], 0) : dtop;   // lane 31: first interval of the next pass
       if (lane == 31) dn = dnext;
-      out[lane + 32 * r] = U[r] + dn;
+      const float mv = U[r] + dn;
+      out[lane + 32 * r] = mv;
+      fmx = fmaxf(fmx, fabsf(mv));
+    }
+    if (clip_max_ws) {   // fused log-mel: the clip maximum the dB clamp needs (slot kNMels of the clip's amp_to_db workspace)
+      fmx = warp_max(fmx);
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(clip_max_ws + (size_t)b * (kNMels + 1) + kNMels), __float_as_uint(fmx));
     }
     __syncwarp();
   }
@@ -249,7 +257,13 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 1) melspec_kernel(const float* 
 constexpr size_t FE_SMEM_BYTES = sizeof(float) * (2 * FE_AUD + kNFFT) + sizeof(float2) * (1024 + 516 + FE_IVW) +
                                  sizeof(int) * 2 * (FE_NIV + 3) + sizeof(float2) * FE_WARPS * FE_BUF;
 
+static int melspec_impl(bsed_context* h, const float* audio, int B, int n_samples, float* mel, double* clip_max_ws, cudaStream_t st);
+
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st) {
+  return melspec_impl(h, audio, B, n_samples, mel, nullptr, st);
+}
+
+static int melspec_impl(bsed_context* h, const float* audio, int B, int n_samples, float* mel, double* clip_max_ws, cudaStream_t st) {
   BSED_REQUIRE(n_samples >= kNFFT / 2 + 1, "melspec: n_samples=%d < 1025 (reflect padding)", n_samples);
   BSED_REQUIRE(B > 0, "melspec: B=%d", B);
   static bool configured = false;
@@ -266,7 +280,8 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
   const int grid = (int)(n_tiles < h->num_sms ? n_tiles : h->num_sms);
   // algorithmic bytes: audio in + mel out; flops: rFFT-2048 + magnitude + sparse mel
   ProfScope prof(PROF_MELSPEC, (double)B * n_frames * 70000.0, 4.0 * B * ((double)n_samples + (double)n_frames * kNMels), st);
-  melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, tiles_per_clip, (int)n_tiles, mel, tb);
+  melspec_kernel<<<grid, FE_WARPS * 32, FE_SMEM_BYTES, st>>>(audio, n_samples, n_frames, tiles_per_clip, (int)n_tiles, mel, tb,
+                                                             clip_max_ws);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -419,6 +434,31 @@ int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_i
     db_apply_kernel<true><<<grid, 256, 0, st>>>(mel, noise, snr_scale, t_in, frames, sc_mean, sc_std, w, out);
   else
     db_apply_kernel<false><<<grid, 256, 0, st>>>(mel, nullptr, snr_scale, t_in, frames, sc_mean, sc_std, w, out);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+// preprocess(audio, compute_log=True) / the load-time ApplyLog -> PadOrTrunc -> [Normalize] of a clean clip in one call:
+// the STFT + mel kernel also takes the per-clip maximum (atomicMax on the float bits), so the dB pass reads the
+// amplitude-mel once instead of twice.  Results are bit-identical to melspec followed by amp_to_db without noise.
+int logmel(bsed_context* h, const float* audio, int B, int n_samples, int frames, const float* sc_mean, const float* sc_std,
+           float* mel, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  BSED_REQUIRE(frames > 0, "logmel: frames=%d", frames);
+  BSED_REQUIRE((sc_mean == nullptr) == (sc_std == nullptr), "logmel: scaler mean/std must come together");
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  BSED_REQUIRE(aligned16(mel) && aligned16(out) && aligned16(sc_mean) && aligned16(sc_std) && aligned16(ws),
+               "logmel: buffers must be 16-byte aligned (float4 accesses)");
+  const size_t need = sizeof(double) * (size_t)B * (kNMels + 1);
+  if (ws_bytes < need) {
+    bsed_set_error("logmel: workspace %zu < %zu", ws_bytes, need);
+    return BSED_E_WORKSPACE;
+  }
+  BSED_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  BSED_TRY(melspec_impl(h, audio, B, n_samples, mel, (double*)ws, st));
+  const int t_in = 1 + n_samples / kHop;
+  ProfScope prof(PROF_ELEMENTWISE, 0.0, 4.0 * B * kNMels * ((double)t_in + (double)frames), st);
+  dim3 grid(ceil_div((long long)frames * (kNMels / 4), 256), B);
+  db_apply_kernel<false><<<grid, 256, 0, st>>>(mel, nullptr, 1.0, t_in, frames, sc_mean, sc_std, (const double*)ws, out);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

@@ -167,6 +167,8 @@ int tc_wgrad(const float* X, const float* dY, float* dW, long long rs, long long
 
 // ---- frontend.cu
 int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* mel, cudaStream_t st);
+int logmel(bsed_context* h, const float* audio, int B, int n_samples, int frames, const float* sc_mean, const float* sc_std,
+           float* mel, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_in, int frames,
               const float* sc_mean, const float* sc_std, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int median_decode(const float* strong, int B, int T, int C, float threshold, int win, int32_t* events,

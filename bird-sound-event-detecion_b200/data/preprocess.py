@@ -21,10 +21,9 @@ def _device():
 
 def preprocess_batch(audio, compute_log=False):
     """audio: (B, N) float32 CUDA tensor -> (B, T, 128) CUDA tensor."""
-    mel = engine.melspec(audio)
     if compute_log:
-        mel = engine.amp_to_db(mel, frames=mel.shape[1])
-    return mel
+        return engine.logmel(audio, frames=1 + audio.shape[1] // cfg.hop_size)
+    return engine.melspec(audio)
 
 
 def preprocess(audio, compute_log=False):

@@ -276,6 +276,23 @@ def amp_to_db(mel, frames, unit_noise=None, snr=30.0, scaler_mean=None, scaler_s
     return out
 
 
+def logmel(audio, frames, scaler_mean=None, scaler_std=None, return_mel=False):
+    """audio (B, n) fp32 cuda -> (B, frames, 128) log-mel in one call (STFT + mel with the clip maximum, then one dB pass);
+    bit-identical to amp_to_db(melspec(audio), frames)."""
+    lib = _lib.load()
+    h = _lib.handle(audio.device.index)
+    audio = audio.contiguous()
+    B, n = audio.shape
+    nf = lib.bsed_frontend_n_frames(n)
+    mel = torch.empty(B, nf, 128, dtype=torch.float32, device=audio.device)
+    out = torch.empty(B, frames, 128, dtype=torch.float32, device=audio.device)
+    wsb = int(lib.bsed_amp_to_db_workspace_bytes(B))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=audio.device)
+    check(lib.bsed_logmel(h, ptr(audio), B, n, int(frames), ptr(scaler_mean), ptr(scaler_std), ptr(mel), ptr(out), ptr(ws), wsb,
+                          stream_ptr()), "bsed_logmel")
+    return (out, mel) if return_mel else out
+
+
 def median_decode(strong, threshold=0.5, win=14, max_events=None):
     """strong (B, T, C) -> (events int32 (B, max_events, 3), n_events int32 (B,))."""
     lib = _lib.load()

@@ -57,8 +57,7 @@ def pseudo_label_stream(audio, model, predictor, batch_clips=48, weak_threshold=
             if not torch.is_tensor(chunk):
                 chunk = torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.float32))
             clips = chunk.to(dev, non_blocking=True).reshape(b1 - b0, seg)
-            mel = engine.melspec(clips)
-            x = engine.amp_to_db(mel, cfg.max_frames, scaler_mean=mean, scaler_std=std)[:, None]
+            x = engine.logmel(clips, cfg.max_frames, scaler_mean=mean, scaler_std=std)[:, None]     # fused frontend
             enc, _ = model(x)
             strong, weak = predictor(enc)
             decoded = decode_events(strong, (strong_threshold,), median_window)[strong_threshold]

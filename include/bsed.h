@@ -72,6 +72,13 @@ int bsed_amp_to_db(bsed_handle h, const float* mel, const float* unit_noise, flo
                    int t_in, int frames, const float* scaler_mean, const float* scaler_std,
                    float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* preprocess(audio, compute_log=True) -- or preprocess + the load-time ApplyLog -> PadOrTrunc -> [Normalize] of a clean
+ * clip -- in one call: the STFT + mel kernel also takes the per-clip maximum the 80 dB clamp needs, so the dB pass reads
+ * the amplitude-mel once.  mel [B][n_frames][128] receives the amplitude-mel (the cache format), out [B][frames][128] the
+ * log-mel; bit-identical to bsed_melspec followed by bsed_amp_to_db without noise.  workspace as bsed_amp_to_db. */
+int bsed_logmel(bsed_handle h, const float* audio, int B, int n_samples, int frames, const float* scaler_mean,
+                const float* scaler_std, float* mel, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Post-processing.         src/evaluation_measures.py:188-209, src/utilities/ManyHotEncoder.py:148-164
  * strong [B][T][C] probabilities -> events, class-major then time, per clip.

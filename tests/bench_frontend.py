@@ -33,6 +33,9 @@ def main():
     out = torch.empty(B, 1255, 128, device="cuda")
     ms2 = timeit(lambda: engine.amp_to_db(mel, 1255, out=out))
     print(f"amp_to_db {B} clips: {ms2:.3f} ms -> {2 * B * 1255 * 128 * 4 / ms2 / 1e6:.0f} GB/s (read + write)")
+    ms3 = timeit(lambda: engine.logmel(a, 1255))
+    print(f"logmel (fused STFT + mel + clip max, one dB pass) {B} clips: {ms3:.3f} ms -> {B / ms3 * 1e3:.0f} clips/s, "
+          f"{B * 1922560 / ms3 / 1e6:.1f} GB/s algorithmic")
 
 
 if __name__ == "__main__":

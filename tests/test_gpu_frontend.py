@@ -109,3 +109,19 @@ def test_reference_signature_preprocess_and_transforms():
     ref_clean, ref_noisy = ofe.transform(mel, unit_noise=unit.astype(np.float32))
     assert logmel_close(clean.numpy(), ref_clean)[0] <= RTOL
     assert logmel_close(noisy.numpy(), ref_noisy)[0] <= RTOL
+
+
+def test_fused_logmel_is_bit_identical_to_the_two_calls():
+    """bsed_logmel (STFT + mel with the clip maximum, then one dB pass) == bsed_melspec -> bsed_amp_to_db, with and without
+    the scaler, for full and ragged lengths."""
+    from bsed_b200 import engine
+    from bsed_b200.utilities import synth
+    clips = torch.from_numpy(synth.make_clips(3, seed=5)).cuda()
+    mean, std = torch.randn(128, device="cuda"), torch.rand(128, device="cuda") + 0.5
+    for n in (320000, 200001):
+        a = clips[:, :n].contiguous()
+        mel = engine.melspec(a)
+        for kw in ({}, dict(scaler_mean=mean, scaler_std=std)):
+            ref = engine.amp_to_db(mel, 1255, **kw)
+            got, mel2 = engine.logmel(a, 1255, return_mel=True, **kw)
+            assert torch.equal(mel2, mel) and torch.equal(got, ref)
