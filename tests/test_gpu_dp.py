@@ -41,3 +41,19 @@ def test_world1_equals_plain_optimizer_step(kind):
         assert torch.equal(va, vb)
     f = flags.cpu()
     assert int(f[0]) == 4 and int(f[16]) == 4 and int(f[32]) == 0 and int(f[33]) == 0     # arrive, depart, counter, error
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (run by hand with gpurun --gpus 2)")
+def test_two_rank_fused_step_equals_nccl_plus_optimizer():
+    """tests/dp_fused_check.py under torchrun: every rank holds different gradients; the fused kernel must give the same
+    parameters / EMA as NCCL all-reduce + bsed_opt_ema_step and bit-identical replicas."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "dp_fused_check.py")],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "replicas bit-identical: True" in r.stdout or "FUSED-DP UNAVAILABLE" in r.stdout, r.stdout[-2000:]
