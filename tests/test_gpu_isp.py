@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import bsed_models, max_abs, oracle_models, rel_l2
+from helpers import bsed_fpn_models, bsed_models, max_abs, oracle_fpn_models, oracle_models, rel_l2
 from oracle import train as otrain
 from bsed_b200.utilities import synth
 
@@ -59,14 +59,16 @@ def test_loss_terms_match_torch():
     assert rel_l2(dw.cpu().numpy(), w.grad.numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("p_drop", [0.0, 0.5])
-def test_isp_step_matches_oracle(p_drop):
+@pytest.mark.parametrize("p_drop,fpn", [(0.0, False), (0.5, False), (0.5, True)])
+def test_isp_step_matches_oracle(p_drop, fpn):
+    """fpn: the same step on CRNN_fpn, the model the reference's author trains with -ISP."""
     from bsed_b200.main import ISP_SLOTS, ShiftConsistencyTrainer
     n = 2
-    oc, op = oracle_models(seed=5, linear_std=0.2, dropout=p_drop, train=True)
-    tc, tp = oracle_models(seed=6, linear_std=0.2, dropout=p_drop, train=True)
-    m, p = bsed_models(oc, op, dropout=p_drop)
-    em, ep = bsed_models(tc, tp, dropout=p_drop)
+    omk, bmk = (oracle_fpn_models, bsed_fpn_models) if fpn else (oracle_models, bsed_models)
+    oc, op = omk(seed=5, linear_std=0.2, dropout=p_drop, train=True)
+    tc, tp = omk(seed=6, linear_std=0.2, dropout=p_drop, train=True)
+    m, p = bmk(oc, op, dropout=p_drop)
+    em, ep = bmk(tc, tp, dropout=p_drop)
     for mod in (m, p, em, ep):
         mod.train()
     for prm in list(tc.parameters()) + list(tp.parameters()) + list(em.parameters()) + list(ep.parameters()):
@@ -114,9 +116,11 @@ def test_isp_step_matches_oracle(p_drop):
             bad.append((fullname, e))
     assert not bad, bad
     # BatchNorm counters: 6 student / 3 teacher calls
-    assert int(m.cnn.batchnorm0.num_batches_tracked) == 6
-    assert int(oc.cnn.batchnorm0.num_batches_tracked) == 6
-    assert max_abs(m.cnn.batchnorm3.running_mean.cpu().numpy(), oc.state_dict()["cnn.batchnorm3.running_mean"].numpy()) < 1e-3
+    trunk, key3 = (m.cnn.cnn, "cnn.cnn.batchnorm3.running_mean") if fpn else (m.cnn, "cnn.batchnorm3.running_mean")
+    assert int(trunk.batchnorm0.num_batches_tracked) == 6
+    assert max_abs(trunk.batchnorm3.running_mean.cpu().numpy(), oc.state_dict()[key3].numpy()) < 1e-3
+    if fpn:
+        assert int(m.cnn.bn_fcn.num_batches_tracked) == 12 == int(oc.cnn.bn_fcn.num_batches_tracked)
     assert max_abs(em.rnn.rnn.weight_hh_l0.detach().cpu().numpy(), tc.state_dict()["rnn.rnn.weight_hh_l0"].numpy()) < 1e-4
 
 
