@@ -354,6 +354,7 @@ def _generic_step(model, predictor, ema_model, ema_predictor, optimizer, batch, 
                                               strong_ema if ema_model is not None else None,
                                               weak_ema if ema_model is not None else None, cons_w)
     torch.autograd.backward([cat_s, cat_w], [d_strong, d_weak])
+    shard.allreduce_module_grads([model, predictor])     # data parallel (no-op on one rank)
     optimizer.step()
     if ema_model is not None:
         update_ema_variables(model, ema_model, 0.999, global_step + 1)
@@ -371,6 +372,7 @@ def adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_
     optimizer_d.zero_grad()
     domain_loss = discriminator(syn_strong_pred, syn_d_input, strong_pred, d_input)
     domain_loss.backward()
+    shard.allreduce_module_grads([model, discriminator])     # data parallel: replicas take the same adversarial step
     optimizer_crnn.step()
     optimizer_d.step()
     return domain_loss.detach()

@@ -31,6 +31,24 @@ def allreduce_gradients(flat_grads, group=None):
     return 1.0 / n
 
 
+def allreduce_module_grads(modules, group=None):
+    """Average the .grad of every parameter of `modules` over the ranks with ONE all-reduce of a flat copy (the generic
+    torch-optimizer paths: the adversarial update of src/main_scmt_ada_weak_seperate.py:314-335 under data parallelism)."""
+    n = world_size(group)
+    if n == 1:
+        return
+    grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / n)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
 def gather_in_rank_order(obj, group=None):
     """Concatenate per-rank Python lists (event lists, pseudo-label rows) in rank order."""
     n = world_size(group)

@@ -34,6 +34,12 @@ def _worker(rank, world, port, out):
         ev = [(rank, i, i + 1) for i in range(rank + 1)]
         allev = shard.gather_in_rank_order(ev)
         torch.save(allev, os.path.join(out, f"e{rank}.pt"))
+        # generic-optimizer paths: one flat all-reduce averages the parameter gradients of several modules
+        lin = torch.nn.Linear(3, 2)
+        for prm in lin.parameters():
+            prm.grad = torch.full_like(prm, float(rank + 1))
+        shard.allreduce_module_grads([lin])
+        torch.save([prm.grad.clone() for prm in lin.parameters()], os.path.join(out, f"g{rank}.pt"))
         # the fused peer-memory step cannot be set up without GPUs: every rank must get None (and none may hang), so the
         # trainers fall back to the all-reduce path together
         buf = torch.zeros(16)
@@ -53,3 +59,5 @@ def test_gradient_exchange_and_gather_world2(tmp_path):
         ev = torch.load(os.path.join(str(tmp_path), f"e{r}.pt"))
         assert ev == [(0, 0, 1), (1, 0, 1), (1, 1, 2)]
         assert torch.load(os.path.join(str(tmp_path), f"d{r}.pt")) is True
+        for gr in torch.load(os.path.join(str(tmp_path), f"g{r}.pt")):
+            assert torch.allclose(gr, torch.full_like(gr, 1.5))
