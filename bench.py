@@ -36,6 +36,28 @@ STEP_FLOP = (24 * 3 + 12) * FLOP_PER_CLIP_FWD             # 309.5 GFLOP
 FLOP_PER_CLIP_FWD_FPN = FLOP_PER_CLIP_FWD + 0.507e9
 
 
+class StdoutGuard:
+    """Rank 0 must print exactly ONE line on stdout.  Libraries may write banners to the C-level stdout (NCCL prints its
+    version there when NCCL_DEBUG is set on the box), so during the run file descriptor 1 points at stderr and the JSON
+    line goes to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -134,7 +156,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_b200(args):
+def run_b200(args, out):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,12 +368,12 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_pseudo_label(args):
+def run_pseudo_label(args, out):
     """Secondary workload (BASELINE.json configs[4]): 1 h of synthetic audio (360 clips) -> log-mel -> CRNN + Predictor
     eval -> weak labels + strong events, clips sharded over the ranks, audio in pinned host memory."""
     import numpy as np
@@ -386,7 +408,7 @@ def run_pseudo_label(args):
     e0.record()
     reps = max(1, args.steps // 4)
     for _ in range(reps):
-        out = pseudo_label_stream(audio, m, p, batch_clips=48, rank=rank, world=world, gather=False)
+        res = pseudo_label_stream(audio, m, p, batch_clips=48, rank=rank, world=world, gather=False)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -394,14 +416,14 @@ def run_pseudo_label(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         cps = n_clips * reps / (float(ms) * 1e-3)
-        print(json.dumps({"metric": "log-mel + CRNN pseudo-label inference clips/s", "value": cps, "unit": "clips/s",
+        out.emit(json.dumps({"metric": "log-mel + CRNN pseudo-label inference clips/s", "value": cps, "unit": "clips/s",
                           "n_gpus": world, "steps": reps, "warmup": args.warmup, "ms_per_step": float(ms) / reps,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": m.precision or engine.default_precision(), "data": "synthetic",
                           "config": {"workload": "1 h synthetic audio (360 x 10 s clips) from pinned host memory -> framed STFT "
                                                  "-> mel -> dB -> CRNN + Predictor eval -> weak labels + median-filtered events "
                                                  "(pseudo_labeling.pseudo_label_stream), clips sharded over ranks",
-                                     "events_rank0": len(out["events"]), "audio_GBps": cps * 1280000 / 1e9}}), flush=True)
+                                     "events_rank0": len(res["events"]), "audio_GBps": cps * 1280000 / 1e9}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -420,10 +442,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "pseudo_label":
-        run_pseudo_label(args)
-    else:
-        run_b200(args)
+        return
+    with StdoutGuard() as out:
+        if args.workload == "pseudo_label":
+            run_pseudo_label(args, out)
+        else:
+            run_b200(args, out)
 
 
 if __name__ == "__main__":
