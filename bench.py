@@ -3,15 +3,23 @@
 (src/main.py:train_mt shapes: 12 synthetic + 12 real clips through the student forward + backward,
 the 12 real clips through the teacher forward, BCE/MSE losses, Adam, EMA), plus the log-mel frontend.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|pseudo_label]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line (rank 0).  `value` = student clips/s of the whole job with inputs resident in HBM;
-`e2e` = the same step driven from pinned HOST buffers through the public trainer call (H2D of the
-inputs and D2H of the losses inside the timed region); `roofline` = the dominant kernel class timed
-live with CUDA events; `cpu_baseline` = the oracle port of the reference step on the host cores.
---impl reference times that CPU port alone (the reference is 100% Python and cannot travel to the GPU
-box; oracle/crnn.py restates its modules with the same torch.nn layers -- see DESIGN.md).
+Prints ONE JSON line (rank 0).
+  value            student clips/s of the whole job, inputs resident in HBM, library DEFAULT precision (error-compensated
+                   3xTF32 on the tcgen05 tensor cores: the <= 1e-3 parity mode)
+  e2e              the same step driven from pinned HOST buffers through the public trainer call (H2D of the inputs
+                   and D2H of the losses inside the timed region)
+  roofline         the conv forward + data-gradient kernel class, timed live with CUDA events over the timed steps
+  cpu_baseline     the oracle port of the reference step on the host cores, the SAME 12 + 12 + 12 configuration
+  parity           (N = 1) the first GPU step against that CPU oracle step on the same clips / weights / dropout masks
+  single_pass_tf32 the same step in the single-pass tf32 mode (what cuDNN gives the reference's convolutions on a GPU)
+  gpu_eager_baseline  the reference's torch.nn modules (oracle/crnn.py restates them layer for layer) in eager mode on
+                   the same B200, stock cuDNN / cuBLAS settings, same step -- the like-for-like GPU comparison
+  sustained        the device-resident step again over >= 300 steps (>= 2 s of GPU time)
+--impl reference times the CPU port alone (the reference is 100% Python and cannot travel to the GPU box;
+oracle/crnn.py restates its modules with the same torch.nn layers -- see DESIGN.md).
 """
 import argparse
 import json
@@ -30,10 +38,12 @@ METRIC = "CRNN mean-teacher train clips/s"
 N_SYN = N_REAL = 12
 CLIP_BYTES_FRONTEND = 320000 * 4 + 1255 * 128 * 4
 FLOP_PER_CLIP_FWD = 3.684e9
-STEP_FLOP = (24 * 3 + 12) * FLOP_PER_CLIP_FWD             # 309.5 GFLOP
 # CRNN_fpn adds per clip: the shared stage twice (conv 3x3 + GLU on 313 + 156 frames, 77 MMAC), rnn_2 / rnn_4
 # ((156 + 78) / 313 of the GRU's 154 MMAC) and the two 512 -> 256 merges (61 MMAC): + 0.507 GFLOP forward
 FLOP_PER_CLIP_FWD_FPN = FLOP_PER_CLIP_FWD + 0.507e9
+# conv forward + data gradient, algorithmic: blocks 1-6 forward 1.385 GMAC per clip (block 0 runs on
+# the CUDA cores and is not in the class), data gradient of blocks 1-6 the same MACs
+CONV_CLASS_GMAC_PER_CLIP = 1.385
 
 
 class StdoutGuard:
@@ -96,67 +106,159 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_mean_teacher(n_syn, n_real, steps, warmup, threads=None, fpn=False):
-    """The oracle port of the reference step (torch.nn Conv2d / BatchNorm2d / GRU on the host cores)."""
+# ------------------------------------------------------------------------------------------------
+# baselines (test infrastructure: the oracle's restatement of the reference modules)
+# ------------------------------------------------------------------------------------------------
+def _oracle_models(fpn, seed_s=1, seed_t=2, dropout=0.5):
     import torch
     from oracle import crnn as ocrnn
-    from oracle import train as otrain
-    from bsed_b200.utilities import synth
-    # all host cores (torchrun exports OMP_NUM_THREADS=1; the baseline runs on rank 0 alone)
-    torch.set_num_threads(threads or os.cpu_count() or 1)
     cls = ocrnn.OracleCRNNfpn if fpn else ocrnn.OracleCRNN
-    oc = cls(**ocrnn.CRNN_KWARGS)
-    op = ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
-    tc = cls(**ocrnn.CRNN_KWARGS)
-    tp = ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
-    ocrnn.reference_style_init(oc, op, 1)
-    ocrnn.reference_style_init(tc, tp, 2)
+    kw = {**ocrnn.CRNN_KWARGS, "dropout": dropout}
+    oc, op = cls(**kw), ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
+    tc, tp = cls(**kw), ocrnn.OraclePredictor(**ocrnn.PREDICTOR_KWARGS)
+    ocrnn.reference_style_init(oc, op, seed_s, 0.2)
+    ocrnn.reference_style_init(tc, tp, seed_t, 0.2)
     for m in (oc, op, tc, tp):
         m.train()
     for prm in list(tc.parameters()) + list(tp.parameters()):
         prm.detach_()
+    return oc, op, tc, tp
+
+
+def _step_inputs(n_syn, n_real):
+    import torch
+    from bsed_b200.utilities import synth
     xs = torch.from_numpy(synth.make_logmel_like(n_syn, seed=3))
     xr = torch.from_numpy(synth.make_logmel_like(n_real, seed=4))
+    xr_ema = xr + 0.05 * torch.from_numpy(synth.make_logmel_like(n_real, seed=6))
     ts = torch.from_numpy(synth.make_targets(n_syn, seed=5))
+    return xs, xr, xr_ema, ts
+
+
+def _stock_dropout(mod):
+    """The reference uses nn.Dropout; the hash dropout of the oracle is a parity-test device (numpy masks on the host)."""
+    from torch import nn
+    from oracle import crnn as ocrnn
+    for name, child in list(mod.named_children()):
+        if isinstance(child, (ocrnn.HashDropout, ocrnn.CycleHashDropout)):
+            setattr(mod, name, nn.Dropout(child.p))
+        else:
+            _stock_dropout(child)
+
+
+def cpu_mean_teacher(n_syn, n_real, steps, warmup, threads=None, fpn=False, keep_first=False):
+    """The oracle port of the reference step (torch.nn Conv2d / BatchNorm2d / GRU / Dropout on the host cores), the full
+    n_syn + n_real student clips and n_real teacher clips per step.  keep_first: one extra untimed step 0 with the hash
+    dropout masks the CUDA kernels use; its losses / probabilities and the initial weights are returned so the GPU step
+    can be compared with it (bench `parity`)."""
+    import torch
+    from oracle import train as otrain
+    # all host cores (torchrun exports OMP_NUM_THREADS=1; the baseline runs on rank 0 alone)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    oc, op, tc, tp = _oracle_models(fpn)
+    xs, xr, xr_ema, ts = _step_inputs(n_syn, n_real)
     opt = torch.optim.Adam(list(oc.parameters()) + list(op.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    init = first = None
+    if keep_first:
+        init = [{k: v.clone() for k, v in m.state_dict().items()} for m in (oc, op, tc, tp)]
+
+        def hook(tag):
+            # device batch order: synthetic [0, ns), real [ns, ns + nr), teacher [ns + nr, ...)
+            (tc if tag == "teacher" else oc).set_dropout_keys(2023, 0, {"teacher": n_syn + n_real, "syn": 0, "real": n_syn}[tag])
+        loss, parts, outs = otrain.mt_step(oc, op, tc, tp, opt, xr, xr_ema, xs, ts, 0, 5000, ema_flavour="state_dict",
+                                           dropout_hook=hook)
+        first = dict(parts={k: float(v) for k, v in parts.items()}, strong=outs["strong"].numpy(), weak=outs["weak"].numpy(),
+                     syn_strong=outs["syn_strong"].numpy())
     for m in (oc, tc):
-        m.set_dropout_keys(2023, 0, 0)
+        _stock_dropout(m)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        otrain.mt_step(oc, op, tc, tp, opt, xr, xr, xs, ts, i, 500, ema_flavour="state_dict")
+        loss, _, _ = otrain.mt_step(oc, op, tc, tp, opt, xr, xr_ema, xs, ts, 1 + i, 5000, ema_flavour="state_dict")
+        loss.item()              # src/main.py:511 reads the loss every iteration
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
     total = sum(times)
-    return (n_syn + n_real) * steps / total, total / steps, torch.get_num_threads()
+    res = dict(clips_per_s=(n_syn + n_real) * steps / total, sec_per_step=total / steps, threads=torch.get_num_threads())
+    return (res, init, first) if keep_first else res
+
+
+def gpu_eager_mean_teacher(n_syn, n_real, steps, warmup, fpn, dev, allow_tf32=None):
+    """The reference's own module structure (torch.nn.Conv2d / BatchNorm2d / Linear / GRU / Dropout, restated layer for
+    layer in oracle/crnn.py) in PyTorch eager mode on the B200, stock cuDNN / cuBLAS settings, driven by the reference's
+    statement order (oracle/train.py:mt_step = src/main.py:250-254,339-343,376-477,517-523 incl. the per-step
+    loss read-back of :511): the like-for-like GPU comparison BASELINE.md 5.4 asks for."""
+    import torch
+    from oracle import train as otrain
+    if allow_tf32 is not None:
+        torch.backends.cudnn.allow_tf32 = allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    oc, op, tc, tp = _oracle_models(fpn)
+
+    for m in (oc, tc):
+        _stock_dropout(m)
+    for m in (oc, op, tc, tp):
+        m.to(dev).train()
+    xs, xr, xr_ema, ts = [t.to(dev) for t in _step_inputs(n_syn, n_real)]
+    opt = torch.optim.Adam(list(oc.parameters()) + list(op.parameters()), lr=5e-4, betas=(0.9, 0.999))
+
+    def step(i):
+        loss, _, _ = otrain.mt_step(oc, op, tc, tp, opt, xr, xr_ema, xs, ts, i, 5000, ema_flavour="state_dict")
+        return loss.item()       # src/main.py:511 reads the loss every iteration
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(value=(n_syn + n_real) / (ms * 1e-3), unit="clips/s", ms_per_step=ms, steps=steps, warmup=warmup,
+                cudnn_allow_tf32=bool(torch.backends.cudnn.allow_tf32),
+                matmul_allow_tf32=bool(torch.backends.cuda.matmul.allow_tf32),
+                kind="port (oracle/crnn.py restates src/models/{CNN,RNN,CRNN}.py with the same torch.nn layers; "
+                     "oracle/train.py:mt_step is src/main.py:train_mt's statement order)",
+                torch=torch.__version__, cudnn=torch.backends.cudnn.version())
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ns = nr = 2
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 2))
     fpn = args.model == "crnn_fpn"
-    cps, sec, threads = cpu_mean_teacher(ns, nr, steps, warmup, fpn=fpn)
+    # the SAME configuration as the GPU arm: 12 synthetic + 12 real student clips, 12 teacher clips per step.  One step
+    # is ~5 s of CPU work on 16 cores, so more than 40 steps would not end "within a few minutes": capped there.
+    steps = max(1, min(args.steps, 40))
+    warmup = max(0, min(args.warmup, 10))
+    r = cpu_mean_teacher(N_SYN, N_REAL, steps, warmup, fpn=fpn)
+    cps, sec, threads = r["clips_per_s"], r["sec_per_step"], r["threads"]
     line = {
         "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mean-teacher CRNN training step (main.py shapes), CPU sample of 2 synthetic + 2 real clips "
-                               "per step instead of 12 + 12 (clips/s is per clip)", "model": args.model,
-                   "parallelism": "cpu threads"},
+        "config": {"workload": "mean-teacher CRNN training step (src/main.py:train_mt, pretrain -mt): 12 synthetic + 12 real "
+                               "clips student fwd+bwd, 12 clips teacher fwd (train mode), BCE+MSE, Adam lr 5e-4, state-dict "
+                               "EMA; log-mel features 1255x128 resident in host memory",
+                   "model": args.model, "clips_per_step_per_gpu": 24, "parallelism": "cpu threads"},
         "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps x (2 syn + 2 real student clips, 2 teacher clips), oracle port of "
-                                   "src/main.py:train_mt with the reference's torch.nn layers"},
+                         "sample": f"{steps} steps x (12 syn + 12 real student clips, 12 teacher clips) after {warmup} warm-up "
+                                   "steps, oracle port of src/main.py:train_mt with the reference's torch.nn layers"},
         "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
 def run_b200(args, out):
+    import ctypes as C
+    import numpy as np
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,21 +283,25 @@ def run_b200(args, out):
     model_cls = CRNN_fpn if fpn else CRNN
     step_flop = (24 * 3 + 12) * (FLOP_PER_CLIP_FWD_FPN if fpn else FLOP_PER_CLIP_FWD)
     dev = torch.device("cuda", local)
+    default_precision = engine.default_precision()
 
     torch.manual_seed(2023 + rank)
 
-    def make():
-        m, p = model_cls(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+    def make(precision=None):
+        m, p = model_cls(**engine.REFERENCE_CRNN_KWARGS, precision=precision), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
         weights_init(m)
         weights_init(p)
         return m.to(dev).train(), p.to(dev).train()
 
-    model, predictor = make()
-    ema_model, ema_predictor = make()
-    for prm in list(ema_model.parameters()) + list(ema_predictor.parameters()):
-        prm.detach_()
-    trainer = MeanTeacherTrainer(model, predictor, ema_model, ema_predictor, lr=5e-4, n_syn=N_SYN, n_real=N_REAL,
-                                 dropout_seed=2023 + rank)
+    def make_trainer(precision=None):
+        model, predictor = make(precision)
+        ema_model, ema_predictor = make(precision)
+        for prm in list(ema_model.parameters()) + list(ema_predictor.parameters()):
+            prm.detach_()
+        return MeanTeacherTrainer(model, predictor, ema_model, ema_predictor, lr=5e-4, n_syn=N_SYN, n_real=N_REAL,
+                                  dropout_seed=2023 + rank, precision=precision)
+
+    trainer = make_trainer()
 
     # synthetic clips -> log-mel through our own frontend (also measured below)
     clips = torch.from_numpy(synth.make_clips(N_SYN + N_REAL, seed=2023 + rank)).to(dev)
@@ -213,10 +319,14 @@ def run_b200(args, out):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, before_timed=None):
+        """W untimed warm-up steps, then EXACTLY `steps` steps between two events, barrier + synchronize on both sides,
+        max over ranks.  before_timed runs between the warm-up and the timed region (profile / launch-counter reset)."""
         for i in range(warmup):
             fn(i)
         sync_all()
+        if before_timed is not None:
+            before_timed()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -232,7 +342,7 @@ def run_b200(args, out):
     if rank == 0:
         sampler.start()
 
-    # ---- device-resident run (value) with the dominant kernel class timed by CUDA events
+    # ---- device-resident run (value) with the conv kernel class timed by CUDA events over the SAME timed steps
     # host time to enqueue one step (no synchronisation inside): must stay below the device time or the GPU starves
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -241,15 +351,23 @@ def run_b200(args, out):
     host_enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
     torch.cuda.synchronize()
 
-    launches0 = lib.bsed_launch_count()
-    lib.bsed_profile_begin(1)
-    ms = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup)
-    import ctypes as C
+    counters = {}
+
+    def begin_profile():
+        counters["launches0"] = lib.bsed_launch_count()
+        lib.bsed_profile_begin(1)
+
+    ms = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup, begin_profile)
+    launches = lib.bsed_launch_count() - counters["launches0"]
     pm, pf, pb, pn = C.c_double(), C.c_double(), C.c_double(), C.c_int()
     _lib.check(lib.bsed_profile_end(C.byref(pm), C.byref(pf), C.byref(pb), C.byref(pn)), "profile_end")
-    launches = (lib.bsed_launch_count() - launches0)
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
     value = (N_SYN + N_REAL) * world * args.steps / (ms * 1e-3)
+
+    # ---- the same device-resident step over >= 300 steps (>= 2 s of GPU time)
+    sus_steps = max(300, args.steps)
+    ms_sus = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), sus_steps, 0)
+    sustained = {"steps": sus_steps, "ms_per_step": ms_sus / sus_steps, "seconds": ms_sus * 1e-3,
+                 "value": (N_SYN + N_REAL) * world * sus_steps / (ms_sus * 1e-3), "unit": "clips/s"}
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the losses, every step.  The copies of step i+1 are
     # issued on a copy stream while step i computes (double-buffered device inputs), as a training loop's prefetcher
@@ -285,51 +403,92 @@ def run_b200(args, out):
         hloss.copy_(losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss (reference: loss.item())
 
-    ms_e2e = timed(e2e_step, args.steps, 1)
+    ms_e2e = timed(e2e_step, args.steps, 2)
     e2e = (N_SYN + N_REAL) * world * args.steps / (ms_e2e * 1e-3)
     h2d_bytes = sum(t.numel() * 4 for t in (hx, hxe, hxs, hts))
 
+    # ---- the single-pass tf32 mode on the same step (not the parity mode; what cuDNN TF32 convolutions correspond to)
+    other = "tf32" if default_precision != "tf32" else "tf32x3"
+    tr2 = make_trainer(other)
+    ms2 = timed(lambda i: tr2.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup)
+    other_mode = {"precision": other, "value": (N_SYN + N_REAL) * world * args.steps / (ms2 * 1e-3), "unit": "clips/s",
+                  "ms_per_step": ms2 / args.steps}
+    del tr2
+    torch.cuda.empty_cache()
+
     # ---- frontend: audio resident in HBM -> log-mel (second half of the metric)
     fe_clips = clips.repeat(16, 1)[:256].contiguous()                 # 256 clips = 328 MB > L2
-    lib.bsed_profile_begin(5)
-    ms_fe = timed(lambda i: engine.logmel(fe_clips, 1255), max(3, args.steps // 2), 3)       # STFT + mel + dB, one call
+    fe_steps = max(3, args.steps // 2)
+    ms_fe = timed(lambda i: engine.logmel(fe_clips, 1255), fe_steps, 3, lambda: lib.bsed_profile_begin(5))   # STFT + mel + dB
     fm = C.c_double()
     fn_ = C.c_int()
     _lib.check(lib.bsed_profile_end(C.byref(fm), None, None, C.byref(fn_)), "profile_end")
-    fe_steps = max(3, args.steps // 2)
     fe_cps = 256 * world * fe_steps / (ms_fe * 1e-3)
     # the dB transform alone (the HBM-bound elementwise half of the frontend): algorithmic bytes = mel in + log-mel out
     fe_mel = engine.melspec(fe_clips)
     fe_out = torch.empty(256, 1255, 128, device=dev)
-    lib.bsed_profile_begin(7)
-    timed(lambda i: engine.amp_to_db(fe_mel, 1255, out=fe_out), fe_steps, 3)
+    timed(lambda i: engine.amp_to_db(fe_mel, 1255, out=fe_out), fe_steps, 3, lambda: lib.bsed_profile_begin(7))
     dm, db_, dn = C.c_double(), C.c_double(), C.c_int()
     _lib.check(lib.bsed_profile_end(C.byref(dm), None, C.byref(db_), C.byref(dn)), "profile_end")
     db_gbps = db_.value / (dm.value * 1e-3) / 1e9 if dm.value > 0 else None
+    del fe_clips, fe_mel, fe_out
+    torch.cuda.empty_cache()
 
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
         clocks = sampler.summary()
         conv_tflops = pf.value / (pm.value * 1e-3) / 1e12 if pm.value > 0 else None
-        # the CPU port on this box's host cores, bounded sample
+        cpu_baseline = parity = eager = None
         if world == 1:
-            cps_cpu, sec_cpu, threads = cpu_mean_teacher(2, 2, 12, 1, fpn=fpn)
-            cpu_baseline = {"value": cps_cpu, "unit": "clips/s", "cores": threads, "kind": "port",
-                            "sample": "12 steps of 2 synthetic + 2 real clips (oracle port of src/main.py:train_mt, "
-                                      "torch.nn on host cores, %.1f s of CPU work)" % (sec_cpu * 12)}
-        else:
-            cpu_baseline = None     # reported at N = 1 only
+            # ---- the reference modules in PyTorch eager mode on this B200 (stock cuDNN / cuBLAS)
+            eager = gpu_eager_mean_teacher(N_SYN, N_REAL, 20, 5, fpn, dev)
+            torch.cuda.empty_cache()
+            # ---- the CPU port on this box's host cores: the SAME 12 + 12 + 12 step, 3 steps after 1 warm-up, and the
+            # first GPU step (default precision and single-pass tf32) against its first step
+            r, init, first = cpu_mean_teacher(N_SYN, N_REAL, 3, 1, fpn=fpn, keep_first=True)
+            cpu_baseline = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["threads"], "kind": "port",
+                            "ms_per_step": r["sec_per_step"] * 1e3,
+                            "sample": "3 steps (after 1 warm-up) of 12 synthetic + 12 real student clips and 12 teacher clips "
+                                      "(oracle port of src/main.py:train_mt, torch.nn on host cores, %.0f s of CPU work)"
+                                      % (r["sec_per_step"] * 4)}
+            xs_c, xr_c, xr_ema_c, ts_c = _step_inputs(N_SYN, N_REAL)
+            parity = {"against": "first step of the CPU oracle port on the same clips, weights and dropout masks "
+                                 "(12 + 12 + 12 clips)", "tolerance_north_star": 1e-3}
+            want = np.array([first["parts"][k] for k in ("strong_class", "weak_class", "cons_strong", "cons_weak")])
+            for prec in (default_precision, other):
+                mods = []
+                for sd_c, sd_p in ((init[0], init[1]), (init[2], init[3])):
+                    m_, p_ = model_cls(**engine.REFERENCE_CRNN_KWARGS, precision=prec), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+                    m_.load_state_dict(sd_c)
+                    p_.load_state_dict(sd_p)
+                    mods += [m_.to(dev).train(), p_.to(dev).train()]
+                for prm in list(mods[2].parameters()) + list(mods[3].parameters()):
+                    prm.detach_()
+                tr = MeanTeacherTrainer(*mods, lr=5e-4, n_syn=N_SYN, n_real=N_REAL, dropout_seed=2023, precision=prec)
+                got = tr.step(xr_c.to(dev), xr_ema_c.to(dev), xs_c.to(dev), ts_c.to(dev), 0, 5000).cpu().numpy()
+                parity[prec] = {
+                    "strong_max_abs_err": float(np.abs(tr.last["strong"][N_SYN:].cpu().numpy() - first["strong"]).max()),
+                    "syn_strong_max_abs_err": float(np.abs(tr.last["strong"][:N_SYN].cpu().numpy() - first["syn_strong"]).max()),
+                    "weak_max_abs_err": float(np.abs(tr.last["weak"][N_SYN:].cpu().numpy() - first["weak"]).max()),
+                    "loss_terms_max_rel_err": float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-6)))}
+                del tr, mods
+                torch.cuda.empty_cache()
+        conv_flop_algorithmic = (36 + 24) * CONV_CLASS_GMAC_PER_CLIP * 2e9 if not fpn else None
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if trainer.plan.precision == "tf32" else "f32",
+            "dtype": {"tf32x3": "tf32x3", "tf32": "tf32", "fp32": "f32"}[trainer.plan.precision],
             "data": "synthetic",
             "config": {"workload": "mean-teacher CRNN training step (src/main.py:train_mt, pretrain -mt): per GPU 12 synthetic + "
                                    "12 real clips student fwd+bwd, 12 clips teacher fwd (train mode), BCE+MSE, Adam lr 5e-4, "
                                    "state-dict EMA; log-mel features 1255x128 resident in HBM",
-                       "precision": trainer.plan.precision + (" (tcgen05 kind::tf32 contractions, fp32 accumulate; everything "
-                                                              "else fp32)" if trainer.plan.precision == "tf32" else ""),
+                       "precision": {"tf32x3": "tf32x3: error-compensated 3xTF32 on tcgen05 (a*w_hi + a*w_lo + a_lo*w_hi, fp32 "
+                                               "accumulation in TMEM) for every forward / data-gradient contraction = fp32-grade, "
+                                               "the <= 1e-3 parity mode; weight-gradient reductions single-pass tf32; everything "
+                                               "else fp32",
+                                     "tf32": "tf32 (single-pass tcgen05 kind::tf32 contractions, fp32 accumulate; everything else fp32)",
+                                     "fp32": "fp32 CUDA cores"}[trainer.plan.precision],
                        "model": args.model + (" (src/models/CRNN.py:243-337)" if fpn else " (src/models/CRNN.py:178-240)"),
                        "clips_per_step_per_gpu": 24,
                        "parallelism": f"dp{world} (%s of the %.2f MB flat gradient)" % (
@@ -340,20 +499,26 @@ def run_b200(args, out):
                        "step_gflop_algorithmic": step_flop / 1e9},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches_timed),
-            "roofline": {"kernel": ("tc_conv_col_kernel + tc_kmajor_kernel (tcgen05 tf32 implicit-GEMM 3x3 conv forward + data "
-                                    "gradient, TMA-fed; all such launches of the step)"
-                                    if trainer.plan.precision == "tf32" else
+            "gpu_launches": int(launches),
+            "sustained": sustained,
+            "roofline": {"kernel": ("tc_conv_col_kernel + tc_kmajor_kernel conv launches (tcgen05 implicit-GEMM 3x3 conv forward "
+                                    "+ data gradient of blocks 1-6, TMA-fed; all such launches of the timed steps)"
+                                    if trainer.plan.precision != "fp32" else
                                     "gemm_nn_kernel<ConvRows> (implicit-GEMM 3x3 conv forward + data gradient, fp32 SIMT)"),
-                         "bound": "tensor", "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "bound": "tensor",
+                         # ALGORITHMIC flops of the launches (2*9*Cin*Cout per output pixel; the 3xTF32 mode executes three
+                         # MMAs per algorithmic one, the pixel-pair view of block 1 counts its true 16 input channels)
+                         "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None,
-                         # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 18 conv launches of one step,
-                         # per launch (profiles/r01_ncu_tc_kernels.md); algorithmic bytes per launch beside it
-                         "traffic": 3.899e7 if trainer.plan.precision == "tf32" else None,
-                         "traffic_unit": "bytes per launch (average over the conv forward + data-gradient launches)",
+                         "traffic": None,
+                         "traffic_note": "ncu dram bytes of these launches: profiles/ (see DESIGN.md section 5)",
+                         "algorithmic_gflop_per_step": pf.value / args.steps / 1e9,
+                         "algorithmic_gflop_per_step_expected": conv_flop_algorithmic / 1e9 if conv_flop_algorithmic else None,
                          "algorithmic_bytes_per_launch": pb.value / pn.value if pn.value else None,
+                         "executed_mma_factor": 3 if trainer.plan.precision == "tf32x3" else 1,
                          "peak_source": peaks["source"] + " bf16 sustained (tf32 nominal dense peak is half of bf16)",
-                         "launches": pn.value,
+                         "launches": pn.value, "launches_per_step": pn.value / args.steps,
+                         "ms_per_step": pm.value / args.steps,
                          "share_of_step": pm.value / ms if ms else None,
                          "step_tflops": step_flop * args.steps / (ms * 1e-3) / 1e12},
             "frontend": {"metric": "log-mel frontend", "clips_per_s": fe_cps, "algorithmic_GBps": fe_cps * CLIP_BYTES_FRONTEND / 1e9,
@@ -365,6 +530,9 @@ def run_b200(args, out):
                                           "ms_per_256_clips": dm.value / max(1, dn.value),
                                           "note": "algorithmic bytes (amplitude-mel read once + log-mel written once); the per-clip "
                                                   "80 dB clamp needs the clip maximum first, so the kernel pair reads the mel twice"}},
+            "single_pass_tf32" if other == "tf32" else "parity_mode_tf32x3": other_mode,
+            "parity": parity,
+            "gpu_eager_baseline": eager,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }
@@ -397,7 +565,7 @@ def run_pseudo_label(args, out):
     weights_init(p)
     m, p = m.to(dev).eval(), p.to(dev).eval()
     base = synth.make_clips(24, seed=11).reshape(-1)
-    audio = torch.from_numpy(np.tile(base, 15)).pin_memory()          # 360 clips = 1 h at 32 kHz
+    audio = torch.from_numpy(np.tile(base, 15 * max(1, args.replicate))).pin_memory()   # 360 clips = 1 h at 32 kHz (x replicate)
     n_clips = audio.shape[0] // 320000
     for _ in range(max(1, args.warmup)):
         pseudo_label_stream(audio, m, p, batch_clips=48, rank=rank, world=world, gather=False)
@@ -420,9 +588,9 @@ def run_pseudo_label(args, out):
                           "n_gpus": world, "steps": reps, "warmup": args.warmup, "ms_per_step": float(ms) / reps,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": m.precision or engine.default_precision(), "data": "synthetic",
-                          "config": {"workload": "1 h synthetic audio (360 x 10 s clips) from pinned host memory -> framed STFT "
+                          "config": {"workload": "%d x 10 s clips of synthetic audio (%.1f h) from pinned host memory -> framed STFT "
                                                  "-> mel -> dB -> CRNN + Predictor eval -> weak labels + median-filtered events "
-                                                 "(pseudo_labeling.pseudo_label_stream), clips sharded over ranks",
+                                                 "(pseudo_labeling.pseudo_label_stream), clips sharded over ranks" % (n_clips, n_clips / 360),
                                      "events_rank0": len(res["events"]), "audio_GBps": cps * 1280000 / 1e9}}))
     if world > 1:
         dist.destroy_process_group()
@@ -438,6 +606,7 @@ def main():
                     help="crnn = src/models/CRNN.py:CRNN (default, the headline); crnn_fpn = CRNN_fpn (SURVEY 8f-1)")
     ap.add_argument("--workload", default="train", choices=["train", "pseudo_label"],
                     help="train = the headline mean-teacher step (default); pseudo_label = configs[4] inference pipeline")
+    ap.add_argument("--replicate", type=int, default=1, help="pseudo_label: repeat the 1 h stream this many times")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -31,9 +31,9 @@ SYMBOLS = [
     "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
     "bsed_bn_rows_workspace_bytes", "bsed_bn_rows_train", "bsed_bn_rows_backward", "bsed_col2im_nhwc",
     "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward", "bsed_gemm_tn_tc",
-    "bsed_logmel",
+    "bsed_logmel", "bsed_conv3x3_tc3", "bsed_gemm_nt_tc3",
 ]
-PRECISIONS = {"fp32": 0, "tf32": 1}
+PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
 class CrnnCfg(C.Structure):
@@ -149,6 +149,8 @@ def load():
         proto("bsed_gemm_tn_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i64, vp, sz, vp)
         proto("bsed_gemm_nt_tc", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp)
         proto("bsed_conv3x3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+        proto("bsed_conv3x3_tc3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
+        proto("bsed_gemm_nt_tc3", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp)
         proto("bsed_disc_set_precision", i32, vp, i32)
         proto("bsed_disc_param_count", i64)
         proto("bsed_disc_bn_buffer_count", i64)

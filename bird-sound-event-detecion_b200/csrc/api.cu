@@ -429,7 +429,33 @@ extern "C" int bsed_conv3x3_tc(bsed_handle h, const float* x, const float* weigh
   tb.ops[0].d0 = Cout;
   tb.ops[0].d1 = Cin;
   BSED_TRY(run_prep(tb, as_stream(stream)));
-  return tc_conv3x3(x, wpack, y, B, T, F, Cin, Cout, bias, 0, h->num_sms, as_stream(stream));
+  return tc_conv3x3(x, wpack, nullptr, y, B, T, F, Cin, Cout, bias, 0, h->num_sms, as_stream(stream));
+}
+
+extern "C" int bsed_conv3x3_tc3(bsed_handle h, const float* x, const float* weight, const float* bias, float* y, int B,
+                                int T, int F, int Cin, int Cout, float* wpack, void* stream) {
+  BSED_REQUIRE(h && x && weight && y && wpack, "bsed_conv3x3_tc3: null argument");
+  PrepTable tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.n = 1;
+  tb.ops[0].type = PREP_CONV_KMAJOR;
+  tb.ops[0].src = weight;
+  tb.ops[0].dst = wpack;
+  tb.ops[0].d0 = Cout;
+  tb.ops[0].d1 = Cin;
+  BSED_TRY(run_prep(tb, as_stream(stream)));
+  const long long n = 9LL * Cin * Cout;
+  BSED_TRY(split_hi_lo(wpack, wpack + n, n, as_stream(stream)));
+  return tc_conv3x3(x, wpack, wpack + n, y, B, T, F, Cin, Cout, bias, 0, h->num_sms, as_stream(stream));
+}
+
+extern "C" int bsed_gemm_nt_tc3(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
+                                int M, int N, int K, const float* bias, int accumulate, float* split_ws, void* stream) {
+  BSED_REQUIRE(h && A && Bk && C && split_ws, "bsed_gemm_nt_tc3: null argument");
+  const long long n = (long long)N * ldb;
+  BSED_CHECK_CUDA(cudaMemcpyAsync(split_ws, Bk, sizeof(float) * n, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  BSED_TRY(split_hi_lo(split_ws, split_ws + n, n, as_stream(stream)));
+  return tc_gemm_nt(A, lda, split_ws, split_ws + n, ldb, C, ldc, M, N, K, bias, accumulate, h->num_sms, as_stream(stream));
 }
 
 // C[M][N] += sum_k A[k][M]^T Bm[k][N] on tcgen05 (kind::tf32): the weight-gradient kernel with one tap and rows = k
@@ -445,7 +471,7 @@ extern "C" int bsed_gemm_tn_tc(bsed_handle h, const float* A, int lda, const flo
 extern "C" int bsed_gemm_nt_tc(bsed_handle h, const float* A, int lda, const float* Bk, int ldb, float* C, int ldc,
                                int M, int N, int K, const float* bias, int accumulate, void* stream) {
   BSED_REQUIRE(h && A && Bk && C, "bsed_gemm_nt_tc: null argument");
-  return tc_gemm_nt(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, h->num_sms, as_stream(stream));
+  return tc_gemm_nt(A, lda, Bk, nullptr, ldb, C, ldc, M, N, K, bias, accumulate, h->num_sms, as_stream(stream));
 }
 
 // conv weight gradient: dw (Cout,Cin,3,3) += ...; unit-test entry (tensor_cores = 0 -> fp32 SIMT split-K)

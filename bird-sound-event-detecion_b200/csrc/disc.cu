@@ -319,7 +319,7 @@ extern "C" int bsed_disc_forward(bsed_handle h, const float* params, float* bn_b
     const bool tc = h->disc_precision == BSED_PRECISION_TF32;
     if (g.Np[l] == Cout) {
       if (tc)   // y = col * Wk^T on tcgen05 (Wk [Np][Kp] is the K-major B operand)
-        BSED_TRY(tc_gemm_nt(col, g.Kp[l], wsp<float>(ws, w.wk[l]), g.Kp[l], y, Cout, M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0,
+        BSED_TRY(tc_gemm_nt(col, g.Kp[l], wsp<float>(ws, w.wk[l]), nullptr, g.Kp[l], y, Cout, M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0,
                             h->num_sms, st));
       else
         BSED_TRY(gemm_nn(col, g.Kp[l], wsp<float>(ws, w.wt[l]), g.Np[l], y, Cout, (int)M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0, st));
@@ -445,7 +445,7 @@ extern "C" int bsed_disc_backward(bsed_handle h, const float* params, const floa
         for (int n0 = 0; n0 < g.Kp[l];) {
           const int rem = g.Kp[l] - n0;
           const int nw = rem >= 128 ? 128 : rem >= 64 ? 64 : rem >= 32 ? 32 : 16;
-          BSED_TRY(tc_gemm_nt(dy, ldy, wsp<float>(ws, w.wt[l]) + (size_t)n0 * g.Np[l], g.Np[l], col + n0, g.Kp[l], M, nw, g.Np[l],
+          BSED_TRY(tc_gemm_nt(dy, ldy, wsp<float>(ws, w.wt[l]) + (size_t)n0 * g.Np[l], nullptr, g.Np[l], col + n0, g.Kp[l], M, nw, g.Np[l],
                               nullptr, 0, h->num_sms, st));
           n0 += nw;
         }

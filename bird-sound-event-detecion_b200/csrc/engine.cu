@@ -105,7 +105,7 @@ struct bsed_crnn_plan {
   size_t off_G, off_dscratch[kMaxStacks], off_wgpart[kMaxStacks], off_bsums, off_bntab;
   size_t wgpart_bytes;
   size_t ws_bytes;
-  int precision;  // BSED_PRECISION_FP32 (SIMT fp32) or BSED_PRECISION_TF32 (tcgen05 kind::tf32)
+  int precision;  // BSED_PRECISION_FP32 (SIMT fp32), BSED_PRECISION_TF32 (tcgen05 kind::tf32), BSED_PRECISION_TF32X3
   // state of the last forward
   bool saved_valid;
   int n_groups, B;
@@ -328,7 +328,8 @@ void carve_workspace(bsed_crnn_plan* p) {
     o = align_up(o + bytes);
     return r;
   };
-  for (int s = 0; s < 2; ++s) p->off_packed[s] = takeb(sizeof(float) * p->pk.total);
+  // packed operands of each parameter set, followed by the low parts of the GEMM operands (3xTF32) at + pk.total
+  for (int s = 0; s < 2; ++s) p->off_packed[s] = takeb(sizeof(float) * 2 * p->pk.total);
   long long max_full = 0, max_pool = 0;
   for (int i = 0; i < p->n_blocks; ++i) {
     const LayerGeom& g = p->L[i];
@@ -409,39 +410,61 @@ struct PrepAdder {
 };
 
 // conv / BatchNorm / GLU operands of the trunk blocks and (fpn) of the shared stage, prepared once for both applications
-void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
+// `sp` collects the packed GEMM-operand ranges the 3xTF32 mode splits into (hi, lo) after the table has run
+void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packed, bool need_bwd, PrepTable* tb,
+                      SplitTable* sp) {
   const bsed_crnn_cfg& c = p->cfg;
   const ParamLayout& pl = p->pl;
   const PackedLayout& pk = p->pk;
-  const bool tc = p->precision == BSED_PRECISION_TF32;
+  const bool tc = p->precision != BSED_PRECISION_FP32;
   tb->n = 0;
   PrepAdder add{tb};
+  auto split = [&](long long off, long long n) {
+    sp->off[sp->n] = off;
+    sp->len[sp->n++] = n;
+  };
   for (int i = 0; i < c.n_cnn + (c.fpn ? 1 : 0); ++i) {
     const LayerGeom& g = p->L[i];
+    const long long wn = (long long)g.Cout * g.Cin * 9;
     if (i > 0) {
-      if (tc && conv_pair_ok(g))
+      if (tc && conv_pair_ok(g)) {
         add(PREP_CONV_PAIR, params + pl.conv_w[i], packed + pk.wpair[i], g.Cout, g.Cin, 0, 0, params + pl.conv_b[i], nullptr,
             nullptr, packed + pk.bpair[i]);
+        split(pk.wpair[i], 36LL * g.Cin * g.Cout);
+      }
       add(tc ? PREP_CONV_KMAJOR : PREP_CONV_PACK, params + pl.conv_w[i], packed + pk.wp[i], g.Cout, g.Cin);
-      if (need_bwd)
+      split(pk.wp[i], wn);
+      if (need_bwd) {
         add(tc ? PREP_CONV_KMAJOR_FLIP : PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
+        split(pk.wd[i], wn);
+      }
     }
     // d1 != 0: K-major folded matrix [c'][c] for the tensor-core GEMM (B operand [N][K])
+    const long long cp = (long long)g.Cout * glu_pack(g.Cout);
     add(PREP_GLU_FOLD, params + pl.glu_w[i], packed + pk.glu_wT[i], g.Cout, tc ? 1 : 0, glu_pack(g.Cout), 0,
         params + pl.bn_w[i], params + pl.bn_b[i], params + pl.glu_b[i], packed + pk.glu_bf[i]);
+    split(pk.glu_wT[i], cp * cp);
     if (tc) add(PREP_GATE_TAB, params + pl.bn_w[i], packed + pk.gate_tab[i], g.Cout, glu_pack(g.Cout), 0, 0, params + pl.bn_b[i]);
-    if (tc && need_bwd) add(PREP_TRANSPOSE_BD, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, glu_pack(g.Cout));
+    if (tc && need_bwd) {
+      add(PREP_TRANSPOSE_BD, params + pl.glu_w[i], packed + pk.glu_wgT[i], g.Cout, glu_pack(g.Cout));
+      split(pk.glu_wgT[i], cp * cp);
+    }
   }
 }
 
 // recurrent operands of GRU stack s (and, with s == 0 and fpn, the two merge convolutions)
-void build_prep_table_stack(const bsed_crnn_plan* p, int s, const float* params, float* packed, bool need_bwd, PrepTable* tb) {
+void build_prep_table_stack(const bsed_crnn_plan* p, int s, const float* params, float* packed, bool need_bwd, PrepTable* tb,
+                            SplitTable* sp) {
   const bsed_crnn_cfg& c = p->cfg;
   const ParamLayout& pl = p->pl;
   const PackedLayout& pk = p->pk;
-  const bool tc = p->precision == BSED_PRECISION_TF32;
+  const bool tc = p->precision != BSED_PRECISION_FP32;
   tb->n = 0;
   PrepAdder add{tb};
+  auto split = [&](long long off, long long n) {
+    sp->off[sp->n] = off;
+    sp->len[sp->n++] = n;
+  };
   for (int l = 0; l < c.rnn_layers; ++l) {
     int In = l == 0 ? 128 : 256;
     for (int d = 0; d < 2; ++d) {
@@ -454,11 +477,16 @@ void build_prep_table_stack(const bsed_crnn_plan* p, int s, const float* params,
       if (need_bwd) add(PREP_COPY, params + pl.whh[s][l][d], packed + pk.whh[s][l] + (long long)d * 384 * 128, 384 * 128);
       if (need_bwd || tc) add(PREP_COPY, params + pl.wih[s][l][d], packed + pk.wih_cat[s][l] + (long long)d * 384 * In, 384 * In);
     }
+    // tensor-core B operands: wih_cat (forward projection), wihT (its data gradient)
+    split(pk.wih_cat[s][l], 768LL * In);
+    split(pk.wihT[s][l], 768LL * In);
   }
   if (c.fpn && s == 0)
     for (int j = 0; j < 2; ++j) {
       add(PREP_COPY, params + pl.m_w[j], packed + pk.m_w[j], 256 * 512);
       add(PREP_TRANSPOSE, params + pl.m_w[j], packed + pk.m_wT[j], 256, 512, 256, 0);   // [256][512] -> [512][256]
+      split(pk.m_w[j], 256LL * 512);
+      split(pk.m_wT[j], 256LL * 512);
     }
 }
 
@@ -520,7 +548,7 @@ extern "C" int bsed_plan_create(bsed_handle h, const bsed_crnn_cfg* cfg, int max
   p->cfg = *cfg;
   p->max_clips = max_clips;
   p->saved_valid = false;
-  p->precision = BSED_PRECISION_TF32;
+  p->precision = BSED_PRECISION_TF32X3;
   int r = build_layouts(p);
   if (r != BSED_OK) {
     delete p;
@@ -574,7 +602,8 @@ extern "C" int bsed_plan_destroy(bsed_plan p) {
 
 extern "C" int bsed_plan_set_precision(bsed_plan p, int precision) {
   BSED_REQUIRE(p, "plan_set_precision: null plan");
-  BSED_REQUIRE(precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32, "plan_set_precision: mode %d", precision);
+  BSED_REQUIRE(precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32 || precision == BSED_PRECISION_TF32X3,
+               "plan_set_precision: mode %d", precision);
   p->precision = precision;
   p->saved_valid = false;
   return BSED_OK;
@@ -611,7 +640,10 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
   cudaStream_t st = as_stream(stream);
   const bsed_crnn_cfg& c = p->cfg;
   void* ws = workspace;
-  const bool tc = p->precision == BSED_PRECISION_TF32;
+  const bool tc = p->precision != BSED_PRECISION_FP32;
+  const bool x3 = p->precision == BSED_PRECISION_TF32X3;
+  const long long lo_off = p->pk.total;   // low parts of the packed GEMM operands (3xTF32)
+  auto LO = [&](const float* w) -> const float* { return x3 ? w + lo_off : nullptr; };
   const int sms = p->ctx->num_sms;
 
   // groups must tile [0, B)
@@ -673,13 +705,16 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
   // operand preparation
   for (int s = 0; s < p->n_psets; ++s) {
     PrepTable tb;
+    SplitTable sp;
+    sp.n = 0;
     float* packed = wsp<float>(ws, p->off_packed[s]);
-    build_prep_table(p, p->pset_params[s], packed, save, &tb);
+    build_prep_table(p, p->pset_params[s], packed, save, &tb, &sp);
     BSED_TRY(run_prep(tb, st));
     for (int k = 0; k < p->n_stacks; ++k) {
-      build_prep_table_stack(p, k, p->pset_params[s], packed, save, &tb);
+      build_prep_table_stack(p, k, p->pset_params[s], packed, save, &tb, &sp);
       BSED_TRY(run_prep(tb, st));
     }
+    if (x3) BSED_TRY(run_split(sp, packed, lo_off, st));
   }
 
   // GRU stacks: rnn on the trunk output, (fpn) rnn_2 / rnn_4 on the two coarser scales; each followed by dropout.
@@ -701,7 +736,8 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         float* xgr = xg + (size_t)runs[r].first * T * 768;
         if (tc) {
           for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
-            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In, In, xgr + n0, 768,
+            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In,
+                                LO(packed + p->pk.wih_cat[s][l] + (size_t)n0 * In), In, xgr + n0, 768,
                                 (long long)runs[r].count * T, 128, In, packed + p->pk.bih[s][l] + n0, 0, sms, ss));
         } else {
           BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[s][l], 768, xgr, 768, runs[r].count * T, 768, In,
@@ -768,11 +804,11 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
             }
           double* st_run = train ? stats + (size_t)i * kMaxGroups * 128 * 2 + (size_t)gbase * L.Cout * 2 : nullptr;
           if (conv_pair_ok(L))
-            BSED_TRY(tc_conv3x3_col(xr, packed + p->pk.wpair[i], yr, runs[r].count, L.T, L.F / 2, 32, 2 * L.Cout,
-                                    packed + p->pk.bpair[i], st_run, ng, gfirst_rel, sms, st, L.Cout));
+            BSED_TRY(tc_conv3x3_col(xr, packed + p->pk.wpair[i], LO(packed + p->pk.wpair[i]), yr, runs[r].count, L.T, L.F / 2, 32,
+                                    2 * L.Cout, packed + p->pk.bpair[i], st_run, ng, gfirst_rel, sms, st, L.Cout));
           else
-            BSED_TRY(tc_conv3x3_stats(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st_run, ng,
-                                      gfirst_rel, sms, st));
+            BSED_TRY(tc_conv3x3_stats(xr, packed + p->pk.wp[i], LO(packed + p->pk.wp[i]), yr, runs[r].count, L.T, L.F, L.Cin,
+                                      L.Cout, cb, 0, st_run, ng, gfirst_rel, sms, st));
         } else {
           BSED_TRY(conv3x3_nn(xr, packed + p->pk.wp[i], yr, runs[r].count, L.T, L.F, L.Cin, L.Cout, cb, 0, st));
         }
@@ -815,22 +851,22 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       BSED_REQUIRE(M < (1ll << 31), "crnn_forward: too many pixels");
       if (tc) {
         const int pack = glu_pack(L.Cout), CP = L.Cout * pack;   // L.rows is a multiple of 4 (F is even twice over)
-        if (glu_fused(L)) {
+        if (!x3 && glu_fused(L)) {
           // GEMM + gate + dropout + average pool in one kernel; lin is stored only when backward will need it
           BSED_TRY(tc_glu_gate_fwd(y + off, packed + p->pk.glu_wT[i], packed + p->pk.glu_bf[i], packed + p->pk.gate_tab[i],
                                    lin + off, pool + (size_t)runs[r].first * L.prows * L.Cout, runs[r].count, L.T, L.F,
                                    L.Cout, pack, L.pt, L.pf, p->bkeys[i], p->bthresh[i], p->binv[i], (uint32_t)off, save ? 1 : 0,
                                    sms, st));
         } else {
-          BSED_TRY(tc_gemm_nt(y + off, CP, packed + p->pk.glu_wT[i], CP, lin + off, CP, M / pack, CP, CP,
-                              packed + p->pk.glu_bf[i], 0, sms, st));
+          BSED_TRY(tc_gemm_nt(y + off, CP, packed + p->pk.glu_wT[i], LO(packed + p->pk.glu_wT[i]), CP, lin + off, CP, M / pack,
+                              CP, CP, packed + p->pk.glu_bf[i], 0, sms, st));
         }
       }
       else
         BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
                          packed + p->pk.glu_bf[i], 0, st));
     }
-    if (!(tc && glu_fused(L)))
+    if (!(tc && !x3 && glu_fused(L)))
       BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
                                  p->binv[i], st));
     for (int s = 0; s < p->n_stacks; ++s)
@@ -862,8 +898,8 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         const long long M = (long long)runs[r].count * Ta;
         if (tc) {
           for (int n0 = 0; n0 < 256; n0 += 128)   // B operand rows = output channels n0.., K-major as the reference stores them
-            BSED_TRY(tc_gemm_nt(A, 512, packed + p->pk.m_w[j] + (size_t)n0 * 512, 512, Y + n0, 256, M, 128, 512, bias + n0, 0,
-                                sms, st));
+            BSED_TRY(tc_gemm_nt(A, 512, packed + p->pk.m_w[j] + (size_t)n0 * 512, LO(packed + p->pk.m_w[j] + (size_t)n0 * 512), 512,
+                                Y + n0, 256, M, 128, 512, bias + n0, 0, sms, st));
         } else {
           BSED_TRY(gemm_nn(A, 512, packed + p->pk.m_wT[j], 256, Y, 256, (int)M, 256, 512, bias, 0, st));
         }
@@ -914,7 +950,10 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
   const float* packed = wsp<float>(ws, p->off_packed[p->gpset[ids[0]]]);
   const int sms = p->ctx->num_sms;
   const int target = sms * 4;
-  const bool tc = p->precision == BSED_PRECISION_TF32;
+  const bool tc = p->precision != BSED_PRECISION_FP32;
+  const bool x3 = p->precision == BSED_PRECISION_TF32X3;
+  const long long lo_off = p->pk.total;
+  auto LO = [&](const float* w) -> const float* { return x3 ? w + lo_off : nullptr; };
   float* wgpart = wsp<float>(ws, p->off_wgpart[0]);
   double* dscr = wsp<double>(ws, p->off_dscratch[0]);
 
@@ -953,8 +992,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       // dcat = dy * W   ([M][256] x [256][512])
       if (tc) {
         for (int n0 = 0; n0 < 512; n0 += 128)
-          BSED_TRY(tc_gemm_nt(dy, 256, packed + p->pk.m_wT[j] + (size_t)n0 * 256, 256, dcat + roa * 512 + n0, 512, M, 128, 256,
-                              nullptr, 0, sms, st));
+          BSED_TRY(tc_gemm_nt(dy, 256, packed + p->pk.m_wT[j] + (size_t)n0 * 256, LO(packed + p->pk.m_wT[j] + (size_t)n0 * 256), 256,
+                              dcat + roa * 512 + n0, 512, M, 128, 256, nullptr, 0, sms, st));
       } else {
         BSED_TRY(gemm_nn(dy, 256, packed + p->pk.m_w[j], 512, dcat + roa * 512, 512, (int)M, 512, 256, nullptr, 0, st));
       }
@@ -1015,8 +1054,9 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       const int acc = l == 0 ? accumulate_dx : 0;
       if (tc) {
         for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
-          BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l] + (size_t)n0 * 768, 768, dX + n0, In, BTn, 128,
-                              768, nullptr, acc, sms, ss));
+          BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l] + (size_t)n0 * 768,
+                              LO(packed + p->pk.wihT[s][l] + (size_t)n0 * 768), 768, dX + n0, In, BTn, 128, 768, nullptr, acc, sms,
+                              ss));
       } else {
         BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[s][l], In, dX, In, (int)BTn, In, 768, nullptr, acc, ss));
       }
@@ -1074,19 +1114,15 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       BSED_TRY(bn_bwd_prepare(bsums, G, n, L.Cout, gb, L.rows, bn, params + pl.glu_w[i], params + pl.bn_w[i],
                               params + pl.bn_b[i], pack, tab, grads + pl.bn_w[i], grads + pl.bn_b[i], grads + pl.glu_w[i],
                               grads + pl.glu_b[i], st));
-      BSED_TRY(tc_gemm_nt_bnbwd(lin + off, packed + p->pk.glu_wgT[i], dxn + off, xhat + off, M / pack, CP, CP, tab, n,
-                                L.rows / pack, gfirst_rel, sms, st));
+      BSED_TRY(tc_gemm_nt_bnbwd(lin + off, packed + p->pk.glu_wgT[i], LO(packed + p->pk.glu_wgT[i]), dxn + off, xhat + off,
+                                M / pack, CP, CP, tab, n, L.rows / pack, gfirst_rel, sms, st));
     } else {
     // gate / dropout / pool backward: lin -> d_lin (in place), dxn <- direct gate path
     BSED_TRY(glu_gate_pool_bwd(xhat, lin, dpool_cur, dxn, gb, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
                                p->binv[i], st));
     // dxn += d_lin * Wg        (Wg [c'][c] is already K-major for this product)
-    if (tc)
-      BSED_TRY(tc_gemm_nt(lin + off, L.Cout, packed + p->pk.glu_wgT[i], L.Cout, dxn + off, L.Cout, M, L.Cout, L.Cout,
-                          nullptr, 1, sms, st));
-    else
-      BSED_TRY(gemm_nn(lin + off, L.Cout, params + pl.glu_w[i], L.Cout, dxn + off, L.Cout, (int)M, L.Cout, L.Cout,
-                       nullptr, 1, st));
+    BSED_TRY(gemm_nn(lin + off, L.Cout, params + pl.glu_w[i], L.Cout, dxn + off, L.Cout, (int)M, L.Cout, L.Cout,
+                     nullptr, 1, st));
     // G = d_lin^T xhat ; dbg = colsum(d_lin)
     BSED_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.Cout * L.Cout, st));
     if (tc && L.Cout % 32 == 0 && L.F <= 64 && 64 % L.F == 0) {
@@ -1136,8 +1172,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       cur ^= 1;
       float* dnext = wsp<float>(ws, p->off_dpool[cur]);
       if (tc)
-        BSED_TRY(tc_conv3x3(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
-                            L.Cin, nullptr, 0, sms, st));
+        BSED_TRY(tc_conv3x3(dxn + off, packed + p->pk.wd[i], LO(packed + p->pk.wd[i]), dnext + (size_t)first * L.rows * L.Cin, nb,
+                            L.T, L.F, L.Cout, L.Cin, nullptr, 0, sms, st));
       else
         BSED_TRY(conv3x3_nn(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
                             L.Cin, nullptr, 0, st));

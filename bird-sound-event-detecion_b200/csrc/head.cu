@@ -7,6 +7,8 @@
 //   weak   = sum_t strong * sof / sum_t sof
 // The two linears are one GEMM producing logits [B][T][ldl] (cols 0..C-1 dense, C..2C-1
 // dense_softmax); this file holds everything after it.
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace bsed {
@@ -584,7 +586,10 @@ int opt_ema_step(float* params, const float* grads, float* m, float* v, float* e
 //      2 n (world - 1) / world parameter floats out over NVLink instead of the world * n of a one-shot all-reduce;
 //   3. depart: the last CTA to finish (device-scope counter) stores `epoch` into every peer's done[my_rank] and waits
 //      until all peers have done the same: all pushes have landed and nobody still reads this rank's gradients.
-// Spins give up after ~4 s and raise flags[33] instead of hanging the GPU.
+// A spin that waits longer than the timeout (BSED_DP_TIMEOUT_S, default 60 s) is FATAL: it raises the sticky error flag
+// flags[33], the rank applies nothing further and never signals depart (so its peers run into the same timeout instead of
+// reducing gradients this rank may be overwriting), and the host raises on its next health check
+// (utilities/shard.py: FusedDataParallel.check).
 // flag block (int32[64], zero-initialised by the host): arrive[0..15], done[16..31], counter [32], error [33].
 // ---------------------------------------------------------------------------------------------
 constexpr int kDpMaxWorld = 8;
@@ -616,12 +621,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// spin until flags[idx] >= epoch for idx in [base, base + world); false on timeout
-__device__ bool dp_wait(const int* flags, int base, int world, int epoch) {
+// spin until flags[idx] >= epoch for idx in [base, base + world); false on timeout or when the error flag is up
+__device__ bool dp_wait(const int* flags, int base, int world, int epoch, unsigned long long timeout_ns) {
   const unsigned long long t0 = global_ns();
   for (int r = 0; r < world; ++r) {
     while (ld_acquire_sys(flags + base + r) < epoch) {
-      if (global_ns() - t0 > 4000000000ull) return false;
+      if (global_ns() - t0 > timeout_ns || ld_acquire_sys(flags + 33) != 0) return false;
       __nanosleep(100);
     }
   }
@@ -630,16 +635,18 @@ __device__ bool dp_wait(const int* flags, int base, int world, int epoch) {
 
 __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank, int world, int epoch, float* __restrict__ p,
                                                          float* __restrict__ m, float* __restrict__ v,
-                                                         float* __restrict__ ema, long long lo, long long hi, OptScalars o) {
+                                                         float* __restrict__ ema, long long lo, long long hi, OptScalars o,
+                                                         unsigned long long timeout_ns) {
   int* my = peers.flags[rank];
   __shared__ int ok_s;
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
+    const bool healthy = ld_acquire_sys(my + 33) == 0;      // a rank that timed out once stays out
+    if (blockIdx.x == 0 && healthy) {
       __threadfence_system();
       for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + rank, epoch);       // arrive
     }
-    ok_s = dp_wait(my, 0, world, epoch) ? 1 : 0;
-    if (!ok_s) my[33] = 1;
+    ok_s = healthy && dp_wait(my, 0, world, epoch, timeout_ns) ? 1 : 0;
+    if (!ok_s) atomicExch(my + 33, 1);
   }
   __syncthreads();
   if (ok_s) {
@@ -669,8 +676,10 @@ __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank
     if (done == (int)gridDim.x - 1) {          // last CTA of this rank: every push is out, every peer read is complete
       my[32] = 0;
       __threadfence_system();
-      for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + 16 + rank, epoch);   // depart
-      if (!dp_wait(my, 16, world, epoch)) my[33] = 1;
+      if (ld_acquire_sys(my + 33) == 0) {      // no depart after a timeout anywhere on this rank
+        for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + 16 + rank, epoch);   // depart
+        if (!dp_wait(my, 16, world, epoch, timeout_ns)) atomicExch(my + 33, 1);
+      }
     }
   }
 }
@@ -700,7 +709,13 @@ int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* 
   int grid = num_sms * 2;
   const long long need = (hi - lo + 255) / 256;
   if (grid > need) grid = (int)(need > 0 ? need : 1);
-  dp_opt_ema_kernel<<<grid, 256, 0, st>>>(peers, rank, world, (int)epoch, peers.params[rank], m, v, peers.ema[rank], lo, hi, o);
+  static double timeout_s = -1.0;
+  if (timeout_s < 0) {
+    const char* e = getenv("BSED_DP_TIMEOUT_S");
+    timeout_s = e && atof(e) > 0 ? atof(e) : 60.0;
+  }
+  dp_opt_ema_kernel<<<grid, 256, 0, st>>>(peers, rank, world, (int)epoch, peers.params[rank], m, v, peers.ema[rank], lo, hi, o,
+                                          (unsigned long long)(timeout_s * 1e9));
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

@@ -96,6 +96,14 @@ struct PrepTable {
   PrepOp ops[kMaxPrepOps];
 };
 int run_prep(const PrepTable& table, cudaStream_t st);
+// 3xTF32 weight split of packed GEMM operands: ranges [off, off + n) of `packed` become their tf32 roundings, the
+// remainders go to packed + lo_offset
+constexpr int kMaxSplitRanges = 64;
+struct SplitTable {
+  int n;
+  long long off[kMaxSplitRanges], len[kMaxSplitRanges];
+};
+int run_split(const SplitTable& table, float* packed, long long lo_offset, cudaStream_t st);
 
 // ---- gru.cu
 // xg [B][T][768] input projections (both directions); whhT per group: [2][128][384]; bhh per group: [2][384]
@@ -135,25 +143,31 @@ int fpn_cat_upsample_fwd(const float* a, const float* b, float* cat, int B, int 
 int fpn_cat_upsample_bwd(const float* dcat, float* da, float* db, int B, int Ta, int Tb, cudaStream_t st);
 
 // ---- tc_gemm.cu (tcgen05 / TMA)
-int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-               int accumulate, int sms, cudaStream_t st);
+// Wk_lo / Bk_lo != nullptr select the error-compensated 3xTF32 products (fp32-grade): the hi array holds the tf32-rounded
+// weights, the lo array their fp32 remainders (split_hi_lo below); nullptr = plain kind::tf32.
+int tc_conv3x3(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+               const float* bias, int accumulate, int sms, cudaStream_t st);
 // stats != nullptr: also accumulates the per-channel sum / sum of squares of the output per group
 // (stats[(group * Cout + c) * 2 + {0,1}], group = last k with clip >= gfirst[k], clips relative to X)
-int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                     int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st);
+int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+                     const float* bias, int accumulate, double* stats, int stats_groups, const int* gfirst, int sms,
+                     cudaStream_t st);
 // column-tiled variant with shared-memory halo reuse (tc_conv.cu); no accumulate mode
 bool tc_conv_col_supported(int F, int Cin, int Cout);
 // stats_c: number of true channels the statistics fold onto (output column c counts for channel c % stats_c)
-int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st, int stats_c = 0);
-int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
-               const float* bias, int accumulate, int sms, cudaStream_t st);
+int tc_conv3x3_col(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+                   const float* bias, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st,
+                   int stats_c = 0);
+int tc_gemm_nt(const float* A, int lda, const float* Bk, const float* Bk_lo, int ldb, float* C, int ldc, long long M, int N,
+               int K, const float* bias, int accumulate, int sms, cudaStream_t st);
+// in place: w[i] <- tf32(w[i]) (round to nearest), lo[i] <- w[i] - tf32(w[i])
+int split_hi_lo(float* w, float* lo, long long n, cudaStream_t st);
 
 int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const float* tab, float* lin, float* pooled,
                     int B, int T, int F, int C, int pack, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
                     uint32_t drop_base, int store_lin, int sms, cudaStream_t st);
-int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xhat, long long M, int N, int K,
-                     const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st);
+int tc_gemm_nt_bnbwd(const float* A, const float* Bk, const float* Bk_lo, float* C, const float* xhat, long long M, int N,
+                     int K, const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st);
 size_t tc_wgrad_workspace_bytes(int sms);
 // [rows][ld] fp32 tensor, channels [c0, c0 + C) of every row take part
 struct TcOperand {

@@ -128,6 +128,39 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepT
   }
 }
 
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ SplitTable table, float* __restrict__ packed,
+                                                    long long lo_offset) {
+  float* w = packed + table.off[blockIdx.x];
+  const long long n = table.len[blockIdx.x];
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x) {
+    const float x = w[i], hi = tf32_rna(x);
+    w[i] = hi;
+    w[i + lo_offset] = tf32_rna(x - hi);   // 13 significant bits -> nearest tf32 (the tensor core would truncate)
+  }
+}
+
+int run_split(const SplitTable& table, float* packed, long long lo_offset, cudaStream_t st) {
+  if (table.n == 0) return BSED_OK;
+  dim3 grid(table.n, 8);
+  split_kernel<<<grid, 256, 0, st>>>(table, packed, lo_offset);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+int split_hi_lo(float* w, float* lo, long long n, cudaStream_t st) {
+  SplitTable tb;
+  tb.n = 1;
+  tb.off[0] = 0;
+  tb.len[0] = n;
+  return run_split(tb, w, lo - w, st);
+}
+
 int run_prep(const PrepTable& table, cudaStream_t st) {
   if (table.n == 0) return BSED_OK;
   dim3 grid(table.n, 8);

@@ -10,7 +10,8 @@ namespace bsed {
 namespace tc {
 
 constexpr int kBM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kThreadsX3 = 320;   // + warps 6-9: operand splitters of the 3xTF32 mode
 constexpr uint32_t kSpinLimit = 1u << 26;   // bounded mbarrier waits: trap instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------
@@ -93,6 +94,22 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" 
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// 3xTF32 operand split.  kind::tf32 reads the upper 19 bits of a 32-bit container (measured on B200: rewriting the tile
+// as its truncated high part changes nothing), so a raw fp32 tile acts as its own high part hi = a & 0xffffe000; the low
+// part is the exact fp32 difference a - hi (13 significant bits) rounded to NEAREST tf32, so that the tensor core's
+// truncation of it is exact and the remaining error (<= 2^-22 |a|) is unbiased:
+//   a * b ~= hi * b_hi + hi * b_lo + lo * b_hi.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_lo4(float4 v) {
+  return make_float4(tf32_rna(v.x - tf32_trunc(v.x)), tf32_rna(v.y - tf32_trunc(v.y)), tf32_rna(v.z - tf32_trunc(v.z)),
+                     tf32_rna(v.w - tf32_trunc(v.w)));
+}
+__device__ __forceinline__ void split_barrier() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -187,6 +204,8 @@ static inline EncodeTiledFn encode_fn() {
 }
 
 // rank-R fp32 map; dims/strides innermost first (strides in bytes for dims 1..R-1)
+// `store` (and the operand maps of the 3xTF32 mode) use the plain FLOAT32 element type: the bytes land in shared memory
+// untouched; the TFLOAT32 type of the 1xTF32 operand maps lets the copy engine prepare tf32 values.
 static inline int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                     const cuuint32_t* box, int row_bytes, bool store = false) {
   EncodeTiledFn fn = encode_fn();
@@ -210,6 +229,17 @@ static inline int make_map(CUtensorMap* m, const void* base, int rank, const cuu
 }
 
 }  // namespace tc
+
+// per-device one-time kernel attributes (one handle per device; cudaFuncSetAttribute is a per-device setting)
+constexpr int kMaxDevices = 64;
+static inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  const bool first = !done[dev];
+  done[dev] = true;
+  return first;
+}
 
 static inline int tc_debug() {   // BSED_TC_DEBUG: measurement experiments only
   static int v = -1;

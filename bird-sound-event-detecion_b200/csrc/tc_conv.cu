@@ -21,8 +21,11 @@ namespace tc {
 
 constexpr int kG = 2;               // frequency bins per CTA step
 constexpr int kHaloRows = 130;      // t0-1 .. t0+128
-constexpr int kACopy = 17 * 1024;   // one column copy: 130 rows x 128 B, padded to the 1024-byte swizzle repeat
+constexpr int kHaloPad = 136;       // rows of one column copy, padded to the 8-row swizzle repeat
 constexpr int kAStages = 2;
+// 3xTF32 (X3, see tc_gemm.cu): the input is walked in 16-channel chunks (64-byte rows, SWIZZLE_64B), so that the raw
+// column copies, their low parts (one set per stage, written by four splitter warps) and a ring of (hi, lo) weight tiles
+// fit the 227 KB of shared memory; every (tap, k-step) issues a*w_hi + a*w_lo + a_lo*w_hi.
 
 struct CArgs {
   int n_tiles, fgroups, tblocks;   // tile = (clip, f group, t block)
@@ -36,35 +39,46 @@ struct CArgs {
   int gfirst[kMaxGroups];
 };
 
-// K-major SWIZZLE_128B descriptor whose start may sit on any 128-byte row of the 1024-byte swizzle repeat
+// K-major swizzled descriptor (rows of ROWB = 128 / 64 bytes) whose start may sit on any row of the swizzle repeat
+template <int ROWB>
 __device__ __forceinline__ uint64_t kmajor_desc_rows(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t layout = ROWB == 128 ? 2 : 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
 }
 
-template <int N>
+template <int N, bool X3>
 struct CSmem {
-  static constexpr int KCH = 32;
-  static constexpr int A_STAGE = (kG + 2) * kACopy;
+  static constexpr int KCH = X3 ? 16 : 32;
+  static constexpr int ROWB = KCH * 4;
+  static constexpr int A_COPY = kHaloPad * ROWB;                      // one column copy (17 KB / 8.5 KB)
+  static constexpr int A_STAGE = (kG + 2) * A_COPY;
+  static constexpr int LO_BYTES = X3 ? kAStages * A_STAGE : 0;        // low parts, one set per stage
   static constexpr int B_TILE = N * KCH * 4;                          // one tap, one chunk
   static constexpr int B_STRIDE = (B_TILE + 1023) / 1024 * 1024;
+  static constexpr int NB = X3 ? 2 : 1;                               // weight tiles per (tap, chunk): hi [, lo]
+  static constexpr int B_SLOT = NB * B_STRIDE;
   static constexpr int HW = N < 64 ? N : 64;                          // columns staged per pass
   static constexpr int STG_BYTES = kBM * HW * 4;
   static constexpr int BAR_BYTES = 512;
 };
 
-template <int N>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int N, bool X3>
+__global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
 tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const __grid_constant__ CUtensorMap mapC, const float* __restrict__ bias, CArgs a) {
-  using S = CSmem<N>;
+                   const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+                   const float* __restrict__ bias, CArgs a) {
+  using S = CSmem<N, X3>;
   constexpr int KCH = S::KCH;
+  constexpr int ROWB = S::ROWB;
   constexpr uint32_t TMEM_COLS = (2 * kG * N <= 64) ? 64 : (2 * kG * N <= 128) ? 128 : (2 * kG * N <= 256) ? 256 : 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = 9 * a.cpt;
   const int nb = a.rb ? nk : a.bstages;                               // weight tiles held in shared memory
-  unsigned char* sB = smem + kAStages * S::A_STAGE;
-  unsigned char* stg = sB + nb * S::B_STRIDE;
+  unsigned char* alo = smem + kAStages * S::A_STAGE;                  // low parts of the column copies (X3)
+  unsigned char* sB = alo + S::LO_BYTES;
+  unsigned char* stg = sB + nb * S::B_SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + S::STG_BYTES);
   uint64_t* afull = bars;
   uint64_t* aempty = bars + kAStages;
@@ -73,7 +87,8 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint64_t* tfull = bempty + 16;
   uint64_t* tempty = tfull + 2;
   uint64_t* rbfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbfull + 1);
+  uint64_t* lofull = rbfull + 1;                  // [kAStages] low parts written (X3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lofull + kAStages);
   float* sbias = reinterpret_cast<float*>(stg + S::STG_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -84,6 +99,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 1);
+      mbar_init(&lofull[s], 1);
     }
     for (int s = 0; s < 16; ++s) {
       mbar_init(&bfull[s], 1);
@@ -110,8 +126,11 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       int sb = 0;
       uint32_t phb = 0;
       if (a.rb) {
-        mbar_expect_tx(rbfull, nk * S::B_TILE);
-        for (int i = 0; i < nk; ++i) tma_load_2d(&mapB, sB + i * S::B_STRIDE, rbfull, i * KCH, 0);
+        mbar_expect_tx(rbfull, S::NB * nk * S::B_TILE);
+        for (int i = 0; i < nk; ++i) {
+          tma_load_2d(&mapB, sB + i * S::B_SLOT, rbfull, i * KCH, 0);
+          if (X3) tma_load_2d(&mapBlo, sB + i * S::B_SLOT + S::B_STRIDE, rbfull, i * KCH, 0);
+        }
       }
       // flat sequence of (tile, chunk) steps; the activation columns of step i + 1 are requested BEFORE the nine weight
       // tiles of step i (which are paced by the MMAs through the weight ring), so they land while step i computes
@@ -128,7 +147,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           mbar_wait(&aempty[stage], ((step / kAStages) & 1) ^ 1);
           mbar_expect_tx(&afull[stage], (kG + 2) * kHaloRows * KCH * 4);
         }
-        tma_load_4d(&mapA, smem + stage * S::A_STAGE + j * kACopy, &afull[stage], ch * KCH, f0 - 1 + j, t0 - 1, b);
+        tma_load_4d(&mapA, smem + stage * S::A_STAGE + j * S::A_COPY, &afull[stage], ch * KCH, f0 - 1 + j, t0 - 1, b);
       };
       if (steps > 0)
         for (int j = 0; j < kG + 2; ++j) issue_a(0, j);
@@ -138,8 +157,9 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (step + 1 < steps && (tap & 1) == 0 && tap / 2 < kG + 2) issue_a(step + 1, tap / 2);
           if (!a.rb) {
             mbar_wait(&bempty[sb], phb ^ 1);
-            mbar_expect_tx(&bfull[sb], S::B_TILE);
-            tma_load_2d(&mapB, sB + sb * S::B_STRIDE, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
+            mbar_expect_tx(&bfull[sb], S::NB * S::B_TILE);
+            tma_load_2d(&mapB, sB + sb * S::B_SLOT, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
+            if (X3) tma_load_2d(&mapBlo, sB + sb * S::B_SLOT + S::B_STRIDE, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
             if (++sb == a.bstages) {
               sb = 0;
               phb ^= 1;
@@ -162,29 +182,35 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_after();
       for (int ch = 0; ch < a.cpt; ++ch) {
         mbar_wait(&afull[sa], pha);
+        if (X3) mbar_wait(&lofull[sa], pha);      // the splitters have written the low parts of this stage
         tc_fence_after();
         const uint32_t abase = smem_u32(smem + sa * S::A_STAGE);
+        const uint32_t lobase = smem_u32(alo + sa * S::A_STAGE);
         for (int tap = 0; tap < 9; ++tap) {
           const int dt = tap / 3 - 1, df = tap % 3 - 1;
           uint32_t bbase;
           if (a.rb) {
-            bbase = smem_u32(sB + (tap * a.cpt + ch) * S::B_STRIDE);
+            bbase = smem_u32(sB + (tap * a.cpt + ch) * S::B_SLOT);
           } else {
             mbar_wait(&bfull[sb], phb);
             tc_fence_after();
-            bbase = smem_u32(sB + sb * S::B_STRIDE);
+            bbase = smem_u32(sB + sb * S::B_SLOT);
           }
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
             for (int g = 0; g < kG; ++g) {
-              const uint32_t arow = abase + (g + df + 1) * kACopy + (dt + 1) * 128;
+              const uint32_t aoff = (g + df + 1) * S::A_COPY + (dt + 1) * ROWB;
               const uint32_t d_tmem = tmem_base + (ab * kG + g) * N;
 #pragma unroll
               for (int k = 0; k < KCH / 8; ++k) {
-                const uint64_t da = kmajor_desc_rows(arow + k * 32);
-                const uint64_t db = kmajor_desc<128>(bbase + k * 32);
+                const uint64_t da = kmajor_desc_rows<ROWB>(abase + aoff + k * 32);
+                const uint64_t db = kmajor_desc<ROWB>(bbase + k * 32);
                 umma_tf32(d_tmem, da, db, idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                if (X3) {
+                  umma_tf32(d_tmem, da, kmajor_desc<ROWB>(bbase + S::B_STRIDE + k * 32), idesc, 1u);
+                  umma_tf32(d_tmem, kmajor_desc_rows<ROWB>(lobase + aoff + k * 32), db, idesc, 1u);
+                }
               }
             }
             if (!a.rb) umma_commit(&bempty[sb]);
@@ -204,6 +230,25 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           pha ^= 1;
         }
       }
+    }
+  } else if (X3 && warp >= 6) {
+    // ===================== operand splitters (warps 6..9, 3xTF32) =====================
+    // lo[sa] is free whenever A[sa] is: a stage is refilled only after the MMAs that read both have completed
+    const int tid = threadIdx.x - 6 * 32;
+    const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int steps = my_tiles * a.cpt;
+    for (int step = 0; step < steps; ++step) {
+      const int sa = step % kAStages;
+      mbar_wait(&afull[sa], (step / kAStages) & 1);
+      const uint32_t src = smem_u32(smem + sa * S::A_STAGE), dst = smem_u32(alo + sa * S::A_STAGE);
+#pragma unroll 4
+      for (int i = tid; i < S::A_STAGE / 16; i += 128) {
+        const float4 v = lds128(src + i * 16);
+        sts128(dst + i * 16, tf32_lo4(v));
+      }
+      fence_proxy_async();
+      split_barrier();
+      if (tid == 0) mbar_arrive(&lofull[sa]);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -309,34 +354,32 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int N>
-static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const float* bias, CArgs& a,
-                      int sms, cudaStream_t st) {
-  using S = CSmem<N>;
+template <int N, bool X3>
+static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
+                      const float* bias, CArgs& a, int sms, cudaStream_t st) {
+  using S = CSmem<N, X3>;
   const int nk = 9 * a.cpt;
-  const long long fixed = (long long)kAStages * S::A_STAGE + S::STG_BYTES + S::BAR_BYTES + 512 + 1024;
+  const long long fixed = (long long)kAStages * S::A_STAGE + S::LO_BYTES + S::STG_BYTES + S::BAR_BYTES + 512 + 1024;
   const long long budget = 227 * 1024 - fixed;
-  if ((long long)nk * S::B_STRIDE <= budget && (long long)nk * S::B_STRIDE <= 24 * 1024) {
+  if ((long long)nk * S::B_SLOT <= budget && (long long)nk * S::B_SLOT <= 24 * 1024) {
     a.rb = 1;
     a.bstages = 0;
   } else {
     a.rb = 0;
-    long long bs = budget / S::B_STRIDE;
+    long long bs = budget / S::B_SLOT;
     a.bstages = (int)(bs > 9 ? 9 : bs);
     if (a.bstages < 2) {
       bsed_set_error("tc_conv_col: no room for the weight ring (N=%d)", N);
       return BSED_E_INVALID;
     }
   }
-  const size_t smem_bytes = (size_t)(fixed + (long long)(a.rb ? nk : a.bstages) * S::B_STRIDE);
-  auto kern = tc_conv_col_kernel<N>;
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    configured = smem_bytes;
-  }
+  const size_t smem_bytes = (size_t)(fixed + (long long)(a.rb ? nk : a.bstages) * S::B_SLOT);
+  auto kern = tc_conv_col_kernel<N, X3>;
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  kern<<<grid, kThreads, smem_bytes, st>>>(mA, mB, mC, bias, a);
+  kern<<<grid, X3 ? kThreadsX3 : kThreads, smem_bytes, st>>>(mA, mB, mBlo, mC, bias, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -349,19 +392,23 @@ bool tc_conv_col_supported(int F, int Cin, int Cout) {
 }
 
 // Y[B][T][F][Cout] = conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin] (k = tap*Cin + ci)
-int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                   double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st, int stats_c) {
+// Wk_lo != nullptr selects 3xTF32 (Wk = tf32-rounded weights, Wk_lo = their fp32 remainders, same layout)
+int tc_conv3x3_col(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+                   const float* bias, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st, int stats_c) {
   BSED_REQUIRE(tc_conv_col_supported(F, Cin, Cout), "tc_conv3x3_col: F=%d Cin=%d Cout=%d", F, Cin, Cout);
   const int CW = Cout >= 32 ? 32 : 16;
-  CUtensorMap mA, mB, mC;
+  const bool x3 = Wk_lo != nullptr;
+  const int KCH = x3 ? 16 : 32;
+  CUtensorMap mA, mB, mBlo, mC;
   cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t sA[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
-  cuuint32_t bA[4] = {32, 1, (cuuint32_t)tc::kHaloRows, 1};
-  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, 128));
+  cuuint32_t bA[4] = {(cuuint32_t)KCH, 1, (cuuint32_t)tc::kHaloRows, 1};
+  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, KCH * 4, x3));
   cuuint64_t dB[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
   cuuint64_t sB[1] = {(cuuint64_t)9 * Cin * 4};
-  cuuint32_t bB[2] = {32, (cuuint32_t)Cout};
-  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, 128));
+  cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)Cout};
+  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, KCH * 4, x3));
+  BSED_TRY(tc::make_map(&mBlo, x3 ? Wk_lo : Wk, 2, dB, sB, bB, KCH * 4, x3));
   cuuint64_t dC[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t sC[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
   cuuint32_t bC[4] = {(cuuint32_t)CW, 1, 128, 1};
@@ -372,19 +419,30 @@ int tc_conv3x3_col(const float* X, const float* Wk, float* Y, int B, int T, int 
   a.n_tiles = B * a.fgroups * a.tblocks;
   a.T = T;
   a.F = F;
-  a.cpt = Cin / 32;
+  a.cpt = Cin / KCH;
   a.debug = tc_debug();
   a.stats = stats;
   a.stats_groups = stats ? stats_groups : 0;
   a.stats_c = stats_c > 0 ? stats_c : Cout;
   for (int k = 0; k < kMaxGroups; ++k) a.gfirst[k] = stats && k < stats_groups ? gfirst[k] : 0;
-  ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
-                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
+  // algorithmic flops: in the pixel-pair view (stats_c = true channel count < Cout) half of the packed weight matrix
+  // is structural zeros -- the convolution it stands for has Cin / 2 input channels
+  const double algo = stats_c > 0 && stats_c < Cout ? 0.5 : 1.0;
+  ProfScope prof(PROF_CONV, algo * 2.0 * B * T * F * Cout * 9.0 * Cin,
+                 4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + algo * 9.0 * Cin * Cout), st);
+  if (x3) {
+    switch (Cout) {
+      case 16: return tc::launch_col<16, true>(mA, mB, mBlo, mC, bias, a, sms, st);
+      case 32: return tc::launch_col<32, true>(mA, mB, mBlo, mC, bias, a, sms, st);
+      case 64: return tc::launch_col<64, true>(mA, mB, mBlo, mC, bias, a, sms, st);
+      default: return tc::launch_col<128, true>(mA, mB, mBlo, mC, bias, a, sms, st);
+    }
+  }
   switch (Cout) {
-    case 16: return tc::launch_col<16>(mA, mB, mC, bias, a, sms, st);
-    case 32: return tc::launch_col<32>(mA, mB, mC, bias, a, sms, st);
-    case 64: return tc::launch_col<64>(mA, mB, mC, bias, a, sms, st);
-    default: return tc::launch_col<128>(mA, mB, mC, bias, a, sms, st);
+    case 16: return tc::launch_col<16, false>(mA, mB, mBlo, mC, bias, a, sms, st);
+    case 32: return tc::launch_col<32, false>(mA, mB, mBlo, mC, bias, a, sms, st);
+    case 64: return tc::launch_col<64, false>(mA, mB, mBlo, mC, bias, a, sms, st);
+    default: return tc::launch_col<128, false>(mA, mB, mBlo, mC, bias, a, sms, st);
   }
 }
 

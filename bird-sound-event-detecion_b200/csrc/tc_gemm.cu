@@ -27,6 +27,8 @@ struct KArgs {
   int ldc;
   int accumulate;
   int debug;           // BSED_TC_DEBUG (measurement experiments only): 1 = skip the epilogue's global stores
+  int stages;          // depth of the TMA ring (host: as many as fit the shared memory)
+  int rb_bytes;        // bytes reserved for the resident weights (RB)
   // epi == 1: BatchNorm-backward epilogue (plain mode): C holds the direct gate path dxd on entry and
   //   dY = k * (dxd + acc - m1 - xhat * m2) on exit; (k, m1, m2) per group and column from `tab` [groups][3][N]
   int epi;
@@ -52,33 +54,43 @@ struct KArgs {
 // for the GLU linears and blocks 1-2 is 20-50 % of the L2 -> SM traffic these kernels are bound by.
 constexpr int kRbBytes = 72 * 1024;
 
-template <int N, int KCH, int STAGES, bool RB>
+constexpr int kMaxStages = 24;
+constexpr int kLoBufs = 2;   // 3xTF32: low-part tiles in flight between the splitters and the MMA issuer
+
+// X3 ("3xTF32"): error-compensated fp32-grade products on the tf32 tensor cores.  The activation tile arrives raw; four
+// extra warps write its low part a - tf32(a) into a second tile; the weights come pre-split (hi, lo) from the prep pass;
+// every k-step issues three MMAs: a*b_hi + a*b_lo + a_lo*b_hi.
+template <int N, int KCH, bool RB, bool X3>
 struct KSmem {
   static constexpr int A_BYTES = kBM * KCH * 4;
   static constexpr int B_BYTES = N * KCH * 4;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE = A_BYTES + (RB ? 0 : B_STRIDE);
-  static constexpr int RB_BYTES = RB ? kRbBytes : 0;
+  static constexpr int NB = X3 ? 2 : 1;                                  // weight tiles per k-chunk (hi [, lo])
+  static constexpr int STAGE = A_BYTES + (RB ? 0 : NB * B_STRIDE);
+  static constexpr int LO_BYTES = X3 ? kLoBufs * A_BYTES : 0;
   static constexpr int STG_BYTES = kBM * N * 4;   // output tile staged for the TMA store
-  static constexpr int STG2_BYTES = N <= 64 ? kBM * N * 4 : 0;   // gated tile of the fused GLU epilogue (epi == 2)
-  static constexpr int BAR_BYTES = 512;   // 2 * STAGES + 5 mbarriers + the TMEM slot
+  static constexpr int STG2_BYTES = (!X3 && N <= 64) ? kBM * N * 4 : 0;   // gated tile of the fused GLU epilogue (epi == 2)
+  static constexpr int BAR_BYTES = 512;   // 2 * stages + 9 mbarriers + the TMEM slot
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
-  static constexpr int TOTAL =
-      STAGES * STAGE + RB_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
-  static_assert((2 * STAGES + 6) * 8 <= BAR_BYTES, "barrier region too small");
+  static constexpr int FIXED = LO_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
+  static_assert((2 * kMaxStages + 10) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
-template <int N, int KCH, int STAGES, bool RB>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int N, int KCH, bool RB, bool X3>
+__global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
 tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapC, float* __restrict__ Y, const float* __restrict__ bias, KArgs a) {
-  using S = KSmem<N, KCH, STAGES, RB>;
+                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC, float* __restrict__ Y,
+                 const float* __restrict__ bias, KArgs a) {
+  using S = KSmem<N, KCH, RB, X3>;
   constexpr int ROWB = KCH * 4;
+  constexpr int NT = X3 ? kThreadsX3 : kThreads;
   constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* rb = smem + STAGES * S::STAGE;   // resident weights (RB)
-  unsigned char* stg = rb + S::RB_BYTES;          // output staging (1024-byte aligned: STAGE and kRbBytes are)
+  const int STAGES = a.stages;
+  unsigned char* rb = smem + STAGES * S::STAGE;   // resident weights (RB): hi tiles, then (X3) lo tiles
+  unsigned char* lo = rb + a.rb_bytes;            // low-part activation tiles (X3)
+  unsigned char* stg = lo + S::LO_BYTES;          // output staging (1024-byte aligned: every region above is)
   unsigned char* stg2 = stg + S::STG_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg2 + S::STG2_BYTES);
   uint64_t* full = bars;
@@ -86,7 +98,9 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* rbfull = bars + 2 * STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  uint64_t* lofull = bars + 2 * STAGES + 5;
+  uint64_t* loempty = bars + 2 * STAGES + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 9);
   float* sbias = reinterpret_cast<float*>(stg2 + S::STG2_BYTES + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -101,6 +115,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+      mbar_init(&lofull[i], 1);
+      mbar_init(&loempty[i], 1);
     }
     mbar_init(rbfull, 1);
     fence_barrier_init();
@@ -108,9 +124,9 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
   float* stab = sbias + 128;
   if (a.epi == 1)
-    for (int i = threadIdx.x; i < a.tab_groups * 3 * N; i += kThreads) stab[i] = a.tab[i];
+    for (int i = threadIdx.x; i < a.tab_groups * 3 * N; i += NT) stab[i] = a.tab[i];
   if (a.epi == 2)
-    for (int i = threadIdx.x; i < 2 * N; i += kThreads) stab[i] = a.tab[i];
+    for (int i = threadIdx.x; i < 2 * N; i += NT) stab[i] = a.tab[i];
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -124,8 +140,10 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       if (RB) {
-        mbar_expect_tx(rbfull, nk * S::B_BYTES);
+        mbar_expect_tx(rbfull, S::NB * nk * S::B_BYTES);
         for (int i = 0; i < nk; ++i) tma_load_2d(&mapB, rb + i * S::B_STRIDE, rbfull, i * KCH, 0);
+        if (X3)
+          for (int i = 0; i < nk; ++i) tma_load_2d(&mapBlo, rb + (nk + i) * S::B_STRIDE, rbfull, i * KCH, 0);
       }
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         int b = 0, t0 = 0;
@@ -139,10 +157,11 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_wait(&empty[s], ph ^ 1);
             unsigned char* sa = smem + s * S::STAGE;
             unsigned char* sb = sa + S::A_BYTES;
-            mbar_expect_tx(&full[s], S::A_BYTES + (RB ? 0 : S::B_BYTES));
+            mbar_expect_tx(&full[s], S::A_BYTES + (RB ? 0 : S::NB * S::B_BYTES));
             if (a.plain) tma_load_2d(&mapA, sa, &full[s], ch * KCH, tile * kBM);
             else tma_load_4d(&mapA, sa, &full[s], ch * KCH, df, t0 + dt, b);
             if (!RB) tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, 0);
+            if (!RB && X3) tma_load_2d(&mapBlo, sb + S::B_STRIDE, &full[s], (tap * a.cpt + ch) * KCH, 0);
             if (++s == STAGES) {
               s = 0;
               ph ^= 1;
@@ -154,8 +173,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
-    int s = 0;
-    uint32_t ph = 0;
+    int s = 0, lj = 0;
+    uint32_t ph = 0, lph = 0;
     int it = 0;
     if (RB) mbar_wait(rbfull, 0);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -166,24 +185,64 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const uint32_t d_tmem = tmem_base + acc * N;
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(&full[s], ph);
+        if (X3) mbar_wait(&lofull[lj], lph);   // the splitters have written the low part of this stage
         tc_fence_after();
         __syncwarp();
         if (lane == 0) {   // one fixed lane issues the MMAs and their commits (commit tracks the issuing thread)
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
           const uint32_t sb = RB ? smem_u32(rb + kc * S::B_STRIDE) : sa + S::A_BYTES;
+          const uint32_t sblo = RB ? smem_u32(rb + (nk + kc) * S::B_STRIDE) : sb + S::B_STRIDE;
+          const uint32_t salo = smem_u32(lo + lj * S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < KCH / 8; ++k) {
             uint64_t da = kmajor_desc<ROWB>(sa + k * 32);
             uint64_t db = kmajor_desc<ROWB>(sb + k * 32);
             umma_tf32(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+            if (X3) {
+              umma_tf32(d_tmem, da, kmajor_desc<ROWB>(sblo + k * 32), idesc, 1u);
+              umma_tf32(d_tmem, kmajor_desc<ROWB>(salo + k * 32), db, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);                      // frees the stage once these MMAs have read it
+          if (X3) umma_commit(&loempty[lj]);
           if (kc == nk - 1) umma_commit(&tfull[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
+        }
+        if (X3 && ++lj == kLoBufs) {
+          lj = 0;
+          lph ^= 1;
+        }
+      }
+    }
+  } else if (X3 && warp >= 6) {
+    // ===================== operand splitters (warps 6..9, 3xTF32) =====================
+    const int tid = threadIdx.x - 6 * 32;
+    int s = 0, lj = 0;
+    uint32_t ph = 0, lph = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&full[s], ph);
+        mbar_wait(&loempty[lj], lph ^ 1);
+        const uint32_t src = smem_u32(smem + s * S::STAGE), dst = smem_u32(lo + lj * S::A_BYTES);
+#pragma unroll 4
+        for (int i = tid; i < S::A_BYTES / 16; i += 128) {
+          const float4 v = lds128(src + i * 16);
+          sts128(dst + i * 16, tf32_lo4(v));
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        split_barrier();
+        if (tid == 0) mbar_arrive(&lofull[lj]);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+        if (++lj == kLoBufs) {
+          lj = 0;
+          lph ^= 1;
         }
       }
     }
@@ -384,49 +443,72 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------
-template <int N, int KCH, bool RB>
-static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
-                     const KArgs& a, int sms, cudaStream_t st) {
-  // as many stages as fit ~200 KB (max 24): the small-tile GEMMs (GLU, block 1) are streaming kernels that need
-  // tens of KB of loads in flight per SM to cover the HBM latency
-  constexpr int STAGE_BYTES = KSmem<N, KCH, 1, RB>::STAGE;
-  constexpr int BUDGET = 200 * 1024 - (RB ? kRbBytes : 0) - kBM * N * 4 - (N <= 64 ? kBM * N * 4 : 0);
-  constexpr int STAGES = (BUDGET / STAGE_BYTES) > 24 ? 24 : (BUDGET / STAGE_BYTES);
-  using S = KSmem<N, KCH, STAGES, RB>;
-  static_assert(S::TOTAL <= 227 * 1024, "stage ring exceeds shared memory");
-  auto kern = tc_kmajor_kernel<N, KCH, STAGES, RB>;
-  static bool configured = false;
-  if (!configured) {
-    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
+constexpr int kSmemMax = 227 * 1024;
+
+template <int N, int KCH, bool RB, bool X3>
+static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC, float* Y,
+                     const float* bias, KArgs& a, int sms, cudaStream_t st) {
+  // as many stages as fit the shared memory (max 24): the small-tile GEMMs (GLU, block 1) are streaming kernels that
+  // need tens of KB of loads in flight per SM to cover the HBM latency
+  using S = KSmem<N, KCH, RB, X3>;
+  a.rb_bytes = RB ? S::NB * a.ntaps * a.cpt * S::B_STRIDE : 0;
+  int stages = (kSmemMax - S::FIXED - a.rb_bytes) / S::STAGE;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    bsed_set_error("tc gemm: no room for a 2-stage ring (N=%d KCH=%d rb=%d x3=%d)", N, KCH, a.rb_bytes, (int)X3);
+    return BSED_E_INVALID;
   }
+  a.stages = stages;
+  const int total = stages * S::STAGE + a.rb_bytes + S::FIXED;
+  auto kern = tc_kmajor_kernel<N, KCH, RB, X3>;
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
+    BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, mC, Y, bias, a);
+  kern<<<grid, X3 ? kThreadsX3 : kThreads, total, st>>>(mA, mB, mBlo, mC, Y, bias, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
 
-template <int N, int KCH>
-static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
-                    const KArgs& a, int sms, cudaStream_t st) {
-  const bool rb = (long long)a.ntaps * a.cpt * KSmem<N, KCH, 1, true>::B_STRIDE <= kRbBytes;
-  if (rb) return launch_k2<N, KCH, true>(mA, mB, mC, Y, bias, a, sms, st);
-  return launch_k2<N, KCH, false>(mA, mB, mC, Y, bias, a, sms, st);
+template <int N, int KCH, bool X3>
+static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC, float* Y,
+                    const float* bias, KArgs& a, int sms, cudaStream_t st) {
+  const bool rb = (long long)(X3 ? 2 : 1) * a.ntaps * a.cpt * KSmem<N, KCH, true, X3>::B_STRIDE <= kRbBytes;
+  if (rb) return launch_k2<N, KCH, true, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
+  return launch_k2<N, KCH, false, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
 }
 
-template <int KCH>
-static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, float* Y, const float* bias,
-                      const KArgs& a, int sms, cudaStream_t st) {
+template <int KCH, bool X3>
+static int dispatch_n(int N, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
+                      float* Y, const float* bias, KArgs& a, int sms, cudaStream_t st) {
   switch (N) {
-    case 16: return launch_k<16, KCH>(mA, mB, mC, Y, bias, a, sms, st);
-    case 32: return launch_k<32, KCH>(mA, mB, mC, Y, bias, a, sms, st);
-    case 64: return launch_k<64, KCH>(mA, mB, mC, Y, bias, a, sms, st);
-    case 128: return launch_k<128, KCH>(mA, mB, mC, Y, bias, a, sms, st);
+    case 16: return launch_k<16, KCH, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
+    case 32: return launch_k<32, KCH, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
+    case 64: return launch_k<64, KCH, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
+    case 128: return launch_k<128, KCH, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
   }
   bsed_set_error("tc gemm: N=%d unsupported (16/32/64/128)", N);
   return BSED_E_INVALID;
 }
 
+static int dispatch_k(int KCH, bool x3, int N, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo,
+                      const CUtensorMap& mC, float* Y, const float* bias, KArgs& a, int sms, cudaStream_t st) {
+  if (x3) {
+    if (KCH == 32) return dispatch_n<32, true>(N, mA, mB, mBlo, mC, Y, bias, a, sms, st);
+    return dispatch_n<16, true>(N, mA, mB, mBlo, mC, Y, bias, a, sms, st);
+  }
+  if (KCH == 32) return dispatch_n<32, false>(N, mA, mB, mBlo, mC, Y, bias, a, sms, st);
+  return dispatch_n<16, false>(N, mA, mB, mBlo, mC, Y, bias, a, sms, st);
+}
+
+// k-chunk width.  3xTF32 doubles the weight tiles and adds the low-part activation tiles: where the weights cannot
+// stay resident, 16-wide chunks (64-byte rows) keep a >= 4-stage ring inside the 227 KB of shared memory.
+static inline int pick_kch(int K, int N, int ntaps, bool x3) {
+  if (K % 32 != 0) return 16;
+  if (!x3) return 32;
+  const long long rb32 = 2LL * ntaps * (K / 32) * ((N * 32 * 4 + 1023) / 1024 * 1024);
+  return (rb32 <= kRbBytes || N <= 32) ? 32 : 16;
+}
 
 // ---------------------------------------------------------------------------------------------
 // MN-major kernel: reductions over rows ("weight gradients").
@@ -887,11 +969,9 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
   using S = WSmem<N, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "wgrad stage ring exceeds shared memory");
   auto kern = tc_wgrad_kernel<N, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
   kern<<<grid, kThreads, S::TOTAL, st>>>(mA, mB, part, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
@@ -901,24 +981,28 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
 
 // Y[B][T][F][Cout] (+)= conv3x3(X[B][T][F][Cin], Wk) + bias ; Wk = K-major packed weights [Cout][9*Cin]
 // (k = tap*Cin + ci).  Requires F in {2..128} dividing 128.
-int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-                     int accumulate, double* stats, int stats_groups, const int* gfirst, int sms, cudaStream_t st) {
+// Wk_lo != nullptr selects 3xTF32: Wk holds the tf32-rounded weights, Wk_lo their fp32 remainders (same layout).
+int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+                     const float* bias, int accumulate, double* stats, int stats_groups, const int* gfirst, int sms,
+                     cudaStream_t st) {
   if (!accumulate && tc_conv_col_supported(F, Cin, Cout))
-    return tc_conv3x3_col(X, Wk, Y, B, T, F, Cin, Cout, bias, stats, stats_groups, gfirst, sms, st);
+    return tc_conv3x3_col(X, Wk, Wk_lo, Y, B, T, F, Cin, Cout, bias, stats, stats_groups, gfirst, sms, st);
   BSED_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128, "tc_conv3x3: Cin=%d Cout=%d", Cin, Cout);
   BSED_REQUIRE(F >= 1 && F <= 128 && 128 % F == 0, "tc_conv3x3: F=%d must divide 128", F);
-  const int KCH = Cin % 32 == 0 ? 32 : 16;
+  const bool x3 = Wk_lo != nullptr;
+  const int KCH = tc::pick_kch(Cin, Cout, 9, x3);
   const int th = 128 / F;
   const int CW = Cout >= 32 ? 32 : 16;
-  CUtensorMap mA, mB, mC;
+  CUtensorMap mA, mB, mBlo, mC;
   cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t sA[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)F * Cin * 4, (cuuint64_t)T * F * Cin * 4};
   cuuint32_t bA[4] = {(cuuint32_t)KCH, (cuuint32_t)F, (cuuint32_t)th, 1};
-  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, KCH * 4));
+  BSED_TRY(tc::make_map(&mA, X, 4, dA, sA, bA, KCH * 4, x3));
   cuuint64_t dB[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
   cuuint64_t sB[1] = {(cuuint64_t)9 * Cin * 4};
   cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)Cout};
-  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, KCH * 4));
+  BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, KCH * 4, x3));
+  BSED_TRY(tc::make_map(&mBlo, x3 ? Wk_lo : Wk, 2, dB, sB, bB, KCH * 4, x3));
   cuuint64_t dC[4] = {(cuuint64_t)Cout, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t sC[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)F * Cout * 4, (cuuint64_t)T * F * Cout * 4};
   cuuint32_t bC[4] = {(cuuint32_t)CW, (cuuint32_t)F, (cuuint32_t)th, 1};
@@ -952,13 +1036,12 @@ int tc_conv3x3_stats(const float* X, const float* Wk, float* Y, int B, int T, in
   a.inv_keep = 1.f;
   ProfScope prof(PROF_CONV, 2.0 * B * T * F * Cout * 9.0 * Cin,
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + 9.0 * Cin * Cout), st);
-  if (KCH == 32) return tc::dispatch_n<32>(Cout, mA, mB, mC, Y, bias, a, sms, st);
-  return tc::dispatch_n<16>(Cout, mA, mB, mC, Y, bias, a, sms, st);
+  return tc::dispatch_k(KCH, x3, Cout, mA, mB, mBlo, mC, Y, bias, a, sms, st);
 }
 
-int tc_conv3x3(const float* X, const float* Wk, float* Y, int B, int T, int F, int Cin, int Cout, const float* bias,
-               int accumulate, int sms, cudaStream_t st) {
-  return tc_conv3x3_stats(X, Wk, Y, B, T, F, Cin, Cout, bias, accumulate, nullptr, 0, nullptr, sms, st);
+int tc_conv3x3(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
+               const float* bias, int accumulate, int sms, cudaStream_t st) {
+  return tc_conv3x3_stats(X, Wk, Wk_lo, Y, B, T, F, Cin, Cout, bias, accumulate, nullptr, 0, nullptr, sms, st);
 }
 
 // C[M][N] (+)= A[M][K] * Bk^T + bias ; Bk = [N][K] K-major.  bnb != nullptr selects the BatchNorm-backward epilogue.
@@ -969,20 +1052,22 @@ struct BnBwdEpi {
   long long rows_per_clip;
   int gfirst[kMaxGroups];
 };
-static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
-                           const float* bias, int accumulate, const BnBwdEpi* bnb, int sms, cudaStream_t st) {
+static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float* Bk_lo, int ldb, float* C, int ldc, long long M,
+                           int N, int K, const float* bias, int accumulate, const BnBwdEpi* bnb, int sms, cudaStream_t st) {
   BSED_REQUIRE(K % 16 == 0 && N % 16 == 0 && N <= 128 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
                "tc_gemm_nt: M=%lld N=%d K=%d", M, N, K);
-  const int KCH = K % 32 == 0 ? 32 : 16;
-  CUtensorMap mA, mB;
+  const bool x3 = Bk_lo != nullptr;
+  const int KCH = tc::pick_kch(K, N, 1, x3);
+  CUtensorMap mA, mB, mBlo;
   cuuint64_t dA[2] = {(cuuint64_t)K, (cuuint64_t)M};
   cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
   cuuint32_t bA[2] = {(cuuint32_t)KCH, 128};
-  BSED_TRY(tc::make_map(&mA, A, 2, dA, sA, bA, KCH * 4));
+  BSED_TRY(tc::make_map(&mA, A, 2, dA, sA, bA, KCH * 4, x3));
   cuuint64_t dB[2] = {(cuuint64_t)K, (cuuint64_t)N};
   cuuint64_t sB[1] = {(cuuint64_t)ldb * 4};
   cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)N};
-  BSED_TRY(tc::make_map(&mB, Bk, 2, dB, sB, bB, KCH * 4));
+  BSED_TRY(tc::make_map(&mB, Bk, 2, dB, sB, bB, KCH * 4, x3));
+  BSED_TRY(tc::make_map(&mBlo, x3 ? Bk_lo : Bk, 2, dB, sB, bB, KCH * 4, x3));
   const int CW = N >= 32 ? 32 : 16;
   CUtensorMap mC;
   cuuint64_t dC[2] = {(cuuint64_t)N, (cuuint64_t)M};
@@ -1017,13 +1102,12 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, int ldb, fl
   a.drop_key = a.drop_thresh = a.drop_base = 0;
   a.inv_keep = 1.f;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
-  if (KCH == 32) return tc::dispatch_n<32>(N, mA, mB, mC, C, bias, a, sms, st);
-  return tc::dispatch_n<16>(N, mA, mB, mC, C, bias, a, sms, st);
+  return tc::dispatch_k(KCH, x3, N, mA, mB, mBlo, mC, C, bias, a, sms, st);
 }
 
-int tc_gemm_nt(const float* A, int lda, const float* Bk, int ldb, float* C, int ldc, long long M, int N, int K,
-               const float* bias, int accumulate, int sms, cudaStream_t st) {
-  return tc_gemm_nt_impl(A, lda, Bk, ldb, C, ldc, M, N, K, bias, accumulate, nullptr, sms, st);
+int tc_gemm_nt(const float* A, int lda, const float* Bk, const float* Bk_lo, int ldb, float* C, int ldc, long long M, int N,
+               int K, const float* bias, int accumulate, int sms, cudaStream_t st) {
+  return tc_gemm_nt_impl(A, lda, Bk, Bk_lo, ldb, C, ldc, M, N, K, bias, accumulate, nullptr, sms, st);
 }
 
 // GLU forward of one block with gate, dropout and average pool fused (KArgs::epi == 2).  xhat / lin are the
@@ -1081,19 +1165,19 @@ int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const
   a.inv_keep = inv_keep;
   const double M = (double)B * T * Fp;
   ProfScope prof(PROF_GEMM, 2.0 * M * CP * CP, 4.0 * (2.0 * M * CP + (double)CP * CP), st);
-  return tc::dispatch_n<32>(CP, mA, mB, mC, lin, bias, a, sms, st);
+  return tc::dispatch_k(32, false, CP, mA, mB, mB, mC, lin, bias, a, sms, st);
 }
 
 // dY = k * (dxd + A * Bk^T - m1 - xhat * m2), in place on C (= dxd on entry); see KArgs::epi
-int tc_gemm_nt_bnbwd(const float* A, const float* Bk, float* C, const float* xhat, long long M, int N, int K,
-                     const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st) {
+int tc_gemm_nt_bnbwd(const float* A, const float* Bk, const float* Bk_lo, float* C, const float* xhat, long long M, int N,
+                     int K, const float* tab, int groups, long long rows_per_clip, const int* gfirst, int sms, cudaStream_t st) {
   BnBwdEpi e;
   e.xhat = xhat;
   e.tab = tab;
   e.groups = groups;
   e.rows_per_clip = rows_per_clip;
   for (int k = 0; k < kMaxGroups; ++k) e.gfirst[k] = k < groups ? gfirst[k] : 0;
-  return tc_gemm_nt_impl(A, K, Bk, K, C, N, M, N, K, nullptr, 0, &e, sms, st);
+  return tc_gemm_nt_impl(A, K, Bk, Bk_lo, K, C, N, M, N, K, nullptr, 0, &e, sms, st);
 }
 
 }  // namespace bsed
@@ -1140,11 +1224,9 @@ static int tc_wgrad9(TcOperand A, TcOperand Bm, int Bn, int T, int Fv, int kmode
     bsed_set_error("tc_wgrad9: workspace %zu < %zu", part_bytes, need);
     return BSED_E_WORKSPACE;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
     BSED_CHECK_CUDA(cudaFuncSetAttribute(tc::tc_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::W9Smem::TOTAL));
-    configured = true;
-  }
   const double rows = (double)Bn * T * Fv;
   const double taps_real = 9.0;
   const double cin = kmode == tc::W_PAIR ? 16.0 : Bm.C;

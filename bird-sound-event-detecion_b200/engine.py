@@ -35,9 +35,11 @@ def make_cfg(nclass=20, dropout=0.5, nb_filters=(16, 32, 64, 128, 128, 128, 128)
 
 
 def default_precision():
-    """"tf32" (tcgen05 tensor cores; what cuDNN gives the reference on a GPU) unless BSED_PRECISION=fp32."""
+    """"tf32x3" -- error-compensated 3xTF32 on the tcgen05 tensor cores: fp32-grade products, the parity mode against the
+    reference's fp32 arithmetic -- unless BSED_PRECISION says "tf32" (single-pass tf32, what cuDNN convolutions give the
+    reference on a GPU; stated looser tolerance) or "fp32" (CUDA-core cross-check)."""
     import os
-    return os.environ.get("BSED_PRECISION", "tf32").lower()
+    return os.environ.get("BSED_PRECISION", "tf32x3").lower()
 
 
 def _dev_index(device):
@@ -356,28 +358,34 @@ def gemm_tn_tc(a, b, out):
     return out
 
 
-def gemm_nt_tc(a, bk, bias=None, out=None, accumulate=False):
-    """tcgen05: out[M][N] (+)= a[M][K] @ bk[N][K]^T (+ bias)."""
+def gemm_nt_tc(a, bk, bias=None, out=None, accumulate=False, x3=False):
+    """tcgen05: out[M][N] (+)= a[M][K] @ bk[N][K]^T (+ bias); x3 = error-compensated 3xTF32."""
     lib = _lib.load()
     h = _lib.handle(a.device.index)
     M, K = a.shape
     N = bk.shape[0]
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    if x3:
+        ws = torch.empty(2 * N * bk.stride(0), dtype=torch.float32, device=a.device)
+        check(lib.bsed_gemm_nt_tc3(h, _rows(a), a.stride(0), _rows(bk), bk.stride(0), _rows(out), out.stride(0), M, N, K,
+                                   ptr(bias), int(bool(accumulate)), ptr(ws), stream_ptr()), "bsed_gemm_nt_tc3")
+        return out
     check(lib.bsed_gemm_nt_tc(h, _rows(a), a.stride(0), _rows(bk), bk.stride(0), _rows(out), out.stride(0), M, N, K,
                               ptr(bias), int(bool(accumulate)), stream_ptr()), "bsed_gemm_nt_tc")
     return out
 
 
 def conv3x3(x, weight, bias=None, tensor_cores=False):
-    """channels-last x (B, T, F, Cin), weight (Cout, Cin, 3, 3) -> (B, T, F, Cout)."""
+    """channels-last x (B, T, F, Cin), weight (Cout, Cin, 3, 3) -> (B, T, F, Cout).
+    tensor_cores: False = fp32 CUDA cores, True / "tf32" = tcgen05 kind::tf32, "tf32x3" = error-compensated 3xTF32."""
     lib = _lib.load()
     h = _lib.handle(x.device.index)
     B, T, F, Cin = x.shape
     Cout = weight.shape[0]
     y = torch.empty(B, T, F, Cout, dtype=torch.float32, device=x.device)
-    wpack = torch.empty(9 * Cin * Cout, dtype=torch.float32, device=x.device)
-    fn = lib.bsed_conv3x3_tc if tensor_cores else lib.bsed_conv3x3
+    wpack = torch.empty(2 * 9 * Cin * Cout, dtype=torch.float32, device=x.device)
+    fn = (lib.bsed_conv3x3_tc3 if tensor_cores == "tf32x3" else lib.bsed_conv3x3_tc) if tensor_cores else lib.bsed_conv3x3
     check(fn(h, ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(y), B, T, F, Cin, Cout, ptr(wpack),
              stream_ptr()), "bsed_conv3x3")
     return y

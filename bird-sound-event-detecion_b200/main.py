@@ -38,9 +38,16 @@ log = logging.getLogger("bsed_b200.train")
 
 
 def adjust_learning_rate(optimizer, rampup_value, rampdown_value=1, optimizer_d=None, optimizer_crnn=None,
-                         c_epoch=None, rampup_value_adv=None):
-    """lr = rampup * rampdown * max_lr; the d / crnn optimizers get 0.1 x (src/main.py:51-83)."""
+                         c_epoch=None, rampup_value_adv=None, step_decay=False):
+    """lr = rampup * rampdown * max_lr; the d / crnn optimizers get 0.1 x (src/main.py:51-83).
+    step_decay=True is the variant of src/main_baseline.py:53-90: after epoch 100 the rate is halved once and then
+    again every 20 epochs (:72-73, `lr * 0.5 ** (1 + (c_epoch - 100) // 20)`); it needs c_epoch, as there."""
     lr = rampup_value * rampdown_value * cfg.max_learning_rate
+    if step_decay:
+        if c_epoch is None:
+            raise TypeError("adjust_learning_rate(step_decay=True) needs c_epoch (src/main_baseline.py:72 compares it)")
+        if c_epoch > 100:
+            lr = lr * (0.5 ** (1 + ((c_epoch - 100) // 20)))
     for group in optimizer.param_groups:
         group['lr'] = lr
     for opt in (optimizer_d, optimizer_crnn):
@@ -70,9 +77,42 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.fused_step = 0
         self._trainer = None
+        self._pending_state = None      # a state dict loaded before train_mt built the trainer
 
     def step(self, closure=None):
         raise RuntimeError("FusedAdam is driven by MeanTeacherTrainer.step / train_mt")
+
+    def _attach(self, trainer):
+        self._trainer = trainer
+        if self._pending_state is not None:
+            trainer.load_optimizer_state(self._pending_state, self._flat_params())
+            self._pending_state = None
+
+    def _flat_params(self):
+        return [p for g in self.param_groups for p in g["params"]]
+
+    def state_dict(self):
+        """torch.optim.Adam's format -- {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} -- so the
+        reference's `optim.load_state_dict(state['optimizer']['state_dict'])` (src/main.py:866-869 layout) accepts it.
+        The moments live in the trainer's flat buffers (sharded per rank under the fused data-parallel step: gathered here,
+        a collective)."""
+        sd = super().state_dict()
+        if self._trainer is not None:
+            sd["state"] = self._trainer.optimizer_state(self._flat_params())
+        elif self._pending_state is not None:
+            sd["state"] = self._pending_state["state"]
+        return sd
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(g["params"]) != len(mine["params"]) for g, mine in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has a different parameter-group layout")
+        for g, mine in zip(groups, self.param_groups):
+            mine.update({k: v for k, v in g.items() if k != "params"})
+        if self._trainer is not None:
+            self._trainer.load_optimizer_state(state_dict, self._flat_params())
+        else:
+            self._pending_state = state_dict
 
 
 def _rehome(modules, device):
@@ -86,7 +126,57 @@ def _rehome(modules, device):
     return joint, sizes
 
 
-class MeanTeacherTrainer:
+class _TrainerHealth:
+    def check_health(self):
+        """Host sync: raises if the fused data-parallel exchange ever timed out on this rank (utilities/shard.py)."""
+        if getattr(self, "dp", None) is not None:
+            self.dp.check()
+
+    # ---- optimiser state in torch.optim.Adam's layout (checkpoints: utilities/checkpoint.py)
+    def _param_slices(self, params):
+        """(offset, numel) of each optimiser parameter inside the flat buffer (they are views into it)."""
+        base = self.params.data_ptr()
+        out = []
+        for p in params:
+            off = (p.data_ptr() - base) // 4
+            if (p.data_ptr() - base) % 4 or off < 0 or off + p.numel() > self.params.numel():
+                raise RuntimeError("an optimiser parameter does not live in the trainer's flat parameter buffer")
+            out.append((off, p.numel()))
+        return out
+
+    def _full_moments(self):
+        """(m, v) over the whole flat buffer.  Under the fused data-parallel step every rank owns the moments of its slice
+        only: gathered here (collective over the process group)."""
+        if getattr(self, "dp", None) is None:
+            return self.m, self.v
+        return self.dp.gather_owned(self.m), self.dp.gather_owned(self.v)
+
+    def optimizer_state(self, params):
+        m, v = self._full_moments()
+        if self.opt_step == 0:
+            return {}
+        step = torch.tensor(float(self.opt_step))
+        return {i: {"step": step.clone(), "exp_avg": m[o:o + k].view_as(p).clone(), "exp_avg_sq": v[o:o + k].view_as(p).clone()}
+                for i, (p, (o, k)) in enumerate(zip(params, self._param_slices(params)))}
+
+    def load_optimizer_state(self, state_dict, params):
+        st = state_dict.get("state", {})
+        self.m.zero_()
+        self.v.zero_()
+        steps = set()
+        for i, (o, k) in enumerate(self._param_slices(params)):
+            e = st.get(i, st.get(str(i)))
+            if e is None:
+                continue
+            self.m[o:o + k].copy_(e["exp_avg"].reshape(-1))
+            self.v[o:o + k].copy_(e["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(e["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter Adam steps differ ({sorted(steps)}): the fused update keeps one step counter")
+        self.opt_step = steps.pop() if steps else 0
+
+
+class MeanTeacherTrainer(_TrainerHealth):
     """One fused mean-teacher iteration (src/main.py:190-523, pretrain stage, -mt)."""
 
     def __init__(self, model, predictor, ema_model=None, ema_predictor=None, lr=cfg.default_learning_rate,
@@ -131,26 +221,46 @@ class MeanTeacherTrainer:
         self.d_enc = torch.zeros(B, self.plan.t_out, 256, dtype=torch.float32, device=dev)
         self.last = {}
 
+    def _assert_homed(self):
+        """The modules' parameters must still be the views into this trainer's joint buffers (a later model.to() /
+        .cuda() / .float() re-allocates them and would silently detach the optimiser from the forward pass)."""
+        pairs = [(self.model, self.params, 0), (self.predictor, self.params, self.n_crnn)]
+        if self.has_teacher:
+            pairs += [(self.ema_model, self.ema_params, 0), (self.ema_predictor, self.ema_params, self.n_crnn)]
+        for mod, buf, off in pairs:
+            if mod.flat_tensors()[0].data_ptr() != buf.data_ptr() + 4 * off:
+                raise RuntimeError(f"{type(mod).__name__} no longer lives in the trainer's parameter buffer (moved with .to() / "
+                                   ".cuda() after the trainer was built?): build the trainer after the last move")
+
     def step(self, x, x_ema, xs, ts, global_step, rampup_length, max_consistency_cost=cfg.max_consistency_cost):
         """x / x_ema: real batch (student / teacher inputs), xs / ts: synthetic batch and its strong
         targets; all CUDA tensors.  Returns the 4 loss terms as a device tensor
-        [strong_bce, weak_bce, cons_strong, cons_weak] (no host sync)."""
-        ns, nr = self.n_syn, self.n_real
+        [strong_bce, weak_bce, cons_strong, cons_weak] (no host sync).
+        The batch sizes are read from the tensors: anything up to the (n_syn, n_real) the trainer was built for runs in
+        the same plan and buffers (the reference's loaders have no drop_last, so the last batch of an epoch is short)."""
+        ns, nr = int(xs.shape[0]), int(x.shape[0])
+        if ns < 1 or nr < 1 or x_ema.shape[0] != nr or ts.shape[0] != ns:
+            raise ValueError(f"mean-teacher step: {ns} synthetic / {nr} real / {x_ema.shape[0]} teacher clips, {ts.shape[0]} targets")
+        if ns > self.n_syn or nr > self.n_real:
+            raise ValueError(f"mean-teacher step: batch of {ns} + {nr} clips exceeds the {self.n_syn} + {self.n_real} this trainer "
+                             "was built for (build it with the loaders' batch_size)")
+        self._assert_homed()
         nst = ns + nr
+        B = nst + (nr if self.has_teacher else 0)
         m, p = self.model, self.predictor
         self.x[:ns].copy_(xs.reshape(ns, 1, cfg.max_frames, cfg.n_mels))
         self.x[ns:nst].copy_(x.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
         sp, sbn, snbt = m.flat_tensors()
         groups = [dict(params=sp, bn=sbn, nbt=snbt, n=ns), dict(params=sp, bn=sbn, nbt=snbt, n=nr)]
         if self.has_teacher:
-            self.x[nst:].copy_(x_ema.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
+            self.x[nst:B].copy_(x_ema.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
             tp, tbn, tnbt = self.ema_model.flat_tensors()
             groups.append(dict(params=tp, bn=tbn, nbt=tnbt, n=nr))
-        self.plan.forward(groups, self.x, train=True, save=True, seed=self.dropout_seed, step=global_step, enc=self.enc)
+        self.plan.forward(groups, self.x[:B], train=True, save=True, seed=self.dropout_seed, step=global_step, enc=self.enc[:B])
         pp = self.params[self.n_crnn:]
         logits, strong, weak = self.plan.predictor_forward(pp, self.enc[:nst])
         if self.has_teacher:
-            _, strong_ema, weak_ema = self.plan.predictor_forward(self.ema_params[self.n_crnn:], self.enc[nst:])
+            _, strong_ema, weak_ema = self.plan.predictor_forward(self.ema_params[self.n_crnn:], self.enc[nst:B])
             cons_w = max_consistency_cost * ramps.exp_rampup(global_step, rampup_length)
             losses, d_strong, d_weak = engine.mt_loss(strong, weak, 0, ns, ts.contiguous().float(), ns, nr, strong_ema,
                                                       weak_ema, cons_w)
@@ -180,7 +290,7 @@ ISP_SLOTS = ("strong_class", "weak_class", "cons_strong", "cons_weak", "weak_fre
              "cons_weak_freq_shift")
 
 
-class ShiftConsistencyTrainer:
+class ShiftConsistencyTrainer(_TrainerHealth):
     """One fused iteration of train_mt(ISP=True) with a teacher (src/main_baseline.py:229-277, 337-584).
 
     Model calls (each its own BatchNorm batch statistics, in the reference's order per network):
@@ -237,8 +347,16 @@ class ShiftConsistencyTrainer:
              max_consistency_cost=cfg.max_consistency_cost):
         """x / x_ema (n,1,T,F): real batch, student / teacher inputs; target_weak (n,C): its weak labels; xs / ts: synthetic
         batch and strong targets; shift_list (frames, multiples of pooling_time_ratio) / freq_shift_list (bins): per-clip
-        shifts.  Returns the 12 loss terms (ISP_SLOTS order, device tensor, no host sync)."""
-        n, dev = self.n, self.device
+        shifts.  Returns the 12 loss terms (ISP_SLOTS order, device tensor, no host sync).  The batch size is read from
+        the tensors (any n up to the one the trainer was built for; the reference's loaders have no drop_last); like the
+        reference's loop (one shift list serves both batches, src/main_baseline.py:232-277) it needs as many synthetic
+        as real clips."""
+        n, dev = int(x.shape[0]), self.device
+        if n < 1 or xs.shape[0] != n or x_ema.shape[0] != n or len(shift_list) != n or len(freq_shift_list) != n:
+            raise ValueError(f"shift-consistency step: {n} real / {xs.shape[0]} synthetic / {x_ema.shape[0]} teacher clips, "
+                             f"{len(shift_list)} / {len(freq_shift_list)} shifts -- the batches must be equally long")
+        if n > self.n:
+            raise ValueError(f"shift-consistency step: batch of {n} clips exceeds the {self.n} this trainer was built for")
         T, F = cfg.max_frames, cfg.n_mels
         st = torch.tensor([int(v) for v in shift_list], dtype=torch.int32, device=dev)
         sf = torch.tensor([int(v) for v in freq_shift_list], dtype=torch.int32, device=dev)
@@ -246,29 +364,32 @@ class ShiftConsistencyTrainer:
         xr = x.reshape(n, 1, T, F).float().contiguous()
         xe = x_ema.reshape(n, 1, T, F).float().contiguous()
         xsy = xs.reshape(n, 1, T, F).float().contiguous()
-        self.xA[:n].copy_(xsy)
-        self.xA[n:2 * n].copy_(xr)
-        self.xA[2 * n:].copy_(xe)
-        engine.roll_clips(xr, st, None, out=self.xB[:n])
-        engine.roll_clips(xr, None, sf, out=self.xB[n:2 * n])
-        engine.roll_clips(xsy, st, None, out=self.xB[2 * n:3 * n])
-        engine.roll_clips(xsy, None, sf, out=self.xB[3 * n:])
-        engine.roll_clips(xe, st, None, out=self.xC[:n])
-        engine.roll_clips(xe, None, sf, out=self.xC[n:])
+        xA, xB, xC = self.xA[:3 * n], self.xB[:4 * n], self.xC[:2 * n]
+        xA[:n].copy_(xsy)
+        xA[n:2 * n].copy_(xr)
+        xA[2 * n:].copy_(xe)
+        engine.roll_clips(xr, st, None, out=xB[:n])
+        engine.roll_clips(xr, None, sf, out=xB[n:2 * n])
+        engine.roll_clips(xsy, st, None, out=xB[2 * n:3 * n])
+        engine.roll_clips(xsy, None, sf, out=xB[3 * n:])
+        engine.roll_clips(xe, st, None, out=xC[:n])
+        engine.roll_clips(xe, None, sf, out=xC[n:])
         sp, sbn, snbt = self.model.flat_tensors()
         tp, tbn, tnbt = self.ema_model.flat_tensors()
         S = lambda k: dict(params=sp, bn=sbn, nbt=snbt, n=k)
         Tg = lambda k: dict(params=tp, bn=tbn, nbt=tnbt, n=k)
         seed = self.dropout_seed
-        encA, encB, encC = self.enc[:3 * n], self.enc[3 * n:7 * n], self.enc[7 * n:]
-        self.planA.forward([S(n), S(n), Tg(n)], self.xA, train=True, save=True, seed=seed, step=3 * global_step, enc=encA)
-        self.planB.forward([S(n), S(n), S(n), S(n)], self.xB, train=True, save=True, seed=seed, step=3 * global_step + 1,
+        encA, encB, encC = self.enc[:3 * n], self.enc[3 * n:7 * n], self.enc[7 * n:9 * n]
+        self.planA.forward([S(n), S(n), Tg(n)], xA, train=True, save=True, seed=seed, step=3 * global_step, enc=encA)
+        self.planB.forward([S(n), S(n), S(n), S(n)], xB, train=True, save=True, seed=seed, step=3 * global_step + 1,
                            enc=encB)
-        self.planC.forward([Tg(n), Tg(n)], self.xC, train=True, save=False, seed=seed, step=3 * global_step + 2, enc=encC)
+        self.planC.forward([Tg(n), Tg(n)], xC, train=True, save=False, seed=seed, step=3 * global_step + 2, enc=encC)
         pp, tpp = self.params[self.n_crnn:], self.ema_params[self.n_crnn:]
+        s_logits, s_strong, s_weak = self.s_logits[:6 * n], self.s_strong[:6 * n], self.s_weak[:6 * n]
+        t_logits, t_strong, t_weak = self.t_logits[:3 * n], self.t_strong[:3 * n], self.t_weak[:3 * n]
         sl = lambda t, a, b: t[a:b]
-        outS = lambda a, b: (sl(self.s_logits, a, b), sl(self.s_strong, a, b), sl(self.s_weak, a, b))
-        outT = lambda a, b: (sl(self.t_logits, a, b), sl(self.t_strong, a, b), sl(self.t_weak, a, b))
+        outS = lambda a, b: (sl(s_logits, a, b), sl(s_strong, a, b), sl(s_weak, a, b))
+        outT = lambda a, b: (sl(t_logits, a, b), sl(t_strong, a, b), sl(t_weak, a, b))
         self.planA.predictor_forward(pp, encA[:2 * n], out=outS(0, 2 * n))
         self.planA.predictor_forward(pp, encB, out=outS(2 * n, 6 * n))
         self.planA.predictor_forward(tpp, encA[2 * n:], out=outT(0, n))
@@ -281,7 +402,7 @@ class ShiftConsistencyTrainer:
         widx = n // 2
         ts = ts.float().contiguous()
         tw = target_weak.float().contiguous()
-        Ss, Sw, Ts, Tw = self.s_strong, self.s_weak, self.t_strong, self.t_weak
+        Ss, Sw, Ts, Tw = s_strong, s_weak, t_strong, t_weak
         terms = [
             dict(kind=BS, pred_first=0, n=n, ref=ts, slot=0),                                            # :475
             dict(kind=BW, pred_first=0, n=n, ref=ts, ref_is_strong=True, slot=1),                        # :433-434
@@ -305,9 +426,9 @@ class ShiftConsistencyTrainer:
 
         gp = self.grads[self.n_crnn:]
         dA, dB = self.d_enc[:3 * n], self.d_enc[3 * n:7 * n]
-        self.planA.predictor_backward(pp, encA[:2 * n], self.s_logits[:2 * n], Ss[:2 * n], Sw[:2 * n], d_strong[:2 * n],
+        self.planA.predictor_backward(pp, encA[:2 * n], s_logits[:2 * n], Ss[:2 * n], Sw[:2 * n], d_strong[:2 * n],
                                       d_weak[:2 * n], gp, accumulate=False, d_enc=dA[:2 * n])
-        self.planA.predictor_backward(pp, encB, self.s_logits[2 * n:], Ss[2 * n:], Sw[2 * n:], d_strong[2 * n:],
+        self.planA.predictor_backward(pp, encB, s_logits[2 * n:], Ss[2 * n:], Sw[2 * n:], d_strong[2 * n:],
                                       d_weak[2 * n:], gp, accumulate=True, d_enc=dB)
         gc = self.grads[:self.n_crnn]
         self.planA.backward(0b011, dA, gc, accumulate=False)
@@ -396,6 +517,10 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
     n_syn_batches = len(syn_loader)
     losses = None
     fused = isinstance(optimizer, FusedAdam)
+    if shard.world_size() > 1:
+        # ranks enter an epoch together: rank-local work between epochs (validation, checkpoints on rank 0) must not eat
+        # into the peer-arrival timeout of the fused data-parallel step
+        torch.distributed.barrier()
     for i, data1 in enumerate(train_loader):
         try:
             data2 = next(syn_iter)
@@ -408,8 +533,9 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
         rampup_len = cfg.n_epoch_rampup * n_syn_batches
         rampup_value = ramps.exp_rampup(global_step, rampup_len)
         if adjust_lr:
+            # ISP=True is src/main_baseline.py's train_mt, whose adjust_learning_rate halves the rate after epoch 100
             adjust_learning_rate(optimizer, rampup_value, optimizer_d=optimizer_d, optimizer_crnn=optimizer_crnn,
-                                 c_epoch=c_epoch)
+                                 c_epoch=c_epoch, step_decay=bool(ISP))
         dev = model._flat.device
         x = batch_input.to(dev, non_blocking=True)
         x_ema = ema_batch_input.to(dev, non_blocking=True)
@@ -418,13 +544,19 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
         if discriminator is not None:
             domain_loss = adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_d, x, xs)
         if ISP:
+            if xs.shape[0] != x.shape[0]:
+                # the two loaders are cycled independently and have no drop_last: a short last batch on one side.  The
+                # reference's loop applies one per-clip shift list to both batches (src/main_baseline.py:232-277) and
+                # cannot run such a pair either; here the longer batch is cut to the shorter one
+                k = min(xs.shape[0], x.shape[0])
+                x, x_ema, target, xs, ts = x[:k], x_ema[:k], target[:k], xs[:k], ts[:k]
             tr = optimizer._trainer
             if tr is None:
                 g = optimizer.param_groups[0]
                 tr = ShiftConsistencyTrainer(model, predictor, ema_model, ema_predictor, lr=g['lr'], betas=g['betas'],
                                              eps=g['eps'], weight_decay=g['weight_decay'], n=x.shape[0],
                                              dropout_seed=_dropout_state["seed"])
-                optimizer._trainer = tr
+                optimizer._attach(tr)
             tr.lr = optimizer.param_groups[0]['lr']
             # src/main_baseline.py:232-233: per-clip random shifts, +-64 pooled frames in time, +-4 mel bins
             shift_list = [random.randint(-64, 64) * cfg.pooling_time_ratio for _ in range(x.shape[0])]
@@ -440,7 +572,7 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
                 tr = MeanTeacherTrainer(model, predictor, ema_model, ema_predictor, lr=g['lr'], betas=g['betas'],
                                         eps=g['eps'], weight_decay=g['weight_decay'], n_syn=xs.shape[0],
                                         n_real=x.shape[0], dropout_seed=_dropout_state["seed"])
-                optimizer._trainer = tr
+                optimizer._attach(tr)
             tr.lr = optimizer.param_groups[0]['lr']
             losses = tr.step(x, x_ema, xs, ts, global_step, rampup_len)
         else:
@@ -448,6 +580,8 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
             losses = _generic_step(model, predictor, ema_model, ema_predictor, optimizer, (x, x_ema, target_d),
                                    (xs, None, ts), global_step, rampup_value)
     loss = losses.sum() if losses is not None else None
+    if fused and optimizer._trainer is not None:
+        optimizer._trainer.check_health()
     if losses is not None:
         lv = losses.tolist()   # the only host sync of the epoch
         log.info("Epoch: %d\t Time %.2f\t strong %.4f weak %.4f cons_strong %.4f cons_weak %.4f", c_epoch,

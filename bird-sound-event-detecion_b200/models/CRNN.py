@@ -107,7 +107,11 @@ class _FlatModule(nn.Module):
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
-        self._reflatten()
+        # a no-op move (.cuda() / .to() / .float() to where the module already is) leaves every parameter the view it was:
+        # keep the flat storage then -- a trainer may have re-homed it into its joint buffer (main.py: _rehome), and fresh
+        # storage would silently detach the optimiser from the forward pass
+        if not self._flat_ok():
+            self._reflatten()
         return self
 
     def load_state_dict(self, state_dict, *a, **k):

@@ -73,7 +73,7 @@ class Net_resnet(_FlatModule):
             raise NotImplementedError("Net_resnet(pretrained=True) needs torchvision's ImageNet checkpoint (no network here); "
                                       "build with pretrained=False and load a state dict")
         self.n_class = n_class
-        self.precision = precision          # forward GEMMs: "tf32" (tcgen05) / "fp32"; None = engine.default_precision()
+        self.precision = precision          # GEMMs: "tf32x3" / "tf32" (tcgen05) / "fp32"; None = engine.default_precision()
         # backward GEMMs: None = as the forward.  Note for tf32: train-mode BatchNorm on a small batch behind the global
         # average pool is ill-conditioned, so the tf32 rounding of the FORWARD activations already moves the gradients
         # (0.19 rel. L2 on the 2-clip fixture, where the fp32 kernels sit at 0.017 and torch fp32 vs float64 at 0.004);
@@ -175,13 +175,17 @@ class Net_resnet(_FlatModule):
         if tc:
             for n0 in range(0, cout, 128):
                 n1 = min(cout, n0 + 128)
-                engine.gemm_nt_tc(col, wk[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=y[:, n0:n1])
+                engine.gemm_nt_tc(col, wk[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=y[:, n0:n1],
+                                  x3=self._use_x3())
         else:
             engine.gemm_nn(col, wkT, bias, out=y)
         return y
 
     def _use_tc(self):
-        return (self.precision or engine.default_precision()).lower() == "tf32"
+        return (self.precision or engine.default_precision()).lower() in ("tf32", "tf32x3")
+
+    def _use_x3(self):
+        return (self.precision or engine.default_precision()).lower() == "tf32x3"
 
     # ------------------------------------------------------------------------------------------ eval
     def _forward_eval(self, x):
@@ -232,7 +236,7 @@ class Net_resnet(_FlatModule):
                                      self.BN_EPS, self.BN_MOMENTUM)
         tape.append(dict(conv=conv, bn=bn, inp=h, xhat=z, y=y if relu else None, mr=mr, wk=wk, K=K, kpad=kpad,
                          has_res=residual is not None,
-                         tc=(self.backward_precision.lower() == "tf32") if self.backward_precision else tc))
+                         tc=(self.backward_precision.lower() in ("tf32", "tf32x3")) if self.backward_precision else tc))
         return y.view(B, Ho, Wo, conv.cout)
 
     def _forward_train(self, x):
@@ -280,7 +284,7 @@ class Net_resnet(_FlatModule):
                 dcol = torch.empty(dy.shape[0], rec["kpad"], dtype=torch.float32, device=dy.device)
                 for n0 in range(0, rec["kpad"], 128):
                     n1 = min(rec["kpad"], n0 + 128)
-                    engine.gemm_nt_tc(dy, wkT[n0:n1], None, out=dcol[:, n0:n1])
+                    engine.gemm_nt_tc(dy, wkT[n0:n1], None, out=dcol[:, n0:n1], x3=self._use_x3())
             else:
                 dcol = engine.gemm_nn(dy, rec["wk"])
             dx = engine.col2im_nhwc(dcol, tuple(inp.shape), conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad,

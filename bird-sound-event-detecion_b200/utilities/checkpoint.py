@@ -42,8 +42,8 @@ def build_state(model, predictor, crnn_kwargs, predictor_kwargs, optimizer=None,
     if optimizer is not None:
         state["optimizer"] = {"name": type(optimizer).__name__, "args": "",
                               "kwargs": {k: v for k, v in optimizer.defaults.items()},
-                              "state_dict": optimizer.state_dict() if getattr(optimizer, "_trainer", None) is None
-                              else {"fused": True}}
+                              # FusedAdam emits torch.optim.Adam's layout (step / exp_avg / exp_avg_sq per parameter)
+                              "state_dict": optimizer.state_dict()}
     return state
 
 
@@ -51,12 +51,16 @@ def save_state(state, path):
     torch.save(state, path)
 
 
-def load_models(state, model, predictor, ema_model=None, ema_predictor=None):
-    """Load a reference-format checkpoint dict into this package's modules (either CNN key spelling)."""
+def load_models(state, model, predictor, ema_model=None, ema_predictor=None, optimizer=None):
+    """Load a reference-format checkpoint dict into this package's modules (either CNN key spelling) and, when given,
+    the optimizer (`optim.load_state_dict(state['optimizer']['state_dict'])`; a FusedAdam takes torch.optim.Adam's
+    moments into the trainer's flat buffers, so a resumed run continues with its bias correction and moments)."""
     model.load_state_dict(canonical_state_dict(state["model"]["state_dict"]))
     predictor.load_state_dict(state["model_p"]["state_dict"])
     if ema_model is not None and "model_ema" in state:
         ema_model.load_state_dict(canonical_state_dict(state["model_ema"]["state_dict"]))
     if ema_predictor is not None and "model_p_ema" in state:
         ema_predictor.load_state_dict(state["model_p_ema"]["state_dict"])
+    if optimizer is not None and "optimizer" in state:
+        optimizer.load_state_dict(state["optimizer"]["state_dict"])
     return state.get("epoch", 0)

@@ -109,6 +109,21 @@ class FusedDataParallel:
                 self.peer_ema[r] = self._open(r, *info["ema"]) if ema is not None else None
                 self.peer_flags[r] = self._open(r, *info["flags"])
         self.epoch = 0
+        self.check_every = max(1, int(os.environ.get("BSED_DP_CHECK_EVERY", "50")))
+        self._hflag = self._hflag_ev = None
+
+    def close(self):
+        """Unmap the peers' allocations (after the last step; every rank alike)."""
+        from .. import _lib
+        for base in getattr(self, "_opened", {}).values():
+            try:
+                self.lib.bsed_ipc_close(self.h, C.c_void_p(base), 0)
+            except Exception:   # noqa: BLE001 -- interpreter shutdown
+                pass
+        self._opened = {}
+
+    def __del__(self):
+        self.close()
 
     def _open(self, r, handle, offset):
         key = (r, handle)
@@ -149,7 +164,52 @@ class FusedDataParallel:
                                             self.peer_ema if self.ema is not None else None, self.peer_flags, self.epoch,
                                             ptr(m), ptr(v), self.params.numel(), C.byref(cfg), stream_ptr()),
               "bsed_dp_opt_ema_step")
+        if self.epoch % self.check_every == 0:
+            self._poll()
+
+    def owned_slice(self):
+        """[lo, hi) of the flat buffers this rank reduces and updates (csrc/head.cu: dp_opt_ema_step)."""
+        n = self.grads.numel()
+        chunk = -(-n // self.world)
+        chunk = (chunk + 3) // 4 * 4
+        lo = min(n, self.rank * chunk)
+        return lo, min(n, lo + chunk), chunk
+
+    def gather_owned(self, t):
+        """Full-length copy of a per-rank-sharded flat tensor (optimiser moments): every rank contributes its slice."""
+        lo, hi, chunk = self.owned_slice()
+        mine = torch.zeros(chunk, dtype=t.dtype, device=t.device)
+        mine[:hi - lo].copy_(t[lo:hi])
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return torch.cat(parts)[:t.numel()]
+
+    def _poll(self):
+        """Non-blocking health check: read the error flag copied to pinned memory by an EARLIER poll (if that copy has
+        landed), then queue the next copy behind the work already enqueued.  Never stalls the host."""
+        if self._hflag is None:
+            self._hflag = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._hflag_ev = None
+        if self._hflag_ev is not None and self._hflag_ev.query():
+            if int(self._hflag[0]) != 0:
+                self._raise()
+            self._hflag_ev = None
+        if self._hflag_ev is None:
+            self._hflag.copy_(self.flags[33:34], non_blocking=True)
+            self._hflag_ev = torch.cuda.Event()
+            self._hflag_ev.record()
 
     def timed_out(self):
         """True if a spin gave up (a peer never arrived); host sync."""
         return bool(int(self.flags[33].item()))
+
+    def check(self):
+        """Host sync; raises if the exchange kernel ever timed out on this rank (updates after that were dropped)."""
+        if self.timed_out():
+            self._raise()
+
+    def _raise(self):
+        raise RuntimeError(
+            f"fused data-parallel step: rank {self.rank} waited longer than BSED_DP_TIMEOUT_S for a peer (by step {self.epoch}); "
+            "no update was applied after the timeout -- the replicas are no longer in step.  Restart from the last "
+            "checkpoint, or set BSED_DP=nccl.")

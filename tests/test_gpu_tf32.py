@@ -1,5 +1,7 @@
-"""The tensor-core path (tcgen05.mma kind::tf32 fed by TMA; the library default, BSED_PRECISION=tf32)
-against the same oracle and reference fixtures as the fp32 tests.
+"""The single-pass tensor-core mode (tcgen05.mma kind::tf32 fed by TMA, BSED_PRECISION=tf32: what cuDNN gives the
+reference's convolutions on a GPU) against the same oracle and reference fixtures as the other tests.  It is NOT the
+library default and not an inference parity mode: the default is the error-compensated 3xTF32 mode of
+tests/test_gpu_x3.py, which meets the north-star 1e-3 on the same tensor cores.
 
 TF32 keeps 10 mantissa bits of every operand (the tensor core drops the low 13 bits of the fp32 words it
 reads), so one contraction carries ~3e-4 relative error and the 7-block CNN + 2 GRU layers compound it.
@@ -34,10 +36,9 @@ def _report(name, **kv):
     print("[tf32] " + name + " " + " ".join(f"{k}={v:.3e}" for k, v in kv.items()))
 
 
-def test_default_precision_is_tensor_cores(monkeypatch):
+def test_single_pass_mode_is_selectable(monkeypatch):
     from bsed_b200 import engine
-    monkeypatch.delenv("BSED_PRECISION")
-    assert engine.default_precision() == "tf32"
+    assert engine.default_precision() == "tf32"          # the environment override of this file
     plan = engine.Plan(engine.make_cfg(), max_clips=1, device="cuda", with_workspace=False)
     assert plan.precision == "tf32" and plan.lib.bsed_plan_get_precision(plan.p) == 1
 
