@@ -3,7 +3,7 @@
 (src/main.py:train_mt shapes: 12 synthetic + 12 real clips through the student forward + backward,
 the 12 real clips through the teacher forward, BCE/MSE losses, Adam, EMA), plus the log-mel frontend.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|pseudo_label]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|ada|pseudo_label]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).
@@ -342,30 +342,42 @@ def run_b200(args, out):
     if rank == 0:
         sampler.start()
 
-    # ---- device-resident run (value) with the conv kernel class timed by CUDA events over the SAME timed steps
-    # host time to enqueue one step (no synchronisation inside): must stay below the device time or the GPU starves
+    # ---- device-resident run (value): the public trainer call, which replays ONE CUDA graph per iteration from its
+    # second call on (main.py: MeanTeacherTrainer.step).  Host time to enqueue one step (no synchronisation inside) is
+    # measured on the replay path.
+    for i in range(3):
+        trainer.step(x, x_ema, xs, ts, i, rampup_len)           # eager, capture, first replay
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(3):
+    for i in range(3, 13):
         trainer.step(x, x_ema, xs, ts, i, rampup_len)
-    host_enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    host_enqueue_ms = (time.perf_counter() - t0) / 10 * 1e3
     torch.cuda.synchronize()
 
+    ms = timed(lambda i: trainer.step(x, x_ema, xs, ts, 13 + i, rampup_len), args.steps, args.warmup)
+    value = (N_SYN + N_REAL) * world * args.steps / (ms * 1e-3)
+    graphed = bool(trainer._graphs)
+    launches_per_step = next(iter(trainer.graph_launches.values())) if graphed else None
+
+    # ---- the conv kernel class timed by CUDA events: the same steps enqueued kernel by kernel (events cannot be read
+    # out of a replayed graph), its share taken against THIS run's own step time
     counters = {}
 
     def begin_profile():
         counters["launches0"] = lib.bsed_launch_count()
         lib.bsed_profile_begin(1)
 
-    ms = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup, begin_profile)
-    launches = lib.bsed_launch_count() - counters["launches0"]
+    trainer.use_graph = False
+    ms_eager = timed(lambda i: trainer.step(x, x_ema, xs, ts, 100 + i, rampup_len), args.steps, args.warmup, begin_profile)
+    launches_eager = lib.bsed_launch_count() - counters["launches0"]
     pm, pf, pb, pn = C.c_double(), C.c_double(), C.c_double(), C.c_int()
     _lib.check(lib.bsed_profile_end(C.byref(pm), C.byref(pf), C.byref(pb), C.byref(pn)), "profile_end")
-    value = (N_SYN + N_REAL) * world * args.steps / (ms * 1e-3)
+    trainer.use_graph = graphed
+    launches = launches_per_step * args.steps if graphed else launches_eager
 
     # ---- the same device-resident step over >= 300 steps (>= 2 s of GPU time)
     sus_steps = max(300, args.steps)
-    ms_sus = timed(lambda i: trainer.step(x, x_ema, xs, ts, i, rampup_len), sus_steps, 0)
+    ms_sus = timed(lambda i: trainer.step(x, x_ema, xs, ts, 200 + i, rampup_len), sus_steps, 0)
     sustained = {"steps": sus_steps, "ms_per_step": ms_sus / sus_steps, "seconds": ms_sus * 1e-3,
                  "value": (N_SYN + N_REAL) * world * sus_steps / (ms_sus * 1e-3), "unit": "clips/s"}
 
@@ -495,6 +507,9 @@ def run_b200(args, out):
                            "one kernel per rank: reduce-scatter over NVLink peer memory + Adam + EMA + all-gather" if trainer.dp is not None
                            else "NCCL sum all-reduce", trainer.grads.numel() * 4 / 1e6),
                        "host_enqueue_ms_per_step": host_enqueue_ms,
+                       "cuda_graph": ("one graph launch per iteration (device-resident step state: dropout keys, Adam bias "
+                                      "corrections, EMA coefficient, consistency weight)" if graphed else "off"),
+                       "ms_per_step_without_graph": ms_eager / args.steps,
                        "l2": "working set 2.7 GB of activations per step >> 126 MB L2 (no flush needed)",
                        "step_gflop_algorithmic": step_flop / 1e9},
             "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
@@ -510,16 +525,19 @@ def run_b200(args, out):
                          # MMAs per algorithmic one, the pixel-pair view of block 1 counts its true 16 input channels)
                          "achieved": conv_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None,
+                         "frac_of_executed_mmas": (conv_tflops / peaks["tf_sustained"] * (3 * 36 + 24) / 60.0
+                                                   if conv_tflops and trainer.plan.precision == "tf32x3" else None),
                          "traffic": None,
                          "traffic_note": "ncu dram bytes of these launches: profiles/ (see DESIGN.md section 5)",
                          "algorithmic_gflop_per_step": pf.value / args.steps / 1e9,
                          "algorithmic_gflop_per_step_expected": conv_flop_algorithmic / 1e9 if conv_flop_algorithmic else None,
                          "algorithmic_bytes_per_launch": pb.value / pn.value if pn.value else None,
-                         "executed_mma_factor": 3 if trainer.plan.precision == "tf32x3" else 1,
+                         "executed_mma_factor": ("3 on the 36 forward clips, 1 on the 24 data-gradient clips"
+                                                 if trainer.plan.precision == "tf32x3" else 1),
                          "peak_source": peaks["source"] + " bf16 sustained (tf32 nominal dense peak is half of bf16)",
                          "launches": pn.value, "launches_per_step": pn.value / args.steps,
                          "ms_per_step": pm.value / args.steps,
-                         "share_of_step": pm.value / ms if ms else None,
+                         "share_of_step": pm.value / ms_eager if ms_eager else None,
                          "step_tflops": step_flop * args.steps / (ms * 1e-3) / 1e12},
             "frontend": {"metric": "log-mel frontend", "clips_per_s": fe_cps, "algorithmic_GBps": fe_cps * CLIP_BYTES_FRONTEND / 1e9,
                          "hbm_frac": fe_cps * CLIP_BYTES_FRONTEND / 1e9 / peaks["hbm"] / world,
@@ -539,6 +557,171 @@ def run_b200(args, out):
         out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ada(args, out):
+    """BASELINE.json configs[2]: the SCMT + adversarial-domain-adaptation iteration (src/main_scmt_ada_weak_seperate.py:
+    train_mt with a discriminator) -- adversarial update (student forward of both domains -> gradient reversal ->
+    Clip_Discriminator -> BCE -> optimizer_crnn / optimizer_d), then the mean-teacher update with the weak labels of the
+    real batch; SGD-Nesterov x 3; per GPU 12 synthetic + 12 real (6 weak-labelled + 6 pseudo-labelled) clips."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from bsed_b200 import _lib, engine
+    from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
+    from bsed_b200.main import AdaptationTrainer
+    from bsed_b200.models import CRNN, Predictor
+    from bsed_b200.models.CRNN import Clip_Discriminator
+    from bsed_b200.utilities import synth
+    from bsed_b200.utilities.utils import weights_init
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    torch.manual_seed(2023 + rank)
+
+    def make():
+        m, p = CRNN(**engine.REFERENCE_CRNN_KWARGS), Predictor(**engine.REFERENCE_PREDICTOR_KWARGS)
+        weights_init(m)
+        weights_init(p)
+        return m.to(dev).train(), p.to(dev).train()
+
+    model, predictor = make()
+    ema_model, ema_predictor = make()
+    for prm in list(ema_model.parameters()) + list(ema_predictor.parameters()):
+        prm.detach_()
+    torch.manual_seed(7)                                   # identical discriminator on every rank
+    disc = Clip_Discriminator(256).to(dev).train()
+    crit = ConditionalDomainAdversarialLoss(disc)
+    tr = AdaptationTrainer(model, predictor, ema_model, ema_predictor, crit, lr=5e-4, momentum=0.9, weight_decay=1e-4,
+                           n_syn=N_SYN, n_real=N_REAL, dropout_seed=2023 + rank)
+    xs = torch.from_numpy(synth.make_logmel_like(N_SYN, seed=3 + rank)).to(dev)
+    x = torch.from_numpy(synth.make_logmel_like(N_REAL, seed=40 + rank)).to(dev)
+    x_ema = (x + 0.05 * torch.from_numpy(synth.make_logmel_like(N_REAL, seed=60 + rank)).to(dev)).contiguous()
+    ts = torch.from_numpy(synth.make_targets(N_SYN, seed=5 + rank)).to(dev)
+    tw = torch.from_numpy(synth.make_targets(N_REAL, seed=8 + rank)).max(1)[0].to(dev)
+    ramp = 50 * 100
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, before=None):
+        for i in range(warmup):
+            fn(i)
+        sync_all()
+        if before is not None:
+            before()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    cnt = {}
+    ms = timed(lambda i: tr.step(x, x_ema, tw, xs, ts, i, ramp), args.steps, args.warmup,
+               lambda: cnt.update(l0=lib.bsed_launch_count()))
+    launches = lib.bsed_launch_count() - cnt["l0"]
+    value = (N_SYN + N_REAL) * world * args.steps / (ms * 1e-3)
+    # end to end: inputs from pinned host memory every step, losses read back
+    host = [t.cpu().pin_memory() for t in (x, x_ema, tw, xs, ts)]
+    dbuf = [torch.empty_like(t) for t in (x, x_ema, tw, xs, ts)]
+    hloss = torch.empty(5).pin_memory()
+
+    def e2e_step(i):
+        for d_, h_ in zip(dbuf, host):
+            d_.copy_(h_, non_blocking=True)
+        losses, dom = tr.step(dbuf[0], dbuf[1], dbuf[2], dbuf[3], dbuf[4], 1000 + i, ramp)
+        hloss[:4].copy_(losses, non_blocking=True)
+        hloss[4:].copy_(dom, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(e2e_step, args.steps, 2)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        eager = cpu = None
+        if world == 1:
+            eager = _eager_ada(dev, 10, 3)
+            cpu = _eager_ada(torch.device("cpu"), 2, 1)
+        out.emit(json.dumps({
+            "metric": "SCMT + ADA CRNN train clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": tr.plan.precision, "data": "synthetic",
+            "config": {"workload": "SCMT + adversarial domain adaptation step (src/main_scmt_ada_weak_seperate.py:train_mt with "
+                                   "Clip_Discriminator + cdan_frame + gradient reversal): per GPU 12 synthetic + 12 real clips; "
+                                   "adversarial update (2 student calls fwd+bwd, D fwd+bwd, 2 x SGD-Nesterov) then the mean-teacher "
+                                   "update (3 calls, BCE strong/weak incl. the real batch's weak labels, MSE consistency, "
+                                   "SGD-Nesterov, state-dict EMA)", "model": "crnn + clip_discriminator", "clips_per_step_per_gpu": 24,
+                       "parallelism": f"dp{world}: " + ("three fused peer-memory reduce + update kernels per step (encoder+predictor, "
+                                                        "encoder-adversarial, discriminator)" if tr.dp is not None else
+                                                        "NCCL all-reduce" if world > 1 else "single GPU"),
+                       "discriminator_precision": disc.precision},
+            "e2e": {"value": (N_SYN + N_REAL) * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "gpu_eager_baseline": eager, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _eager_ada(dev, steps, warmup):
+    """The reference's module structure (oracle restatement, stock nn.Dropout) running oracle/train.py:ada_step in PyTorch
+    eager mode on `dev` (the B200 with stock cuDNN / cuBLAS settings, or the host cores)."""
+    import torch
+    from oracle import da as oda
+    from oracle import train as otrain
+    from bsed_b200.utilities import synth
+    if dev.type == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    oc, op, tc, tp = _oracle_models(False)
+    for m in (oc, tc):
+        _stock_dropout(m)
+    od = oda.OracleClipDiscriminator()
+    oda.seeded_disc_init(od, 3)
+    for m in (oc, op, tc, tp, od):
+        m.to(dev).train()
+    xs, xr, xr_ema, ts = [t.to(dev) for t in _step_inputs(N_SYN, N_REAL)]
+    tw = torch.from_numpy(synth.make_targets(N_REAL, seed=8)).max(1)[0].to(dev)
+    sgd = dict(lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    opt = torch.optim.SGD(list(oc.parameters()) + list(op.parameters()), **sgd)
+    opt_c, opt_d = torch.optim.SGD(oc.parameters(), **sgd), torch.optim.SGD(od.parameters(), **sgd)
+
+    def step(i):
+        loss, _, _ = otrain.ada_step(oc, op, tc, tp, od, opt, opt_c, opt_d, xr, xr_ema, tw, xs, ts, i, 5000, i)
+        return loss.item()
+
+    for i in range(warmup):
+        step(i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    r = dict(value=(N_SYN + N_REAL) / sec, unit="clips/s", ms_per_step=sec * 1e3, steps=steps, warmup=warmup,
+             kind="port (oracle/train.py:ada_step over oracle/crnn.py + oracle/da.py = the reference's torch.nn layers)")
+    if dev.type == "cpu":
+        r.update(cores=torch.get_num_threads(), sample=f"{steps} steps of the full 12 + 12 (+ 12 teacher) clip iteration")
+    else:
+        r.update(cudnn_allow_tf32=bool(torch.backends.cudnn.allow_tf32), matmul_allow_tf32=bool(torch.backends.cuda.matmul.allow_tf32))
+    return r
 
 
 def run_pseudo_label(args, out):
@@ -604,8 +787,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="crnn", choices=["crnn", "crnn_fpn"],
                     help="crnn = src/models/CRNN.py:CRNN (default, the headline); crnn_fpn = CRNN_fpn (SURVEY 8f-1)")
-    ap.add_argument("--workload", default="train", choices=["train", "pseudo_label"],
-                    help="train = the headline mean-teacher step (default); pseudo_label = configs[4] inference pipeline")
+    ap.add_argument("--workload", default="train", choices=["train", "pseudo_label", "ada"],
+                    help="train = the headline mean-teacher step (default); pseudo_label = configs[4] inference pipeline; "
+                         "ada = configs[2], the SCMT + adversarial domain adaptation iteration")
     ap.add_argument("--replicate", type=int, default=1, help="pseudo_label: repeat the 1 h stream this many times")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -615,6 +799,8 @@ def main():
     with StdoutGuard() as out:
         if args.workload == "pseudo_label":
             run_pseudo_label(args, out)
+        elif args.workload == "ada":
+            run_ada(args, out)
         else:
             run_b200(args, out)
 

@@ -31,7 +31,8 @@ SYMBOLS = [
     "bsed_im2col_nhwc", "bsed_add_relu", "bsed_maxpool_nhwc", "bsed_avgpool_nhwc", "bsed_sigmoid_rows",
     "bsed_bn_rows_workspace_bytes", "bsed_bn_rows_train", "bsed_bn_rows_backward", "bsed_col2im_nhwc",
     "bsed_maxpool_nhwc_backward", "bsed_avgpool_nhwc_backward", "bsed_sigmoid_rows_backward", "bsed_gemm_tn_tc",
-    "bsed_logmel", "bsed_conv3x3_tc3", "bsed_gemm_nt_tc3",
+    "bsed_logmel", "bsed_conv3x3_tc3", "bsed_gemm_nt_tc3", "bsed_scale_f32", "bsed_step_state_advance",
+    "bsed_set_step_state",
 ]
 PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
@@ -60,6 +61,19 @@ class LossTerm(C.Structure):
     _fields_ = [("kind", C.c_int), ("pred_first", C.c_int), ("n_clips", C.c_int), ("ref", C.c_void_p),
                 ("roll", C.c_void_p), ("ref_is_strong", C.c_int), ("weight", C.c_float), ("grad_weight", C.c_float),
                 ("slot", C.c_int)]
+
+
+class StepState(C.Structure):
+    """bsed_step_state (include/bsed.h): the device-resident per-iteration scalars of a captured training step."""
+    _fields_ = [("global_step", C.c_int64), ("opt_step", C.c_int64), ("dp_epoch", C.c_int64), ("keys", C.c_uint32 * 16),
+                ("lr", C.c_float), ("cons_w", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
+                ("ema_a", C.c_float), ("ema_b", C.c_float), ("first_step", C.c_int32), ("pad", C.c_int32)]
+
+
+class StepCfg(C.Structure):
+    _fields_ = [("dropout_seed", C.c_uint64), ("key_mul", C.c_int64), ("key_add", C.c_int64), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("ema_alpha", C.c_float), ("max_consistency_cost", C.c_float),
+                ("rampup_length", C.c_int64)]
 
 
 LOSS_BCE_STRONG, LOSS_BCE_WEAK, LOSS_MSE_STRONG, LOSS_MSE_WEAK = 0, 1, 2, 3
@@ -152,6 +166,9 @@ def load():
         proto("bsed_conv3x3_tc3", i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp)
         proto("bsed_gemm_nt_tc3", i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp)
         proto("bsed_disc_set_precision", i32, vp, i32)
+        proto("bsed_scale_f32", i32, vp, vp, vp, i64, f32, vp)
+        proto("bsed_step_state_advance", i32, vp, vp, P(StepCfg), vp)
+        proto("bsed_set_step_state", i32, vp, vp)
         proto("bsed_disc_param_count", i64)
         proto("bsed_disc_bn_buffer_count", i64)
         proto("bsed_disc_workspace_bytes", sz, i32)

@@ -306,7 +306,7 @@ extern "C" int bsed_mt_loss(bsed_handle h, const float* strong, const float* wea
   BSED_REQUIRE(syn_first >= 0 && syn_first + syn_n <= B && real_first >= 0 && real_first + real_n <= B,
                "bsed_mt_loss: clip ranges outside [0,B)");
   return mt_loss(strong, weak, B, T, C, syn_first, syn_n, syn_target, real_first, real_n, strong_ema, weak_ema, cons_w,
-                 losses, d_strong, d_weak, as_stream(stream));
+                 h->step_state, losses, d_strong, d_weak, as_stream(stream));
 }
 
 extern "C" int bsed_loss_terms(bsed_handle h, const float* strong, const float* weak, int B, int T, int C,
@@ -325,11 +325,27 @@ extern "C" int bsed_roll_clips(bsed_handle h, const float* x, const int32_t* shi
   return roll_clips(x, shift_t, shift_f, out, B, T, F, as_stream(stream));
 }
 
+extern "C" int bsed_step_state_advance(bsed_handle h, bsed_step_state* state, const bsed_step_cfg* cfg, void* stream) {
+  BSED_REQUIRE(h && state && cfg, "bsed_step_state_advance: null argument");
+  return step_state_advance(state, cfg, as_stream(stream));
+}
+
+extern "C" int bsed_set_step_state(bsed_handle h, const bsed_step_state* state) {
+  BSED_REQUIRE(h, "bsed_set_step_state: null handle");
+  h->step_state = state;
+  return BSED_OK;
+}
+
+extern "C" int bsed_scale_f32(bsed_handle h, float* dst, const float* src, int64_t n, float alpha, void* stream) {
+  BSED_REQUIRE(h && dst && src, "bsed_scale_f32: null argument");
+  return scale_f32(dst, src, n, alpha, as_stream(stream));
+}
+
 extern "C" int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m, float* v, float* ema,
                                  int64_t n, const bsed_opt_cfg* cfg, void* stream) {
   BSED_REQUIRE(h && params && grads && m && cfg, "bsed_opt_ema_step: null argument");
   BSED_REQUIRE(cfg->kind != 0 || v, "bsed_opt_ema_step: Adam needs v");
-  return opt_ema_step(params, grads, m, v, ema, n, cfg, as_stream(stream));
+  return opt_ema_step(params, grads, m, v, ema, n, cfg, h->step_state, as_stream(stream));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,14 +392,14 @@ extern "C" int bsed_dp_opt_ema_step(bsed_handle h, int rank, int world, const fl
   BSED_REQUIRE(h && peer_grads && peer_params && peer_flags && m && cfg, "bsed_dp_opt_ema_step: null argument");
   BSED_REQUIRE(cfg->kind != 0 || v, "bsed_dp_opt_ema_step: Adam needs v");
   return dp_opt_ema_step(rank, world, peer_grads, peer_params, peer_ema, reinterpret_cast<int* const*>(peer_flags), epoch, m, v,
-                         n, cfg, h->num_sms, as_stream(stream));
+                         n, cfg, h->step_state, h->num_sms, as_stream(stream));
 }
 
 extern "C" int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffers, int64_t n,
                                 const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float ema_alpha, int64_t ema_step,
                                 void* stream) {
   BSED_REQUIRE(h && bn_buffers && ema_bn_buffers, "bsed_ema_buffers: null argument");
-  return ema_buffers(bn_buffers, ema_bn_buffers, n, nbt, ema_nbt, n_nbt, ema_alpha, ema_step, as_stream(stream));
+  return ema_buffers(bn_buffers, ema_bn_buffers, n, nbt, ema_nbt, n_nbt, ema_alpha, ema_step, h->step_state, as_stream(stream));
 }
 
 // ---------------------------------------------------------------------------------------------

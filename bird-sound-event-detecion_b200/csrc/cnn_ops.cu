@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(256) glu_gate_pool_fwd_kernel(const float* __r
                                                                 const float* __restrict__ lin,
                                                                 float* __restrict__ pooled, Groups g, BNPtrs bn,
                                                                 int T, int F, int C, int pt_rt, int pf_rt, int To, int Fo,
-                                                                uint32_t key, uint32_t thresh, float inv_keep) {
+                                                                DropKey dkey, uint32_t thresh, float inv_keep) {
+  const uint32_t key = dkey.get();
   const int pt = PT ? PT : pt_rt, pf = PF ? PF : pf_rt;
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(256) glu_gate_pool_fwd_kernel(const float* __r
 }
 
 int glu_gate_pool_fwd(const float* xhat, const float* lin, float* pooled, const Groups& g, const BNPtrs& bn,
-                      int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
+                      int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh, float inv_keep,
                       cudaStream_t st) {
   int To = T / pt, Fo = F / pf;
   long long work = (long long)To * Fo * (C / 4);
@@ -573,7 +574,8 @@ __global__ void __launch_bounds__(256) glu_gate_pool_bwd_kernel(const float* __r
                                                                 const float* __restrict__ dpooled,
                                                                 float* __restrict__ dxn, Groups g, BNPtrs bn, int T,
                                                                 int F, int C, int pt, int pf, int To, int Fo,
-                                                                uint32_t key, uint32_t thresh, float inv_keep) {
+                                                                DropKey dkey, uint32_t thresh, float inv_keep) {
+  const uint32_t key = dkey.get();
   constexpr int U = 2;   // quads per thread, loads issued first
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(256) glu_gate_pool_bwd_kernel(const float* __r
 }
 
 int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
-                      const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                      const BNPtrs& bn, int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh,
                       float inv_keep, cudaStream_t st) {
   int To = T / pt, Fo = F / pf;
   long long work = (long long)T * F * (C / 4);
@@ -649,9 +651,10 @@ __global__ void __launch_bounds__(256) glu_gate_pool_bwd_sums_kernel(const float
                                                                      const float* __restrict__ dpooled,
                                                                      float* __restrict__ dxn, Groups g, BNPtrs bn,
                                                                      int T, int F, int C, int pt, int pf, int To,
-                                                                     int Fo, uint32_t key, uint32_t thresh,
+                                                                     int Fo, DropKey dkey, uint32_t thresh,
                                                                      float inv_keep, long long rows_per_cta,
                                                                      double* __restrict__ sums) {
+  const uint32_t key = dkey.get();
   constexpr int U = 2;
   const int clip = g.first[0] + blockIdx.y;
   const int grp = group_of(g, clip);
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(256) glu_gate_pool_bwd_sums_kernel(const float
 }
 
 int glu_gate_pool_bwd_sums(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
-                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh,
                            float inv_keep, double* sums, int num_sms, cudaStream_t st) {
   BSED_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "glu_gate_pool_bwd_sums: C=%d", C);
   const int To = T / pt, Fo = F / pf;

@@ -85,6 +85,16 @@ struct bsed_context {
   int mel_iv_bin0;      // bin of entry 0
   int mel_iv_n;         // entries
   int disc_precision;   // BSED_PRECISION_* of the Clip_Discriminator GEMMs (default FP32, see bsed_disc_set_precision)
+  const bsed_step_state* step_state;   // device-resident per-iteration scalars (bsed_set_step_state) or nullptr
+};
+
+// A dropout key by value (host-computed: bsed_mix_key) or by reference into the device-resident step state
+struct DropKey {
+  uint32_t key;
+  const uint32_t* dev;
+#ifdef __CUDACC__
+  __device__ __forceinline__ uint32_t get() const { return dev ? *dev : key; }
+#endif
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -117,6 +127,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Two independent fp32 FMAs in one instruction (sm_100: FFMA2): d = a * b + d per component, each with the single
+// rounding of fmaf -- bit-identical to two fmaf calls, at half the issue slots and register-file reads.  The dot products
+// of the GRU recurrence are bound by exactly those.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

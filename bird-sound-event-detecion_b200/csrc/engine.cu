@@ -5,6 +5,8 @@
 // (src/models/CNN.py:43-67) -> BiGRU x2 (src/models/RNN.py) -> dropout; Predictor.forward
 // (src/models/CRNN.py:559-577).  One "group" is one reference model call (its own BatchNorm batch
 // statistics); groups that share a parameter buffer are batched in the same GEMM launches.
+#include <stdlib.h>
+
 #include <string>
 #include <vector>
 
@@ -65,6 +67,20 @@ inline bool glu_fused(const LayerGeom& g) {
                                      // (7.9 ms vs 6.8 ms per step on B200), so the separate gate kernel stays the default
 }
 
+// 3xTF32 covers every forward contraction (the parity grade of the probabilities) and the data gradients of the linear
+// layers (GLU, GRU input projections, fpn merges: nn.Linear / 1x1 convolutions are fp32 on the reference's GPU path).
+// The data gradient of the 3x3 convolutions stays single-pass tf32 -- what cuDNN gives the reference
+// (torch.backends.cudnn.allow_tf32) -- unless BSED_X3_DGRAD=1: with 16 ... 64 output columns its three-fold MMA count
+// costs 0.6 ms per step for gradient digits the weight-gradient reductions (single-pass as well) do not keep.
+inline bool x3_conv_dgrad() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BSED_X3_DGRAD");
+    v = e && atoi(e) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr int kLdl = 48;  // padded logits row: [0,20) dense, [20,40) dense_softmax, rest zero
 
 }  // namespace
@@ -115,8 +131,8 @@ struct bsed_crnn_plan {
   const float* pset_params[2];
   int n_psets;
   const float* x_in;
-  uint32_t bkeys[kMaxBlocks];   // dropout keys of the blocks
-  uint32_t skeys[kMaxStacks];   // dropout keys of the stack outputs
+  DropKey bkeys[kMaxBlocks];    // dropout keys of the blocks (by value, or references into the device step state)
+  DropKey skeys[kMaxStacks];    // dropout keys of the stack outputs
   uint32_t thresh;              // encoder-output and trunk-block dropout (cfg.dropout)
   float inv_keep;
   uint32_t bthresh[kMaxBlocks]; // per block: the fpn stage drops with p = 0.5 whatever cfg.dropout is
@@ -436,7 +452,7 @@ void build_prep_table(const bsed_crnn_plan* p, const float* params, float* packe
       split(pk.wp[i], wn);
       if (need_bwd) {
         add(tc ? PREP_CONV_KMAJOR_FLIP : PREP_CONV_PACK_FLIP, params + pl.conv_w[i], packed + pk.wd[i], g.Cout, g.Cin);
-        split(pk.wd[i], wn);
+        if (x3_conv_dgrad()) split(pk.wd[i], wn);
       }
     }
     // d1 != 0: K-major folded matrix [c'][c] for the tensor-core GEMM (B operand [N][K])
@@ -689,8 +705,17 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
   }
   // dropout streams (restated in oracle/crnn.py): trunk block i -> i, encoder output -> 7, fpn stage applications -> 8, 9,
   // rnn_2 / rnn_4 outputs -> 10, 11
-  for (int i = 0; i < p->n_blocks; ++i) p->bkeys[i] = bsed_mix_key(dropout_seed, dropout_step, i < c.n_cnn ? i : 8 + (i - c.n_cnn));
-  for (int s = 0; s < p->n_stacks; ++s) p->skeys[s] = bsed_mix_key(dropout_seed, dropout_step, s == 0 ? 7 : 9 + s);
+  // with a device-resident step state installed (bsed_set_step_state) the keys are read from it at run time, so that a
+  // captured graph of the iteration draws fresh masks on every replay
+  const bsed_step_state* ss = p->ctx->step_state;
+  auto drop_key = [&](int stream) {
+    DropKey k;
+    k.key = ss ? 0u : bsed_mix_key(dropout_seed, dropout_step, stream);
+    k.dev = ss ? ss->keys + stream : nullptr;
+    return k;
+  };
+  for (int i = 0; i < p->n_blocks; ++i) p->bkeys[i] = drop_key(i < c.n_cnn ? i : 8 + (i - c.n_cnn));
+  for (int s = 0; s < p->n_stacks; ++s) p->skeys[s] = drop_key(s == 0 ? 7 : 9 + s);
 
   // runs of clips sharing a parameter set
   struct Run {
@@ -851,11 +876,11 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
       BSED_REQUIRE(M < (1ll << 31), "crnn_forward: too many pixels");
       if (tc) {
         const int pack = glu_pack(L.Cout), CP = L.Cout * pack;   // L.rows is a multiple of 4 (F is even twice over)
-        if (!x3 && glu_fused(L)) {
+        if (!x3 && !ss && glu_fused(L)) {
           // GEMM + gate + dropout + average pool in one kernel; lin is stored only when backward will need it
           BSED_TRY(tc_glu_gate_fwd(y + off, packed + p->pk.glu_wT[i], packed + p->pk.glu_bf[i], packed + p->pk.gate_tab[i],
                                    lin + off, pool + (size_t)runs[r].first * L.prows * L.Cout, runs[r].count, L.T, L.F,
-                                   L.Cout, pack, L.pt, L.pf, p->bkeys[i], p->bthresh[i], p->binv[i], (uint32_t)off, save ? 1 : 0,
+                                   L.Cout, pack, L.pt, L.pf, p->bkeys[i].key, p->bthresh[i], p->binv[i], (uint32_t)off, save ? 1 : 0,
                                    sms, st));
         } else {
           BSED_TRY(tc_gemm_nt(y + off, CP, packed + p->pk.glu_wT[i], LO(packed + p->pk.glu_wT[i]), CP, lin + off, CP, M / pack,
@@ -866,7 +891,7 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         BSED_TRY(gemm_nn(y + off, L.Cout, packed + p->pk.glu_wT[i], L.Cout, lin + off, L.Cout, (int)M, L.Cout, L.Cout,
                          packed + p->pk.glu_bf[i], 0, st));
     }
-    if (!(tc && !x3 && glu_fused(L)))
+    if (!(tc && !x3 && !ss && glu_fused(L)))
       BSED_TRY(glu_gate_pool_fwd(y, lin, pool, g, bn, L.T, L.F, L.Cout, L.pt, L.pf, p->bkeys[i], p->bthresh[i],
                                  p->binv[i], st));
     for (int s = 0; s < p->n_stacks; ++s)
@@ -1172,8 +1197,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       cur ^= 1;
       float* dnext = wsp<float>(ws, p->off_dpool[cur]);
       if (tc)
-        BSED_TRY(tc_conv3x3(dxn + off, packed + p->pk.wd[i], LO(packed + p->pk.wd[i]), dnext + (size_t)first * L.rows * L.Cin, nb,
-                            L.T, L.F, L.Cout, L.Cin, nullptr, 0, sms, st));
+        BSED_TRY(tc_conv3x3(dxn + off, packed + p->pk.wd[i], x3_conv_dgrad() ? LO(packed + p->pk.wd[i]) : nullptr,
+                            dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout, L.Cin, nullptr, 0, sms, st));
       else
         BSED_TRY(conv3x3_nn(dxn + off, packed + p->pk.wd[i], dnext + (size_t)first * L.rows * L.Cin, nb, L.T, L.F, L.Cout,
                             L.Cin, nullptr, 0, st));

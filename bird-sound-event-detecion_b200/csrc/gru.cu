@@ -29,15 +29,16 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + ex
 __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict__ xg, Groups g, FloatPtrs whhT,
                                                         FloatPtrs bhh, float* __restrict__ out,
                                                         float* __restrict__ enc, float* __restrict__ saved, int T,
-                                                        uint32_t key, uint32_t thresh, float inv_keep) {
+                                                        DropKey dkey, uint32_t thresh, float inv_keep) {
+  const uint32_t key = dkey.get();
   const int clip = g.first[0] + blockIdx.x;
   const int dir = blockIdx.y;
   const int j = threadIdx.x;
   const int grp = gru_group_of(g, clip);
   const float* WT = whhT.p[grp] + (size_t)dir * kH * kG;  // [k][j]
-  float w[kH];
+  float2 w[kH / 2];   // row j of W_hh as (even, odd) pairs: the operands of the packed FMAs below
 #pragma unroll
-  for (int k = 0; k < kH; ++k) w[k] = WT[(size_t)k * kG + j];
+  for (int k = 0; k < kH / 2; ++k) w[k] = make_float2(WT[(size_t)(2 * k) * kG + j], WT[(size_t)(2 * k + 1) * kG + j]);
   const float bj = bhh.p[grp][dir * kG + j];
 
   __shared__ __align__(16) float h_s[2][kH];   // double-buffered hidden state: two barriers per step
@@ -56,17 +57,17 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
     const size_t row = xrow(step);
     const float x = nx;
     if (step + 1 < T) nx = xg[xrow(step + 1) * (2 * kG) + dir * kG + j];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // four independent accumulation chains (k mod 4), two per packed FMA: the same sums, in the same order, as four
+    // scalar fmaf chains
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
     const float4* h4 = reinterpret_cast<const float4*>(h_s[buf]);
 #pragma unroll
     for (int k4 = 0; k4 < kH / 4; ++k4) {
-      float4 hv = h4[k4];
-      a0 = fmaf(w[4 * k4 + 0], hv.x, a0);
-      a1 = fmaf(w[4 * k4 + 1], hv.y, a1);
-      a2 = fmaf(w[4 * k4 + 2], hv.z, a2);
-      a3 = fmaf(w[4 * k4 + 3], hv.w, a3);
+      const float4 hv = h4[k4];
+      ffma2(a01, w[2 * k4], make_float2(hv.x, hv.y));
+      ffma2(a23, w[2 * k4 + 1], make_float2(hv.z, hv.w));
     }
-    const float acc = (a0 + a1) + (a2 + a3) + bj;
+    const float acc = (a01.x + a01.y) + (a23.x + a23.y) + bj;
     float* sv = saved ? saved + (row * 2 + dir) * (4 * kH) : nullptr;
     if (j < 2 * kH) {
       const float sg = sigmoid_acc(x + acc);
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
 }
 
 int gru_forward(const float* xg, const Groups& g, const FloatPtrs& whhT, const FloatPtrs& bhh, float* out,
-                float* enc, float* saved, int T, uint32_t key, uint32_t thresh, float inv_keep,
+                float* enc, float* saved, int T, DropKey key, uint32_t thresh, float inv_keep,
                 cudaStream_t st) {
   int B = 0;
   for (int i = 0; i < g.n; ++i) B += g.count[i];
@@ -123,9 +124,10 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
   const int i = threadIdx.x % kH;
   const int gs = threadIdx.x / kH;
   const float* W = whh + (size_t)dir * kG * kH;  // [j][i]
-  float w[kH];
+  float2 w[kH / 2];
 #pragma unroll
-  for (int k = 0; k < kH; ++k) w[k] = W[(size_t)(gs * kH + k) * kH + i];
+  for (int k = 0; k < kH / 2; ++k)
+    w[k] = make_float2(W[(size_t)(gs * kH + 2 * k) * kH + i], W[(size_t)(gs * kH + 2 * k + 1) * kH + i]);
 
   __shared__ __align__(16) float dg_s[kG];
   __shared__ float part_s[3][kH];
@@ -191,17 +193,15 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
     }
     __syncthreads();
     issue(step + kRing - 1);                    // refills the slot consumed in the previous step
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
     const float4* d4 = reinterpret_cast<const float4*>(dg_s + gs * kH);
 #pragma unroll
     for (int k4 = 0; k4 < kH / 4; ++k4) {
-      float4 dv = d4[k4];
-      a0 = fmaf(w[4 * k4 + 0], dv.x, a0);
-      a1 = fmaf(w[4 * k4 + 1], dv.y, a1);
-      a2 = fmaf(w[4 * k4 + 2], dv.z, a2);
-      a3 = fmaf(w[4 * k4 + 3], dv.w, a3);
+      const float4 dv = d4[k4];
+      ffma2(a01, w[2 * k4], make_float2(dv.x, dv.y));
+      ffma2(a23, w[2 * k4 + 1], make_float2(dv.z, dv.w));
     }
-    part_s[gs][i] = (a0 + a1) + (a2 + a3);
+    part_s[gs][i] = (a01.x + a01.y) + (a23.x + a23.y);
     cp_async_wait<kRing - 2>();                 // the group of step + 1 has landed (for this thread) ...
     __syncthreads();                            // ... and for every thread
     if (gs == 0) dh_carry = dh_z + part_s[0][i] + part_s[1][i] + part_s[2][i];

@@ -154,7 +154,8 @@ int head_backward(const float* logits, const float* strong, const float* weak, c
 
 // d[i] = (d[i] + extra[i]) * keep(first_elem + i) / (1 - p)
 __global__ void dropout_bwd_mask_kernel(float* d, const float* extra, long long first_elem, long long n,
-                                        uint32_t key, uint32_t thresh, float inv_keep) {
+                                        DropKey dkey, uint32_t thresh, float inv_keep) {
+  const uint32_t key = dkey.get();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = d[i] + (extra ? extra[i] : 0.f);
@@ -173,7 +174,18 @@ int add_f32(float* dst, const float* src, long long n, cudaStream_t st) {
   return BSED_OK;
 }
 
-int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long long n, uint32_t key,
+__global__ void scale_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float alpha) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = alpha * src[i];
+}
+int scale_f32(float* dst, const float* src, long long n, float alpha, cudaStream_t st) {
+  if (n <= 0) return BSED_OK;
+  scale_f32_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dst, src, n, alpha);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
+int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long long n, DropKey key,
                      uint32_t thresh, float inv_keep, cudaStream_t st) {
   if (n <= 0) return BSED_OK;
   dropout_bwd_mask_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d, extra, first_elem, n, key, thresh, inv_keep);
@@ -298,8 +310,10 @@ __global__ void __launch_bounds__(256) mt_loss_kernel(const float* __restrict__ 
                                                       int T, int C, int syn_first, int syn_n,
                                                       const float* __restrict__ syn_target, int real_first, int real_n,
                                                       const float* __restrict__ strong_ema,
-                                                      const float* __restrict__ weak_ema, float cons_w, float* losses,
+                                                      const float* __restrict__ weak_ema, float cons_w_arg,
+                                                      const bsed_step_state* __restrict__ ss, float* losses,
                                                       float* __restrict__ d_strong, float* __restrict__ d_weak) {
+  const float cons_w = ss ? ss->cons_w : cons_w_arg;
   const int b = blockIdx.x;
   const bool is_syn = b >= syn_first && b < syn_first + syn_n;
   const bool is_real = b >= real_first && b < real_first + real_n;
@@ -371,11 +385,11 @@ __global__ void __launch_bounds__(256) mt_loss_kernel(const float* __restrict__ 
 
 int mt_loss(const float* strong, const float* weak, int B, int T, int C, int syn_first, int syn_n,
             const float* syn_target, int real_first, int real_n, const float* strong_ema, const float* weak_ema,
-            float cons_w, float* losses, float* d_strong, float* d_weak, cudaStream_t st) {
+            float cons_w, const bsed_step_state* ss, float* losses, float* d_strong, float* d_weak, cudaStream_t st) {
   BSED_REQUIRE(C <= kMaxC, "mt_loss: C=%d", C);
   BSED_CHECK_CUDA(cudaMemsetAsync(losses, 0, 4 * sizeof(float), st));
   mt_loss_kernel<<<B, 256, 0, st>>>(strong, weak, T, C, syn_first, syn_n, syn_target, real_first, real_n,
-                                    strong_ema, weak_ema, cons_w, losses, d_strong, d_weak);
+                                    strong_ema, weak_ema, cons_w, ss, losses, d_strong, d_weak);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -505,6 +519,17 @@ struct OptScalars {
   int has_ema;
 };
 
+// per-iteration scalars from the device-resident step state (bsed_set_step_state), when one is installed
+__device__ __forceinline__ void opt_from_state(OptScalars& o, const bsed_step_state* ss) {
+  if (!ss) return;
+  o.lr = ss->lr;
+  o.step_size = ss->step_size;
+  o.bc2_sqrt = ss->bc2_sqrt;
+  o.ema_a = ss->ema_a;
+  o.ema_b = ss->ema_b;
+  o.first_step = ss->first_step;
+}
+
 __device__ __forceinline__ void opt_update(long long i, float grad, float* __restrict__ p, float* __restrict__ m,
                                            float* __restrict__ v, float* __restrict__ ema, const OptScalars& o) {
   float w = p[i];
@@ -530,9 +555,11 @@ __device__ __forceinline__ void opt_update(long long i, float grad, float* __res
 
 __global__ void __launch_bounds__(256) opt_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                       float* __restrict__ m, float* __restrict__ v,
-                                                      float* __restrict__ ema, long long n, OptScalars o) {
+                                                      float* __restrict__ ema, long long n, OptScalars o,
+                                                      const bsed_step_state* __restrict__ ss) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  opt_from_state(o, ss);
   opt_update(i, g[i] * o.grad_scale, p, m, v, ema, o);
 }
 
@@ -562,11 +589,55 @@ static int make_opt_scalars(const bsed_opt_cfg* cfg, bool has_ema, OptScalars* o
   return BSED_OK;
 }
 
+// One thread: next iteration's counters, dropout keys and derived scalars -- the host formulas of bsed_mix_key,
+// make_opt_scalars and utilities/ramps.py:exp_rampup in double precision.
+__global__ void step_state_advance_kernel(bsed_step_state* s, bsed_step_cfg c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long g = s->global_step + 1;
+  const long long t = s->opt_step + 1;
+  s->global_step = g;
+  s->opt_step = t;
+  s->dp_epoch += 1;
+  const unsigned long long dstep = (unsigned long long)(c.key_mul * g + c.key_add);
+  for (int stream = 0; stream < 16; ++stream) {
+    unsigned long long z = c.dropout_seed * 0x9E3779B97F4A7C15ull + dstep * 0xD1B54A32D192ED03ull +
+                           (unsigned long long)stream * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    s->keys[stream] = (uint32_t)(z >> 32);
+  }
+  double ramp = 1.0;
+  if (c.rampup_length > 0) {
+    double cur = (double)g;
+    if (cur < 0) cur = 0;
+    if (cur > (double)c.rampup_length) cur = (double)c.rampup_length;
+    const double phase = 1.0 - cur / (double)c.rampup_length;
+    ramp = exp(-5.0 * phase * phase);
+  }
+  s->cons_w = (float)((double)c.max_consistency_cost * ramp);
+  const double bc1 = 1.0 - pow((double)c.beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)c.beta2, (double)t);
+  s->step_size = (float)((double)s->lr / bc1);
+  s->bc2_sqrt = (float)sqrt(bc2);
+  double a = 1.0 - 1.0 / ((double)(g + 1) + 1.0);
+  if (a > (double)c.ema_alpha) a = (double)c.ema_alpha;
+  s->ema_a = (float)a;
+  s->ema_b = (float)(1.0 - a);
+  s->first_step = t == 1;
+}
+
+int step_state_advance(bsed_step_state* state, const bsed_step_cfg* cfg, cudaStream_t st) {
+  step_state_advance_kernel<<<1, 32, 0, st>>>(state, *cfg);
+  BSED_CHECK_LAUNCH();
+  return BSED_OK;
+}
+
 int opt_ema_step(float* params, const float* grads, float* m, float* v, float* ema, long long n,
-                 const bsed_opt_cfg* cfg, cudaStream_t st) {
+                 const bsed_opt_cfg* cfg, const bsed_step_state* ss, cudaStream_t st) {
   OptScalars o;
   BSED_TRY(make_opt_scalars(cfg, ema != nullptr, &o));
-  opt_ema_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, m, v, ema, n, o);
+  opt_ema_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, m, v, ema, n, o, ss);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -636,7 +707,9 @@ __device__ bool dp_wait(const int* flags, int base, int world, int epoch, unsign
 __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank, int world, int epoch, float* __restrict__ p,
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          float* __restrict__ ema, long long lo, long long hi, OptScalars o,
-                                                         unsigned long long timeout_ns) {
+                                                         unsigned long long timeout_ns, const bsed_step_state* __restrict__ ss) {
+  opt_from_state(o, ss);
+  if (ss) epoch = (int)ss->dp_epoch;
   int* my = peers.flags[rank];
   __shared__ int ok_s;
   if (threadIdx.x == 0) {
@@ -686,7 +759,7 @@ __global__ void __launch_bounds__(256) dp_opt_ema_kernel(DpPeers peers, int rank
 
 int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* const* peer_params, float* const* peer_ema,
                     int* const* peer_flags, long long epoch, float* m, float* v, long long n, const bsed_opt_cfg* cfg,
-                    int num_sms, cudaStream_t st) {
+                    const bsed_step_state* ss, int num_sms, cudaStream_t st) {
   BSED_REQUIRE(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "dp_opt: rank %d of %d", rank, world);
   BSED_REQUIRE(epoch >= 1 && epoch < (1ll << 31), "dp_opt: epoch %lld", epoch);
   const bool has_ema = peer_ema != nullptr && peer_ema[rank] != nullptr;
@@ -715,13 +788,18 @@ int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* 
     timeout_s = e && atof(e) > 0 ? atof(e) : 60.0;
   }
   dp_opt_ema_kernel<<<grid, 256, 0, st>>>(peers, rank, world, (int)epoch, peers.params[rank], m, v, peers.ema[rank], lo, hi, o,
-                                          (unsigned long long)(timeout_s * 1e9));
+                                          (unsigned long long)(timeout_s * 1e9), ss);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
 
 __global__ void ema_buffers_kernel(const float* __restrict__ src, float* __restrict__ ema, long long n,
-                                   const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float a, float bcoef) {
+                                   const int64_t* nbt, int64_t* ema_nbt, int n_nbt, float a, float bcoef,
+                                   const bsed_step_state* __restrict__ ss) {
+  if (ss) {
+    a = ss->ema_a;
+    bcoef = ss->ema_b;
+  }
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ema[i] = __fadd_rn(__fmul_rn(ema[i], a), __fmul_rn(src[i], bcoef));
   if (i < n_nbt) {
@@ -731,13 +809,13 @@ __global__ void ema_buffers_kernel(const float* __restrict__ src, float* __restr
 }
 
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
-                int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st) {
+                int n_nbt, float ema_alpha, int64_t ema_step, const bsed_step_state* ss, cudaStream_t st) {
   double a = 1.0 - 1.0 / ((double)ema_step + 1.0);
   if (a > (double)ema_alpha) a = (double)ema_alpha;
   long long work = n > n_nbt ? n : n_nbt;
   if (work <= 0) return BSED_OK;
   ema_buffers_kernel<<<ceil_div(work, 256), 256, 0, st>>>(bn_buffers, ema_bn_buffers, n, nbt, ema_nbt,
-                                                          nbt && ema_nbt ? n_nbt : 0, (float)a, (float)(1.0 - a));
+                                                          nbt && ema_nbt ? n_nbt : 0, (float)a, (float)(1.0 - a), ss);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

@@ -56,13 +56,13 @@ int bn_prepare_eval(const Groups& g, int C, float eps, const BNPtrs& bn, float* 
 int bn_normalize(float* y, const Groups& g, long long rows_per_clip, int C, const BNPtrs& bn,
                  cudaStream_t st);
 int glu_gate_pool_fwd(const float* xhat, const float* lin, float* pooled, const Groups& g, const BNPtrs& bn,
-                      int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh, float inv_keep,
+                      int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh, float inv_keep,
                       cudaStream_t st);
 int glu_gate_pool_bwd(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
-                      const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                      const BNPtrs& bn, int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh,
                       float inv_keep, cudaStream_t st);
 int glu_gate_pool_bwd_sums(const float* xhat, float* lin_dlin, const float* dpooled, float* dxn, const Groups& g,
-                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, uint32_t key, uint32_t thresh,
+                           const BNPtrs& bn, int T, int F, int C, int pt, int pf, DropKey key, uint32_t thresh,
                            float inv_keep, double* sums, int num_sms, cudaStream_t st);
 int bn_bwd_prepare(const double* sums, const float* G, int n_groups, int C, const Groups& g, long long rows_per_clip,
                    const BNPtrs& bn, const float* wg, const float* gamma, const float* beta, int pack, float* tab,
@@ -109,7 +109,7 @@ int run_split(const SplitTable& table, float* packed, long long lo_offset, cudaS
 // xg [B][T][768] input projections (both directions); whhT per group: [2][128][384]; bhh per group: [2][384]
 // out [B][T][256]; enc (optional) = dropout(out); saved (optional) [B][T][2][4][128] = r, z, n, W_hn h + b_hn
 int gru_forward(const float* xg, const Groups& g, const FloatPtrs& whhT, const FloatPtrs& bhh, float* out,
-                float* enc, float* saved, int T, uint32_t key, uint32_t thresh, float inv_keep,
+                float* enc, float* saved, int T, DropKey key, uint32_t thresh, float inv_keep,
                 cudaStream_t st);
 // whh: [2][384][128]; dxg / dgh [B][T][768]
 int gru_backward(const float* dout, const float* saved, const float* out, const float* whh, float* dxg,
@@ -121,22 +121,24 @@ int head_forward(const float* logits, float* strong, float* weak, int B, int T, 
 int head_backward(const float* logits, const float* strong, const float* weak, const float* d_strong,
                   const float* d_weak, float* d_logits, int first_clip, int n_clips, int T, int C, int ldl,
                   cudaStream_t st);
-int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long long n, uint32_t key,
+int dropout_bwd_mask(float* d, const float* extra, long long first_elem, long long n, DropKey key,
                      uint32_t thresh, float inv_keep, cudaStream_t st);
 int mt_loss(const float* strong, const float* weak, int B, int T, int C, int syn_first, int syn_n,
             const float* syn_target, int real_first, int real_n, const float* strong_ema, const float* weak_ema,
-            float cons_w, float* losses, float* d_strong, float* d_weak, cudaStream_t st);
+            float cons_w, const bsed_step_state* ss, float* losses, float* d_strong, float* d_weak, cudaStream_t st);
 int loss_terms(const float* strong, const float* weak, int B, int T, int C, const bsed_loss_term* terms, int n_terms,
                float* losses, int n_slots, float* d_strong, float* d_weak, cudaStream_t st);
 int roll_clips(const float* x, const int* shift_t, const int* shift_f, float* out, int B, int T, int F, cudaStream_t st);
 int opt_ema_step(float* params, const float* grads, float* m, float* v, float* ema, long long n,
-                 const bsed_opt_cfg* cfg, cudaStream_t st);
+                 const bsed_opt_cfg* cfg, const bsed_step_state* ss, cudaStream_t st);
+int step_state_advance(bsed_step_state* state, const bsed_step_cfg* cfg, cudaStream_t st);
 int dp_opt_ema_step(int rank, int world, const float* const* peer_grads, float* const* peer_params, float* const* peer_ema,
                     int* const* peer_flags, long long epoch, float* m, float* v, long long n, const bsed_opt_cfg* cfg,
-                    int num_sms, cudaStream_t st);
+                    const bsed_step_state* ss, int num_sms, cudaStream_t st);
 int ema_buffers(const float* bn_buffers, float* ema_bn_buffers, long long n, const int64_t* nbt, int64_t* ema_nbt,
-                int n_nbt, float ema_alpha, int64_t ema_step, cudaStream_t st);
+                int n_nbt, float ema_alpha, int64_t ema_step, const bsed_step_state* ss, cudaStream_t st);
 int add_f32(float* dst, const float* src, long long n, cudaStream_t st);
+int scale_f32(float* dst, const float* src, long long n, float alpha, cudaStream_t st);
 // feature-pyramid merge (src/models/CRNN.py:323-328): cat[b][t][0:256] = a[b][t], cat[b][t][256:512] = bilinear
 // (align_corners=True) upsampling of b from Tb to Ta frames; backward splits dcat into da and the transposed upsampling db
 int fpn_cat_upsample_fwd(const float* a, const float* b, float* cat, int B, int Ta, int Tb, cudaStream_t st);

@@ -11,7 +11,9 @@ namespace tc {
 
 constexpr int kBM = 128;
 constexpr int kThreads = 192;     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
-constexpr int kThreadsX3 = 320;   // + warps 6-9: operand splitters of the 3xTF32 mode
+constexpr int kThreadsX3 = 256;   // + warps 6-7: operand splitters of the 3xTF32 mode (8 warps keep the 255-register
+                                  // budget of the epilogue warps; with 10 warps ptxas caps every thread at 168)
+constexpr int kSplitThreads = kThreadsX3 - kThreads;
 constexpr uint32_t kSpinLimit = 1u << 26;   // bounded mbarrier waits: trap instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------
@@ -109,7 +111,8 @@ __device__ __forceinline__ float4 tf32_lo4(float4 v) {
   return make_float4(tf32_rna(v.x - tf32_trunc(v.x)), tf32_rna(v.y - tf32_trunc(v.y)), tf32_rna(v.z - tf32_trunc(v.z)),
                      tf32_rna(v.w - tf32_trunc(v.w)));
 }
-__device__ __forceinline__ void split_barrier() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void split_barrier() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+static_assert(kThreadsX3 - kThreads == 64, "split_barrier counts the splitter threads");
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

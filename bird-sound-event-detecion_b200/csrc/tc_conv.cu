@@ -24,7 +24,7 @@ constexpr int kHaloRows = 130;      // t0-1 .. t0+128
 constexpr int kHaloPad = 136;       // rows of one column copy, padded to the 8-row swizzle repeat
 constexpr int kAStages = 2;
 // 3xTF32 (X3, see tc_gemm.cu): the input is walked in 16-channel chunks (64-byte rows, SWIZZLE_64B), so that the raw
-// column copies, their low parts (one set per stage, written by four splitter warps) and a ring of (hi, lo) weight tiles
+// column copies, their low parts (one set per stage, written by two splitter warps) and a ring of (hi, lo) weight tiles
 // fit the 227 KB of shared memory; every (tap, k-step) issues a*w_hi + a*w_lo + a_lo*w_hi.
 
 struct CArgs {
@@ -232,7 +232,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (X3 && warp >= 6) {
-    // ===================== operand splitters (warps 6..9, 3xTF32) =====================
+    // ===================== operand splitters (warps 6..7, 3xTF32) =====================
     // lo[sa] is free whenever A[sa] is: a stage is refilled only after the MMAs that read both have completed
     const int tid = threadIdx.x - 6 * 32;
     const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -242,7 +242,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       mbar_wait(&afull[sa], (step / kAStages) & 1);
       const uint32_t src = smem_u32(smem + sa * S::A_STAGE), dst = smem_u32(alo + sa * S::A_STAGE);
 #pragma unroll 4
-      for (int i = tid; i < S::A_STAGE / 16; i += 128) {
+      for (int i = tid; i < S::A_STAGE / 16; i += kSplitThreads) {
         const float4 v = lds128(src + i * 16);
         sts128(dst + i * 16, tf32_lo4(v));
       }

@@ -55,9 +55,9 @@ struct KArgs {
 constexpr int kRbBytes = 72 * 1024;
 
 constexpr int kMaxStages = 24;
-constexpr int kLoBufs = 2;   // 3xTF32: low-part tiles in flight between the splitters and the MMA issuer
+constexpr int kLoBufs = 3;   // 3xTF32: low-part tiles in flight between the splitters and the MMA issuer
 
-// X3 ("3xTF32"): error-compensated fp32-grade products on the tf32 tensor cores.  The activation tile arrives raw; four
+// X3 ("3xTF32"): error-compensated fp32-grade products on the tf32 tensor cores.  The activation tile arrives raw; two
 // extra warps write its low part a - tf32(a) into a second tile; the weights come pre-split (hi, lo) from the prep pass;
 // every k-step issues three MMAs: a*b_hi + a*b_lo + a_lo*b_hi.
 template <int N, int KCH, bool RB, bool X3>
@@ -70,10 +70,10 @@ struct KSmem {
   static constexpr int LO_BYTES = X3 ? kLoBufs * A_BYTES : 0;
   static constexpr int STG_BYTES = kBM * N * 4;   // output tile staged for the TMA store
   static constexpr int STG2_BYTES = (!X3 && N <= 64) ? kBM * N * 4 : 0;   // gated tile of the fused GLU epilogue (epi == 2)
-  static constexpr int BAR_BYTES = 512;   // 2 * stages + 9 mbarriers + the TMEM slot
+  static constexpr int BAR_BYTES = 512;   // 2 * stages + 5 + 2 * kLoBufs mbarriers + the TMEM slot
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
   static constexpr int FIXED = LO_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
-  static_assert((2 * kMaxStages + 10) * 8 <= BAR_BYTES, "barrier region too small");
+  static_assert((2 * kMaxStages + 6 + 2 * kLoBufs) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
 template <int N, int KCH, bool RB, bool X3>
@@ -99,8 +99,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* rbfull = bars + 2 * STAGES + 4;
   uint64_t* lofull = bars + 2 * STAGES + 5;
-  uint64_t* loempty = bars + 2 * STAGES + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 9);
+  uint64_t* loempty = lofull + kLoBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(loempty + kLoBufs);
   float* sbias = reinterpret_cast<float*>(stg2 + S::STG2_BYTES + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -115,6 +115,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+    }
+    for (int i = 0; i < kLoBufs; ++i) {
       mbar_init(&lofull[i], 1);
       mbar_init(&loempty[i], 1);
     }
@@ -219,7 +221,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (X3 && warp >= 6) {
-    // ===================== operand splitters (warps 6..9, 3xTF32) =====================
+    // ===================== operand splitters (warps 6..7, 3xTF32) =====================
     const int tid = threadIdx.x - 6 * 32;
     int s = 0, lj = 0;
     uint32_t ph = 0, lph = 0;
@@ -229,7 +231,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(&loempty[lj], lph ^ 1);
         const uint32_t src = smem_u32(smem + s * S::STAGE), dst = smem_u32(lo + lj * S::A_BYTES);
 #pragma unroll 4
-        for (int i = tid; i < S::A_BYTES / 16; i += 128) {
+        for (int i = tid; i < S::A_BYTES / 16; i += kSplitThreads) {
           const float4 v = lds128(src + i * 16);
           sts128(dst + i * 16, tf32_lo4(v));
         }

@@ -181,8 +181,13 @@ class MeanTeacherTrainer(_TrainerHealth):
 
     def __init__(self, model, predictor, ema_model=None, ema_predictor=None, lr=cfg.default_learning_rate,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, n_syn=cfg.batch_size, n_real=cfg.batch_size,
-                 ema_flavour="state_dict", dropout_seed=2023, process_group=None, precision=None):
+                 ema_flavour="state_dict", dropout_seed=2023, process_group=None, precision=None, opt_kind="adam",
+                 momentum=0.9, graph=None):
+        """opt_kind "adam" (src/main.py:823-828) or "sgd" = SGD with Nesterov momentum, the optimiser of the adaptation
+        scripts (src/main_scmt_ada_weak_seperate.py:858-866: lr, momentum .9, weight_decay 1e-4, nesterov)."""
         assert isinstance(model, CRNN) and isinstance(predictor, Predictor)
+        assert opt_kind in ("adam", "sgd")
+        self.opt_kind, self.momentum = opt_kind, momentum
         self.model, self.predictor, self.ema_model, self.ema_predictor = model, predictor, ema_model, ema_predictor
         dev = model._flat.device
         if dev.type != "cuda":
@@ -220,6 +225,12 @@ class MeanTeacherTrainer(_TrainerHealth):
         self.enc = torch.empty(B, self.plan.t_out, 256, dtype=torch.float32, device=dev)
         self.d_enc = torch.zeros(B, self.plan.t_out, 256, dtype=torch.float32, device=dev)
         self.last = {}
+        # CUDA-graph path (see step): static target buffer, device-resident step state, one graph per batch shape
+        self.use_graph = (os.environ.get("BSED_GRAPH", "1") != "0") if graph is None else bool(graph)
+        self.ts_static = torch.zeros(n_syn, self.plan.t_out, self.plan.n_class, dtype=torch.float32, device=dev)
+        self._state = None
+        self._dev_gs = self._dev_opt = self._dev_lr = self._dev_dp = None
+        self._graphs, self._seen, self.graph_launches = {}, set(), {}
 
     def _assert_homed(self):
         """The modules' parameters must still be the views into this trainer's joint buffers (a later model.to() /
@@ -232,12 +243,21 @@ class MeanTeacherTrainer(_TrainerHealth):
                 raise RuntimeError(f"{type(mod).__name__} no longer lives in the trainer's parameter buffer (moved with .to() / "
                                    ".cuda() after the trainer was built?): build the trainer after the last move")
 
-    def step(self, x, x_ema, xs, ts, global_step, rampup_length, max_consistency_cost=cfg.max_consistency_cost):
+    def step(self, x, x_ema, xs, ts, global_step, rampup_length, max_consistency_cost=cfg.max_consistency_cost,
+             target_weak=None, dropout_step=None):
         """x / x_ema: real batch (student / teacher inputs), xs / ts: synthetic batch and its strong
         targets; all CUDA tensors.  Returns the 4 loss terms as a device tensor
         [strong_bce, weak_bce, cons_strong, cons_weak] (no host sync).
+        target_weak (n_real, C): weak labels of the real batch -- adds BCE(weak_pred, target_weak) to the weak term, the
+        loss of the weak-label scripts (src/main_scmt_ada_weak_seperate.py:437-445).
         The batch sizes are read from the tensors: anything up to the (n_syn, n_real) the trainer was built for runs in
-        the same plan and buffers (the reference's loaders have no drop_last, so the last batch of an epoch is short)."""
+        the same plan and buffers (the reference's loaders have no drop_last, so the last batch of an epoch is short).
+
+        With `use_graph` (default; BSED_GRAPH=0 turns it off) the iteration runs as ONE CUDA-graph launch from the second
+        call with a given batch shape on: everything that changes between iterations (dropout draw, Adam bias corrections,
+        EMA coefficient, consistency weight, data-parallel epoch) lives in a device-resident step state that a one-thread
+        kernel at the head of the graph advances (include/bsed.h: bsed_step_state).  The returned tensors are then static
+        buffers that the next call overwrites."""
         ns, nr = int(xs.shape[0]), int(x.shape[0])
         if ns < 1 or nr < 1 or x_ema.shape[0] != nr or ts.shape[0] != ns:
             raise ValueError(f"mean-teacher step: {ns} synthetic / {nr} real / {x_ema.shape[0]} teacher clips, {ts.shape[0]} targets")
@@ -247,42 +267,254 @@ class MeanTeacherTrainer(_TrainerHealth):
         self._assert_homed()
         nst = ns + nr
         B = nst + (nr if self.has_teacher else 0)
-        m, p = self.model, self.predictor
         self.x[:ns].copy_(xs.reshape(ns, 1, cfg.max_frames, cfg.n_mels))
         self.x[ns:nst].copy_(x.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
+        if self.has_teacher:
+            self.x[nst:B].copy_(x_ema.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
+        graphable = (self.use_graph and target_weak is None and dropout_step is None
+                     and (self.world == 1 or self.dp is not None))
+        if not graphable:
+            out = self._body(ns, nr, ts.contiguous().float(), global_step, rampup_length, max_consistency_cost, target_weak,
+                             dropout_step, device_state=False)
+        else:
+            self.ts_static[:ns].copy_(ts)
+            self._sync_state(global_step)
+            key = (ns, nr, int(rampup_length), float(max_consistency_cost))
+            if key in self._graphs:
+                g, out = self._graphs[key]
+                g.replay()
+            elif key in self._seen:          # second iteration with this shape: capture it, then run it
+                from . import _lib
+                lib = _lib.load()
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                n0 = lib.bsed_launch_count()
+                with torch.cuda.graph(g):
+                    out = self._body(ns, nr, self.ts_static[:ns], global_step, rampup_length, max_consistency_cost, None, None,
+                                     device_state=True)
+                self.graph_launches[key] = int(lib.bsed_launch_count() - n0)
+                self._graphs[key] = (g, out)
+                g.replay()
+            else:
+                self._seen.add(key)
+                out = self._body(ns, nr, self.ts_static[:ns], global_step, rampup_length, max_consistency_cost, None, None,
+                                 device_state=True)
+            self._dev_gs = global_step
+            if self.dp is not None:
+                self.dp.note_graph_step()
+        self.opt_step += 1
+        self.last = out
+        return out["losses"]
+
+    # ---- device-resident step state (CUDA-graph path)
+    def _step_cfg(self, rampup_length, max_consistency_cost):
+        from ._lib import StepCfg
+        c = StepCfg()
+        c.dropout_seed, c.key_mul, c.key_add = int(self.dropout_seed), 1, 0
+        c.beta1, c.beta2, c.ema_alpha = float(self.betas[0]), float(self.betas[1]), 0.999
+        c.max_consistency_cost, c.rampup_length = float(max_consistency_cost), int(rampup_length)
+        return c
+
+    def _sync_state(self, global_step):
+        """Make the device counters agree with the host's view before an iteration: normally they already do (each
+        iteration advances them by one on the device); a jump of global_step, a changed learning rate or an optimiser
+        state loaded from a checkpoint is written through with one small copy."""
+        import ctypes as C
+        from ._lib import StepState
+        dp_epoch = self.dp.epoch if self.dp is not None else 0
+        want = (global_step - 1, self.opt_step, float(self.lr), dp_epoch)
+        if self._state is None:
+            self._state = torch.zeros(C.sizeof(StepState), dtype=torch.uint8, device=self.device)
+            self._dev_view = None
+        have = (self._dev_gs, self._dev_opt, self._dev_lr, self._dev_dp)
+        if have != want:
+            hs = StepState()
+            hs.global_step, hs.opt_step, hs.dp_epoch, hs.lr = global_step - 1, self.opt_step, dp_epoch, float(self.lr)
+            self._state.copy_(torch.frombuffer(bytearray(bytes(hs)), dtype=torch.uint8))
+        # what the device will hold after this iteration's advance
+        self._dev_gs, self._dev_opt, self._dev_lr, self._dev_dp = global_step, self.opt_step + 1, float(self.lr), dp_epoch + 1
+
+    def _body(self, ns, nr, ts, global_step, rampup_length, max_consistency_cost, target_weak, dropout_step, device_state):
+        """The kernel sequence of one iteration.  device_state: the per-iteration scalars come from the device-resident
+        step state (advanced here), not from the host values passed along -- the form that can be captured."""
+        from . import _lib
+        nst = ns + nr
+        B = nst + (nr if self.has_teacher else 0)
+        m, p = self.model, self.predictor
         sp, sbn, snbt = m.flat_tensors()
         groups = [dict(params=sp, bn=sbn, nbt=snbt, n=ns), dict(params=sp, bn=sbn, nbt=snbt, n=nr)]
         if self.has_teacher:
-            self.x[nst:B].copy_(x_ema.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
             tp, tbn, tnbt = self.ema_model.flat_tensors()
             groups.append(dict(params=tp, bn=tbn, nbt=tnbt, n=nr))
-        self.plan.forward(groups, self.x[:B], train=True, save=True, seed=self.dropout_seed, step=global_step, enc=self.enc[:B])
-        pp = self.params[self.n_crnn:]
-        logits, strong, weak = self.plan.predictor_forward(pp, self.enc[:nst])
-        if self.has_teacher:
-            _, strong_ema, weak_ema = self.plan.predictor_forward(self.ema_params[self.n_crnn:], self.enc[nst:B])
-            cons_w = max_consistency_cost * ramps.exp_rampup(global_step, rampup_length)
-            losses, d_strong, d_weak = engine.mt_loss(strong, weak, 0, ns, ts.contiguous().float(), ns, nr, strong_ema,
-                                                      weak_ema, cons_w)
+        lib, h = _lib.load(), _lib.handle(self.device.index)
+        if device_state:
+            sptr = _lib.C.c_void_p(self._state.data_ptr())
+            _lib.check(lib.bsed_step_state_advance(h, sptr, _lib.C.byref(self._step_cfg(rampup_length, max_consistency_cost)),
+                                                   _lib.stream_ptr()), "bsed_step_state_advance")
+            _lib.check(lib.bsed_set_step_state(h, sptr), "bsed_set_step_state")
+        try:
+            self.plan.forward(groups, self.x[:B], train=True, save=True, seed=self.dropout_seed,
+                              step=global_step if dropout_step is None else dropout_step, enc=self.enc[:B])
+            pp = self.params[self.n_crnn:]
+            logits, strong, weak = self.plan.predictor_forward(pp, self.enc[:nst])
+            cons_w = 0.0
+            if self.has_teacher:
+                _, strong_ema, weak_ema = self.plan.predictor_forward(self.ema_params[self.n_crnn:], self.enc[nst:B])
+                cons_w = max_consistency_cost * ramps.exp_rampup(global_step, rampup_length)
+            if target_weak is not None:
+                from ._lib import LOSS_BCE_STRONG as BS, LOSS_BCE_WEAK as BW, LOSS_MSE_STRONG as MS, LOSS_MSE_WEAK as MW
+                terms = [dict(kind=BS, pred_first=0, n=ns, ref=ts, slot=0),
+                         dict(kind=BW, pred_first=0, n=ns, ref=ts, ref_is_strong=True, slot=1),
+                         dict(kind=BW, pred_first=ns, n=nr, ref=target_weak.contiguous().float(), slot=1)]
+                if self.has_teacher:
+                    terms += [dict(kind=MS, pred_first=ns, n=nr, ref=strong_ema, weight=float(cons_w), slot=2),
+                              dict(kind=MW, pred_first=ns, n=nr, ref=weak_ema, weight=float(cons_w), slot=3)]
+                losses, d_strong, d_weak = engine.loss_terms(strong, weak, terms, 4)
+            elif self.has_teacher:
+                losses, d_strong, d_weak = engine.mt_loss(strong, weak, 0, ns, ts, ns, nr, strong_ema, weak_ema, cons_w)
+            else:
+                losses, d_strong, d_weak = engine.mt_loss(strong, weak, 0, ns, ts, 0, 0, None, None, 0.0)
+            self.plan.predictor_backward(pp, self.enc[:nst], logits, strong, weak, d_strong, d_weak,
+                                         self.grads[self.n_crnn:], accumulate=False, d_enc=self.d_enc[:nst])
+            self.plan.backward(0b011, self.d_enc, self.grads[:self.n_crnn], accumulate=False)
+            ema = self.ema_params if self.has_teacher else None
+            opt_step = self.opt_step + 1
+            if self.dp is not None:    # all-reduce over peer memory + Adam / SGD + EMA in one kernel
+                self.dp.opt_ema_step(self.m, self.v, step=opt_step, ema_step=global_step + 1, kind=self.opt_kind, lr=self.lr,
+                                     betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, momentum=self.momentum,
+                                     count=not device_state)
+            else:
+                grad_scale = shard.allreduce_gradients(self.grads, self.pg)   # NCCL sum over NVLink; 1/N folded below
+                engine.opt_ema_step(self.params, self.grads, self.m, self.v, ema, step=opt_step, ema_step=global_step + 1,
+                                    kind=self.opt_kind, lr=self.lr, betas=self.betas, eps=self.eps,
+                                    weight_decay=self.weight_decay, momentum=self.momentum, grad_scale=grad_scale)
+            if self.has_teacher and self.ema_flavour == "state_dict":
+                engine.ema_buffers(sbn, tbn, snbt, tnbt, global_step + 1)
+        finally:
+            if device_state:
+                _lib.check(lib.bsed_set_step_state(h, None), "bsed_set_step_state")
+        return dict(strong=strong, weak=weak, losses=losses)
+
+
+class FusedSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(lr, momentum, weight_decay, nesterov=True)-compatible front of the fused SGD-Nesterov(+EMA) kernel
+    (csrc/head.cu: opt_ema_kernel), the optimiser of the adaptation scripts
+    (src/main_scmt_ada_weak_seperate.py:858-870: optim, optim_crnn, optim_d)."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0, nesterov=True, dampening=0):
+        if not nesterov or dampening != 0:
+            raise NotImplementedError("the fused kernel implements SGD with Nesterov momentum and no dampening")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=True, dampening=0))
+        self._trainer = None
+
+    def step(self, closure=None):
+        raise RuntimeError("FusedSGD is driven by AdaptationTrainer.step / train_mt")
+
+
+class AdaptationTrainer(MeanTeacherTrainer):
+    """One fused iteration of the SCMT + adversarial-domain-adaptation loop (BASELINE.json configs[2];
+    src/main_scmt_ada_weak_seperate.py:train_mt with a discriminator):
+
+      1. adversarial update (:314-335): student forward of the synthetic and the real batch (two model calls) ->
+         gradient reversal (src/DA/grl.py) -> Clip_Discriminator -> BCE against the domain labels (src/DA/cdan_frame.py)
+         -> backward through D and, reversed, through the encoder -> optimizer_crnn.step(), optimizer_d.step()
+      2. the mean-teacher update (:337-521): the three model calls, strong / weak BCE on the synthetic batch, weak BCE
+         of the real batch against its weak labels, MSE consistency with the teacher -> optimizer.step() -> EMA
+    with all three optimisers SGD-Nesterov (:858-870).  Everything runs in libbsed.so kernels over flat buffers; under
+    data parallelism the three gradient exchanges (encoder + predictor, encoder-adversarial, discriminator) each go
+    through the fused peer-memory reduce + update kernel (utilities/shard.py)."""
+
+    def __init__(self, model, predictor, ema_model, ema_predictor, domain_loss, lr=cfg.default_learning_rate, lr_adv=None,
+                 momentum=0.9, weight_decay=1e-4, n_syn=cfg.batch_size, n_real=cfg.batch_size, dropout_seed=2023,
+                 process_group=None, precision=None):
+        super().__init__(model, predictor, ema_model, ema_predictor, lr=lr, weight_decay=weight_decay, n_syn=n_syn,
+                         n_real=n_real, dropout_seed=dropout_seed, process_group=process_group, precision=precision,
+                         opt_kind="sgd", momentum=momentum)
+        self.domain_loss = domain_loss                      # DA.cdan_frame.ConditionalDomainAdversarialLoss
+        self.disc = domain_loss.domain_discriminator
+        self.lr_adv = lr if lr_adv is None else lr_adv
+        dev = self.device
+        d_flat, _, _ = self.disc.flat_tensors()
+        if d_flat.device != dev:
+            raise RuntimeError("move the discriminator to the trainer's device before building the trainer")
+        self.grads_adv = torch.zeros(self.n_crnn, dtype=torch.float32, device=dev)
+        self.m_adv = torch.zeros(self.n_crnn, dtype=torch.float32, device=dev)
+        self.grads_d = torch.zeros_like(d_flat)
+        self.m_d = torch.zeros_like(d_flat)
+        self.adv_step = 0
+        nst = n_syn + n_real
+        self.dx = torch.empty(nst, self.plan.t_out, 256, dtype=torch.float32, device=dev)
+        self.prob = torch.empty(nst, dtype=torch.float32, device=dev)
+        self.d_prob = torch.empty(nst, dtype=torch.float32, device=dev)
+        self.dom_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.dp_adv = self.dp_d = None
+        if self.dp is not None:
+            self.dp_adv = shard.FusedDataParallel.create(self.grads_adv, self.params[:self.n_crnn], None, process_group)
+            self.dp_d = shard.FusedDataParallel.create(self.grads_d, d_flat, None, process_group)
+
+    def adversarial_update(self, x, xs, global_step):
+        """src/main_scmt_ada_weak_seperate.py:314-335.  Returns the domain loss (device scalar, no host sync)."""
+        from . import _lib
+        from ._lib import check, ptr, stream_ptr
+        lib, h = _lib.load(), _lib.handle(self.device.index)
+        ns, nr = int(xs.shape[0]), int(x.shape[0])
+        nst = ns + nr
+        self.x[:ns].copy_(xs.reshape(ns, 1, cfg.max_frames, cfg.n_mels))
+        self.x[ns:nst].copy_(x.reshape(nr, 1, cfg.max_frames, cfg.n_mels))
+        sp, sbn, snbt = self.model.flat_tensors()
+        S = lambda k: dict(params=sp, bn=sbn, nbt=snbt, n=k)
+        enc = self.enc[:nst]
+        self.plan.forward([S(ns), S(nr)], self.x[:nst], train=True, save=True, seed=self.dropout_seed, step=2 * global_step + 1,
+                          enc=enc)
+        grl = self.domain_loss.grl
+        coeff = grl.coeff()
+        if grl.auto_step:
+            grl.step()
+        d = self.disc
+        if not d.training:
+            raise RuntimeError("the adversarial update needs the discriminator in train() mode (batch statistics)")
+        d_flat, d_bn, d_nbt = d.flat_tensors()
+        ws, wsb = d._workspace(nst)
+        check(lib.bsed_disc_set_precision(h, _lib.PRECISIONS[(d.precision or "fp32").lower()]), "bsed_disc_set_precision")
+        prob, d_prob = self.prob[:nst], self.d_prob[:nst]
+        check(lib.bsed_disc_forward(h, ptr(d_flat), ptr(d_bn), ptr(d_nbt), ptr(enc), nst, 1, ptr(prob), ptr(ws), wsb, stream_ptr()),
+              "bsed_disc_forward")
+        key = (ns, nr)
+        if getattr(self, "_labels_key", None) != key:
+            self._labels = torch.cat((torch.ones(ns, device=self.device), torch.zeros(nr, device=self.device)))
+            self._labels_key = key
+        check(lib.bsed_disc_bce(h, ptr(prob), ptr(self._labels), nst, ptr(self.dom_loss), ptr(d_prob), stream_ptr()), "bsed_disc_bce")
+        dx = self.dx[:nst]
+        check(lib.bsed_disc_backward(h, ptr(d_flat), ptr(prob), ptr(d_prob), nst, ptr(self.grads_d), 0, ptr(dx), ptr(ws), wsb,
+                                     stream_ptr()), "bsed_disc_backward")
+        # gradient reversal: -coeff * grad (src/DA/grl.py:28-31)
+        check(lib.bsed_scale_f32(h, ptr(self.d_enc[:nst]), ptr(dx), dx.numel(), -float(coeff), stream_ptr()), "bsed_scale_f32")
+        self.plan.backward(0b011, self.d_enc, self.grads_adv, accumulate=False)
+        self.adv_step += 1
+        sgd = dict(kind="sgd", lr=self.lr_adv, weight_decay=self.weight_decay, momentum=self.momentum)
+        if self.dp_adv is not None:
+            self.dp_adv.opt_ema_step(self.m_adv, None, step=self.adv_step, ema_step=self.adv_step, **sgd)
+            self.dp_d.opt_ema_step(self.m_d, None, step=self.adv_step, ema_step=self.adv_step, **sgd)
         else:
-            losses, d_strong, d_weak = engine.mt_loss(strong, weak, 0, ns, ts.contiguous().float(), 0, 0, None, None, 0.0)
-        self.plan.predictor_backward(pp, self.enc[:nst], logits, strong, weak, d_strong, d_weak,
-                                     self.grads[self.n_crnn:], accumulate=False, d_enc=self.d_enc[:nst])
-        self.plan.backward(0b011, self.d_enc, self.grads[:self.n_crnn], accumulate=False)
-        self.opt_step += 1
-        ema = self.ema_params if self.has_teacher else None
-        if self.dp is not None:    # all-reduce over peer memory + Adam + EMA in one kernel
-            self.dp.opt_ema_step(self.m, self.v, step=self.opt_step, ema_step=global_step + 1, kind="adam", lr=self.lr,
-                                 betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
-        else:
-            grad_scale = shard.allreduce_gradients(self.grads, self.pg)   # NCCL sum over NVLink; 1/N folded below
-            engine.opt_ema_step(self.params, self.grads, self.m, self.v, ema, step=self.opt_step, ema_step=global_step + 1,
-                                kind="adam", lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay,
-                                grad_scale=grad_scale)
-        if self.has_teacher and self.ema_flavour == "state_dict":
-            engine.ema_buffers(sbn, tbn, snbt, tnbt, global_step + 1)
-        self.last = dict(strong=strong, weak=weak, losses=losses)
-        return losses
+            scale = shard.allreduce_gradients(self.grads_adv, self.pg)
+            shard.allreduce_gradients(self.grads_d, self.pg)
+            engine.opt_ema_step(self.params[:self.n_crnn], self.grads_adv, self.m_adv, None, None, step=self.adv_step,
+                                grad_scale=scale, **sgd)
+            engine.opt_ema_step(d_flat, self.grads_d, self.m_d, None, None, step=self.adv_step, grad_scale=scale, **sgd)
+        return self.dom_loss
+
+    def step(self, x, x_ema, target_weak, xs, ts, global_step, rampup_length, max_consistency_cost=cfg.max_consistency_cost):
+        """Returns (the 4 loss terms of the mean-teacher update [strong, weak, cons_strong, cons_weak], domain loss), device
+        tensors, no host sync."""
+        dom = self.adversarial_update(x, xs, global_step)
+        losses = super().step(x, x_ema, xs, ts, global_step, rampup_length, max_consistency_cost, target_weak=target_weak,
+                              dropout_step=2 * global_step)
+        return losses, dom
+
+    def check_health(self):
+        for d in (self.dp, self.dp_adv, self.dp_d):
+            if d is not None:
+                d.check()
 
 
 ISP_SLOTS = ("strong_class", "weak_class", "cons_strong", "cons_weak", "weak_freq_shift_class", "strong_shift_class",
@@ -541,6 +773,23 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
         x_ema = ema_batch_input.to(dev, non_blocking=True)
         xs = syn_batch_input.to(dev, non_blocking=True)
         ts = syn_target.to(dev, non_blocking=True)
+        fused_ada = (discriminator is not None and isinstance(optimizer, FusedSGD) and isinstance(optimizer_d, FusedSGD)
+                     and isinstance(optimizer_crnn, FusedSGD) and not ISP)
+        if fused_ada:
+            # the whole iteration of src/main_scmt_ada_weak_seperate.py (adversarial update + mean-teacher update with the
+            # weak labels of the real batch) in libbsed.so kernels
+            tr = optimizer._trainer
+            if tr is None:
+                g, ga = optimizer.param_groups[0], optimizer_crnn.param_groups[0]
+                tr = AdaptationTrainer(model, predictor, ema_model, ema_predictor, discriminator, lr=g['lr'], lr_adv=ga['lr'],
+                                       momentum=g['momentum'], weight_decay=g['weight_decay'], n_syn=xs.shape[0],
+                                       n_real=x.shape[0], dropout_seed=_dropout_state["seed"])
+                optimizer._trainer = optimizer_d._trainer = optimizer_crnn._trainer = tr
+            tr.lr, tr.lr_adv = optimizer.param_groups[0]['lr'], optimizer_crnn.param_groups[0]['lr']
+            tgt = target.to(dev, non_blocking=True).float()
+            target_weak = tgt if tgt.dim() == 2 else tgt.max(-2)[0]
+            losses, domain_loss = tr.step(x, x_ema, target_weak, xs, ts, global_step, rampup_len)
+            continue
         if discriminator is not None:
             domain_loss = adversarial_step(model, predictor, discriminator, optimizer_crnn, optimizer_d, x, xs)
         if ISP:
@@ -580,7 +829,7 @@ def train_mt(train_loader, syn_loader, model, optimizer, c_epoch, ema_model=None
             losses = _generic_step(model, predictor, ema_model, ema_predictor, optimizer, (x, x_ema, target_d),
                                    (xs, None, ts), global_step, rampup_value)
     loss = losses.sum() if losses is not None else None
-    if fused and optimizer._trainer is not None:
+    if getattr(optimizer, "_trainer", None) is not None:
         optimizer._trainer.check_health()
     if losses is not None:
         lv = losses.tolist()   # the only host sync of the epoch

@@ -149,9 +149,18 @@ class FusedDataParallel:
             torch.cuda.synchronize(grads.device)
         return obj if int(flag.item()) == 1 else None
 
+    def note_graph_step(self):
+        """One iteration ran from a captured graph (the kernel took its epoch from the device step state): keep the
+        host's epoch and the health poll in step."""
+        self.epoch += 1
+        if self.epoch % self.check_every == 0:
+            self._poll()
+
     def opt_ema_step(self, m, v, step, ema_step, kind="adam", lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                     momentum=0.9, ema_alpha=0.999):
-        """Updates self.params / self.ema (every rank ends with identical buffers); m, v: this rank's optimiser state."""
+                     momentum=0.9, ema_alpha=0.999, count=True):
+        """Updates self.params / self.ema (every rank ends with identical buffers); m, v: this rank's optimiser state.
+        count=False: the call is being recorded for / run under the device step state, which carries the epoch; the
+        host's copy is advanced by note_graph_step."""
         from .._lib import OptCfg, check, ptr, stream_ptr
         cfg = OptCfg()
         cfg.kind = 0 if kind == "adam" else 1
@@ -159,12 +168,14 @@ class FusedDataParallel:
         cfg.weight_decay, cfg.momentum, cfg.ema_alpha = float(weight_decay), float(momentum), float(ema_alpha)
         cfg.grad_scale = 1.0 / self.world
         cfg.step, cfg.ema_step = int(step), int(ema_step)
-        self.epoch += 1
+        epoch = self.epoch + 1
+        if count:
+            self.epoch = epoch
         check(self.lib.bsed_dp_opt_ema_step(self.h, self.rank, self.world, self.peer_grads, self.peer_params,
-                                            self.peer_ema if self.ema is not None else None, self.peer_flags, self.epoch,
+                                            self.peer_ema if self.ema is not None else None, self.peer_flags, epoch,
                                             ptr(m), ptr(v), self.params.numel(), C.byref(cfg), stream_ptr()),
               "bsed_dp_opt_ema_step")
-        if self.epoch % self.check_every == 0:
+        if count and self.epoch % self.check_every == 0:
             self._poll()
 
     def owned_slice(self):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BSED_ABI_VERSION 3
+#define BSED_ABI_VERSION 4
 
 #define BSED_OK 0
 #define BSED_E_INVALID (-1) /* bad argument / shape / alignment */
@@ -294,8 +294,10 @@ int bsed_opt_ema_step(bsed_handle h, float* params, const float* grads, float* m
  * waits until every peer's gradients are complete, sums the slice in rank order straight out of peer memory, applies
  * bsed_opt_ema_step's update with cfg->grad_scale (1 / world) to its own copy, stores the new parameter / EMA values
  * into every peer's buffers, and leaves only when every peer has done the same (all replicas bit-identical; m and v are
- * only touched inside the owner's slice).  world <= 8.  A peer that never arrives raises flag[33] after ~4 s instead
- * of hanging.  Buffers must come from cudaMalloc-backed allocations (the default torch allocator).
+ * only touched inside the owner's slice).  world <= 8.  A peer that does not arrive within BSED_DP_TIMEOUT_S (default
+ * 60 s) is fatal for the run: the rank raises the sticky flag[33], applies nothing further and never signals depart
+ * (its peers time out as well); hosts must poll flag[33].  Buffers must come from cudaMalloc-backed allocations (the
+ * default torch allocator).
  * ------------------------------------------------------------------------------------------ */
 #define BSED_IPC_HANDLE_BYTES 64
 int bsed_ipc_export(bsed_handle h, const void* dev_ptr, unsigned char* handle, uint64_t* offset);
@@ -304,6 +306,46 @@ int bsed_ipc_close(bsed_handle h, void* mapped, uint64_t offset);
 int bsed_dp_opt_ema_step(bsed_handle h, int rank, int world, const float* const* peer_grads,
                          float* const* peer_params, float* const* peer_ema, int32_t* const* peer_flags,
                          int64_t epoch, float* m, float* v, int64_t n, const bsed_opt_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident step state: what makes one training iteration CUDA-graph capturable.
+ * Everything that changes from one iteration to the next on the host side of the reference loop -- the dropout draw,
+ * the Adam bias corrections (src/main.py:823-828 torch.optim.Adam), the EMA coefficient min(1 - 1/(step+1), alpha)
+ * (src/main.py:86-100), the consistency weight max_consistency_cost * exp_rampup(step) (src/main.py:474-477,
+ * src/utilities/ramps.py:11-18), the epoch of the data-parallel exchange -- lives in one small device struct.
+ * bsed_step_state_advance enqueues a one-thread kernel that increments the counters and recomputes the derived
+ * scalars (double precision, the host formulas); while a state is installed with bsed_set_step_state, the
+ * step-dependent entry points ignore their by-value step arguments and read the struct instead:
+ *   bsed_crnn_forward (dropout_seed / dropout_step -> keys[]), bsed_mt_loss (cons_w), bsed_opt_ema_step and
+ *   bsed_dp_opt_ema_step (cfg->step, cfg->ema_step, cfg->lr, epoch), bsed_ema_buffers (ema_step).
+ * A captured graph of [advance, forward, loss, backward, optimiser + EMA] can then be replayed unchanged.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t global_step;   /* index of the current iteration (dropout draw, rampup); the host presets start - 1 */
+  int64_t opt_step;      /* optimiser updates applied so far, counting the current one (Adam's t)          */
+  int64_t dp_epoch;      /* bsed_dp_opt_ema_step epoch of the current iteration                             */
+  uint32_t keys[16];     /* dropout keys of the current iteration, one per stream (oracle/crnn.py: mix_key)  */
+  float lr;              /* learning rate: written by the HOST whenever the schedule changes it              */
+  float cons_w;          /* consistency weight of the current iteration                                      */
+  float step_size;       /* lr / (1 - beta1^t)                                                               */
+  float bc2_sqrt;        /* sqrt(1 - beta2^t)                                                                */
+  float ema_a, ema_b;    /* EMA coefficient of this iteration and (float)(1 - a)                             */
+  int32_t first_step;    /* SGD: the momentum buffer starts as the gradient                                  */
+  int32_t pad;
+} bsed_step_state;
+
+typedef struct {
+  uint64_t dropout_seed;
+  int64_t key_mul, key_add;     /* dropout step of iteration g = key_mul * g + key_add (1, 0 for src/main.py)   */
+  float beta1, beta2;           /* Adam                                                                          */
+  float ema_alpha;              /* 0.999                                                                         */
+  float max_consistency_cost;   /* src/data/config.py:84                                                         */
+  int64_t rampup_length;        /* n_epoch_rampup * len(loader); 0 = weight 1                                    */
+} bsed_step_cfg;
+
+int bsed_step_state_advance(bsed_handle h, bsed_step_state* state, const bsed_step_cfg* cfg, void* stream);
+/* Install (device pointer) or remove (NULL) the step state the entry points above read.  Per handle, not per stream. */
+int bsed_set_step_state(bsed_handle h, const bsed_step_state* state);
 
 /* State-dict flavour of update_ema_variables for the non-parameter entries: BN running stats
  * (fp32) and num_batches_tracked (int64, blended in fp32 and truncated, as load_state_dict does). */
@@ -322,6 +364,9 @@ int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffe
  * the gradient handed to the gradient-reversal layer.  bsed_disc_bce: mean BCE against the domain labels + gradient.
  * ------------------------------------------------------------------------------------------ */
 int bsed_disc_set_precision(bsed_handle h, int precision);   /* BSED_PRECISION_FP32 (default) | BSED_PRECISION_TF32 */
+/* dst = alpha * src (n floats; dst may alias src).  The gradient-reversal layer's backward, -coeff * grad
+ * (src/DA/grl.py:19-31), between bsed_disc_backward and bsed_crnn_backward. */
+int bsed_scale_f32(bsed_handle h, float* dst, const float* src, int64_t n, float alpha, void* stream);
 int64_t bsed_disc_param_count(void);
 int64_t bsed_disc_bn_buffer_count(void);
 size_t bsed_disc_workspace_bytes(int B);

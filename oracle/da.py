@@ -57,7 +57,7 @@ def cdan_clip_loss(disc, f_s, f_t, iter_num):
     """BCE(D(GRL(cat(f_s, f_t))), [1]*B_s + [0]*B_t), GRL coefficient of iteration `iter_num`."""
     f = torch.cat((f_s, f_t), dim=0)
     d = torch.squeeze(disc(_GRL.apply(f, grl_coeff(iter_num))))
-    label = torch.cat((torch.ones(f_s.size(0)), torch.zeros(f_t.size(0))))
+    label = torch.cat((torch.ones(f_s.size(0), device=f.device), torch.zeros(f_t.size(0), device=f.device)))
     return F.binary_cross_entropy(d, label), d
 
 

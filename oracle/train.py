@@ -210,3 +210,60 @@ def isp_step(model, predictor, ema_model, ema_predictor, optimizer, x, x_ema, ta
     outs = dict(strong=strong.detach(), weak=weak.detach(), syn_strong=syn_strong.detach(),
                 strong_shift=strong_shift.detach(), syn_strong_fshift=syn_strong_fshift.detach(), grads=grads)
     return loss.detach(), {k: v.detach() for k, v in parts.items()}, outs
+
+
+def ada_step(model, predictor, ema_model, ema_predictor, disc, optimizer, optimizer_crnn, optimizer_d, x, x_ema,
+             target_weak, xs, ts, global_step, rampup_length, grl_iter, max_consistency_cost=1.0, dropout_hook=None):
+    """One iteration of src/main_scmt_ada_weak_seperate.py:train_mt with a discriminator (no ISP):
+      :314-335  adversarial update -- student forward of the synthetic and the real batch, ConditionalDomainAdversarialLoss
+                (oracle/da.py: cdan_clip_loss, GRL coefficient of iteration `grl_iter`), backward, optimizer_crnn.step(),
+                optimizer_d.step()
+      :337-521  mean-teacher update -- strong / weak BCE on the synthetic batch, weak BCE of the real batch against
+                `target_weak` (:437-445), MSE consistency with the teacher, optimizer.step(), EMA (parameters + buffers)
+    `dropout_hook(tag)` with tag in {'adv_syn', 'adv_real', 'teacher', 'syn', 'real'} keys the hash-dropout masks.
+    Returns (loss, parts incl. 'domain', outputs)."""
+    from oracle import da as oda
+    hook = dropout_hook or (lambda tag: None)
+    rampup = exp_rampup(global_step, rampup_length)
+
+    hook("adv_syn")
+    _, syn_d_input = model(xs)
+    hook("adv_real")
+    _, d_input = model(x)
+    optimizer_crnn.zero_grad()
+    optimizer_d.zero_grad()
+    domain_loss, _ = oda.cdan_clip_loss(disc, syn_d_input, d_input, grl_iter)
+    domain_loss.backward()
+    adv_grads = {"crnn." + n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    d_grads = {n: p.grad.detach().clone() for n, p in disc.named_parameters()}
+    optimizer_crnn.step()
+    optimizer_d.step()
+
+    hook("teacher")
+    enc_ema, _ = ema_model(x_ema)
+    strong_ema, weak_ema = ema_predictor(enc_ema)
+    strong_ema, weak_ema = strong_ema.detach(), weak_ema.detach()
+    optimizer.zero_grad()
+    hook("syn")
+    syn_strong, syn_weak = predictor(model(xs)[0])
+    hook("real")
+    strong, weak = predictor(model(x)[0])
+    bce, mse = nn.BCELoss(), nn.MSELoss()
+    weak_class = bce(syn_weak, ts.max(-2)[0]) + bce(weak, target_weak)
+    strong_class = bce(syn_strong, ts)
+    cc = max_consistency_cost * rampup
+    cons_strong, cons_weak = cc * mse(strong, strong_ema), cc * mse(weak, weak_ema)
+    loss = strong_class + weak_class + (cons_weak + cons_strong)
+    loss.backward()
+    grads = {}
+    for prefix, mod in (("crnn.", model), ("pred.", predictor)):
+        for n, p in mod.named_parameters():
+            grads[prefix + n] = p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)
+    optimizer.step()
+    update_ema_state_dict(model, ema_model, 0.999, global_step + 1)
+    update_ema_state_dict(predictor, ema_predictor, 0.999, global_step + 1)
+    parts = dict(strong_class=strong_class, weak_class=weak_class, cons_strong=cons_strong, cons_weak=cons_weak,
+                 domain=domain_loss)
+    outs = dict(strong=strong.detach(), weak=weak.detach(), syn_strong=syn_strong.detach(), grads=grads, adv_grads=adv_grads,
+                d_grads=d_grads)
+    return loss.detach(), {k: v.detach() for k, v in parts.items()}, outs

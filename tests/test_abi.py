@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), f"{s} declared in include/bsed.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared, "ctypes binding list and header disagree"
-    assert _lib.load().bsed_version() == 3
+    assert _lib.load().bsed_version() == 4
 
 
 def test_no_torch_types_in_signatures():
