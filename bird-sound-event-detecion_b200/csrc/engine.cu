@@ -760,10 +760,10 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         const float* Xr = X + (size_t)runs[r].first * T * In;
         float* xgr = xg + (size_t)runs[r].first * T * 768;
         if (tc) {
-          for (int n0 = 0; n0 < 768; n0 += 128)   // B operand = [W_ih ; W_ih_reverse] rows n0.., K-major as stored
-            BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l] + (size_t)n0 * In,
-                                LO(packed + p->pk.wih_cat[s][l] + (size_t)n0 * In), In, xgr + n0, 768,
-                                (long long)runs[r].count * T, 128, In, packed + p->pk.bih[s][l] + n0, 0, sms, ss));
+          // B operand = [W_ih ; W_ih_reverse], K-major as stored; the six 128-column blocks of the 768 gate
+          // pre-activations in one launch
+          BSED_TRY(tc_gemm_nt(Xr, In, packed + p->pk.wih_cat[s][l], LO(packed + p->pk.wih_cat[s][l]), In, xgr, 768,
+                              (long long)runs[r].count * T, 768, In, packed + p->pk.bih[s][l], 0, sms, ss));
         } else {
           BSED_TRY(gemm_nn(Xr, In, packed + p->pk.wihT[s][l], 768, xgr, 768, runs[r].count * T, 768, In,
                            packed + p->pk.bih[s][l], 0, ss));
@@ -921,10 +921,8 @@ extern "C" int bsed_crnn_forward(bsed_plan p, const bsed_group* groups, int n_gr
         const float* A = cat + (size_t)runs[r].first * Ta * 512;
         float* Y = outs[j] + (size_t)runs[r].first * Ta * 256;
         const long long M = (long long)runs[r].count * Ta;
-        if (tc) {
-          for (int n0 = 0; n0 < 256; n0 += 128)   // B operand rows = output channels n0.., K-major as the reference stores them
-            BSED_TRY(tc_gemm_nt(A, 512, packed + p->pk.m_w[j] + (size_t)n0 * 512, LO(packed + p->pk.m_w[j] + (size_t)n0 * 512), 512,
-                                Y + n0, 256, M, 128, 512, bias + n0, 0, sms, st));
+        if (tc) {   // B operand rows = output channels, K-major as the reference stores them
+          BSED_TRY(tc_gemm_nt(A, 512, packed + p->pk.m_w[j], LO(packed + p->pk.m_w[j]), 512, Y, 256, M, 256, 512, bias, 0, sms, st));
         } else {
           BSED_TRY(gemm_nn(A, 512, packed + p->pk.m_wT[j], 256, Y, 256, (int)M, 256, 512, bias, 0, st));
         }
@@ -1016,9 +1014,8 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       BSED_TRY(add_double_to_float(dscr, 2, grads + pl.m_b[j], 256, st));
       // dcat = dy * W   ([M][256] x [256][512])
       if (tc) {
-        for (int n0 = 0; n0 < 512; n0 += 128)
-          BSED_TRY(tc_gemm_nt(dy, 256, packed + p->pk.m_wT[j] + (size_t)n0 * 256, LO(packed + p->pk.m_wT[j] + (size_t)n0 * 256), 256,
-                              dcat + roa * 512 + n0, 512, M, 128, 256, nullptr, 0, sms, st));
+        BSED_TRY(tc_gemm_nt(dy, 256, packed + p->pk.m_wT[j], LO(packed + p->pk.m_wT[j]), 256, dcat + roa * 512, 512, M, 512, 256,
+                            nullptr, 0, sms, st));
       } else {
         BSED_TRY(gemm_nn(dy, 256, packed + p->pk.m_w[j], 512, dcat + roa * 512, 512, (int)M, 512, 256, nullptr, 0, st));
       }
@@ -1077,11 +1074,9 @@ extern "C" int bsed_crnn_backward(bsed_plan p, uint32_t group_mask, const float*
       BSED_TRY(add_double_to_float(dsc + 2 * 384, 2, grads + pl.bhh[s][l][1], 384, ss));
       float* dX = l == 0 ? dx_target + ro * 128 : dxin + ro * 256;
       const int acc = l == 0 ? accumulate_dx : 0;
-      if (tc) {
-        for (int n0 = 0; n0 < In; n0 += 128)   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
-          BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l] + (size_t)n0 * 768,
-                              LO(packed + p->pk.wihT[s][l] + (size_t)n0 * 768), 768, dX + n0, In, BTn, 128, 768, nullptr, acc, sms,
-                              ss));
+      if (tc) {   // dX = dxg * [W_ih ; W_ih_reverse]: B operand rows = wihT [In][768]
+        BSED_TRY(tc_gemm_nt(dxg + ro * 768, 768, packed + p->pk.wihT[s][l], LO(packed + p->pk.wihT[s][l]), 768, dX, In, BTn, In,
+                            768, nullptr, acc, sms, ss));
       } else {
         BSED_TRY(gemm_nn(dxg + ro * 768, 768, packed + p->pk.wih_cat[s][l], In, dX, In, (int)BTn, In, 768, nullptr, acc, ss));
       }

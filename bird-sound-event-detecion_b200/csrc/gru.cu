@@ -6,9 +6,11 @@
 //   n = tanh  (W_in x + b_in + r * (W_hn h + b_hn))
 //   h' = (1 - z) * n + z * h                      gate order (r, z, n), h_0 = 0
 // The input projections xg = W_i* x + b_i* come from one GEMM per layer (both directions,
-// [B][T][768]); this kernel runs the 313 dependent steps.  One CTA per (clip, direction),
-// 384 threads: thread j owns row j of W_hh (128 registers) and produces gate pre-activation j;
-// the 128 hidden values are exchanged through shared memory.
+// [B][T][768]); this kernel runs the 313 dependent steps.  One CTA per (clip, direction), 384 threads, W_hh resident in
+// registers (128 per thread), the 128 hidden values exchanged through shared memory.  The recurrent dot products are
+// split four ways along k inside each quad of lanes: a thread multiplies a quarter of h (8 broadcast LDS.128 instead of
+// 32 -- the shared-memory loads were what the step stalled on) into 4 gate rows with packed FMAs, and a 3-shuffle
+// transpose-reduce leaves lane q of the quad with the complete pre-activation of row 4 * quad + q = its thread index.
 #include "launch.h"
 
 namespace bsed {
@@ -26,6 +28,33 @@ __device__ __forceinline__ int gru_group_of(const Groups& g, int clip) {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Four dot products of length 128 shared by a quad of lanes.  Lane q holds w[r][.] = rows r = 0..3 restricted to
+// k in [32 q, 32 q + 32) and reads that quarter of the vector (v4: its eight float4); returns the complete dot product of
+// row q.  Partial sums: two packed accumulators per row (even / odd k), then a transpose-reduce over the quad.
+__device__ __forceinline__ float quad_dot(const float2 (&w)[4][kH / 8], const float4* __restrict__ v4, int q) {
+  float2 a[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 hv = v4[k4];
+    const float2 lo = make_float2(hv.x, hv.y), hi = make_float2(hv.z, hv.w);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ffma2(a[r], w[r][2 * k4], lo);
+      ffma2(a[r], w[r][2 * k4 + 1], hi);
+    }
+  }
+  float p0 = a[0].x + a[0].y, p1 = a[1].x + a[1].y, p2 = a[2].x + a[2].y, p3 = a[3].x + a[3].y;
+  // lanes with q & 1 keep rows 1, 3 and hand over rows 0, 2 (and vice versa); then q & 2 splits {0, 1} from {2, 3}
+  const bool odd = q & 1;
+  const float s0 = odd ? p0 : p1, s1 = odd ? p2 : p3;
+  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  const float u0 = (odd ? p1 : p0) + r0;      // row (q & 1)
+  const float u1 = (odd ? p3 : p2) + r1;      // row 2 + (q & 1)
+  const bool up = q & 2;
+  const float r2 = __shfl_xor_sync(0xffffffffu, up ? u0 : u1, 2);
+  return (up ? u1 : u0) + r2;                 // row q
+}
+
 __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict__ xg, Groups g, FloatPtrs whhT,
                                                         FloatPtrs bhh, float* __restrict__ out,
                                                         float* __restrict__ enc, float* __restrict__ saved, int T,
@@ -36,9 +65,13 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
   const int j = threadIdx.x;
   const int grp = gru_group_of(g, clip);
   const float* WT = whhT.p[grp] + (size_t)dir * kH * kG;  // [k][j]
-  float2 w[kH / 2];   // row j of W_hh as (even, odd) pairs: the operands of the packed FMAs below
+  const int q = j & 3, row0 = j & ~3;   // k quarter of this lane, first of the quad's four gate rows
+  float2 w[4][kH / 8];                  // rows row0 .. row0 + 3, k in [32 q, 32 q + 32), as (even, odd) pairs
 #pragma unroll
-  for (int k = 0; k < kH / 2; ++k) w[k] = make_float2(WT[(size_t)(2 * k) * kG + j], WT[(size_t)(2 * k + 1) * kG + j]);
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int k = 0; k < kH / 8; ++k)
+      w[r][k] = make_float2(WT[(size_t)(32 * q + 2 * k) * kG + row0 + r], WT[(size_t)(32 * q + 2 * k + 1) * kG + row0 + r]);
   const float bj = bhh.p[grp][dir * kG + j];
 
   __shared__ __align__(16) float h_s[2][kH];   // double-buffered hidden state: two barriers per step
@@ -57,17 +90,7 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
     const size_t row = xrow(step);
     const float x = nx;
     if (step + 1 < T) nx = xg[xrow(step + 1) * (2 * kG) + dir * kG + j];
-    // four independent accumulation chains (k mod 4), two per packed FMA: the same sums, in the same order, as four
-    // scalar fmaf chains
-    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
-    const float4* h4 = reinterpret_cast<const float4*>(h_s[buf]);
-#pragma unroll
-    for (int k4 = 0; k4 < kH / 4; ++k4) {
-      const float4 hv = h4[k4];
-      ffma2(a01, w[2 * k4], make_float2(hv.x, hv.y));
-      ffma2(a23, w[2 * k4 + 1], make_float2(hv.z, hv.w));
-    }
-    const float acc = (a01.x + a01.y) + (a23.x + a23.y) + bj;
+    const float acc = quad_dot(w, reinterpret_cast<const float4*>(h_s[buf]) + 8 * q, q) + bj;
     float* sv = saved ? saved + (row * 2 + dir) * (4 * kH) : nullptr;
     if (j < 2 * kH) {
       const float sg = sigmoid_acc(x + acc);
@@ -110,8 +133,8 @@ int gru_forward(const float* xg, const Groups& g, const FloatPtrs& whhT, const F
   return BSED_OK;
 }
 
-// backward through time.  thread (i = tid % 128, gs = tid / 128) owns W_hh[gs*128 + k][i], k = 0..127
-// and produces the gs-th partial of dh_{t-1}[i] = sum_j W_hh[j][i] * dg_h[j].
+// backward through time.  thread (i = tid % 128, gs = tid / 128) produces the gs-th partial of
+// dh_{t-1}[i] = sum_j W_hh[j][i] * dg_h[j] (the quad it belongs to shares the four outputs i & ~3 .. and splits k).
 //   dxg : gradient w.r.t. the input projections  (dr_pre, dz_pre, dn_pre)
 //   dgh : gradient w.r.t. W_hh h + b_hh          (dr_pre, dz_pre, dn_pre * r)
 __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict__ dout,
@@ -124,10 +147,15 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
   const int i = threadIdx.x % kH;
   const int gs = threadIdx.x / kH;
   const float* W = whh + (size_t)dir * kG * kH;  // [j][i]
-  float2 w[kH / 2];
+  // same quad scheme as the forward kernel: the quad of this thread owns outputs i0 .. i0 + 3 of gate group gs, lane q
+  // the quarter k in [32 q, 32 q + 32) of the reduction over the group's 128 gate rows
+  const int q = threadIdx.x & 3, i0 = i & ~3;
+  float2 w[4][kH / 8];
 #pragma unroll
-  for (int k = 0; k < kH / 2; ++k)
-    w[k] = make_float2(W[(size_t)(gs * kH + 2 * k) * kH + i], W[(size_t)(gs * kH + 2 * k + 1) * kH + i]);
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int k = 0; k < kH / 8; ++k)
+      w[r][k] = make_float2(W[(size_t)(gs * kH + 32 * q + 2 * k) * kH + i0 + r], W[(size_t)(gs * kH + 32 * q + 2 * k + 1) * kH + i0 + r]);
 
   __shared__ __align__(16) float dg_s[kG];
   __shared__ float part_s[3][kH];
@@ -193,15 +221,7 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
     }
     __syncthreads();
     issue(step + kRing - 1);                    // refills the slot consumed in the previous step
-    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
-    const float4* d4 = reinterpret_cast<const float4*>(dg_s + gs * kH);
-#pragma unroll
-    for (int k4 = 0; k4 < kH / 4; ++k4) {
-      const float4 dv = d4[k4];
-      ffma2(a01, w[2 * k4], make_float2(dv.x, dv.y));
-      ffma2(a23, w[2 * k4 + 1], make_float2(dv.z, dv.w));
-    }
-    part_s[gs][i] = (a01.x + a01.y) + (a23.x + a23.y);
+    part_s[gs][i] = quad_dot(w, reinterpret_cast<const float4*>(dg_s + gs * kH) + 8 * q, q);
     cp_async_wait<kRing - 2>();                 // the group of step + 1 has landed (for this thread) ...
     __syncthreads();                            // ... and for every thread
     if (gs == 0) dh_carry = dh_z + part_s[0][i] + part_s[1][i] + part_s[2][i];

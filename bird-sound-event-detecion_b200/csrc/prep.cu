@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
 
 int run_split(const SplitTable& table, float* packed, long long lo_offset, cudaStream_t st) {
   if (table.n == 0) return BSED_OK;
-  dim3 grid(table.n, 8);
+  dim3 grid(table.n, 32);   // the big ranges (GRU / conv matrices of 10^5 floats) need more than a handful of CTAs
   split_kernel<<<grid, 256, 0, st>>>(table, packed, lo_offset);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
@@ -163,7 +163,7 @@ int split_hi_lo(float* w, float* lo, long long n, cudaStream_t st) {
 
 int run_prep(const PrepTable& table, cudaStream_t st) {
   if (table.n == 0) return BSED_OK;
-  dim3 grid(table.n, 8);
+  dim3 grid(table.n, 32);   // the big ranges (GRU / conv matrices of 10^5 floats) need more than a handful of CTAs
   prep_kernel<<<grid, 256, 0, st>>>(table);
   BSED_CHECK_LAUNCH();
   return BSED_OK;

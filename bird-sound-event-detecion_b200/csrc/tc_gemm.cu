@@ -27,6 +27,7 @@ struct KArgs {
   int ldc;
   int accumulate;
   int debug;           // BSED_TC_DEBUG (measurement experiments only): 1 = skip the epilogue's global stores
+  int n_chunks;        // plain mode: the output is n_chunks column blocks of N; tile = (row tile, column block)
   int stages;          // depth of the TMA ring (host: as many as fit the shared memory)
   int rb_bytes;        // bytes reserved for the resident weights (RB)
   // epi == 1: BatchNorm-backward epilogue (plain mode): C holds the direct gate path dxd on entry and
@@ -72,7 +73,8 @@ struct KSmem {
   static constexpr int STG2_BYTES = (!X3 && N <= 64) ? kBM * N * 4 : 0;   // gated tile of the fused GLU epilogue (epi == 2)
   static constexpr int BAR_BYTES = 512;   // 2 * stages + 5 + 2 * kLoBufs mbarriers + the TMEM slot
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
-  static constexpr int FIXED = LO_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + 512 /*bias*/ + TAB_BYTES;
+  static constexpr int BIAS_BYTES = 4096;   // up to 1024 bias values (n_chunks * N)
+  static constexpr int FIXED = LO_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES + TAB_BYTES;
   static_assert((2 * kMaxStages + 6 + 2 * kLoBufs) * 8 <= BAR_BYTES, "barrier region too small");
 };
 
@@ -123,8 +125,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     mbar_init(rbfull, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < N) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  float* stab = sbias + 128;
+  for (int i = threadIdx.x; i < N * a.n_chunks; i += NT) sbias[i] = bias ? bias[i] : 0.f;
+  float* stab = sbias + S::BIAS_BYTES / 4;
   if (a.epi == 1)
     for (int i = threadIdx.x; i < a.tab_groups * 3 * N; i += NT) stab[i] = a.tab[i];
   if (a.epi == 2)
@@ -160,10 +162,11 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             unsigned char* sa = smem + s * S::STAGE;
             unsigned char* sb = sa + S::A_BYTES;
             mbar_expect_tx(&full[s], S::A_BYTES + (RB ? 0 : S::NB * S::B_BYTES));
-            if (a.plain) tma_load_2d(&mapA, sa, &full[s], ch * KCH, tile * kBM);
+            if (a.plain) tma_load_2d(&mapA, sa, &full[s], ch * KCH, (tile / a.n_chunks) * kBM);
             else tma_load_4d(&mapA, sa, &full[s], ch * KCH, df, t0 + dt, b);
-            if (!RB) tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, 0);
-            if (!RB && X3) tma_load_2d(&mapBlo, sb + S::B_STRIDE, &full[s], (tap * a.cpt + ch) * KCH, 0);
+            const int brow = a.plain ? (tile % a.n_chunks) * N : 0;     // column block of the output = row block of B
+            if (!RB) tma_load_2d(&mapB, sb, &full[s], (tap * a.cpt + ch) * KCH, brow);
+            if (!RB && X3) tma_load_2d(&mapBlo, sb + S::B_STRIDE, &full[s], (tap * a.cpt + ch) * KCH, brow);
             if (++s == STAGES) {
               s = 0;
               ph ^= 1;
@@ -280,10 +283,12 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       long long grow;                       // global output row
       bool valid;
       int b = 0, t0 = 0, valid_rows = kBM;
+      const int mt = a.plain ? tile / a.n_chunks : tile;            // row tile
+      const int ncol0 = a.plain ? (tile % a.n_chunks) * N : 0;      // first output column of the tile
       if (a.plain) {
-        grow = (long long)tile * kBM + row;
+        grow = (long long)mt * kBM + row;
         valid = grow < a.rows;
-        if (a.rows - (long long)tile * kBM < kBM) valid_rows = (int)(a.rows - (long long)tile * kBM);
+        if (a.rows - (long long)mt * kBM < kBM) valid_rows = (int)(a.rows - (long long)mt * kBM);
       } else {
         b = tile / a.tiles_per_clip;
         t0 = (tile - b * a.tiles_per_clip) * a.th;
@@ -353,7 +358,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             o = make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
                             kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w));
           } else {
-            const float4 bv = lds128(sbias_addr + (c0 + j) * 4);
+            const float4 bv = lds128(sbias_addr + (ncol0 + c0 + j) * 4);
             o = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
           }
           sts128(sub + chunk_addr(row, j / 4), o);
@@ -382,7 +387,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += CW) {
           const void* src = stg + (c0 / CW) * (kBM * CW * 4);
-          if (a.plain) tma_store_2d(&mapC, src, c0, tile * kBM, a.accumulate != 0);
+          if (a.plain) tma_store_2d(&mapC, src, ncol0 + c0, mt * kBM, a.accumulate != 0);
           else tma_store_4d(&mapC, src, c0, 0, t0, b, a.accumulate != 0);
         }
         bulk_commit();
@@ -475,7 +480,7 @@ static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
 template <int N, int KCH, bool X3>
 static int launch_k(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC, float* Y,
                     const float* bias, KArgs& a, int sms, cudaStream_t st) {
-  const bool rb = (long long)(X3 ? 2 : 1) * a.ntaps * a.cpt * KSmem<N, KCH, true, X3>::B_STRIDE <= kRbBytes;
+  const bool rb = a.n_chunks == 1 && (long long)(X3 ? 2 : 1) * a.ntaps * a.cpt * KSmem<N, KCH, true, X3>::B_STRIDE <= kRbBytes;
   if (rb) return launch_k2<N, KCH, true, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
   return launch_k2<N, KCH, false, X3>(mA, mB, mBlo, mC, Y, bias, a, sms, st);
 }
@@ -1018,6 +1023,7 @@ int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float*
   a.F = F;
   a.rows = 0;
   a.ntaps = 9;
+  a.n_chunks = 1;
   a.cpt = Cin / KCH;
   a.ldc = Cout;
   a.accumulate = accumulate;
@@ -1054,10 +1060,15 @@ struct BnBwdEpi {
   long long rows_per_clip;
   int gfirst[kMaxGroups];
 };
+// N > 128: the output is walked in column blocks of 128 inside ONE launch (tile = (row tile, column block), the row
+// tile's A chunks re-read from L2), instead of one launch per block
 static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float* Bk_lo, int ldb, float* C, int ldc, long long M,
-                           int N, int K, const float* bias, int accumulate, const BnBwdEpi* bnb, int sms, cudaStream_t st) {
-  BSED_REQUIRE(K % 16 == 0 && N % 16 == 0 && N <= 128 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0,
-               "tc_gemm_nt: M=%lld N=%d K=%d", M, N, K);
+                           int N_total, int K, const float* bias, int accumulate, const BnBwdEpi* bnb, int sms, cudaStream_t st) {
+  const int n_chunks = N_total > 128 ? N_total / 128 : 1;
+  const int N = N_total > 128 ? 128 : N_total;
+  BSED_REQUIRE(K % 16 == 0 && N % 16 == 0 && N * n_chunks == N_total && N_total <= 1024 && lda % 4 == 0 && ldb % 4 == 0 &&
+                   ldc % 4 == 0 && (n_chunks == 1 || !bnb),
+               "tc_gemm_nt: M=%lld N=%d K=%d", M, N_total, K);
   const bool x3 = Bk_lo != nullptr;
   const int KCH = tc::pick_kch(K, N, 1, x3);
   CUtensorMap mA, mB, mBlo;
@@ -1065,20 +1076,21 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float
   cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
   cuuint32_t bA[2] = {(cuuint32_t)KCH, 128};
   BSED_TRY(tc::make_map(&mA, A, 2, dA, sA, bA, KCH * 4, x3));
-  cuuint64_t dB[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t dB[2] = {(cuuint64_t)K, (cuuint64_t)N_total};
   cuuint64_t sB[1] = {(cuuint64_t)ldb * 4};
   cuuint32_t bB[2] = {(cuuint32_t)KCH, (cuuint32_t)N};
   BSED_TRY(tc::make_map(&mB, Bk, 2, dB, sB, bB, KCH * 4, x3));
   BSED_TRY(tc::make_map(&mBlo, x3 ? Bk_lo : Bk, 2, dB, sB, bB, KCH * 4, x3));
   const int CW = N >= 32 ? 32 : 16;
   CUtensorMap mC;
-  cuuint64_t dC[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t dC[2] = {(cuuint64_t)N_total, (cuuint64_t)M};
   cuuint64_t sC[1] = {(cuuint64_t)ldc * 4};
   cuuint32_t bC[2] = {(cuuint32_t)CW, 128};
   BSED_TRY(tc::make_map(&mC, C, 2, dC, sC, bC, CW * 4, true));
   tc::KArgs a;
   a.plain = 1;
-  a.n_tiles = (int)((M + 127) / 128);
+  a.n_chunks = n_chunks;
+  a.n_tiles = (int)((M + 127) / 128) * n_chunks;
   a.tiles_per_clip = 1;
   a.th = 1;
   a.T = 1;
@@ -1103,7 +1115,7 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float
   a.store_lin = 1;
   a.drop_key = a.drop_thresh = a.drop_base = 0;
   a.inv_keep = 1.f;
-  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)K * N + (double)M * N), st);
+  ProfScope prof(PROF_GEMM, 2.0 * M * N_total * K, 4.0 * ((double)M * K + (double)K * N_total + (double)M * N_total), st);
   return tc::dispatch_k(KCH, x3, N, mA, mB, mBlo, mC, C, bias, a, sms, st);
 }
 
@@ -1141,6 +1153,7 @@ int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const
   a.F = Fp;
   a.rows = 0;
   a.ntaps = 1;
+  a.n_chunks = 1;
   a.cpt = CP / 32;
   a.ldc = CP;
   a.accumulate = 0;

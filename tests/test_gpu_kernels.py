@@ -173,7 +173,9 @@ def test_conv3x3_tensor_cores(B, T, Fq, Cin, Cout):
 @pytest.mark.parametrize("M,K,N,bias,acc", [(1000, 128, 128, False, False), (300, 16, 16, True, False),
                                             (777, 256, 64, True, False), (513, 768, 128, False, True),
                                             (129, 64, 64, True, True), (5, 32, 32, False, False),
-                                            (40000, 32, 32, True, False)])
+                                            (40000, 32, 32, True, False),
+                                            # N > 128: column blocks of 128 inside one launch
+                                            (2000, 256, 768, True, False), (900, 768, 256, False, True)])
 def test_gemm_nt_tensor_cores(M, K, N, bias, acc):
     from bsed_b200 import engine
     a, bk = _rand(M, K, seed=1), _rand(N, K, seed=2)

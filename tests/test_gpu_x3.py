@@ -50,7 +50,9 @@ def test_default_precision_is_3xtf32():
     (40000, 64, 64, True, False),        # 32-wide chunks, resident (hi, lo) weights (GLU of the packed 16/32/64-channel blocks)
     (300, 16, 16, True, False), (777, 256, 64, True, False), (513, 768, 128, False, True),     # GRU data gradient shape
     (129, 64, 64, True, True), (5, 32, 32, False, False), (11268, 256, 128, True, False),      # GRU layer-1 projection
-    (3000, 512, 128, True, False)])      # fpn merge
+    (3000, 512, 128, True, False),       # fpn merge
+    # N > 128: column blocks of 128 inside one launch (GRU projections 768, fpn merge 256, their data gradients)
+    (11268, 128, 768, True, False), (1000, 768, 256, False, True), (700, 256, 512, True, False)])
 def test_gemm_nt_3xtf32(M, K, N, bias, acc):
     from bsed_b200 import engine
     a, bk = _rand(M, K, seed=1), _rand(N, K, seed=2)
