@@ -28,6 +28,10 @@ __device__ __forceinline__ int gru_group_of(const Groups& g, int clip) {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// shared-memory position of element k of a 128-vector read by quad_dot: quarter k / 32 starts at float 36 * (k / 32)
+constexpr int kQuadVec = 4 * 36;
+__device__ __forceinline__ int quad_pos(int k) { return (k >> 5) * 36 + (k & 31); }
+
 // Four dot products of length 128 shared by a quad of lanes.  Lane q holds w[r][.] = rows r = 0..3 restricted to
 // k in [32 q, 32 q + 32) and reads that quarter of the vector (v4: its eight float4); returns the complete dot product of
 // row q.  Partial sums: two packed accumulators per row (even / odd k), then a transpose-reduce over the quad.
@@ -74,9 +78,11 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
       w[r][k] = make_float2(WT[(size_t)(32 * q + 2 * k) * kG + row0 + r], WT[(size_t)(32 * q + 2 * k + 1) * kG + row0 + r]);
   const float bj = bhh.p[grp][dir * kG + j];
 
-  __shared__ __align__(16) float h_s[2][kH];   // double-buffered hidden state: two barriers per step
+  // double-buffered hidden state (two barriers per step), stored as four quarters of 32 values 36 floats apart: the four
+  // lanes of a quad read four different quarters in one LDS.128, and a 32-float stride would put them on the same banks
+  __shared__ __align__(16) float h_s[2][kQuadVec];
   __shared__ float gates_s[kG];                // r, z (after the sigmoid) and W_hn h + b_hn
-  if (j < kH) h_s[0][j] = 0.f;
+  if (j < kH) h_s[0][quad_pos(j)] = 0.f;
   __syncthreads();
 
   // Thread j owns gate row j end to end: its input projection x_j (fetched one step ahead, so the load latency is
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
     const size_t row = xrow(step);
     const float x = nx;
     if (step + 1 < T) nx = xg[xrow(step + 1) * (2 * kG) + dir * kG + j];
-    const float acc = quad_dot(w, reinterpret_cast<const float4*>(h_s[buf]) + 8 * q, q) + bj;
+    const float acc = quad_dot(w, reinterpret_cast<const float4*>(h_s[buf]) + 9 * q, q) + bj;
     float* sv = saved ? saved + (row * 2 + dir) * (4 * kH) : nullptr;
     if (j < 2 * kH) {
       const float sg = sigmoid_acc(x + acc);
@@ -101,9 +107,9 @@ __global__ void __launch_bounds__(kG, 1) gru_fwd_kernel(const float* __restrict_
     if (j >= 2 * kH) {
       const float r = gates_s[u], z = gates_s[kH + u];
       const float n = tanhf(fmaf(r, acc, x));
-      const float hold = h_s[buf][u];
+      const float hold = h_s[buf][quad_pos(u)];
       const float hnew = (1.f - z) * n + z * hold;
-      h_s[buf ^ 1][u] = hnew;
+      h_s[buf ^ 1][quad_pos(u)] = hnew;
       size_t o = row * (2 * kH) + dir * kH + u;
       out[o] = hnew;
       if (enc) {
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
     for (int k = 0; k < kH / 8; ++k)
       w[r][k] = make_float2(W[(size_t)(gs * kH + 32 * q + 2 * k) * kH + i0 + r], W[(size_t)(gs * kH + 32 * q + 2 * k + 1) * kH + i0 + r]);
 
-  __shared__ __align__(16) float dg_s[kG];
+  __shared__ __align__(16) float dg_s[3][kQuadVec];   // per gate group, in quad_dot's padded layout
   __shared__ float part_s[3][kH];
   // operands of the coming steps (r, z, n, W_hn h + b_hn, d_out, h_prev: 6 x 128 floats = 192 16-byte chunks per
   // step) are staged through shared memory kRing - 1 steps ahead with cp.async: the DRAM latency of these cold
@@ -214,14 +220,14 @@ __global__ void __launch_bounds__(kG, 1) gru_bwd_kernel(const float* __restrict_
       gh[i] = drp;
       gh[kH + i] = dzp;
       gh[2 * kH + i] = dhn;
-      dg_s[i] = drp;
-      dg_s[kH + i] = dzp;
-      dg_s[2 * kH + i] = dhn;
+      dg_s[0][quad_pos(i)] = drp;
+      dg_s[1][quad_pos(i)] = dzp;
+      dg_s[2][quad_pos(i)] = dhn;
       dh_z = dh * z;
     }
     __syncthreads();
     issue(step + kRing - 1);                    // refills the slot consumed in the previous step
-    part_s[gs][i] = quad_dot(w, reinterpret_cast<const float4*>(dg_s + gs * kH) + 8 * q, q);
+    part_s[gs][i] = quad_dot(w, reinterpret_cast<const float4*>(dg_s[gs]) + 9 * q, q);
     cp_async_wait<kRing - 2>();                 // the group of step + 1 has landed (for this thread) ...
     __syncthreads();                            // ... and for every thread
     if (gs == 0) dh_carry = dh_z + part_s[0][i] + part_s[1][i] + part_s[2][i];

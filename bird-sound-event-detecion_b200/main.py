@@ -332,7 +332,8 @@ class MeanTeacherTrainer(_TrainerHealth):
             hs.global_step, hs.opt_step, hs.dp_epoch, hs.lr = global_step - 1, self.opt_step, dp_epoch, float(self.lr)
             self._state.copy_(torch.frombuffer(bytearray(bytes(hs)), dtype=torch.uint8))
         # what the device will hold after this iteration's advance
-        self._dev_gs, self._dev_opt, self._dev_lr, self._dev_dp = global_step, self.opt_step + 1, float(self.lr), dp_epoch + 1
+        self._dev_gs, self._dev_opt, self._dev_lr = global_step, self.opt_step + 1, float(self.lr)
+        self._dev_dp = dp_epoch + 1 if self.dp is not None else 0     # without data parallelism the host never counts it
 
     def _body(self, ns, nr, ts, global_step, rampup_length, max_consistency_cost, target_weak, dropout_step, device_state):
         """The kernel sequence of one iteration.  device_state: the per-iteration scalars come from the device-resident

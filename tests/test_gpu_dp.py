@@ -57,3 +57,18 @@ def test_two_rank_fused_step_equals_nccl_plus_optimizer():
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "replicas bit-identical: True" in r.stdout or "FUSED-DP UNAVAILABLE" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (run by hand with gpurun --gpus 2)")
+def test_two_rank_training_steps_keep_replicas_identical():
+    """tests/dp_train_check.py under torchrun: mean-teacher step (fused exchange inside the CUDA graph, and the NCCL path)
+    and the config-3 adaptation step keep the replicas bit-identical."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29300 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "dp_train_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DP-TRAIN-CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
