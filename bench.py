@@ -376,7 +376,7 @@ def run_b200(args, out):
     launches = launches_per_step * args.steps if graphed else launches_eager
 
     # ---- the same device-resident step over >= 300 steps (>= 2 s of GPU time)
-    sus_steps = max(300, args.steps)
+    sus_steps = max(340, args.steps)
     ms_sus = timed(lambda i: trainer.step(x, x_ema, xs, ts, 200 + i, rampup_len), sus_steps, 0)
     sustained = {"steps": sus_steps, "ms_per_step": ms_sus / sus_steps, "seconds": ms_sus * 1e-3,
                  "value": (N_SYN + N_REAL) * world * sus_steps / (ms_sus * 1e-3), "unit": "clips/s"}
@@ -423,8 +423,17 @@ def run_b200(args, out):
     other = "tf32" if default_precision != "tf32" else "tf32x3"
     tr2 = make_trainer(other)
     ms2 = timed(lambda i: tr2.step(x, x_ema, xs, ts, i, rampup_len), args.steps, args.warmup)
+    # its conv class, timed the same way (kernel by kernel, CUDA events)
+    tr2.use_graph = False
+    ms2_eager = timed(lambda i: tr2.step(x, x_ema, xs, ts, 100 + i, rampup_len), args.steps, 3, lambda: lib.bsed_profile_begin(1))
+    qm, qf = C.c_double(), C.c_double()
+    _lib.check(lib.bsed_profile_end(C.byref(qm), C.byref(qf), None, None), "profile_end")
+    conv2 = qf.value / (qm.value * 1e-3) / 1e12 if qm.value > 0 else None
     other_mode = {"precision": other, "value": (N_SYN + N_REAL) * world * args.steps / (ms2 * 1e-3), "unit": "clips/s",
-                  "ms_per_step": ms2 / args.steps}
+                  "ms_per_step": ms2 / args.steps,
+                  "roofline": {"kernel": "the same conv forward + data-gradient class", "achieved": conv2, "unit": "TFLOP/s",
+                               "peak": peaks["tf_sustained"], "frac": conv2 / peaks["tf_sustained"] if conv2 else None,
+                               "ms_per_step": qm.value / args.steps, "share_of_step": qm.value / ms2_eager if ms2_eager else None}}
     del tr2
     torch.cuda.empty_cache()
 
@@ -747,11 +756,18 @@ def run_pseudo_label(args, out):
     weights_init(m)
     weights_init(p)
     m, p = m.to(dev).eval(), p.to(dev).eval()
-    base = synth.make_clips(24, seed=11).reshape(-1)
-    audio = torch.from_numpy(np.tile(base, 15 * max(1, args.replicate))).pin_memory()   # 360 clips = 1 h at 32 kHz (x replicate)
-    n_clips = audio.shape[0] // 320000
+    from bsed_b200.utilities import shard
+    base = synth.make_clips(24, seed=11)                                   # the stream is these 24 clips over and over
+    n_clips = 360 * max(1, args.replicate)                                 # 360 clips = 1 h at 32 kHz
+    begin, end = shard.clip_shard(n_clips, rank, world)
+    # every rank holds ITS contiguous block of the stream in pinned host memory (a x64 stream is 29 GB: only the shard
+    # is materialised); pseudo_label_stream then walks that block exactly as it walks its shard of a whole stream
+    idx = np.arange(begin, end) % 24
+    audio = torch.from_numpy(np.ascontiguousarray(base[idx]).reshape(-1)).pin_memory()
+    run = lambda: pseudo_label_stream(audio, m, p, batch_clips=48, rank=0, world=1, gather=False,
+                                      name_fmt="stream_{:05d}" if begin == 0 else "stream_" + str(begin) + "+{:05d}")
     for _ in range(max(1, args.warmup)):
-        pseudo_label_stream(audio, m, p, batch_clips=48, rank=rank, world=world, gather=False)
+        run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -759,7 +775,7 @@ def run_pseudo_label(args, out):
     e0.record()
     reps = max(1, args.steps // 4)
     for _ in range(reps):
-        res = pseudo_label_stream(audio, m, p, batch_clips=48, rank=rank, world=world, gather=False)
+        res = run()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
