@@ -169,14 +169,22 @@ class Net_resnet(_FlatModule):
         r = self.resnet
         return [blk for li in range(1, 5) for blk in getattr(r, f"layer{li}")]
 
+    def _gemm_wide(self, a, w, bias, out):
+        """out[:, n] = a @ w[n]^T (+ bias[n]) on the tensor cores: up to 1024 output columns per launch (multiples of 128; the
+        kernel walks (row tile, column block) pairs), then the remainder."""
+        n, n0 = w.shape[0], 0
+        while n0 < n:
+            left = n - n0
+            n1 = n0 + (min(left // 128 * 128, 1024) if left >= 128 else left)
+            engine.gemm_nt_tc(a, w[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=out[:, n0:n1],
+                              x3=self._use_x3())
+            n0 = n1
+
     def _gemm(self, col, wk, wkT, bias, tc):
         M, cout = col.shape[0], wk.shape[0]
         y = torch.empty(M, cout, dtype=torch.float32, device=col.device)
         if tc:
-            for n0 in range(0, cout, 128):
-                n1 = min(cout, n0 + 128)
-                engine.gemm_nt_tc(col, wk[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=y[:, n0:n1],
-                                  x3=self._use_x3())
+            self._gemm_wide(col, wk, bias, y)
         else:
             engine.gemm_nn(col, wkT, bias, out=y)
         return y
@@ -286,12 +294,10 @@ class Net_resnet(_FlatModule):
         self._grad_view(grads, conv, "weight").add_(dwk[:, :rec["K"]].view(conv.cout, conv.k, conv.k, conv.cin).permute(0, 3, 1, 2))
         dx = None
         if need_dx:
-            if tc:                                                       # (M, Kpad) = dconv * Wk, 128 columns per launch
+            if tc:                                                       # (M, Kpad) = dconv * Wk
                 wkT = rec["wk"].t().contiguous()
                 dcol = torch.empty(dy.shape[0], rec["kpad"], dtype=torch.float32, device=dy.device)
-                for n0 in range(0, rec["kpad"], 128):
-                    n1 = min(rec["kpad"], n0 + 128)
-                    engine.gemm_nt_tc(dy, wkT[n0:n1], None, out=dcol[:, n0:n1], x3=self._use_x3())
+                self._gemm_wide(dy, wkT, None, dcol)
             else:
                 dcol = engine.gemm_nn(dy, rec["wk"])
             dx = engine.col2im_nhwc(dcol, tuple(inp.shape), conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad,

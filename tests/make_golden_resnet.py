@@ -61,6 +61,40 @@ def train_fixture():
     print("resnet train fixture: loss", rec["loss"], "nbt", rec["nbt"])
 
 
+def train_fixture8():
+    """The same iteration on 4 + 4 clips (better conditioned: four times the rows behind every train-mode BatchNorm), with
+    the float64 run of the same model next to torch's fp32 one: `g64_*` is the yardstick, `dev32` records how far torch's
+    own fp32 gradients are from it, tensor by tensor (worst and median printed)."""
+    torch.set_num_threads(8)
+    xs = torch.from_numpy(synth.make_logmel_like(4, seed=81))
+    xr = torch.from_numpy(synth.make_logmel_like(4, seed=82))
+    ts = torch.from_numpy(synth.make_targets(4, seed=83))
+    tw = (torch.from_numpy(synth.make_targets(4, seed=84)).max(-2)[0] > 0).float()
+    rec, grads = {}, {}
+    for dt in (torch.float32, torch.float64):
+        m = ores.seeded_init(ores.OracleNetResnet(20), seed=17).to(dt).train()
+        loss, _ = ores.tagger_step_loss(m, xs.to(dt), ts.to(dt), xr.to(dt), tw.to(dt))
+        loss.backward()
+        grads[dt] = {n: p.grad.detach().double().numpy().reshape(-1) for n, p in m.named_parameters()}
+        rec["loss" if dt == torch.float32 else "loss64"] = float(loss)
+    devs = []
+    for n, g32 in grads[torch.float32].items():
+        g64 = grads[torch.float64][n]
+        sl = slice(None) if g32.size <= 4096 else slice(None, None, max(1, g32.size // 4096))
+        rec["g64_" + n] = g64[sl][:4096].astype(np.float32)
+        rec["gn_" + n] = float(np.linalg.norm(g64))
+        rec["dev32_" + n] = float(np.linalg.norm(g32 - g64) / max(np.linalg.norm(g64), 1e-30))
+        if rec["gn_" + n] > 1e-6:
+            devs.append(rec["dev32_" + n])
+            if devs[-1] > 1e-4:
+                print("   torch fp32 vs fp64", n, devs[-1], "norm", rec["gn_" + n])
+    rec["dev32_worst"], rec["dev32_median"] = max(devs), float(np.median(devs))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "resnet_train8.npz"), **rec)
+    print("resnet 4 + 4 fixture: loss", rec["loss"], "loss64", rec["loss64"], "torch fp32 vs fp64 gradients: worst",
+          rec["dev32_worst"], "median", rec["dev32_median"])
+
+
 if __name__ == "__main__":
     main()
     train_fixture()
+    train_fixture8()

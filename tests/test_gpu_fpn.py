@@ -99,8 +99,16 @@ def test_fpn_train_forward_backward(precision, tol_p, tol_g):
     assert not bad, bad
 
 
-def test_fpn_fused_trainer_matches_reference_fixture():
+@pytest.mark.parametrize("precision", ["fp32", "default"])
+def test_fpn_fused_trainer_matches_reference_fixture(precision, monkeypatch):
+    """"default" = the library default precision (3xTF32), "fp32" = the CUDA-core cross-check; same fixture, same bars
+    except the mean parameter distance after two Adam steps (sign flips of near-zero gradients)."""
     from bsed_b200.main import MeanTeacherTrainer
+    if precision == "default":
+        monkeypatch.delenv("BSED_PRECISION", raising=False)
+    else:
+        monkeypatch.setenv("BSED_PRECISION", precision)
+    mean_tol = 2e-5 if precision == "fp32" else 6e-5
     g = golden("fpn_mt_step_drop.npz")
     oc, op = oracle_fpn_models(seed=5, linear_std=0.2)
     tc, tp = oracle_fpn_models(seed=6, linear_std=0.2)
@@ -143,7 +151,10 @@ def test_fpn_fused_trainer_matches_reference_fixture():
               "cnn.bn_fcn.weight", "cnn.conv1x1.weight", "rnn.rnn.weight_hh_l0", "rnn_2.rnn.weight_ih_l1_reverse",
               "rnn_4.rnn.bias_hh_l0", "conv1x1_2.weight", "conv1x1_4.bias", "cnn.bn_fcn.running_var"):
         d = np.abs(ssd[k].cpu().numpy().reshape(-1)[:2048].astype(np.float64) - g["s_" + k])
-        assert d.max() < 1.1e-3 and d.mean() < 2e-5, (k, d.max(), d.mean())       # two Adam steps of lr 5e-4
+        # two Adam steps of lr 5e-4; running_var in the default precision: see tests/test_gpu_train.py (a first-block
+        # parameter whose near-zero gradient flips sign rescales every batch variance downstream by ~1e-3)
+        tol = mean_tol + (2e-3 * float(np.abs(g["s_" + k]).mean()) if precision != "fp32" and "running_var" in k else 0.0)
+        assert d.max() < 1.1e-3 and d.mean() < tol, (k, d.max(), d.mean(), tol)
         assert max_abs(tsd[k].cpu().numpy().reshape(-1)[:2048], g["t_" + k]) < 1e-4, k
     assert int(tsd["cnn.bn_fcn.num_batches_tracked"]) == int(g["t_nbt_fcn"]) == 4
     assert int(ssd["cnn.bn_fcn.num_batches_tracked"]) == int(g["s_nbt_fcn"]) == 8

@@ -59,10 +59,16 @@ def test_loss_terms_match_torch():
     assert rel_l2(dw.cpu().numpy(), w.grad.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "default"])
 @pytest.mark.parametrize("p_drop,fpn", [(0.0, False), (0.5, False), (0.5, True)])
-def test_isp_step_matches_oracle(p_drop, fpn):
-    """fpn: the same step on CRNN_fpn, the model the reference's author trains with -ISP."""
+def test_isp_step_matches_oracle(p_drop, fpn, precision, monkeypatch):
+    """fpn: the same step on CRNN_fpn, the model the reference's author trains with -ISP.  precision "default" = the
+    library default (3xTF32 tensor-core path), "fp32" = the CUDA-core cross-check; same tolerances."""
     from bsed_b200.main import ISP_SLOTS, ShiftConsistencyTrainer
+    if precision == "default":
+        monkeypatch.delenv("BSED_PRECISION", raising=False)
+    else:
+        monkeypatch.setenv("BSED_PRECISION", precision)
     n = 2
     omk, bmk = (oracle_fpn_models, bsed_fpn_models) if fpn else (oracle_models, bsed_models)
     oc, op = omk(seed=5, linear_std=0.2, dropout=p_drop, train=True)

@@ -284,6 +284,50 @@ def test_tf32_against_fp32_on_a_larger_batch():
     assert losses["tf32"] == pytest.approx(losses["fp32"], rel=1e-3) and e < 2e-2
 
 
+# measured on B200: fp32 2.9e-3 (torch's own fp32: 1.6e-3); tf32x3 1.3e-2 (forward products fp32-grade, the weight-gradient
+# reductions single-pass tf32); default = single-pass tf32 everywhere, cuDNN's arithmetic for the reference: 0.17 on the
+# small-norm layer1 BatchNorm scales (|g| ~ 5e-4), 0.14 on conv1.weight -- 20 train-mode BatchNorms amplify the forward rounding
+GRAD_TOL8 = {"fp32": 6e-3, "tf32x3": 3e-2, "default": 0.3}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "default"])
+def test_training_step_on_eight_clips_against_float64(precision, monkeypatch):
+    """4 + 4 clips: four times the rows behind every train-mode BatchNorm, and the yardstick is a FLOAT64 run of torchvision's
+    resnet18 assembled as the reference's Net_resnet (tests/make_golden_resnet.py: train_fixture8), from which torch's own
+    fp32 gradients differ by up to 1.6e-3 (dev32_*; layer1 / layer2 tensors ~1e-3, median 4e-6)."""
+    from bsed_b200.models.ResNet import Net_resnet, TaggerTrainer
+    if precision == "default":
+        monkeypatch.delenv("BSED_PRECISION", raising=False)
+    g = golden("resnet_train8.npz")
+    oc = ores.seeded_init(ores.OracleNetResnet(20), seed=17)
+    m = Net_resnet(pretrained=False, precision=None if precision == "default" else precision)
+    m.load_state_dict(oc.state_dict())
+    m = m.cuda().train()
+    xs = torch.from_numpy(synth.make_logmel_like(4, seed=81)).cuda()
+    xr = torch.from_numpy(synth.make_logmel_like(4, seed=82)).cuda()
+    ts = torch.from_numpy(synth.make_targets(4, seed=83)).cuda()
+    tw = (torch.from_numpy(synth.make_targets(4, seed=84)).max(-2)[0] > 0).float().cuda()
+    tr = TaggerTrainer(m, lr=1e-3)
+    loss = tr.step(xs, ts, xr, tw)
+    assert float(loss) == pytest.approx(float(g["loss64"]), rel=1e-4)
+    o, bad, worst = 0, [], (0.0, "")
+    for (mod, pname, shape), n in zip(m._param_specs, [n for n, _ in m.named_parameters()]):
+        k = int(np.prod(shape))
+        got = tr.grads[o:o + k].cpu().numpy().reshape(-1).astype(np.float64)
+        o += k
+        if float(g["gn_" + n]) < 1e-6:
+            continue
+        got = got if got.size <= 4096 else got[:: max(1, got.size // 4096)][:4096]
+        ref = g["g64_" + n].astype(np.float64)
+        e = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        worst = max(worst, (e, n))
+        if e > GRAD_TOL8[precision]:
+            bad.append((n, e, float(g["dev32_" + n])))
+    print(f"resnet train 4 + 4 clips vs float64 ({precision}): loss {float(loss):.6f}, worst gradient rel_l2 {worst[0]:.2e} "
+          f"({worst[1]}); torch fp32's own worst {float(g['dev32_worst']):.2e}")
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_tagger_train_mt_entry_point(fused):
     """train_mt of src/audio_tagging_system_cnn.py:199 with the reference's three loaders, through the fused trainer and

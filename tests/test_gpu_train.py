@@ -30,7 +30,7 @@ def _models(p_drop):
     return m, p, em, ep
 
 
-def _check_against_fixture(g, m, p, em, ep, losses, grads_flat=None, n_crnn=None):
+def _check_against_fixture(g, m, p, em, ep, losses, grads_flat=None, n_crnn=None, mean_tol=1e-5, var_rel=0.0):
     for it in range(2):
         lv = losses[it]
         ref = [float(g[f"strong_class{it}"]), float(g[f"weak_class{it}"]), float(g[f"cons_strong{it}"]),
@@ -54,7 +54,11 @@ def _check_against_fixture(g, m, p, em, ep, losses, grads_flat=None, n_crnn=None
             # amount; BatchNorm subtracts it again, nothing downstream sees it
             assert d.max() < 1.1e-3, (k, d.max())
         else:
-            assert d.max() < 1.1e-3 and d.mean() < 1e-5, (k, d.max(), d.mean())
+            # running_var (default precision): ONE first-block parameter (16 BatchNorm scales, 144 conv weights) whose
+            # near-zero gradient changes sign under the single-pass tf32 weight-gradient reductions moves by 2 lr = 1e-3
+            # and rescales every channel's batch variance downstream by ~1e-3 (measured 9e-4 on the dropout fixture)
+            tol = mean_tol + (var_rel * float(np.abs(s_ref).mean()) if "running_var" in k else 0.0)
+            assert d.max() < 1.1e-3 and d.mean() < tol, (k, d.max(), d.mean(), tol)
         assert max_abs(t_got, t_ref) < 1e-4, (k, max_abs(t_got, t_ref))
     assert int(tsd["cnn.batchnorm0.num_batches_tracked"]) == int(g["t_nbt"])
     assert int(ssd["cnn.batchnorm0.num_batches_tracked"]) == int(g["s_nbt"]) == 4
@@ -62,13 +66,22 @@ def _check_against_fixture(g, m, p, em, ep, losses, grads_flat=None, n_crnn=None
     assert max_abs(ep.dense.weight.detach().cpu().numpy().reshape(-1), g["t_dense_w"]) < 1e-4
 
 
+@pytest.mark.parametrize("precision", ["fp32", "default"])
 @pytest.mark.parametrize("name,p_drop", [("mt_step_nodrop.npz", 0.0), ("mt_step_drop.npz", 0.5)])
-def test_fused_trainer_matches_reference_fixture(name, p_drop):
+def test_fused_trainer_matches_reference_fixture(name, p_drop, precision, monkeypatch):
+    """Two iterations against the fixtures the reference's own modules produced (tests/make_golden.py): losses, every
+    gradient tensor, probabilities, parameters, teacher, BatchNorm state.  "default" = the library default precision
+    (3xTF32 on the tensor cores; the second iteration is replayed from the CUDA graph), "fp32" = the CUDA-core cross-check."""
     from bsed_b200.main import MeanTeacherTrainer
+    if precision == "default":
+        monkeypatch.delenv("BSED_PRECISION", raising=False)
+    else:
+        monkeypatch.setenv("BSED_PRECISION", precision)
     g = golden(name)
     m, p, em, ep = _models(p_drop)
     xs, xr, xr_ema, ts = [t.cuda() for t in _inputs()]
     tr = MeanTeacherTrainer(m, p, em, ep, lr=5e-4, n_syn=2, n_real=2, dropout_seed=2023)
+    assert tr.plan.precision == ("tf32x3" if precision == "default" else precision)
     losses = []
     for it in range(2):
         l = tr.step(xr, xr_ema, xs, ts, global_step=100 + it, rampup_length=500)
@@ -92,7 +105,9 @@ def test_fused_trainer_matches_reference_fixture(name, p_drop):
                     bad.append((fullname, rel_l2(gs, ref)))
             assert not bad, bad
             assert max_abs(tr.last["strong"][2:].cpu().numpy(), g["strong0"]) < 1e-3
-    _check_against_fixture(g, m, p, em, ep, losses)
+    # single-pass tf32 weight-gradient reductions: a few more near-zero gradients change sign under Adam's first steps
+    _check_against_fixture(g, m, p, em, ep, losses, mean_tol=1e-5 if precision == "fp32" else 4e-5,
+                           var_rel=0.0 if precision == "fp32" else 2e-3)
 
 
 def test_generic_module_path_matches_reference_fixture():
