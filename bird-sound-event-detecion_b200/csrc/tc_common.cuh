@@ -46,6 +46,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();
   }
 }
+// non-blocking probe of a phase (a producer that serves two rings polls both instead of blocking on one)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {   // explicit shared-space load (a generic LD costs a long scoreboard)
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -127,6 +141,20 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler keeps the code under this predicate on the
+// uniform datapath -- descriptors stay in uniform registers and every tcgen05.mma is issued without a per-instruction
+// vector-to-uniform "waterfall" loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~15 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -140,6 +168,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same MMA with the descriptors given as (low word, shared high word): low word = (address >> 4) | LBO, so a tile
+// `off` bytes further on is `lo + (off >> 4)` -- one uniform add per MMA in an issue loop instead of shift / mask / or.
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
@@ -180,6 +224,13 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_addr) {
   constexpr uint64_t sbo = (8 * ROWB) >> 4;
   constexpr uint64_t layout = ROWB == 128 ? 2 : 4;   // SWIZZLE_128B : SWIZZLE_64B
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// the two words of that descriptor: the low one carries the start address (shared memory is < 256 KB: no carry out of the
+// 14-bit field when a byte offset >> 4 is added), the high one is the same for every tile of the layout
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+template <int ROWB>
+__host__ __device__ constexpr uint32_t kmajor_desc_hi() {
+  return (uint32_t)((8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
 }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_tf32(int n, int a_mn_major, int b_mn_major) {

@@ -58,7 +58,8 @@ struct CSmem {
   static constexpr int B_STRIDE = (B_TILE + 1023) / 1024 * 1024;
   static constexpr int NB = X3 ? 2 : 1;                               // weight tiles per (tap, chunk): hi [, lo]
   static constexpr int B_SLOT = NB * B_STRIDE;
-  static constexpr int HW = N < 64 ? N : 64;                          // columns staged per pass
+  // columns staged per pass; 3xTF32 with 128 output channels stages 32 (16 KB) so that a fourth (hi, lo) weight slot fits
+  static constexpr int HW = N < 64 ? N : (X3 && N == 128) ? 32 : 64;
   static constexpr int STG_BYTES = kBM * HW * 4;
   static constexpr int BAR_BYTES = 512;
 };
@@ -122,7 +123,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int sb = 0;
       uint32_t phb = 0;
       if (a.rb) {
@@ -132,40 +133,55 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (X3) tma_load_2d(&mapBlo, sB + i * S::B_SLOT + S::B_STRIDE, rbfull, i * KCH, 0);
         }
       }
-      // flat sequence of (tile, chunk) steps; the activation columns of step i + 1 are requested BEFORE the nine weight
-      // tiles of step i (which are paced by the MMAs through the weight ring), so they land while step i computes
+      // Two independent request streams served by this one thread, polled without blocking: the activation columns of a
+      // step are requested as soon as their stage is free (up to kAStages steps ahead of the MMAs), the weight tiles as
+      // soon as their ring slot is.  (Blocking on the activation stage between two weight tiles drained the weight ring at
+      // every step boundary: the MMAs of the next step then started behind a full L2 round trip.)  The column copies go
+      // out one per loop turn, interleaved with the weight tiles, so that no 35-70 KB burst sits ahead of a weight tile
+      // in the TMA queue.
       const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const int steps = my_tiles * a.cpt;
-      // The column copies of step i + 1 are interleaved one by one with the weight tiles of step i: a 68 KB burst of
-      // activation boxes ahead of them in the TMA queue would add its whole service time to the weight tiles' latency.
-      auto issue_a = [&](int step, int j) {   // column copy j of step `step`
-        const int tile = blockIdx.x + (step / a.cpt) * gridDim.x, ch = step % a.cpt;
-        const int b = tile / per_clip, r = tile - b * per_clip;
-        const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
-        const int stage = step % kAStages;
-        if (j == 0) {
-          mbar_wait(&aempty[stage], ((step / kAStages) & 1) ^ 1);
-          mbar_expect_tx(&afull[stage], (kG + 2) * kHaloRows * KCH * 4);
-        }
-        tma_load_4d(&mapA, smem + stage * S::A_STAGE + j * S::A_COPY, &afull[stage], ch * KCH, f0 - 1 + j, t0 - 1, b);
-      };
-      if (steps > 0)
-        for (int j = 0; j < kG + 2; ++j) issue_a(0, j);
-      for (int step = 0; step < steps; ++step) {
-        const int ch = step % a.cpt;
-        for (int tap = 0; tap < 9; ++tap) {
-          if (step + 1 < steps && (tap & 1) == 0 && tap / 2 < kG + 2) issue_a(step + 1, tap / 2);
-          if (!a.rb) {
-            mbar_wait(&bempty[sb], phb ^ 1);
-            mbar_expect_tx(&bfull[sb], S::NB * S::B_TILE);
-            tma_load_2d(&mapB, sB + sb * S::B_SLOT, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
-            if (X3) tma_load_2d(&mapBlo, sB + sb * S::B_SLOT + S::B_STRIDE, &bfull[sb], (tap * a.cpt + ch) * KCH, 0);
-            if (++sb == a.bstages) {
-              sb = 0;
-              phb ^= 1;
+      const int total_b = a.rb ? 0 : steps * 9;
+      int a_step = 0, a_copy = 0, b_idx = 0, b_tap = 0, b_ch = 0;
+      uint32_t idle = 0;
+      while (a_step < steps || b_idx < total_b) {
+        bool progressed = false;
+        if (a_step < steps) {
+          const int stage = a_step % kAStages;
+          if (a_copy > 0 || mbar_test(&aempty[stage], ((a_step / kAStages) & 1) ^ 1)) {
+            const int tile = blockIdx.x + (a_step / a.cpt) * gridDim.x, ch = a_step % a.cpt;
+            const int b = tile / per_clip, r = tile - b * per_clip;
+            const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
+            if (a_copy == 0) mbar_expect_tx(&afull[stage], (kG + 2) * kHaloRows * KCH * 4);
+            tma_load_4d(&mapA, smem + stage * S::A_STAGE + a_copy * S::A_COPY, &afull[stage], ch * KCH, f0 - 1 + a_copy, t0 - 1, b);
+            if (++a_copy == kG + 2) {
+              a_copy = 0;
+              ++a_step;
             }
+            progressed = true;
           }
         }
+        if (b_idx < total_b && mbar_test(&bempty[sb], phb ^ 1)) {
+          if (a.debug == 2 && b_idx >= a.bstages) {   // experiment: the ring is never refilled
+            mbar_arrive(&bfull[sb]);
+          } else {
+            mbar_expect_tx(&bfull[sb], S::NB * S::B_TILE);
+            tma_load_2d(&mapB, sB + sb * S::B_SLOT, &bfull[sb], (b_tap * a.cpt + b_ch) * KCH, 0);
+            if (X3) tma_load_2d(&mapBlo, sB + sb * S::B_SLOT + S::B_STRIDE, &bfull[sb], (b_tap * a.cpt + b_ch) * KCH, 0);
+          }
+          if (++sb == a.bstages) {
+            sb = 0;
+            phb ^= 1;
+          }
+          ++b_idx;
+          if (++b_tap == 9) {
+            b_tap = 0;
+            if (++b_ch == a.cpt) b_ch = 0;
+          }
+          progressed = true;
+        }
+        if (progressed) idle = 0;
+        else if (++idle > kSpinLimit) __trap();
       }
     }
   } else if (warp == 1) {
@@ -182,35 +198,42 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_after();
       for (int ch = 0; ch < a.cpt; ++ch) {
         mbar_wait(&afull[sa], pha);
-        if (X3) mbar_wait(&lofull[sa], pha);      // the splitters have written the low parts of this stage
+        if (X3 && a.debug != 3) mbar_wait(&lofull[sa], pha);      // the splitters have written the low parts of this stage
         tc_fence_after();
-        const uint32_t abase = smem_u32(smem + sa * S::A_STAGE);
-        const uint32_t lobase = smem_u32(alo + sa * S::A_STAGE);
+        // descriptor low words ((address >> 4) | LBO): every tile of the step is these plus a compile-time constant
+        const uint32_t a_w = kmajor_desc_lo(smem_u32(smem + sa * S::A_STAGE));
+        const uint32_t l_w = kmajor_desc_lo(smem_u32(alo + sa * S::A_STAGE));
+        const uint32_t d_tmem = tmem_base + ab * kG * N;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dt = tap / 3 - 1, df = tap % 3 - 1;
-          uint32_t bbase;
+          uint32_t b_w;
           if (a.rb) {
-            bbase = smem_u32(sB + (tap * a.cpt + ch) * S::B_SLOT);
+            b_w = kmajor_desc_lo(smem_u32(sB + (tap * a.cpt + ch) * S::B_SLOT));
           } else {
             mbar_wait(&bfull[sb], phb);
             tc_fence_after();
-            bbase = smem_u32(sB + sb * S::B_SLOT);
+            b_w = kmajor_desc_lo(smem_u32(sB + sb * S::B_SLOT));
           }
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
+            // consecutive MMAs alternate between the two accumulators (bins g = 0, 1)
+            constexpr uint32_t DHI = kmajor_desc_hi<ROWB>();
+            const uint32_t aoff = (uint32_t)((df + 1) * S::A_COPY + (dt + 1) * ROWB) >> 4;
 #pragma unroll
-            for (int g = 0; g < kG; ++g) {
-              const uint32_t aoff = (g + df + 1) * S::A_COPY + (dt + 1) * ROWB;
-              const uint32_t d_tmem = tmem_base + (ab * kG + g) * N;
+            for (int k = 0; k < KCH / 8; ++k) {
+              const uint32_t acc = (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u);
 #pragma unroll
-              for (int k = 0; k < KCH / 8; ++k) {
-                const uint64_t da = kmajor_desc_rows<ROWB>(abase + aoff + k * 32);
-                const uint64_t db = kmajor_desc<ROWB>(bbase + k * 32);
-                umma_tf32(d_tmem, da, db, idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                if (X3) {
-                  umma_tf32(d_tmem, da, kmajor_desc<ROWB>(bbase + S::B_STRIDE + k * 32), idesc, 1u);
-                  umma_tf32(d_tmem, kmajor_desc_rows<ROWB>(lobase + aoff + k * 32), db, idesc, 1u);
-                }
+              for (int g = 0; g < kG; ++g)
+                umma_tf32_w(d_tmem + g * N, a_w + aoff + ((g * S::A_COPY + k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, acc);
+              if (X3) {
+#pragma unroll
+                for (int g = 0; g < kG; ++g)
+                  umma_tf32_w(d_tmem + g * N, a_w + aoff + ((g * S::A_COPY + k * 32) >> 4),
+                              b_w + ((S::B_STRIDE + k * 32) >> 4), DHI, idesc, 1u);
+#pragma unroll
+                for (int g = 0; g < kG; ++g)
+                  umma_tf32_w(d_tmem + g * N, l_w + aoff + ((g * S::A_COPY + k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, 1u);
               }
             }
             if (!a.rb) umma_commit(&bempty[sb]);
@@ -263,8 +286,11 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (CW == 32) return (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4));
       return (uint32_t)(r * 64 + ((c4 ^ ((r >> 1) & 3)) << 4));
     };
-    // thread `row` owns output channels row (pass 0) and 64 + row (pass 1) for the statistics
-    double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
+    // thread `row` < HW owns output channels h * HW + row of every pass h for the statistics
+    constexpr int NPASS = N / HW;
+    double st_sum[NPASS], st_sq[NPASS];
+#pragma unroll
+    for (int h = 0; h < NPASS; ++h) st_sum[h] = st_sq[h] = 0.0;
     int st_grp = -1;
     auto flush_stats = [&]() {
       if (st_grp >= 0) {
@@ -276,7 +302,8 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             atomicAdd(a.stats + ((size_t)st_grp * a.stats_c + c) * 2 + 1, st_sq[h]);
           }
       }
-      st_sum[0] = st_sum[1] = st_sq[0] = st_sq[1] = 0.0;
+#pragma unroll
+      for (int h = 0; h < NPASS; ++h) st_sum[h] = st_sq[h] = 0.0;
     };
     int it = 0, pass_no = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -368,6 +395,10 @@ static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
     a.rb = 0;
     long long bs = budget / S::B_SLOT;
     a.bstages = (int)(bs > 9 ? 9 : bs);
+    if (const char* e = getenv("BSED_COL_BSTAGES")) {      // measurement experiments only
+      const int v = atoi(e);
+      if (v >= 2 && v < a.bstages) a.bstages = v;
+    }
     if (a.bstages < 2) {
       bsed_set_error("tc_conv_col: no room for the weight ring (N=%d)", N);
       return BSED_E_INVALID;

@@ -140,7 +140,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       if (RB) {
@@ -193,19 +193,21 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (X3) mbar_wait(&lofull[lj], lph);   // the splitters have written the low part of this stage
         tc_fence_after();
         __syncwarp();
-        if (lane == 0) {   // one fixed lane issues the MMAs and their commits (commit tracks the issuing thread)
+        if (elect_one()) {   // one fixed lane issues the MMAs and their commits (commit tracks the issuing thread)
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
           const uint32_t sb = RB ? smem_u32(rb + kc * S::B_STRIDE) : sa + S::A_BYTES;
           const uint32_t sblo = RB ? smem_u32(rb + (nk + kc) * S::B_STRIDE) : sb + S::B_STRIDE;
           const uint32_t salo = smem_u32(lo + lj * S::A_BYTES);
+          // BSED_TC_DEBUG=4 (measurement experiment, wrong results): every other MMA accumulates into the OTHER buffer
+          const uint32_t d_alt = a.debug == 4 ? tmem_base + (acc ^ 1) * N : d_tmem;
 #pragma unroll
           for (int k = 0; k < KCH / 8; ++k) {
             uint64_t da = kmajor_desc<ROWB>(sa + k * 32);
             uint64_t db = kmajor_desc<ROWB>(sb + k * 32);
-            umma_tf32(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32((k & 1) ? d_alt : d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
             if (X3) {
-              umma_tf32(d_tmem, da, kmajor_desc<ROWB>(sblo + k * 32), idesc, 1u);
-              umma_tf32(d_tmem, kmajor_desc<ROWB>(salo + k * 32), db, idesc, 1u);
+              umma_tf32((k & 1) ? d_tmem : d_alt, da, kmajor_desc<ROWB>(sblo + k * 32), idesc, 1u);
+              umma_tf32((k & 1) ? d_alt : d_tmem, kmajor_desc<ROWB>(salo + k * 32), db, idesc, 1u);
             }
           }
           umma_commit(&empty[s]);                      // frees the stage once these MMAs have read it
@@ -626,7 +628,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = a_chunks * S::A_CHUNK + S::B_BYTES;
@@ -654,7 +656,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       mbar_wait(&full[s], ph);
       tc_fence_after();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + s * S::STAGE);
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
@@ -759,7 +761,7 @@ tc_wgrad9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int b_ch = a.b_c0 + nt * N;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (a_sets * a_chunks + 9) * S::CHUNK;
@@ -790,7 +792,7 @@ tc_wgrad9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&full[s], ph);
       tc_fence_after();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + s * S::STAGE);
         const uint32_t sb = sa + S::A_BYTES;
         for (int tap = 0; tap < ntaps; ++tap) {
