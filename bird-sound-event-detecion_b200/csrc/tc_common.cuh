@@ -127,6 +127,22 @@ __device__ __forceinline__ float4 tf32_lo4(float4 v) {
 }
 __device__ __forceinline__ void split_barrier() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 static_assert(kThreadsX3 - kThreads == 64, "split_barrier counts the splitter threads");
+// low parts of n16 float4 starting at shared address src -> dst, one of kSplitThreads threads (tid).  The loads of a batch are
+// issued together: the explicit ld.shared / st.shared wrappers are volatile asm and stay in program order, so a plain
+// "load, convert, store" loop pays the whole shared-memory latency per float4 (measured: ~150 clk per float4 and thread,
+// which made the splitters the bottleneck of every streaming 3xTF32 GEMM).
+template <int BATCH>
+__device__ __forceinline__ void split_lo_range(uint32_t src, uint32_t dst, int n16, int tid) {
+  int i = tid;
+  for (; i + (BATCH - 1) * kSplitThreads < n16; i += BATCH * kSplitThreads) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) v[b] = lds128(src + (i + b * kSplitThreads) * 16);
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) sts128(dst + (i + b * kSplitThreads) * 16, tf32_lo4(v[b]));
+  }
+  for (; i < n16; i += kSplitThreads) sts128(dst + i * 16, tf32_lo4(lds128(src + i * 16)));
+}
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

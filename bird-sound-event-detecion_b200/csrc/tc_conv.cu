@@ -23,6 +23,12 @@ constexpr int kG = 2;               // frequency bins per CTA step
 constexpr int kHaloRows = 130;      // t0-1 .. t0+128
 constexpr int kHaloPad = 136;       // rows of one column copy, padded to the 8-row swizzle repeat
 constexpr int kAStages = 2;
+// Warp roles: 0 TMA producer, 1 and 6 MMA issuers (one frequency bin = one accumulator each), 2-5 epilogue, 7-8 operand
+// splitters (3xTF32).  Two issuers because the tensor core's MMA queue is shallow: one thread that also waits on the weight
+// ring, fences and commits between its MMAs leaves the pipe idle for all of that time (measured with tests/probes/
+// umma_probe.cu: 74.6 clk per 128x128x8 MMA with one issuer, the 64.1 clk floor with two; in this kernel 104 clk).
+constexpr int kColThreads = 7 * 32;
+constexpr int kColThreadsX3 = 9 * 32;
 // 3xTF32 (X3, see tc_gemm.cu): the input is walked in 16-channel chunks (64-byte rows, SWIZZLE_64B), so that the raw
 // column copies, their low parts (one set per stage, written by two splitter warps) and a ring of (hi, lo) weight tiles
 // fit the 227 KB of shared memory; every (tap, k-step) issues a*w_hi + a*w_lo + a_lo*w_hi.
@@ -65,7 +71,7 @@ struct CSmem {
 };
 
 template <int N, bool X3>
-__global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
+__global__ void __launch_bounds__(X3 ? kColThreadsX3 : kColThreads, 1)
 tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
                    const float* __restrict__ bias, CArgs a) {
@@ -99,15 +105,15 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     prefetch_tmap(&mapC);
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(&afull[s], 1);
-      mbar_init(&aempty[s], 1);
+      mbar_init(&aempty[s], kG);        // one tcgen05.commit per issuer warp
       mbar_init(&lofull[s], 1);
     }
     for (int s = 0; s < 16; ++s) {
       mbar_init(&bfull[s], 1);
-      mbar_init(&bempty[s], 1);
+      mbar_init(&bempty[s], kG);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
+      mbar_init(&tfull[i], kG);
       mbar_init(&tempty[i], 4);
     }
     mbar_init(rbfull, 1);
@@ -184,8 +190,9 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         else if (++idle > kSpinLimit) __trap();
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 6) {
+    // ===================== MMA issuers: bin g = 0 (warp 1), g = 1 (warp 6) =====================
+    const int g = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
@@ -201,9 +208,9 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (X3 && a.debug != 3) mbar_wait(&lofull[sa], pha);      // the splitters have written the low parts of this stage
         tc_fence_after();
         // descriptor low words ((address >> 4) | LBO): every tile of the step is these plus a compile-time constant
-        const uint32_t a_w = kmajor_desc_lo(smem_u32(smem + sa * S::A_STAGE));
-        const uint32_t l_w = kmajor_desc_lo(smem_u32(alo + sa * S::A_STAGE));
-        const uint32_t d_tmem = tmem_base + ab * kG * N;
+        const uint32_t a_w = kmajor_desc_lo(smem_u32(smem + sa * S::A_STAGE + g * S::A_COPY));
+        const uint32_t l_w = kmajor_desc_lo(smem_u32(alo + sa * S::A_STAGE + g * S::A_COPY));
+        const uint32_t d_tmem = tmem_base + (ab * kG + g) * N;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dt = tap / 3 - 1, df = tap % 3 - 1;
@@ -217,23 +224,15 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
           __syncwarp();
           if (elect_one()) {
-            // consecutive MMAs alternate between the two accumulators (bins g = 0, 1)
             constexpr uint32_t DHI = kmajor_desc_hi<ROWB>();
             const uint32_t aoff = (uint32_t)((df + 1) * S::A_COPY + (dt + 1) * ROWB) >> 4;
 #pragma unroll
             for (int k = 0; k < KCH / 8; ++k) {
               const uint32_t acc = (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u);
-#pragma unroll
-              for (int g = 0; g < kG; ++g)
-                umma_tf32_w(d_tmem + g * N, a_w + aoff + ((g * S::A_COPY + k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, acc);
+              umma_tf32_w(d_tmem, a_w + aoff + ((k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, acc);
               if (X3) {
-#pragma unroll
-                for (int g = 0; g < kG; ++g)
-                  umma_tf32_w(d_tmem + g * N, a_w + aoff + ((g * S::A_COPY + k * 32) >> 4),
-                              b_w + ((S::B_STRIDE + k * 32) >> 4), DHI, idesc, 1u);
-#pragma unroll
-                for (int g = 0; g < kG; ++g)
-                  umma_tf32_w(d_tmem + g * N, l_w + aoff + ((g * S::A_COPY + k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, 1u);
+                umma_tf32_w(d_tmem, a_w + aoff + ((k * 32) >> 4), b_w + ((S::B_STRIDE + k * 32) >> 4), DHI, idesc, 1u);
+                umma_tf32_w(d_tmem, l_w + aoff + ((k * 32) >> 4), b_w + ((k * 32) >> 4), DHI, idesc, 1u);
               }
             }
             if (!a.rb) umma_commit(&bempty[sb]);
@@ -254,21 +253,17 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
       }
     }
-  } else if (X3 && warp >= 6) {
-    // ===================== operand splitters (warps 6..7, 3xTF32) =====================
+  } else if (X3 && warp >= 7) {
+    // ===================== operand splitters (warps 7..8, 3xTF32) =====================
     // lo[sa] is free whenever A[sa] is: a stage is refilled only after the MMAs that read both have completed
-    const int tid = threadIdx.x - 6 * 32;
+    const int tid = threadIdx.x - 7 * 32;
     const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int steps = my_tiles * a.cpt;
     for (int step = 0; step < steps; ++step) {
       const int sa = step % kAStages;
       mbar_wait(&afull[sa], (step / kAStages) & 1);
       const uint32_t src = smem_u32(smem + sa * S::A_STAGE), dst = smem_u32(alo + sa * S::A_STAGE);
-#pragma unroll 4
-      for (int i = tid; i < S::A_STAGE / 16; i += kSplitThreads) {
-        const float4 v = lds128(src + i * 16);
-        sts128(dst + i * 16, tf32_lo4(v));
-      }
+      split_lo_range<8>(src, dst, S::A_STAGE / 16, tid);
       fence_proxy_async();
       split_barrier();
       if (tid == 0) mbar_arrive(&lofull[sa]);
@@ -324,6 +319,12 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
       mbar_wait(&tfull[ab], ab_ph);
       tc_fence_after();
+      if (a.debug == 5) {   // experiment: accumulators dropped (main-loop time alone)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
+        continue;
+      }
       for (int g = 0; g < kG; ++g) {
         const uint32_t taddr = tmem_base + (ab * kG + g) * N + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -338,11 +339,12 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if constexpr (CW == 32) tmem_ld32(taddr + h * HW + c0, v);
             else tmem_ld16(taddr + h * HW + c0, v);
             const uint32_t sub = stg_addr + (c0 / CW) * (kBM * CW * 4);
+            float4 bv[CW / 4];   // bias reads as one batch ahead of the stores (volatile asm keeps program order)
 #pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              const float4 bv = lds128(sbias_addr + (h * HW + c0 + j) * 4);
-              sts128(sub + chunk_addr(row, j / 4), make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w));
-            }
+            for (int u = 0; u < CW / 4; ++u) bv[u] = lds128(sbias_addr + (h * HW + c0 + 4 * u) * 4);
+#pragma unroll
+            for (int u = 0; u < CW / 4; ++u)
+              sts128(sub + chunk_addr(row, u), make_float4(v[4 * u] + bv[u].x, v[4 * u + 1] + bv[u].y, v[4 * u + 2] + bv[u].z, v[4 * u + 3] + bv[u].w));
           }
           if (g == kG - 1 && h == N / HW - 1) {   // accumulators of this step fully read
             tc_fence_before();
@@ -410,15 +412,27 @@ static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
   if (first_use_on_device(configured))
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  kern<<<grid, X3 ? kThreadsX3 : kThreads, smem_bytes, st>>>(mA, mB, mBlo, mC, bias, a);
+  kern<<<grid, X3 ? kColThreadsX3 : kColThreads, smem_bytes, st>>>(mA, mB, mBlo, mC, bias, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
 
 }  // namespace tc
 
+// The column-tiled kernel wins from F = 4 up in both precisions (128 -> 128 channels, 24 clips, F = 4: 49 us against the
+// row-tiled kernel's 110 us in 3xTF32, 27 against 35 single-pass); at F = 2 its 72 tiles leave half the SMs idle: still
+// ahead in 3xTF32 (49 vs 59 us), behind single-pass (27 vs 23 us) -- tc_conv3x3_stats picks accordingly.
+static int col_min_f() {   // BSED_COL_MIN_F: measurement experiments
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BSED_COL_MIN_F");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 bool tc_conv_col_supported(int F, int Cin, int Cout) {
-  return F >= 8 && F % tc::kG == 0 && Cin % 32 == 0 && (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) &&
+  return F >= col_min_f() && F % tc::kG == 0 && Cin % 32 == 0 && (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) &&
          !getenv("BSED_CONV_ROW_TILES");
 }
 

@@ -235,11 +235,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(&full[s], ph);
         mbar_wait(&loempty[lj], lph ^ 1);
         const uint32_t src = smem_u32(smem + s * S::STAGE), dst = smem_u32(lo + lj * S::A_BYTES);
-#pragma unroll 4
-        for (int i = tid; i < S::A_BYTES / 16; i += kSplitThreads) {
-          const float4 v = lds128(src + i * 16);
-          sts128(dst + i * 16, tf32_lo4(v));
-        }
+        split_lo_range<8>(src, dst, S::A_BYTES / 16, tid);
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         split_barrier();
         if (tid == 0) mbar_arrive(&lofull[lj]);
@@ -323,6 +319,12 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
+      if (a.debug == 5) {   // experiment: accumulators dropped (main-loop time alone)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+      }
       // the staging tile is free once the previous tile's TMA stores have read it (and every thread is done with its
       // statistics pass)
       if (it > 0) {
@@ -333,8 +335,17 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
       for (int c0 = 0; c0 < N; c0 += CW) {
         float v[CW];
-        if constexpr (CW == 32) tmem_ld32(taddr + c0, v);
-        else tmem_ld16(taddr + c0, v);
+        if (a.debug == 6) {   // experiment: no TMEM read
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = 0.f;
+        } else {
+          if constexpr (CW == 32) tmem_ld32(taddr + c0, v);
+          else tmem_ld16(taddr + c0, v);
+        }
+        if (a.debug == 7) {   // experiment: TMEM read only
+          if (v[0] == 123.456f) sts128(stg_addr, make_float4(v[1], v[2], v[3], v[4]));
+          continue;
+        }
         float4 ccur[CW / 4], xcur[CW / 4];
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
@@ -349,22 +360,36 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
         const uint32_t sub = stg_addr + (c0 / CW) * (kBM * CW * 4);
+        // The shared-memory wrappers are volatile asm (program order): table / bias reads are issued as a batch ahead of
+        // the stores, not interleaved with them -- interleaved, every float4 paid a shared-memory round trip and this
+        // loop, not HBM, set the pace of the streaming GEMMs (measured: 117 us with it, 60 us without, M = 963840).
+        if (a.epi == 1) {
 #pragma unroll
-        for (int j = 0; j < CW; j += 4) {
-          float4 o;
-          if (a.epi == 1) {
-            const float4 kk = lds128(tab_addr + (c0 + j) * 4);
-            const float4 m1 = lds128(tab_addr + (N + c0 + j) * 4);
-            const float4 m2 = lds128(tab_addr + (2 * N + c0 + j) * 4);
-            const float4 cv = ccur[j / 4], xv = xcur[j / 4];
-            o = make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
-                            kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w));
-          } else {
-            const float4 bv = lds128(sbias_addr + (ncol0 + c0 + j) * 4);
-            o = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
+          for (int j0 = 0; j0 < CW; j0 += 16) {
+            float4 kk[4], m1[4], m2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              kk[u] = lds128(tab_addr + (c0 + j0 + 4 * u) * 4);
+              m1[u] = lds128(tab_addr + (N + c0 + j0 + 4 * u) * 4);
+              m2[u] = lds128(tab_addr + (2 * N + c0 + j0 + 4 * u) * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + 4 * u;
+              const float4 cv = ccur[j / 4], xv = xcur[j / 4];
+              sts128(sub + chunk_addr(row, j / 4),
+                     make_float4(kk[u].x * (cv.x + v[j] - m1[u].x - xv.x * m2[u].x), kk[u].y * (cv.y + v[j + 1] - m1[u].y - xv.y * m2[u].y),
+                                 kk[u].z * (cv.z + v[j + 2] - m1[u].z - xv.z * m2[u].z),
+                                 kk[u].w * (cv.w + v[j + 3] - m1[u].w - xv.w * m2[u].w)));
+            }
           }
-          sts128(sub + chunk_addr(row, j / 4), o);
-          if (S::STG2_BYTES > 0 && a.epi == 2) {   // gated value into the second staging tile
+        } else if (S::STG2_BYTES > 0 && a.epi == 2) {
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            const float4 bv = lds128(sbias_addr + (ncol0 + c0 + j) * 4);
+            const float4 o = make_float4(v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w);
+            sts128(sub + chunk_addr(row, j / 4), o);
+            // gated value into the second staging tile
             const float4 ga = lds128(smem_u32(stab) + (c0 + j) * 4);
             const float4 be = lds128(smem_u32(stab) + (N + c0 + j) * 4);
             const float4 xv = xcur[j / 4];
@@ -378,6 +403,13 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (!valid) gv[0] = gv[1] = gv[2] = gv[3] = 0.f;
             sts128(smem_u32(stg2) + (c0 / CW) * (kBM * CW * 4) + chunk_addr(row, j / 4), make_float4(gv[0], gv[1], gv[2], gv[3]));
           }
+        } else {
+          float4 bv[CW / 4];
+#pragma unroll
+          for (int u = 0; u < CW / 4; ++u) bv[u] = lds128(sbias_addr + (ncol0 + c0 + 4 * u) * 4);
+#pragma unroll
+          for (int u = 0; u < CW / 4; ++u)
+            sts128(sub + chunk_addr(row, u), make_float4(v[4 * u] + bv[u].x, v[4 * u + 1] + bv[u].y, v[4 * u + 2] + bv[u].z, v[4 * u + 3] + bv[u].w));
         }
       }
       tc_fence_before();
@@ -385,7 +417,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: the next MMAs may overwrite it
       fence_proxy_async();                         // staged tile visible to the TMA (async proxy)
       epi_barrier();
-      if (leader && a.debug != 1 && !(a.epi == 2 && !a.store_lin)) {
+      if (leader && a.debug != 1 && a.debug != 6 && a.debug != 7 && !(a.epi == 2 && !a.store_lin)) {
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += CW) {
           const void* src = stg + (c0 / CW) * (kBM * CW * 4);
@@ -994,7 +1026,7 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
 int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
                      const float* bias, int accumulate, double* stats, int stats_groups, const int* gfirst, int sms,
                      cudaStream_t st) {
-  if (!accumulate && tc_conv_col_supported(F, Cin, Cout))
+  if (!accumulate && tc_conv_col_supported(F, Cin, Cout) && (F >= 4 || Wk_lo != nullptr))
     return tc_conv3x3_col(X, Wk, Wk_lo, Y, B, T, F, Cin, Cout, bias, stats, stats_groups, gfirst, sms, st);
   BSED_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128, "tc_conv3x3: Cin=%d Cout=%d", Cin, Cout);
   BSED_REQUIRE(F >= 1 && F <= 128 && 128 % F == 0, "tc_conv3x3: F=%d must divide 128", F);

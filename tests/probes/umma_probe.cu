@@ -9,6 +9,11 @@
 // MODE 4: MODE 0 with the A tile starting 1 / 2 rows into the 8-row swizzle atom (the halo trick of tc_conv.cu)
 // MODE 5: MODE 0 while warp 0 streams global memory into shared memory with 16 KB bulk copies (what the TMA producer does)
 // MODE 6: MODE 4 + MODE 5
+// MODE 10: the issue pattern of tc_conv_col_kernel<.., X3>: per "tap" elect.sync, 12 MMAs (two accumulators, 3xTF32 triple,
+//          descriptors = base + constant), one tcgen05.commit
+// MODE 11: MODE 10 + what precedes each tap in the kernel: mbarrier wait (already complete), tcgen05.fence, __syncwarp
+// MODE 12: MODE 11 without the per-tap commit
+// MODE 13: MODE 11 issued by TWO warps, one accumulator each (6 MMAs per tap and warp)
 #include <cstdio>
 
 #include "tc_common.cuh"
@@ -24,13 +29,17 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(unsigned long long* out, 
   unsigned char* sB = smem + 2 * A_BYTES;           // two B tiles
   unsigned char* extra = sB + 2 * B_BYTES;          // 32 KB for MODE 3
   uint64_t* bar = reinterpret_cast<uint64_t*>(extra + 32768);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 6);
   __shared__ volatile int stop;
   const int warp = threadIdx.x / 32;
   for (int i = threadIdx.x; i < (2 * A_BYTES + 2 * B_BYTES + 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
+    mbar_init(bar + 2, MODE == 13 ? 2 : 1);
+    mbar_init(bar + 3, 1);
+    mbar_init(bar + 4, 1);
+    mbar_init(bar + 5, 1);
     fence_barrier_init();
     stop = 0;
   }
@@ -40,7 +49,77 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(unsigned long long* out, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (warp == 1) {
+  if ((warp == 1 || warp == 2) && MODE == 13) {
+    constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
+    constexpr uint32_t DHI = kmajor_desc_hi<ROWB>();
+    const int g = warp - 1;
+    uint64_t* tapbar = bar + 2;      // per-tap commits of both warps land here (count 2, nobody waits)
+    uint64_t* ready = bar + 3;
+    uint64_t* fin = bar + 4 + g;
+    const uint32_t a_w = kmajor_desc_lo(smem_u32(sA)), l_w = kmajor_desc_lo(smem_u32(sA) + 128 * ROWB);
+    long long t0 = 0;
+    if (threadIdx.x % 32 == 0) t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t b_w = kmajor_desc_lo(smem_u32(sB) + (it & 1) * 2 * N * ROWB / 2);
+      mbar_wait(ready, 1);
+      tc_fence_after();
+      __syncwarp();
+      if (elect_one()) {
+        const uint32_t aoff = (uint32_t)((it % 3) * ROWB) >> 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_tf32_w(tmem + g * N, a_w + aoff + k * 2, b_w + k * 2, DHI, idesc, 1u);
+          umma_tf32_w(tmem + g * N, a_w + aoff + k * 2, b_w + 4 + k * 2, DHI, idesc, 1u);
+          umma_tf32_w(tmem + g * N, l_w + aoff + k * 2, b_w + k * 2, DHI, idesc, 1u);
+        }
+        umma_commit(tapbar);
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x % 32 == 0) {
+      umma_commit(fin);
+      mbar_wait(fin, 0);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) out[4 + g] = (unsigned long long)(t1 - t0);
+    }
+  } else if (warp == 1 && MODE >= 10) {
+    constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
+    constexpr uint32_t DHI = kmajor_desc_hi<ROWB>();
+    uint64_t* tapbar = bar + 2;      // per-tap commits land here (nobody waits)
+    uint64_t* ready = bar + 3;       // never armed: parity 1 is "complete"
+    const uint32_t a_w = kmajor_desc_lo(smem_u32(sA)), l_w = kmajor_desc_lo(smem_u32(sA) + 128 * ROWB);
+    long long t0 = 0;
+    if (threadIdx.x == 32) t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t b_w = kmajor_desc_lo(smem_u32(sB) + (it & 1) * 2 * N * ROWB / 2);
+      if (MODE >= 11) {
+        mbar_wait(ready, 1);
+        tc_fence_after();
+        __syncwarp();
+      }
+      if (elect_one()) {
+        const uint32_t aoff = (uint32_t)((it % 3) * ROWB) >> 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) umma_tf32_w(tmem + g * N, a_w + aoff + k * 2, b_w + k * 2, DHI, idesc, 1u);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) umma_tf32_w(tmem + g * N, a_w + aoff + k * 2, b_w + 4 + k * 2, DHI, idesc, 1u);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) umma_tf32_w(tmem + g * N, l_w + aoff + k * 2, b_w + k * 2, DHI, idesc, 1u);
+        }
+        if (MODE != 12) umma_commit(tapbar);
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x == 32) {
+      umma_commit(bar);
+      mbar_wait(bar, 0);
+      const long long t1 = clock64();
+      stop = 1;
+      if (blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+    }
+  } else if (warp == 1) {
     constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
     if (elect_one()) {
       const uint32_t a0 = smem_u32(sA), a1 = a0 + A_BYTES, b0 = smem_u32(sB), b1 = b0 + B_BYTES;
@@ -112,7 +191,7 @@ static void run(unsigned long long* d_out, int sms, const unsigned char* src = n
     cudaMemset(g_src, 0, 64u << 20);
   }
   src = g_src;
-  const int iters = 512, per_it = (ROWB / 32) * (MODE == 1 ? 3 : 1);
+  const int iters = 512, per_it = MODE >= 10 ? 12 : (ROWB / 32) * (MODE == 1 ? 3 : 1);
   const size_t smem = 2 * 128 * ROWB + 2 * N * ROWB + 32768 + 64 + 1024;
   auto kern = probe_kernel<N, ROWB, MODE>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -125,9 +204,9 @@ static void run(unsigned long long* d_out, int sms, const unsigned char* src = n
       return;
     }
   }
-  unsigned long long hh[3] = {0, 0, 0};
+  unsigned long long hh[6] = {0, 0, 0, 0, 0, 0};
   cudaMemcpy(hh, d_out, sizeof(hh), cudaMemcpyDeviceToHost);
-  h = hh[0];
+  h = MODE == 13 ? (hh[4] > hh[5] ? hh[4] : hh[5]) : hh[0];
   const double cyc = (double)h / (iters * per_it);
   if (MODE >= 5) printf("   (bulk copies into shared memory meanwhile: %.1f B/clk per SM)\n", (double)hh[2] / (double)h);
   printf("N=%3d rows of %3d B, mode %d: %7.1f clk per MMA (128 x %d x 8; %d MMAs), operand bytes per MMA %d -> %.1f B/clk\n", N, ROWB, MODE,
@@ -162,6 +241,13 @@ int main() {
   run<128, 64, 5>(d_out, sms);
   run<128, 64, 6>(d_out, sms);
   run<64, 64, 6>(d_out, sms);
+  run<128, 64, 10>(d_out, sms);
+  run<128, 64, 11>(d_out, sms);
+  run<128, 64, 12>(d_out, sms);
+  run<128, 64, 13>(d_out, sms);
+  run<64, 64, 13>(d_out, sms);
+  run<64, 64, 10>(d_out, sms);
+  run<64, 64, 11>(d_out, sms);
   run<16, 128, 0>(d_out, sms);
   run<32, 128, 0>(d_out, sms);
   return 0;
