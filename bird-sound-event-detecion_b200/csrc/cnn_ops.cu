@@ -751,7 +751,8 @@ int glu_gate_pool_bwd_sums(const float* xhat, float* lin_dlin, const float* dpoo
 //       tab[g][0][j] = gamma*rstd, tab[g][1][j] = s1/n, tab[g][2][j] = s2/n      (j = p*C + c)
 //   parameter gradients: d_beta += sum_g s1, d_gamma += sum_g s2, d_bg += sum_g A1,
 //                        d_Wg[c'][c] += gamma[c] * sum_g G[g][c'][c] + beta[c] * sum_g A1[g][c']
-__global__ void __launch_bounds__(256) bn_bwd_prepare_kernel(const double* __restrict__ sums, const float* __restrict__ G,
+constexpr int kPrepParts = 4;   // block 0: 512 threads = 128 channels x 4 slices of the c' range
+__global__ void __launch_bounds__(128 * kPrepParts) bn_bwd_prepare_kernel(const double* __restrict__ sums, const float* __restrict__ G,
                                                              int n_groups, int C, Groups g, long long rows_per_clip,
                                                              BNPtrs bn, const float* __restrict__ wg,
                                                              const float* __restrict__ gamma,
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(256) bn_bwd_prepare_kernel(const double* __res
                                                              float* d_wg, float* d_bg) {
   if (blockIdx.x > 0) {
     // d_Wg[c'][c] += gamma[c] * sum_g G[g][c'][c] + beta[c] * sum_g A1[g][c']     (one element per thread)
-    const int i = (blockIdx.x - 1) * 256 + threadIdx.x;
+    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
     if (i >= C * C) return;
     const int cp = i / C, col = i % C;
     float gsum = 0.f;
@@ -772,15 +773,18 @@ __global__ void __launch_bounds__(256) bn_bwd_prepare_kernel(const double* __res
     d_wg[i] += gamma[col] * gsum + beta[col] * (float)a1;
     return;
   }
-  // block 0: per-channel statistics.  Thread (c, part) sums a quarter of the c' range; combined through smem.
-  __shared__ double ps1[kMaxGroups][4][128], ps2[kMaxGroups][4][128];
-  const int c = threadIdx.x % 128, part = threadIdx.x / 128;   // 256 threads: 2 parts ... use 2
+  // block 0: per-channel statistics.  Thread (c, part) sums one slice of the c' range (this launch sits on the critical
+  // path of every block's backward: the loop is latency-bound, so it is cut four ways with its loads in flight together);
+  // combined through smem in a fixed order.
+  __shared__ double ps1[kMaxGroups][kPrepParts][128], ps2[kMaxGroups][kPrepParts][128];
+  const int c = threadIdx.x % 128, part = threadIdx.x / 128;
   if (c < C) {
     for (int gi = 0; gi < n_groups; ++gi) {
       const double* sg = sums + (size_t)gi * C * 4;
       const float* Gg = G + (size_t)gi * C * C;
       double s1 = 0.0, s2 = 0.0;
-      for (int cp = part; cp < C; cp += 2) {
+#pragma unroll 4
+      for (int cp = part; cp < C; cp += kPrepParts) {
         const double w = (double)wg[(size_t)cp * C + c];
         s1 += sg[cp * 4 + 0] * w;
         s2 += w * (double)Gg[(size_t)cp * C + c];
@@ -794,8 +798,12 @@ __global__ void __launch_bounds__(256) bn_bwd_prepare_kernel(const double* __res
   double s1_all = 0.0, s2_all = 0.0, a1_all = 0.0;
   for (int gi = 0; gi < n_groups; ++gi) {
     const double* sg = sums + (size_t)gi * C * 4;
-    const double s1 = sg[c * 4 + 1] + ps1[gi][0][c] + ps1[gi][1][c];
-    const double s2 = sg[c * 4 + 2] + ps2[gi][0][c] + ps2[gi][1][c];
+    double s1 = sg[c * 4 + 1], s2 = sg[c * 4 + 2];
+#pragma unroll
+    for (int p = 0; p < kPrepParts; ++p) {
+      s1 += ps1[gi][p][c];
+      s2 += ps2[gi][p][c];
+    }
     const double n = (double)g.count[gi] * (double)rows_per_clip;
     const float k = bn.gamma[gi][c] * bn.rstd[gi][c];
     for (int p = 0; p < pack; ++p) {
@@ -816,8 +824,9 @@ __global__ void __launch_bounds__(256) bn_bwd_prepare_kernel(const double* __res
 int bn_bwd_prepare(const double* sums, const float* G, int n_groups, int C, const Groups& g, long long rows_per_clip,
                    const BNPtrs& bn, const float* wg, const float* gamma, const float* beta, int pack, float* tab,
                    float* d_gamma, float* d_beta, float* d_wg, float* d_bg, cudaStream_t st) {
-  bn_bwd_prepare_kernel<<<1 + ceil_div(C * C, 256), 256, 0, st>>>(sums, G, n_groups, C, g, rows_per_clip, bn, wg, gamma, beta,
-                                                                  pack, tab, d_gamma, d_beta, d_wg, d_bg);
+  constexpr int threads = 128 * kPrepParts;
+  bn_bwd_prepare_kernel<<<1 + ceil_div(C * C, threads), threads, 0, st>>>(sums, G, n_groups, C, g, rows_per_clip, bn, wg, gamma,
+                                                                          beta, pack, tab, d_gamma, d_beta, d_wg, d_bg);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }

@@ -33,6 +33,12 @@ struct KArgs {
   // epi == 1: BatchNorm-backward epilogue (plain mode): C holds the direct gate path dxd on entry and
   //   dY = k * (dxd + acc - m1 - xhat * m2) on exit; (k, m1, m2) per group and column from `tab` [groups][3][N]
   int epi;
+  // op_ring (epi == 1, N == 64): the two per-element operands (dxd = C on entry, xhat) reach the epilogue through a ring of
+  // kOpSlots shared-memory slots filled by TMA one to two 32-column chunks ahead, and the result is written in place over
+  // the dxd half of the slot and stored from there.  (Read by each thread straight from global memory they arrive one
+  // chunk ahead at best: the epilogue then waits a DRAM round trip per chunk and the kernel runs at half the HBM rate.)
+  int op_ring, ring_extra;   // ring_extra: bytes of the ring beyond the staging tile(s) it overlays
+  const void* mX_host;       // host only: tensor map of xhat (same geometry as C's)
   const float* xh;           // xhat, same shape / leading dimension as C
   const float* tab;
   int tab_groups;
@@ -56,7 +62,9 @@ struct KArgs {
 constexpr int kRbBytes = 72 * 1024;
 
 constexpr int kMaxStages = 24;
-constexpr int kLoBufs = 3;   // 3xTF32: low-part tiles in flight between the splitters and the MMA issuer
+constexpr int kLoBufs = 3;
+constexpr int kOpSlots = 3;                    // operand ring of the BatchNorm-backward epilogue (KArgs::op_ring)
+constexpr int kOpSlotBytes = 2 * kBM * 32 * 4;   // one 128 x 32 chunk of dxd + one of xhat   // 3xTF32: low-part tiles in flight between the splitters and the MMA issuer
 
 // X3 ("3xTF32"): error-compensated fp32-grade products on the tf32 tensor cores.  The activation tile arrives raw; two
 // extra warps write its low part a - tf32(a) into a second tile; the weights come pre-split (hi, lo) from the prep pass;
@@ -75,14 +83,14 @@ struct KSmem {
   static constexpr int TAB_BYTES = kMaxGroups * 3 * 128 * 4;   // BatchNorm-backward table
   static constexpr int BIAS_BYTES = 4096;   // up to 1024 bias values (n_chunks * N)
   static constexpr int FIXED = LO_BYTES + STG_BYTES + STG2_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES + TAB_BYTES;
-  static_assert((2 * kMaxStages + 6 + 2 * kLoBufs) * 8 <= BAR_BYTES, "barrier region too small");
+  static_assert((2 * kMaxStages + 6 + 2 * kLoBufs + kOpSlots) * 8 + 8 <= BAR_BYTES, "barrier region too small");
 };
 
 template <int N, int KCH, bool RB, bool X3>
 __global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
 tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC, float* __restrict__ Y,
-                 const float* __restrict__ bias, KArgs a) {
+                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+                 const __grid_constant__ CUtensorMap mapX, float* __restrict__ Y, const float* __restrict__ bias, KArgs a) {
   using S = KSmem<N, KCH, RB, X3>;
   constexpr int ROWB = KCH * 4;
   constexpr int NT = X3 ? kThreadsX3 : kThreads;
@@ -94,7 +102,8 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   unsigned char* lo = rb + a.rb_bytes;            // low-part activation tiles (X3)
   unsigned char* stg = lo + S::LO_BYTES;          // output staging (1024-byte aligned: every region above is)
   unsigned char* stg2 = stg + S::STG_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg2 + S::STG2_BYTES);
+  unsigned char* after_stg = stg2 + S::STG2_BYTES + a.ring_extra;   // the operand ring overlays stg, stg2 and ring_extra
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_stg);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -102,8 +111,9 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* rbfull = bars + 2 * STAGES + 4;
   uint64_t* lofull = bars + 2 * STAGES + 5;
   uint64_t* loempty = lofull + kLoBufs;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(loempty + kLoBufs);
-  float* sbias = reinterpret_cast<float*>(stg2 + S::STG2_BYTES + S::BAR_BYTES);   // bias staged once per CTA
+  uint64_t* opfull = loempty + kLoBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(opfull + kOpSlots);
+  float* sbias = reinterpret_cast<float*>(after_stg + S::BAR_BYTES);   // bias staged once per CTA
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -122,8 +132,10 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(&lofull[i], 1);
       mbar_init(&loempty[i], 1);
     }
+    for (int i = 0; i < kOpSlots; ++i) mbar_init(&opfull[i], 1);
     mbar_init(rbfull, 1);
     fence_barrier_init();
+    if (a.op_ring) prefetch_tmap(&mapX);
   }
   for (int i = threadIdx.x; i < N * a.n_chunks; i += NT) sbias[i] = bias ? bias[i] : 0.f;
   float* stab = sbias + S::BIAS_BYTES / 4;
@@ -274,6 +286,24 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       st_sum = st_sq = 0.0;
     };
+    // ---- operand ring of the BatchNorm-backward epilogue (a.op_ring): chunk n = 32-column block (n % NCH) of this CTA's
+    // tile number n / NCH lives in slot n % kOpSlots; the leader requests chunk n + kOpSlots - 1 right after it has
+    // handed chunk n's result to the TMA store (the slot it refills is the one whose store was committed one chunk earlier)
+    constexpr int NCH = N / CW;
+    const bool ring = a.op_ring != 0;
+    const uint32_t ring_addr = stg_addr;
+    int opn = 0;
+    auto request_ops = [&](int n) {
+      const int tl = blockIdx.x + (n / NCH) * gridDim.x;
+      if (tl >= a.n_tiles) return;
+      const int slot = n % kOpSlots;
+      unsigned char* dst = stg + slot * kOpSlotBytes;
+      mbar_expect_tx(&opfull[slot], kOpSlotBytes);
+      tma_load_2d(&mapC, dst, &opfull[slot], (n % NCH) * CW, tl * kBM);
+      tma_load_2d(&mapX, dst + kOpSlotBytes / 2, &opfull[slot], (n % NCH) * CW, tl * kBM);
+    };
+    if (ring && leader)
+      for (int n = 0; n < kOpSlots - 1; ++n) request_ops(n);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -297,7 +327,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       // operands of the BatchNorm-backward epilogue: requested before the accumulator is awaited, next chunk's while
       // the current one is combined
-      const bool bn_rd = (a.epi == 1 || a.epi == 2) && valid;   // operands read per element: (dxd, xhat) / xhat
+      const bool bn_rd = (a.epi == 1 || a.epi == 2) && valid && !ring;   // operands read per element: (dxd, xhat) / xhat
       const float* yrow = Y + grow * a.ldc;
       const float* xrow = a.xh + grow * a.ldc;
       uint32_t tab_addr = 0;
@@ -327,7 +357,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       // the staging tile is free once the previous tile's TMA stores have read it (and every thread is done with its
       // statistics pass)
-      if (it > 0) {
+      if (it > 0 && !ring) {
         if (leader) bulk_wait_read0();
         epi_barrier();
       }
@@ -344,6 +374,50 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         if (a.debug == 7) {   // experiment: TMEM read only
           if (v[0] == 123.456f) sts128(stg_addr, make_float4(v[1], v[2], v[3], v[4]));
+          continue;
+        }
+        if (ring) {
+          if constexpr (CW == 32) {
+            const int slot = opn % kOpSlots;
+            mbar_wait(&opfull[slot], (opn / kOpSlots) & 1);
+            const uint32_t dxd_addr = ring_addr + slot * kOpSlotBytes, xh_addr = dxd_addr + kOpSlotBytes / 2;
+#pragma unroll
+            for (int j0 = 0; j0 < CW; j0 += 8) {   // two float4 per batch: reads first, then the in-place stores
+              float4 kk[2], m1[2], m2[2], cv[2], xv[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int j = j0 + 4 * u;
+                kk[u] = lds128(tab_addr + (c0 + j) * 4);
+                m1[u] = lds128(tab_addr + (N + c0 + j) * 4);
+                m2[u] = lds128(tab_addr + (2 * N + c0 + j) * 4);
+                cv[u] = lds128(dxd_addr + chunk_addr(row, j / 4));
+                xv[u] = lds128(xh_addr + chunk_addr(row, j / 4));
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int j = j0 + 4 * u;
+                sts128(dxd_addr + chunk_addr(row, j / 4),
+                       make_float4(kk[u].x * (cv[u].x + v[j] - m1[u].x - xv[u].x * m2[u].x),
+                                   kk[u].y * (cv[u].y + v[j + 1] - m1[u].y - xv[u].y * m2[u].y),
+                                   kk[u].z * (cv[u].z + v[j + 2] - m1[u].z - xv[u].z * m2[u].z),
+                                   kk[u].w * (cv[u].w + v[j + 3] - m1[u].w - xv[u].w * m2[u].w)));
+              }
+            }
+            if (c0 + CW >= N) {   // accumulator fully read
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            fence_proxy_async();
+            epi_barrier();
+            if (leader) {
+              if (a.debug != 1) tma_store_2d(&mapC, stg + slot * kOpSlotBytes, c0, mt * kBM, false);
+              bulk_commit();
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // chunk opn - 1's store has left its slot
+              request_ops(opn + kOpSlots - 1);
+            }
+            ++opn;
+          }
           continue;
         }
         float4 ccur[CW / 4], xcur[CW / 4];
@@ -363,25 +437,16 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // The shared-memory wrappers are volatile asm (program order): table / bias reads are issued as a batch ahead of
         // the stores, not interleaved with them -- interleaved, every float4 paid a shared-memory round trip and this
         // loop, not HBM, set the pace of the streaming GEMMs (measured: 117 us with it, 60 us without, M = 963840).
-        if (a.epi == 1) {
+        if (a.epi == 1) {   // paced by its two global operands per element: the per-float4 order is the faster one here
 #pragma unroll
-          for (int j0 = 0; j0 < CW; j0 += 16) {
-            float4 kk[4], m1[4], m2[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              kk[u] = lds128(tab_addr + (c0 + j0 + 4 * u) * 4);
-              m1[u] = lds128(tab_addr + (N + c0 + j0 + 4 * u) * 4);
-              m2[u] = lds128(tab_addr + (2 * N + c0 + j0 + 4 * u) * 4);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int j = j0 + 4 * u;
-              const float4 cv = ccur[j / 4], xv = xcur[j / 4];
-              sts128(sub + chunk_addr(row, j / 4),
-                     make_float4(kk[u].x * (cv.x + v[j] - m1[u].x - xv.x * m2[u].x), kk[u].y * (cv.y + v[j + 1] - m1[u].y - xv.y * m2[u].y),
-                                 kk[u].z * (cv.z + v[j + 2] - m1[u].z - xv.z * m2[u].z),
-                                 kk[u].w * (cv.w + v[j + 3] - m1[u].w - xv.w * m2[u].w)));
-            }
+          for (int j = 0; j < CW; j += 4) {
+            const float4 kk = lds128(tab_addr + (c0 + j) * 4);
+            const float4 m1 = lds128(tab_addr + (N + c0 + j) * 4);
+            const float4 m2 = lds128(tab_addr + (2 * N + c0 + j) * 4);
+            const float4 cv = ccur[j / 4], xv = xcur[j / 4];
+            sts128(sub + chunk_addr(row, j / 4),
+                   make_float4(kk.x * (cv.x + v[j] - m1.x - xv.x * m2.x), kk.y * (cv.y + v[j + 1] - m1.y - xv.y * m2.y),
+                               kk.z * (cv.z + v[j + 2] - m1.z - xv.z * m2.z), kk.w * (cv.w + v[j + 3] - m1.w - xv.w * m2.w)));
           }
         } else if (S::STG2_BYTES > 0 && a.epi == 2) {
 #pragma unroll
@@ -412,6 +477,7 @@ tc_kmajor_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             sts128(sub + chunk_addr(row, u), make_float4(v[4 * u] + bv[u].x, v[4 * u + 1] + bv[u].y, v[4 * u + 2] + bv[u].z, v[4 * u + 3] + bv[u].w));
         }
       }
+      if (ring) continue;   // stored chunk by chunk above
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: the next MMAs may overwrite it
@@ -493,20 +559,27 @@ static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
   // need tens of KB of loads in flight per SM to cover the HBM latency
   using S = KSmem<N, KCH, RB, X3>;
   a.rb_bytes = RB ? S::NB * a.ntaps * a.cpt * S::B_STRIDE : 0;
-  int stages = (kSmemMax - S::FIXED - a.rb_bytes) / S::STAGE;
+  a.ring_extra = 0;
+  if (a.op_ring) {   // the operand ring overlays the staging tile(s); it needs a 4-stage A ring beside it
+    const int extra = kOpSlots * kOpSlotBytes - S::STG_BYTES - S::STG2_BYTES;
+    a.ring_extra = extra > 0 ? extra : 0;
+    if (N != 64 || (kSmemMax - S::FIXED - a.rb_bytes - a.ring_extra) / S::STAGE < 4) a.op_ring = a.ring_extra = 0;
+  }
+  int stages = (kSmemMax - S::FIXED - a.rb_bytes - a.ring_extra) / S::STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     bsed_set_error("tc gemm: no room for a 2-stage ring (N=%d KCH=%d rb=%d x3=%d)", N, KCH, a.rb_bytes, (int)X3);
     return BSED_E_INVALID;
   }
   a.stages = stages;
-  const int total = stages * S::STAGE + a.rb_bytes + S::FIXED;
+  const int total = stages * S::STAGE + a.rb_bytes + S::FIXED + a.ring_extra;
   auto kern = tc_kmajor_kernel<N, KCH, RB, X3>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured))
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   int grid = a.n_tiles < sms ? a.n_tiles : sms;
-  kern<<<grid, X3 ? kThreadsX3 : kThreads, total, st>>>(mA, mB, mBlo, mC, Y, bias, a);
+  const CUtensorMap& mX = a.op_ring ? *static_cast<const CUtensorMap*>(a.mX_host) : mC;
+  kern<<<grid, X3 ? kThreadsX3 : kThreads, total, st>>>(mA, mB, mBlo, mC, mX, Y, bias, a);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
@@ -1049,6 +1122,8 @@ int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float*
   cuuint32_t bC[4] = {(cuuint32_t)CW, (cuuint32_t)F, (cuuint32_t)th, 1};
   BSED_TRY(tc::make_map(&mC, Y, 4, dC, sC, bC, CW * 4, true));
   tc::KArgs a;
+  a.op_ring = a.ring_extra = 0;
+  a.mX_host = nullptr;
   a.plain = 0;
   a.tiles_per_clip = (T + th - 1) / th;
   a.n_tiles = a.tiles_per_clip * B;
@@ -1104,7 +1179,9 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float
                    ldc % 4 == 0 && (n_chunks == 1 || !bnb),
                "tc_gemm_nt: M=%lld N=%d K=%d", M, N_total, K);
   const bool x3 = Bk_lo != nullptr;
-  const int KCH = tc::pick_kch(K, N, 1, x3);
+  // BatchNorm-backward epilogue on 64 columns: operand ring (KArgs::op_ring); in 3xTF32 it fits beside 16-channel chunks only
+  const bool op_ring = bnb && N_total == 64 && !accumulate && !getenv("BSED_NO_OP_RING");
+  const int KCH = (op_ring && x3) ? 16 : tc::pick_kch(K, N, 1, x3);
   CUtensorMap mA, mB, mBlo;
   cuuint64_t dA[2] = {(cuuint64_t)K, (cuuint64_t)M};
   cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
@@ -1121,7 +1198,11 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float
   cuuint64_t sC[1] = {(cuuint64_t)ldc * 4};
   cuuint32_t bC[2] = {(cuuint32_t)CW, 128};
   BSED_TRY(tc::make_map(&mC, C, 2, dC, sC, bC, CW * 4, true));
+  CUtensorMap mX = mC;
+  if (op_ring) BSED_TRY(tc::make_map(&mX, bnb->xhat, 2, dC, sC, bC, CW * 4, true));
   tc::KArgs a;
+  a.op_ring = op_ring ? 1 : 0;
+  a.mX_host = &mX;
   a.plain = 1;
   a.n_chunks = n_chunks;
   a.n_tiles = (int)((M + 127) / 128) * n_chunks;
@@ -1179,6 +1260,8 @@ int tc_glu_gate_fwd(const float* xhat, const float* Wk, const float* bias, const
   BSED_TRY(tc::make_map(&mB, Wk, 2, dB, sB, bB, 128));
   BSED_TRY(tc::make_map(&mC, lin, 4, dA, sA, bA, 128, true));
   tc::KArgs a;
+  a.op_ring = a.ring_extra = 0;
+  a.mX_host = nullptr;
   a.plain = 0;
   a.tiles_per_clip = (T + th - 1) / th;
   a.n_tiles = a.tiles_per_clip * B;
