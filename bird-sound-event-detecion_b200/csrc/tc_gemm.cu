@@ -33,7 +33,7 @@ struct KArgs {
   // epi == 1: BatchNorm-backward epilogue (plain mode): C holds the direct gate path dxd on entry and
   //   dY = k * (dxd + acc - m1 - xhat * m2) on exit; (k, m1, m2) per group and column from `tab` [groups][3][N]
   int epi;
-  // op_ring (epi == 1, N == 64): the two per-element operands (dxd = C on entry, xhat) reach the epilogue through a ring of
+  // op_ring (epi == 1, N == 64 or 128): the two per-element operands (dxd = C on entry, xhat) reach the epilogue through a ring of
   // kOpSlots shared-memory slots filled by TMA one to two 32-column chunks ahead, and the result is written in place over
   // the dxd half of the slot and stored from there.  (Read by each thread straight from global memory they arrive one
   // chunk ahead at best: the epilogue then waits a DRAM round trip per chunk and the kernel runs at half the HBM rate.)
@@ -563,7 +563,9 @@ static int launch_k2(const CUtensorMap& mA, const CUtensorMap& mB, const CUtenso
   if (a.op_ring) {   // the operand ring overlays the staging tile(s); it needs a 4-stage A ring beside it
     const int extra = kOpSlots * kOpSlotBytes - S::STG_BYTES - S::STG2_BYTES;
     a.ring_extra = extra > 0 ? extra : 0;
-    if (N != 64 || (kSmemMax - S::FIXED - a.rb_bytes - a.ring_extra) / S::STAGE < 4) a.op_ring = a.ring_extra = 0;
+    const int min_stages = N == 64 ? 4 : 3;
+    if ((N != 64 && N != 128) || (kSmemMax - S::FIXED - a.rb_bytes - a.ring_extra) / S::STAGE < min_stages)
+      a.op_ring = a.ring_extra = 0;
   }
   int stages = (kSmemMax - S::FIXED - a.rb_bytes - a.ring_extra) / S::STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1179,8 +1181,9 @@ static int tc_gemm_nt_impl(const float* A, int lda, const float* Bk, const float
                    ldc % 4 == 0 && (n_chunks == 1 || !bnb),
                "tc_gemm_nt: M=%lld N=%d K=%d", M, N_total, K);
   const bool x3 = Bk_lo != nullptr;
-  // BatchNorm-backward epilogue on 64 columns: operand ring (KArgs::op_ring); in 3xTF32 it fits beside 16-channel chunks only
-  const bool op_ring = bnb && N_total == 64 && !accumulate && !getenv("BSED_NO_OP_RING");
+  // BatchNorm-backward epilogue on 64 / 128 columns: operand ring (KArgs::op_ring); in 3xTF32 it fits beside 16-channel
+  // chunks only
+  const bool op_ring = bnb && (N_total == 64 || N_total == 128) && !accumulate && !getenv("BSED_NO_OP_RING");
   const int KCH = (op_ring && x3) ? 16 : tc::pick_kch(K, N, 1, x3);
   CUtensorMap mA, mB, mBlo;
   cuuint64_t dA[2] = {(cuuint64_t)K, (cuuint64_t)M};
