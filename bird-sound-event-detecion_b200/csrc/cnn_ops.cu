@@ -25,7 +25,7 @@ __device__ __forceinline__ int group_of(const Groups& g, int clip) {
 // statistics) are accumulated on the way: stats[(group * Cout + c) * 2 + {0, 1}].
 // grid (column blocks x row strips, clip); block = 256 threads = (256 / nq) columns x nq quads.
 // ---------------------------------------------------------------------------------------------
-constexpr int kConv0Rows = 32;   // rows per strip
+constexpr int kConv0Rows = 64;   // rows per strip
 
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ x, Groups g, FloatPtrs w,
                                                         FloatPtrs bias, float* __restrict__ y, int T, int F,
@@ -97,24 +97,37 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
     }
   }
   if (!stats) return;
-  __shared__ float red[2][256][4];
+  // threads with equal q inside a warp (lanes l, l + nq, ...) first, then the 8 warps through shared memory: the serial
+  // 64-column sum this replaces was a third of the CTA's time
+  __shared__ float red[2][8][128];   // [sum | sum of squares][warp][channel], Cout <= 128
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    red[0][threadIdx.x][j] = s1[j];
-    red[1][threadIdx.x][j] = s2[j];
+    for (int o = 16; o >= nq; o >>= 1) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+    }
+  }
+  if (lane < nq) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[0][warp][lane * 4 + j] = s1[j];
+      red[1][warp][lane * 4 + j] = s2[j];
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * Cout; i += 256) {
     const int k = i / Cout, c = i % Cout;
     float tsum = 0.f;
-    for (int r = 0; r < cols_per_cta; ++r) tsum += red[k][r * nq + c / 4][c % 4];
+#pragma unroll
+    for (int wdx = 0; wdx < 8; ++wdx) tsum += red[k][wdx][c];
     atomicAdd(stats + ((size_t)grp * Cout + c) * 2 + k, (double)tsum);
   }
 }
 
 int conv0_fwd(const float* x, const Groups& g, const FloatPtrs& w, const FloatPtrs& bias, float* y, int T,
               int F, int Cout, double* stats, int num_sms, cudaStream_t st) {
-  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128 && 256 % (Cout / 4) == 0, "conv0: Cout=%d", Cout);
+  BSED_REQUIRE(Cout % 4 == 0 && Cout <= 128 && 32 % (Cout / 4) == 0, "conv0: Cout=%d", Cout);
   (void)num_sms;
   int B = g.first[g.n - 1] + g.count[g.n - 1];
   const int cols_per_cta = 256 / (Cout / 4);
@@ -156,20 +169,21 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
         r[0] = r[1] = r[2] = 0.f;
       }
     };
-    float rw[6][3];
+    constexpr int R = 8;   // rows of gradient and of input in flight before the FMAs (the kernel streams dY: bytes in flight)
+    float rw[R + 2][3];
     load_row(t0 - 1, rw[0]);
     load_row(t0, rw[1]);
     const float* dp = dY + (((size_t)clip * T + t0) * F + col) * Cout + q * 4;
-    for (int t = t0; t < t1; t += 4) {
-      float4 d[4];
+    for (int t = t0; t < t1; t += R) {
+      float4 d[R];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {     // four rows of gradient and of input in flight before the FMAs
+      for (int u = 0; u < R; ++u) {
         load_row(t + 1 + u, rw[2 + u]);
         d[u] = t + u < t1 ? *reinterpret_cast<const float4*>(dp + (size_t)u * F * Cout) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      dp += (size_t)4 * F * Cout;
+      dp += (size_t)R * F * Cout;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < R; ++u) {
         const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -182,8 +196,8 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        rw[0][k] = rw[4][k];
-        rw[1][k] = rw[5][k];
+        rw[0][k] = rw[R][k];
+        rw[1][k] = rw[R + 1][k];
       }
     }
   }
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   if (rend > rows_per_clip) rend = rows_per_clip;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   if (r0 < rstep) {
-    constexpr int U = 2;   // rows in flight per thread
+    constexpr int U = 4;   // rows in flight per thread
     const float* abase = a + (size_t)clip * rows_per_clip * C + q * 4;
     const float* bbase = MODE == 1 ? b + (size_t)clip * rows_per_clip * C + q * 4 : nullptr;
     for (long long r = rbeg + r0; r < rend; r += (long long)U * rstep) {
@@ -303,10 +317,11 @@ int col_stats(const float* a, const float* b, int mode, const Groups& g, long lo
   int nclips = 0;
   for (int i = 0; i < g.n; ++i) nclips += g.count[i];
   if (nclips == 0) return BSED_OK;
-  // aim for ~8 CTAs per SM overall, at least 64 rows per CTA
+  // aim for ~8 CTAs per SM overall, at least 16 rows per CTA (the short, wide matrices of the GRU backward -- 7512 x 768 --
+  // are latency-bound: with 64 rows per CTA every thread walked 32 dependent load rounds, 21 us per launch)
   long long want = (long long)num_sms * 8 / nclips + 1;
   long long rows_per_cta = (rows_per_clip + want - 1) / want;
-  if (rows_per_cta < 64) rows_per_cta = 64;
+  if (rows_per_cta < 16) rows_per_cta = 16;
   dim3 grid(ceil_div(rows_per_clip, rows_per_cta), nclips);
   int threads = (C / 4) * (256 / (C / 4));  // a multiple of the quads per row, <= 256
   if (mode == 0) col_stats_kernel<0><<<grid, threads, 0, st>>>(a, b, g, rows_per_clip, C, rows_per_cta, out);

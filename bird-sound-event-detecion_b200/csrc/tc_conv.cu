@@ -19,7 +19,7 @@
 namespace bsed {
 namespace tc {
 
-constexpr int kG = 2;               // frequency bins per CTA step
+constexpr int kG = 2;               // frequency bins per CTA step (template G: 1 where 2 would leave half the SMs idle)
 constexpr int kHaloRows = 130;      // t0-1 .. t0+128
 constexpr int kHaloPad = 136;       // rows of one column copy, padded to the 8-row swizzle repeat
 constexpr int kAStages = 2;
@@ -53,12 +53,12 @@ __device__ __forceinline__ uint64_t kmajor_desc_rows(uint32_t smem_addr) {
          (layout << 61);
 }
 
-template <int N, bool X3>
+template <int N, bool X3, int G = kG>
 struct CSmem {
   static constexpr int KCH = X3 ? 16 : 32;
   static constexpr int ROWB = KCH * 4;
   static constexpr int A_COPY = kHaloPad * ROWB;                      // one column copy (17 KB / 8.5 KB)
-  static constexpr int A_STAGE = (kG + 2) * A_COPY;
+  static constexpr int A_STAGE = (G + 2) * A_COPY;
   static constexpr int LO_BYTES = X3 ? kAStages * A_STAGE : 0;        // low parts, one set per stage
   static constexpr int B_TILE = N * KCH * 4;                          // one tap, one chunk
   static constexpr int B_STRIDE = (B_TILE + 1023) / 1024 * 1024;
@@ -70,15 +70,15 @@ struct CSmem {
   static constexpr int BAR_BYTES = 512;
 };
 
-template <int N, bool X3>
+template <int N, bool X3, int G>
 __global__ void __launch_bounds__(X3 ? kColThreadsX3 : kColThreads, 1)
 tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
                    const float* __restrict__ bias, CArgs a) {
-  using S = CSmem<N, X3>;
+  using S = CSmem<N, X3, G>;
   constexpr int KCH = S::KCH;
   constexpr int ROWB = S::ROWB;
-  constexpr uint32_t TMEM_COLS = (2 * kG * N <= 64) ? 64 : (2 * kG * N <= 128) ? 128 : (2 * kG * N <= 256) ? 256 : 512;
+  constexpr uint32_t TMEM_COLS = (2 * G * N <= 64) ? 64 : (2 * G * N <= 128) ? 128 : (2 * G * N <= 256) ? 256 : 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nk = 9 * a.cpt;
@@ -105,15 +105,15 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     prefetch_tmap(&mapC);
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(&afull[s], 1);
-      mbar_init(&aempty[s], kG);        // one tcgen05.commit per issuer warp
+      mbar_init(&aempty[s], G);         // one tcgen05.commit per issuer warp
       mbar_init(&lofull[s], 1);
     }
     for (int s = 0; s < 16; ++s) {
       mbar_init(&bfull[s], 1);
-      mbar_init(&bempty[s], kG);
+      mbar_init(&bempty[s], G);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], kG);
+      mbar_init(&tfull[i], G);
       mbar_init(&tempty[i], 4);
     }
     mbar_init(rbfull, 1);
@@ -157,10 +157,10 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (a_copy > 0 || mbar_test(&aempty[stage], ((a_step / kAStages) & 1) ^ 1)) {
             const int tile = blockIdx.x + (a_step / a.cpt) * gridDim.x, ch = a_step % a.cpt;
             const int b = tile / per_clip, r = tile - b * per_clip;
-            const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
-            if (a_copy == 0) mbar_expect_tx(&afull[stage], (kG + 2) * kHaloRows * KCH * 4);
+            const int f0 = (r / a.tblocks) * G, t0 = (r % a.tblocks) * kBM;
+            if (a_copy == 0) mbar_expect_tx(&afull[stage], (G + 2) * kHaloRows * KCH * 4);
             tma_load_4d(&mapA, smem + stage * S::A_STAGE + a_copy * S::A_COPY, &afull[stage], ch * KCH, f0 - 1 + a_copy, t0 - 1, b);
-            if (++a_copy == kG + 2) {
+            if (++a_copy == G + 2) {
               a_copy = 0;
               ++a_step;
             }
@@ -190,7 +190,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         else if (++idle > kSpinLimit) __trap();
       }
     }
-  } else if (warp == 1 || warp == 6) {
+  } else if (warp == 1 || (warp == 6 && G == 2)) {
     // ===================== MMA issuers: bin g = 0 (warp 1), g = 1 (warp 6) =====================
     const int g = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = idesc_tf32(N, 0, 0);
@@ -210,7 +210,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // descriptor low words ((address >> 4) | LBO): every tile of the step is these plus a compile-time constant
         const uint32_t a_w = kmajor_desc_lo(smem_u32(smem + sa * S::A_STAGE + g * S::A_COPY));
         const uint32_t l_w = kmajor_desc_lo(smem_u32(alo + sa * S::A_STAGE + g * S::A_COPY));
-        const uint32_t d_tmem = tmem_base + (ab * kG + g) * N;
+        const uint32_t d_tmem = tmem_base + (ab * G + g) * N;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dt = tap / 3 - 1, df = tap % 3 - 1;
@@ -253,6 +253,8 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
       }
     }
+  } else if (warp == 6) {
+    // G == 1: no second accumulator, no second issuer
   } else if (X3 && warp >= 7) {
     // ===================== operand splitters (warps 7..8, 3xTF32) =====================
     // lo[sa] is free whenever A[sa] is: a stage is refilled only after the MMAs that read both have completed
@@ -305,7 +307,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const int ab = it & 1;
       const uint32_t ab_ph = (it >> 1) & 1;
       const int b = tile / per_clip, r = tile - b * per_clip;
-      const int f0 = (r / a.tblocks) * kG, t0 = (r % a.tblocks) * kBM;
+      const int f0 = (r / a.tblocks) * G, t0 = (r % a.tblocks) * kBM;
       const int valid_rows = a.T - t0 < kBM ? a.T - t0 : kBM;
       if (a.stats) {
         int gi = 0;
@@ -325,8 +327,8 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (lane == 0) mbar_arrive(&tempty[ab]);
         continue;
       }
-      for (int g = 0; g < kG; ++g) {
-        const uint32_t taddr = tmem_base + (ab * kG + g) * N + ((uint32_t)(q * 32) << 16);
+      for (int g = 0; g < G; ++g) {
+        const uint32_t taddr = tmem_base + (ab * G + g) * N + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int h = 0; h < N / HW; ++h, ++pass_no) {
           if (pass_no > 0) {      // staging free: previous TMA stores have read it, statistics pass finished
@@ -346,7 +348,7 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             for (int u = 0; u < CW / 4; ++u)
               sts128(sub + chunk_addr(row, u), make_float4(v[4 * u] + bv[u].x, v[4 * u + 1] + bv[u].y, v[4 * u + 2] + bv[u].z, v[4 * u + 3] + bv[u].w));
           }
-          if (g == kG - 1 && h == N / HW - 1) {   // accumulators of this step fully read
+          if (g == G - 1 && h == N / HW - 1) {   // accumulators of this step fully read
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -383,10 +385,10 @@ tc_conv_col_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int N, bool X3>
+template <int N, bool X3, int G>
 static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
                       const float* bias, CArgs& a, int sms, cudaStream_t st) {
-  using S = CSmem<N, X3>;
+  using S = CSmem<N, X3, G>;
   const int nk = 9 * a.cpt;
   const long long fixed = (long long)kAStages * S::A_STAGE + S::LO_BYTES + S::STG_BYTES + S::BAR_BYTES + 512 + 1024;
   const long long budget = 227 * 1024 - fixed;
@@ -407,7 +409,7 @@ static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
     }
   }
   const size_t smem_bytes = (size_t)(fixed + (long long)(a.rb ? nk : a.bstages) * S::B_SLOT);
-  auto kern = tc_conv_col_kernel<N, X3>;
+  auto kern = tc_conv_col_kernel<N, X3, G>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured))
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -419,9 +421,8 @@ static int launch_col(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
 
 }  // namespace tc
 
-// The column-tiled kernel wins from F = 4 up in both precisions (128 -> 128 channels, 24 clips, F = 4: 49 us against the
-// row-tiled kernel's 110 us in 3xTF32, 27 against 35 single-pass); at F = 2 its 72 tiles leave half the SMs idle: still
-// ahead in 3xTF32 (49 vs 59 us), behind single-pass (27 vs 23 us) -- tc_conv3x3_stats picks accordingly.
+// The column-tiled kernel wins from F = 2 up in both precisions (128 -> 128 channels, 24 clips: F = 4 49 us against the
+// row-tiled kernel's 110 us in 3xTF32, 27 against 35 single-pass; F = 2 with one bin per step 37 against 59 and 21 against 23).
 static int col_min_f() {   // BSED_COL_MIN_F: measurement experiments
   static int v = -1;
   if (v < 0) {
@@ -432,7 +433,7 @@ static int col_min_f() {   // BSED_COL_MIN_F: measurement experiments
 }
 
 bool tc_conv_col_supported(int F, int Cin, int Cout) {
-  return F >= col_min_f() && F % tc::kG == 0 && Cin % 32 == 0 && (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) &&
+  return F >= col_min_f() && (F % tc::kG == 0 || Cout == 128) && Cin % 32 == 0 && (Cout == 16 || Cout == 32 || Cout == 64 || Cout == 128) &&
          !getenv("BSED_CONV_ROW_TILES");
 }
 
@@ -459,8 +460,10 @@ int tc_conv3x3_col(const float* X, const float* Wk, const float* Wk_lo, float* Y
   cuuint32_t bC[4] = {(cuuint32_t)CW, 1, 128, 1};
   BSED_TRY(tc::make_map(&mC, Y, 4, dC, sC, bC, CW * 4, true));
   tc::CArgs a;
-  a.fgroups = F / tc::kG;
+  // one bin per CTA step (G = 1, 128 output channels only) where two would leave half of the SMs without a tile
   a.tblocks = (T + 127) / 128;
+  const bool g1 = Cout == 128 && (F % tc::kG != 0 || 2 * B * (F / tc::kG) * a.tblocks <= sms) && !getenv("BSED_COL_G2");
+  a.fgroups = g1 ? F : F / tc::kG;
   a.n_tiles = B * a.fgroups * a.tblocks;
   a.T = T;
   a.F = F;
@@ -477,17 +480,21 @@ int tc_conv3x3_col(const float* X, const float* Wk, const float* Wk_lo, float* Y
                  4.0 * ((double)B * T * F * Cin + (double)B * T * F * Cout + algo * 9.0 * Cin * Cout), st);
   if (x3) {
     switch (Cout) {
-      case 16: return tc::launch_col<16, true>(mA, mB, mBlo, mC, bias, a, sms, st);
-      case 32: return tc::launch_col<32, true>(mA, mB, mBlo, mC, bias, a, sms, st);
-      case 64: return tc::launch_col<64, true>(mA, mB, mBlo, mC, bias, a, sms, st);
-      default: return tc::launch_col<128, true>(mA, mB, mBlo, mC, bias, a, sms, st);
+      case 16: return tc::launch_col<16, true, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+      case 32: return tc::launch_col<32, true, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+      case 64: return tc::launch_col<64, true, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+      default:
+        return g1 ? tc::launch_col<128, true, 1>(mA, mB, mBlo, mC, bias, a, sms, st)
+                  : tc::launch_col<128, true, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
     }
   }
   switch (Cout) {
-    case 16: return tc::launch_col<16, false>(mA, mB, mBlo, mC, bias, a, sms, st);
-    case 32: return tc::launch_col<32, false>(mA, mB, mBlo, mC, bias, a, sms, st);
-    case 64: return tc::launch_col<64, false>(mA, mB, mBlo, mC, bias, a, sms, st);
-    default: return tc::launch_col<128, false>(mA, mB, mBlo, mC, bias, a, sms, st);
+    case 16: return tc::launch_col<16, false, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+    case 32: return tc::launch_col<32, false, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+    case 64: return tc::launch_col<64, false, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
+    default:
+      return g1 ? tc::launch_col<128, false, 1>(mA, mB, mBlo, mC, bias, a, sms, st)
+                : tc::launch_col<128, false, 2>(mA, mB, mBlo, mC, bias, a, sms, st);
   }
 }
 

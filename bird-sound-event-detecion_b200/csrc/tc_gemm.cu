@@ -1101,7 +1101,7 @@ static int launch_w(const CUtensorMap& mA, const CUtensorMap& mB, float* part, c
 int tc_conv3x3_stats(const float* X, const float* Wk, const float* Wk_lo, float* Y, int B, int T, int F, int Cin, int Cout,
                      const float* bias, int accumulate, double* stats, int stats_groups, const int* gfirst, int sms,
                      cudaStream_t st) {
-  if (!accumulate && tc_conv_col_supported(F, Cin, Cout) && (F >= 4 || Wk_lo != nullptr))
+  if (!accumulate && tc_conv_col_supported(F, Cin, Cout))
     return tc_conv3x3_col(X, Wk, Wk_lo, Y, B, T, F, Cin, Cout, bias, stats, stats_groups, gfirst, sms, st);
   BSED_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128, "tc_conv3x3: Cin=%d Cout=%d", Cin, Cout);
   BSED_REQUIRE(F >= 1 && F <= 128 && 128 % F == 0, "tc_conv3x3: F=%d must divide 128", F);

@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python tests/prof_step.py --steps 1 --warmup 3 > gpurun_out/plain_q.log 2>&1 && \
-BSED_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r02q_x3.csv python tests/prof_step.py --steps 1 --warmup 3 > gpurun_out/ncu_q1.log 2>&1
-du -sh gpurun_out
+(timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/gpu_all_t.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_all_t.log)
+(timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_t.json 2> gpurun_out/bench_t.err; echo "rc=$?" >> gpurun_out/bench_t.err)
+(BSED_WGRAD_ASIDE=1 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_t_aside.json 2> gpurun_out/bench_t_aside.err; echo "rc=$?" >> gpurun_out/bench_t_aside.err)
