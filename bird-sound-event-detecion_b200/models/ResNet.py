@@ -151,9 +151,10 @@ class Net_resnet(_FlatModule):
         """eval-mode BatchNorm folded into the convolution."""
         with torch.no_grad():
             scale = bn.weight / torch.sqrt(bn.running_var + self.BN_EPS)
-            wk, K, kpad = self._pack(conv.weight * scale[:, None, None, None])
+            w4 = (conv.weight * scale[:, None, None, None]).float().contiguous()
+            wk, K, kpad = self._pack(w4)
             bias = (bn.bias - bn.running_mean * scale).float().contiguous()
-            return dict(wk=wk, wkT=wk.t().contiguous(), bias=bias, kpad=kpad)
+            return dict(wk=wk, wkT=wk.t().contiguous(), bias=bias, kpad=kpad, w4=w4)
 
     def _fc_operands(self):
         r = self.resnet
@@ -168,6 +169,13 @@ class Net_resnet(_FlatModule):
     def _blocks(self):
         r = self.resnet
         return [blk for li in range(1, 5) for blk in getattr(r, f"layer{li}")]
+
+    @staticmethod
+    def _implicit(conv, h):
+        """3x3 / stride 1 / padding 1 units with 64 or 128 output channels (layer1, layer2: half of the network's FLOPs) run on
+        the CRNN's implicit-GEMM tcgen05 convolution: no materialised im2col (23 MB per clip and unit in layer1)."""
+        return (conv.k == 3 and conv.stride == 1 and conv.pad == 1 and conv.cin % 32 == 0 and conv.cout in (64, 128)
+                and h.shape[2] % 2 == 0 and 128 % h.shape[2] == 0)
 
     def _gemm_wide(self, a, w, bias, out):
         """out[:, n] = a @ w[n]^T (+ bias[n]) on the tensor cores: up to 1024 output columns per launch (multiples of 128; the
@@ -213,6 +221,8 @@ class Net_resnet(_FlatModule):
 
         def conv(h, c):
             op = ops[id(c)]
+            if tc and self._implicit(c, h):
+                return engine.conv3x3(h, op["w4"], op["bias"], tensor_cores=self._precision())
             col, Ho, Wo = engine.im2col_nhwc(h, c.k, c.k, c.stride, c.stride, c.pad, c.pad, op["kpad"])
             return self._gemm(col, op["wk"], op["wkT"], op["bias"], tc).view(h.shape[0], Ho, Wo, c.cout)
 
@@ -242,9 +252,14 @@ class Net_resnet(_FlatModule):
         """conv -> train-mode BatchNorm -> [+ residual] -> [ReLU] on channels-last h; records what backward needs."""
         B = h.shape[0]
         wk, K, kpad = self._pack(conv.weight.detach())
-        col, Ho, Wo = engine.im2col_nhwc(h, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, kpad)
-        z = self._gemm(col, wk, None if tc else wk.t().contiguous(), None, tc)              # (M, Cout), becomes xhat
-        del col
+        if tc and self._implicit(conv, h):
+            Ho, Wo = h.shape[1], h.shape[2]
+            z = engine.conv3x3(h, conv.weight.detach().float().contiguous(), None,
+                               tensor_cores=self._precision()).view(-1, conv.cout)           # (M, Cout), becomes xhat
+        else:
+            col, Ho, Wo = engine.im2col_nhwc(h, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, kpad)
+            z = self._gemm(col, wk, None if tc else wk.t().contiguous(), None, tc)          # (M, Cout), becomes xhat
+            del col
         nbt = self._flat_nbt[self._counter_mods.index(bn):][:1]
         res = residual.reshape(-1, conv.cout) if residual is not None else None
         y, mr = engine.bn_rows_train(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, nbt, res, relu,
@@ -286,6 +301,18 @@ class Net_resnet(_FlatModule):
         d_res = engine.bn_rows_backward(dy, rec["y"], rec["xhat"], bn.weight.detach(), rec["mr"],
                                         self._grad_view(grads, bn, "weight"), self._grad_view(grads, bn, "bias"), rec["has_res"])
         inp = rec["inp"]
+        if rec["tc"] and self._implicit(conv, inp):
+            # layer1 / layer2 units: weight and data gradient by the CRNN's tensor-core kernels on the unit's own tensors
+            # (dW: MN-major tcgen05 reduction over the pixels; dX: the forward kernel with flipped, transposed weights)
+            dy4 = dy.view(inp.shape[0], inp.shape[1], inp.shape[2], conv.cout)
+            self._grad_view(grads, conv, "weight").add_(engine.conv3x3_wgrad(inp, dy4, tensor_cores=True))
+            dx = None
+            if need_dx:
+                wflip = conv.weight.detach().permute(1, 0, 2, 3).flip(2, 3).float().contiguous()
+                dx = engine.conv3x3(dy4, wflip, None, tensor_cores=self._precision())
+                if dx_out is not None:
+                    dx = dx_out.add_(dx.view(dx_out.shape))
+            return dx, d_res
         col, _, _ = engine.im2col_nhwc(inp, conv.k, conv.k, conv.stride, conv.stride, conv.pad, conv.pad, rec["kpad"])
         dwk = torch.zeros(conv.cout, rec["kpad"], dtype=torch.float32, device=dy.device)
         tc = rec["tc"]

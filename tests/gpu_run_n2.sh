@@ -1,5 +1,4 @@
 set -x
 cd $GRAFT_REPO_ROOT
-(timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/gpu_all_t.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_all_t.log)
-(timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_t.json 2> gpurun_out/bench_t.err; echo "rc=$?" >> gpurun_out/bench_t.err)
-(BSED_WGRAD_ASIDE=1 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_t_aside.json 2> gpurun_out/bench_t_aside.err; echo "rc=$?" >> gpurun_out/bench_t_aside.err)
+(timeout 900 python -m pytest tests/test_gpu_resnet.py tests/test_gpu_crnn.py -q -s > gpurun_out/gpu_resnet_u.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_resnet_u.log)
+(timeout 600 python tests/bench_resnet.py > gpurun_out/bench_resnet_u.log 2>&1; echo "rc=$?" >> gpurun_out/bench_resnet_u.log)
