@@ -376,7 +376,7 @@ def run_b200(args, out):
     launches = launches_per_step * args.steps if graphed else launches_eager
 
     # ---- the same device-resident step over >= 300 steps (>= 2 s of GPU time)
-    sus_steps = max(340, args.steps)
+    sus_steps = max(480, args.steps)          # >= 2 s of GPU time at 5.3 ms per step (4.8 ms single-pass)
     ms_sus = timed(lambda i: trainer.step(x, x_ema, xs, ts, 200 + i, rampup_len), sus_steps, 0)
     sustained = {"steps": sus_steps, "ms_per_step": ms_sus / sus_steps, "seconds": ms_sus * 1e-3,
                  "value": (N_SYN + N_REAL) * world * sus_steps / (ms_sus * 1e-3), "unit": "clips/s"}

@@ -14,4 +14,4 @@ fi
 if [ "$N" = "2" ]; then
 (timeout 600 python -m pytest tests/test_gpu_dp.py -q > gpurun_out/pytest_dp_n2_${TAG}.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_dp_n2_${TAG}.log)
 fi
-tail -2 gpurun_out/*_n${N}_${TAG}.log gpurun_out/*_n${N}_${TAG}.err
+true
