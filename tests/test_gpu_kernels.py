@@ -158,7 +158,9 @@ TF32_REL = 2e-3
                                              # column-tiled halo kernel (F >= 8, Cin % 32 == 0): partial t blocks,
                                              # every output width, weights resident / ringed
                                              (2, 313, 16, 64, 128), (1, 130, 8, 128, 128), (3, 129, 64, 32, 16),
-                                             (1, 257, 32, 64, 32), (2, 128, 8, 128, 64), (1, 1, 8, 32, 32)])
+                                             (1, 257, 32, 64, 32), (2, 128, 8, 128, 64), (1, 1, 8, 32, 32),
+                                             # 128 output channels with enough tiles for two bins per step (two issuer warps)
+                                             (8, 313, 8, 128, 128), (25, 313, 2, 128, 128)])
 def test_conv3x3_tensor_cores(B, T, Fq, Cin, Cout):
     from bsed_b200 import engine
     x = _rand(B, Cin, T, Fq, seed=10)

@@ -68,11 +68,14 @@ def test_gemm_nt_3xtf32(M, K, N, bias, acc):
 
 
 @pytest.mark.parametrize("B,T,Fq,Cin,Cout", [
-    # column-tiled halo kernel (F >= 8): partial t blocks, every output width, every chunk count
+    # column-tiled halo kernel (F >= 2, Cin % 32 == 0): partial t blocks, every output width, every chunk count; with 128
+    # output channels one frequency bin per step (G = 1) while the tiles would not fill the SMs, two (G = 2, two issuer
+    # warps) from 75 two-bin tiles up: (8, 313, 8, ...) = 96 tiles
     (2, 313, 16, 64, 128), (1, 130, 8, 128, 128), (3, 129, 64, 32, 16), (1, 257, 32, 64, 32), (2, 128, 8, 128, 64),
-    (1, 1, 8, 32, 32), (2, 37, 16, 32, 32), (2, 313, 32, 32, 64),
-    # row-tiled kernel (F < 8, or 16 input channels)
-    (3, 11, 2, 128, 128), (2, 9, 4, 32, 16), (1, 313, 1, 128, 128), (2, 5, 64, 16, 16), (2, 100, 4, 128, 128)])
+    (1, 1, 8, 32, 32), (2, 37, 16, 32, 32), (2, 313, 32, 32, 64), (8, 313, 8, 128, 128), (3, 11, 2, 128, 128),
+    (2, 9, 4, 32, 16), (2, 100, 4, 128, 128), (13, 313, 2, 128, 128),
+    # row-tiled kernel (F = 1, or 16 input channels)
+    (1, 313, 1, 128, 128), (2, 5, 64, 16, 16)])
 def test_conv3x3_3xtf32(B, T, Fq, Cin, Cout):
     from bsed_b200 import engine
     x = _rand(B, Cin, T, Fq, seed=10)
