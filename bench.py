@@ -77,6 +77,36 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def _conv_traffic_from_profile(launches_per_step, precision):
+    """`roofline.traffic`: DRAM bytes (read + write) per launch of the conv-class kernels, averaged over the launches of one
+    step, from the committed ncu capture of this build (`profiles/r02z_tc_kernels_metrics.csv`, command in
+    `profiles/r02z_step_ncu.md`).  null unless that capture is of the default precision, holds exactly the launches the live
+    run counted per step and the kernel is the same template (the capture does not travel into a different build)."""
+    import collections
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02z_tc_kernels_metrics.csv")
+    note = {"traffic": None, "traffic_note": "ncu dram bytes of these launches: profiles/r02z_step_ncu.md"}
+    if precision != "tf32x3" or not os.path.exists(path):
+        return note
+    try:
+        with open(path) as f:
+            lines = [l for l in f if not l.startswith("==")]
+        rows = collections.OrderedDict()
+        for r in csv.DictReader(lines):
+            if "tc_conv_col_kernel" not in r["Kernel Name"] or "dram__bytes" not in r["Metric Name"]:
+                continue
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0)
+            rows[int(r["ID"])] = rows.get(int(r["ID"]), 0.0) + float(r["Metric Value"].replace(",", "")) * scale
+        if not rows or abs(len(rows) - launches_per_step) > 1e-6:
+            return note
+        return {"traffic": sum(rows.values()) / len(rows),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the %d conv launches of one step "
+                                "in profiles/r02z_tc_kernels_metrics.csv (ncu, same build; below the algorithmic bytes because the "
+                                "teacher group and the data gradient find activations of the preceding launches in L2)" % len(rows)}
+    except Exception:
+        return note
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -536,8 +566,7 @@ def run_b200(args, out):
                          "frac": conv_tflops / peaks["tf_sustained"] if conv_tflops else None,
                          "frac_of_executed_mmas": (conv_tflops / peaks["tf_sustained"] * (3 * 36 + 24) / 60.0
                                                    if conv_tflops and trainer.plan.precision == "tf32x3" else None),
-                         "traffic": None,
-                         "traffic_note": "ncu dram bytes of these launches: profiles/ (see DESIGN.md section 5)",
+                         **_conv_traffic_from_profile(pn.value / args.steps if args.steps else 0, trainer.plan.precision),
                          "algorithmic_gflop_per_step": pf.value / args.steps / 1e9,
                          "algorithmic_gflop_per_step_expected": conv_flop_algorithmic / 1e9 if conv_flop_algorithmic else None,
                          "algorithmic_bytes_per_launch": pb.value / pn.value if pn.value else None,

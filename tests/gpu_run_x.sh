@@ -1,5 +1,4 @@
 set -x
 cd $GRAFT_REPO_ROOT
-(timeout 900 python -m pytest tests/test_gpu_x3.py tests/test_gpu_kernels.py tests/test_gpu_tf32.py -q -x > gpurun_out/gpu_cat.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_cat.log)
-timeout 300 python tests/bench_conv.py tf32x3 > gpurun_out/bench_conv_cat.log 2>&1
-(timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_cat.json 2> gpurun_out/bench_cat.err; echo "rc=$?" >> gpurun_out/bench_cat.err)
+(BSED_SANITIZE_PRECISION=tf32x3 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python tests/gpu_sanitize.py > gpurun_out/memcheck_x3.log 2>&1; echo "rc=$?" >> gpurun_out/memcheck_x3.log)
+(BSED_SANITIZE_PRECISION=tf32 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python tests/gpu_sanitize.py > gpurun_out/memcheck_tf32.log 2>&1; echo "rc=$?" >> gpurun_out/memcheck_tf32.log)
