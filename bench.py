@@ -595,6 +595,14 @@ def run_b200(args, out):
                          "hbm_frac": fe_cps * CLIP_BYTES_FRONTEND / 1e9 / peaks["hbm"] / world,
                          "stft_mel_kernel_ms_per_256_clips": fm.value / max(1, fn_.value),
                          "stft_mel_fp32_tflops": 256 * 1255 * 70000.0 / (fm.value / max(1, fn_.value) * 1e-3) / 1e12,
+                         # the roof that applies: 70 kFLOP of fp32 work per frame (2048-point real FFT, untangle, magnitude,
+                         # interval projection) = 88 MFLOP per clip; at 70 % of the HBM copy rate the kernel would have to
+                         # sustain 2.4 M clips/s = 209 TFLOP/s, 2.8x the fp32 FMA peak below
+                         "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                         "stft_mel_frac_of_fp32_peak": 256 * 1255 * 70000.0 / (fm.value / max(1, fn_.value) * 1e-3) / 1e12
+                                                        / (148 * 128 * 2 * 1.965e9 / 1e12),
+                         "bound": "fp32 / shared-memory pipes (ncu: issue slots 50-54 %, LSU shared-memory pipe 71-75 % busy, "
+                                  "profiles/r01g_frontend_kernels.md); HBM roofline at 70 % would need 209 TFLOP/s fp32",
                          "db_transform": {"bound": "hbm", "achieved_GBps": db_gbps, "peak_GBps": peaks["hbm"],
                                           "frac": db_gbps / peaks["hbm"] if db_gbps else None,
                                           "ms_per_256_clips": dm.value / max(1, dn.value),
