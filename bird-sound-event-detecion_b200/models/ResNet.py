@@ -180,13 +180,20 @@ class Net_resnet(_FlatModule):
     def _gemm_wide(self, a, w, bias, out):
         """out[:, n] = a @ w[n]^T (+ bias[n]) on the tensor cores: up to 1024 output columns per launch (multiples of 128; the
         kernel walks (row tile, column block) pairs), then the remainder."""
-        n, n0 = w.shape[0], 0
+        for n0, n1 in self._wide_chunks(w.shape[0]):
+            engine.gemm_nt_tc(a, w[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=out[:, n0:n1],
+                              x3=self._use_x3())
+
+    @staticmethod
+    def _wide_chunks(n):
+        """Column ranges of one wide-GEMM launch each: multiples of 128 up to 1024 columns, then the remainder (< 128)."""
+        chunks, n0 = [], 0
         while n0 < n:
             left = n - n0
             n1 = n0 + (min(left // 128 * 128, 1024) if left >= 128 else left)
-            engine.gemm_nt_tc(a, w[n0:n1], bias[n0:n1].contiguous() if bias is not None else None, out=out[:, n0:n1],
-                              x3=self._use_x3())
+            chunks.append((n0, n1))
             n0 = n1
+        return chunks
 
     def _gemm(self, col, wk, wkT, bias, tc):
         M, cout = col.shape[0], wk.shape[0]

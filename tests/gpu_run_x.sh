@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-for i in 1 2 3; do
-(timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/gpu_flaky_$i.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_flaky_$i.log)
-done
+python tests/prof_step.py --ada --steps 1 --warmup 3 > gpurun_out/plain_ada.log 2>&1 && \
+BSED_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_ada.csv python tests/prof_step.py --ada --steps 1 --warmup 3 > gpurun_out/ncu_ada.log 2>&1
+tail -2 gpurun_out/plain_ada.log

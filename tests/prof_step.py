@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--frontend", action="store_true")
     ap.add_argument("--precision", default=None)
     ap.add_argument("--model", default="crnn", choices=["crnn", "crnn_fpn"])
+    ap.add_argument("--ada", action="store_true", help="the SCMT + adversarial domain adaptation iteration (config 3)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(2023)
@@ -34,6 +35,24 @@ def main():
         weights_init(p)
         return m.to(dev).train(), p.to(dev).train()
 
+    if a.ada:
+        from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
+        from bsed_b200.main import AdaptationTrainer
+        from bsed_b200.models.CRNN import Clip_Discriminator
+        model, predictor = make()
+        ema_model, ema_predictor = make()
+        disc = Clip_Discriminator(256).to(dev).train()
+        tr = AdaptationTrainer(model, predictor, ema_model, ema_predictor, ConditionalDomainAdversarialLoss(disc), lr=5e-4,
+                               momentum=0.9, weight_decay=1e-4, n_syn=12, n_real=12, dropout_seed=2023)
+        xs = torch.from_numpy(synth.make_logmel_like(12, seed=3)).to(dev)
+        x = torch.from_numpy(synth.make_logmel_like(12, seed=40)).to(dev)
+        ts = torch.from_numpy(synth.make_targets(12, seed=5)).to(dev)
+        tw = torch.from_numpy(synth.make_targets(12, seed=8)).max(1)[0].to(dev)
+        for i in range(a.warmup + a.steps):
+            tr.step(x, x, tw, xs, ts, i, 5000)
+        torch.cuda.synchronize()
+        print("prof_step (ada) done: precision", tr.plan.precision)
+        return
     model, predictor = make()
     ema_model, ema_predictor = make()
     tr = MeanTeacherTrainer(model, predictor, ema_model, ema_predictor, lr=5e-4, n_syn=12, n_real=12,

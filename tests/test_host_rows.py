@@ -115,3 +115,43 @@ def test_weights_init_keeps_flat_views():
         assert torch.equal(prm.detach().reshape(-1), flat[o:o + prm.numel()])
         o += prm.numel()
     assert o == flat.numel()
+
+
+def test_resnet_wide_gemm_chunks_and_implicit_predicate():
+    """Host-side planning of the ResNet tagger's tensor-core launches (models/ResNet.py): a wide GEMM covers multiples of
+    128 columns up to 1024 per launch plus a remainder below 128; the implicit-GEMM convolution takes the 3x3 / stride-1 /
+    padding-1 units with 64 or 128 output channels whose width divides 128."""
+    import types
+    from bsed_b200.models.ResNet import Net_resnet
+    ch = Net_resnet._wide_chunks
+    assert ch(64) == [(0, 64)] and ch(128) == [(0, 128)] and ch(512) == [(0, 512)]
+    assert ch(576) == [(0, 512), (512, 576)] and ch(1152) == [(0, 1024), (1024, 1152)]
+    assert ch(4608) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096), (4096, 4608)]
+    for n in (16, 48, 64, 576, 1152, 2304, 4608):
+        c = ch(n)
+        assert c[0][0] == 0 and c[-1][1] == n and all(a[1] == b[0] for a, b in zip(c, c[1:]))
+        assert all((n1 - n0) % 128 == 0 and n1 - n0 <= 1024 for n0, n1 in c[:-1]) and c[-1][1] - c[-1][0] <= 1024
+    unit = lambda k, s, p, cin, cout: types.SimpleNamespace(k=k, stride=s, pad=p, cin=cin, cout=cout)
+    h = lambda F: types.SimpleNamespace(shape=(2, 10, F, 64))
+    imp = Net_resnet._implicit
+    assert imp(unit(3, 1, 1, 64, 64), h(32)) and imp(unit(3, 1, 1, 128, 128), h(16))
+    assert not imp(unit(3, 2, 1, 64, 128), h(32))          # stride 2
+    assert not imp(unit(1, 1, 0, 64, 128), h(32))          # 1x1 downsample
+    assert not imp(unit(3, 1, 1, 256, 256), h(8))          # 256 output channels: im2col + wide GEMM
+    assert not imp(unit(7, 2, 3, 1, 64), h(128))           # stem
+    assert not imp(unit(3, 1, 1, 64, 64), h(24))           # width does not divide 128
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_capture():
+    """bench.py: `roofline.traffic` is the mean DRAM bytes per conv launch of the committed ncu capture, and null when the
+    live launch count per step or the precision does not match the capture."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rec = bench._conv_traffic_from_profile(18.0, "tf32x3")
+    assert rec["traffic"] is not None and 2e7 < rec["traffic"] < 7e7          # 39.5 MB per launch in r02z
+    assert bench._conv_traffic_from_profile(17.0, "tf32x3")["traffic"] is None
+    assert bench._conv_traffic_from_profile(18.0, "tf32")["traffic"] is None
