@@ -67,6 +67,7 @@ size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct DiscWs {
   size_t col[kDL], y[kDL], act[kDL], wt[kDL], wk[kDL], bp[kDL], dwt[kDL], ypad, mr, stats, stats2, feat, dscr, wgpart;
+  size_t wt_lo[kDL], wk_lo[kDL];   // 3xTF32: fp32 remainders of the tf32-rounded weight operands
   size_t wgpart_bytes, total;
 };
 
@@ -88,6 +89,8 @@ DiscWs disc_ws(const DiscGeom& g, int B) {
     w.wk[l] = take((size_t)g.Np[l] * g.Kp[l] * 4);
     w.bp[l] = take((size_t)g.Np[l] * 4);
     w.dwt[l] = take((size_t)g.Kp[l] * g.Np[l] * 4);
+    w.wt_lo[l] = take((size_t)g.Kp[l] * g.Np[l] * 4);
+    w.wk_lo[l] = take((size_t)g.Np[l] * g.Kp[l] * 4);
     if (g.Np[l] != kDC[l + 1] && M * g.Np[l] * 4 > ypad) ypad = M * g.Np[l] * 4;
   }
   w.ypad = take(ypad ? ypad : 16);
@@ -280,7 +283,8 @@ int grid_for(long long n) {
 using namespace bsed;
 
 extern "C" int bsed_disc_set_precision(bsed_handle h, int precision) {
-  BSED_REQUIRE(h && (precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32), "disc_set_precision: bad argument");
+  BSED_REQUIRE(h && (precision == BSED_PRECISION_FP32 || precision == BSED_PRECISION_TF32 || precision == BSED_PRECISION_TF32X3),
+               "disc_set_precision: bad argument");
   h->disc_precision = precision;
   return BSED_OK;
 }
@@ -316,12 +320,17 @@ extern "C" int bsed_disc_forward(bsed_handle h, const float* params, float* bn_b
     disc_im2col_kernel<<<grid_for(M * g.Kp[l]), 256, 0, st>>>(x, col, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], l == 0);
     BSED_CHECK_LAUNCH();
     BSED_REQUIRE(M < (1ll << 31), "disc_forward: too many rows");
-    const bool tc = h->disc_precision == BSED_PRECISION_TF32;
+    const bool tc = h->disc_precision != BSED_PRECISION_FP32;
+    const bool x3 = h->disc_precision == BSED_PRECISION_TF32X3;
     if (g.Np[l] == Cout) {
-      if (tc)   // y = col * Wk^T on tcgen05 (Wk [Np][Kp] is the K-major B operand)
-        BSED_TRY(tc_gemm_nt(col, g.Kp[l], wsp<float>(ws, w.wk[l]), nullptr, g.Kp[l], y, Cout, M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0,
-                            h->num_sms, st));
-      else
+      if (tc) {   // y = col * Wk^T on tcgen05 (Wk [Np][Kp] is the K-major B operand)
+        if (x3) {   // error-compensated: the weight operands of this layer (forward and data gradient) become (hi, lo) pairs
+          BSED_TRY(split_hi_lo(wsp<float>(ws, w.wk[l]), wsp<float>(ws, w.wk_lo[l]), (long long)g.Np[l] * g.Kp[l], st));
+          BSED_TRY(split_hi_lo(wsp<float>(ws, w.wt[l]), wsp<float>(ws, w.wt_lo[l]), (long long)g.Kp[l] * g.Np[l], st));
+        }
+        BSED_TRY(tc_gemm_nt(col, g.Kp[l], wsp<float>(ws, w.wk[l]), x3 ? wsp<float>(ws, w.wk_lo[l]) : nullptr, g.Kp[l], y, Cout, M,
+                            Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0, h->num_sms, st));
+      } else
         BSED_TRY(gemm_nn(col, g.Kp[l], wsp<float>(ws, w.wt[l]), g.Np[l], y, Cout, (int)M, Cout, g.Kp[l], wsp<float>(ws, w.bp[l]), 0, st));
     } else {
       float* ypad = wsp<float>(ws, w.ypad);
@@ -427,7 +436,8 @@ extern "C" int bsed_disc_backward(bsed_handle h, const float* params, const floa
     // weight gradient: dWt [Kp][Np] = col^T dy
     float* dwt = wsp<float>(ws, w.dwt[l]);
     BSED_CHECK_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * g.Kp[l] * g.Np[l], st));
-    const bool tc = h->disc_precision == BSED_PRECISION_TF32;
+    const bool tc = h->disc_precision != BSED_PRECISION_FP32;
+    const bool x3 = h->disc_precision == BSED_PRECISION_TF32X3;
     if (tc && g.Kp[l] % 32 == 0 && g.Np[l] % 32 == 0 && g.Np[l] == Cout) {
       TcOperand Aop{col, g.Kp[l], 0, g.Kp[l]}, Bop{dy, ldy, 0, g.Np[l]};   // rows = im2col rows, as a (1, M, 1) grid
       BSED_TRY(tc_wgrad_ex(Aop, Bop, 1, (int)M, 1, 1, 0, dwt, g.Np[l], 1, 0, wsp<float>(ws, w.wgpart), w.wgpart_bytes,
@@ -445,8 +455,9 @@ extern "C" int bsed_disc_backward(bsed_handle h, const float* params, const floa
         for (int n0 = 0; n0 < g.Kp[l];) {
           const int rem = g.Kp[l] - n0;
           const int nw = rem >= 128 ? 128 : rem >= 64 ? 64 : rem >= 32 ? 32 : 16;
-          BSED_TRY(tc_gemm_nt(dy, ldy, wsp<float>(ws, w.wt[l]) + (size_t)n0 * g.Np[l], nullptr, g.Np[l], col + n0, g.Kp[l], M, nw, g.Np[l],
-                              nullptr, 0, h->num_sms, st));
+          BSED_TRY(tc_gemm_nt(dy, ldy, wsp<float>(ws, w.wt[l]) + (size_t)n0 * g.Np[l],
+                              x3 ? wsp<float>(ws, w.wt_lo[l]) + (size_t)n0 * g.Np[l] : nullptr, g.Np[l], col + n0, g.Kp[l], M, nw,
+                              g.Np[l], nullptr, 0, h->num_sms, st));
           n0 += nw;
         }
       } else {

@@ -427,10 +427,15 @@ class AdaptationTrainer(MeanTeacherTrainer):
 
     def __init__(self, model, predictor, ema_model, ema_predictor, domain_loss, lr=cfg.default_learning_rate, lr_adv=None,
                  momentum=0.9, weight_decay=1e-4, n_syn=cfg.batch_size, n_real=cfg.batch_size, dropout_seed=2023,
-                 process_group=None, precision=None):
+                 process_group=None, precision=None, disc_precision=None):
         super().__init__(model, predictor, ema_model, ema_predictor, lr=lr, weight_decay=weight_decay, n_syn=n_syn,
                          n_real=n_real, dropout_seed=dropout_seed, process_group=process_group, precision=precision,
                          opt_kind="sgd", momentum=momentum)
+        # contractions of the discriminator: `disc_precision`, else BSED_DISC_PRECISION, else the plan's mode when that is
+        # "tf32x3" (error-compensated forward / data-gradient GEMMs on the tensor cores with single-pass weight-gradient
+        # reductions, as in the CRNN), else the module's own setting ("fp32" unless changed; "tf32" = single pass everywhere)
+        self.disc_precision = (disc_precision or os.environ.get("BSED_DISC_PRECISION")
+                               or ("tf32x3" if self.plan.precision == "tf32x3" else None))
         self.domain_loss = domain_loss                      # DA.cdan_frame.ConditionalDomainAdversarialLoss
         self.disc = domain_loss.domain_discriminator
         self.lr_adv = lr if lr_adv is None else lr_adv
@@ -476,7 +481,8 @@ class AdaptationTrainer(MeanTeacherTrainer):
             raise RuntimeError("the adversarial update needs the discriminator in train() mode (batch statistics)")
         d_flat, d_bn, d_nbt = d.flat_tensors()
         ws, wsb = d._workspace(nst)
-        check(lib.bsed_disc_set_precision(h, _lib.PRECISIONS[(d.precision or "fp32").lower()]), "bsed_disc_set_precision")
+        check(lib.bsed_disc_set_precision(h, _lib.PRECISIONS[(self.disc_precision or d.precision or "fp32").lower()]),
+              "bsed_disc_set_precision")
         prob, d_prob = self.prob[:nst], self.d_prob[:nst]
         check(lib.bsed_disc_forward(h, ptr(d_flat), ptr(d_bn), ptr(d_nbt), ptr(enc), nst, 1, ptr(prob), ptr(ws), wsb, stream_ptr()),
               "bsed_disc_forward")

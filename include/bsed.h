@@ -363,7 +363,7 @@ int bsed_ema_buffers(bsed_handle h, const float* bn_buffers, float* ema_bn_buffe
  * bsed_disc_backward undoes the last train-mode bsed_disc_forward on the same workspace; d_dinput (may be NULL) is
  * the gradient handed to the gradient-reversal layer.  bsed_disc_bce: mean BCE against the domain labels + gradient.
  * ------------------------------------------------------------------------------------------ */
-int bsed_disc_set_precision(bsed_handle h, int precision);   /* BSED_PRECISION_FP32 (default) | BSED_PRECISION_TF32 */
+int bsed_disc_set_precision(bsed_handle h, int precision);   /* BSED_PRECISION_FP32 (default) | _TF32 | _TF32X3 */
 /* dst = alpha * src (n floats; dst may alias src).  The gradient-reversal layer's backward, -coeff * grad
  * (src/DA/grl.py:19-31), between bsed_disc_backward and bsed_crnn_backward. */
 int bsed_scale_f32(bsed_handle h, float* dst, const float* src, int64_t n, float alpha, void* stream);

@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python tests/prof_step.py --ada --steps 1 --warmup 3 > gpurun_out/plain_ada.log 2>&1 && \
-BSED_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_ada.csv python tests/prof_step.py --ada --steps 1 --warmup 3 > gpurun_out/ncu_ada.log 2>&1
-tail -2 gpurun_out/plain_ada.log
+(timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/gpu_all_w.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_all_w.log)
+(timeout 600 python bench.py --workload ada --steps 10 --warmup 3 > gpurun_out/bench_ada_w.json 2> gpurun_out/bench_ada_w.err; echo "rc=$?" >> gpurun_out/bench_ada_w.err)
+(timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke_w.log 2>&1; echo "rc=$?" >> gpurun_out/smoke_w.log)

@@ -38,8 +38,9 @@ def _setup(n, p_drop):
     return oc, op, tc, tp, od, xs, xr, xr_ema, ts, tw
 
 
+@pytest.mark.parametrize("disc_precision", ["fp32", None])          # None = the trainer's default (tf32x3 with the plan)
 @pytest.mark.parametrize("p_drop", [0.0, 0.5])
-def test_adaptation_step_matches_oracle(p_drop):
+def test_adaptation_step_matches_oracle(p_drop, disc_precision):
     from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
     from bsed_b200.main import AdaptationTrainer
     from bsed_b200.models.CRNN import Clip_Discriminator
@@ -56,8 +57,9 @@ def test_adaptation_step_matches_oracle(p_drop):
     crit = ConditionalDomainAdversarialLoss(d)
     crit.grl.iter_num = grl_iter
     tr = AdaptationTrainer(m, p, em, ep, crit, lr=lr, lr_adv=lr, momentum=mom, weight_decay=wd, n_syn=n, n_real=n,
+                           disc_precision=disc_precision,
                            dropout_seed=2023)
-    assert tr.plan.precision == "tf32x3"
+    assert tr.plan.precision == "tf32x3" and tr.disc_precision == (disc_precision or "tf32x3")
     p_before = tr.params.clone()
     losses, dom = tr.step(xr.cuda(), xr_ema.cuda(), tw.cuda(), xs.cuda(), ts.cuda(), gstep, ramp)
     torch.cuda.synchronize()

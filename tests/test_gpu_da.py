@@ -138,14 +138,22 @@ def test_train_mt_with_the_adaptation_branch(fused):
     assert int(d.bn_1.num_batches_tracked) == 2
 
 
-def test_tensor_core_discriminator_within_stated_tolerance(monkeypatch):
-    """Opt-in tf32 tcgen05 GEMMs for the discriminator's convolutions (Clip_Discriminator.precision = "tf32"): loss 2e-3
-    relative, gradients 5e-2 relative L2 (measured 2e-2: five BatchNorms over a 5-clip batch amplify the rounding)."""
+# (loss rel., data-gradient rel. L2, worst parameter-gradient rel. L2).  tf32x3: forward and data-gradient GEMMs error-compensated
+# (loss and df at the fp32 mode's level), weight-gradient reductions single-pass tf32 as in the CRNN
+TC_TOL = {"tf32": (2e-3, 5e-2, 5e-2), "tf32x3": (2e-5, 2e-3, 2e-2)}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_tensor_core_discriminator_within_stated_tolerance(precision):
+    """Opt-in tcgen05 GEMMs for the discriminator's convolutions (Clip_Discriminator.precision = "tf32" / "tf32x3"): single-pass
+    tf32: loss 2e-3 relative, gradients 5e-2 relative L2 (measured 2e-2: five BatchNorms over a 5-clip batch amplify the
+    rounding); 3xTF32: see TC_TOL."""
     from bsed_b200.DA.cdan_frame import ConditionalDomainAdversarialLoss
     g = golden("ada.npz")
     _, d = _disc()
     d.train()
-    d.precision = "tf32"
+    d.precision = precision
+    tol_loss, tol_df, tol_g = TC_TOL[precision]
     f_s = oda.seeded_features(2, 31).cuda().requires_grad_(True)
     f_t = oda.seeded_features(3, 32).cuda().requires_grad_(True)
     crit = ConditionalDomainAdversarialLoss(d)
@@ -153,8 +161,8 @@ def test_tensor_core_discriminator_within_stated_tolerance(monkeypatch):
     loss = crit(None, f_s, None, f_t)
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(g["loss"])) < 2e-3 * float(g["loss"])
-    assert rel_l2(f_s.grad.cpu().numpy()[:, ::7, ::5], g["df_s"]) < 5e-2
+    e_loss = abs(float(loss) - float(g["loss"])) / float(g["loss"])
+    e_df = rel_l2(f_s.grad.cpu().numpy()[:, ::7, ::5], g["df_s"])
     worst = 0.0
     for name, p in d.named_parameters():
         if name.startswith("conv_") and name.endswith(".bias"):
@@ -162,5 +170,5 @@ def test_tensor_core_discriminator_within_stated_tolerance(monkeypatch):
         got = p.grad.reshape(-1).cpu().numpy()
         got = got[:: max(1, got.size // 2048)][:2048]
         worst = max(worst, rel_l2(got, g["g_" + name]))
-    print("[tf32] discriminator worst gradient rel_l2 %.3e" % worst)
-    assert worst < 5e-2
+    print("[%s] discriminator: loss rel %.2e, df rel_l2 %.2e, worst gradient rel_l2 %.3e" % (precision, e_loss, e_df, worst))
+    assert e_loss < tol_loss and e_df < tol_df and worst < tol_g
