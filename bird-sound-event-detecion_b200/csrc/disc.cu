@@ -317,8 +317,12 @@ extern "C" int bsed_disc_forward(bsed_handle h, const float* params, float* bn_b
                                                                              wsp<float>(ws, w.wt[l]), wsp<float>(ws, w.wk[l]),
                                                                              wsp<float>(ws, w.bp[l]), Cin, Cout, g.Kp[l], g.Np[l]);
     BSED_CHECK_LAUNCH();
-    disc_im2col_kernel<<<grid_for(M * g.Kp[l]), 256, 0, st>>>(x, col, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], l == 0);
-    BSED_CHECK_LAUNCH();
+    if (l == 0) {   // d_input arrives [B][W][H] with one channel
+      disc_im2col_kernel<<<grid_for(M * g.Kp[l]), 256, 0, st>>>(x, col, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], 1);
+      BSED_CHECK_LAUNCH();
+    } else {        // channels-last: the float4 im2col shared with the ResNet tagger (resnet.cu)
+      BSED_TRY(im2col_nhwc(x, col, B, g.H[l], g.W[l], Cin, 3, 3, 2, 2, 0, 0, Ho, Wo, g.Kp[l], st));
+    }
     BSED_REQUIRE(M < (1ll << 31), "disc_forward: too many rows");
     const bool tc = h->disc_precision != BSED_PRECISION_FP32;
     const bool x3 = h->disc_precision == BSED_PRECISION_TF32X3;
@@ -463,10 +467,14 @@ extern "C" int bsed_disc_backward(bsed_handle h, const float* params, const floa
       } else {
         BSED_TRY(gemm_nn(dy, ldy, wsp<float>(ws, w.wk[l]), g.Kp[l], col, g.Kp[l], (int)M, g.Kp[l], g.Np[l], nullptr, 0, st));
       }
-      const long long nin = (long long)B * g.H[l] * g.W[l] * Cin;
-      BSED_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * nin, st));
-      disc_col2im_kernel<<<grid_for(M * 9 * Cin), 256, 0, st>>>(col, dx, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], l == 0);
-      BSED_CHECK_LAUNCH();
+      if (l == 0) {
+        const long long nin = (long long)B * g.H[l] * g.W[l] * Cin;
+        BSED_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * nin, st));
+        disc_col2im_kernel<<<grid_for(M * 9 * Cin), 256, 0, st>>>(col, dx, B, g.H[l], g.W[l], Cin, Ho, Wo, g.Kp[l], 1);
+        BSED_CHECK_LAUNCH();
+      } else {   // gather form (every input pixel sums the <= 4 windows that read it): no atomics, no memset, fixed order
+        BSED_TRY(col2im_nhwc(col, dx, B, g.H[l], g.W[l], Cin, 3, 3, 2, 2, 0, 0, Ho, Wo, g.Kp[l], 0, st));
+      }
     }
   }
   return BSED_OK;

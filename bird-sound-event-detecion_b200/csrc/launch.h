@@ -190,4 +190,11 @@ int amp_to_db(const float* mel, const float* noise, float snr_db, int B, int t_i
 int median_decode(const float* strong, int B, int T, int C, float threshold, int win, int32_t* events,
                   int max_events, int32_t* n_events, cudaStream_t st);
 
+// channels-last im2col (float4 when Cin % 4 == 0) and its transpose in gather form (resnet.cu; also the discriminator's
+// stride-2 convolutions): col[(b*Ho+ho)*Wo+wo][(ky*kw+kx)*Cin+ci], columns [kh*kw*Cin, Kpad) zero
+int im2col_nhwc(const float* x, float* col, int B, int H, int W, int Cin, int kh, int kw, int sh, int sw, int ph, int pw,
+                int Ho, int Wo, int Kpad, cudaStream_t st);
+int col2im_nhwc(const float* dcol, float* dx, int B, int H, int W, int Cin, int kh, int kw, int sh, int sw, int ph, int pw,
+                int Ho, int Wo, int Kpad, int accumulate, cudaStream_t st);
+
 }  // namespace bsed
