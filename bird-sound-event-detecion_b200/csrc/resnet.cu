@@ -299,16 +299,22 @@ int bn_rows_backward(float* dy, const float* y, const float* xhat, long long M, 
 
 // transpose of im2col: dx[b][hi][wi][ci] (+)= sum over the windows (ho, wo, ky, kx) that read this pixel of
 // dcol[(b*Ho+ho)*Wo+wo][(ky*kw+kx)*Cin+ci]  -- a gather, so no atomics and a fixed summation order
+template <bool VEC>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int H, int W,
                                                           int Cin, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
                                                           int Wo, int Kpad, int accumulate, long long total) {
+  // one thread per input element, or (VEC: Cin % 4 == 0) per four consecutive channels
+  constexpr int V = VEC ? 4 : 1;
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= total) return;
-  const int ci = (int)(id % Cin);
-  const long long pix = id / Cin;
+  const int cq = Cin / V;
+  const int ci = (int)(id % cq) * V;
+  const long long pix = id / cq;
   const int wi = (int)(pix % W), hi = (int)((pix / W) % H);
   const long long b = pix / ((long long)W * H);
-  float acc = 0.f;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
   for (int ky = 0; ky < kh; ++ky) {
     const int t = hi + ph - ky;
     if (t < 0 || t % sh != 0) continue;
@@ -319,19 +325,43 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restric
       if (u < 0 || u % sw != 0) continue;
       const int wo = u / sw;
       if (wo >= Wo) continue;
-      acc += dcol[((b * Ho + ho) * Wo + wo) * Kpad + (ky * kw + kx) * Cin + ci];
+      const float* src = dcol + ((b * Ho + ho) * Wo + wo) * Kpad + (ky * kw + kx) * Cin + ci;
+      if (VEC) {
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        acc[0] += v.x;
+        acc[V > 1 ? 1 : 0] += v.y;
+        acc[V > 2 ? 2 : 0] += v.z;
+        acc[V > 3 ? 3 : 0] += v.w;
+      } else {
+        acc[0] += *src;
+      }
     }
   }
-  if (accumulate) dx[id] += acc;
-  else dx[id] = acc;
+  float* dst = dx + pix * Cin + ci;
+  if (VEC) {
+    float4 o = make_float4(acc[0], acc[V > 1 ? 1 : 0], acc[V > 2 ? 2 : 0], acc[V > 3 ? 3 : 0]);
+    if (accumulate) {
+      const float4 p = *reinterpret_cast<const float4*>(dst);
+      o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+    }
+    *reinterpret_cast<float4*>(dst) = o;
+  } else {
+    if (accumulate) *dst += acc[0];
+    else *dst = acc[0];
+  }
 }
 
 int col2im_nhwc(const float* dcol, float* dx, int B, int H, int W, int Cin, int kh, int kw, int sh, int sw, int ph, int pw,
                 int Ho, int Wo, int Kpad, int accumulate, cudaStream_t st) {
   BSED_REQUIRE(Ho == (H + 2 * ph - kh) / sh + 1 && Wo == (W + 2 * pw - kw) / sw + 1 && Kpad >= kh * kw * Cin, "col2im: geometry");
-  const long long total = (long long)B * H * W * Cin;
-  col2im_nhwc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dcol, dx, H, W, Cin, kh, kw, sh, sw, ph, pw, Ho, Wo, Kpad, accumulate,
-                                                           total);
+  const bool vec = Cin % 4 == 0 && Kpad % 4 == 0;
+  const long long total = (long long)B * H * W * (vec ? Cin / 4 : Cin);
+  if (vec)
+    col2im_nhwc_kernel<true><<<ceil_div(total, 256), 256, 0, st>>>(dcol, dx, H, W, Cin, kh, kw, sh, sw, ph, pw, Ho, Wo, Kpad,
+                                                                   accumulate, total);
+  else
+    col2im_nhwc_kernel<false><<<ceil_div(total, 256), 256, 0, st>>>(dcol, dx, H, W, Cin, kh, kw, sh, sw, ph, pw, Ho, Wo, Kpad,
+                                                                    accumulate, total);
   BSED_CHECK_LAUNCH();
   return BSED_OK;
 }
