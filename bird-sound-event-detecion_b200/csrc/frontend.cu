@@ -266,11 +266,10 @@ int melspec(bsed_context* h, const float* audio, int B, int n_samples, float* me
 static int melspec_impl(bsed_context* h, const float* audio, int B, int n_samples, float* mel, double* clip_max_ws, cudaStream_t st) {
   BSED_REQUIRE(n_samples >= kNFFT / 2 + 1, "melspec: n_samples=%d < 1025 (reflect padding)", n_samples);
   BSED_REQUIRE(B > 0, "melspec: B=%d", B);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     BSED_CHECK_CUDA(cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FE_SMEM_BYTES));
-    configured = true;
   }
   int n_frames = 1 + n_samples / kHop;
   FrontendTables tb{h->window, h->tw1024, h->tw2048, h->mel_iv_w, h->mel_iv_start, h->mel_iv_len, h->mel_iv_bin0, h->mel_iv_n};
@@ -545,11 +544,10 @@ int median_decode(const float* strong, int B, int T, int C, float threshold, int
   BSED_REQUIRE(T > 0 && T <= PP_MAXT && C > 0 && C <= PP_MAXC, "median_decode: T=%d C=%d (max 1024 x 32)", T, C);
   BSED_REQUIRE(win >= 1 && win <= 65536, "median_decode: win=%d", win);
   BSED_REQUIRE(B > 0 && max_events >= 0, "median_decode: B=%d", B);
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   size_t smem = 2 * PP_MAXC * PP_MAXT;
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     BSED_CHECK_CUDA(cudaFuncSetAttribute(median_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   median_decode_kernel<<<B, 256, smem, st>>>(strong, T, C, threshold, win, events, max_events, n_events);
   BSED_CHECK_LAUNCH();

@@ -10,10 +10,9 @@ static int launch_nn_t(ALoad aload, const float* Bm, int ldb, int M, int N, int 
   constexpr int STAGES = 3;
   constexpr size_t smem = gemm_nn_smem<BM, BN, TM, TN, STAGES>();
   auto kern = gemm_nn_kernel<BM, BN, TM, TN, STAGES, ALoad>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     BSED_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid(ceil_div(M, BM), N / BN);
   kern<<<grid, 256, smem, st>>>(aload, Bm, ldb, M, N, K, epi);

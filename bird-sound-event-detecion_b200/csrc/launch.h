@@ -4,6 +4,18 @@
 
 namespace bsed {
 
+// per-device one-time kernel attributes (one handle per device; cudaFuncSetAttribute is a per-device setting)
+constexpr int kMaxDevices = 64;
+static inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  const bool first = !done[dev];
+  done[dev] = true;
+  return first;
+}
+
+
 constexpr int kMaxGroups = 4;
 
 // clip ranges of the forward groups (one group == one reference model call)

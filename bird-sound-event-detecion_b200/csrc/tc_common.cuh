@@ -300,17 +300,6 @@ static inline int make_map(CUtensorMap* m, const void* base, int rank, const cuu
 
 }  // namespace tc
 
-// per-device one-time kernel attributes (one handle per device; cudaFuncSetAttribute is a per-device setting)
-constexpr int kMaxDevices = 64;
-static inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= kMaxDevices) return true;
-  const bool first = !done[dev];
-  done[dev] = true;
-  return first;
-}
-
 static inline int tc_debug() {   // BSED_TC_DEBUG: measurement experiments only
   static int v = -1;
   if (v < 0) {
